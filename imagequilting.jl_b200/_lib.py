@@ -1,0 +1,114 @@
+"""ctypes binding of libiqb200.so (C ABI: include/iqb200.h, include/iqb200_host.h).
+
+There is no CPU fallback: if the shared library has not been built, or no sm_100 device is
+visible, the calls fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libiqb200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+IQ_OK = 0
+ERRORS = {-1: "IQ_ERR_INVALID", -2: "IQ_ERR_NO_DEVICE", -3: "IQ_ERR_CUDA", -4: "IQ_ERR_NOMEM", -5: "IQ_ERR_STATE"}
+
+c_float_p = C.POINTER(C.c_float)
+c_double_p = C.POINTER(C.c_double)
+c_u8_p = C.POINTER(C.c_uint8)
+c_i32_p = C.POINTER(C.c_int32)
+c_i64_p = C.POINTER(C.c_int64)
+
+
+class IqCtxDesc(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("ti_size", C.c_int64 * 3), ("tile_size", C.c_int64 * 3),
+                ("ti", c_float_p), ("disabled", c_u8_p), ("nsoft", C.c_int32),
+                ("auxti", C.POINTER(c_float_p)), ("device", C.c_int32), ("max_batch", C.c_int32)]
+
+
+class IqTile(C.Structure):
+    _fields_ = [("simdev", c_float_p), ("hard_nnz", C.c_int32), ("hard_offset", c_i32_p),
+                ("hard_value", c_float_p), ("softdev", C.POINTER(c_float_p))]
+
+
+class IqResult(C.Structure):
+    _fields_ = [("count", C.c_int64), ("idx", c_i64_p), ("prob", c_double_p), ("picked", C.c_int64),
+                ("relax_iters", C.c_int32), ("dmin", C.c_float)]
+
+
+class IqhDesc(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("ti_size", C.c_int64 * 3), ("tile_size", C.c_int64 * 3),
+                ("ovl_size", C.c_int64 * 3), ("ntiles", C.c_int64 * 3), ("pad_size", C.c_int64 * 3),
+                ("ti", c_double_p), ("ti_f32", c_float_p), ("disabled", c_u8_p), ("nsoft", C.c_int32),
+                ("aux", C.POINTER(c_float_p)), ("auxti", C.POINTER(c_float_p)),
+                ("hard_has", c_u8_p), ("hard_val", c_float_p), ("path", c_i64_p), ("npath", C.c_int64),
+                ("tol", C.c_double), ("nreal", C.c_int32), ("u", c_double_p), ("debug", C.c_int32),
+                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32)]
+
+
+class IqhStats(C.Structure):
+    _fields_ = [("search_ms", C.c_double), ("search_device_ms", C.c_double), ("cut_ms", C.c_double),
+                ("total_ms", C.c_double), ("searches", C.c_int64), ("kernel_launches", C.c_int64),
+                ("candidates", C.c_int64)]
+
+
+# every symbol include/*.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "iq_abi_version": (C.c_int32, []),
+    "iq_device_count": (C.c_int32, []),
+    "iq_last_error": (C.c_char_p, []),
+    "iq_ctx_create": (C.c_int32, [C.POINTER(C.c_void_p), C.POINTER(IqCtxDesc)]),
+    "iq_ctx_destroy": (C.c_int32, [C.c_void_p]),
+    "iq_ctx_npos": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p]),
+    "iq_search": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqTile), C.c_int32, C.c_double, C.POINTER(IqResult)]),
+    "iq_search_pick": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqTile), C.c_int32, C.c_double, c_double_p,
+                                   C.POINTER(IqResult)]),
+    "iq_distance": (C.c_int32, [C.c_void_p, C.c_int32, c_u8_p, C.POINTER(IqTile), c_float_p]),
+    "iq_fetch_tile": (C.c_int32, [C.c_void_p, C.c_int64, c_float_p]),
+    "iq_last_search_stats": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
+    "iq_ctx_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "iqh_run": (C.c_int32, [C.POINTER(IqhDesc), c_double_p, c_u8_p, c_i64_p, C.POINTER(IqhStats)]),
+    "iqh_graphcut": (C.c_int32, [c_double_p, c_double_p, C.c_int32, c_i64_p, C.c_int32, c_u8_p]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libiqb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libiqb200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class IqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def check(rc):
+    if rc != IQ_OK:
+        raise IqError(rc, lib().iq_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,438 @@
+"""Python mirror of the reference's public API for the accelerated path.
+
+    iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None, tol=0.1,
+          path="raster", nreal=1, debug=False, showprogress=False, rng=None)
+    voxelreuse(trainimg, tilesize, *, overlap=None, nreal=10, **kwargs)
+
+mirror /root/reference/src/iqsim.jl:50-63 and /root/reference/src/voxelreuse.jl:18-24 (same
+argument names, meaning and assertion messages).  Differences forced by the host language:
+indices are 0-based (`hard` keys, returned linear indices), `path` is a string, `rng` is a
+numpy Generator, and `Union{Missing,T}` results are numpy masked arrays.
+
+Host-side set-up (geometry, pre-processing, disabled / skipped tiles, simulation path) is done
+here in NumPy; the tile loop runs in the native driver (csrc/iq_host.cpp) which calls the CUDA
+search through the C ABI.  Nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import (IqCtxDesc, IqhDesc, IqhStats, IqResult, IqTile, c_double_p, c_float_p, c_i32_p, c_i64_p,
+                   c_u8_p, check, lib)
+
+
+# --------------------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------------------
+def _f(arr, dtype):
+    """Fortran-contiguous copy/view with the given dtype (Julia memory layout)."""
+    return np.asfortranarray(arr, dtype=dtype)
+
+
+def _ptr(arr, typ):
+    return arr.ctypes.data_as(typ)
+
+
+def _i64x3(vals):
+    out = (C.c_int64 * 3)(1, 1, 1)
+    for i, v in enumerate(vals):
+        out[i] = int(v)
+    return out
+
+
+def _isnan(v):
+    try:
+        return math.isnan(v)
+    except TypeError:
+        return False
+
+
+def geometry(TIsize, tilesize, simsize=None, overlap=None):
+    """geoconfig of src/iqsim.jl:92-127."""
+    TIsize = tuple(int(v) for v in TIsize)
+    tilesize = tuple(int(v) for v in tilesize)
+    N = len(TIsize)
+    simsize = TIsize if simsize is None else tuple(int(v) for v in simsize)
+    overlap = (1.0 / 6.0,) * N if overlap is None else tuple(float(o) for o in overlap)
+    ovlsize = tuple(int(math.ceil(o * t)) for o, t in zip(overlap, tilesize))
+    spacing = tuple(t - o for t, o in zip(tilesize, ovlsize))
+    ntiles = tuple(int(math.ceil(s / max(sp, 1))) for s, sp in zip(simsize, spacing))
+    padsize = tuple(n * (t - o) + o for n, t, o in zip(ntiles, tilesize, ovlsize))
+    distsize = tuple(a - b + 1 for a, b in zip(TIsize, tilesize))
+    ovlvol = int(np.prod(padsize, dtype=np.int64)) - int(
+        np.prod([p - (n - 1) * o for p, n, o in zip(padsize, ntiles, ovlsize)], dtype=np.int64))
+    return dict(N=N, TIsize=TIsize, tilesize=tilesize, simsize=simsize, overlap=overlap, ovlsize=ovlsize,
+                spacing=spacing, ntiles=ntiles, padsize=padsize, distsize=distsize, ovlvol=ovlvol)
+
+
+def _prepare(img):
+    """missing/NaN -> 0, floats keep their type, everything else becomes Float64 (src/utils.jl:96-102).
+    Returns (prepared array, nan-mask of the original)."""
+    if isinstance(img, np.ma.MaskedArray):
+        base = img.astype(img.dtype if np.issubdtype(img.dtype, np.floating) else np.float64).filled(np.nan)
+    else:
+        base = np.asarray(img)
+    F = base.dtype if np.issubdtype(base.dtype, np.floating) and base.dtype.itemsize >= 4 else np.float64
+    out = np.array(base, dtype=F, copy=True, order="F")
+    nan = np.isnan(out)
+    out[nan] = 0
+    return out, nan
+
+
+def _window_any(flag, win):
+    """any(flag[p : p+win]) for every valid window origin p (integral-image box count)."""
+    acc = flag.astype(np.int64)
+    for ax, w in enumerate(win):
+        cs = np.cumsum(acc, axis=ax)
+        cs = np.concatenate([np.zeros_like(np.take(cs, [0], axis=ax)), cs], axis=ax)
+        n = acc.shape[ax] - w + 1
+        acc = np.take(cs, range(w, w + n), axis=ax) - np.take(cs, range(0, n), axis=ax)
+    return acc > 0
+
+
+def _finddisabled(nanmask, geo):
+    """src/utils.jl:115-129: a patch is disabled iff it contains an inactive (NaN) voxel."""
+    if not nanmask.any():
+        return None
+    return np.asfortranarray(_window_any(nanmask, geo["tilesize"]).astype(np.uint8))
+
+
+def _dilate(grid):
+    """3^N box dilation (ImageMorphology.dilate default, src/utils.jl:181,197)."""
+    out = grid.copy()
+    pad = np.pad(grid, 1, mode="constant")
+    N = grid.ndim
+    for off in np.ndindex(*(3,) * N):
+        sl = tuple(slice(o, o + s) for o, s in zip(off, grid.shape))
+        out |= pad[sl]
+    return out
+
+
+def _genpath(rng, extent, kind, datainds):
+    """src/utils.jl:158-204 with a numpy Generator: raster / random (randperm) / dilation, or the
+    data-first dilation path when hard data exists."""
+    nelm = int(np.prod(extent))
+    path = []
+    grid = np.zeros(extent, dtype=bool)
+
+    def grow():
+        nonlocal grid
+        while not grid.all():
+            dil = _dilate(grid)
+            path.extend(int(v) for v in np.flatnonzero((dil & ~grid).ravel(order="F")))
+            grid = dil
+
+    if len(datainds) == 0:
+        if kind == "raster":
+            path = list(range(nelm))
+        elif kind == "random":
+            path = [int(v) for v in rng.permutation(nelm)]
+        elif kind == "dilation":
+            pivot = int(rng.integers(0, nelm))
+            grid[np.unravel_index(pivot, extent, order="F")] = True
+            path.append(pivot)
+            grow()
+    else:
+        datainds = list(datainds)
+        rng.shuffle(datainds)
+        for pivot in datainds:
+            grid[np.unravel_index(pivot, extent, order="F")] = True
+            path.append(int(pivot))
+        grow()
+    return path
+
+
+# --------------------------------------------------------------------------------------
+# iqsim
+# --------------------------------------------------------------------------------------
+def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None, tol=0.1, path="raster", nreal=1,
+          debug=False, showprogress=False, rng=None, device=0, batch=0, nthreads=0, return_stats=False,
+          return_picks=False, _path_override=None, _uniforms=None):
+    """Image quilting simulation with the GPU distance search (see module docstring)."""
+    timg = trainimg if isinstance(trainimg, np.ma.MaskedArray) else np.asarray(trainimg)
+    N = timg.ndim
+    if N not in (2, 3):
+        raise NotImplementedError("only 2-D and 3-D training images are supported by the B200 path")
+    tilesize = tuple(int(t) for t in tilesize)
+    simsize = tuple(timg.shape) if simsize is None else tuple(int(s) for s in simsize)
+    overlap = (1.0 / 6.0,) * N if overlap is None else tuple(overlap)
+    hard = dict(hard) if hard else {}
+    soft = list(soft)
+    rng = np.random.default_rng() if rng is None else rng
+
+    # sanity checks, messages as in src/iqsim.jl:69-89
+    assert len(tilesize) == N and all(0 < t <= s for t, s in zip(tilesize, timg.shape)), "invalid tile size"
+    assert len(simsize) == N and all(s >= t for s, t in zip(simsize, tilesize)), "invalid grid size"
+    assert all(0 < o < 1 for o in overlap), "overlaps must be in range (0,1)"
+    assert 0 < tol <= 1, "tolerance must be in range (0,1]"
+    assert path in ("raster", "dilation", "random"), "invalid simulation path"
+    assert nreal > 0, "invalid number of realizations"
+    for aux, auxTI in soft:
+        assert all(a >= s for a, s in zip(np.shape(aux), simsize)), "soft data size < grid size"
+        assert np.shape(auxTI) == timg.shape, "auxiliary TI must have the same size as TI"
+    if hard:
+        coords = np.array([tuple(k) for k in hard.keys()], dtype=np.int64)
+        assert np.all(coords.max(axis=0) <= np.array(simsize) - 1), "hard data coordinates outside of grid"
+        assert np.all(coords.min(axis=0) >= 0), "hard data coordinates must be positive indices"
+
+    geo = geometry(timg.shape, tilesize, simsize, overlap)
+    ntiles, spacing, padsize = geo["ntiles"], geo["spacing"], geo["padsize"]
+
+    # pre-processing (src/utils.jl:69-92)
+    TI, nanmask = _prepare(timg)
+    is_float = np.issubdtype(np.asarray(timg).dtype, np.floating)
+    out_dtype = TI.dtype
+    ti64 = _f(TI, np.float64)
+    ti32 = _f(TI, np.float32)
+    disabled = _finddisabled(nanmask, geo)
+    aux_pad, aux_ti = [], []
+    for aux, auxTI in soft:
+        a = np.asarray(aux.filled(np.nan) if isinstance(aux, np.ma.MaskedArray) else aux, dtype=np.float64)
+        append = tuple(p - min(p, s) for p, s in zip(padsize, a.shape))
+        a = np.pad(a, [(0, ap) for ap in append], mode="symmetric")
+        a = a[tuple(slice(0, p) for p in padsize)]
+        a = np.where(np.isnan(a), 0.0, a)
+        aux_pad.append(_f(a, np.float32))
+        at, _ = _prepare(auxTI)
+        aux_ti.append(_f(at, np.float32))
+
+    # hard data as dense grids over the padded domain
+    hard_has = hard_val = hard_nan = None
+    if hard:
+        hard_has = np.zeros(padsize, dtype=np.uint8, order="F")
+        hard_nan = np.zeros(padsize, dtype=bool, order="F")
+        hard_val = np.zeros(padsize, dtype=np.float32, order="F")
+        for coord, val in hard.items():
+            coord = tuple(int(c) for c in coord)
+            if _isnan(val):
+                hard_nan[coord] = True
+            else:
+                hard_has[coord] = 1
+                hard_val[coord] = val
+
+    # skipped tiles and tiles with data (src/utils.jl:131-156)
+    skipped, datainds = set(), []
+    for lin in range(int(np.prod(ntiles))):
+        tileind = np.unravel_index(lin, ntiles, order="F")
+        start = tuple(int(t) * sp for t, sp in zip(tileind, spacing))
+        sl = tuple(slice(s, s + t) for s, t in zip(start, tilesize))
+        beyond = any(s >= sz for s, sz in zip(start, simsize))
+        all_inactive = bool(hard_nan[sl].all()) if hard else False
+        if beyond or all_inactive:
+            skipped.add(lin)
+        elif hard and hard_has[sl].any():
+            datainds.append(lin)
+
+    simpath = _genpath(rng, ntiles, path, datainds) if _path_override is None else list(_path_override)
+    visited = np.array([p for p in simpath if p not in skipped], dtype=np.int64)
+    nvis = int(visited.size)
+    if _uniforms is None:
+        u = rng.random(nreal * nvis).reshape(nreal, nvis) if nvis else np.zeros((nreal, 0))
+    else:
+        u = np.asarray(_uniforms, dtype=np.float64).reshape(nreal, nvis)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+
+    padvol = int(np.prod(padsize, dtype=np.int64))
+    grids = np.zeros((nreal, padvol), dtype=np.float64)
+    cuts = np.zeros((nreal, padvol), dtype=np.uint8) if debug else None
+    picks = np.full((nreal, max(nvis, 1)), -1, dtype=np.int64)
+
+    d = IqhDesc()
+    d.ndim = N
+    d.ti_size, d.tile_size = _i64x3(timg.shape), _i64x3(tilesize)
+    d.ovl_size, d.ntiles, d.pad_size = _i64x3(geo["ovlsize"]), _i64x3(ntiles), _i64x3(padsize)
+    d.ti, d.ti_f32 = _ptr(ti64, c_double_p), _ptr(ti32, c_float_p)
+    d.disabled = _ptr(disabled, c_u8_p) if disabled is not None else None
+    d.nsoft = len(soft)
+    if soft:
+        auxarr = (c_float_p * len(soft))(*[_ptr(a, c_float_p) for a in aux_pad])
+        auxtiarr = (c_float_p * len(soft))(*[_ptr(a, c_float_p) for a in aux_ti])
+        d.aux, d.auxti = auxarr, auxtiarr
+    if hard and hard_has.any():
+        d.hard_has, d.hard_val = _ptr(hard_has, c_u8_p), _ptr(hard_val, c_float_p)
+    d.path, d.npath = _ptr(visited, c_i64_p), nvis
+    d.tol, d.nreal = float(tol), int(nreal)
+    d.u = _ptr(u, c_double_p)
+    d.debug, d.device, d.batch, d.nthreads = int(bool(debug)), int(device), int(batch), int(nthreads)
+    stats = IqhStats()
+    if nvis > 0:
+        check(lib().iqh_run(C.byref(d), _ptr(grids, c_double_p), _ptr(cuts, c_u8_p) if debug else None,
+                            _ptr(picks, c_i64_p), C.byref(stats)))
+
+    # post-processing (src/iqsim.jl:287-308)
+    crop = tuple(slice(0, s) for s in simsize)
+    realizations, boundarycuts, voxs = [], [], []
+    for r in range(nreal):
+        simgrid = grids[r].reshape(padsize, order="F").astype(out_dtype)
+        cutgrid = cuts[r].reshape(padsize, order="F").astype(np.float64) if debug else None
+        if debug:
+            voxs.append(float(cutgrid.sum()) / geo["ovlvol"])
+        for coord, val in hard.items():
+            simgrid[tuple(coord)] = val
+            if debug and _isnan(val):
+                cutgrid[tuple(coord)] = val
+        res = np.array(simgrid[crop], copy=True)
+        realizations.append(res if is_float else np.ma.masked_invalid(res))
+        if debug:
+            boundarycuts.append(np.array(cutgrid[crop], copy=True))
+    out = (realizations, boundarycuts, voxs) if debug else realizations
+    extras = {}
+    if return_stats:
+        extras["stats"] = {k: getattr(stats, k) for k, _ in IqhStats._fields_}
+        extras["stats"].update(nvisited=nvis, geo=geo)
+    if return_picks:
+        extras["picks"] = picks[:, :nvis]
+        extras["path"] = visited
+        extras["u"] = u
+    return (out, extras) if extras else out
+
+
+def voxelreuse(trainimg, tilesize, *, overlap=None, nreal=10, **kwargs):
+    """Mean voxel reuse in [0,1] and its standard deviation (src/voxelreuse.jl:18-41)."""
+    N = np.ndim(trainimg)
+    overlap = (1.0 / 6.0,) * N if overlap is None else tuple(overlap)
+    ovlsize = tuple(int(math.ceil(o * t)) for o, t in zip(overlap, tilesize))
+    ntiles = tuple(2 if o > 1 else 1 for o in ovlsize)
+    simsize = tuple(n * (t - o) + o for n, t, o in zip(ntiles, tilesize, ovlsize))
+    _, _, voxs = iqsim(trainimg, tilesize, simsize, overlap=overlap, nreal=nreal, debug=True, **kwargs)
+    mu = float(np.mean(voxs))
+    sigma = float(np.std(voxs, ddof=1)) if len(voxs) > 1 else float("nan")
+    return mu, sigma
+
+
+def graphcut(A, B, dim):
+    """Boundary cut keep-mask through the native host routine (src/graphcut.jl:5-84)."""
+    A = _f(A, np.float64)
+    B = _f(B, np.float64)
+    assert A.shape == B.shape, "arrays must have the same size for cut"
+    keep = np.zeros(A.shape, dtype=np.uint8, order="F")
+    sz = np.array(A.shape, dtype=np.int64)
+    check(lib().iqh_graphcut(_ptr(A, c_double_p), _ptr(B, c_double_p), A.ndim, _ptr(sz, c_i64_p), int(dim),
+                             _ptr(keep, c_u8_p)))
+    return keep.astype(bool)
+
+
+# --------------------------------------------------------------------------------------
+# thin object wrapper over iq_ctx: what a host language binds (used by tests and benchmarks)
+# --------------------------------------------------------------------------------------
+class SearchContext:
+    """Owns one iq_ctx: resident training image(s) on one device + the search entry points."""
+
+    def __init__(self, ti, tilesize, disabled=None, auxti=(), device=0, max_batch=1):
+        ti = np.asarray(ti)
+        self.N = ti.ndim
+        self.ti_shape = tuple(ti.shape)
+        self.tilesize = tuple(int(t) for t in tilesize)
+        self.distsize = tuple(a - b + 1 for a, b in zip(ti.shape, self.tilesize))
+        self.tilevol = int(np.prod(self.tilesize))
+        self._ti = _f(ti, np.float32)
+        self._aux = [_f(a, np.float32) for a in auxti]
+        self._disabled = None if disabled is None else _f(np.asarray(disabled).astype(np.uint8), np.uint8)
+        d = IqCtxDesc()
+        d.ndim = self.N
+        d.ti_size, d.tile_size = _i64x3(ti.shape), _i64x3(self.tilesize)
+        d.ti = _ptr(self._ti, c_float_p)
+        d.disabled = _ptr(self._disabled, c_u8_p) if self._disabled is not None else None
+        d.nsoft = len(self._aux)
+        if self._aux:
+            self._auxarr = (c_float_p * len(self._aux))(*[_ptr(a, c_float_p) for a in self._aux])
+            d.auxti = self._auxarr
+        d.device, d.max_batch = int(device), int(max_batch)
+        self._h = C.c_void_p()
+        check(lib().iq_ctx_create(C.byref(self._h), C.byref(d)))
+        n, ne = C.c_int64(), C.c_int64()
+        check(lib().iq_ctx_npos(self._h, C.byref(n), C.byref(ne)))
+        self.npos, self.nenabled = n.value, ne.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().iq_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, key, value):
+        check(lib().iq_ctx_set_option(self._h, key.encode(), int(value)))
+
+    def _tile(self, simdev=None, hard=None, softdev=()):
+        """-> (IqTile, keepalive list)."""
+        keep = []
+        t = IqTile()
+        if simdev is not None:
+            a = _f(simdev, np.float32)
+            assert a.shape == self.tilesize
+            keep.append(a)
+            t.simdev = _ptr(a, c_float_p)
+        if hard is not None:
+            hm, hv = hard
+            hm = np.asarray(hm, dtype=bool)
+            off = np.flatnonzero(hm.ravel(order="F")).astype(np.int32)
+            val = np.asarray(hv, dtype=np.float32).ravel(order="F")[off].copy()
+            keep += [off, val]
+            t.hard_nnz = int(off.size)
+            t.hard_offset, t.hard_value = _ptr(off, c_i32_p), _ptr(val, c_float_p)
+        if softdev:
+            arrs = [_f(s, np.float32) for s in softdev]
+            ptrs = (c_float_p * len(arrs))(*[_ptr(a, c_float_p) for a in arrs])
+            keep += arrs + [ptrs]
+            t.softdev = ptrs
+        return t, keep
+
+    def distance(self, which, ovlmask=None, simdev=None, hard=None, softdev=()):
+        """One full distance map as a `distsize` array (iq_distance)."""
+        t, keep = self._tile(simdev, hard, softdev)
+        m = None if ovlmask is None else _f(np.asarray(ovlmask).astype(np.uint8), np.uint8)
+        out = np.zeros(self.distsize, dtype=np.float32, order="F")
+        check(lib().iq_distance(self._h, int(which), _ptr(m, c_u8_p) if m is not None else None, C.byref(t),
+                                _ptr(out, c_float_p)))
+        return out
+
+    def search(self, ovlmask, tiles, tol=0.1, u=None):
+        """tiles: list of dict(simdev=, hard=(mask, values) | None, softdev=[...]).  Returns a list of
+        dict(idx, prob, picked, relax_iters, dmin)."""
+        m = _f(np.asarray(ovlmask).astype(np.uint8), np.uint8)
+        n = len(tiles)
+        arr = (IqTile * n)()
+        keep = []
+        for i, td in enumerate(tiles):
+            t, k = self._tile(td.get("simdev"), td.get("hard"), td.get("softdev", ()))
+            arr[i] = t
+            keep.append(k)
+        res = (IqResult * n)()
+        if u is None:
+            check(lib().iq_search(self._h, _ptr(m, c_u8_p), arr, n, float(tol), res))
+        else:
+            uu = np.ascontiguousarray(u, dtype=np.float64)
+            check(lib().iq_search_pick(self._h, _ptr(m, c_u8_p), arr, n, float(tol), _ptr(uu, c_double_p), res))
+        out = []
+        for i in range(n):
+            cnt = res[i].count
+            idx = np.ctypeslib.as_array(res[i].idx, shape=(cnt,)).copy() if cnt else np.zeros(0, np.int64)
+            prob = np.ctypeslib.as_array(res[i].prob, shape=(cnt,)).copy() if cnt else np.zeros(0)
+            out.append(dict(idx=idx, prob=prob, picked=int(res[i].picked), relax_iters=int(res[i].relax_iters),
+                            dmin=float(res[i].dmin)))
+        return out
+
+    def fetch_tile(self, pos):
+        out = np.zeros(self.tilesize, dtype=np.float32, order="F")
+        check(lib().iq_fetch_tile(self._h, int(pos), _ptr(out, c_float_p)))
+        return out
+
+    def last_stats(self):
+        ms, nl = C.c_double(), C.c_int64()
+        check(lib().iq_last_search_stats(self._h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value

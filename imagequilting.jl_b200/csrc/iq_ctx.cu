@@ -1,0 +1,1038 @@
+// iq_ctx.cu -- context, per-batch orchestration and the exported C ABI (include/iqb200.h).
+//
+// Host-side pieces restated here (FP64, exactly as the reference computes them) because they run on a
+// few hundred candidates at most and their result must be bit-identical to the reference's host code:
+//   taumodel            /root/reference/src/taumodel.jl:5-45
+//   StatsBase.sample    /root/reference/src/iqsim.jl:243 (cumulative walk; Base.sum's pairwise order)
+//   relaxation's k      /root/reference/src/relaxation.jl:11,20-22,35 (dbsize / frac arithmetic)
+// Everything that touches all npos patch positions runs in the kernels of iq_kernels.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/iqb200.h"
+#include "iq_internal.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return fail(IQ_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+
+using iq::BoxDesc;
+
+struct MaskEntry {
+  std::vector<uint8_t> mask;
+  uint64_t hash = 0;
+  std::vector<BoxDesc> boxes;
+  BoxDesc* d_boxes = nullptr;
+  long long nnz = 0;
+  long long tmpl_floats = 0;           // packed template floats per tile
+  std::map<int, float*> a2;            // image id (-1 = TI, s = aux s) -> A2 map
+  int WX = 1, WY = 1;
+};
+
+struct TileResult {
+  std::vector<int64_t> idx;
+  std::vector<double> prob;
+  const int64_t* idx_ptr = nullptr;
+  const double* prob_ptr = nullptr;
+  int64_t count = 0;
+};
+
+uint64_t fnv1a(const uint8_t* p, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+// Base.sum's pairwise reduction (Base.mapreduce_impl, block 1024): sequential inside a block.
+double julia_sum(const double* w, int64_t lo, int64_t hi) {  // inclusive bounds
+  if (hi - lo < 1024) {
+    double v = w[lo];
+    for (int64_t i = lo + 1; i <= hi; ++i) v += w[i];
+    return v;
+  }
+  const int64_t mid = lo + ((hi - lo) >> 1);
+  return julia_sum(w, lo, mid) + julia_sum(w, mid + 1, hi);
+}
+double julia_sum_const(double c, int64_t lo, int64_t hi) {
+  if (hi - lo < 1024) {
+    double v = c;
+    for (int64_t i = lo + 1; i <= hi; ++i) v += c;
+    return v;
+  }
+  const int64_t mid = lo + ((hi - lo) >> 1);
+  return julia_sum_const(c, lo, mid) + julia_sum_const(c, mid + 1, hi);
+}
+
+// StatsBase.sample(rng, wv): t = u*sum(wv); first i with cumulative >= t, else the last.
+int64_t sample_walk(const double* p, int64_t n, double u) {
+  const double t = u * julia_sum(p, 0, n - 1);
+  int64_t i = 0;
+  double cw = p[0];
+  while (cw < t && i < n - 1) { ++i; cw += p[i]; }
+  return i;
+}
+
+// taumodel (src/taumodel.jl:5-45). vals[j*n + i] = distance of candidate i under source j.
+void taumodel(int64_t n, int nsrc, const float* vals, std::vector<double>& prob) {
+  prob.assign((size_t)n, 1.0);
+  if (n == 1) return;
+  const double dn = (double)n;
+  const double x0 = (1.0 - 1.0 / dn) / (1.0 / dn);
+  std::vector<double> prod((size_t)n, 1.0);
+  std::vector<float> sorted;
+  std::vector<double> P((size_t)n);
+  for (int j = 0; j < nsrc; ++j) {
+    const float* v = vals + (size_t)j * n;
+    sorted.assign(v, v + n);
+    std::sort(sorted.begin(), sorted.end());
+    sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    double colsum = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+      const double r = (double)(std::lower_bound(sorted.begin(), sorted.end(), v[i]) - sorted.begin() + 1);
+      P[i] = (dn - r) + 1.0;
+      colsum += P[i];  // integer-valued: exact
+    }
+    for (int64_t i = 0; i < n; ++i) {
+      const double Pi = P[i] / colsum;
+      const double X = (1.0 - Pi) / Pi;
+      const double ratio = X / x0;
+      prod[i] = (j == 0) ? ratio : prod[i] * ratio;
+    }
+  }
+  for (int64_t i = 0; i < n; ++i) prob[i] = 1.0 / (1.0 + x0 * prod[i]);
+}
+
+}  // namespace
+
+struct iq_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int ndim = 3;
+  int nx = 1, ny = 1, nz = 1, tx = 1, ty = 1, tz = 1, nxo = 1, nyo = 1, nzo = 1;
+  long long npos = 0, tilevol = 0, nenabled = 0;
+  int nsoft = 0, max_batch = 1;
+  int rb_opt = 0;  // 0 = auto
+
+  float* d_ti = nullptr;
+  std::vector<float*> d_aux;
+  double* d_sat_ti = nullptr;
+  std::vector<double*> d_sat_aux;
+  uint8_t* d_disabled = nullptr;
+  std::vector<uint8_t> h_disabled;
+
+  float* d_Dovl = nullptr;
+  float* d_Dhard = nullptr;
+  std::vector<float*> d_Dsoft;
+  unsigned* d_minmax = nullptr;  // [kind][2][max_batch], kind 0 = ovl, 1 = hard, 2+s = soft
+  unsigned* h_minmax = nullptr;
+
+  // bump-allocated staging (pinned host + device mirror)
+  char* h_stage = nullptr;
+  char* d_stage = nullptr;
+  size_t stage_cap = 0, stage_used = 0;
+
+  iq::SelJob* d_sel = nullptr;
+  iq::SelJob* h_sel = nullptr;
+  iq::PickJob* d_pick = nullptr;
+  iq::PickJob* h_pick = nullptr;
+  unsigned* d_blockcount = nullptr;
+  unsigned* d_total = nullptr;
+  unsigned* h_total = nullptr;
+  unsigned* d_cand_idx = nullptr;
+  float* d_cand_val = nullptr;
+  int max_src = 1;
+  unsigned* h_cand_idx = nullptr;
+  float* h_cand_val = nullptr;
+  size_t h_cand_cap = 0;
+  int* d_shifts = nullptr;
+  int nshift = 0;
+  float* d_fetch = nullptr;
+
+  std::vector<std::unique_ptr<MaskEntry>> masks;
+  MaskEntry* full_mask = nullptr;
+
+  std::vector<TileResult> res;
+  // cached "every enabled patch, uniform weights" answer of an empty overlap mask
+  std::vector<int64_t> enabled_idx;
+  std::vector<double> uniform_prob, uniform_cum;
+  double uniform_sum = 0.0;
+
+  double last_ms = 0.0;
+  int64_t last_launches = 0;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int stage_reserve(iq_ctx* c, size_t bytes) {
+  if (bytes <= c->stage_cap) return IQ_OK;
+  size_t cap = std::max(bytes, c->stage_cap * 2);
+  cap = (cap + 4095) & ~(size_t)4095;
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->d_stage) cudaFree(c->d_stage);
+  c->h_stage = nullptr;
+  c->d_stage = nullptr;
+  c->stage_cap = 0;
+  CK(cudaMallocHost((void**)&c->h_stage, cap));
+  CK(cudaMalloc((void**)&c->d_stage, cap));
+  c->stage_cap = cap;
+  return IQ_OK;
+}
+size_t stage_alloc(iq_ctx* c, size_t bytes) {
+  const size_t off = (c->stage_used + 255) & ~(size_t)255;
+  c->stage_used = off + bytes;
+  return off;
+}
+
+// Disjoint box decomposition of an arbitrary tile mask: x-runs -> rectangles in y -> boxes in z.
+struct Rect {
+  int x0, x1, y0, y1;
+  bool operator<(const Rect& o) const {
+    if (x0 != o.x0) return x0 < o.x0;
+    if (x1 != o.x1) return x1 < o.x1;
+    if (y0 != o.y0) return y0 < o.y0;
+    return y1 < o.y1;
+  }
+};
+
+void decompose(const uint8_t* m, int tx, int ty, int tz, std::vector<BoxDesc>& out) {
+  out.clear();
+  std::map<Rect, int> open;  // rect -> z start
+  auto close_box = [&](const Rect& r, int z0, int z1) {
+    BoxDesc b;
+    b.x0 = r.x0; b.y0 = r.y0; b.z0 = z0;
+    b.w = r.x1 - r.x0; b.h = r.y1 - r.y0; b.d = z1 - z0;
+    b.nch = (b.w + 7) / 8;
+    b.tmpl_off = 0;
+    out.push_back(b);
+  };
+  for (int z = 0; z <= tz; ++z) {
+    std::vector<Rect> rects;
+    if (z < tz) {
+      std::map<std::pair<int, int>, int> runs_open;  // (x0,x1) -> y start
+      for (int y = 0; y <= ty; ++y) {
+        std::vector<std::pair<int, int>> runs;
+        if (y < ty) {
+          const uint8_t* row = m + ((size_t)z * ty + y) * tx;
+          int x = 0;
+          while (x < tx) {
+            if (!row[x]) { ++x; continue; }
+            int x1 = x;
+            while (x1 < tx && row[x1]) ++x1;
+            runs.push_back({x, x1});
+            x = x1;
+          }
+        }
+        for (auto it = runs_open.begin(); it != runs_open.end();) {
+          if (std::find(runs.begin(), runs.end(), it->first) == runs.end()) {
+            rects.push_back({it->first.first, it->first.second, it->second, y});
+            it = runs_open.erase(it);
+          } else {
+            ++it;
+          }
+        }
+        for (auto& r : runs)
+          if (!runs_open.count(r)) runs_open[r] = y;
+      }
+    }
+    std::sort(rects.begin(), rects.end());
+    for (auto it = open.begin(); it != open.end();) {
+      if (!std::binary_search(rects.begin(), rects.end(), it->first)) {
+        close_box(it->first, it->second, z);
+        it = open.erase(it);
+      } else {
+        ++it;
+      }
+    }
+    for (auto& r : rects)
+      if (!open.count(r)) open[r] = z;
+  }
+}
+
+// Choose the CTA shape (warps along x / y) for a box list: minimise padded work x tail effect.
+void choose_shape(const iq_ctx* c, const std::vector<BoxDesc>& boxes, int rb, int ngrp_hint, int* WX, int* WY) {
+  double best = 1e300;
+  int bx = 1, by = 1;
+  const int maxwx = (c->nxo + iq::kWarpX - 1) / iq::kWarpX, maxwy = (c->nyo + iq::kWarpY - 1) / iq::kWarpY;
+  for (int wx = 1; wx <= 8; ++wx)
+    for (int wy = 1; wx * wy <= 8; ++wy) {
+      if (wx > maxwx || wy > maxwy) continue;
+      const size_t smem = iq::dist_boxes_smem(boxes.data(), (int)boxes.size(), wx, wy, rb, nullptr, nullptr);
+      if (smem > 200 * 1024) continue;
+      const long long gx = (c->nxo + wx * iq::kWarpX - 1) / (wx * iq::kWarpX);
+      const long long gy = (c->nyo + wy * iq::kWarpY - 1) / (wy * iq::kWarpY);
+      const double padded = (double)gx * wx * iq::kWarpX * gy * wy * iq::kWarpY;
+      const double nblk = (double)gx * gy * c->nzo * ngrp_hint;
+      // resident CTAs per SM: limited by smem (227 KB) and by 2048 threads / registers (~2 x 256)
+      int per_sm = (int)std::min<double>((227.0 * 1024) / std::max<size_t>(smem, 1), 16.0 / (wx * wy));
+      per_sm = std::max(per_sm, 1);
+      const double slots = 148.0 * per_sm;
+      const double waves = nblk / slots;
+      const double tail = std::ceil(waves) / waves;
+      // small CTAs pay relatively more halo staging and sync; mild preference for >= 4 warps
+      const double small_pen = 1.0 + 0.02 * (8 - wx * wy);
+      const double cost = padded * tail * small_pen;
+      if (cost < best) { best = cost; bx = wx; by = wy; }
+    }
+  *WX = bx;
+  *WY = by;
+}
+
+int get_mask(iq_ctx* c, const uint8_t* mask, MaskEntry** out) {
+  const uint64_t h = fnv1a(mask, (size_t)c->tilevol);
+  for (auto& e : c->masks)
+    if (e->hash == h && std::memcmp(e->mask.data(), mask, (size_t)c->tilevol) == 0) { *out = e.get(); return IQ_OK; }
+  auto e = std::make_unique<MaskEntry>();
+  e->mask.assign(mask, mask + c->tilevol);
+  e->hash = h;
+  for (long long i = 0; i < c->tilevol; ++i) e->nnz += mask[i] ? 1 : 0;
+  decompose(mask, c->tx, c->ty, c->tz, e->boxes);
+  if ((int)e->boxes.size() > iq::kMaxBox) {  // very fragmented mask: one dense box, zeros carry the mask
+    e->boxes.clear();
+    BoxDesc b{0, 0, 0, c->tx, c->ty, c->tz, (c->tx + 7) / 8, 0};
+    e->boxes.push_back(b);
+  }
+  long long off = 0;
+  for (auto& b : e->boxes) {
+    b.tmpl_off = (int)off;
+    off += (long long)b.d * b.h * b.nch * 8;
+  }
+  e->tmpl_floats = off;
+  if (!e->boxes.empty()) {
+    CK(cudaMalloc((void**)&e->d_boxes, e->boxes.size() * sizeof(BoxDesc)));
+    CK(cudaMemcpyAsync(e->d_boxes, e->boxes.data(), e->boxes.size() * sizeof(BoxDesc), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  choose_shape(c, e->boxes, 1, std::max(1, c->max_batch), &e->WX, &e->WY);
+  *out = e.get();
+  c->masks.push_back(std::move(e));
+  return IQ_OK;
+}
+
+int get_a2(iq_ctx* c, MaskEntry* e, int image, const float** out) {
+  if (e->boxes.empty()) { *out = nullptr; return IQ_OK; }
+  auto it = e->a2.find(image);
+  if (it != e->a2.end()) { *out = it->second; return IQ_OK; }
+  float* d = nullptr;
+  CK(cudaMalloc((void**)&d, (size_t)c->npos * sizeof(float)));
+  const double* sat = image < 0 ? c->d_sat_ti : c->d_sat_aux[image];
+  CK(iq::launch_a2map(sat, c->nx, c->ny, c->nz, e->d_boxes, (int)e->boxes.size(), d, c->nxo, c->nyo, c->nzo, c->stream));
+  c->launches++;
+  e->a2[image] = d;
+  *out = d;
+  return IQ_OK;
+}
+
+int pick_rb(const iq_ctx* c, int R) {
+  if (c->rb_opt == 1 || c->rb_opt == 2 || c->rb_opt == 4) return c->rb_opt;
+  if (R >= 4) return 4;
+  if (R >= 2) return 2;
+  return 1;
+}
+
+// Pack R templates (tile-sized arrays `kern[r]`, masked by e->mask) into the kernel layout
+// [grp][box][qz][qy][chunk][r(RB)][8] at staging offset; also B2[r] = sum(mask * kern^2) in FP64.
+void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* kern, int R, int rb, float* dst, double* b2) {
+  const int ngrp = (R + rb - 1) / rb;
+  const long long gstride = e->tmpl_floats * rb;
+  std::memset(dst, 0, (size_t)ngrp * gstride * sizeof(float));
+  const uint8_t* m = e->mask.data();
+  for (int r = 0; r < R; ++r) {
+    const int g = r / rb, ri = r % rb;
+    const float* k = kern[r];
+    double s = 0.0;
+    for (const BoxDesc& b : e->boxes) {
+      float* base = dst + g * gstride + (long long)b.tmpl_off * rb;
+      for (int qz = 0; qz < b.d; ++qz)
+        for (int qy = 0; qy < b.h; ++qy) {
+          const long long trow = ((long long)(b.z0 + qz) * c->ty + (b.y0 + qy)) * c->tx + b.x0;
+          float* drow = base + ((long long)qz * b.h + qy) * b.nch * 8 * rb + ri * 8;
+          for (int x = 0; x < b.w; ++x) {
+            const float v = m[trow + x] ? k[trow + x] : 0.f;
+            drow[(x >> 3) * 8 * rb + (x & 7)] = v;
+            s += (double)v * (double)v;
+          }
+        }
+    }
+    b2[r] = s;
+  }
+}
+
+int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R, float* d_out, int kind) {
+  const int rb = pick_rb(c, R);
+  const int ngrp = (R + rb - 1) / rb;
+  const size_t tbytes = (size_t)ngrp * e->tmpl_floats * rb * sizeof(float);
+  const size_t off_t = stage_alloc(c, std::max<size_t>(tbytes, 16));
+  const size_t off_b = stage_alloc(c, (size_t)R * sizeof(double));
+  if (c->stage_used > c->stage_cap) return fail(IQ_ERR_STATE, "staging overflow (internal)");
+  pack_templates(c, e, kern, R, rb, (float*)(c->h_stage + off_t), (double*)(c->h_stage + off_b));
+  CK(cudaMemcpyAsync(c->d_stage + off_t, c->h_stage + off_t, (off_b + R * sizeof(double)) - off_t, cudaMemcpyHostToDevice,
+                     c->stream));
+  const float* a2 = nullptr;
+  int rc = get_a2(c, e, image, &a2);
+  if (rc) return rc;
+  iq::DistParams p{};
+  p.img = image < 0 ? c->d_ti : c->d_aux[image];
+  p.nx = c->nx; p.ny = c->ny; p.nz = c->nz;
+  p.nxo = c->nxo; p.nyo = c->nyo; p.nzo = c->nzo;
+  p.npos = c->npos;
+  p.nbox = (int)e->boxes.size();
+  p.boxes = e->d_boxes;
+  p.tmpl = (const float*)(c->d_stage + off_t);
+  p.tmpl_grp_stride = e->tmpl_floats * rb;
+  p.a2 = a2;
+  p.b2 = (const double*)(c->d_stage + off_b);
+  p.disabled = c->d_disabled;
+  p.out = d_out;
+  p.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch;
+  p.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch;
+  p.R = R;
+  p.WX = e->WX;
+  p.WY = e->WY;
+  const size_t smem = iq::dist_boxes_smem(e->boxes.data(), p.nbox, p.WX, p.WY, rb, &p.pitch_max, &p.patch_floats);
+  CK(iq::launch_dist_boxes(p, rb, std::max<size_t>(smem, 64), c->stream));
+  c->launches++;
+  return IQ_OK;
+}
+
+int build_uniform(iq_ctx* c) {
+  if (!c->enabled_idx.empty() || c->nenabled == 0) return IQ_OK;
+  c->enabled_idx.reserve((size_t)c->nenabled);
+  for (long long p = 0; p < c->npos; ++p)
+    if (c->h_disabled.empty() || !c->h_disabled[p]) c->enabled_idx.push_back(p);
+  const int64_t n = (int64_t)c->enabled_idx.size();
+  std::vector<float> zeros((size_t)std::min<int64_t>(n, 2), 0.f);
+  std::vector<double> pr;
+  double pc = 1.0;
+  if (n > 1) {  // all distances equal: every rank is 1 -> every probability is the same number
+    taumodel(2, 1, zeros.data(), pr);  // placeholder to keep the code path exercised
+    const double dn = (double)n;
+    const double x0 = (1.0 - 1.0 / dn) / (1.0 / dn);
+    const double colsum = ((dn - 1.0) + 1.0) * dn;  // n entries each (n - 1) + 1
+    const double Pi = ((dn - 1.0) + 1.0) / colsum;
+    const double X = (1.0 - Pi) / Pi;
+    pc = 1.0 / (1.0 + x0 * (X / x0));
+  }
+  c->uniform_prob.assign((size_t)n, pc);
+  c->uniform_sum = julia_sum_const(pc, 0, n - 1);
+  c->uniform_cum.resize((size_t)n);
+  double cw = 0.0;
+  for (int64_t i = 0; i < n; ++i) { cw = (i == 0) ? pc : cw + pc; c->uniform_cum[i] = cw; }
+  return IQ_OK;
+}
+
+int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double tol, const double* u, iq_result* results,
+                 int res_base) {
+  const int S = c->nsoft;
+  bool any_hard = false;
+  for (int r = 0; r < R; ++r) any_hard |= tiles[r].hard_nnz > 0;
+
+  // ---- fast path: empty overlap mask, no auxiliary information -> every enabled patch, uniform ----
+  if (e->nnz == 0 && !any_hard && S == 0) {
+    int rc = build_uniform(c);
+    if (rc) return rc;
+    const int64_t n = (int64_t)c->enabled_idx.size();
+    if (n == 0) return fail(IQ_ERR_INVALID, "all patches of the training image are disabled");
+    for (int r = 0; r < R; ++r) {
+      TileResult& tr = c->res[res_base + r];
+      tr.idx_ptr = c->enabled_idx.data();
+      tr.prob_ptr = c->uniform_prob.data();
+      tr.count = n;
+      iq_result& o = results[r];
+      o.count = n; o.idx = tr.idx_ptr; o.prob = tr.prob_ptr; o.picked = -1; o.relax_iters = 0; o.dmin = 0.f;
+      if (u) {
+        const double t = u[r] * c->uniform_sum;
+        // first i with cum[i] >= t among i < n-1, else n-1 (cum is non-decreasing)
+        const auto it = std::lower_bound(c->uniform_cum.begin(), c->uniform_cum.end() - 1, t);
+        o.picked = c->enabled_idx[(size_t)(it - c->uniform_cum.begin())];
+      }
+    }
+    return IQ_OK;
+  }
+
+  // ---- staging size ----
+  const int rb = pick_rb(c, R);
+  const int ngrp = (R + rb - 1) / rb;
+  size_t need = 4096 + (size_t)ngrp * rb * e->tmpl_floats * sizeof(float) + R * sizeof(double) + 512;
+  if (S > 0) need += (size_t)S * ((size_t)ngrp * rb * c->full_mask->tmpl_floats * sizeof(float) + R * sizeof(double) + 512);
+  long long hard_total = 0;
+  for (int r = 0; r < R; ++r) hard_total += tiles[r].hard_nnz;
+  need += (size_t)hard_total * (sizeof(long long) + sizeof(float)) + (R + 1) * sizeof(int) + 1024;
+  int rc = stage_reserve(c, need);
+  if (rc) return rc;
+  c->stage_used = 0;
+
+  const int nkind = 2 + S;
+  // init min = +Inf bits, max = 0 for every kind
+  for (int k = 0; k < nkind; ++k) {
+    CK(iq::launch_fill_u32(c->d_minmax + (size_t)(k * 2 + 0) * c->max_batch, 0x7f800000u, c->max_batch, c->stream));
+    CK(iq::launch_fill_u32(c->d_minmax + (size_t)(k * 2 + 1) * c->max_batch, 0u, c->max_batch, c->stream));
+    c->launches += 2;
+  }
+
+  // ---- distances ----
+  std::vector<const float*> kern(R);
+  for (int r = 0; r < R; ++r) kern[r] = tiles[r].simdev;
+  rc = run_dense(c, e, -1, kern.data(), R, c->d_Dovl, 0);
+  if (rc) return rc;
+  if (any_hard) {
+    const size_t off_ptr = stage_alloc(c, (R + 1) * sizeof(int));
+    const size_t off_off = stage_alloc(c, (size_t)hard_total * sizeof(long long));
+    const size_t off_val = stage_alloc(c, (size_t)hard_total * sizeof(float));
+    int* ptr = (int*)(c->h_stage + off_ptr);
+    long long* off = (long long*)(c->h_stage + off_off);
+    float* val = (float*)(c->h_stage + off_val);
+    int n = 0;
+    for (int r = 0; r < R; ++r) {
+      ptr[r] = n;
+      for (int i = 0; i < tiles[r].hard_nnz; ++i) {
+        const int o = tiles[r].hard_offset[i];
+        if (o < 0 || o >= c->tilevol) return fail(IQ_ERR_INVALID, "hard_offset out of the tile");
+        const int qx = o % c->tx, qy = (o / c->tx) % c->ty, qz = o / (c->tx * c->ty);
+        off[n] = ((long long)qz * c->ny + qy) * c->nx + qx;
+        val[n] = tiles[r].hard_value[i];
+        ++n;
+      }
+    }
+    ptr[R] = n;
+    CK(cudaMemcpyAsync(c->d_stage + off_ptr, c->h_stage + off_ptr, c->stage_used - off_ptr, cudaMemcpyHostToDevice, c->stream));
+    iq::SparseParams sp{};
+    sp.img = c->d_ti;
+    sp.nx = c->nx; sp.ny = c->ny; sp.nz = c->nz; sp.nxo = c->nxo; sp.nyo = c->nyo; sp.nzo = c->nzo;
+    sp.npos = c->npos;
+    sp.ptr = (const int*)(c->d_stage + off_ptr);
+    sp.off = (const long long*)(c->d_stage + off_off);
+    sp.val = (const float*)(c->d_stage + off_val);
+    sp.disabled = c->d_disabled;
+    sp.out = c->d_Dhard;
+    sp.minbits = c->d_minmax + (size_t)(1 * 2 + 0) * c->max_batch;
+    sp.maxbits = c->d_minmax + (size_t)(1 * 2 + 1) * c->max_batch;
+    sp.R = R;
+    CK(iq::launch_dist_sparse(sp, c->stream));
+    c->launches++;
+  }
+  for (int s = 0; s < S; ++s) {
+    for (int r = 0; r < R; ++r) {
+      if (!tiles[r].softdev || !tiles[r].softdev[s]) return fail(IQ_ERR_INVALID, "tile %d lacks softdev[%d]", r, s);
+      kern[r] = tiles[r].softdev[s];
+    }
+    rc = run_dense(c, c->full_mask, s, kern.data(), R, c->d_Dsoft[s], 2 + s);
+    if (rc) return rc;
+  }
+
+  // ---- per-tile source lists (src/iqsim.jl:230-234) ----
+  std::vector<int> nsrc(R);
+  std::vector<int> prim_kind(R);
+  bool any_relax = false;
+  for (int r = 0; r < R; ++r) {
+    iq::PickJob& J = c->h_pick[r];
+    std::memset(&J, 0, sizeof J);
+    int n = 0;
+    const bool hardtile = tiles[r].hard_nnz > 0;
+    if (hardtile) J.src[n++] = c->d_Dhard + (size_t)r * c->npos;
+    J.src[n++] = c->d_Dovl + (size_t)r * c->npos;
+    for (int s = 0; s < S; ++s) J.src[n++] = c->d_Dsoft[s] + (size_t)r * c->npos;
+    nsrc[r] = n;
+    prim_kind[r] = hardtile ? 1 : 0;
+    J.nsrc = n;
+    J.mode = n > 1 ? 1 : 0;
+    J.tol = tol;
+    J.minbits = c->d_minmax + (size_t)(prim_kind[r] * 2 + 0) * c->max_batch + r;
+    J.blockcount = c->d_blockcount + (size_t)r * iq::pick_nblk(c->npos);
+    J.total = c->d_total + r;
+    J.ticket = 0;
+    J.cand_idx = c->d_cand_idx + (size_t)r * c->npos;
+    J.cand_val = c->d_cand_val + (size_t)r * c->max_src * c->npos;
+    J.cap = c->npos;
+    any_relax |= n > 1;
+  }
+
+  // ---- relaxation bookkeeping (src/relaxation.jl:7-22) ----
+  std::vector<double> frac(R, 0.0);
+  std::vector<long long> dbsize(R, 0);
+  std::vector<int> iters(R, 0);
+  std::vector<char> pending(R, 0);
+  const long long npatterns = c->nenabled;
+  if (any_relax) {
+    if (npatterns <= 0) return fail(IQ_ERR_INVALID, "all patches of the training image are disabled");
+    CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, (size_t)nkind * 2 * c->max_batch * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < R; ++r) {
+      if (nsrc[r] <= 1) continue;
+      const unsigned mx = c->h_minmax[(size_t)(prim_kind[r] * 2 + 1) * c->max_batch + r];
+      const bool allzero = (mx == 0u);  // all(distance[enabled] .== 0)
+      dbsize[r] = allzero ? npatterns : (long long)std::ceil(tol * (double)npatterns);
+      frac[r] = 0.1 * ((double)dbsize[r] / (double)npatterns);
+      pending[r] = 1;
+    }
+  }
+
+  // ---- selection ----
+  const int maxS = c->max_src;
+  bool first_round = true;
+  for (;;) {
+    int njobs = 0;
+    if (any_relax) {
+      for (int r = 0; r < R; ++r) {
+        if (!pending[r]) continue;
+        const long long softk = (long long)std::ceil(frac[r] * (double)npatterns);
+        for (int s = 0; s < nsrc[r]; ++s) {
+          iq::SelJob& sj = c->h_sel[(size_t)r * maxS + s];
+          if (s == 0 && !first_round) continue;  // primary threshold already known
+          std::memset(&sj, 0, sizeof sj);
+          sj.map = c->h_pick[r].src[s];
+          sj.k = (unsigned long long)std::max<long long>(1, std::min<long long>(s == 0 ? dbsize[r] : softk, c->npos));
+          sj.active = 1;
+          ++njobs;
+        }
+        iters[r]++;
+      }
+      if (njobs > 0) {
+        // upload every job of the batch (inactive ones are skipped by the kernel)
+        if (first_round) {
+          for (int r = 0; r < R; ++r)
+            for (int s = 0; s < maxS; ++s)
+              if (!(pending[r] && s < nsrc[r])) std::memset(&c->h_sel[(size_t)r * maxS + s], 0, sizeof(iq::SelJob));
+          CK(cudaMemcpyAsync(c->d_sel, c->h_sel, (size_t)R * maxS * sizeof(iq::SelJob), cudaMemcpyHostToDevice, c->stream));
+        } else {
+          for (int r = 0; r < R; ++r) {
+            if (!pending[r]) continue;
+            CK(cudaMemcpyAsync(c->d_sel + (size_t)r * maxS + 1, c->h_sel + (size_t)r * maxS + 1,
+                               (size_t)(nsrc[r] - 1) * sizeof(iq::SelJob), cudaMemcpyHostToDevice, c->stream));
+          }
+        }
+        for (int pass = 0; pass < c->nshift; ++pass) {
+          CK(iq::launch_select_pass(c->d_sel, R * maxS, c->npos, c->d_shifts, c->nshift, c->stream));
+          c->launches++;
+        }
+      }
+    }
+    // pick jobs read the finished SelJob thresholds straight from device memory (no host round trip)
+    if (first_round) {
+      for (int r = 0; r < R; ++r) c->h_pick[r].sel = c->d_sel + (size_t)r * maxS;
+      CK(cudaMemcpyAsync(c->d_pick, c->h_pick, (size_t)R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(iq::launch_pick_count(c->d_pick, R, c->npos, c->stream));
+    c->launches++;
+    CK(cudaMemcpyAsync(c->h_total, c->d_total, (size_t)R * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    if (!any_relax) break;  // totals are read together with the candidates below
+    CK(cudaStreamSynchronize(c->stream));
+    bool again = false;
+    for (int r = 0; r < R; ++r) {
+      if (!pending[r]) continue;
+      if (c->h_total[r] > 0) { pending[r] = 0; continue; }
+      if (frac[r] >= 1.0) return fail(IQ_ERR_STATE, "relaxation found no candidate at frac = 1 (internal)");
+      frac[r] = std::min(frac[r] + 0.1, 1.0);
+      again = true;
+    }
+    first_round = false;
+    if (!again) break;
+  }
+
+  CK(iq::launch_pick_write(c->d_pick, R, c->npos, c->stream));
+  c->launches++;
+  CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, (size_t)nkind * 2 * c->max_batch * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // totals now valid
+
+  // ---- candidates back to the host ----
+  size_t tot = 0;
+  for (int r = 0; r < R; ++r) tot += c->h_total[r];
+  if (tot > c->h_cand_cap) {
+    if (c->h_cand_idx) cudaFreeHost(c->h_cand_idx);
+    if (c->h_cand_val) cudaFreeHost(c->h_cand_val);
+    c->h_cand_idx = nullptr; c->h_cand_val = nullptr;
+    const size_t cap = std::max<size_t>(tot * 2, 1 << 16);
+    CK(cudaMallocHost((void**)&c->h_cand_idx, cap * sizeof(unsigned)));
+    CK(cudaMallocHost((void**)&c->h_cand_val, cap * maxS * sizeof(float)));
+    c->h_cand_cap = cap;
+  }
+  {
+    size_t o = 0;
+    for (int r = 0; r < R; ++r) {
+      const size_t n = c->h_total[r];
+      if (n == 0) continue;
+      CK(cudaMemcpyAsync(c->h_cand_idx + o, c->d_cand_idx + (size_t)r * c->npos, n * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                         c->stream));
+      for (int s = 0; s < nsrc[r]; ++s)
+        CK(cudaMemcpyAsync(c->h_cand_val + (o * maxS) + (size_t)s * n, c->d_cand_val + ((size_t)r * maxS + s) * c->npos,
+                           n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      o += n;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+  }
+
+  // ---- tau model + optional sampling on the host (FP64, candidate-set sized) ----
+  {
+    size_t o = 0;
+    for (int r = 0; r < R; ++r) {
+      const int64_t n = c->h_total[r];
+      TileResult& tr = c->res[res_base + r];
+      tr.idx.resize((size_t)n);
+      for (int64_t i = 0; i < n; ++i) tr.idx[(size_t)i] = (int64_t)c->h_cand_idx[o + i];
+      if (n > 0) taumodel(n, nsrc[r], c->h_cand_val + o * maxS, tr.prob);
+      else tr.prob.clear();
+      tr.idx_ptr = tr.idx.data();
+      tr.prob_ptr = tr.prob.data();
+      tr.count = n;
+      iq_result& out = results[r];
+      out.count = n;
+      out.idx = tr.idx_ptr;
+      out.prob = tr.prob_ptr;
+      out.picked = -1;
+      out.relax_iters = iters[r];
+      const unsigned mb = c->h_minmax[(size_t)(prim_kind[r] * 2 + 0) * c->max_batch + r];
+      std::memcpy(&out.dmin, &mb, 4);
+      if (u && n > 0) out.picked = tr.idx[(size_t)sample_walk(tr.prob.data(), n, u[r])];
+      o += n;
+    }
+  }
+  return IQ_OK;
+}
+
+int do_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int ntile, double tol, const double* u, iq_result* results) {
+  if (!c || !ovlmask || !tiles || !results || ntile <= 0) return fail(IQ_ERR_INVALID, "iq_search: NULL argument or ntile <= 0");
+  if (!(tol > 0.0 && tol <= 1.0)) return fail(IQ_ERR_INVALID, "tolerance must be in range (0,1]");
+  for (int i = 0; i < ntile; ++i)
+    if (!tiles[i].simdev) return fail(IQ_ERR_INVALID, "tile %d: simdev is NULL", i);
+  CK(cudaSetDevice(c->device));
+  MaskEntry* e = nullptr;
+  int rc = get_mask(c, ovlmask, &e);
+  if (rc) return rc;
+  if ((int)c->res.size() < ntile) c->res.resize(ntile);
+  const int64_t l0 = c->launches;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  for (int base = 0; base < ntile; base += c->max_batch) {
+    const int R = std::min(c->max_batch, ntile - base);
+    rc = search_chunk(c, e, tiles + base, R, tol, u ? u + base : nullptr, results + base, base);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  c->last_launches = c->launches - l0;
+  return IQ_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// exported ABI
+// ================================================================================================
+extern "C" {
+
+int32_t iq_abi_version(void) { return IQ_ABI_VERSION; }
+
+int32_t iq_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* iq_last_error(void) { return g_err.c_str(); }
+
+int32_t iq_ctx_destroy(iq_ctx* c) {
+  if (!c) return IQ_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_ti);
+  for (auto p : c->d_aux) cudaFree(p);
+  cudaFree(c->d_sat_ti);
+  for (auto p : c->d_sat_aux) cudaFree(p);
+  cudaFree(c->d_disabled);
+  cudaFree(c->d_Dovl);
+  cudaFree(c->d_Dhard);
+  for (auto p : c->d_Dsoft) cudaFree(p);
+  cudaFree(c->d_minmax);
+  if (c->h_minmax) cudaFreeHost(c->h_minmax);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  cudaFree(c->d_stage);
+  cudaFree(c->d_sel);
+  if (c->h_sel) cudaFreeHost(c->h_sel);
+  cudaFree(c->d_pick);
+  if (c->h_pick) cudaFreeHost(c->h_pick);
+  cudaFree(c->d_blockcount);
+  cudaFree(c->d_total);
+  if (c->h_total) cudaFreeHost(c->h_total);
+  cudaFree(c->d_cand_idx);
+  cudaFree(c->d_cand_val);
+  if (c->h_cand_idx) cudaFreeHost(c->h_cand_idx);
+  if (c->h_cand_val) cudaFreeHost(c->h_cand_val);
+  cudaFree(c->d_shifts);
+  cudaFree(c->d_fetch);
+  for (auto& e : c->masks) {
+    cudaFree(e->d_boxes);
+    for (auto& kv : e->a2) cudaFree(kv.second);
+  }
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return IQ_OK;
+}
+
+static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(IQ_ERR_NO_DEVICE, "no CUDA device visible: libiqb200 has no CPU fallback");
+  }
+  if (d->device < 0 || d->device >= ndev) return fail(IQ_ERR_NO_DEVICE, "device %d out of range (have %d)", d->device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, d->device));
+  if (prop.major != 10) return fail(IQ_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", d->device, prop.major, prop.minor);
+  CK(cudaSetDevice(d->device));
+  c->device = d->device;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+
+  const size_t nimg = (size_t)c->nx * c->ny * c->nz;
+  const size_t nsat = (size_t)(c->nx + 1) * (c->ny + 1) * (c->nz + 1);
+  const size_t slack = 64;  // floats of zeroed slack after each image
+  auto upload = [&](const float* src, float** dimg, double** dsat) -> int {
+    CK(cudaMalloc((void**)dimg, (nimg + slack) * sizeof(float)));
+    CK(cudaMemsetAsync(*dimg, 0, (nimg + slack) * sizeof(float), c->stream));
+    CK(cudaMemcpyAsync(*dimg, src, nimg * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMalloc((void**)dsat, nsat * sizeof(double)));
+    CK(cudaMemsetAsync(*dsat, 0, nsat * sizeof(double), c->stream));
+    CK(iq::launch_sat_build(*dimg, *dsat, c->nx, c->ny, c->nz, c->stream));
+    c->launches += 3;
+    CK(cudaStreamSynchronize(c->stream));
+    return IQ_OK;
+  };
+  int rc = upload(d->ti, &c->d_ti, &c->d_sat_ti);
+  if (rc) return rc;
+  c->d_aux.assign(c->nsoft, nullptr);
+  c->d_sat_aux.assign(c->nsoft, nullptr);
+  for (int s = 0; s < c->nsoft; ++s) {
+    if (!d->auxti || !d->auxti[s]) return fail(IQ_ERR_INVALID, "auxti[%d] is NULL", s);
+    rc = upload(d->auxti[s], &c->d_aux[s], &c->d_sat_aux[s]);
+    if (rc) return rc;
+  }
+  c->nenabled = c->npos;
+  if (d->disabled) {
+    c->h_disabled.assign(d->disabled, d->disabled + c->npos);
+    long long nd = 0;
+    for (long long p = 0; p < c->npos; ++p) nd += c->h_disabled[p] ? 1 : 0;
+    c->nenabled = c->npos - nd;
+    if (nd > 0) {
+      CK(cudaMalloc((void**)&c->d_disabled, (size_t)c->npos));
+      CK(cudaMemcpyAsync(c->d_disabled, c->h_disabled.data(), (size_t)c->npos, cudaMemcpyHostToDevice, c->stream));
+    } else {
+      c->h_disabled.clear();
+    }
+  }
+  const size_t B = (size_t)c->max_batch;
+  c->max_src = 2 + c->nsoft;
+  CK(cudaMalloc((void**)&c->d_Dovl, B * c->npos * sizeof(float)));
+  CK(cudaMalloc((void**)&c->d_Dhard, B * c->npos * sizeof(float)));
+  c->d_Dsoft.assign(c->nsoft, nullptr);
+  for (int s = 0; s < c->nsoft; ++s) CK(cudaMalloc((void**)&c->d_Dsoft[s], B * c->npos * sizeof(float)));
+  const size_t nmm = (size_t)(2 + c->nsoft) * 2 * B;
+  CK(cudaMalloc((void**)&c->d_minmax, nmm * sizeof(unsigned)));
+  CK(cudaMallocHost((void**)&c->h_minmax, nmm * sizeof(unsigned)));
+  CK(cudaMalloc((void**)&c->d_sel, B * c->max_src * sizeof(iq::SelJob)));
+  CK(cudaMallocHost((void**)&c->h_sel, B * c->max_src * sizeof(iq::SelJob)));
+  CK(cudaMemsetAsync(c->d_sel, 0, B * c->max_src * sizeof(iq::SelJob), c->stream));
+  CK(cudaMalloc((void**)&c->d_pick, B * sizeof(iq::PickJob)));
+  CK(cudaMallocHost((void**)&c->h_pick, B * sizeof(iq::PickJob)));
+  CK(cudaMalloc((void**)&c->d_blockcount, B * iq::pick_nblk(c->npos) * sizeof(unsigned)));
+  CK(cudaMalloc((void**)&c->d_total, B * sizeof(unsigned)));
+  CK(cudaMallocHost((void**)&c->h_total, B * sizeof(unsigned)));
+  CK(cudaMalloc((void**)&c->d_cand_idx, B * c->npos * sizeof(unsigned)));
+  CK(cudaMalloc((void**)&c->d_cand_val, B * c->max_src * c->npos * sizeof(float)));
+  CK(cudaMalloc((void**)&c->d_fetch, (size_t)c->tilevol * sizeof(float)));
+  // radix-select schedule: 4 value bytes, then only the index bytes that can be non-zero
+  std::vector<int> shifts = {56, 48, 40, 32};
+  int nib = 1;
+  while (nib < 4 && ((unsigned long long)(c->npos - 1) >> (8 * nib)) != 0) ++nib;
+  for (int b = nib - 1; b >= 0; --b) shifts.push_back(8 * b);
+  c->nshift = (int)shifts.size();
+  CK(cudaMalloc((void**)&c->d_shifts, shifts.size() * sizeof(int)));
+  CK(cudaMemcpyAsync(c->d_shifts, shifts.data(), shifts.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  // the all-ones mask of the soft-data distance (fastdistance default weights, src/utils.jl:5)
+  if (c->nsoft > 0) {
+    std::vector<uint8_t> ones((size_t)c->tilevol, 1);
+    rc = get_mask(c, ones.data(), &c->full_mask);
+    if (rc) return rc;
+  }
+  return IQ_OK;
+}
+
+int32_t iq_ctx_create(iq_ctx** out, const iq_ctx_desc* d) {
+  if (!out || !d) return fail(IQ_ERR_INVALID, "iq_ctx_create: NULL argument");
+  *out = nullptr;
+  if (d->ndim != 2 && d->ndim != 3) return fail(IQ_ERR_INVALID, "ndim must be 2 or 3");
+  if (!d->ti) return fail(IQ_ERR_INVALID, "training image is NULL");
+  if (d->nsoft < 0 || d->nsoft > 6) return fail(IQ_ERR_INVALID, "nsoft must be in [0,6]");
+  for (int i = 0; i < 3; ++i) {
+    const int64_t n = i < d->ndim ? d->ti_size[i] : 1, t = i < d->ndim ? d->tile_size[i] : 1;
+    if (!(t > 0 && t <= n)) return fail(IQ_ERR_INVALID, "invalid tile size");
+    if (n > (1 << 20)) return fail(IQ_ERR_INVALID, "training image dimension too large");
+  }
+  iq_ctx* c = new (std::nothrow) iq_ctx();
+  if (!c) return fail(IQ_ERR_NOMEM, "out of host memory");
+  c->ndim = d->ndim;
+  c->nx = (int)d->ti_size[0]; c->ny = (int)d->ti_size[1]; c->nz = d->ndim == 3 ? (int)d->ti_size[2] : 1;
+  c->tx = (int)d->tile_size[0]; c->ty = (int)d->tile_size[1]; c->tz = d->ndim == 3 ? (int)d->tile_size[2] : 1;
+  c->nxo = c->nx - c->tx + 1; c->nyo = c->ny - c->ty + 1; c->nzo = c->nz - c->tz + 1;
+  c->npos = (long long)c->nxo * c->nyo * c->nzo;
+  c->tilevol = (long long)c->tx * c->ty * c->tz;
+  if (c->npos >= (1ll << 32)) { delete c; return fail(IQ_ERR_INVALID, "more than 2^32 patch positions"); }
+  c->nsoft = d->nsoft;
+  c->max_batch = std::max(1, d->max_batch);
+  const int rc = ctx_create_impl(c, d);
+  if (rc != IQ_OK) {
+    const std::string keep = g_err;
+    iq_ctx_destroy(c);
+    g_err = keep;
+    return rc;
+  }
+  *out = c;
+  return IQ_OK;
+}
+
+int32_t iq_ctx_npos(const iq_ctx* c, int64_t* npos, int64_t* nenabled) {
+  if (!c) return fail(IQ_ERR_INVALID, "NULL context");
+  if (npos) *npos = c->npos;
+  if (nenabled) *nenabled = c->nenabled;
+  return IQ_OK;
+}
+
+int32_t iq_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int32_t ntile, double tol, iq_result* results) {
+  return do_search(c, ovlmask, tiles, ntile, tol, nullptr, results);
+}
+
+int32_t iq_search_pick(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int32_t ntile, double tol, const double* u,
+                       iq_result* results) {
+  if (!u) return fail(IQ_ERR_INVALID, "iq_search_pick: u is NULL");
+  return do_search(c, ovlmask, tiles, ntile, tol, u, results);
+}
+
+int32_t iq_distance(iq_ctx* c, int32_t which, const uint8_t* ovlmask, const iq_tile* tile, float* out_map) {
+  if (!c || !tile || !out_map) return fail(IQ_ERR_INVALID, "iq_distance: NULL argument");
+  CK(cudaSetDevice(c->device));
+  c->stage_used = 0;
+  int rc;
+  const float* src = nullptr;
+  if (which == -1) {
+    if (!ovlmask || !tile->simdev) return fail(IQ_ERR_INVALID, "iq_distance: overlap distance needs ovlmask and simdev");
+    MaskEntry* e = nullptr;
+    rc = get_mask(c, ovlmask, &e);
+    if (rc) return rc;
+    rc = stage_reserve(c, 8192 + (size_t)4 * e->tmpl_floats * sizeof(float));
+    if (rc) return rc;
+    const float* k = tile->simdev;
+    rc = run_dense(c, e, -1, &k, 1, c->d_Dovl, 0);
+    if (rc) return rc;
+    src = c->d_Dovl;
+  } else if (which == -2) {
+    if (tile->hard_nnz <= 0) return fail(IQ_ERR_INVALID, "iq_distance: tile has no hard data");
+    rc = stage_reserve(c, 8192 + (size_t)tile->hard_nnz * 16);
+    if (rc) return rc;
+    const size_t off_ptr = stage_alloc(c, 2 * sizeof(int));
+    const size_t off_off = stage_alloc(c, (size_t)tile->hard_nnz * sizeof(long long));
+    const size_t off_val = stage_alloc(c, (size_t)tile->hard_nnz * sizeof(float));
+    int* ptr = (int*)(c->h_stage + off_ptr);
+    long long* off = (long long*)(c->h_stage + off_off);
+    float* val = (float*)(c->h_stage + off_val);
+    ptr[0] = 0; ptr[1] = tile->hard_nnz;
+    for (int i = 0; i < tile->hard_nnz; ++i) {
+      const int o = tile->hard_offset[i];
+      if (o < 0 || o >= c->tilevol) return fail(IQ_ERR_INVALID, "hard_offset out of the tile");
+      const int qx = o % c->tx, qy = (o / c->tx) % c->ty, qz = o / (c->tx * c->ty);
+      off[i] = ((long long)qz * c->ny + qy) * c->nx + qx;
+      val[i] = tile->hard_value[i];
+    }
+    CK(cudaMemcpyAsync(c->d_stage + off_ptr, c->h_stage + off_ptr, c->stage_used - off_ptr, cudaMemcpyHostToDevice, c->stream));
+    iq::SparseParams sp{};
+    sp.img = c->d_ti;
+    sp.nx = c->nx; sp.ny = c->ny; sp.nz = c->nz; sp.nxo = c->nxo; sp.nyo = c->nyo; sp.nzo = c->nzo;
+    sp.npos = c->npos;
+    sp.ptr = (const int*)(c->d_stage + off_ptr);
+    sp.off = (const long long*)(c->d_stage + off_off);
+    sp.val = (const float*)(c->d_stage + off_val);
+    sp.disabled = c->d_disabled;
+    sp.out = c->d_Dhard;
+    sp.minbits = nullptr; sp.maxbits = nullptr;
+    sp.R = 1;
+    CK(iq::launch_dist_sparse(sp, c->stream));
+    c->launches++;
+    src = c->d_Dhard;
+  } else if (which >= 0 && which < c->nsoft) {
+    if (!tile->softdev || !tile->softdev[which]) return fail(IQ_ERR_INVALID, "iq_distance: softdev missing");
+    rc = stage_reserve(c, 8192 + (size_t)4 * c->full_mask->tmpl_floats * sizeof(float));
+    if (rc) return rc;
+    const float* k = tile->softdev[which];
+    rc = run_dense(c, c->full_mask, which, &k, 1, c->d_Dsoft[which], 2 + which);
+    if (rc) return rc;
+    src = c->d_Dsoft[which];
+  } else {
+    return fail(IQ_ERR_INVALID, "iq_distance: bad `which`");
+  }
+  CK(cudaMemcpyAsync(out_map, src, (size_t)c->npos * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return IQ_OK;
+}
+
+int32_t iq_fetch_tile(iq_ctx* c, int64_t pos, float* out_tile) {
+  if (!c || !out_tile) return fail(IQ_ERR_INVALID, "iq_fetch_tile: NULL argument");
+  if (pos < 0 || pos >= c->npos) return fail(IQ_ERR_INVALID, "iq_fetch_tile: position out of range");
+  CK(cudaSetDevice(c->device));
+  const long long x0 = pos % c->nxo, y0 = (pos / c->nxo) % c->nyo, z0 = pos / ((long long)c->nxo * c->nyo);
+  CK(iq::launch_fetch_tile(c->d_ti, c->nx, c->ny, c->nz, c->tx, c->ty, c->tz, x0, y0, z0, c->d_fetch, c->stream));
+  c->launches++;
+  CK(cudaMemcpyAsync(out_tile, c->d_fetch, (size_t)c->tilevol * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return IQ_OK;
+}
+
+int32_t iq_last_search_stats(const iq_ctx* c, double* device_ms, int64_t* kernel_launches) {
+  if (!c) return fail(IQ_ERR_INVALID, "NULL context");
+  if (device_ms) *device_ms = c->last_ms;
+  if (kernel_launches) *kernel_launches = c->last_launches;
+  return IQ_OK;
+}
+
+int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
+  if (!c || !key) return fail(IQ_ERR_INVALID, "NULL argument");
+  if (std::strcmp(key, "rb") == 0) {
+    if (value != 0 && value != 1 && value != 2 && value != 4) return fail(IQ_ERR_INVALID, "rb must be 0 (auto), 1, 2 or 4");
+    c->rb_opt = (int)value;
+    return IQ_OK;
+  }
+  return fail(IQ_ERR_INVALID, "unknown option '%s'", key);
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// iq_internal.h -- shared declarations between the kernel TU (iq_kernels.cu) and the context /
+// orchestration TU (iq_ctx.cu).  Not part of the public ABI (include/iqb200.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace iq {
+
+constexpr int kMaxBox = 64;     // boxes per mask decomposition (slab unions need <= 6)
+constexpr int kT = 8;           // outputs per thread along x (register tile)
+constexpr int kWarpX = 32;      // outputs per warp along x  (4 lanes x 8)
+constexpr int kWarpY = 8;       // outputs per warp along y  (8 lanes)
+
+// One axis-aligned box of the (disjoint) mask decomposition, in tile coordinates.
+struct BoxDesc {
+  int x0, y0, z0;   // origin inside the tile
+  int w, h, d;      // extent
+  int nch;          // ceil(w / 8): template rows are zero-padded to nch*8
+  int tmpl_off;     // offset (floats, for ONE tile) of this box's packed template
+};
+
+// Parameters of the dense (box) correlation kernel.
+struct DistParams {
+  const float* img;            // training image / auxiliary TI, dense column-major
+  int nx, ny, nz;              // image size
+  int nxo, nyo, nzo;           // distance-map size
+  long long npos;              // nxo*nyo*nzo
+  int nbox;
+  const BoxDesc* boxes;        // device array [nbox]
+  const float* tmpl;           // packed templates [grp][box][qz][qy][chunk][r(RB)][8]
+  long long tmpl_grp_stride;   // floats per tile group
+  const float* a2;             // sum of img^2 over the mask per position (npos) or nullptr (=0)
+  const double* b2;            // [R] sum of w*kern^2 per tile
+  const uint8_t* disabled;     // [npos] or nullptr
+  float* out;                  // [R][npos]
+  unsigned* minbits;           // [R] atomicMin of float bits over enabled positions (or nullptr)
+  unsigned* maxbits;           // [R] atomicMax of float bits over enabled positions (or nullptr)
+  int R;                       // tiles in this launch
+  int WX, WY;                  // warps per CTA along x / y
+  int pitch_max;               // smem patch pitch upper bound (floats)
+  int patch_floats;            // smem floats reserved for the image patch
+};
+
+struct SparseParams {
+  const float* img;
+  int nx, ny, nz, nxo, nyo, nzo;
+  long long npos;
+  const int* ptr;              // [R+1] CSR row pointers
+  const long long* off;        // image offsets of the data voxels relative to the patch origin
+  const float* val;            // data values
+  const uint8_t* disabled;
+  float* out;                  // [R][npos]
+  unsigned* minbits;
+  unsigned* maxbits;
+  int R;
+};
+
+// Radix-select job: k-th smallest (value,index) key of one distance map.
+struct SelJob {
+  const float* map;              // npos floats
+  unsigned long long k;          // 1-based rank still wanted inside the current prefix
+  unsigned long long prefix;     // decided high bits of the key
+  unsigned long long mask;       // which bits are decided
+  unsigned long long kth;        // result: all keys <= kth are selected
+  int pass;                      // index into the shift schedule
+  int active;                    // 0 = done / skip
+  unsigned ticket;               // last-block detection
+  unsigned hist[256];
+};
+
+// Candidate predicate + outputs for one tile.
+struct PickJob {
+  int mode;                      // 0 = threshold on source 0, 1 = key <= kth for all sources
+  int nsrc;
+  const float* src[8];           // source maps (primary first)
+  const SelJob* sel;             // mode 1: device array [nsrc] of finished radix-select jobs
+  double tol;                    // mode 0: thr = (1+tol)*min
+  const unsigned* minbits;       // mode 0: pointer to the tile's min bits
+  unsigned* blockcount;          // [nblk] scratch
+  unsigned* total;               // [1] out: number of candidates
+  unsigned ticket;
+  unsigned* cand_idx;            // [cap]
+  float* cand_val;               // [nsrc][cap]
+  long long cap;
+};
+
+// ---- launch wrappers (iq_kernels.cu) -------------------------------------------------
+cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
+size_t dist_boxes_smem(const BoxDesc* boxes, int nbox, int WX, int WY, int rb, int* pitch_max, int* patch_floats);
+cudaError_t launch_dist_sparse(const SparseParams& p, cudaStream_t s);
+cudaError_t launch_sat_build(const float* img, double* sat, int nx, int ny, int nz, cudaStream_t s);
+cudaError_t launch_a2map(const double* sat, int nx, int ny, int nz, const BoxDesc* boxes, int nbox,
+                         float* a2, int nxo, int nyo, int nzo, cudaStream_t s);
+cudaError_t launch_fill_u32(unsigned* p, unsigned v, long long n, cudaStream_t s);
+cudaError_t launch_select_pass(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift,
+                               cudaStream_t s);
+cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
+cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
+cudaError_t launch_fetch_tile(const float* img, int nx, int ny, int nz, int tx, int ty, int tz,
+                              long long x0, long long y0, long long z0, float* out, cudaStream_t s);
+int pick_nblk(long long npos);
+
+}  // namespace iq

@@ -1,0 +1,589 @@
+// iq_kernels.cu -- hand-written sm_100a kernels for the overlap-distance search.
+//
+//   k_dist_boxes   masked SSD cross-correlation of R templates against every patch position of the
+//                  training image (replaces the two imfilter calls of fastdistance,
+//                  /root/reference/src/utils.jl:5-13 + src/imfilter.jl:5-26), fused with the
+//                  |A2 - 2AB + B2| combine (utils.jl:12), the disabled knock-out (iqsim.jl:207)
+//                  and the min/max reduction needed by the selection (iqsim.jl:237, relaxation.jl:11)
+//   k_dist_sparse  hard-data distance (iqsim.jl:210-219) as a direct sum over the few data voxels
+//   k_sat_* / k_a2map   summed-volume table of img^2 and the per-mask A2 map (the template-
+//                  independent half of fastdistance, utils.jl:8)
+//   k_select_pass  radix select of the k-th smallest (value,index) key = Base.partialsortperm with
+//                  the Perm ordering (relaxation.jl:12,27)
+//   k_pick_count / k_pick_write   ordered compaction of the candidate set = findall (iqsim.jl:237)
+//                  and fastintersect (relaxation.jl:41-48)
+#include "iq_internal.h"
+
+#include <math_constants.h>
+
+namespace iq {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8(float (&v)[8], const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// 8 template taps x 8 outputs x RB tiles of FMAs.  `lo`/`hi` hold 16 consecutive image values; output
+// t and tap j use value t+j (sliding window kept in registers, indices are compile-time).
+template <int RB>
+__device__ __forceinline__ void fma_chunk(float (&acc)[RB][8], const float (&lo)[8], const float (&hi)[8],
+                                          const float* __restrict__ kp) {
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    float k[8];
+    ld8(k, kp + r * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float w = (t + j < 8) ? lo[t + j] : hi[t + j - 8];
+        acc[r][t] = fmaf(w, k[j], acc[r][t]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned warp_min_u(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned warp_max_u(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense box correlation
+// ------------------------------------------------------------------------------------------------
+// CTA = WX x WY warps; a warp covers 32 (x) x 8 (y) output positions of one z plane, a thread 8
+// consecutive x positions.  For every box of the mask and every z plane of the box the CTA stages the
+// image patch (plus the template plane of its RB tiles) in shared memory and slides the template rows
+// over it.  Patch pitch = PW + 4 floats (== 4 mod 8) so that the LDS.128 of a quarter warp
+// (4 x-lanes, 2 rows) hit 8 distinct 16-byte bank groups.
+template <int RB>
+__global__ void __launch_bounds__(256) k_dist_boxes(const DistParams P) {
+  extern __shared__ __align__(16) float smem[];
+  float* patch = smem;
+  float* tmplS = smem + P.patch_floats;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int wx = warp % P.WX, wy = warp / P.WX;
+  const int lx = lane & 3, ly = lane >> 2;
+  const int X0 = blockIdx.x * (P.WX * kWarpX), Y0 = blockIdx.y * (P.WY * kWarpY);
+  const int pz = blockIdx.z % P.nzo, grp = blockIdx.z / P.nzo;
+  const int tx0 = (wx * 4 + lx) * kT;  // first output column of this thread, relative to X0
+  const int tyr = wy * kWarpY + ly;    // output row of this thread, relative to Y0
+
+  float tot[RB][8];
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) tot[r][t] = 0.f;
+
+  for (int b = 0; b < P.nbox; ++b) {
+    const BoxDesc bx = P.boxes[b];
+    const int PW = P.WX * kWarpX + bx.nch * 8;
+    const int pitch = PW + 4;
+    const int PH = P.WY * kWarpY + bx.h - 1;
+    const int plane_floats = bx.h * bx.nch * 8 * RB;
+    const float* tsrc = P.tmpl + (long long)grp * P.tmpl_grp_stride + (long long)bx.tmpl_off * RB;
+
+    for (int qz = 0; qz < bx.d; ++qz) {
+      __syncthreads();  // previous plane fully consumed
+      // ---- stage the image patch of plane pz + z0 + qz ----
+      const int gz = pz + bx.z0 + qz;
+      const float* src = P.img + (long long)gz * P.nx * P.ny;
+      for (int row = warp; row < PH; row += nwarps) {
+        const int gy = Y0 + bx.y0 + row;
+        const bool rowok = gy < P.ny;
+        const float* srow = src + (long long)gy * P.nx;
+        float* drow = patch + row * pitch;
+        for (int col = lane; col < PW; col += 32) {
+          const int gx = X0 + bx.x0 + col;
+          drow[col] = (rowok && gx < P.nx) ? __ldg(srow + gx) : 0.f;
+        }
+      }
+      // ---- stage the template plane of the RB tiles ----
+      {
+        const float4* t4 = reinterpret_cast<const float4*>(tsrc + (long long)qz * plane_floats);
+        float4* d4 = reinterpret_cast<float4*>(tmplS);
+        for (int i = tid; i < plane_floats / 4; i += nthreads) d4[i] = __ldg(t4 + i);
+      }
+      __syncthreads();
+
+      // ---- slide the template rows over the patch ----
+      float acc[RB][8];
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[r][t] = 0.f;
+
+      const float* rowp = patch + tyr * pitch + tx0;
+      const float* kp = tmplS;
+      for (int qy = 0; qy < bx.h; ++qy) {
+        float A[8], B[8];
+        ld8(A, rowp);
+        const float* rp = rowp + 8;
+        for (int c = 0; c < bx.nch; c += 2) {
+          ld8(B, rp);
+          rp += 8;
+          fma_chunk<RB>(acc, A, B, kp);
+          kp += RB * 8;
+          if (c + 1 < bx.nch) {
+            ld8(A, rp);
+            rp += 8;
+            fma_chunk<RB>(acc, B, A, kp);
+            kp += RB * 8;
+          }
+        }
+        rowp += pitch;
+      }
+      // two-level accumulation: per-plane partial sums keep the FP32 error growth ~sqrt(plane size)
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) tot[r][t] += acc[r][t];
+    }
+  }
+
+  // ---- epilogue: |A2 - 2AB + B2|, disabled -> +Inf, min/max over enabled positions ----
+  __shared__ unsigned s_min[4], s_max[4];
+  if (tid < 4) { s_min[tid] = 0x7f800000u; s_max[tid] = 0u; }
+  __syncthreads();
+  const int py = Y0 + tyr;
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int tile = grp * RB + r;
+    unsigned vmin = 0x7f800000u, vmax = 0u;
+    if (tile < P.R && py < P.nyo) {
+      const double b2 = P.b2[tile];
+      float* orow = P.out + (long long)tile * P.npos;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int x = X0 + tx0 + t;
+        if (x < P.nxo) {
+          const long long p = ((long long)pz * P.nyo + py) * P.nxo + x;
+          const double a2 = P.a2 ? (double)__ldg(P.a2 + p) : 0.0;
+          float d = (float)fabs(a2 - 2.0 * (double)tot[r][t] + b2);
+          const bool dis = P.disabled && P.disabled[p];
+          if (dis) d = CUDART_INF_F;
+          orow[p] = d;
+          if (!dis) {
+            const unsigned u = __float_as_uint(d);
+            vmin = min(vmin, u);
+            vmax = max(vmax, u);
+          }
+        }
+      }
+    }
+    if (P.minbits) {
+      vmin = warp_min_u(vmin);
+      vmax = warp_max_u(vmax);
+      if (lane == 0 && tile < P.R) {
+        atomicMin(&s_min[r], vmin);
+        atomicMax(&s_max[r], vmax);
+      }
+    }
+  }
+  if (P.minbits) {
+    __syncthreads();
+    if (tid < RB && grp * RB + tid < P.R) {
+      atomicMin(P.minbits + grp * RB + tid, s_min[tid]);
+      atomicMax(P.maxbits + grp * RB + tid, s_max[tid]);
+    }
+  }
+}
+
+size_t dist_boxes_smem(const BoxDesc* boxes, int nbox, int WX, int WY, int rb, int* pitch_max, int* patch_floats) {
+  int pf = 0, tf = 0, pm = 0;
+  for (int b = 0; b < nbox; ++b) {
+    const int PW = WX * kWarpX + boxes[b].nch * 8;
+    const int pitch = PW + 4;
+    const int PH = WY * kWarpY + boxes[b].h - 1;
+    pf = max(pf, PH * pitch);
+    pm = max(pm, pitch);
+    tf = max(tf, boxes[b].h * boxes[b].nch * 8 * rb);
+  }
+  pf = (pf + 3) & ~3;
+  if (pitch_max) *pitch_max = pm;
+  if (patch_floats) *patch_floats = pf;
+  return (size_t)(pf + tf) * sizeof(float);
+}
+
+template <int RB>
+static cudaError_t launch_dist_boxes_t(const DistParams& p, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(k_dist_boxes<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int ngrp = (p.R + RB - 1) / RB;
+  dim3 grid((p.nxo + p.WX * kWarpX - 1) / (p.WX * kWarpX), (p.nyo + p.WY * kWarpY - 1) / (p.WY * kWarpY),
+            p.nzo * ngrp);
+  dim3 block(p.WX * p.WY * 32);
+  k_dist_boxes<RB><<<grid, block, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem, cudaStream_t s) {
+  switch (rb) {
+    case 1: return launch_dist_boxes_t<1>(p, smem, s);
+    case 2: return launch_dist_boxes_t<2>(p, smem, s);
+    case 4: return launch_dist_boxes_t<4>(p, smem, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse (hard data) distance: D[p] = sum_i (img[p + off_i] - v_i)^2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dist_sparse(const SparseParams P) {
+  const int r = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ unsigned s_min, s_max;
+  if (threadIdx.x == 0) { s_min = 0x7f800000u; s_max = 0u; }
+  __syncthreads();
+  unsigned vmin = 0x7f800000u, vmax = 0u;
+  if (p < P.npos) {
+    const int x = (int)(p % P.nxo);
+    const long long q = p / P.nxo;
+    const int y = (int)(q % P.nyo), z = (int)(q / P.nyo);
+    const float* base = P.img + ((long long)z * P.ny + y) * P.nx + x;
+    float sum = 0.f;
+    const int i0 = P.ptr[r], i1 = P.ptr[r + 1];
+    for (int i = i0; i < i1; ++i) {
+      const float diff = __ldg(base + P.off[i]) - __ldg(P.val + i);
+      sum = fmaf(diff, diff, sum);
+    }
+    const bool dis = P.disabled && P.disabled[p];
+    if (dis) sum = CUDART_INF_F;
+    P.out[(long long)r * P.npos + p] = sum;
+    if (!dis) { vmin = __float_as_uint(sum); vmax = vmin; }
+  }
+  vmin = warp_min_u(vmin);
+  vmax = warp_max_u(vmax);
+  if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, vmin); atomicMax(&s_max, vmax); }
+  __syncthreads();
+  if (threadIdx.x == 0 && P.minbits) { atomicMin(P.minbits + r, s_min); atomicMax(P.maxbits + r, s_max); }
+}
+
+cudaError_t launch_dist_sparse(const SparseParams& p, cudaStream_t s) {
+  dim3 grid((unsigned)((p.npos + 255) / 256), p.R);
+  k_dist_sparse<<<grid, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// summed-volume table of img^2 in FP64: sat(x,y,z) = sum_{i<x,j<y,k<z} img(i,j,k)^2,
+// dims (nx+1, ny+1, nz+1), zero on the x=0 / y=0 / z=0 faces.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sat_rows(const float* __restrict__ img, double* __restrict__ sat, int nx, int ny, int nz) {
+  // one warp per (y,z) row: square + inclusive scan along x with shuffles
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)ny * nz) return;
+  const int y = (int)(row % ny), z = (int)(row / ny);
+  const float* src = img + row * nx;
+  double* dst = sat + ((long long)(z + 1) * (ny + 1) + (y + 1)) * (nx + 1);
+  double carry = 0.0;
+  if (lane == 0) dst[0] = 0.0;
+  for (int x0 = 0; x0 < nx; x0 += 32) {
+    const int x = x0 + lane;
+    double v = 0.0;
+    if (x < nx) { const double f = (double)src[x]; v = f * f; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += n;
+    }
+    v += carry;
+    if (x < nx) dst[x + 1] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+__global__ void k_sat_y(double* __restrict__ sat, int nx, int ny, int nz) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;  // 0..nx
+  const int z = blockIdx.y;                             // 0..nz-1 -> plane z+1
+  if (x > nx) return;
+  double* pl = sat + (long long)(z + 1) * (ny + 1) * (nx + 1);
+  double run = 0.0;
+  pl[x] = 0.0;
+  for (int y = 1; y <= ny; ++y) {
+    run += pl[(long long)y * (nx + 1) + x];
+    pl[(long long)y * (nx + 1) + x] = run;
+  }
+}
+__global__ void k_sat_z(double* __restrict__ sat, int nx, int ny, int nz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long plane = (long long)(ny + 1) * (nx + 1);
+  if (i >= plane) return;
+  double run = 0.0;
+  sat[i] = 0.0;
+  for (int z = 1; z <= nz; ++z) {
+    run += sat[z * plane + i];
+    sat[z * plane + i] = run;
+  }
+}
+
+cudaError_t launch_sat_build(const float* img, double* sat, int nx, int ny, int nz, cudaStream_t s) {
+  const long long rows = (long long)ny * nz;
+  k_sat_rows<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(img, sat, nx, ny, nz);
+  k_sat_y<<<dim3((nx + 1 + 127) / 128, nz), 128, 0, s>>>(sat, nx, ny, nz);
+  const long long plane = (long long)(ny + 1) * (nx + 1);
+  k_sat_z<<<(unsigned)((plane + 255) / 256), 256, 0, s>>>(sat, nx, ny, nz);
+  return cudaGetLastError();
+}
+
+__global__ void k_a2map(const double* __restrict__ sat, int nx, int ny, int nz, const BoxDesc* __restrict__ boxes,
+                        int nbox, float* __restrict__ a2, int nxo, int nyo, int nzo) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npos = (long long)nxo * nyo * nzo;
+  if (p >= npos) return;
+  const int x = (int)(p % nxo);
+  const long long q = p / nxo;
+  const int y = (int)(q % nyo), z = (int)(q / nyo);
+  const long long sx = 1, sy = nx + 1, sz = (long long)(nx + 1) * (ny + 1);
+  double sum = 0.0;
+  for (int b = 0; b < nbox; ++b) {
+    const BoxDesc bx = boxes[b];
+    const long long x0 = x + bx.x0, x1 = x0 + bx.w, y0 = y + bx.y0, y1 = y0 + bx.h, z0 = z + bx.z0, z1 = z0 + bx.d;
+    sum += sat[z1 * sz + y1 * sy + x1 * sx] - sat[z1 * sz + y1 * sy + x0 * sx] - sat[z1 * sz + y0 * sy + x1 * sx] +
+           sat[z1 * sz + y0 * sy + x0 * sx] - sat[z0 * sz + y1 * sy + x1 * sx] + sat[z0 * sz + y1 * sy + x0 * sx] +
+           sat[z0 * sz + y0 * sy + x1 * sx] - sat[z0 * sz + y0 * sy + x0 * sx];
+  }
+  a2[p] = (float)sum;
+}
+
+cudaError_t launch_a2map(const double* sat, int nx, int ny, int nz, const BoxDesc* boxes, int nbox, float* a2, int nxo,
+                         int nyo, int nzo, cudaStream_t s) {
+  const long long npos = (long long)nxo * nyo * nzo;
+  k_a2map<<<(unsigned)((npos + 255) / 256), 256, 0, s>>>(sat, nx, ny, nz, boxes, nbox, a2, nxo, nyo, nzo);
+  return cudaGetLastError();
+}
+
+__global__ void k_fill_u32(unsigned* p, unsigned v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+cudaError_t launch_fill_u32(unsigned* p, unsigned v, long long n, cudaStream_t s) {
+  k_fill_u32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix select on the 64-bit key (float bits << 32 | position): values are >= 0 or +Inf so the
+// unsigned order of the bits is the numeric order; the low word breaks ties by ascending position,
+// exactly the Perm ordering of Base.partialsortperm.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long make_key(float v, long long p) {
+  return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)p;
+}
+
+__global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, long long npos, const int* __restrict__ shifts,
+                                                     int nshift) {
+  SelJob* J = jobs + blockIdx.y;
+  __shared__ unsigned h[256];
+  __shared__ int s_active, s_pass, s_last;
+  __shared__ unsigned long long s_prefix, s_mask;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_active = J->active;
+    s_pass = J->pass;
+    s_prefix = J->prefix;
+    s_mask = J->mask;
+  }
+  h[tid] = 0;
+  __syncthreads();
+  if (!s_active) return;
+  const int shift = shifts[s_pass];
+  const unsigned long long prefix = s_prefix, mask = s_mask;
+  const float* __restrict__ map = J->map;
+  for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < npos; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = make_key(map[i], i);
+    if ((key & mask) == prefix) atomicAdd(&h[(unsigned)(key >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  if (h[tid]) atomicAdd(&J->hist[tid], h[tid]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) {
+    __threadfence();
+    volatile unsigned* gh = J->hist;
+    unsigned long long k = J->k, cum = 0, c = 0;
+    int b = 0;
+    for (; b < 256; ++b) {
+      c = gh[b];
+      if (cum + c >= k) break;
+      cum += c;
+    }
+    if (b == 256) { b = 255; }  // k beyond the population: clamp (host never asks for this)
+    k -= cum;
+    const unsigned long long np = prefix | ((unsigned long long)b << shift);
+    const bool exact = (c == k);  // every key sharing the new prefix is selected
+    if (exact || s_pass + 1 == nshift) {
+      J->kth = exact ? (np | ((shift == 0) ? 0ull : ((1ull << shift) - 1ull))) : np;
+      J->active = 0;
+    } else {
+      const int ns = shifts[s_pass + 1];
+      J->mask = ~((1ull << (ns + 8)) - 1ull);
+      J->pass = s_pass + 1;
+    }
+    J->prefix = np;
+    J->k = k;
+    for (int i = 0; i < 256; ++i) gh[i] = 0;
+    J->ticket = 0;
+    __threadfence();
+  }
+}
+
+cudaError_t launch_select_pass(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s) {
+  long long nb = (npos + 256 * 8 - 1) / (256 * 8);
+  if (nb > 148 * 4) nb = 148 * 4;
+  if (nb < 1) nb = 1;
+  k_select_pass<<<dim3((unsigned)nb, njobs), 256, 0, s>>>(jobs, npos, shifts, nshift);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// candidate predicate + ordered compaction
+// ------------------------------------------------------------------------------------------------
+constexpr int kPickChunk = 4096;  // positions per CTA (256 threads x 16)
+
+int pick_nblk(long long npos) { return (int)((npos + kPickChunk - 1) / kPickChunk); }
+
+__device__ __forceinline__ bool pick_pred(const PickJob& J, long long p, double thr) {
+  if (J.mode == 0) return (double)J.src[0][p] <= thr;
+  bool ok = true;
+  for (int s = 0; s < J.nsrc; ++s) ok = ok && (make_key(J.src[s][p], p) <= J.sel[s].kth);
+  return ok;
+}
+
+__global__ void __launch_bounds__(256) k_pick_count(PickJob* jobs, long long npos) {
+  PickJob& J = jobs[blockIdx.y];
+  const int tid = threadIdx.x;
+  const double thr = (J.mode == 0) ? (1.0 + J.tol) * (double)__uint_as_float(*J.minbits) : 0.0;
+  const long long base = (long long)blockIdx.x * kPickChunk;
+  unsigned cnt = 0;
+#pragma unroll 4
+  for (int it = 0; it < kPickChunk / 256; ++it) {
+    const long long p = base + it * 256 + tid;
+    if (p < npos && pick_pred(J, p, thr)) ++cnt;
+  }
+  __shared__ unsigned s_w[8];
+  __shared__ int s_last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((tid & 31) == 0) s_w[tid >> 5] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    J.blockcount[blockIdx.x] = t;
+    __threadfence();
+    s_last = (atomicAdd(&J.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // last CTA of this job: exclusive scan of the block counts (in place) + total
+  __threadfence();
+  volatile unsigned* bc = J.blockcount;
+  __shared__ unsigned s_scan[256];
+  __shared__ unsigned s_carry;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  const int nblk = gridDim.x;
+  for (int b0 = 0; b0 < nblk; b0 += 256) {
+    const int i = b0 + tid;
+    const unsigned v = (i < nblk) ? bc[i] : 0u;
+    s_scan[tid] = v;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      const unsigned n = (tid >= o) ? s_scan[tid - o] : 0u;
+      __syncthreads();
+      s_scan[tid] += n;
+      __syncthreads();
+    }
+    const unsigned incl = s_scan[tid];
+    const unsigned carry = s_carry;
+    if (i < nblk) bc[i] = carry + incl - v;
+    __syncthreads();
+    if (tid == 255) s_carry = carry + incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *J.total = s_carry;
+    J.ticket = 0;
+    __threadfence();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pick_write(PickJob* jobs, long long npos) {
+  const PickJob& J = jobs[blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double thr = (J.mode == 0) ? (1.0 + J.tol) * (double)__uint_as_float(*J.minbits) : 0.0;
+  const long long base = (long long)blockIdx.x * kPickChunk;
+  __shared__ unsigned s_w[8];
+  unsigned running = J.blockcount[blockIdx.x];
+  for (int it = 0; it < kPickChunk / 256; ++it) {
+    const long long p = base + it * 256 + tid;
+    const bool ok = (p < npos) && pick_pred(J, p, thr);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    unsigned before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const unsigned c = s_w[w];
+      if (w < warp) before += c;
+      all += c;
+    }
+    if (ok) {
+      const long long slot = (long long)running + before + __popc(bal & ((1u << lane) - 1u));
+      if (slot < J.cap) {
+        J.cand_idx[slot] = (unsigned)p;
+        for (int s = 0; s < J.nsrc; ++s) J.cand_val[(long long)s * J.cap + slot] = J.src[s][p];
+      }
+    }
+    running += all;
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStream_t s) {
+  k_pick_count<<<dim3(pick_nblk(npos), njobs), 256, 0, s>>>(jobs, npos);
+  return cudaGetLastError();
+}
+cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStream_t s) {
+  k_pick_write<<<dim3(pick_nblk(npos), njobs), 256, 0, s>>>(jobs, npos);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// view_kernel (utils.jl:63-67): gather one tile-sized patch of the resident image
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fetch_tile(const float* __restrict__ img, int nx, int ny, int nz, int tx, int ty, int tz,
+                             long long x0, long long y0, long long z0, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)tx * ty * tz;
+  if (i >= n) return;
+  const int qx = (int)(i % tx);
+  const long long q = i / tx;
+  const int qy = (int)(q % ty), qz = (int)(q / ty);
+  out[i] = img[((z0 + qz) * ny + (y0 + qy)) * nx + (x0 + qx)];
+}
+cudaError_t launch_fetch_tile(const float* img, int nx, int ny, int nz, int tx, int ty, int tz, long long x0,
+                              long long y0, long long z0, float* out, cudaStream_t s) {
+  const long long n = (long long)tx * ty * tz;
+  k_fetch_tile<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(img, nx, ny, nz, tx, ty, tz, x0, y0, z0, out);
+  return cudaGetLastError();
+}
+
+}  // namespace iq

@@ -1,0 +1,135 @@
+/*
+ * iqb200.h -- C ABI of libiqb200.so, the B200-native (sm_100a) replacement for the per-tile
+ * overlap-distance search of ImageQuilting.jl v1.3.1.
+ *
+ * What it replaces (citations relative to the reference checkout):
+ *   - the backend shim  imfilter_kernel / array_kernel / view_kernel
+ *         src/imfilter.jl:5-28, src/utils.jl:57-67
+ *   - fastdistance       src/utils.jl:5-13
+ *   - the distance assembly + candidate selection inside the tile loop of iqsim
+ *         src/iqsim.jl:187-240  (overlap / hard / soft distances, disabled knock-out,
+ *         threshold selection), relaxation src/relaxation.jl:5-48,
+ *         taumodel src/taumodel.jl:5-45
+ * What stays with the caller: RNG and sampling (src/iqsim.jl:243) unless the caller asks
+ * for a fused pick and supplies the uniform itself; the boundary cut (src/graphcut.jl) and
+ * the paste (src/iqsim.jl:251-278).
+ *
+ * Conventions
+ *   - All arrays are column-major (Julia layout, first index fastest), densely packed.
+ *   - ndim is 2 or 3; sizes are passed as int64_t[ndim]; a 2-D problem is a 3-D one with nz = 1.
+ *   - Linear indices returned are 0-BASED column-major indices into the distance map of size
+ *     distsize = ti_size - tile_size + 1 (Julia callers add 1; src/iqsim.jl:244).
+ *   - Every entry point returns an int32_t status: IQ_OK (0) or a negative IQ_ERR_* code; the
+ *     message of the last failure on the calling thread is returned by iq_last_error().
+ *   - No exceptions cross the ABI, no callbacks, no global state other than the thread-local
+ *     error string.  No CPU fallback: iq_ctx_create fails with IQ_ERR_NO_DEVICE when there is
+ *     no sm_100 device.
+ *   - A context is bound to one device and one stream; calls on ONE context must be serialised
+ *     by the caller; different contexts may be driven from different host threads (one per GPU).
+ *   - Host buffers passed in belong to the caller and are only read during the call.  Buffers
+ *     handed out in iq_result belong to the context and stay valid until the next iq_search* /
+ *     iq_ctx_destroy on that context.
+ */
+#ifndef IQB200_H
+#define IQB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IQ_ABI_VERSION 1
+
+enum {
+  IQ_OK = 0,
+  IQ_ERR_INVALID = -1,    /* bad argument (NULL, size mismatch, out-of-range) */
+  IQ_ERR_NO_DEVICE = -2,  /* no CUDA device of compute capability 10.x / bad device index */
+  IQ_ERR_CUDA = -3,       /* a CUDA runtime call failed; see iq_last_error() */
+  IQ_ERR_NOMEM = -4,      /* host or device allocation failed */
+  IQ_ERR_STATE = -5       /* call sequence error (e.g. result read before a search) */
+};
+
+typedef struct iq_ctx iq_ctx;
+
+/* Geometry + resident images.  Replaces `geoconfig` (src/iqsim.jl:118-127) and the uploads done
+ * by imagepreproc/array_kernel (src/utils.jl:57-61,86-89). */
+typedef struct iq_ctx_desc {
+  int32_t ndim;               /* 2 or 3 */
+  int64_t ti_size[3];         /* training image size (unused dims = 1) */
+  int64_t tile_size[3];       /* tile size (unused dims = 1) */
+  const float* ti;            /* training image, NaN/missing already replaced by 0 (src/utils.jl:96-102) */
+  const uint8_t* disabled;    /* distsize bytes, nonzero = patch contains an inactive voxel
+                                 (finddisabled, src/utils.jl:115-129); may be NULL */
+  int32_t nsoft;              /* number of auxiliary variables (soft data), >= 0 */
+  const float* const* auxti;  /* nsoft auxiliary training images, same size as ti (src/iqsim.jl:222-227) */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t max_batch;          /* max tiles per iq_search call that share device buffers (>=1); larger
+                                 batches are processed in chunks */
+} iq_ctx_desc;
+
+/* One tile of a batch.  All tiles of one iq_search call share the overlap mask (on any path the
+ * mask depends only on the path step, not on the realization: src/iqsim.jl:188-205). */
+typedef struct iq_tile {
+  const float* simdev;          /* tile-sized current content of the simulation grid (src/iqsim.jl:185) */
+  int32_t hard_nnz;             /* number of hard data inside this tile; 0 = none (src/iqsim.jl:210-219) */
+  const int32_t* hard_offset;   /* hard_nnz 0-based column-major offsets inside the tile */
+  const float* hard_value;      /* hard_nnz values */
+  const float* const* softdev;  /* ctx.nsoft tile-sized views of the padded auxiliary grids (src/iqsim.jl:224) */
+} iq_tile;
+
+typedef struct iq_result {
+  int64_t count;        /* number of candidates (length of patterndb, src/iqsim.jl:237) */
+  const int64_t* idx;   /* ascending 0-based linear indices into the distance map */
+  const double* prob;   /* taumodel output, unnormalised (src/taumodel.jl:44) */
+  int64_t picked;       /* iq_search_pick only: the sampled linear index (src/iqsim.jl:243), else -1 */
+  int32_t relax_iters;  /* number of relaxation rounds used (0 on the threshold path) */
+  float dmin;           /* minimum of the primary distance over enabled positions */
+} iq_result;
+
+/* library / device info */
+int32_t iq_abi_version(void);
+int32_t iq_device_count(void);
+const char* iq_last_error(void);
+
+/* lifetime */
+int32_t iq_ctx_create(iq_ctx** out, const iq_ctx_desc* desc);
+int32_t iq_ctx_destroy(iq_ctx* ctx);
+int32_t iq_ctx_npos(const iq_ctx* ctx, int64_t* npos, int64_t* nenabled);
+
+/* The hot path: for each of `ntile` tiles sharing `ovlmask` (tile-sized, nonzero = voxel belongs
+ * to the overlap with an already pasted neighbour) compute the overlap / hard / soft distance maps,
+ * knock out disabled patches, select the candidate set (threshold rule when there is no auxiliary
+ * distance, relaxation otherwise) and evaluate the tau model.  results[i] describes tile i.
+ * Replaces src/iqsim.jl:187-240. */
+int32_t iq_search(iq_ctx* ctx, const uint8_t* ovlmask, const iq_tile* tiles, int32_t ntile,
+                  double tol, iq_result* results);
+
+/* Same, plus the inverse-CDF walk of StatsBase.sample (src/iqsim.jl:243) with caller-supplied
+ * uniforms u[i] in [0,1): results[i].picked is the chosen pattern.  idx/prob are still exposed. */
+int32_t iq_search_pick(iq_ctx* ctx, const uint8_t* ovlmask, const iq_tile* tiles, int32_t ntile,
+                       double tol, const double* u, iq_result* results);
+
+/* Parity / debugging entry: one full distance map (distsize floats, +Inf on disabled patches).
+ *   which = -1 : overlap distance   fastdistance(TI, simdev, weights=ovlmask)
+ *   which = -2 : hard distance      fastdistance(TI, harddev, weights=hardmask)
+ *   which >= 0 : soft distance for auxiliary variable `which`
+ * Replaces one fastdistance call (src/utils.jl:5-13) + the knock-out (src/iqsim.jl:207,216,226). */
+int32_t iq_distance(iq_ctx* ctx, int32_t which, const uint8_t* ovlmask, const iq_tile* tile,
+                    float* out_map);
+
+/* Fetch a tile-sized patch of the resident training image starting at linear index `pos` of the
+ * distance map (view_kernel, src/utils.jl:63-67). */
+int32_t iq_fetch_tile(iq_ctx* ctx, int64_t pos, float* out_tile);
+
+/* Timing hooks for benchmarks: device time (ms, CUDA events on the context's stream) and number
+ * of kernels launched by the most recent iq_search* call. */
+int32_t iq_last_search_stats(const iq_ctx* ctx, double* device_ms, int64_t* kernel_launches);
+
+/* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 1,2,4), "variant". */
+int32_t iq_ctx_set_option(iq_ctx* ctx, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IQB200_H */

