@@ -313,11 +313,6 @@ int get_mask(iq_ctx* c, const uint8_t* mask, MaskEntry** out) {
   e->hash = h;
   for (long long i = 0; i < c->tilevol; ++i) e->nnz += mask[i] ? 1 : 0;
   decompose(mask, c->tx, c->ty, c->tz, e->boxes);
-  if ((int)e->boxes.size() > iq::kMaxBox) {  // very fragmented mask: one dense box, zeros carry the mask
-    e->boxes.clear();
-    BoxDesc b{0, 0, 0, c->tx, c->ty, c->tz, (c->tx + 7) / 8, 0};
-    e->boxes.push_back(b);
-  }
   long long off = 0;
   for (auto& b : e->boxes) {
     b.tmpl_off = (int)off;

@@ -6,7 +6,6 @@
 
 namespace iq {
 
-constexpr int kMaxBox = 64;     // boxes per mask decomposition (slab unions need <= 6)
 constexpr int kT = 8;           // outputs per thread along x (register tile)
 constexpr int kWarpX = 32;      // outputs per warp along x  (4 lanes x 8)
 constexpr int kWarpY = 8;       // outputs per warp along y  (8 lanes)

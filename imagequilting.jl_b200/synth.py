@@ -16,7 +16,7 @@ def gaussian_field(shape, ranges, seed):
         sh = [1] * len(shape)
         sh[ax] = g.size
         spec = spec * g.reshape(sh)
-    field = np.fft.irfftn(spec, s=shape)
+    field = np.fft.irfftn(spec, s=shape, axes=tuple(range(len(shape))))
     field = (field - field.mean()) / field.std()
     return np.asfortranarray(field.astype(np.float32))
 

@@ -84,7 +84,7 @@ def test_fragmented_and_dense_masks():
     tile = (16, 12, 5)
     r = np.random.default_rng(4)
     with api.SearchContext(ti, tile) as ctx:
-        for density in (0.02, 0.5, 1.0):  # random masks: many boxes / > kMaxBox fallback / the full tile
+        for density in (0.02, 0.5, 1.0):  # random masks: few boxes / hundreds of boxes / the full tile
             m = r.random(tile) < density
             simdev = r.standard_normal(tile).astype(np.float32)
             got = ctx.distance(-1, m, simdev)
@@ -211,12 +211,17 @@ def test_fetch_tile():
 
 
 # ---- end-to-end: realizations bit-exact against the oracle on identical seeds -----------------------
-def run_both(cfg, seed, **over):
+def run_both(cfg, seed, native_cut=False, **over):
+    """native_cut=True hands the product's host cut routine to the oracle so that the comparison isolates
+    the search: on categorical images the reference's capacities mix ~1e16 (division by eps) with O(1)
+    terms, equal-cost cuts abound and which one a max-flow code returns is decided by FP rounding (cut
+    parity on well-conditioned slabs is tested separately in tests/test_abi_cpu.py)."""
     kw = dict(cfg["kwargs"])
     kw.update(over)
     got, ex = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(seed), return_picks=True, **kw)
     trace = []
-    want = O.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(seed), method="direct", trace=trace, **kw)
+    want = O.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(seed), method="direct", trace=trace,
+                   cut_fn=iqb200.graphcut if native_cut else None, **kw)
     return got, want, ex, trace
 
 
@@ -236,7 +241,7 @@ def test_iqsim_3d_categorical_hard_soft_bit_exact():
     aux = np.asfortranarray(np.round(synth.box_mean(ti, (3, 3, 3)) * 2) / 2)
     hard = {k: v for k, v in cfg["kwargs"]["hard"].items()}
     hard[(0, 0, 0)] = float("nan")
-    got, want, ex, trace = run_both(cfg, 7, nreal=2, hard=hard, soft=[(aux, aux)], debug=True)
+    got, want, ex, trace = run_both(cfg, 7, native_cut=True, nreal=2, hard=hard, soft=[(aux, aux)], debug=True)
     picks_ref = np.array([t["rind"] for t in trace]).reshape(2, -1)
     assert np.array_equal(ex["picks"], picks_ref)
     for a, b in zip(got[0], want[0]):
@@ -251,7 +256,7 @@ def test_iqsim_paths_bit_exact(path):
     r = np.random.default_rng(3)
     ti = np.asfortranarray(r.integers(0, 4, (36, 30)).astype(np.float64))
     cfg = dict(trainimg=ti, tilesize=(12, 10), kwargs=dict(path=path, nreal=3, overlap=(0.25, 0.3)))
-    got, want, ex, trace = run_both(cfg, 5, simsize=(40, 33))
+    got, want, ex, trace = run_both(cfg, 5, native_cut=True, simsize=(40, 33))
     for g, w in zip(got, want):
         assert g.dtype == np.float64 and np.array_equal(g, w)
 
