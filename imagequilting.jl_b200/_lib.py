@@ -51,7 +51,8 @@ class IqhDesc(C.Structure):
 class IqhStats(C.Structure):
     _fields_ = [("search_ms", C.c_double), ("search_device_ms", C.c_double), ("cut_ms", C.c_double),
                 ("total_ms", C.c_double), ("searches", C.c_int64), ("kernel_launches", C.c_int64),
-                ("candidates", C.c_int64)]
+                ("candidates", C.c_int64), ("setup_ms", C.c_double), ("dist_kernel_ms", C.c_double),
+                ("dist_launches", C.c_int64)]
 
 
 # every symbol include/*.h declares: name -> (restype, argtypes)
@@ -68,6 +69,8 @@ SYMBOLS = {
     "iq_distance": (C.c_int32, [C.c_void_p, C.c_int32, c_u8_p, C.POINTER(IqTile), c_float_p]),
     "iq_fetch_tile": (C.c_int32, [C.c_void_p, C.c_int64, c_float_p]),
     "iq_last_search_stats": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
+    "iq_last_search_kernel_ms": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
+    "iq_bench_fma_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "iq_ctx_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
     "iqh_run": (C.c_int32, [C.POINTER(IqhDesc), c_double_p, c_u8_p, c_i64_p, C.POINTER(IqhStats)]),
     "iqh_graphcut": (C.c_int32, [c_double_p, c_double_p, C.c_int32, c_i64_p, C.c_int32, c_u8_p]),

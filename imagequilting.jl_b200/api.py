@@ -433,6 +433,15 @@ class SearchContext:
         return out
 
     def last_stats(self):
-        ms, nl = C.c_double(), C.c_int64()
+        """(device ms of the last search, kernel launches, ms inside k_dist_boxes, its launches)."""
+        ms, nl, dm, dl = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
         check(lib().iq_last_search_stats(self._h, C.byref(ms), C.byref(nl)))
-        return ms.value, nl.value
+        check(lib().iq_last_search_kernel_ms(self._h, C.byref(dm), C.byref(dl)))
+        return ms.value, nl.value, dm.value, dl.value
+
+
+def fma_peak(device=0):
+    """Measured FP32 FMA rate of the device in TFMA/s (iq_bench_fma_peak)."""
+    out = C.c_double()
+    check(lib().iq_bench_fma_peak(int(device), C.byref(out)))
+    return out.value

@@ -184,6 +184,10 @@ struct iq_ctx {
 
   double last_ms = 0.0;
   int64_t last_launches = 0;
+  std::vector<cudaEvent_t> dist_ev;  // start/stop pairs around every k_dist_boxes launch of a search
+  size_t dist_ev_used = 0;
+  double last_dist_ms = 0.0;
+  int64_t last_dist_launches = 0;
   int64_t launches = 0;
 };
 
@@ -411,7 +415,17 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
   p.WX = e->WX;
   p.WY = e->WY;
   const size_t smem = iq::dist_boxes_smem(e->boxes.data(), p.nbox, p.WX, p.WY, rb, &p.pitch_max, &p.patch_floats);
+  if (c->dist_ev_used + 2 > c->dist_ev.size()) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    c->dist_ev.push_back(a);
+    c->dist_ev.push_back(b);
+  }
+  CK(cudaEventRecord(c->dist_ev[c->dist_ev_used], c->stream));
   CK(iq::launch_dist_boxes(p, rb, std::max<size_t>(smem, 64), c->stream));
+  CK(cudaEventRecord(c->dist_ev[c->dist_ev_used + 1], c->stream));
+  c->dist_ev_used += 2;
   c->launches++;
   return IQ_OK;
 }
@@ -723,6 +737,7 @@ int do_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int ntile
   if (rc) return rc;
   if ((int)c->res.size() < ntile) c->res.resize(ntile);
   const int64_t l0 = c->launches;
+  c->dist_ev_used = 0;
   CK(cudaEventRecord(c->ev0, c->stream));
   for (int base = 0; base < ntile; base += c->max_batch) {
     const int R = std::min(c->max_batch, ntile - base);
@@ -735,6 +750,13 @@ int do_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int ntile
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->last_ms = ms;
   c->last_launches = c->launches - l0;
+  c->last_dist_ms = 0.0;
+  c->last_dist_launches = (int64_t)(c->dist_ev_used / 2);
+  for (size_t i = 0; i + 1 < c->dist_ev_used; i += 2) {
+    float dm = 0.f;
+    CK(cudaEventElapsedTime(&dm, c->dist_ev[i], c->dist_ev[i + 1]));
+    c->last_dist_ms += dm;
+  }
   return IQ_OK;
 }
 
@@ -788,6 +810,7 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
     cudaFree(e->d_boxes);
     for (auto& kv : e->a2) cudaFree(kv.second);
   }
+  for (auto ev : c->dist_ev) cudaEventDestroy(ev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1017,6 +1040,47 @@ int32_t iq_last_search_stats(const iq_ctx* c, double* device_ms, int64_t* kernel
   if (!c) return fail(IQ_ERR_INVALID, "NULL context");
   if (device_ms) *device_ms = c->last_ms;
   if (kernel_launches) *kernel_launches = c->last_launches;
+  return IQ_OK;
+}
+
+int32_t iq_last_search_kernel_ms(const iq_ctx* c, double* dist_ms, int64_t* dist_launches) {
+  if (!c) return fail(IQ_ERR_INVALID, "NULL context");
+  if (dist_ms) *dist_ms = c->last_dist_ms;
+  if (dist_launches) *dist_launches = c->last_dist_launches;
+  return IQ_OK;
+}
+
+int32_t iq_bench_fma_peak(int32_t device, double* tfma) {
+  if (!tfma) return fail(IQ_ERR_INVALID, "NULL argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(IQ_ERR_NO_DEVICE, "no such CUDA device");
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  float* d = nullptr;
+  CK(cudaMalloc((void**)&d, 64));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(e0, 0));
+    CK(iq::launch_fma_peak(blocks, iters, d, 0));
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fma = (double)blocks * 256.0 * iters * 128.0;
+    if (rep > 0) best = std::max(best, fma / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tfma = best;
   return IQ_OK;
 }
 

@@ -98,5 +98,6 @@ cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStre
 cudaError_t launch_fetch_tile(const float* img, int nx, int ny, int nz, int tx, int ty, int tz,
                               long long x0, long long y0, long long z0, float* out, cudaStream_t s);
 int pick_nblk(long long npos);
+cudaError_t launch_fma_peak(int blocks, int iters, float* out, cudaStream_t s);
 
 }  // namespace iq

@@ -586,4 +586,27 @@ cudaError_t launch_fetch_tile(const float* img, int nx, int ny, int nz, int tx, 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP32 FMA peak microbenchmark: 16 independent register-operand FFMA chains per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fma_peak(int iters, float s, float t, float* out) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], s, t);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sum += a[i];
+  if (sum == 123.456f) out[0] = sum;  // never true in practice; keeps the chains alive
+}
+cudaError_t launch_fma_peak(int blocks, int iters, float* out, cudaStream_t s) {
+  k_fma_peak<<<blocks, 256, 0, s>>>(iters, 0.999f, 0.001f, out);
+  return cudaGetLastError();
+}
+
 }  // namespace iq

@@ -126,6 +126,14 @@ int32_t iq_fetch_tile(iq_ctx* ctx, int64_t pos, float* out_tile);
  * of kernels launched by the most recent iq_search* call. */
 int32_t iq_last_search_stats(const iq_ctx* ctx, double* device_ms, int64_t* kernel_launches);
 
+/* Device time (ms) spent inside the dense correlation kernel (k_dist_boxes) alone during the most recent
+ * iq_search* call, measured with CUDA events on the context's stream, and the number of its launches. */
+int32_t iq_last_search_kernel_ms(const iq_ctx* ctx, double* dist_ms, int64_t* dist_launches);
+
+/* FP32 FMA issue-rate microbenchmark on `device` (register-operand FFMA chains on every SM): writes the
+ * measured rate in TFMA/s (1 FMA = 2 flop).  This is the denominator of the kernel's FMA roofline. */
+int32_t iq_bench_fma_peak(int32_t device, double* tfma_per_s);
+
 /* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 1,2,4), "variant". */
 int32_t iq_ctx_set_option(iq_ctx* ctx, const char* key, int64_t value);
 

@@ -57,6 +57,9 @@ typedef struct iqh_stats {
   int64_t searches;            /* tile searches performed (nreal * npath) */
   int64_t kernel_launches;
   int64_t candidates;          /* sum of candidate-set sizes */
+  double setup_ms;             /* context creation: uploads + summed-volume tables */
+  double dist_kernel_ms;       /* device time inside the dense correlation kernel alone */
+  int64_t dist_launches;
 } iqh_stats;
 
 /* Runs the whole simulation.  `out_grids` receives nreal padded grids (pad_size doubles each,

@@ -615,7 +615,7 @@ def search_tile(TI, simdev, ovlmask, disabled, tol, hard=None, soft=None, method
 # --------------------------------------------------------------------------------------
 def iqsim(trainimg, tilesize, simsize=None, overlap=None, soft=(), hard=None, tol=0.1,
           path="raster", nreal=1, debug=False, rng=None, method="direct", workers=None,
-          cut_fn=None, trace=None):
+          cut_fn=None, trace=None, max_tiles=None):
     """Restatement of the whole driver.  `cut_fn(A, B, dim)` overrides the boundary cut
     (tests use it to isolate search parity); `trace` (a list) receives one dict per
     visited tile for parity tests."""
@@ -659,6 +659,7 @@ def iqsim(trainimg, tilesize, simsize=None, overlap=None, soft=(), hard=None, to
     is_float = np.issubdtype(np.asarray(trainimg_in).dtype, np.floating)
     realizations, boundarycuts, voxelreuse_out = [], [], []
 
+    nvisited_total = 0
     for real in range(nreal):
         simgrid = np.zeros(padsize, dtype=TI.dtype)  # :165
         cutgrid = np.zeros(padsize, dtype=np.float64) if debug else None
@@ -666,6 +667,9 @@ def iqsim(trainimg, tilesize, simsize=None, overlap=None, soft=(), hard=None, to
         for ind in simpath:
             if ind in skipped:
                 continue
+            if max_tiles is not None and nvisited_total >= max_tiles:
+                break  # bounded sample for benchmarks: stop after max_tiles visited tiles
+            nvisited_total += 1
             tileind = tuple(int(v) for v in np.unravel_index(ind, ntiles, order="F"))
             start = tuple(t * sp for t, sp in zip(tileind, spacing))
             tile = tuple(slice(s, s + t) for s, t in zip(start, tilesize))
