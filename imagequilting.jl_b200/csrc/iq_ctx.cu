@@ -137,6 +137,7 @@ struct iq_ctx {
   long long npos = 0, tilevol = 0, nenabled = 0;
   int nsoft = 0, max_batch = 1;
   int rb_opt = 0;  // 0 = auto
+  int variant = 0; // 0 = flat kernel (default), 1 = tiled kernel
 
   float* d_ti = nullptr;
   std::vector<float*> d_aux;
@@ -414,7 +415,25 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
   p.R = R;
   p.WX = e->WX;
   p.WY = e->WY;
-  const size_t smem = iq::dist_boxes_smem(e->boxes.data(), p.nbox, p.WX, p.WY, rb, &p.pitch_max, &p.patch_floats);
+  size_t smem = 0;
+  if (c->variant == 0) {
+    // flat variant: fewest column panels whose patch + templates still let two CTAs share an SM
+    const int nxt = (c->nxo + iq::kT - 1) / iq::kT;
+    int best_xt = 0;
+    for (int pass = 0; pass < 2 && !best_xt; ++pass) {
+      const size_t limit = pass == 0 ? 110 * 1024 : 220 * 1024;
+      for (int np = 1; np <= nxt; ++np) {
+        const int xt = (nxt + np - 1) / np;
+        if (xt > 256) continue;
+        if (iq::dist_flat_smem(e->boxes.data(), p.nbox, xt, rb, nullptr) <= limit) { best_xt = xt; break; }
+      }
+    }
+    if (!best_xt) return fail(IQ_ERR_INVALID, "tile too large for the shared-memory staging of the flat kernel");
+    p.XT = best_xt;
+    smem = iq::dist_flat_smem(e->boxes.data(), p.nbox, p.XT, rb, &p.patch_floats);
+  } else {
+    smem = iq::dist_boxes_smem(e->boxes.data(), p.nbox, p.WX, p.WY, rb, &p.pitch_max, &p.patch_floats);
+  }
   if (c->dist_ev_used + 2 > c->dist_ev.size()) {
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
@@ -423,7 +442,8 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
     c->dist_ev.push_back(b);
   }
   CK(cudaEventRecord(c->dist_ev[c->dist_ev_used], c->stream));
-  CK(iq::launch_dist_boxes(p, rb, std::max<size_t>(smem, 64), c->stream));
+  if (c->variant == 0) CK(iq::launch_dist_flat(p, rb, std::max<size_t>(smem, 64), c->stream));
+  else CK(iq::launch_dist_boxes(p, rb, std::max<size_t>(smem, 64), c->stream));
   CK(cudaEventRecord(c->dist_ev[c->dist_ev_used + 1], c->stream));
   c->dist_ev_used += 2;
   c->launches++;
@@ -1089,6 +1109,11 @@ int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
   if (std::strcmp(key, "rb") == 0) {
     if (value != 0 && value != 1 && value != 2 && value != 4) return fail(IQ_ERR_INVALID, "rb must be 0 (auto), 1, 2 or 4");
     c->rb_opt = (int)value;
+    return IQ_OK;
+  }
+  if (std::strcmp(key, "variant") == 0) {
+    if (value != 0 && value != 1) return fail(IQ_ERR_INVALID, "variant must be 0 (flat) or 1 (tiled)");
+    c->variant = (int)value;
     return IQ_OK;
   }
   return fail(IQ_ERR_INVALID, "unknown option '%s'", key);

@@ -38,6 +38,7 @@ struct DistParams {
   int WX, WY;                  // warps per CTA along x / y
   int pitch_max;               // smem patch pitch upper bound (floats)
   int patch_floats;            // smem floats reserved for the image patch
+  int XT;                      // flat variant: x-threads (8 outputs each) per panel row
 };
 
 struct SparseParams {
@@ -85,6 +86,8 @@ struct PickJob {
 
 // ---- launch wrappers (iq_kernels.cu) -------------------------------------------------
 cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
+cudaError_t launch_dist_flat(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
+size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats);
 size_t dist_boxes_smem(const BoxDesc* boxes, int nbox, int WX, int WY, int rb, int* pitch_max, int* patch_floats);
 cudaError_t launch_dist_sparse(const SparseParams& p, cudaStream_t s);
 cudaError_t launch_sat_build(const float* img, double* sat, int nx, int ny, int nz, cudaStream_t s);

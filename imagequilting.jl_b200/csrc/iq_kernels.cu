@@ -240,6 +240,192 @@ cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem, cudaStre
 }
 
 // ------------------------------------------------------------------------------------------------
+// dense box correlation, flat variant (default)
+// ------------------------------------------------------------------------------------------------
+// Same arithmetic as k_dist_boxes, different decomposition: the distance map of one z plane is cut in
+// column panels of XT x-threads (8 outputs each); inside a panel the (x-thread, row) work items are
+// numbered row-major and every CTA takes 256 consecutive items -- always 8 full warps (2 per SMSP), no
+// idle lanes and no padding beyond the 8-output granularity, whatever the image width.  A quarter warp
+// then reads 8 chunks of one patch row at a 32-byte stride; the patch is stored with the two 16-byte
+// halves of every 8-float chunk swapped in odd 128-byte groups (unit' = unit ^ ((unit >> 3) & 1)), which
+// makes those LDS.128 conflict-free.
+constexpr int kFlatThreads = 256;
+
+__device__ __forceinline__ void ld8sw(float (&v)[8], const float* rowp, int ci) {
+  const float* a = rowp + ci * 8;
+  const int sw = ((ci >> 2) & 1) << 2;
+  const float4 lo = *reinterpret_cast<const float4*>(a + sw);
+  const float4 hi = *reinterpret_cast<const float4*>(a + (sw ^ 4));
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+  v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
+template <int RB>
+__global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat(const DistParams P) {
+  extern __shared__ __align__(16) float smem[];
+  float* patch = smem;
+  float* tmplS = smem + P.patch_floats;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int XT = P.XT;
+  const int X0 = blockIdx.x * XT * kT;
+  const int nitem = XT * P.nyo;
+  const int i0 = blockIdx.y * kFlatThreads;
+  const int item = min(i0 + tid, nitem - 1);  // clamped threads recompute the last item; they never store
+  const bool valid = (i0 + tid) < nitem;
+  const int row = item / XT, xt = item - row * XT;
+  const int rlo = i0 / XT;
+  const int rhi = min(i0 + kFlatThreads - 1, nitem - 1) / XT;
+  const int PHO = rhi - rlo + 1;
+  const int pz = blockIdx.z % P.nzo, grp = blockIdx.z / P.nzo;
+
+  float tot[RB][8];
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) tot[r][t] = 0.f;
+
+  for (int b = 0; b < P.nbox; ++b) {
+    const BoxDesc bx = P.boxes[b];
+    const int PW = (XT + bx.nch) * 8;
+    const int pitch = PW + 4;
+    const int PH = PHO + bx.h - 1;
+    const int plane_floats = bx.h * bx.nch * 8 * RB;
+    const float* tsrc = P.tmpl + (long long)grp * P.tmpl_grp_stride + (long long)bx.tmpl_off * RB;
+
+    for (int qz = 0; qz < bx.d; ++qz) {
+      __syncthreads();
+      const int gz = pz + bx.z0 + qz;
+      const float* src = P.img + (long long)gz * P.nx * P.ny;
+      for (int prow = warp; prow < PH; prow += kFlatThreads / 32) {
+        const int gy = rlo + bx.y0 + prow;
+        const bool rowok = gy < P.ny;
+        const float* srow = src + (long long)gy * P.nx;
+        float* drow = patch + prow * pitch;
+        for (int col = lane; col < PW; col += 32) {
+          const int gx = X0 + bx.x0 + col;
+          const int pcol = col ^ ((((col >> 5) & 1)) << 2);  // swap the chunk halves in odd 32-float groups
+          drow[pcol] = (rowok && gx < P.nx) ? __ldg(srow + gx) : 0.f;
+        }
+      }
+      {
+        const float4* t4 = reinterpret_cast<const float4*>(tsrc + (long long)qz * plane_floats);
+        float4* d4 = reinterpret_cast<float4*>(tmplS);
+        for (int i = tid; i < plane_floats / 4; i += kFlatThreads) d4[i] = __ldg(t4 + i);
+      }
+      __syncthreads();
+
+      float acc[RB][8];
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[r][t] = 0.f;
+
+      const float* rowp = patch + (row - rlo) * pitch;
+      const float* kp = tmplS;
+      for (int qy = 0; qy < bx.h; ++qy) {
+        float A[8], B[8];
+        int ci = xt;
+        ld8sw(A, rowp, ci);
+        for (int c = 0; c < bx.nch; c += 2) {
+          ld8sw(B, rowp, ++ci);
+          fma_chunk<RB>(acc, A, B, kp);
+          kp += RB * 8;
+          if (c + 1 < bx.nch) {
+            ld8sw(A, rowp, ++ci);
+            fma_chunk<RB>(acc, B, A, kp);
+            kp += RB * 8;
+          }
+        }
+        rowp += pitch;
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) tot[r][t] += acc[r][t];
+    }
+  }
+
+  __shared__ unsigned s_min[4], s_max[4];
+  if (tid < 4) { s_min[tid] = 0x7f800000u; s_max[tid] = 0u; }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int tile = grp * RB + r;
+    unsigned vmin = 0x7f800000u, vmax = 0u;
+    if (tile < P.R && valid) {
+      const double b2 = P.b2[tile];
+      float* orow = P.out + (long long)tile * P.npos;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int x = X0 + xt * kT + t;
+        if (x < P.nxo) {
+          const long long p = ((long long)pz * P.nyo + row) * P.nxo + x;
+          const double a2 = P.a2 ? (double)__ldg(P.a2 + p) : 0.0;
+          float d = (float)fabs(a2 - 2.0 * (double)tot[r][t] + b2);
+          const bool dis = P.disabled && P.disabled[p];
+          if (dis) d = CUDART_INF_F;
+          orow[p] = d;
+          if (!dis) {
+            const unsigned u = __float_as_uint(d);
+            vmin = min(vmin, u);
+            vmax = max(vmax, u);
+          }
+        }
+      }
+    }
+    if (P.minbits) {
+      vmin = warp_min_u(vmin);
+      vmax = warp_max_u(vmax);
+      if (lane == 0 && tile < P.R) {
+        atomicMin(&s_min[r], vmin);
+        atomicMax(&s_max[r], vmax);
+      }
+    }
+  }
+  if (P.minbits) {
+    __syncthreads();
+    if (tid < RB && grp * RB + tid < P.R) {
+      atomicMin(P.minbits + grp * RB + tid, s_min[tid]);
+      atomicMax(P.maxbits + grp * RB + tid, s_max[tid]);
+    }
+  }
+}
+
+size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats) {
+  int pf = 0, tf = 0;
+  const int pho = (kFlatThreads + XT - 1) / XT + 1;
+  for (int b = 0; b < nbox; ++b) {
+    const int pitch = (XT + boxes[b].nch) * 8 + 4;
+    pf = max(pf, (pho + boxes[b].h - 1) * pitch);
+    tf = max(tf, boxes[b].h * boxes[b].nch * 8 * rb);
+  }
+  pf = (pf + 3) & ~3;
+  if (patch_floats) *patch_floats = pf;
+  return (size_t)(pf + tf) * sizeof(float);
+}
+
+template <int RB>
+static cudaError_t launch_dist_flat_t(const DistParams& p, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(k_dist_flat<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int ngrp = (p.R + RB - 1) / RB;
+  const int nxt = (p.nxo + kT - 1) / kT;
+  dim3 grid((nxt + p.XT - 1) / p.XT, (p.XT * p.nyo + kFlatThreads - 1) / kFlatThreads, p.nzo * ngrp);
+  k_dist_flat<RB><<<grid, kFlatThreads, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dist_flat(const DistParams& p, int rb, size_t smem, cudaStream_t s) {
+  switch (rb) {
+    case 1: return launch_dist_flat_t<1>(p, smem, s);
+    case 2: return launch_dist_flat_t<2>(p, smem, s);
+    case 4: return launch_dist_flat_t<4>(p, smem, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // sparse (hard data) distance: D[p] = sum_i (img[p + off_i] - v_i)^2
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dist_sparse(const SparseParams P) {

@@ -48,6 +48,8 @@ def make_ti(kind, shape, seed):
 
 
 CASES = [
+    ("gauss", (300, 40), (16, 12), (4, 3)),   # wide image: several column panels in the flat kernel
+    ("cat", (19, 23, 6), (4, 5, 2), (2, 2, 1)),
     ("cat", (40, 37), (12, 10), (3, 2)),
     ("gauss", (90, 70), (30, 30), (5, 5)),
     ("cat", (30, 28, 12), (10, 9, 4), (2, 3, 2)),
@@ -56,14 +58,16 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("kind,shape,tile,ovl", CASES)
-def test_overlap_distance_all_mask_shapes(kind, shape, tile, ovl):
+def test_overlap_distance_all_mask_shapes(kind, shape, tile, ovl, variant):
     ti = make_ti(kind, shape, 1)
     r = np.random.default_rng(2)
     N = len(shape)
     disabled = np.zeros(tuple(a - b + 1 for a, b in zip(shape, tile)), dtype=bool)
     disabled[tuple(r.integers(0, s, 5) for s in disabled.shape)] = True
     with api.SearchContext(ti, tile, disabled=disabled) as ctx:
+        ctx.set_option("variant", variant)  # 0 = flat kernel (default), 1 = tiled kernel
         combos = list(itertools.product([0, 1], repeat=2 * N))
         for bits in combos[1:: max(1, len(combos) // 12)] + [combos[-1]]:
             m = slab_mask(tile, ovl, bits[:N], bits[N:])
