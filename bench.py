@@ -259,7 +259,7 @@ def main():
         "gpu_launches": int(sum(s["stats"]["kernel_launches"] for s in stats)),
         "roofline": {"bound": "fp32_fma", "achieved": 2 * achieved_tfma, "peak": 2 * fma_peak, "unit": "TFLOP/s",
                      "frac": achieved_tfma / fma_peak if fma_peak else None, "traffic": None,
-                     "kernel": "k_dist_boxes", "launches": int(dist_launches), "kernel_ms_total": dist_ms,
+                     "kernel": "k_dist_flat", "launches": int(dist_launches), "kernel_ms_total": dist_ms,
                      "peak_source": "iq_bench_fma_peak measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                      "hbm_term": {"achieved_gbs": achieved_gbs, "peak_gbs": peaks.get("hbm_gbs"), "of": peak_kind,
                                   "frac": achieved_gbs / peaks.get("hbm_gbs", 1.0)}},

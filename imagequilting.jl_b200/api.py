@@ -440,8 +440,9 @@ class SearchContext:
         return ms.value, nl.value, dm.value, dl.value
 
 
-def fma_peak(device=0):
-    """Measured FP32 FMA rate of the device in TFMA/s (iq_bench_fma_peak)."""
+def fma_peak(device=0, packed=False):
+    """Measured FP32 FMA rate of the device in TFMA/s (iq_bench_fma_peak / iq_bench_fma2_peak)."""
     out = C.c_double()
-    check(lib().iq_bench_fma_peak(int(device), C.byref(out)))
+    fn = lib().iq_bench_fma2_peak if packed else lib().iq_bench_fma_peak
+    check(fn(int(device), C.byref(out)))
     return out.value

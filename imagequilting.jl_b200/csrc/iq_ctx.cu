@@ -137,7 +137,7 @@ struct iq_ctx {
   long long npos = 0, tilevol = 0, nenabled = 0;
   int nsoft = 0, max_batch = 1;
   int rb_opt = 0;  // 0 = auto
-  int variant = 0; // 0 = flat kernel (default), 1 = tiled kernel
+  int variant = 0; // 0 = flat kernel (default), 1 = tiled kernel, 2 = flat kernel with packed FMAs (experimental: slower)
 
   float* d_ti = nullptr;
   std::vector<float*> d_aux;
@@ -358,7 +358,10 @@ int pick_rb(const iq_ctx* c, int R) {
 
 // Pack R templates (tile-sized arrays `kern[r]`, masked by e->mask) into the kernel layout
 // [grp][box][qz][qy][chunk][r(RB)][8] at staging offset; also B2[r] = sum(mask * kern^2) in FP64.
-void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* kern, int R, int rb, float* dst, double* b2) {
+// tap_major = false: [grp][box][qz][qy][chunk][tile][8 taps]   (scalar kernels)
+// tap_major = true : [grp][box][qz][qy][chunk][8 taps][tile]   (packed FFMA2 kernel)
+void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* kern, int R, int rb, bool tap_major, float* dst,
+                    double* b2) {
   const int ngrp = (R + rb - 1) / rb;
   const long long gstride = e->tmpl_floats * rb;
   std::memset(dst, 0, (size_t)ngrp * gstride * sizeof(float));
@@ -372,10 +375,11 @@ void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* ker
       for (int qz = 0; qz < b.d; ++qz)
         for (int qy = 0; qy < b.h; ++qy) {
           const long long trow = ((long long)(b.z0 + qz) * c->ty + (b.y0 + qy)) * c->tx + b.x0;
-          float* drow = base + ((long long)qz * b.h + qy) * b.nch * 8 * rb + ri * 8;
+          float* drow = base + ((long long)qz * b.h + qy) * b.nch * 8 * rb;
           for (int x = 0; x < b.w; ++x) {
             const float v = m[trow + x] ? k[trow + x] : 0.f;
-            drow[(x >> 3) * 8 * rb + (x & 7)] = v;
+            if (tap_major) drow[(x >> 3) * 8 * rb + (x & 7) * rb + ri] = v;
+            else drow[(x >> 3) * 8 * rb + ri * 8 + (x & 7)] = v;
             s += (double)v * (double)v;
           }
         }
@@ -391,7 +395,8 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
   const size_t off_t = stage_alloc(c, std::max<size_t>(tbytes, 16));
   const size_t off_b = stage_alloc(c, (size_t)R * sizeof(double));
   if (c->stage_used > c->stage_cap) return fail(IQ_ERR_STATE, "staging overflow (internal)");
-  pack_templates(c, e, kern, R, rb, (float*)(c->h_stage + off_t), (double*)(c->h_stage + off_b));
+  const bool packed = (c->variant == 2 && rb >= 2);  // experimental FFMA2 kernel
+  pack_templates(c, e, kern, R, rb, packed, (float*)(c->h_stage + off_t), (double*)(c->h_stage + off_b));
   CK(cudaMemcpyAsync(c->d_stage + off_t, c->h_stage + off_t, (off_b + R * sizeof(double)) - off_t, cudaMemcpyHostToDevice,
                      c->stream));
   const float* a2 = nullptr;
@@ -416,8 +421,8 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
   p.WX = e->WX;
   p.WY = e->WY;
   size_t smem = 0;
-  if (c->variant == 0) {
-    // flat variant: fewest column panels whose patch + templates still let two CTAs share an SM
+  if (c->variant != 1) {
+    // flat variants: fewest column panels whose patch + templates still let two CTAs share an SM
     const int nxt = (c->nxo + iq::kT - 1) / iq::kT;
     int best_xt = 0;
     for (int pass = 0; pass < 2 && !best_xt; ++pass) {
@@ -442,7 +447,8 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
     c->dist_ev.push_back(b);
   }
   CK(cudaEventRecord(c->dist_ev[c->dist_ev_used], c->stream));
-  if (c->variant == 0) CK(iq::launch_dist_flat(p, rb, std::max<size_t>(smem, 64), c->stream));
+  if (packed) CK(iq::launch_dist_flat2(p, rb, std::max<size_t>(smem, 64), c->stream));
+  else if (c->variant != 1) CK(iq::launch_dist_flat(p, rb, std::max<size_t>(smem, 64), c->stream));
   else CK(iq::launch_dist_boxes(p, rb, std::max<size_t>(smem, 64), c->stream));
   CK(cudaEventRecord(c->dist_ev[c->dist_ev_used + 1], c->stream));
   c->dist_ev_used += 2;
@@ -1070,7 +1076,10 @@ int32_t iq_last_search_kernel_ms(const iq_ctx* c, double* dist_ms, int64_t* dist
   return IQ_OK;
 }
 
-int32_t iq_bench_fma_peak(int32_t device, double* tfma) {
+static int32_t bench_fma_impl(int32_t device, int packed, double* tfma);
+int32_t iq_bench_fma_peak(int32_t device, double* tfma) { return bench_fma_impl(device, 0, tfma); }
+int32_t iq_bench_fma2_peak(int32_t device, double* tfma) { return bench_fma_impl(device, 1, tfma); }
+static int32_t bench_fma_impl(int32_t device, int packed, double* tfma) {
   if (!tfma) return fail(IQ_ERR_INVALID, "NULL argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -1089,7 +1098,7 @@ int32_t iq_bench_fma_peak(int32_t device, double* tfma) {
   double best = 0.0;
   for (int rep = 0; rep < 6; ++rep) {
     CK(cudaEventRecord(e0, 0));
-    CK(iq::launch_fma_peak(blocks, iters, d, 0));
+    CK(iq::launch_fma_peak(blocks, packed ? -iters : iters, d, 0));
     CK(cudaEventRecord(e1, 0));
     CK(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -1112,7 +1121,7 @@ int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
     return IQ_OK;
   }
   if (std::strcmp(key, "variant") == 0) {
-    if (value != 0 && value != 1) return fail(IQ_ERR_INVALID, "variant must be 0 (flat) or 1 (tiled)");
+    if (value < 0 || value > 2) return fail(IQ_ERR_INVALID, "variant must be 0 (flat), 1 (tiled) or 2 (flat with packed f32x2 FMAs, experimental)");
     c->variant = (int)value;
     return IQ_OK;
   }

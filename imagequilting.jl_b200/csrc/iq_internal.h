@@ -87,6 +87,7 @@ struct PickJob {
 // ---- launch wrappers (iq_kernels.cu) -------------------------------------------------
 cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
 cudaError_t launch_dist_flat(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
+cudaError_t launch_dist_flat2(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
 size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats);
 size_t dist_boxes_smem(const BoxDesc* boxes, int nbox, int WX, int WY, int rb, int* pitch_max, int* patch_floats);
 cudaError_t launch_dist_sparse(const SparseParams& p, cudaStream_t s);

@@ -133,6 +133,8 @@ int32_t iq_last_search_kernel_ms(const iq_ctx* ctx, double* dist_ms, int64_t* di
 /* FP32 FMA issue-rate microbenchmark on `device` (register-operand FFMA chains on every SM): writes the
  * measured rate in TFMA/s (1 FMA = 2 flop).  This is the denominator of the kernel's FMA roofline. */
 int32_t iq_bench_fma_peak(int32_t device, double* tfma_per_s);
+/* Same with the packed fma.rn.f32x2 instruction (two FMAs per issue slot on sm_100). */
+int32_t iq_bench_fma2_peak(int32_t device, double* tfma_per_s);
 
 /* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 1,2,4), "variant". */
 int32_t iq_ctx_set_option(iq_ctx* ctx, const char* key, int64_t value);

@@ -58,7 +58,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("kind,shape,tile,ovl", CASES)
 def test_overlap_distance_all_mask_shapes(kind, shape, tile, ovl, variant):
     ti = make_ti(kind, shape, 1)
@@ -67,7 +67,7 @@ def test_overlap_distance_all_mask_shapes(kind, shape, tile, ovl, variant):
     disabled = np.zeros(tuple(a - b + 1 for a, b in zip(shape, tile)), dtype=bool)
     disabled[tuple(r.integers(0, s, 5) for s in disabled.shape)] = True
     with api.SearchContext(ti, tile, disabled=disabled) as ctx:
-        ctx.set_option("variant", variant)  # 0 = flat kernel (default), 1 = tiled kernel
+        ctx.set_option("variant", variant)  # 0 = flat (default), 1 = tiled, 2 = flat with packed f32x2 FMAs
         combos = list(itertools.product([0, 1], repeat=2 * N))
         for bits in combos[1:: max(1, len(combos) // 12)] + [combos[-1]]:
             m = slab_mask(tile, ovl, bits[:N], bits[N:])
