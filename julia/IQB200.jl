@@ -1,0 +1,108 @@
+# IQB200.jl -- thin Julia binding of libiqb200.so (C ABI: include/iqb200.h).
+#
+# UNTESTED: Julia is not available in the environment this repository was built in.  The file is the
+# binding a maintainer of ImageQuilting.jl would add; INTEGRATION.md shows where it plugs into
+# src/iqsim.jl.  Struct layouts mirror include/iqb200.h field by field.
+module IQB200
+
+const lib = get(ENV, "IQB200_LIB", joinpath(@__DIR__, "..", "imagequilting.jl_b200", "libiqb200.so"))
+
+struct CtxDesc
+  ndim::Int32
+  ti_size::NTuple{3,Int64}
+  tile_size::NTuple{3,Int64}
+  ti::Ptr{Float32}
+  disabled::Ptr{UInt8}
+  nsoft::Int32
+  auxti::Ptr{Ptr{Float32}}
+  device::Int32
+  max_batch::Int32
+end
+
+struct Tile
+  simdev::Ptr{Float32}
+  hard_nnz::Int32
+  hard_offset::Ptr{Int32}
+  hard_value::Ptr{Float32}
+  softdev::Ptr{Ptr{Float32}}
+end
+
+struct Result
+  count::Int64
+  idx::Ptr{Int64}
+  prob::Ptr{Float64}
+  picked::Int64
+  relax_iters::Int32
+  dmin::Float32
+end
+
+lasterror() = unsafe_string(ccall((:iq_last_error, lib), Cstring, ()))
+check(rc) = rc == 0 || error("libiqb200: ", lasterror())
+
+pad3(t::Dims{N}) where {N} = ntuple(i -> i <= N ? Int64(t[i]) : Int64(1), 3)
+
+mutable struct Context
+  handle::Ptr{Cvoid}
+  keep::Vector{Any}   # arrays the library reads during create
+end
+
+"""
+    Context(TI, tilesize; disabled=nothing, auxTIs=[], device=0, max_batch=1)
+
+Uploads the (NaN-free) training image and auxiliary images once; replaces `array_kernel`
+(src/utils.jl:57-61) and the `geoconfig` tuple (src/iqsim.jl:118-127).
+"""
+function Context(TI::AbstractArray{<:Real,N}, tilesize::Dims{N}; disabled=nothing, auxTIs=[], device=0, max_batch=1) where {N}
+  ti = Array{Float32}(TI)
+  aux = [Array{Float32}(a) for a in auxTIs]
+  auxptr = [pointer(a) for a in aux]
+  dis = disabled === nothing ? UInt8[] : Array{UInt8}(vec(disabled))
+  out = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve ti aux auxptr dis begin
+    desc = CtxDesc(N, pad3(size(TI)), pad3(tilesize), pointer(ti),
+                   isempty(dis) ? Ptr{UInt8}(C_NULL) : pointer(dis), length(aux),
+                   isempty(aux) ? Ptr{Ptr{Float32}}(C_NULL) : pointer(auxptr), device, max_batch)
+    check(ccall((:iq_ctx_create, lib), Int32, (Ref{Ptr{Cvoid}}, Ref{CtxDesc}), out, desc))
+  end
+  ctx = Context(out[], Any[])
+  finalizer(c -> ccall((:iq_ctx_destroy, lib), Int32, (Ptr{Cvoid},), c.handle), ctx)
+  ctx
+end
+
+"""
+    search(ctx, ovlmask, simdevs; hard=nothing, softdevs=nothing, tol=0.1)
+
+One call per path step for a batch of tiles sharing `ovlmask`.  Returns, per tile, `(patterndb, probs)`
+with 1-based linear indices into the distance map -- exactly what src/iqsim.jl:237-240 produces, ready
+for `sample(rng, patterndb, weights(probs))` (src/iqsim.jl:243), which stays in Julia.
+`hard` is `(offsets::Vector{Int32} (0-based, column-major inside the tile), values::Vector{Float32})` or
+`nothing`; `softdevs[i]` is the vector of tile-sized soft events of tile i.
+"""
+function search(ctx::Context, ovlmask::AbstractArray{Bool}, simdevs::Vector; hard=nothing, softdevs=nothing, tol=0.1)
+  n = length(simdevs)
+  mask = Array{UInt8}(vec(ovlmask))
+  devs = [Array{Float32}(vec(s)) for s in simdevs]
+  softs = softdevs === nothing ? nothing : [[Array{Float32}(vec(a)) for a in sd] for sd in softdevs]
+  softptrs = softs === nothing ? nothing : [[pointer(a) for a in sd] for sd in softs]
+  hoff, hval = hard === nothing ? (Int32[], Float32[]) : (Vector{Int32}(hard[1]), Vector{Float32}(hard[2]))
+  tiles = Vector{Tile}(undef, n)
+  results = Vector{Result}(undef, n)
+  out = Vector{Tuple{Vector{Int},Vector{Float64}}}(undef, n)
+  GC.@preserve mask devs softs softptrs hoff hval tiles results begin
+    for i in 1:n
+      tiles[i] = Tile(pointer(devs[i]), length(hoff), isempty(hoff) ? Ptr{Int32}(C_NULL) : pointer(hoff),
+                      isempty(hval) ? Ptr{Float32}(C_NULL) : pointer(hval),
+                      softptrs === nothing ? Ptr{Ptr{Float32}}(C_NULL) : pointer(softptrs[i]))
+    end
+    check(ccall((:iq_search, lib), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Tile}, Int32, Float64, Ptr{Result}),
+                ctx.handle, mask, tiles, n, tol, results))
+    for i in 1:n
+      r = results[i]
+      idx = unsafe_wrap(Array, r.idx, r.count) .+ 1          # copy: buffers belong to the context
+      out[i] = (Vector{Int}(idx), copy(unsafe_wrap(Array, r.prob, r.count)))
+    end
+  end
+  out
+end
+
+end # module
