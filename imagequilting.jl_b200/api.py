@@ -151,7 +151,7 @@ def _genpath(rng, extent, kind, datainds):
 # --------------------------------------------------------------------------------------
 def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None, tol=0.1, path="raster", nreal=1,
           debug=False, showprogress=False, rng=None, device=0, batch=0, nthreads=0, return_stats=False,
-          return_picks=False, _path_override=None, _uniforms=None):
+          return_picks=False, _path_override=None, _uniforms=None, _real_range=None):
     """Image quilting simulation with the GPU distance search (see module docstring)."""
     timg = trainimg if isinstance(trainimg, np.ma.MaskedArray) else np.asarray(trainimg)
     N = timg.ndim
@@ -234,6 +234,10 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
         u = rng.random(nreal * nvis).reshape(nreal, nvis) if nvis else np.zeros((nreal, 0))
     else:
         u = np.asarray(_uniforms, dtype=np.float64).reshape(nreal, nvis)
+    if _real_range is not None:  # realization sharding: this caller simulates rows r0:r1 of the shared stream
+        r0, r1 = _real_range
+        u = u[r0:r1]
+        nreal = r1 - r0
     u = np.ascontiguousarray(u, dtype=np.float64)
 
     padvol = int(np.prod(padsize, dtype=np.int64))

@@ -277,3 +277,13 @@ def test_iqsim_continuous_matches_oracle_picks():
     vals = set(np.unique(cfg["trainimg"]).tolist())
     for g in got:
         assert set(np.unique(g).tolist()) <= vals
+
+
+def test_realization_range_equals_slice_of_full_run():
+    """Sharding contract (sharding.py): rows r0:r1 of the shared uniform stream reproduce realizations r0:r1."""
+    cfg = synth.config(1)
+    full = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=5, rng=np.random.default_rng(3), path="random")
+    part = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=5, rng=np.random.default_rng(3), path="random", _real_range=(1, 4))
+    assert len(part) == 3
+    for a, b in zip(part, full[1:4]):
+        assert np.array_equal(a, b)
