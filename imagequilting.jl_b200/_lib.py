@@ -69,6 +69,7 @@ SYMBOLS = {
     "iq_distance": (C.c_int32, [C.c_void_p, C.c_int32, c_u8_p, C.POINTER(IqTile), c_float_p]),
     "iq_fetch_tile": (C.c_int32, [C.c_void_p, C.c_int64, c_float_p]),
     "iq_last_search_stats": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
+    "iq_last_search_path": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p, c_double_p]),
     "iq_last_search_kernel_ms": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
     "iq_bench_fma_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "iq_bench_fma2_peak": (C.c_int32, [C.c_int32, c_double_p]),

@@ -18,6 +18,7 @@
 
 #include "../../include/iqb200.h"
 #include "iq_internal.h"
+#include "iq_fft.h"
 
 namespace {
 
@@ -137,6 +138,12 @@ struct iq_ctx {
   long long npos = 0, tilevol = 0, nenabled = 0;
   int nsoft = 0, max_batch = 1;
   int rb_opt = 0;  // 0 = auto
+  int fft_mode = 0;   // 0 = auto (estimated crossover), 1 = always FFT for non-empty masks, -1 = never
+  iqfft::Plan* fft = nullptr;
+  bool fft_failed = false;
+  std::map<int, bool> image_is_int;  // image id -> every voxel is integer-valued (exact rounding of AB)
+  double last_fft_bytes = 0.0;
+  int64_t last_fft_searches = 0, last_direct_searches = 0;
   int variant = 0; // 0 = flat kernel (default), 1 = tiled kernel, 2 = flat kernel with packed FMAs (experimental: slower)
 
   float* d_ti = nullptr;
@@ -388,7 +395,93 @@ void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* ker
   }
 }
 
+bool all_integer(const float* v, long long n) {
+  for (long long i = 0; i < n; ++i)
+    if (v[i] != std::nearbyint(v[i]) || std::fabs(v[i]) > 4096.f) return false;
+  return true;
+}
+
+// Estimated cost model for the direct / FFT choice (seconds); constants measured on B200.
+bool want_fft(const iq_ctx* c, const MaskEntry* e, int R) {
+  if (c->fft_mode < 0 || c->fft_failed || e->nnz == 0) return false;
+  if (c->ny < 2 || c->nx < 2) return false;
+  if (c->fft_mode > 0) return true;
+  const double direct = (double)e->nnz * (double)c->npos * R / (0.62 * 36.2e12) + 6e-6;
+  auto p2 = [](int n) { double v = 1; while (v < n) v *= 2; return v; };
+  const double vol = p2(c->nx) * p2(c->ny) * (c->nz > 1 ? p2(c->nz) : 1.0);
+  const double pairs = (R + 1) / 2;
+  const double fft = pairs * vol * 8.0 * 5.0 / 2.2e12 + 30e-6;  // ~5 volume sweeps per pair at ~2.2 TB/s
+  return fft < direct;
+}
+
+int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R, float* d_out, int kind) {
+  if (!c->fft) {
+    cudaError_t ce = iqfft::plan_create(&c->fft, c->nx, c->ny, c->nz, c->tx, c->ty, c->tz, c->max_batch, c->stream);
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      c->fft_failed = true;
+      return IQ_ERR_STATE;  // caller falls back to the direct kernel (still on the GPU)
+    }
+  }
+  const float* d_img = image < 0 ? c->d_ti : c->d_aux[image];
+  CK(iqfft::plan_set_image(c->fft, image, d_img, c->stream));
+  const size_t tbytes = (size_t)R * c->tilevol * sizeof(float);
+  const size_t off_t = stage_alloc(c, tbytes);
+  const size_t off_b = stage_alloc(c, (size_t)R * sizeof(double));
+  if (c->stage_used > c->stage_cap) return fail(IQ_ERR_STATE, "staging overflow (internal)");
+  float* wk = (float*)(c->h_stage + off_t);
+  double* b2 = (double*)(c->h_stage + off_b);
+  const uint8_t* m = e->mask.data();
+  bool tint = c->image_is_int[image];
+  for (int r = 0; r < R; ++r) {
+    double sum = 0.0;
+    float* dst = wk + (size_t)r * c->tilevol;
+    const float* k = kern[r];
+    for (long long i = 0; i < c->tilevol; ++i) {
+      const float v = m[i] ? k[i] : 0.f;
+      dst[i] = v;
+      sum += (double)v * (double)v;
+    }
+    b2[r] = sum;
+    if (tint) tint = all_integer(dst, c->tilevol);
+  }
+  CK(cudaMemcpyAsync(c->d_stage + off_t, c->h_stage + off_t, (off_b + R * sizeof(double)) - off_t, cudaMemcpyHostToDevice,
+                     c->stream));
+  const float* a2 = nullptr;
+  int rc = get_a2(c, e, image, &a2);
+  if (rc) return rc;
+  iqfft::Epilogue ep{};
+  ep.a2 = a2;
+  ep.b2 = (const double*)(c->d_stage + off_b);
+  ep.disabled = c->d_disabled;
+  ep.out = d_out;
+  ep.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch;
+  ep.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch;
+  ep.round_to_int = tint ? 1 : 0;
+  if (c->dist_ev_used + 2 > c->dist_ev.size()) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    c->dist_ev.push_back(a);
+    c->dist_ev.push_back(b);
+  }
+  int nl = 0;
+  CK(cudaEventRecord(c->dist_ev[c->dist_ev_used], c->stream));
+  CK(iqfft::correlate(c->fft, image, (const float*)(c->d_stage + off_t), R, ep, c->stream, &nl));
+  CK(cudaEventRecord(c->dist_ev[c->dist_ev_used + 1], c->stream));
+  c->dist_ev_used += 2;
+  c->launches += nl;
+  c->last_fft_bytes += iqfft::correlate_bytes(c->fft, R);
+  c->last_fft_searches += R;
+  return IQ_OK;
+}
+
 int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R, float* d_out, int kind) {
+  if (want_fft(c, e, R)) {
+    const int rcf = run_fft(c, e, image, kern, R, d_out, kind);
+    if (!(rcf == IQ_ERR_STATE && c->fft_failed)) return rcf;
+  }
+  c->last_direct_searches += R;
   const int rb = pick_rb(c, R);
   const int ngrp = (R + rb - 1) / rb;
   const size_t tbytes = (size_t)ngrp * e->tmpl_floats * rb * sizeof(float);
@@ -515,6 +608,7 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
   const int rb = pick_rb(c, R);
   const int ngrp = (R + rb - 1) / rb;
   size_t need = 4096 + (size_t)ngrp * rb * e->tmpl_floats * sizeof(float) + R * sizeof(double) + 512;
+  need += (size_t)(1 + S) * ((size_t)R * c->tilevol * sizeof(float) + 1024);  // dense templates of the FFT path
   if (S > 0) need += (size_t)S * ((size_t)ngrp * rb * c->full_mask->tmpl_floats * sizeof(float) + R * sizeof(double) + 512);
   long long hard_total = 0;
   for (int r = 0; r < R; ++r) hard_total += tiles[r].hard_nnz;
@@ -764,6 +858,8 @@ int do_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int ntile
   if ((int)c->res.size() < ntile) c->res.resize(ntile);
   const int64_t l0 = c->launches;
   c->dist_ev_used = 0;
+  c->last_fft_bytes = 0.0;
+  c->last_fft_searches = c->last_direct_searches = 0;
   CK(cudaEventRecord(c->ev0, c->stream));
   for (int base = 0; base < ntile; base += c->max_batch) {
     const int R = std::min(c->max_batch, ntile - base);
@@ -836,6 +932,7 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
     cudaFree(e->d_boxes);
     for (auto& kv : e->a2) cudaFree(kv.second);
   }
+  iqfft::plan_destroy(c->fft);
   for (auto ev : c->dist_ev) cudaEventDestroy(ev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -876,12 +973,14 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   };
   int rc = upload(d->ti, &c->d_ti, &c->d_sat_ti);
   if (rc) return rc;
+  c->image_is_int[-1] = all_integer(d->ti, (long long)nimg);
   c->d_aux.assign(c->nsoft, nullptr);
   c->d_sat_aux.assign(c->nsoft, nullptr);
   for (int s = 0; s < c->nsoft; ++s) {
     if (!d->auxti || !d->auxti[s]) return fail(IQ_ERR_INVALID, "auxti[%d] is NULL", s);
     rc = upload(d->auxti[s], &c->d_aux[s], &c->d_sat_aux[s]);
     if (rc) return rc;
+    c->image_is_int[s] = all_integer(d->auxti[s], (long long)nimg);
   }
   c->nenabled = c->npos;
   if (d->disabled) {
@@ -995,7 +1094,7 @@ int32_t iq_distance(iq_ctx* c, int32_t which, const uint8_t* ovlmask, const iq_t
     MaskEntry* e = nullptr;
     rc = get_mask(c, ovlmask, &e);
     if (rc) return rc;
-    rc = stage_reserve(c, 8192 + (size_t)4 * e->tmpl_floats * sizeof(float));
+    rc = stage_reserve(c, 8192 + (size_t)4 * e->tmpl_floats * sizeof(float) + (size_t)c->tilevol * sizeof(float));
     if (rc) return rc;
     const float* k = tile->simdev;
     rc = run_dense(c, e, -1, &k, 1, c->d_Dovl, 0);
@@ -1036,7 +1135,7 @@ int32_t iq_distance(iq_ctx* c, int32_t which, const uint8_t* ovlmask, const iq_t
     src = c->d_Dhard;
   } else if (which >= 0 && which < c->nsoft) {
     if (!tile->softdev || !tile->softdev[which]) return fail(IQ_ERR_INVALID, "iq_distance: softdev missing");
-    rc = stage_reserve(c, 8192 + (size_t)4 * c->full_mask->tmpl_floats * sizeof(float));
+    rc = stage_reserve(c, 8192 + (size_t)4 * c->full_mask->tmpl_floats * sizeof(float) + (size_t)c->tilevol * sizeof(float));
     if (rc) return rc;
     const float* k = tile->softdev[which];
     rc = run_dense(c, c->full_mask, which, &k, 1, c->d_Dsoft[which], 2 + which);
@@ -1066,6 +1165,14 @@ int32_t iq_last_search_stats(const iq_ctx* c, double* device_ms, int64_t* kernel
   if (!c) return fail(IQ_ERR_INVALID, "NULL context");
   if (device_ms) *device_ms = c->last_ms;
   if (kernel_launches) *kernel_launches = c->last_launches;
+  return IQ_OK;
+}
+
+int32_t iq_last_search_path(const iq_ctx* c, int64_t* direct_searches, int64_t* fft_searches, double* fft_bytes) {
+  if (!c) return fail(IQ_ERR_INVALID, "NULL context");
+  if (direct_searches) *direct_searches = c->last_direct_searches;
+  if (fft_searches) *fft_searches = c->last_fft_searches;
+  if (fft_bytes) *fft_bytes = c->last_fft_bytes;
   return IQ_OK;
 }
 
@@ -1118,6 +1225,11 @@ int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
   if (std::strcmp(key, "rb") == 0) {
     if (value != 0 && value != 1 && value != 2 && value != 4) return fail(IQ_ERR_INVALID, "rb must be 0 (auto), 1, 2 or 4");
     c->rb_opt = (int)value;
+    return IQ_OK;
+  }
+  if (std::strcmp(key, "fft") == 0) {
+    if (value < -1 || value > 1) return fail(IQ_ERR_INVALID, "fft must be -1 (never), 0 (auto) or 1 (always)");
+    c->fft_mode = (int)value;
     return IQ_OK;
   }
   if (std::strcmp(key, "variant") == 0) {

@@ -1,0 +1,535 @@
+// iq_fft.cu -- hand-written shared-memory FFT cross-correlation for sm_100a (no cuFFT).
+//
+// Replaces the FFT route of the reference, imfilter(img, centered(krn), Inner(), Algorithm.FFT())
+// (/root/reference/src/imfilter.jl:5-7) and its cuFFT twin real(ifft(fft(img) .* conj(fft(padkrn))))
+// (src/imfilter.jl:14-25), for templates large enough that the direct kernel loses (measured crossover,
+// DESIGN.md).  What is different from the reference's GPU path:
+//   * the image spectrum is computed ONCE per context and cached (the reference re-transforms the image
+//     for every tile, src/imfilter.jl:19);
+//   * two real templates ride in one complex transform (re = template 2k, im = template 2k+1): correlation
+//     with a real image is a real-linear operator, so the real/imaginary parts of the result are the two
+//     correlations;
+//   * transforms are pruned: the template only occupies tx*ty*tz of the padded volume and only the valid
+//     region (distsize) of the result is needed, so most lines of the outer passes are never touched;
+//   * the forward transform along the last axis, the spectrum product and the inverse transform along
+//     that axis are one kernel; the last inverse pass writes |A2 - 2AB + B2| straight into the distance
+//     maps (with the disabled knock-out and the min/max reduction) -- no padded kernel image, no crop
+//     kernel, no device->host copy of the map (G3-G7 of SURVEY.md 2.1).
+// Layout: complex float2, x fastest.  Sizes are padded to powers of two (Stockham autosort, radix 4 with
+// one radix-2 stage when log2 N is odd), lines live in shared memory with a +1 float2 skew.
+#include "iq_fft.h"
+
+#include <math_constants.h>
+
+#include <cmath>
+#include <map>
+#include <vector>
+
+namespace iqfft {
+
+constexpr int kThreads = 256;
+
+__host__ __device__ constexpr int lines_per_block(int log2n) { return log2n >= 10 ? 4 : (log2n >= 9 ? 8 : 16); }
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// In-place (ping-pong) Stockham FFT of `nlines` lines of length N = 2^LOG2N held in shared memory with line
+// stride N+1.  tw[k] = exp(-2*pi*i*k/N).  Returns the buffer that holds the result.  All threads of the CTA
+// must call it; it ends with a __syncthreads().
+template <int LOG2N, bool INV>
+__device__ float2* fft_lines(float2* src, float2* dst, const float2* __restrict__ tw, int nlines) {
+  constexpr int N = 1 << LOG2N;
+  constexpr int LS = N + 1;
+  const int tid = threadIdx.x;
+  int n = N, s = 1, ls = 0;  // ls = log2(s)
+  while (n >= 4) {
+    const int n1 = n >> 2;
+    const int twstep = N / n;
+    constexpr int NQ = (N / 4) > 0 ? (N / 4) : 1;
+    for (int idx = tid; idx < nlines * NQ; idx += kThreads) {
+      const int line = idx / NQ, b = idx - line * NQ;
+      const int p = b >> ls, q = b & (s - 1);
+      const float2* xb = src + line * LS;
+      float2* yb = dst + line * LS;
+      const float2 a = xb[q + s * p], bb = xb[q + s * (p + n1)], c = xb[q + s * (p + 2 * n1)], d = xb[q + s * (p + 3 * n1)];
+      float2 w1 = tw[p * twstep], w2 = tw[2 * p * twstep], w3 = tw[3 * p * twstep];
+      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+      const float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(bb, d), bmd = csub(bb, d);
+      const float2 jbmd = INV ? make_float2(bmd.y, -bmd.x) : make_float2(-bmd.y, bmd.x);  // forward: +i*(b-d)
+      yb[q + s * (4 * p + 0)] = cadd(apc, bpd);
+      yb[q + s * (4 * p + 1)] = cmul(w1, csub(amc, jbmd));
+      yb[q + s * (4 * p + 2)] = cmul(w2, csub(apc, bpd));
+      yb[q + s * (4 * p + 3)] = cmul(w3, cadd(amc, jbmd));
+    }
+    __syncthreads();
+    float2* t = src; src = dst; dst = t;
+    n >>= 2; s <<= 2; ls += 2;
+  }
+  if (n == 2) {
+    for (int idx = tid; idx < nlines * (N / 2); idx += kThreads) {
+      const int line = idx / (N / 2), q = idx - line * (N / 2);
+      const float2* xb = src + line * LS;
+      float2* yb = dst + line * LS;
+      const float2 a = xb[q], b = xb[q + s];
+      yb[q] = cadd(a, b);
+      yb[q + s] = csub(a, b);
+    }
+    __syncthreads();
+    float2* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+template <int LOG2N>
+__device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* __restrict__ tw_g) {
+  constexpr int N = 1 << LOG2N;
+  for (int i = threadIdx.x; i < N; i += kThreads) tw_s[i] = tw_g[i];
+}
+
+template <int LOG2N>
+__device__ __forceinline__ void zero_lines(float2* buf, int nlines) {
+  constexpr int LS = (1 << LOG2N) + 1;
+  for (int i = threadIdx.x; i < nlines * LS; i += kThreads) buf[i] = make_float2(0.f, 0.f);
+}
+
+// ---- pass A: x lines built from a pair of real templates (flipped placement) -------------------------
+struct TmplPassArgs {
+  const float* tmpl;      // [R][tilevol]
+  float2* out;            // [npair][nlines][N]
+  int tx, nlines;         // nlines = ty*tz
+  long long tilevol;
+  int R;
+  const float2* tw;
+};
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads) k_fft_x_tmpl(const TmplPassArgs A) {
+  constexpr int N = 1 << LOG2N, LS = N + 1, LPB = lines_per_block(LOG2N);
+  extern __shared__ __align__(16) float2 sm[];
+  float2* b0 = sm;
+  float2* b1 = sm + LPB * LS;
+  float2* tw = sm + 2 * LPB * LS;
+  const int pr = blockIdx.y, l0 = blockIdx.x * LPB;
+  const int nl = min(LPB, A.nlines - l0);
+  load_twiddles<LOG2N>(tw, A.tw);
+  zero_lines<LOG2N>(b0, nl);
+  __syncthreads();
+  const float* t0 = A.tmpl + (long long)(2 * pr) * A.tilevol;
+  const bool has1 = (2 * pr + 1) < A.R;
+  const float* t1 = A.tmpl + (long long)(2 * pr + 1) * A.tilevol;
+  for (int i = threadIdx.x; i < nl * A.tx; i += kThreads) {
+    const int line = i / A.tx, qx = i - line * A.tx;
+    const long long src = (long long)(l0 + line) * A.tx + qx;
+    b0[line * LS + ((N - qx) & (N - 1))] = make_float2(t0[src], has1 ? t1[src] : 0.f);
+  }
+  __syncthreads();
+  const float2* res = fft_lines<LOG2N, false>(b0, b1, tw, nl);
+  float2* out = A.out + ((long long)pr * A.nlines + l0) * N;
+  for (int i = threadIdx.x; i < nl * N; i += kThreads) {
+    const int line = i >> LOG2N, e = i & (N - 1);
+    out[(long long)line * N + e] = res[line * LS + e];
+  }
+}
+
+// ---- pass A': x lines of a real image (spectrum set-up) ----------------------------------------------
+struct RealPassArgs {
+  const float* img;  // [nlines][nx]
+  float2* out;       // [nlines][N]
+  int nx, nlines;
+  const float2* tw;
+};
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads) k_fft_x_real(const RealPassArgs A) {
+  constexpr int N = 1 << LOG2N, LS = N + 1, LPB = lines_per_block(LOG2N);
+  extern __shared__ __align__(16) float2 sm[];
+  float2* b0 = sm;
+  float2* b1 = sm + LPB * LS;
+  float2* tw = sm + 2 * LPB * LS;
+  const int l0 = blockIdx.x * LPB;
+  const int nl = min(LPB, A.nlines - l0);
+  load_twiddles<LOG2N>(tw, A.tw);
+  zero_lines<LOG2N>(b0, nl);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nl * A.nx; i += kThreads) {
+    const int line = i / A.nx, x = i - line * A.nx;
+    b0[line * LS + x] = make_float2(A.img[(long long)(l0 + line) * A.nx + x], 0.f);
+  }
+  __syncthreads();
+  const float2* res = fft_lines<LOG2N, false>(b0, b1, tw, nl);
+  float2* out = A.out + (long long)l0 * N;
+  for (int i = threadIdx.x; i < nl * N; i += kThreads) {
+    const int line = i >> LOG2N, e = i & (N - 1);
+    out[(long long)line * N + e] = res[line * LS + e];
+  }
+}
+
+// ---- pass B: strided lines (y or z axis).  MODE 0 forward, 1 forward * spectrum -> inverse, 2 inverse --
+struct StridedArgs {
+  const float2* in;
+  float2* out;
+  long long in_sb, in_se, in_batch;    // element e of line (a,b): in[a + b*in_sb + e*in_se]
+  long long out_sb, out_se, out_batch;
+  int nin, flip, nout;                 // nin input entries (flipped placement if flip), first nout outputs stored
+  int na, nb;
+  const float2* mul;                   // MODE 1: spectrum, same (a,b,e) addressing with mul_sb / mul_se
+  long long mul_sb, mul_se;
+  const float2* tw;
+  float scale;                         // applied on store
+};
+template <int LOG2N, int MODE>
+__global__ void __launch_bounds__(kThreads) k_fft_strided(const StridedArgs A) {
+  constexpr int N = 1 << LOG2N, LS = N + 1, LPB = lines_per_block(LOG2N);
+  extern __shared__ __align__(16) float2 sm[];
+  float2* b0 = sm;
+  float2* b1 = sm + LPB * LS;
+  float2* tw = sm + 2 * LPB * LS;
+  const int a0 = blockIdx.x * LPB, b = blockIdx.y;
+  const int nl = min(LPB, A.na - a0);
+  const float2* in = A.in + (long long)blockIdx.z * A.in_batch + (long long)b * A.in_sb + a0;
+  float2* out = A.out + (long long)blockIdx.z * A.out_batch + (long long)b * A.out_sb + a0;
+  load_twiddles<LOG2N>(tw, A.tw);
+  if (A.nin < N) zero_lines<LOG2N>(b0, LPB);
+  __syncthreads();
+  for (int i = threadIdx.x; i < LPB * A.nin; i += kThreads) {
+    const int al = i % LPB, e = i / LPB;  // a fastest: coalesced
+    if (al < nl) {
+      const int slot = A.flip ? ((N - e) & (N - 1)) : e;
+      b0[al * LS + slot] = in[al + (long long)e * A.in_se];
+    }
+  }
+  __syncthreads();
+  float2* res = fft_lines<LOG2N, MODE == 2>(b0, b1, tw, LPB);
+  if (MODE == 1) {
+    float2* other = (res == b0) ? b1 : b0;
+    const float2* mul = A.mul + (long long)b * A.mul_sb + a0;
+    for (int i = threadIdx.x; i < LPB * N; i += kThreads) {
+      const int al = i % LPB, e = i / LPB;
+      if (al < nl) res[al * LS + e] = cmul(res[al * LS + e], mul[al + (long long)e * A.mul_se]);
+    }
+    __syncthreads();
+    res = fft_lines<LOG2N, true>(res, other, tw, LPB);
+  }
+  for (int i = threadIdx.x; i < LPB * A.nout; i += kThreads) {
+    const int al = i % LPB, e = i / LPB;
+    if (al < nl) {
+      float2 v = res[al * LS + e];
+      v.x *= A.scale;
+      v.y *= A.scale;
+      out[al + (long long)e * A.out_se] = v;
+    }
+  }
+}
+
+// ---- pass C: last inverse pass along x + distance epilogue --------------------------------------------
+struct FinalArgs {
+  const float2* in;     // [npair][nlines][N]
+  int nlines, nxo;      // nlines = nyo*nzo; output position p = line*nxo + x
+  long long npos;
+  int R;
+  Epilogue ep;
+  const float2* tw;
+};
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads) k_fft_x_final(const FinalArgs A) {
+  constexpr int N = 1 << LOG2N, LS = N + 1, LPB = lines_per_block(LOG2N);
+  extern __shared__ __align__(16) float2 sm[];
+  float2* b0 = sm;
+  float2* b1 = sm + LPB * LS;
+  float2* tw = sm + 2 * LPB * LS;
+  __shared__ unsigned s_min[2], s_max[2];
+  const int pr = blockIdx.y, l0 = blockIdx.x * LPB;
+  const int nl = min(LPB, A.nlines - l0);
+  load_twiddles<LOG2N>(tw, A.tw);
+  if (threadIdx.x < 2) { s_min[threadIdx.x] = 0x7f800000u; s_max[threadIdx.x] = 0u; }
+  const float2* in = A.in + ((long long)pr * A.nlines + l0) * N;
+  for (int i = threadIdx.x; i < nl * N; i += kThreads) {
+    const int line = i >> LOG2N, e = i & (N - 1);
+    b0[line * LS + e] = in[(long long)line * N + e];
+  }
+  __syncthreads();
+  const float2* res = fft_lines<LOG2N, true>(b0, b1, tw, nl);
+  const int r0 = 2 * pr, r1 = 2 * pr + 1;
+  const bool has1 = r1 < A.R;
+  const double b20 = A.ep.b2[r0], b21 = has1 ? A.ep.b2[r1] : 0.0;
+  unsigned mn0 = 0x7f800000u, mx0 = 0u, mn1 = 0x7f800000u, mx1 = 0u;
+  for (int i = threadIdx.x; i < nl * A.nxo; i += kThreads) {
+    const int line = i / A.nxo, x = i - line * A.nxo;
+    const long long p = (long long)(l0 + line) * A.nxo + x;
+    float2 ab = res[line * LS + x];
+    if (A.ep.round_to_int) { ab.x = rintf(ab.x); ab.y = rintf(ab.y); }
+    const double a2 = A.ep.a2 ? (double)__ldg(A.ep.a2 + p) : 0.0;
+    const bool dis = A.ep.disabled && A.ep.disabled[p];
+    float d0 = (float)fabs(a2 - 2.0 * (double)ab.x + b20);
+    if (dis) d0 = CUDART_INF_F;
+    A.ep.out[(long long)r0 * A.npos + p] = d0;
+    if (!dis) { const unsigned u = __float_as_uint(d0); mn0 = min(mn0, u); mx0 = max(mx0, u); }
+    if (has1) {
+      float d1 = (float)fabs(a2 - 2.0 * (double)ab.y + b21);
+      if (dis) d1 = CUDART_INF_F;
+      A.ep.out[(long long)r1 * A.npos + p] = d1;
+      if (!dis) { const unsigned u = __float_as_uint(d1); mn1 = min(mn1, u); mx1 = max(mx1, u); }
+    }
+  }
+  if (A.ep.minbits) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
+      mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+      mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+      mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&s_min[0], mn0); atomicMax(&s_max[0], mx0);
+      atomicMin(&s_min[1], mn1); atomicMax(&s_max[1], mx1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { atomicMin(A.ep.minbits + r0, s_min[0]); atomicMax(A.ep.maxbits + r0, s_max[0]); }
+    if (threadIdx.x == 1 && has1) { atomicMin(A.ep.minbits + r1, s_min[1]); atomicMax(A.ep.maxbits + r1, s_max[1]); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int ilog2_ceil(int n) {
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return l;
+}
+static size_t smem_bytes(int log2n) {
+  const int N = 1 << log2n;
+  return (size_t)(2 * lines_per_block(log2n) * (N + 1) + N) * sizeof(float2);
+}
+
+struct Plan {
+  int nx, ny, nz, tx, ty, tz, nxo, nyo, nzo;
+  int lx, ly, lz;       // log2 of the padded sizes (lz = 0 for 2-D)
+  int Nx, Ny, Nz;
+  int max_pairs;
+  long long npos;
+  float2 *twx = nullptr, *twy = nullptr, *twz = nullptr;
+  float2 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
+  long long w1_stride = 0, w2_stride = 0, w3_stride = 0, w4_stride = 0;  // float2 per pair
+  std::map<int, float2*> spectrum;
+  size_t workspace = 0;
+};
+
+#define FFT_DISPATCH(LOG2N, ...)                                   \
+  switch (LOG2N) {                                                 \
+    case 1: { constexpr int L = 1; __VA_ARGS__; } break;                  \
+    case 2: { constexpr int L = 2; __VA_ARGS__; } break;                  \
+    case 3: { constexpr int L = 3; __VA_ARGS__; } break;                  \
+    case 4: { constexpr int L = 4; __VA_ARGS__; } break;                  \
+    case 5: { constexpr int L = 5; __VA_ARGS__; } break;                  \
+    case 6: { constexpr int L = 6; __VA_ARGS__; } break;                  \
+    case 7: { constexpr int L = 7; __VA_ARGS__; } break;                  \
+    case 8: { constexpr int L = 8; __VA_ARGS__; } break;                  \
+    case 9: { constexpr int L = 9; __VA_ARGS__; } break;                  \
+    case 10: { constexpr int L = 10; __VA_ARGS__; } break;                \
+    default: return cudaErrorInvalidValue;                         \
+  }
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static cudaError_t launch_tmpl(const TmplPassArgs& a, int log2n, int npair, cudaStream_t s) {
+  const size_t sm = smem_bytes(log2n);
+  const int LPB = lines_per_block(log2n);
+  dim3 grid((a.nlines + LPB - 1) / LPB, npair);
+  FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_x_tmpl<L>, sm); if (e != cudaSuccess) return e;
+                        k_fft_x_tmpl<L><<<grid, kThreads, sm, s>>>(a); });
+  return cudaGetLastError();
+}
+static cudaError_t launch_real(const RealPassArgs& a, int log2n, cudaStream_t s) {
+  const size_t sm = smem_bytes(log2n);
+  const int LPB = lines_per_block(log2n);
+  dim3 grid((a.nlines + LPB - 1) / LPB);
+  FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_x_real<L>, sm); if (e != cudaSuccess) return e;
+                        k_fft_x_real<L><<<grid, kThreads, sm, s>>>(a); });
+  return cudaGetLastError();
+}
+template <int MODE>
+static cudaError_t launch_strided(const StridedArgs& a, int log2n, int batch, cudaStream_t s) {
+  const size_t sm = smem_bytes(log2n);
+  const int LPB = lines_per_block(log2n);
+  dim3 grid((a.na + LPB - 1) / LPB, a.nb, batch);
+  FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_strided<L, MODE>, sm); if (e != cudaSuccess) return e;
+                        k_fft_strided<L, MODE><<<grid, kThreads, sm, s>>>(a); });
+  return cudaGetLastError();
+}
+static cudaError_t launch_final(const FinalArgs& a, int log2n, int npair, cudaStream_t s) {
+  const size_t sm = smem_bytes(log2n);
+  const int LPB = lines_per_block(log2n);
+  dim3 grid((a.nlines + LPB - 1) / LPB, npair);
+  FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_x_final<L>, sm); if (e != cudaSuccess) return e;
+                        k_fft_x_final<L><<<grid, kThreads, sm, s>>>(a); });
+  return cudaGetLastError();
+}
+
+static cudaError_t make_twiddles(float2** out, int N, cudaStream_t s) {
+  std::vector<float2> h(N);
+  for (int k = 0; k < N; ++k) {
+    const double ang = -2.0 * M_PI * (double)k / (double)N;
+    h[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+  }
+  cudaError_t e = cudaMalloc((void**)out, N * sizeof(float2));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(*out, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
+}
+
+cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int tz, int max_templates, cudaStream_t s) {
+  *out = nullptr;
+  if (ny < 2 || nx < 2) return cudaErrorInvalidValue;
+  Plan* p = new Plan();
+  p->nx = nx; p->ny = ny; p->nz = nz; p->tx = tx; p->ty = ty; p->tz = tz;
+  p->nxo = nx - tx + 1; p->nyo = ny - ty + 1; p->nzo = nz - tz + 1;
+  p->npos = (long long)p->nxo * p->nyo * p->nzo;
+  p->lx = ilog2_ceil(nx); p->ly = ilog2_ceil(ny); p->lz = nz > 1 ? ilog2_ceil(nz) : 0;
+  p->Nx = 1 << p->lx; p->Ny = 1 << p->ly; p->Nz = 1 << p->lz;
+  if (p->lx > 10 || p->ly > 10 || p->lz > 10) { delete p; return cudaErrorInvalidValue; }
+  p->max_pairs = (max_templates + 1) / 2;
+  cudaError_t e;
+  if ((e = make_twiddles(&p->twx, p->Nx, s)) != cudaSuccess) { plan_destroy(p); return e; }
+  if ((e = make_twiddles(&p->twy, p->Ny, s)) != cudaSuccess) { plan_destroy(p); return e; }
+  if (p->lz > 0 && (e = make_twiddles(&p->twz, p->Nz, s)) != cudaSuccess) { plan_destroy(p); return e; }
+  const long long Nx = p->Nx, Ny = p->Ny;
+  p->w1_stride = (long long)tz * ty * Nx;
+  p->w4_stride = (long long)p->nzo * p->nyo * Nx;
+  if (p->lz > 0) {
+    p->w2_stride = (long long)tz * Ny * Nx;
+    p->w3_stride = (long long)p->nzo * Ny * Nx;
+  }
+  const size_t mp = (size_t)p->max_pairs;
+  if ((e = cudaMalloc((void**)&p->w1, mp * p->w1_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+  if ((e = cudaMalloc((void**)&p->w4, mp * p->w4_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+  if (p->lz > 0) {
+    if ((e = cudaMalloc((void**)&p->w2, mp * p->w2_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+    if ((e = cudaMalloc((void**)&p->w3, mp * p->w3_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+  }
+  p->workspace = mp * (p->w1_stride + p->w2_stride + p->w3_stride + p->w4_stride) * sizeof(float2);
+  *out = p;
+  return cudaSuccess;
+}
+
+void plan_destroy(Plan* p) {
+  if (!p) return;
+  cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->twz);
+  cudaFree(p->w1); cudaFree(p->w2); cudaFree(p->w3); cudaFree(p->w4);
+  for (auto& kv : p->spectrum) cudaFree(kv.second);
+  delete p;
+}
+
+size_t plan_workspace_bytes(const Plan* p) { return p->workspace; }
+
+cudaError_t plan_set_image(Plan* p, int id, const float* d_img, cudaStream_t s) {
+  if (p->spectrum.count(id)) return cudaSuccess;
+  const long long Nx = p->Nx, Ny = p->Ny, Nz = p->Nz;
+  float2 *t1 = nullptr, *t2 = nullptr, *spec = nullptr;
+  cudaError_t e;
+  // x pass: [nz][ny][Nx]
+  if ((e = cudaMalloc((void**)&t1, (size_t)p->nz * p->ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+  RealPassArgs ra{d_img, t1, p->nx, p->nz * p->ny, p->twx};
+  if ((e = launch_real(ra, p->lx, s)) != cudaSuccess) return e;
+  const float scale = (float)(1.0 / ((double)Nx * (double)Ny * (double)Nz));
+  if (p->lz == 0) {
+    if ((e = cudaMalloc((void**)&spec, (size_t)Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+    StridedArgs a{};
+    a.in = t1; a.out = spec;
+    a.in_sb = 0; a.in_se = Nx; a.in_batch = 0;
+    a.out_sb = 0; a.out_se = Nx; a.out_batch = 0;
+    a.nin = p->ny; a.flip = 0; a.nout = (int)Ny; a.na = (int)Nx; a.nb = 1; a.tw = p->twy; a.scale = scale;
+    if ((e = launch_strided<0>(a, p->ly, 1, s)) != cudaSuccess) return e;
+  } else {
+    if ((e = cudaMalloc((void**)&t2, (size_t)p->nz * Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&spec, (size_t)Nz * Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+    StridedArgs a{};
+    a.in = t1; a.out = t2;  // y pass: lines (x, z<nz)
+    a.in_sb = (long long)p->ny * Nx; a.in_se = Nx;
+    a.out_sb = Ny * Nx; a.out_se = Nx;
+    a.nin = p->ny; a.flip = 0; a.nout = (int)Ny; a.na = (int)Nx; a.nb = p->nz; a.tw = p->twy; a.scale = 1.f;
+    if ((e = launch_strided<0>(a, p->ly, 1, s)) != cudaSuccess) return e;
+    StridedArgs b{};
+    b.in = t2; b.out = spec;  // z pass: lines (x, y)
+    b.in_sb = Nx; b.in_se = Ny * Nx;
+    b.out_sb = Nx; b.out_se = Ny * Nx;
+    b.nin = p->nz; b.flip = 0; b.nout = (int)Nz; b.na = (int)Nx; b.nb = (int)Ny; b.tw = p->twz; b.scale = scale;
+    if ((e = launch_strided<0>(b, p->lz, 1, s)) != cudaSuccess) return e;
+  }
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+  cudaFree(t1);
+  cudaFree(t2);
+  p->spectrum[id] = spec;
+  return cudaSuccess;
+}
+
+cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogue& ep, cudaStream_t s, int* launches) {
+  auto it = p->spectrum.find(id);
+  if (it == p->spectrum.end()) return cudaErrorInvalidValue;
+  const float2* spec = it->second;
+  const int npair = (R + 1) / 2;
+  if (npair > p->max_pairs) return cudaErrorInvalidValue;
+  const long long Nx = p->Nx, Ny = p->Ny;
+  cudaError_t e;
+  int nl = 0;
+  TmplPassArgs ta{d_tmpl, p->w1, p->tx, p->ty * p->tz, (long long)p->tx * p->ty * p->tz, R, p->twx};
+  if ((e = launch_tmpl(ta, p->lx, npair, s)) != cudaSuccess) return e;
+  ++nl;
+  if (p->lz == 0) {
+    StridedArgs a{};  // fused y: lines (x)
+    a.in = p->w1; a.out = p->w4;
+    a.in_sb = 0; a.in_se = Nx; a.in_batch = p->w1_stride;
+    a.out_sb = 0; a.out_se = Nx; a.out_batch = p->w4_stride;
+    a.nin = p->ty; a.flip = 1; a.nout = p->nyo; a.na = (int)Nx; a.nb = 1;
+    a.mul = spec; a.mul_sb = 0; a.mul_se = Nx; a.tw = p->twy; a.scale = 1.f;
+    if ((e = launch_strided<1>(a, p->ly, npair, s)) != cudaSuccess) return e;
+    ++nl;
+  } else {
+    StridedArgs a{};  // forward y: lines (x, qz)
+    a.in = p->w1; a.out = p->w2;
+    a.in_sb = (long long)p->ty * Nx; a.in_se = Nx; a.in_batch = p->w1_stride;
+    a.out_sb = Ny * Nx; a.out_se = Nx; a.out_batch = p->w2_stride;
+    a.nin = p->ty; a.flip = 1; a.nout = (int)Ny; a.na = (int)Nx; a.nb = p->tz; a.tw = p->twy; a.scale = 1.f;
+    if ((e = launch_strided<0>(a, p->ly, npair, s)) != cudaSuccess) return e;
+    StridedArgs b{};  // fused z: lines (x, y)
+    b.in = p->w2; b.out = p->w3;
+    b.in_sb = Nx; b.in_se = Ny * Nx; b.in_batch = p->w2_stride;
+    b.out_sb = Nx; b.out_se = Ny * Nx; b.out_batch = p->w3_stride;
+    b.nin = p->tz; b.flip = 1; b.nout = p->nzo; b.na = (int)Nx; b.nb = (int)Ny;
+    b.mul = spec; b.mul_sb = Nx; b.mul_se = Ny * Nx; b.tw = p->twz; b.scale = 1.f;
+    if ((e = launch_strided<1>(b, p->lz, npair, s)) != cudaSuccess) return e;
+    StridedArgs c{};  // inverse y: lines (x, z<nzo)
+    c.in = p->w3; c.out = p->w4;
+    c.in_sb = Ny * Nx; c.in_se = Nx; c.in_batch = p->w3_stride;
+    c.out_sb = (long long)p->nyo * Nx; c.out_se = Nx; c.out_batch = p->w4_stride;
+    c.nin = (int)Ny; c.flip = 0; c.nout = p->nyo; c.na = (int)Nx; c.nb = p->nzo; c.tw = p->twy; c.scale = 1.f;
+    if ((e = launch_strided<2>(c, p->ly, npair, s)) != cudaSuccess) return e;
+    nl += 3;
+  }
+  FinalArgs fa{p->w4, p->nyo * p->nzo, p->nxo, p->npos, R, ep, p->twx};
+  if ((e = launch_final(fa, p->lx, npair, s)) != cudaSuccess) return e;
+  ++nl;
+  if (launches) *launches = nl;
+  return cudaSuccess;
+}
+
+double correlate_bytes(const Plan* p, int R) {
+  const double npair = (R + 1) / 2, c = sizeof(float2);
+  const double Nx = p->Nx, Ny = p->Ny, Nz = p->Nz;
+  double b = 4.0 * R * p->tx * p->ty * p->tz + npair * c * p->tz * p->ty * Nx;           // pass A
+  if (p->lz == 0) {
+    b += npair * c * (p->ty * Nx + Ny * Nx + p->nyo * Nx);                                 // fused y
+  } else {
+    b += npair * c * (p->tz * p->ty * Nx + p->tz * Ny * Nx);                               // forward y
+    b += npair * c * (p->tz * Ny * Nx + Nz * Ny * Nx + p->nzo * Ny * Nx);                  // fused z (+ spectrum)
+    b += npair * c * (p->nzo * Ny * Nx + (double)p->nzo * p->nyo * Nx);                    // inverse y
+  }
+  b += npair * c * (double)p->nzo * p->nyo * Nx + (double)R * 4.0 * p->npos + 4.0 * p->npos;  // final + maps + A2
+  return b;
+}
+
+}  // namespace iqfft

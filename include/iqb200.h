@@ -130,13 +130,18 @@ int32_t iq_last_search_stats(const iq_ctx* ctx, double* device_ms, int64_t* kern
  * iq_search* call, measured with CUDA events on the context's stream, and the number of its launches. */
 int32_t iq_last_search_kernel_ms(const iq_ctx* ctx, double* dist_ms, int64_t* dist_launches);
 
+/* Which distance kernels the most recent iq_search* call used: tile searches served by the direct
+ * correlation kernel, by the FFT path, and the algorithmic bytes the FFT passes moved. */
+int32_t iq_last_search_path(const iq_ctx* ctx, int64_t* direct_searches, int64_t* fft_searches, double* fft_bytes);
+
 /* FP32 FMA issue-rate microbenchmark on `device` (register-operand FFMA chains on every SM): writes the
  * measured rate in TFMA/s (1 FMA = 2 flop).  This is the denominator of the kernel's FMA roofline. */
 int32_t iq_bench_fma_peak(int32_t device, double* tfma_per_s);
 /* Same with the packed fma.rn.f32x2 instruction (two FMAs per issue slot on sm_100). */
 int32_t iq_bench_fma2_peak(int32_t device, double* tfma_per_s);
 
-/* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 1,2,4), "variant". */
+/* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 0 = auto,
+ * 1, 2, 4), "variant" (0 flat kernel, 1 tiled, 2 packed-FMA), "fft" (-1 never, 0 auto crossover, 1 always). */
 int32_t iq_ctx_set_option(iq_ctx* ctx, const char* key, int64_t value);
 
 #ifdef __cplusplus

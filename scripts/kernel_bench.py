@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--flush", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--fft", type=int, default=-1)
     ap.add_argument("--mask", default="interior", choices=["interior", "full", "x", "y", "z"])
     args = ap.parse_args()
     import torch
@@ -48,6 +49,7 @@ def main():
         if args.rb:
             ctx.set_option("rb", args.rb)
         ctx.set_option("variant", args.variant)
+        ctx.set_option("fft", args.fft)
         ms_all, dist_all = [], []
         for it in range(args.warmup + args.iters):
             if flush is not None:
@@ -61,7 +63,7 @@ def main():
         npos = ctx.npos
     fma = float(m.sum()) * npos * args.R
     d = float(np.mean(dist_all))
-    out = dict(variant=args.variant, config=args.config, R=args.R, rb=args.rb, mask=args.mask, nnz=int(m.sum()), npos=npos, flush=bool(args.flush),
+    out = dict(fft=args.fft, variant=args.variant, config=args.config, R=args.R, rb=args.rb, mask=args.mask, nnz=int(m.sum()), npos=npos, flush=bool(args.flush),
                search_ms=float(np.mean(ms_all)), dist_ms=d, dist_ms_min=float(np.min(dist_all)), launches=nl,
                tfma=fma / (d * 1e-3) / 1e12, peak_tfma=peak, frac=fma / (d * 1e-3) / 1e12 / peak,
                ncand=[int(x["idx"].size) for x in res][:4])

@@ -58,7 +58,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, "fft"])
 @pytest.mark.parametrize("kind,shape,tile,ovl", CASES)
 def test_overlap_distance_all_mask_shapes(kind, shape, tile, ovl, variant):
     ti = make_ti(kind, shape, 1)
@@ -67,7 +67,11 @@ def test_overlap_distance_all_mask_shapes(kind, shape, tile, ovl, variant):
     disabled = np.zeros(tuple(a - b + 1 for a, b in zip(shape, tile)), dtype=bool)
     disabled[tuple(r.integers(0, s, 5) for s in disabled.shape)] = True
     with api.SearchContext(ti, tile, disabled=disabled) as ctx:
-        ctx.set_option("variant", variant)  # 0 = flat (default), 1 = tiled, 2 = flat with packed f32x2 FMAs
+        if variant == "fft":
+            ctx.set_option("fft", 1)        # force the shared-memory FFT correlation path
+        else:
+            ctx.set_option("fft", -1)       # direct kernels: 0 = flat (default), 1 = tiled, 2 = flat with packed FMAs
+            ctx.set_option("variant", variant)
         combos = list(itertools.product([0, 1], repeat=2 * N))
         for bits in combos[1:: max(1, len(combos) // 12)] + [combos[-1]]:
             m = slab_mask(tile, ovl, bits[:N], bits[N:])
@@ -138,8 +142,9 @@ def assert_candidates(res, ref, exact):
     assert np.all(np.diff(res["idx"]) > 0)
 
 
+@pytest.mark.parametrize("fft", [-1, 1])
 @pytest.mark.parametrize("kind", ["cat", "gauss"])
-def test_threshold_search_batch(kind):
+def test_threshold_search_batch(kind, fft):
     shape, tile, ovl = (64, 60, 16), (16, 16, 8), (3, 3, 2)
     ti = make_ti(kind, shape, 7)
     r = np.random.default_rng(8)
@@ -147,6 +152,7 @@ def test_threshold_search_batch(kind):
     disabled = r.random(dist) < 0.01
     m = slab_mask(tile, ovl, (1, 1, 0), (0, 0, 0))
     with api.SearchContext(ti, tile, disabled=disabled, max_batch=4) as ctx:
+        ctx.set_option("fft", fft)
         tiles, devs = [], []
         for _ in range(7):  # 7 tiles with max_batch 4: exercises chunking and the partial RB group
             p0 = tuple(int(r.integers(0, s)) for s in dist)
@@ -173,16 +179,19 @@ def test_threshold_search_batch(kind):
         assert res[0]["picked"] == int(ref["patterndb"][O.sample_weighted(0.37, ref["probs"])])
 
 
+@pytest.mark.parametrize("fft", [-1, 1])
 @pytest.mark.parametrize("kind,tol", [("cat", 0.1), ("cat", 1.0), ("gauss", 0.1), ("cat", 0.02)])
-def test_relaxation_search_soft_and_hard(kind, tol):
+def test_relaxation_search_soft_and_hard(kind, tol, fft):
     shape, tile, ovl = (50, 44, 14), (12, 12, 6), (2, 2, 2)
     ti = make_ti(kind, shape, 9)
-    aux = np.asfortranarray(np.round(synth.box_mean(ti, (3, 3, 3)) * 4) / 4) if kind == "cat" else synth.box_mean(ti, (3, 3, 3))
+    # integer-valued auxiliary image in the categorical case: the FFT path then rounds AB and stays exact
+    aux = np.asfortranarray(np.round(synth.box_mean(ti, (3, 3, 3)) * 4)) if kind == "cat" else synth.box_mean(ti, (3, 3, 3))
     r = np.random.default_rng(10)
     dist = tuple(a - b + 1 for a, b in zip(shape, tile))
     disabled = r.random(dist) < 0.02
     m = slab_mask(tile, ovl, (1, 0, 1), (0, 0, 0))
     with api.SearchContext(ti, tile, disabled=disabled, auxti=[aux], max_batch=3) as ctx:
+        ctx.set_option("fft", fft)
         tiles, refs = [], []
         for i in range(5):
             p0 = tuple(int(r.integers(0, s)) for s in dist)
