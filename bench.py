@@ -44,45 +44,85 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def start_clock_sampler():
-    try:
-        f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={SMI_QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
-                             stdout=f, stderr=subprocess.DEVNULL)
-        return p, f.name
-    except Exception:
-        return None, None
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region through NVML in a
+    background thread (the `nvidia-smi -lms` loop of the profiling recipe takes driver locks often enough
+    to disturb a host-driven pipeline of ~1 ms CUDA calls; same counters, lighter path).  Falls back to
+    nvidia-smi when pynvml is missing."""
 
+    def __init__(self, device, period=0.25):
+        import threading
+        self.device, self.period = device, period
+        self.sm, self.reasons, self.smmax = [], set(), 0.0
+        self._stop = threading.Event()
+        self._thread = None
+        self._proc = self._file = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self.nv = None
+            try:
+                f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={SMI_QUERY}", "--format=csv,noheader,nounits",
+                                               "-lms", "500"], stdout=f, stderr=subprocess.DEVNULL)
+                self._file = f.name
+            except Exception:
+                pass
 
-def stop_clock_sampler(p, name, device):
-    if p is None:
-        return None
-    p.terminate()
-    try:
-        p.wait(timeout=5)
-    except Exception:
-        p.kill()
-    sm, smmax, reasons = [], 0.0, set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    try:
-        for line in open(name):
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9 or parts[0] != str(device):
-                continue
-            sm.append(float(parts[1]))
-            smmax = max(smmax, float(parts[2]))
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(name)
-    except Exception:
-        pass
-    if not sm:
-        return None
-    sm.sort()
-    # "under load": upper half of the samples (the host cut phases idle the SMs between searches)
-    return {"sm_mhz": float(np.median(sm[len(sm) // 2:])), "sm_mhz_all_median": float(np.median(sm)),
-            "sm_max_mhz": smmax, "reasons": sorted(reasons), "samples": len(sm)}
+    def _loop(self):
+        nv = self.nv
+        masks = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, m in masks.items():
+                    if r & m:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        elif self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            try:
+                for line in open(self._file):
+                    parts = [x.strip() for x in line.split(",")]
+                    if len(parts) < 9 or parts[0] != str(self.device):
+                        continue
+                    self.sm.append(float(parts[1]))
+                    self.smmax = max(self.smmax, float(parts[2]))
+                    for nm, val in zip(names, parts[5:9]):
+                        if val.lower().startswith("active"):
+                            self.reasons.add(nm)
+                os.unlink(self._file)
+            except Exception:
+                pass
+        if not self.sm:
+            return None
+        sm = sorted(self.sm)
+        # "under load": upper half of the samples (host phases idle the SMs between searches)
+        return {"sm_mhz": float(np.median(sm[len(sm) // 2:])), "sm_mhz_all_median": float(np.median(sm)),
+                "sm_max_mhz": self.smmax, "reasons": sorted(self.reasons), "samples": len(sm),
+                "via": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def algorithmic_work(geo, path):
@@ -140,6 +180,7 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=0, help="tiles in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rb", type=int, default=0)
+    ap.add_argument("--fft", type=int, default=0, help="-1 direct kernels only, 0 auto crossover (default), 1 always FFT")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -196,12 +237,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    nthreads = max(1, ncores // max(world, 1))
+    nthreads = max(1, ncores // max(world, 1) - 2)  # per rank: leave the GPU-driving thread and the sampler a core
     seed0 = 1234 + 1000 * rank
 
     def step(i):
         t0 = time.perf_counter()
-        out, ex = iqb200.iqsim(ti, tilesize, rng=np.random.default_rng(seed0 + i), device=local, nthreads=nthreads,
+        out, ex = iqb200.iqsim(ti, tilesize, rng=np.random.default_rng(seed0 + i), device=local, nthreads=nthreads, fft=args.fft,
                                return_stats=True, return_picks=True, **kw)
         chk = float(sum(float(r[0, 0, 0] if r.ndim == 3 else r[0, 0]) for r in out))  # touch the result on the host
         return time.perf_counter() - t0, ex, chk
@@ -209,7 +250,7 @@ def main():
     for i in range(args.warmup):
         step(-1 - i)
     fma_peak = api.fma_peak(local)
-    sampler = start_clock_sampler() if rank == 0 else (None, None)
+    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     t_start = time.perf_counter()
     walls, stats = [], []
@@ -219,7 +260,7 @@ def main():
         stats.append(ex)
     barrier()
     t_total = time.perf_counter() - t_start
-    clocks = stop_clock_sampler(sampler[0], sampler[1], local) if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
 
     geo = stats[0]["stats"]["geo"]
     vox_per_step = float(np.prod(geo["simsize"], dtype=np.float64)) * args.nreal_per_gpu
@@ -246,23 +287,46 @@ def main():
     h2d = sum(s["stats"]["searches"] for s in stats) / args.steps * float(np.prod(tilesize)) * 4.0 + nti * 4.0
     d2h = sum(s["stats"]["candidates"] for s in stats) / args.steps * 8.0
 
+    fft_ms = sum(s["stats"]["fft_ms"] for s in stats)
+    fft_bytes = sum(s["stats"]["fft_bytes"] for s in stats)
+    nfft = sum(s["stats"]["fft_searches"] for s in stats)
+    ndirect = sum(s["stats"]["direct_searches"] for s in stats)
+    direct_ms = max(dist_ms - fft_ms, 0.0)
+    fma_roof = {"bound": "fp32_fma", "achieved": 2 * achieved_tfma, "peak": 2 * fma_peak, "unit": "TFLOP/s",
+                "frac": achieved_tfma / fma_peak if fma_peak else None, "traffic": 129.1e6,
+                "kernel": "k_dist_flat", "launches": int(dist_launches), "kernel_ms_total": dist_ms,
+                "peak_source": "iq_bench_fma_peak measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                "traffic_note": "dram read+write per launch from profiles/r01_k_dist_flat_ncu.txt (8 templates, config 5)",
+                "hbm_term": {"achieved_gbs": achieved_gbs, "peak_gbs": peaks.get("hbm_gbs"), "of": peak_kind,
+                             "frac": achieved_gbs / peaks.get("hbm_gbs", 1.0)}}
+    if fft_ms > direct_ms:
+        # the FFT passes dominate: byte-bound roofline, algorithmic bytes from iqfft::correlate_bytes
+        gbs = fft_bytes / (fft_ms * 1e-3) / 1e9
+        # direct-equivalent FMA rate of the same searches (reported, NOT used for `achieved`)
+        eq_tfma = fma_total * (nfft / max(nfft + ndirect, 1)) / (fft_ms * 1e-3) / 1e12
+        roof = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": gbs / peaks.get("hbm_gbs", 1.0), "of": peak_kind, "traffic": None,
+                "kernel": "FFT correlation passes (k_fft_x_tmpl, k_fft_strided<fwd|fused|inv>, k_fft_x_final)",
+                "kernel_ms_total": fft_ms, "searches_fft": int(nfft), "searches_direct": int(ndirect),
+                "bytes_per_search": fft_bytes / max(nfft, 1), "direct_equivalent_tfma": eq_tfma,
+                "note": "working set per launch (templates x padded volume) is partly L2-resident; bytes are algorithmic"}
+        if direct_ms > 0 and ndirect > 0:
+            roof["direct_kernel_ms_total"] = direct_ms
+    else:
+        roof = fma_roof
+
     line = {
         "metric": "iqsim voxels/sec", "value": world * vox_per_step * args.steps / resident_max, "unit": "voxels/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "tilesize": list(tilesize), "trainimg": list(ti.shape),
-                   "l2": "training image (<= 25 MB) is L2-resident by design; distance maps (R x 15 MB) exceed nothing -- "
-                         "kernel is FMA-bound, no L2 flush applies to whole-job steps",
-                   "host_threads_per_rank": nthreads, "host_cores": ncores},
+                   "l2": "whole-job steps: every search reads fresh templates and writes R x npos distance maps (> L2 at "
+                         "R >= 8 on config 5); the training image / its spectrum stay L2-resident by design, no flush applies",
+                   "host_threads_per_rank": nthreads, "host_cores": ncores, "distance_path": {-1: "direct", 0: "auto", 1: "fft"}[args.fft]},
         "e2e": {"value": world * vox_per_step * args.steps / t_total_max, "unit": "voxels/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(sum(s["stats"]["kernel_launches"] for s in stats)),
-        "roofline": {"bound": "fp32_fma", "achieved": 2 * achieved_tfma, "peak": 2 * fma_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tfma / fma_peak if fma_peak else None, "traffic": None,
-                     "kernel": "k_dist_flat", "launches": int(dist_launches), "kernel_ms_total": dist_ms,
-                     "peak_source": "iq_bench_fma_peak measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
-                     "hbm_term": {"achieved_gbs": achieved_gbs, "peak_gbs": peaks.get("hbm_gbs"), "of": peak_kind,
-                                  "frac": achieved_gbs / peaks.get("hbm_gbs", 1.0)}},
+        "roofline": roof,
         "breakdown_ms_per_step": {k: sum(s["stats"][k] for s in stats) / args.steps
                                   for k in ("search_ms", "search_device_ms", "cut_ms", "setup_ms", "total_ms")},
         "clocks": clocks,

@@ -45,14 +45,15 @@ class IqhDesc(C.Structure):
                 ("aux", C.POINTER(c_float_p)), ("auxti", C.POINTER(c_float_p)),
                 ("hard_has", c_u8_p), ("hard_val", c_float_p), ("path", c_i64_p), ("npath", C.c_int64),
                 ("tol", C.c_double), ("nreal", C.c_int32), ("u", c_double_p), ("debug", C.c_int32),
-                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32)]
+                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32), ("fft_mode", C.c_int32)]
 
 
 class IqhStats(C.Structure):
     _fields_ = [("search_ms", C.c_double), ("search_device_ms", C.c_double), ("cut_ms", C.c_double),
                 ("total_ms", C.c_double), ("searches", C.c_int64), ("kernel_launches", C.c_int64),
                 ("candidates", C.c_int64), ("setup_ms", C.c_double), ("dist_kernel_ms", C.c_double),
-                ("dist_launches", C.c_int64)]
+                ("dist_launches", C.c_int64), ("fft_searches", C.c_int64), ("direct_searches", C.c_int64),
+                ("fft_bytes", C.c_double), ("fft_ms", C.c_double)]
 
 
 # every symbol include/*.h declares: name -> (restype, argtypes)
@@ -69,7 +70,7 @@ SYMBOLS = {
     "iq_distance": (C.c_int32, [C.c_void_p, C.c_int32, c_u8_p, C.POINTER(IqTile), c_float_p]),
     "iq_fetch_tile": (C.c_int32, [C.c_void_p, C.c_int64, c_float_p]),
     "iq_last_search_stats": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
-    "iq_last_search_path": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p, c_double_p]),
+    "iq_last_search_path": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p, c_double_p, c_double_p]),
     "iq_last_search_kernel_ms": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
     "iq_bench_fma_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "iq_bench_fma2_peak": (C.c_int32, [C.c_int32, c_double_p]),

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -104,27 +105,37 @@ void taumodel(int64_t n, int nsrc, const float* vals, std::vector<double>& prob)
   const double dn = (double)n;
   const double x0 = (1.0 - 1.0 / dn) / (1.0 / dn);
   std::vector<double> prod((size_t)n, 1.0);
-  std::vector<float> sorted;
-  std::vector<double> P((size_t)n);
+  std::vector<uint32_t> order((size_t)n), tmp((size_t)n), rank((size_t)n);
   for (int j = 0; j < nsrc; ++j) {
     const float* v = vals + (size_t)j * n;
-    sorted.assign(v, v + n);
-    std::sort(sorted.begin(), sorted.end());
-    sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    const uint32_t* bits = reinterpret_cast<const uint32_t*>(v);  // values are >= 0 or +Inf: bit order = numeric order
+    // LSD radix sort of the candidate slots by value bits (3 passes of 11 bits)
+    for (int64_t i = 0; i < n; ++i) order[(size_t)i] = (uint32_t)i;
+    for (int pass = 0; pass < 3; ++pass) {
+      const int shift = 11 * pass;
+      uint32_t hist[2049] = {0};
+      for (int64_t i = 0; i < n; ++i) hist[((bits[order[(size_t)i]] >> shift) & 2047u) + 1]++;
+      for (int b = 0; b < 2048; ++b) hist[b + 1] += hist[b];
+      for (int64_t i = 0; i < n; ++i) tmp[hist[(bits[order[(size_t)i]] >> shift) & 2047u]++] = order[(size_t)i];
+      order.swap(tmp);
+    }
+    // dense ranks: ties share a rank (taumodel.jl:22-31)
+    uint32_t r = 0;
     double colsum = 0.0;
-    for (int64_t i = 0; i < n; ++i) {
-      const double r = (double)(std::lower_bound(sorted.begin(), sorted.end(), v[i]) - sorted.begin() + 1);
-      P[i] = (dn - r) + 1.0;
-      colsum += P[i];  // integer-valued: exact
+    for (int64_t k = 0; k < n; ++k) {
+      if (k == 0 || bits[order[(size_t)k]] != bits[order[(size_t)k - 1]]) ++r;
+      rank[order[(size_t)k]] = r;
+      colsum += (dn - (double)r) + 1.0;  // integer-valued: exact
     }
     for (int64_t i = 0; i < n; ++i) {
-      const double Pi = P[i] / colsum;
+      const double P = (dn - (double)rank[(size_t)i]) + 1.0;
+      const double Pi = P / colsum;
       const double X = (1.0 - Pi) / Pi;
       const double ratio = X / x0;
-      prod[i] = (j == 0) ? ratio : prod[i] * ratio;
+      prod[(size_t)i] = (j == 0) ? ratio : prod[(size_t)i] * ratio;
     }
   }
-  for (int64_t i = 0; i < n; ++i) prob[i] = 1.0 / (1.0 + x0 * prod[i]);
+  for (int64_t i = 0; i < n; ++i) prob[(size_t)i] = 1.0 / (1.0 + x0 * prod[(size_t)i]);
 }
 
 }  // namespace
@@ -177,6 +188,11 @@ struct iq_ctx {
   unsigned* h_cand_idx = nullptr;
   float* h_cand_val = nullptr;
   size_t h_cand_cap = 0;
+  unsigned* d_rank = nullptr;             // [max_batch][max_src][kTauMax] dense ranks (device tau model)
+  unsigned long long* d_colsum = nullptr; // [max_batch][max_src]
+  double* d_prob = nullptr;               // [max_batch][kTauMax]
+  double* h_prob = nullptr;               // pinned mirror
+  int tau_device = 1;                     // 0 = always evaluate the tau model on the host
   int* d_shifts = nullptr;
   int nshift = 0;
   float* d_fetch = nullptr;
@@ -192,7 +208,9 @@ struct iq_ctx {
 
   double last_ms = 0.0;
   int64_t last_launches = 0;
-  std::vector<cudaEvent_t> dist_ev;  // start/stop pairs around every k_dist_boxes launch of a search
+  std::vector<cudaEvent_t> dist_ev;  // start/stop pairs around every distance computation of a search
+  std::vector<char> dist_ev_fft;     // per pair: 1 = FFT path
+  double last_fft_ms = 0.0;
   size_t dist_ev_used = 0;
   double last_dist_ms = 0.0;
   int64_t last_dist_launches = 0;
@@ -469,6 +487,8 @@ int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R,
   CK(cudaEventRecord(c->dist_ev[c->dist_ev_used], c->stream));
   CK(iqfft::correlate(c->fft, image, (const float*)(c->d_stage + off_t), R, ep, c->stream, &nl));
   CK(cudaEventRecord(c->dist_ev[c->dist_ev_used + 1], c->stream));
+  if (c->dist_ev_fft.size() < c->dist_ev.size() / 2) c->dist_ev_fft.resize(c->dist_ev.size() / 2, 0);
+  c->dist_ev_fft[c->dist_ev_used / 2] = 1;
   c->dist_ev_used += 2;
   c->launches += nl;
   c->last_fft_bytes += iqfft::correlate_bytes(c->fft, R);
@@ -544,6 +564,8 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
   else if (c->variant != 1) CK(iq::launch_dist_flat(p, rb, std::max<size_t>(smem, 64), c->stream));
   else CK(iq::launch_dist_boxes(p, rb, std::max<size_t>(smem, 64), c->stream));
   CK(cudaEventRecord(c->dist_ev[c->dist_ev_used + 1], c->stream));
+  if (c->dist_ev_fft.size() < c->dist_ev.size() / 2) c->dist_ev_fft.resize(c->dist_ev.size() / 2, 0);
+  c->dist_ev_fft[c->dist_ev_used / 2] = 0;
   c->dist_ev_used += 2;
   c->launches++;
   return IQ_OK;
@@ -787,6 +809,10 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
 
   CK(iq::launch_pick_write(c->d_pick, R, c->npos, c->stream));
   c->launches++;
+  if (c->tau_device) {
+    CK(iq::launch_tau(c->d_pick, R, maxS, c->d_rank, c->d_colsum, c->d_prob, c->stream));
+    c->launches += 2;
+  }
   CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, (size_t)nkind * 2 * c->max_batch * sizeof(unsigned), cudaMemcpyDeviceToHost,
                      c->stream));
   CK(cudaStreamSynchronize(c->stream));  // totals now valid
@@ -810,9 +836,15 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
       if (n == 0) continue;
       CK(cudaMemcpyAsync(c->h_cand_idx + o, c->d_cand_idx + (size_t)r * c->npos, n * sizeof(unsigned), cudaMemcpyDeviceToHost,
                          c->stream));
-      for (int s = 0; s < nsrc[r]; ++s)
-        CK(cudaMemcpyAsync(c->h_cand_val + (o * maxS) + (size_t)s * n, c->d_cand_val + ((size_t)r * maxS + s) * c->npos,
-                           n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      const bool on_device = c->tau_device && n >= 2 && n <= (size_t)iq::kTauMax;
+      if (on_device) {
+        CK(cudaMemcpyAsync(c->h_prob + (size_t)r * iq::kTauMax, c->d_prob + (size_t)r * iq::kTauMax, n * sizeof(double),
+                           cudaMemcpyDeviceToHost, c->stream));
+      } else {
+        for (int s = 0; s < nsrc[r]; ++s)
+          CK(cudaMemcpyAsync(c->h_cand_val + (o * maxS) + (size_t)s * n, c->d_cand_val + ((size_t)r * maxS + s) * c->npos,
+                             n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      }
       o += n;
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -826,7 +858,9 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
       TileResult& tr = c->res[res_base + r];
       tr.idx.resize((size_t)n);
       for (int64_t i = 0; i < n; ++i) tr.idx[(size_t)i] = (int64_t)c->h_cand_idx[o + i];
-      if (n > 0) taumodel(n, nsrc[r], c->h_cand_val + o * maxS, tr.prob);
+      const bool on_device = c->tau_device && n >= 2 && n <= (int64_t)iq::kTauMax;
+      if (on_device) tr.prob.assign(c->h_prob + (size_t)r * iq::kTauMax, c->h_prob + (size_t)r * iq::kTauMax + n);
+      else if (n > 0) taumodel(n, nsrc[r], c->h_cand_val + o * maxS, tr.prob);
       else tr.prob.clear();
       tr.idx_ptr = tr.idx.data();
       tr.prob_ptr = tr.prob.data();
@@ -873,11 +907,13 @@ int do_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int ntile
   c->last_ms = ms;
   c->last_launches = c->launches - l0;
   c->last_dist_ms = 0.0;
+  c->last_fft_ms = 0.0;
   c->last_dist_launches = (int64_t)(c->dist_ev_used / 2);
   for (size_t i = 0; i + 1 < c->dist_ev_used; i += 2) {
     float dm = 0.f;
     CK(cudaEventElapsedTime(&dm, c->dist_ev[i], c->dist_ev[i + 1]));
     c->last_dist_ms += dm;
+    if (c->dist_ev_fft[i / 2]) c->last_fft_ms += dm;
   }
   return IQ_OK;
 }
@@ -928,6 +964,10 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   if (c->h_cand_val) cudaFreeHost(c->h_cand_val);
   cudaFree(c->d_shifts);
   cudaFree(c->d_fetch);
+  cudaFree(c->d_rank);
+  cudaFree(c->d_colsum);
+  cudaFree(c->d_prob);
+  if (c->h_prob) cudaFreeHost(c->h_prob);
   for (auto& e : c->masks) {
     cudaFree(e->d_boxes);
     for (auto& kv : e->a2) cudaFree(kv.second);
@@ -1015,6 +1055,10 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   CK(cudaMalloc((void**)&c->d_cand_idx, B * c->npos * sizeof(unsigned)));
   CK(cudaMalloc((void**)&c->d_cand_val, B * c->max_src * c->npos * sizeof(float)));
   CK(cudaMalloc((void**)&c->d_fetch, (size_t)c->tilevol * sizeof(float)));
+  CK(cudaMalloc((void**)&c->d_rank, B * c->max_src * iq::kTauMax * sizeof(unsigned)));
+  CK(cudaMalloc((void**)&c->d_colsum, B * c->max_src * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&c->d_prob, B * iq::kTauMax * sizeof(double)));
+  CK(cudaMallocHost((void**)&c->h_prob, B * iq::kTauMax * sizeof(double)));
   // radix-select schedule: 4 value bytes, then only the index bytes that can be non-zero
   std::vector<int> shifts = {56, 48, 40, 32};
   int nib = 1;
@@ -1055,6 +1099,7 @@ int32_t iq_ctx_create(iq_ctx** out, const iq_ctx_desc* d) {
   if (c->npos >= (1ll << 32)) { delete c; return fail(IQ_ERR_INVALID, "more than 2^32 patch positions"); }
   c->nsoft = d->nsoft;
   c->max_batch = std::max(1, d->max_batch);
+  if (const char* ev = std::getenv("IQB200_TAU_DEVICE")) c->tau_device = std::atoi(ev) ? 1 : 0;  // experiments only
   const int rc = ctx_create_impl(c, d);
   if (rc != IQ_OK) {
     const std::string keep = g_err;
@@ -1168,11 +1213,12 @@ int32_t iq_last_search_stats(const iq_ctx* c, double* device_ms, int64_t* kernel
   return IQ_OK;
 }
 
-int32_t iq_last_search_path(const iq_ctx* c, int64_t* direct_searches, int64_t* fft_searches, double* fft_bytes) {
+int32_t iq_last_search_path(const iq_ctx* c, int64_t* direct_searches, int64_t* fft_searches, double* fft_bytes, double* fft_ms) {
   if (!c) return fail(IQ_ERR_INVALID, "NULL context");
   if (direct_searches) *direct_searches = c->last_direct_searches;
   if (fft_searches) *fft_searches = c->last_fft_searches;
   if (fft_bytes) *fft_bytes = c->last_fft_bytes;
+  if (fft_ms) *fft_ms = c->last_fft_ms;
   return IQ_OK;
 }
 
@@ -1225,6 +1271,10 @@ int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
   if (std::strcmp(key, "rb") == 0) {
     if (value != 0 && value != 1 && value != 2 && value != 4) return fail(IQ_ERR_INVALID, "rb must be 0 (auto), 1, 2 or 4");
     c->rb_opt = (int)value;
+    return IQ_OK;
+  }
+  if (std::strcmp(key, "tau_device") == 0) {
+    c->tau_device = value ? 1 : 0;
     return IQ_OK;
   }
   if (std::strcmp(key, "fft") == 0) {

@@ -9,13 +9,13 @@
 // Scheduling.  The simulation path is shared by all realizations (iqsim.jl:139) and a realization only
 // depends on its own previous tiles, so realizations advance in lockstep: one iq_search_pick call carries
 // the templates of a whole group.  The realizations are split into two groups with a context (stream)
-// each; while the GPU searches step k of one group, a host worker team cuts and pastes step k of the
-// other group, so the host cut hides behind the device search (or vice versa).
-#include <omp.h>
-
+// each; while the GPU searches step k of one group, a pool of host threads cuts and pastes step k of the
+// other group(s), so the host cut hides behind the device search (or vice versa).
 #include <algorithm>
 #include <chrono>
+#include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -38,55 +38,72 @@ struct Slab {
   int lo[3], sz[3];
 };
 
-// One persistent worker thread; it owns the OpenMP team used for cuts and pastes.
-class Worker {
+// Persistent pool of host threads that executes cut / paste tasks of every group from one shared queue:
+// tasks of different groups interleave, so the cores stay busy even when a group has fewer tasks than
+// there are threads.
+class Pool {
  public:
-  Worker() : th_([this] { loop(); }) {}
-  ~Worker() {
+  explicit Pool(int n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+  }
+  ~Pool() {
     {
       std::lock_guard<std::mutex> l(m_);
       quit_ = true;
     }
     cv_.notify_all();
-    th_.join();
+    for (auto& t : th_) t.join();
   }
-  void submit(std::function<void()> f) {
+  void push(std::function<void(int)> f) {
     {
       std::lock_guard<std::mutex> l(m_);
-      job_ = std::move(f);
-      busy_ = true;
+      q_.push_back(std::move(f));
     }
-    cv_.notify_all();
+    cv_.notify_one();
   }
-  void wait() {
-    std::unique_lock<std::mutex> l(m_);
-    done_.wait(l, [this] { return !busy_; });
-  }
+  int size() const { return (int)th_.size(); }
 
  private:
-  void loop() {
+  void loop(int tid) {
     for (;;) {
-      std::function<void()> f;
+      std::function<void(int)> f;
       {
         std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [this] { return quit_ || busy_; });
-        if (quit_) return;
-        f = std::move(job_);
-        job_ = nullptr;
+        cv_.wait(l, [this] { return quit_ || !q_.empty(); });
+        if (q_.empty()) return;  // quit requested and nothing left
+        f = std::move(q_.front());
+        q_.pop_front();
       }
-      f();
-      {
-        std::lock_guard<std::mutex> l(m_);
-        busy_ = false;
-      }
-      done_.notify_all();
+      f(tid);
     }
   }
   std::mutex m_;
-  std::condition_variable cv_, done_;
-  std::function<void()> job_;
-  bool busy_ = false, quit_ = false;
-  std::thread th_;
+  std::condition_variable cv_;
+  std::deque<std::function<void(int)>> q_;
+  bool quit_ = false;
+  std::vector<std::thread> th_;
+};
+
+// Completion latch of one group's cut+paste job.
+struct Latch {
+  std::mutex m;
+  std::condition_variable cv;
+  bool busy = false;
+  void begin() {
+    std::lock_guard<std::mutex> l(m);
+    busy = true;
+  }
+  void finish() {
+    {
+      std::lock_guard<std::mutex> l(m);
+      busy = false;
+    }
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> l(m);
+    cv.wait(l, [this] { return !busy; });
+  }
 };
 
 struct Geo {
@@ -112,8 +129,11 @@ struct Group {
   std::vector<int64_t> picked;
   std::vector<double> ustep;
   std::vector<std::vector<uint8_t>> keepbuf;
-  double search_ms = 0, search_dev_ms = 0, cut_ms = 0, dist_ms = 0;
-  int64_t launches = 0, dist_launches = 0, ncand = 0;
+  std::unique_ptr<Latch> latch{new Latch()};
+  std::atomic<int> cuts_left{0}, pastes_left{0};
+  clk::time_point cut_t0;
+  double search_ms = 0, search_dev_ms = 0, cut_ms = 0, dist_ms = 0, fft_bytes = 0, fft_ms = 0;
+  int64_t launches = 0, dist_launches = 0, ncand = 0, nfft = 0, ndirect = 0;
 };
 
 }  // namespace
@@ -152,7 +172,9 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
 
   // one core stays with the thread that drives the GPU; the rest form the cut/paste team
   const int hw = std::max(1, (int)std::thread::hardware_concurrency());
-  const int nthreads = D->nthreads > 0 ? D->nthreads : std::max(1, hw - 1);
+  // (the driver thread spins in stream synchronisation and the worker thread is itself a team member, so the
+  // team may own at most hw - 2 cores or its barriers wait on descheduled members)
+  const int nthreads = std::max(1, std::min(D->nthreads > 0 ? D->nthreads : hw, hw - 2));
   const int ngroups = (R >= 2) ? 2 : 1;
 
   const auto t_setup = clk::now();
@@ -177,6 +199,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     cd.max_batch = D->batch > 0 ? std::min(D->batch, g.R) : g.R;
     rc = iq_ctx_create(&g.ctx, &cd);
     if (rc != IQ_OK) { destroy_all(); return rc; }
+    iq_ctx_set_option(g.ctx, "fft", D->fft_mode);
     g.pasted.assign((size_t)G.ntile_total, 0);
     g.ovlmask.resize((size_t)G.tilevol);
     g.simdev.resize((size_t)G.tilevol * g.R);
@@ -191,7 +214,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
 
   std::memset(out_grids, 0, sizeof(double) * G.padvol * R);  // simgrid = zeros (iqsim.jl:165)
   if (D->debug) std::memset(out_cuts, 0, (size_t)G.padvol * R);
-  std::vector<iqcut::Work> work(nthreads);
+  std::vector<iqcut::Work> work(nthreads);  // one scratch set per pool thread
 
   // ---- search of one step for one group (iqsim.jl:177-243) ----
   auto do_search = [&](Group& g, int64_t step) -> int {
@@ -274,6 +297,12 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     iq_last_search_kernel_ms(g.ctx, &dms, &nl);
     g.dist_ms += dms;
     g.dist_launches += nl;
+    {
+      int64_t nd = 0, nf = 0;
+      double fb = 0, fm = 0;
+      iq_last_search_path(g.ctx, &nd, &nf, &fb, &fm);
+      g.ndirect += nd; g.nfft += nf; g.fft_bytes += fb; g.fft_ms += fm;
+    }
     for (int r = 0; r < g.R; ++r) {
       g.ncand += g.results[r].count;
       g.picked[r] = g.results[r].picked;
@@ -284,94 +313,106 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     return IQ_OK;
   };
 
-  // ---- boundary cut + paste of one step for one group (iqsim.jl:244-281): one (realization, slab)
-  //      cut per task, then one paste per realization ----
-  auto do_cut = [&](Group& g) {
-    const auto tc = clk::now();
+  // ---- boundary cut + paste of one step for one group (iqsim.jl:244-281): one task per (realization,
+  //      slab) cut; the last cut to finish enqueues one paste task per realization; the last paste
+  //      releases the group's latch ----
+  Pool pool(nthreads);
+  auto cut_task = [&](Group& g, int task, int tid) {
+    iqcut::Work& w = work[tid];
+    const int nslab = (int)g.slabs.size();
+    const int r = task / nslab;
+    const Slab& s = g.slabs[task % nslab];
+    const int* start = g.start;
+    const double* grid = out_grids + (size_t)(g.r0 + r) * G.padvol;
+    const int64_t rind = g.picked[r];
+    const int rs[3] = {(int)(rind % G.dist[0]), (int)((rind / G.dist[0]) % G.dist[1]),
+                       (int)(rind / ((long long)G.dist[0] * G.dist[1]))};
+    const int nv = s.sz[0] * s.sz[1] * s.sz[2];
+    w.A.resize(nv);
+    w.B.resize(nv);
+    g.keepbuf[task].resize(nv);
+    int i = 0;
+    for (int z = 0; z < s.sz[2]; ++z)
+      for (int y = 0; y < s.sz[1]; ++y) {
+        const int qy = s.lo[1] + y, qz = s.lo[2] + z;
+        const double* ga = grid + ((long long)(start[2] + qz) * pad[1] + (start[1] + qy)) * pad[0] + start[0] + s.lo[0];
+        const double* gb = D->ti + ((long long)(rs[2] + qz) * n[1] + (rs[1] + qy)) * n[0] + rs[0] + s.lo[0];
+        for (int x = 0; x < s.sz[0]; ++x, ++i) { w.A[i] = ga[x]; w.B[i] = gb[x]; }
+      }
+    iqcut::graphcut(w.A.data(), w.B.data(), s.sz, s.d, g.keepbuf[task].data(), w);
+  };
+  auto paste_task = [&](Group& g, int r, int tid) {
+    iqcut::Work& w = work[tid];
+    const int nslab = (int)g.slabs.size();
+    const int* start = g.start;
+    double* grid = out_grids + (size_t)(g.r0 + r) * G.padvol;
+    const int64_t rind = g.picked[r];
+    const int rs[3] = {(int)(rind % G.dist[0]), (int)((rind / G.dist[0]) % G.dist[1]),
+                       (int)(rind / ((long long)G.dist[0] * G.dist[1]))};
+    w.cutmask.assign((size_t)G.tilevol, 0);
+    for (int si = 0; si < nslab; ++si) {
+      const Slab& s = g.slabs[si];
+      const uint8_t* keep = g.keepbuf[r * nslab + si].data();
+      int i = 0;
+      for (int z = 0; z < s.sz[2]; ++z)
+        for (int y = 0; y < s.sz[1]; ++y)
+          for (int x = 0; x < s.sz[0]; ++x, ++i) {
+            const size_t q = ((size_t)(s.lo[2] + z) * t[1] + (s.lo[1] + y)) * t[0] + s.lo[0] + x;
+            w.cutmask[q] |= s.prev ? keep[i] : (uint8_t)!keep[i];  // iqsim.jl:264 / :273
+          }
+    }
+    // simdev[.!cutmask] = TIdev[.!cutmask]  (iqsim.jl:278)
+    uint8_t* cg = D->debug ? out_cuts + (size_t)(g.r0 + r) * G.padvol : nullptr;
+    for (int z = 0; z < t[2]; ++z)
+      for (int y = 0; y < t[1]; ++y) {
+        const long long gi = ((long long)(start[2] + z) * pad[1] + (start[1] + y)) * pad[0] + start[0];
+        const double* src = D->ti + ((long long)(rs[2] + z) * n[1] + (rs[1] + y)) * n[0] + rs[0];
+        const uint8_t* cm = &w.cutmask[((size_t)z * t[1] + y) * t[0]];
+        for (int x = 0; x < t[0]; ++x) {
+          if (!cm[x]) grid[gi + x] = src[x];
+          if (cg) cg[gi + x] = cm[x];
+        }
+      }
+  };
+  std::function<void(Group*)> start_pastes = [&](Group* gp) {
+    gp->pastes_left.store(gp->R);
+    for (int r = 0; r < gp->R; ++r)
+      pool.push([&, gp, r](int tid) {
+        paste_task(*gp, r, tid);
+        if (gp->pastes_left.fetch_sub(1) == 1) {
+          gp->cut_ms += ms_since(gp->cut_t0);
+          gp->latch->finish();
+        }
+      });
+  };
+  auto submit_cut = [&](Group& g) {
     const int nslab = (int)g.slabs.size();
     const int ntask = g.R * nslab;
     if ((int)g.keepbuf.size() < ntask) g.keepbuf.resize(ntask);
-    const int* start = g.start;
-    const int team = std::max(1, std::min(nthreads, std::max(ntask, g.R)));
-#pragma omp parallel num_threads(team)
-    {
-      iqcut::Work& w = work[omp_get_thread_num()];
-#pragma omp for schedule(dynamic, 1)
-      for (int task = 0; task < ntask; ++task) {
-        const int r = task / nslab;
-        const Slab& s = g.slabs[task % nslab];
-        const double* grid = out_grids + (size_t)(g.r0 + r) * G.padvol;
-        const int64_t rind = g.picked[r];
-        const int rs[3] = {(int)(rind % G.dist[0]), (int)((rind / G.dist[0]) % G.dist[1]),
-                           (int)(rind / ((long long)G.dist[0] * G.dist[1]))};
-        const int nv = s.sz[0] * s.sz[1] * s.sz[2];
-        w.A.resize(nv);
-        w.B.resize(nv);
-        g.keepbuf[task].resize(nv);
-        int i = 0;
-        for (int z = 0; z < s.sz[2]; ++z)
-          for (int y = 0; y < s.sz[1]; ++y) {
-            const int qy = s.lo[1] + y, qz = s.lo[2] + z;
-            const double* ga = grid + ((long long)(start[2] + qz) * pad[1] + (start[1] + qy)) * pad[0] + start[0] + s.lo[0];
-            const double* gb = D->ti + ((long long)(rs[2] + qz) * n[1] + (rs[1] + qy)) * n[0] + rs[0] + s.lo[0];
-            for (int x = 0; x < s.sz[0]; ++x, ++i) { w.A[i] = ga[x]; w.B[i] = gb[x]; }
-          }
-        iqcut::graphcut(w.A.data(), w.B.data(), s.sz, s.d, g.keepbuf[task].data(), w);
-      }
-#pragma omp for schedule(static)
-      for (int r = 0; r < g.R; ++r) {
-        double* grid = out_grids + (size_t)(g.r0 + r) * G.padvol;
-        const int64_t rind = g.picked[r];
-        const int rs[3] = {(int)(rind % G.dist[0]), (int)((rind / G.dist[0]) % G.dist[1]),
-                           (int)(rind / ((long long)G.dist[0] * G.dist[1]))};
-        w.cutmask.assign((size_t)G.tilevol, 0);
-        for (int si = 0; si < nslab; ++si) {
-          const Slab& s = g.slabs[si];
-          const uint8_t* keep = g.keepbuf[r * nslab + si].data();
-          int i = 0;
-          for (int z = 0; z < s.sz[2]; ++z)
-            for (int y = 0; y < s.sz[1]; ++y)
-              for (int x = 0; x < s.sz[0]; ++x, ++i) {
-                const size_t q = ((size_t)(s.lo[2] + z) * t[1] + (s.lo[1] + y)) * t[0] + s.lo[0] + x;
-                w.cutmask[q] |= s.prev ? keep[i] : (uint8_t)!keep[i];  // iqsim.jl:264 / :273
-              }
-        }
-        // simdev[.!cutmask] = TIdev[.!cutmask]  (iqsim.jl:278)
-        uint8_t* cg = D->debug ? out_cuts + (size_t)(g.r0 + r) * G.padvol : nullptr;
-        for (int z = 0; z < t[2]; ++z)
-          for (int y = 0; y < t[1]; ++y) {
-            const long long gi = ((long long)(start[2] + z) * pad[1] + (start[1] + y)) * pad[0] + start[0];
-            const double* src = D->ti + ((long long)(rs[2] + z) * n[1] + (rs[1] + y)) * n[0] + rs[0];
-            const uint8_t* cm = &w.cutmask[((size_t)z * t[1] + y) * t[0]];
-            for (int x = 0; x < t[0]; ++x) {
-              if (!cm[x]) grid[gi + x] = src[x];
-              if (cg) cg[gi + x] = cm[x];
-            }
-          }
-      }
-    }
-    g.cut_ms += ms_since(tc);
+    g.latch->begin();
+    g.cut_t0 = clk::now();
+    Group* gp = &g;
+    if (ntask == 0) { start_pastes(gp); return; }
+    g.cuts_left.store(ntask);
+    for (int task = 0; task < ntask; ++task)
+      pool.push([&, gp, task](int tid) {
+        cut_task(*gp, task, tid);
+        if (gp->cuts_left.fetch_sub(1) == 1) start_pastes(gp);
+      });
   };
 
-  // ---- pipelined main loop: search(group) on this thread, cut(group) on the worker thread ----
-  {
-    Worker worker;  // one worker = one OpenMP team: cuts of the two groups never oversubscribe the cores
-    for (int64_t step = 0; step < D->npath && rc == IQ_OK; ++step) {
-      for (int gi = 0; gi < ngroups; ++gi) {
-        Group& g = groups[gi];
-        // with two groups the only cut that can still be running is the one of the OTHER group's
-        // current step -- and the one of this group's previous step has been waited for one
-        // iteration ago; a single wait() here therefore covers both orders
-        if (ngroups == 1) worker.wait();
-        rc = do_search(g, step);  // overlaps the other group's cut
-        if (rc != IQ_OK) break;
-        worker.wait();
-        Group* gp = &g;
-        worker.submit([&do_cut, gp] { do_cut(*gp); });
-      }
+  // ---- pipelined main loop: this thread runs the searches; the cut+paste job of a group is in flight
+  //      on the pool until that group's next search needs its grid ----
+  for (int64_t step = 0; step < D->npath && rc == IQ_OK; ++step) {
+    for (int gi = 0; gi < ngroups; ++gi) {
+      Group& g = groups[gi];
+      g.latch->wait();          // cut+paste of this group's previous step
+      rc = do_search(g, step);  // overlaps the cuts of the other groups
+      if (rc != IQ_OK) break;
+      submit_cut(g);
     }
-    worker.wait();
   }
+  for (auto& g : groups) g.latch->wait();
   double search_ms = 0, search_dev_ms = 0, cut_ms = 0, dist_ms = 0;
   int64_t launches = 0, dist_launches = 0, ncand = 0;
   for (auto& g : groups) {
@@ -391,6 +432,12 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     stats->setup_ms = setup_ms;
     stats->dist_kernel_ms = dist_ms;
     stats->dist_launches = dist_launches;
+    stats->fft_searches = stats->direct_searches = 0;
+    stats->fft_bytes = stats->fft_ms = 0;
+    for (auto& g : groups) {
+      stats->fft_searches += g.nfft; stats->direct_searches += g.ndirect;
+      stats->fft_bytes += g.fft_bytes; stats->fft_ms += g.fft_ms;
+    }
   }
   return IQ_OK;
 }

@@ -6,6 +6,7 @@
 
 namespace iq {
 
+constexpr int kTauMax = 16384; // largest candidate set ranked on the device (shared-memory bitonic sort)
 constexpr int kT = 8;           // outputs per thread along x (register tile)
 constexpr int kWarpX = 32;      // outputs per warp along x  (4 lanes x 8)
 constexpr int kWarpY = 8;       // outputs per warp along y  (8 lanes)
@@ -102,6 +103,8 @@ cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStre
 cudaError_t launch_fetch_tile(const float* img, int nx, int ny, int nz, int tx, int ty, int tz,
                               long long x0, long long y0, long long z0, float* out, cudaStream_t s);
 int pick_nblk(long long npos);
+cudaError_t launch_tau(const PickJob* jobs, int njobs, int maxS, unsigned* rank, unsigned long long* colsum, double* prob,
+                       cudaStream_t s);
 cudaError_t launch_fma_peak(int blocks, int iters, float* out, cudaStream_t s);
 
 }  // namespace iq

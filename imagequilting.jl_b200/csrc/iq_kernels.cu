@@ -807,9 +807,18 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, long long npo
   const int shift = shifts[s_pass];
   const unsigned long long prefix = s_prefix, mask = s_mask;
   const float* __restrict__ map = J->map;
-  for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < npos; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long key = make_key(map[i], i);
-    if ((key & mask) == prefix) atomicAdd(&h[(unsigned)(key >> shift) & 255u], 1u);
+  // warp-aggregated histogram: distance values cluster in a few exponent bins, so per-lane shared-memory
+  // atomics would serialise 32-way; lanes with the same bin elect one leader that adds their count
+  const int lane = tid & 31;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); i0 < npos; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + lane;
+    unsigned bin = 0xffffffffu;
+    if (i < npos) {
+      const unsigned long long key = make_key(map[i], i);
+      if ((key & mask) == prefix) bin = (unsigned)(key >> shift) & 255u;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
   }
   __syncthreads();
   if (h[tid]) atomicAdd(&J->hist[tid], h[tid]);
@@ -967,6 +976,112 @@ cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStre
 }
 cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStream_t s) {
   k_pick_write<<<dim3(pick_nblk(npos), njobs), 256, 0, s>>>(jobs, npos);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// tau model on the device (src/taumodel.jl:5-45) for candidate sets of 2 .. kTauMax entries:
+//   k_tau_rank : one CTA per (tile, source): bitonic sort of (value bits << 32 | slot) keys in shared memory,
+//                dense ranks (ties share a rank, taumodel.jl:22-31) scattered back to candidate order, and the
+//                integer column sum of (n - r + 1) (taumodel.jl:34-35)
+//   k_tau_prob : per candidate, the FP64 combination of taumodel.jl:34-44 with every operation individually
+//                rounded (no FMA contraction) so that the result is bit-identical to the host/oracle code
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_tau_rank(const PickJob* jobs, unsigned* rank_out, unsigned long long* colsum,
+                                                   int maxS) {
+  const PickJob& J = jobs[blockIdx.y];
+  const int s = blockIdx.x;
+  const unsigned n = *J.total;
+  if (s >= J.nsrc || n < 2u || n > (unsigned)kTauMax) return;
+  extern __shared__ __align__(16) unsigned long long keys[];
+  __shared__ unsigned s_part[32];
+  __shared__ unsigned long long s_sum;
+  unsigned NP = 2;
+  while (NP < n) NP <<= 1;
+  const int tid = threadIdx.x;
+  const float* vals = J.cand_val + (long long)s * J.cap;
+  for (unsigned i = tid; i < NP; i += 1024)
+    keys[i] = i < n ? (((unsigned long long)__float_as_uint(vals[i]) << 32) | i) : ~0ull;
+  if (tid == 0) s_sum = 0ull;
+  __syncthreads();
+  for (unsigned k = 2; k <= NP; k <<= 1) {
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned t = tid; t < NP / 2; t += 1024) {
+        const unsigned i = 2 * t - (t & (j - 1));
+        const unsigned ixj = i + j;
+        const bool up = (i & k) == 0;
+        const unsigned long long a = keys[i], b = keys[ixj];
+        if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // dense ranks: contiguous segment per thread, block scan of the segment sums
+  const unsigned seg = (NP + 1023) / 1024;
+  const unsigned k0 = tid * seg, k1 = min(k0 + seg, n);
+  unsigned local = 0;
+  for (unsigned k = k0; k < k1; ++k) local += (k == 0 || (unsigned)(keys[k] >> 32) != (unsigned)(keys[k - 1] >> 32)) ? 1u : 0u;
+  unsigned incl = local;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned v = s_part[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    s_part[lane] = v;
+  }
+  __syncthreads();
+  unsigned r = incl - local + (warp > 0 ? s_part[warp - 1] : 0u);
+  unsigned long long mysum = 0ull;
+  unsigned* ro = rank_out + ((long long)blockIdx.y * maxS + s) * kTauMax;
+  for (unsigned k = k0; k < k1; ++k) {
+    if (k == 0 || (unsigned)(keys[k] >> 32) != (unsigned)(keys[k - 1] >> 32)) ++r;
+    ro[(unsigned)(keys[k] & 0xffffffffull)] = r;
+    mysum += (unsigned long long)(n - r + 1u);
+  }
+  atomicAdd(&s_sum, mysum);
+  __syncthreads();
+  if (tid == 0) colsum[blockIdx.y * maxS + s] = s_sum;
+}
+
+__global__ void __launch_bounds__(256) k_tau_prob(const PickJob* jobs, const unsigned* rank, const unsigned long long* colsum,
+                                                  double* prob, int maxS) {
+  const PickJob& J = jobs[blockIdx.y];
+  const unsigned n = *J.total;
+  if (n < 2u || n > (unsigned)kTauMax) return;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double dn = (double)n;
+  const double inv = __ddiv_rn(1.0, dn);
+  const double x0 = __ddiv_rn(__dsub_rn(1.0, inv), inv);  // (1 - 1/n) / (1/n), taumodel.jl:38
+  double prod = 1.0;
+  for (int s = 0; s < J.nsrc; ++s) {
+    const double r = (double)rank[((long long)blockIdx.y * maxS + s) * kTauMax + i];
+    const double P = __dadd_rn(__dsub_rn(dn, r), 1.0);                    // nevents - D + 1
+    const double Pi = __ddiv_rn(P, (double)colsum[blockIdx.y * maxS + s]);  // / sum(P, dims=1)
+    const double X = __ddiv_rn(__dsub_rn(1.0, Pi), Pi);                   // (1 - P) / P
+    const double ratio = __ddiv_rn(X, x0);
+    prod = (s == 0) ? ratio : __dmul_rn(prod, ratio);
+  }
+  prob[(long long)blockIdx.y * kTauMax + i] = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(x0, prod)));
+}
+
+cudaError_t launch_tau(const PickJob* jobs, int njobs, int maxS, unsigned* rank, unsigned long long* colsum, double* prob,
+                       cudaStream_t s) {
+  const size_t smem = (size_t)kTauMax * sizeof(unsigned long long);
+  cudaError_t e = cudaFuncSetAttribute(k_tau_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_tau_rank<<<dim3(maxS, njobs), 1024, smem, s>>>(jobs, rank, colsum, maxS);
+  k_tau_prob<<<dim3(kTauMax / 256, njobs), 256, 0, s>>>(jobs, rank, colsum, prob, maxS);
   return cudaGetLastError();
 }
 

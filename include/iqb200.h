@@ -131,8 +131,9 @@ int32_t iq_last_search_stats(const iq_ctx* ctx, double* device_ms, int64_t* kern
 int32_t iq_last_search_kernel_ms(const iq_ctx* ctx, double* dist_ms, int64_t* dist_launches);
 
 /* Which distance kernels the most recent iq_search* call used: tile searches served by the direct
- * correlation kernel, by the FFT path, and the algorithmic bytes the FFT passes moved. */
-int32_t iq_last_search_path(const iq_ctx* ctx, int64_t* direct_searches, int64_t* fft_searches, double* fft_bytes);
+ * correlation kernel, by the FFT path, the algorithmic bytes the FFT passes moved and their device time. */
+int32_t iq_last_search_path(const iq_ctx* ctx, int64_t* direct_searches, int64_t* fft_searches, double* fft_bytes,
+                            double* fft_ms);
 
 /* FP32 FMA issue-rate microbenchmark on `device` (register-operand FFMA chains on every SM): writes the
  * measured rate in TFMA/s (1 FMA = 2 flop).  This is the denominator of the kernel's FMA roofline. */

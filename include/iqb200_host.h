@@ -47,6 +47,7 @@ typedef struct iqh_desc {
   int32_t device;
   int32_t batch;               /* realizations per iq_search_pick call (<= nreal); 0 = all */
   int32_t nthreads;            /* host threads for cut + paste; 0 = hardware concurrency */
+  int32_t fft_mode;            /* -1 never, 0 auto crossover, 1 always: distance path selection */
 } iqh_desc;
 
 typedef struct iqh_stats {
@@ -60,6 +61,10 @@ typedef struct iqh_stats {
   double setup_ms;             /* context creation: uploads + summed-volume tables */
   double dist_kernel_ms;       /* device time inside the dense correlation kernel alone */
   int64_t dist_launches;
+  int64_t fft_searches;        /* tile searches served by the FFT path / by the direct kernel */
+  int64_t direct_searches;
+  double fft_bytes;            /* algorithmic bytes moved by the FFT passes */
+  double fft_ms;               /* device time inside the FFT passes */
 } iqh_stats;
 
 /* Runs the whole simulation.  `out_grids` receives nreal padded grids (pad_size doubles each,

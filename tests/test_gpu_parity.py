@@ -296,3 +296,31 @@ def test_realization_range_equals_slice_of_full_run():
     assert len(part) == 3
     for a, b in zip(part, full[1:4]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("tol", [0.05, 1.0])
+def test_tau_model_device_equals_host_and_oracle(tol):
+    """The device tau model (k_tau_rank/k_tau_prob, <= 16384 candidates), the host fallback (larger sets) and
+    the oracle give bit-identical probabilities on an integer-valued image."""
+    r = np.random.default_rng(21)
+    ti = np.asfortranarray(r.integers(0, 2, (500, 400)).astype(np.float32))   # binary: huge tie groups
+    aux = np.asfortranarray((synth.box_mean(ti, (3, 3)) > 0.5).astype(np.float32))
+    tile = (8, 8)
+    dist = (493, 393)
+    m = slab_mask(tile, (3, 3), (1, 1), (0, 0))
+    dev = ti[40:48, 60:68].copy()
+    sdev = aux[100:108, 20:28].copy()
+    ref = oracle_search(ti, dev, m, np.zeros(dist, bool), tol, soft=[(aux.astype(np.float64), sdev.astype(np.float64))])
+    out = []
+    for tau_device in (1, 0):
+        with api.SearchContext(ti, tile, auxti=[aux], max_batch=2) as ctx:
+            ctx.set_option("tau_device", tau_device)
+            res = ctx.search(m, [dict(simdev=dev, softdev=[sdev])] * 2, tol=tol, u=[0.3, 0.9])
+            out.append(res)
+    for res in out:
+        for k in range(2):
+            assert res[k]["idx"].tolist() == ref["patterndb"].tolist()
+            assert np.array_equal(res[k]["prob"], ref["probs"])
+    assert out[0][0]["picked"] == out[1][0]["picked"] == int(ref["patterndb"][O.sample_weighted(0.3, ref["probs"])])
+    if tol == 1.0:
+        assert ref["patterndb"].size > 16384, ref["patterndb"].size  # exercises the host fallback
