@@ -45,7 +45,7 @@ class IqhDesc(C.Structure):
                 ("aux", C.POINTER(c_float_p)), ("auxti", C.POINTER(c_float_p)),
                 ("hard_has", c_u8_p), ("hard_val", c_float_p), ("path", c_i64_p), ("npath", C.c_int64),
                 ("tol", C.c_double), ("nreal", C.c_int32), ("u", c_double_p), ("debug", C.c_int32),
-                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32), ("fft_mode", C.c_int32)]
+                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32), ("ngroups", C.c_int32), ("fft_mode", C.c_int32)]
 
 
 class IqhStats(C.Structure):

@@ -150,7 +150,7 @@ def _genpath(rng, extent, kind, datainds):
 # iqsim
 # --------------------------------------------------------------------------------------
 def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None, tol=0.1, path="raster", nreal=1,
-          debug=False, showprogress=False, rng=None, device=0, batch=0, nthreads=0, fft=0, return_stats=False,
+          debug=False, showprogress=False, rng=None, device=0, batch=0, nthreads=0, ngroups=0, fft=0, return_stats=False,
           return_picks=False, _path_override=None, _uniforms=None, _real_range=None):
     """Image quilting simulation with the GPU distance search (see module docstring)."""
     timg = trainimg if isinstance(trainimg, np.ma.MaskedArray) else np.asarray(trainimg)
@@ -262,6 +262,7 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     d.tol, d.nreal = float(tol), int(nreal)
     d.u = _ptr(u, c_double_p)
     d.debug, d.device, d.batch, d.nthreads = int(bool(debug)), int(device), int(batch), int(nthreads)
+    d.ngroups = int(ngroups)
     d.fft_mode = int(fft)  # distance path: -1 direct kernels only, 0 measured crossover, 1 FFT whenever possible
     stats = IqhStats()
     if nvis > 0:

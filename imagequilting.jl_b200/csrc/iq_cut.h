@@ -5,18 +5,25 @@
 
 namespace iqcut {
 
+// One lattice node: residual capacities towards the 6 neighbours (dir = 2*d (+d) / 2*d+1 (-d)) and the
+// Boykov-Kolmogorov bookkeeping, packed in one cache line.
+struct Node {
+  double cap[6];
+  int stamp;        // origin-check cache (augmentation counter)
+  uint8_t tree;     // 0 free, 1 source tree, 2 sink tree
+  int8_t par;       // direction towards the parent, or kTerminal / kNone / kOrphan
+  uint8_t term;     // 1 = source slice, 2 = sink slice, 0 = interior
+  uint8_t valid;    // bit dir set = neighbour in direction dir exists
+  uint8_t inq;      // already in the active queue
+  uint8_t pad[7];
+};
+static_assert(sizeof(Node) == 64, "one node per cache line");
+
 // Scratch space reused across cuts by one host thread.
 struct Work {
-  int sz[3] = {0, 0, 0};
-  int dim = -1;
-  std::vector<int> nbr;          // [nvox][6] neighbour index or -1; dir = 2*d (+d) / 2*d+1 (-d)
-  std::vector<double> cap;       // [nvox][6] residual capacities
-  std::vector<uint8_t> tree;     // 0 free, 1 source tree, 2 sink tree
-  std::vector<int8_t> par;       // direction towards the parent, or kTerminal / kNone
-  std::vector<uint8_t> term;     // 1 = source slice, 2 = sink slice, 0 = interior
+  std::vector<Node> nodes;
   std::vector<int> active, orphans, queue;
-  std::vector<uint8_t> inactive_q, reach;
-  std::vector<int> stamp;        // origin-check cache
+  std::vector<uint8_t> reach;
   std::vector<double> A, B;      // slab extraction buffers (used by the driver)
   std::vector<uint8_t> keep, cutmask;
 };

@@ -175,7 +175,10 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
   // (the driver thread spins in stream synchronisation and the worker thread is itself a team member, so the
   // team may own at most hw - 2 cores or its barriers wait on descheduled members)
   const int nthreads = std::max(1, std::min(D->nthreads > 0 ? D->nthreads : hw, hw - 2));
-  const int ngroups = (R >= 2) ? 2 : 1;
+  // more groups = more searches in flight while cuts run (the per-step critical path is search + slowest
+  // cut of ONE group); fewer groups = larger, more efficient search batches
+  int ngroups = D->ngroups > 0 ? D->ngroups : (R >= 8 ? 4 : (R >= 2 ? 2 : 1));
+  ngroups = std::max(1, std::min(ngroups, R));
 
   const auto t_setup = clk::now();
   std::vector<Group> groups(ngroups);

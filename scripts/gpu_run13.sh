@@ -1,0 +1,1 @@
+python scripts/exp_threads.py 14
