@@ -15,8 +15,9 @@
 //     that axis are one kernel; the last inverse pass writes |A2 - 2AB + B2| straight into the distance
 //     maps (with the disabled knock-out and the min/max reduction) -- no padded kernel image, no crop
 //     kernel, no device->host copy of the map (G3-G7 of SURVEY.md 2.1).
-// Layout: complex float2, x fastest.  Sizes are padded to powers of two (Stockham autosort, radix 4 with
-// one radix-2 stage when log2 N is odd), lines live in shared memory with a +1 float2 skew.
+// Layout: complex float2, x fastest.  Sizes are padded to powers of two; Stockham autosort passes of radix
+// 16 (then 8/4/2) with the butterflies in registers, lines in shared memory with a 1-in-16 padding that
+// makes every pass and every global<->shared copy bank-conflict free.
 #include "iq_fft.h"
 
 #include <math_constants.h>
@@ -30,53 +31,152 @@ namespace iqfft {
 constexpr int kThreads = 256;
 
 __host__ __device__ constexpr int lines_per_block(int log2n) { return log2n >= 10 ? 4 : (log2n >= 9 ? 8 : 16); }
+// shared-memory line layout: element i of a line lives at i + (i >> 4) (one float2 of padding per 16), lines
+// are LS apart.  With this skew every access pattern of the radix-16/8/4/2 Stockham passes below and the
+// line-fastest global<->shared copies is bank-conflict free.
+__host__ __device__ constexpr int line_stride(int log2n) { return (1 << log2n) + ((1 << log2n) >> 4) + 1; }
+__device__ __forceinline__ int PI(int i) { return i + (i >> 4); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by exp(-+ 2 pi i m / 16) (minus sign = forward), compile-time m
+template <int M, bool INV>
+__device__ __forceinline__ float2 mul_w16(float2 v) {
+  constexpr float c[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                          0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+  constexpr float sn[8] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                           1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+  constexpr int m = M & 15;
+  constexpr float wr = (m < 8) ? c[m] : -c[m - 8];
+  constexpr float wi0 = (m < 8) ? -sn[m] : sn[m - 8];  // forward: exp(-i t) = cos t - i sin t
+  constexpr float wi = INV ? -wi0 : wi0;
+  if (m == 0) return v;
+  return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+}
 
-// In-place (ping-pong) Stockham FFT of `nlines` lines of length N = 2^LOG2N held in shared memory with line
-// stride N+1.  tw[k] = exp(-2*pi*i*k/N).  Returns the buffer that holds the result.  All threads of the CTA
-// must call it; it ends with a __syncthreads().
-template <int LOG2N, bool INV>
-__device__ float2* fft_lines(float2* src, float2* dst, const float2* __restrict__ tw, int nlines) {
-  constexpr int N = 1 << LOG2N;
-  constexpr int LS = N + 1;
-  const int tid = threadIdx.x;
-  int n = N, s = 1, ls = 0;  // ls = log2(s)
-  while (n >= 4) {
-    const int n1 = n >> 2;
-    const int twstep = N / n;
-    constexpr int NQ = (N / 4) > 0 ? (N / 4) : 1;
-    for (int idx = tid; idx < nlines * NQ; idx += kThreads) {
-      const int line = idx / NQ, b = idx - line * NQ;
-      const int p = b >> ls, q = b & (s - 1);
-      const float2* xb = src + line * LS;
-      float2* yb = dst + line * LS;
-      const float2 a = xb[q + s * p], bb = xb[q + s * (p + n1)], c = xb[q + s * (p + 2 * n1)], d = xb[q + s * (p + 3 * n1)];
-      float2 w1 = tw[p * twstep], w2 = tw[2 * p * twstep], w3 = tw[3 * p * twstep];
-      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-      const float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(bb, d), bmd = csub(bb, d);
-      const float2 jbmd = INV ? make_float2(bmd.y, -bmd.x) : make_float2(-bmd.y, bmd.x);  // forward: +i*(b-d)
-      yb[q + s * (4 * p + 0)] = cadd(apc, bpd);
-      yb[q + s * (4 * p + 1)] = cmul(w1, csub(amc, jbmd));
-      yb[q + s * (4 * p + 2)] = cmul(w2, csub(apc, bpd));
-      yb[q + s * (4 * p + 3)] = cmul(w3, cadd(amc, jbmd));
+template <bool INV>
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+  const float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
+  const float2 jb = INV ? make_float2(bmd.y, -bmd.x) : make_float2(-bmd.y, bmd.x);  // forward: +i (b - d)
+  a = cadd(apc, bpd);
+  b = csub(amc, jb);
+  c = csub(apc, bpd);
+  d = cadd(amc, jb);
+}
+
+// R-point DFT in registers, natural order in and out (R = 2, 4, 8, 16)
+template <int R, bool INV>
+__device__ __forceinline__ void dft_reg(float2 (&v)[R]) {
+  if constexpr (R == 2) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  } else if constexpr (R == 4) {
+    dft4<INV>(v[0], v[1], v[2], v[3]);
+  } else if constexpr (R == 8) {
+    // j = j0 + 2 j1, k = 4 k0 + k1
+    float2 t0[4] = {v[0], v[2], v[4], v[6]}, t1[4] = {v[1], v[3], v[5], v[7]};
+    dft4<INV>(t0[0], t0[1], t0[2], t0[3]);
+    dft4<INV>(t1[0], t1[1], t1[2], t1[3]);
+    t1[1] = mul_w16<2, INV>(t1[1]);
+    t1[2] = mul_w16<4, INV>(t1[2]);
+    t1[3] = mul_w16<6, INV>(t1[3]);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+      v[k1] = cadd(t0[k1], t1[k1]);
+      v[4 + k1] = csub(t0[k1], t1[k1]);
     }
-    __syncthreads();
-    float2* t = src; src = dst; dst = t;
-    n >>= 2; s <<= 2; ls += 2;
+  } else {
+    // R == 16: j = j0 + 4 j1, k = 4 k0 + k1
+    float2 t[4][4];
+#pragma unroll
+    for (int j0 = 0; j0 < 4; ++j0) {
+      t[j0][0] = v[j0]; t[j0][1] = v[j0 + 4]; t[j0][2] = v[j0 + 8]; t[j0][3] = v[j0 + 12];
+      dft4<INV>(t[j0][0], t[j0][1], t[j0][2], t[j0][3]);
+    }
+    t[1][1] = mul_w16<1, INV>(t[1][1]); t[1][2] = mul_w16<2, INV>(t[1][2]); t[1][3] = mul_w16<3, INV>(t[1][3]);
+    t[2][1] = mul_w16<2, INV>(t[2][1]); t[2][2] = mul_w16<4, INV>(t[2][2]); t[2][3] = mul_w16<6, INV>(t[2][3]);
+    t[3][1] = mul_w16<3, INV>(t[3][1]); t[3][2] = mul_w16<6, INV>(t[3][2]); t[3][3] = mul_w16<9, INV>(t[3][3]);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+      dft4<INV>(t[0][k1], t[1][k1], t[2][k1], t[3][k1]);
+      v[k1] = t[0][k1]; v[4 + k1] = t[1][k1]; v[8 + k1] = t[2][k1]; v[12 + k1] = t[3][k1];
+    }
   }
-  if (n == 2) {
-    for (int idx = tid; idx < nlines * (N / 2); idx += kThreads) {
-      const int line = idx / (N / 2), q = idx - line * (N / 2);
-      const float2* xb = src + line * LS;
-      float2* yb = dst + line * LS;
-      const float2 a = xb[q], b = xb[q + s];
-      yb[q] = cadd(a, b);
-      yb[q + s] = csub(a, b);
+}
+
+// One Stockham autosort pass of radix R over LPB lines in shared memory (padded layout), butterflies in
+// registers:  y[q + s (R p + k)] = w_n^(p k) * sum_j x[q + s (p + j n/R)] w_R^(j k).
+// MUL: the inputs are multiplied by the spectrum tile `spec` (same layout) while they are read -- the
+// spectrum product of the fused forward/inverse kernel costs no extra pass.
+template <int LOG2N, int R, bool INV, bool MUL>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, float2* __restrict__ dst,
+                                              const float2* __restrict__ tw, const float2* __restrict__ spec,
+                                              int nlines, int n, int ls) {
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), NB = N / R;
+  const int s = 1 << ls, m = n / R, step = N / n;
+  for (int idx = threadIdx.x; idx < nlines * NB; idx += kThreads) {
+    const int line = idx / NB, b = idx - line * NB;
+    const int p = b >> ls, q = b & (s - 1);
+    const float2* xb = src + line * LS;
+    float2* yb = dst + line * LS;
+    float2 v[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int i = PI(q + s * (p + j * m));
+      v[j] = xb[i];
+      if (MUL) v[j] = cmul(v[j], spec[line * LS + i]);
     }
-    __syncthreads();
+    dft_reg<R, INV>(v);
+    if (m > 1) {  // twiddles w_n^(p k): one table read, the powers by (shallow) repeated multiplication
+      float2 w1 = tw[p * step];
+      if (INV) w1.y = -w1.y;
+      float2 w[R];
+      w[1] = w1;
+      if constexpr (R >= 4) { w[2] = cmul(w1, w1); w[3] = cmul(w[2], w1); }
+      if constexpr (R >= 8) {
+        w[4] = cmul(w[2], w[2]);
+        w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]);
+      }
+      if constexpr (R >= 16) {
+        w[8] = cmul(w[4], w[4]);
+        w[9] = cmul(w[8], w[1]); w[10] = cmul(w[8], w[2]); w[11] = cmul(w[8], w[3]);
+        w[12] = cmul(w[8], w[4]);
+        w[13] = cmul(w[12], w[1]); w[14] = cmul(w[12], w[2]); w[15] = cmul(w[12], w[3]);
+      }
+#pragma unroll
+      for (int k = 1; k < R; ++k) v[k] = cmul(v[k], w[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) yb[PI(q + s * (R * p + k))] = v[k];
+  }
+  __syncthreads();
+}
+
+// Full transform of `nlines` lines (ping-pong between two buffers); returns the buffer holding the result.
+// Radix schedule: 16 while >= 4 bits remain, then 8 / 4 / 2 for the rest.
+template <int LOG2N, bool INV, bool MUL>
+__device__ float2* fft_lines(float2* src, float2* dst, const float2* __restrict__ tw, const float2* __restrict__ spec,
+                             int nlines) {
+  constexpr int N = 1 << LOG2N;
+  constexpr int n16 = LOG2N / 4, rem = LOG2N % 4;
+  int n = N, ls = 0;
+  bool first = true;
+  if constexpr (n16 > 0) {
+#pragma unroll
+    for (int i = 0; i < n16; ++i) {
+      if (MUL && first) stockham_pass<LOG2N, 16, INV, true>(src, dst, tw, spec, nlines, n, ls);
+      else stockham_pass<LOG2N, 16, INV, false>(src, dst, tw, spec, nlines, n, ls);
+      first = false;
+      float2* t = src; src = dst; dst = t;
+      n >>= 4; ls += 4;
+    }
+  }
+  if constexpr (rem > 0) {
+    constexpr int R = 1 << rem;
+    if (MUL && first) stockham_pass<LOG2N, R, INV, true>(src, dst, tw, spec, nlines, n, ls);
+    else stockham_pass<LOG2N, R, INV, false>(src, dst, tw, spec, nlines, n, ls);
     float2* t = src; src = dst; dst = t;
   }
   return src;
@@ -90,7 +190,7 @@ __device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* __rest
 
 template <int LOG2N>
 __device__ __forceinline__ void zero_lines(float2* buf, int nlines) {
-  constexpr int LS = (1 << LOG2N) + 1;
+  constexpr int LS = line_stride(LOG2N);
   for (int i = threadIdx.x; i < nlines * LS; i += kThreads) buf[i] = make_float2(0.f, 0.f);
 }
 
@@ -105,7 +205,7 @@ struct TmplPassArgs {
 };
 template <int LOG2N>
 __global__ void __launch_bounds__(kThreads) k_fft_x_tmpl(const TmplPassArgs A) {
-  constexpr int N = 1 << LOG2N, LS = N + 1, LPB = lines_per_block(LOG2N);
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
   float2* b1 = sm + LPB * LS;
@@ -121,14 +221,14 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_tmpl(const TmplPassArgs A) {
   for (int i = threadIdx.x; i < nl * A.tx; i += kThreads) {
     const int line = i / A.tx, qx = i - line * A.tx;
     const long long src = (long long)(l0 + line) * A.tx + qx;
-    b0[line * LS + ((N - qx) & (N - 1))] = make_float2(t0[src], has1 ? t1[src] : 0.f);
+    b0[line * LS + PI((N - qx) & (N - 1))] = make_float2(t0[src], has1 ? t1[src] : 0.f);
   }
   __syncthreads();
-  const float2* res = fft_lines<LOG2N, false>(b0, b1, tw, nl);
+  const float2* res = fft_lines<LOG2N, false, false>(b0, b1, tw, nullptr, nl);
   float2* out = A.out + ((long long)pr * A.nlines + l0) * N;
   for (int i = threadIdx.x; i < nl * N; i += kThreads) {
     const int line = i >> LOG2N, e = i & (N - 1);
-    out[(long long)line * N + e] = res[line * LS + e];
+    out[(long long)line * N + e] = res[line * LS + PI(e)];
   }
 }
 
@@ -141,7 +241,7 @@ struct RealPassArgs {
 };
 template <int LOG2N>
 __global__ void __launch_bounds__(kThreads) k_fft_x_real(const RealPassArgs A) {
-  constexpr int N = 1 << LOG2N, LS = N + 1, LPB = lines_per_block(LOG2N);
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
   float2* b1 = sm + LPB * LS;
@@ -153,25 +253,26 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_real(const RealPassArgs A) {
   __syncthreads();
   for (int i = threadIdx.x; i < nl * A.nx; i += kThreads) {
     const int line = i / A.nx, x = i - line * A.nx;
-    b0[line * LS + x] = make_float2(A.img[(long long)(l0 + line) * A.nx + x], 0.f);
+    b0[line * LS + PI(x)] = make_float2(A.img[(long long)(l0 + line) * A.nx + x], 0.f);
   }
   __syncthreads();
-  const float2* res = fft_lines<LOG2N, false>(b0, b1, tw, nl);
+  const float2* res = fft_lines<LOG2N, false, false>(b0, b1, tw, nullptr, nl);
   float2* out = A.out + (long long)l0 * N;
   for (int i = threadIdx.x; i < nl * N; i += kThreads) {
     const int line = i >> LOG2N, e = i & (N - 1);
-    out[(long long)line * N + e] = res[line * LS + e];
+    out[(long long)line * N + e] = res[line * LS + PI(e)];
   }
 }
 
 // ---- pass B: strided lines (y or z axis).  MODE 0 forward, 1 forward * spectrum -> inverse, 2 inverse --
+// MODE 1 loops over the `batch` template pairs inside the CTA so that the spectrum tile is fetched once.
 struct StridedArgs {
   const float2* in;
   float2* out;
   long long in_sb, in_se, in_batch;    // element e of line (a,b): in[a + b*in_sb + e*in_se]
   long long out_sb, out_se, out_batch;
   int nin, flip, nout;                 // nin input entries (flipped placement if flip), first nout outputs stored
-  int na, nb;
+  int na, nb, batch;
   const float2* mul;                   // MODE 1: spectrum, same (a,b,e) addressing with mul_sb / mul_se
   long long mul_sb, mul_se;
   const float2* tw;
@@ -179,44 +280,50 @@ struct StridedArgs {
 };
 template <int LOG2N, int MODE>
 __global__ void __launch_bounds__(kThreads) k_fft_strided(const StridedArgs A) {
-  constexpr int N = 1 << LOG2N, LS = N + 1, LPB = lines_per_block(LOG2N);
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
   float2* b1 = sm + LPB * LS;
   float2* tw = sm + 2 * LPB * LS;
+  float2* spec = tw + N;  // MODE 1 only
   const int a0 = blockIdx.x * LPB, b = blockIdx.y;
   const int nl = min(LPB, A.na - a0);
-  const float2* in = A.in + (long long)blockIdx.z * A.in_batch + (long long)b * A.in_sb + a0;
-  float2* out = A.out + (long long)blockIdx.z * A.out_batch + (long long)b * A.out_sb + a0;
   load_twiddles<LOG2N>(tw, A.tw);
-  if (A.nin < N) zero_lines<LOG2N>(b0, LPB);
-  __syncthreads();
-  for (int i = threadIdx.x; i < LPB * A.nin; i += kThreads) {
-    const int al = i % LPB, e = i / LPB;  // a fastest: coalesced
-    if (al < nl) {
-      const int slot = A.flip ? ((N - e) & (N - 1)) : e;
-      b0[al * LS + slot] = in[al + (long long)e * A.in_se];
-    }
-  }
-  __syncthreads();
-  float2* res = fft_lines<LOG2N, MODE == 2>(b0, b1, tw, LPB);
   if (MODE == 1) {
-    float2* other = (res == b0) ? b1 : b0;
     const float2* mul = A.mul + (long long)b * A.mul_sb + a0;
     for (int i = threadIdx.x; i < LPB * N; i += kThreads) {
       const int al = i % LPB, e = i / LPB;
-      if (al < nl) res[al * LS + e] = cmul(res[al * LS + e], mul[al + (long long)e * A.mul_se]);
+      spec[al * LS + PI(e)] = al < nl ? mul[al + (long long)e * A.mul_se] : make_float2(0.f, 0.f);
+    }
+  }
+  const int p0 = (MODE == 1) ? 0 : blockIdx.z, p1 = (MODE == 1) ? A.batch : blockIdx.z + 1;
+  for (int pr = p0; pr < p1; ++pr) {
+    const float2* in = A.in + (long long)pr * A.in_batch + (long long)b * A.in_sb + a0;
+    float2* out = A.out + (long long)pr * A.out_batch + (long long)b * A.out_sb + a0;
+    __syncthreads();  // previous pair fully stored / twiddles + spectrum visible
+    if (A.nin < N) zero_lines<LOG2N>(b0, LPB);
+    __syncthreads();
+    for (int i = threadIdx.x; i < LPB * A.nin; i += kThreads) {
+      const int al = i % LPB, e = i / LPB;  // a fastest: coalesced
+      if (al < nl) {
+        const int slot = A.flip ? ((N - e) & (N - 1)) : e;
+        b0[al * LS + PI(slot)] = in[al + (long long)e * A.in_se];
+      }
     }
     __syncthreads();
-    res = fft_lines<LOG2N, true>(res, other, tw, LPB);
-  }
-  for (int i = threadIdx.x; i < LPB * A.nout; i += kThreads) {
-    const int al = i % LPB, e = i / LPB;
-    if (al < nl) {
-      float2 v = res[al * LS + e];
-      v.x *= A.scale;
-      v.y *= A.scale;
-      out[al + (long long)e * A.out_se] = v;
+    float2* res = fft_lines<LOG2N, MODE == 2, false>(b0, b1, tw, nullptr, LPB);
+    if (MODE == 1) {
+      float2* other = (res == b0) ? b1 : b0;
+      res = fft_lines<LOG2N, true, true>(res, other, tw, spec, LPB);
+    }
+    for (int i = threadIdx.x; i < LPB * A.nout; i += kThreads) {
+      const int al = i % LPB, e = i / LPB;
+      if (al < nl) {
+        float2 v = res[al * LS + PI(e)];
+        v.x *= A.scale;
+        v.y *= A.scale;
+        out[al + (long long)e * A.out_se] = v;
+      }
     }
   }
 }
@@ -232,7 +339,7 @@ struct FinalArgs {
 };
 template <int LOG2N>
 __global__ void __launch_bounds__(kThreads) k_fft_x_final(const FinalArgs A) {
-  constexpr int N = 1 << LOG2N, LS = N + 1, LPB = lines_per_block(LOG2N);
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
   float2* b1 = sm + LPB * LS;
@@ -245,10 +352,10 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_final(const FinalArgs A) {
   const float2* in = A.in + ((long long)pr * A.nlines + l0) * N;
   for (int i = threadIdx.x; i < nl * N; i += kThreads) {
     const int line = i >> LOG2N, e = i & (N - 1);
-    b0[line * LS + e] = in[(long long)line * N + e];
+    b0[line * LS + PI(e)] = in[(long long)line * N + e];
   }
   __syncthreads();
-  const float2* res = fft_lines<LOG2N, true>(b0, b1, tw, nl);
+  const float2* res = fft_lines<LOG2N, true, false>(b0, b1, tw, nullptr, nl);
   const int r0 = 2 * pr, r1 = 2 * pr + 1;
   const bool has1 = r1 < A.R;
   const double b20 = A.ep.b2[r0], b21 = has1 ? A.ep.b2[r1] : 0.0;
@@ -256,7 +363,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_final(const FinalArgs A) {
   for (int i = threadIdx.x; i < nl * A.nxo; i += kThreads) {
     const int line = i / A.nxo, x = i - line * A.nxo;
     const long long p = (long long)(l0 + line) * A.nxo + x;
-    float2 ab = res[line * LS + x];
+    float2 ab = res[line * LS + PI(x)];
     if (A.ep.round_to_int) { ab.x = rintf(ab.x); ab.y = rintf(ab.y); }
     const double a2 = A.ep.a2 ? (double)__ldg(A.ep.a2 + p) : 0.0;
     const bool dis = A.ep.disabled && A.ep.disabled[p];
@@ -297,9 +404,9 @@ static int ilog2_ceil(int n) {
   while ((1 << l) < n) ++l;
   return l;
 }
-static size_t smem_bytes(int log2n) {
+static size_t smem_bytes(int log2n, bool with_spectrum = false) {
   const int N = 1 << log2n;
-  return (size_t)(2 * lines_per_block(log2n) * (N + 1) + N) * sizeof(float2);
+  return (size_t)((with_spectrum ? 3 : 2) * lines_per_block(log2n) * line_stride(log2n) + N) * sizeof(float2);
 }
 
 struct Plan {
@@ -352,10 +459,12 @@ static cudaError_t launch_real(const RealPassArgs& a, int log2n, cudaStream_t s)
   return cudaGetLastError();
 }
 template <int MODE>
-static cudaError_t launch_strided(const StridedArgs& a, int log2n, int batch, cudaStream_t s) {
-  const size_t sm = smem_bytes(log2n);
+static cudaError_t launch_strided(const StridedArgs& a_in, int log2n, int batch, cudaStream_t s) {
+  const size_t sm = smem_bytes(log2n, MODE == 1);
   const int LPB = lines_per_block(log2n);
-  dim3 grid((a.na + LPB - 1) / LPB, a.nb, batch);
+  StridedArgs a = a_in;
+  a.batch = batch;
+  dim3 grid((a.na + LPB - 1) / LPB, a.nb, MODE == 1 ? 1 : batch);  // the fused kernel loops over the pairs itself
   FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_strided<L, MODE>, sm); if (e != cudaSuccess) return e;
                         k_fft_strided<L, MODE><<<grid, kThreads, sm, s>>>(a); });
   return cudaGetLastError();
@@ -522,10 +631,10 @@ double correlate_bytes(const Plan* p, int R) {
   const double Nx = p->Nx, Ny = p->Ny, Nz = p->Nz;
   double b = 4.0 * R * p->tx * p->ty * p->tz + npair * c * p->tz * p->ty * Nx;           // pass A
   if (p->lz == 0) {
-    b += npair * c * (p->ty * Nx + Ny * Nx + p->nyo * Nx);                                 // fused y
+    b += npair * c * (p->ty * Nx + p->nyo * Nx) + c * Ny * Nx;                             // fused y (+ spectrum once)
   } else {
     b += npair * c * (p->tz * p->ty * Nx + p->tz * Ny * Nx);                               // forward y
-    b += npair * c * (p->tz * Ny * Nx + Nz * Ny * Nx + p->nzo * Ny * Nx);                  // fused z (+ spectrum)
+    b += npair * c * (p->tz * Ny * Nx + p->nzo * Ny * Nx) + c * Nz * Ny * Nx;              // fused z (+ spectrum once)
     b += npair * c * (p->nzo * Ny * Nx + (double)p->nzo * p->nyo * Nx);                    // inverse y
   }
   b += npair * c * (double)p->nzo * p->nyo * Nx + (double)R * 4.0 * p->npos + 4.0 * p->npos;  // final + maps + A2
