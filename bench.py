@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=0, help="tiles in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rb", type=int, default=0)
+    ap.add_argument("--cut", default="auto", choices=["auto", "host", "device"])
     ap.add_argument("--fft", type=int, default=0, help="-1 direct kernels only, 0 auto crossover (default), 1 always FFT")
     args = ap.parse_args()
 
@@ -242,7 +243,7 @@ def main():
 
     def step(i):
         t0 = time.perf_counter()
-        out, ex = iqb200.iqsim(ti, tilesize, rng=np.random.default_rng(seed0 + i), device=local, nthreads=nthreads, fft=args.fft,
+        out, ex = iqb200.iqsim(ti, tilesize, rng=np.random.default_rng(seed0 + i), device=local, nthreads=nthreads, fft=args.fft, cut=args.cut,
                                return_stats=True, return_picks=True, **kw)
         chk = float(sum(float(r[0, 0, 0] if r.ndim == 3 else r[0, 0]) for r in out))  # touch the result on the host
         return time.perf_counter() - t0, ex, chk

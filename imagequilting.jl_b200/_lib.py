@@ -38,6 +38,10 @@ class IqResult(C.Structure):
                 ("relax_iters", C.c_int32), ("dmin", C.c_float)]
 
 
+class IqCutTask(C.Structure):
+    _fields_ = [("A", c_double_p), ("B", c_double_p), ("sz", C.c_int32 * 3), ("dim", C.c_int32), ("keep", c_u8_p)]
+
+
 class IqhDesc(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("ti_size", C.c_int64 * 3), ("tile_size", C.c_int64 * 3),
                 ("ovl_size", C.c_int64 * 3), ("ntiles", C.c_int64 * 3), ("pad_size", C.c_int64 * 3),
@@ -45,7 +49,7 @@ class IqhDesc(C.Structure):
                 ("aux", C.POINTER(c_float_p)), ("auxti", C.POINTER(c_float_p)),
                 ("hard_has", c_u8_p), ("hard_val", c_float_p), ("path", c_i64_p), ("npath", C.c_int64),
                 ("tol", C.c_double), ("nreal", C.c_int32), ("u", c_double_p), ("debug", C.c_int32),
-                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32), ("ngroups", C.c_int32), ("fft_mode", C.c_int32)]
+                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32), ("ngroups", C.c_int32), ("cut_mode", C.c_int32), ("fft_mode", C.c_int32)]
 
 
 class IqhStats(C.Structure):
@@ -69,6 +73,7 @@ SYMBOLS = {
                                    C.POINTER(IqResult)]),
     "iq_distance": (C.c_int32, [C.c_void_p, C.c_int32, c_u8_p, C.POINTER(IqTile), c_float_p]),
     "iq_fetch_tile": (C.c_int32, [C.c_void_p, C.c_int64, c_float_p]),
+    "iq_cut_batch": (C.c_int32, [C.c_void_p, C.POINTER(IqCutTask), C.c_int32, c_i32_p]),
     "iq_last_search_stats": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
     "iq_last_search_path": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p, c_double_p, c_double_p]),
     "iq_last_search_kernel_ms": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),

@@ -21,7 +21,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import (IqCtxDesc, IqhDesc, IqhStats, IqResult, IqTile, c_double_p, c_float_p, c_i32_p, c_i64_p,
+from ._lib import (IqCtxDesc, IqCutTask, IqhDesc, IqhStats, IqResult, IqTile, c_double_p, c_float_p, c_i32_p, c_i64_p,
                    c_u8_p, check, lib)
 
 
@@ -150,7 +150,7 @@ def _genpath(rng, extent, kind, datainds):
 # iqsim
 # --------------------------------------------------------------------------------------
 def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None, tol=0.1, path="raster", nreal=1,
-          debug=False, showprogress=False, rng=None, device=0, batch=0, nthreads=0, ngroups=0, fft=0, return_stats=False,
+          debug=False, showprogress=False, rng=None, device=0, batch=0, nthreads=0, ngroups=0, fft=0, cut="auto", return_stats=False,
           return_picks=False, _path_override=None, _uniforms=None, _real_range=None):
     """Image quilting simulation with the GPU distance search (see module docstring)."""
     timg = trainimg if isinstance(trainimg, np.ma.MaskedArray) else np.asarray(trainimg)
@@ -263,6 +263,7 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     d.u = _ptr(u, c_double_p)
     d.debug, d.device, d.batch, d.nthreads = int(bool(debug)), int(device), int(batch), int(nthreads)
     d.ngroups = int(ngroups)
+    d.cut_mode = {"auto": 0, "host": 1, "device": 2}[cut]  # where the boundary cuts run (host = reference behaviour)
     d.fft_mode = int(fft)  # distance path: -1 direct kernels only, 0 measured crossover, 1 FFT whenever possible
     stats = IqhStats()
     if nvis > 0:
@@ -432,6 +433,26 @@ class SearchContext:
             out.append(dict(idx=idx, prob=prob, picked=int(res[i].picked), relax_iters=int(res[i].relax_iters),
                             dmin=float(res[i].dmin)))
         return out
+
+    def cut_batch(self, slabs):
+        """Device boundary cuts (iq_cut_batch): slabs = [(A, B, dim), ...] -> ([keep masks], [sweeps])."""
+        n = len(slabs)
+        arr = (IqCutTask * n)()
+        keepalive, outs = [], []
+        for i, (A, B, dim) in enumerate(slabs):
+            A = _f(A, np.float64)
+            B = _f(B, np.float64)
+            assert A.shape == B.shape, "arrays must have the same size for cut"
+            keep = np.zeros(A.shape, dtype=np.uint8, order="F")
+            keepalive += [A, B]
+            outs.append(keep)
+            arr[i].A, arr[i].B, arr[i].keep = _ptr(A, c_double_p), _ptr(B, c_double_p), _ptr(keep, c_u8_p)
+            for d in range(3):
+                arr[i].sz[d] = A.shape[d] if d < A.ndim else 1
+            arr[i].dim = int(dim)
+        iters = np.zeros(n, dtype=np.int32)
+        check(lib().iq_cut_batch(self._h, arr, n, _ptr(iters, c_i32_p)))
+        return [k.astype(bool) for k in outs], iters.tolist()
 
     def fetch_tile(self, pos):
         out = np.zeros(self.tilesize, dtype=np.float32, order="F")

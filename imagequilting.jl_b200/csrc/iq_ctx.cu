@@ -20,6 +20,7 @@
 #include "../../include/iqb200.h"
 #include "iq_internal.h"
 #include "iq_fft.h"
+#include "iq_cut.h"
 
 namespace {
 
@@ -193,6 +194,10 @@ struct iq_ctx {
   double* d_prob = nullptr;               // [max_batch][kTauMax]
   double* h_prob = nullptr;               // pinned mirror
   int tau_device = 1;                     // 0 = always evaluate the tau model on the host
+  char* h_cut = nullptr;  // pinned staging of the device boundary cut (slabs, masks, task records)
+  char* d_cut = nullptr;
+  size_t cut_cap = 0;
+  iqcut::Work cut_work;   // host fallback scratch
   int* d_shifts = nullptr;
   int nshift = 0;
   float* d_fetch = nullptr;
@@ -964,6 +969,8 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   if (c->h_cand_val) cudaFreeHost(c->h_cand_val);
   cudaFree(c->d_shifts);
   cudaFree(c->d_fetch);
+  if (c->h_cut) cudaFreeHost(c->h_cut);
+  cudaFree(c->d_cut);
   cudaFree(c->d_rank);
   cudaFree(c->d_colsum);
   cudaFree(c->d_prob);
@@ -1203,6 +1210,108 @@ int32_t iq_fetch_tile(iq_ctx* c, int64_t pos, float* out_tile) {
   c->launches++;
   CK(cudaMemcpyAsync(out_tile, c->d_fetch, (size_t)c->tilevol * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return IQ_OK;
+}
+
+int32_t iq_cut_batch(iq_ctx* c, const iq_cut_task* tasks, int32_t ntask, int32_t* iters) {
+  if (!c || !tasks || ntask < 0) return fail(IQ_ERR_INVALID, "iq_cut_batch: bad argument");
+  if (ntask == 0) return IQ_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t smem_limit = 220 * 1024;
+  // layout of the staging block: [task records][iters][per device task: A, B (doubles), keep (bytes)]
+  struct Plan { int dev; int n0, n1, L, da, db; size_t offA, offB, offK; long long nv; };
+  std::vector<Plan> plan(ntask);
+  size_t off = ((size_t)ntask * (sizeof(iq::CutTask) + sizeof(int)) + 255) & ~(size_t)255;
+  size_t smem = 0;
+  int ndev = 0;
+  for (int t = 0; t < ntask; ++t) {
+    const iq_cut_task& T = tasks[t];
+    if (!T.A || !T.B || !T.keep || T.dim < 0 || T.dim > 2 || T.sz[T.dim] < 2)
+      return fail(IQ_ERR_INVALID, "iq_cut_batch: task %d is malformed", t);
+    Plan& P = plan[t];
+    P.da = T.dim == 0 ? 1 : 0;
+    P.db = T.dim == 2 ? 1 : 2;
+    P.n0 = T.sz[P.da]; P.n1 = T.sz[P.db]; P.L = T.sz[T.dim];
+    P.nv = (long long)T.sz[0] * T.sz[1] * T.sz[2];
+    const size_t need = P.L >= 3 ? iq::graphcut_smem(P.n0, P.n1, P.L) : 0;
+    P.dev = (P.L >= 3 && need <= smem_limit && (long long)(P.L - 2) * P.n0 * P.n1 <= 4096) ? 1 : 0;
+    if (P.dev) {
+      smem = std::max(smem, need);
+      P.offA = off; off += (size_t)P.nv * 8;
+      P.offB = off; off += (size_t)P.nv * 8;
+      P.offK = off; off += ((size_t)P.nv + 255) & ~(size_t)255;
+      ++ndev;
+    }
+  }
+  if (ndev > 0) {
+    if (off > c->cut_cap) {
+      if (c->h_cut) cudaFreeHost(c->h_cut);
+      cudaFree(c->d_cut);
+      c->h_cut = nullptr; c->d_cut = nullptr; c->cut_cap = 0;
+      const size_t cap = off * 2;
+      CK(cudaMallocHost((void**)&c->h_cut, cap));
+      CK(cudaMalloc((void**)&c->d_cut, cap));
+      c->cut_cap = cap;
+    }
+    iq::CutTask* recs = (iq::CutTask*)c->h_cut;
+    int* d_iters = (int*)(c->d_cut + (size_t)ntask * sizeof(iq::CutTask));
+    int k = 0;
+    for (int t = 0; t < ntask; ++t) {
+      const Plan& P = plan[t];
+      if (!P.dev) continue;
+      const iq_cut_task& T = tasks[t];
+      double* a = (double*)(c->h_cut + P.offA);
+      double* b = (double*)(c->h_cut + P.offB);
+      // re-layout: cut dimension slowest
+      const long long st[3] = {1, T.sz[0], (long long)T.sz[0] * T.sz[1]};
+      long long o = 0;
+      for (int kk = 0; kk < P.L; ++kk)
+        for (int bb = 0; bb < P.n1; ++bb)
+          for (int aa = 0; aa < P.n0; ++aa, ++o) {
+            const long long src = kk * st[T.dim] + bb * st[P.db] + aa * st[P.da];
+            a[o] = T.A[src];
+            b[o] = T.B[src];
+          }
+      iq::CutTask& R = recs[k];
+      R.A = (const double*)(c->d_cut + P.offA);
+      R.B = (const double*)(c->d_cut + P.offB);
+      R.keep = (unsigned char*)(c->d_cut + P.offK);
+      R.n0 = P.n0; R.n1 = P.n1; R.L = P.L;
+      R.iters = d_iters + k;
+      ++k;
+    }
+    CK(cudaMemcpyAsync(c->d_cut, c->h_cut, off, cudaMemcpyHostToDevice, c->stream));
+    CK(iq::launch_graphcut((const iq::CutTask*)c->d_cut, ndev, smem, c->stream));
+    c->launches++;
+    CK(cudaMemcpyAsync(c->h_cut, c->d_cut, off, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int* h_iters = (const int*)(c->h_cut + (size_t)ntask * sizeof(iq::CutTask));
+    k = 0;
+    for (int t = 0; t < ntask; ++t) {
+      Plan& P = plan[t];
+      if (!P.dev) continue;
+      const iq_cut_task& T = tasks[t];
+      if (h_iters[k] < 0) {
+        P.dev = 0;  // iteration cap hit (never observed): recompute on the host below
+      } else {
+        const unsigned char* kp = (const unsigned char*)(c->h_cut + P.offK);
+        const long long st[3] = {1, T.sz[0], (long long)T.sz[0] * T.sz[1]};
+        long long o = 0;
+        for (int kk = 0; kk < P.L; ++kk)
+          for (int bb = 0; bb < P.n1; ++bb)
+            for (int aa = 0; aa < P.n0; ++aa, ++o) T.keep[kk * st[T.dim] + bb * st[P.db] + aa * st[P.da]] = kp[o];
+        if (iters) iters[t] = h_iters[k];
+      }
+      ++k;
+    }
+  }
+  for (int t = 0; t < ntask; ++t) {
+    if (plan[t].dev) continue;
+    const iq_cut_task& T = tasks[t];
+    const int sz[3] = {T.sz[0], T.sz[1], T.sz[2]};
+    iqcut::graphcut(T.A, T.B, sz, T.dim, T.keep, c->cut_work);
+    if (iters) iters[t] = 0;
+  }
   return IQ_OK;
 }
 

@@ -1,0 +1,241 @@
+// iq_cutgpu.cu -- boundary cut on the device: one CTA per overlap slab, whole problem in shared memory.
+//
+// Same graph and same answer as the host routine iq_cut.cpp (restating /root/reference/src/graphcut.jl:5-84):
+// the keep-mask is the complement of "can still reach the sink slice in the residual graph of a maximum
+// flow", a set that does not depend on which maximum (pre)flow is found.  The reference stays on the host
+// (GraphsFlows' Boykov-Kolmogorov, graphcut.jl:73); this kernel exists because a multi-GPU box has only a
+// few host cores per GPU and the host cut then bounds the whole simulation.
+//
+// Algorithm: push-relabel, phase 1 only (a maximum preflow already fixes the sink side), made DETERMINISTIC:
+//   * slab re-laid out with the cut dimension slowest, so the source / sink slices are the first / last
+//     layer and only the (L-2) inner layers are unknowns; all their state (6 residuals, excess, height) lives
+//     in shared memory (61 B per voxel -> up to ~3600 inner voxels per CTA);
+//   * voxels are 7-coloured by (a + 2b + 3k) mod 7, so that a voxel and its six neighbours all differ and two
+//     voxels of one colour never share a neighbour.  A sweep discharges the active voxels colour by colour
+//     (push along every admissible arc, relabel if excess is left): no two concurrent voxels touch the same
+//     state, so there are no atomics and the floating-point result is independent of thread scheduling;
+//   * every 32 sweeps an exact global relabel (BFS distances to the sink slice as the fixed point of a
+//     chaotic relaxation), which also parks voxels that cannot reach the sink;
+//   * the final global relabel IS the answer: height < HMAX <=> can reach the sink.
+// FP64 throughout, capacities computed with the reference's formula and operation order
+// ((Du+Dv)/(gAu+gAv+gBu+gBv+eps), graphcut.jl:52) with explicit round-to-nearest intrinsics (no contraction).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdio>
+
+#include "iq_internal.h"
+
+namespace iq {
+
+constexpr int kCutThreads = 1024;
+constexpr int kCutBytesPerNode = 6 * 8 + 8 + 4 + 1;  // residuals, excess, height, topology byte
+
+__device__ __forceinline__ double edge_cap(const double* __restrict__ A, const double* __restrict__ B, int lo, int off,
+                                           bool has_next) {
+  const int v = lo + off;
+  const double Du = fabs(__dsub_rn(A[lo], B[lo])), Dv = fabs(__dsub_rn(A[v], B[v]));
+  const double gAu = fabs(__dsub_rn(A[v], A[lo])), gBu = fabs(__dsub_rn(B[v], B[lo]));
+  double gAv = gAu, gBv = gBu;
+  if (has_next) {
+    const int x = v + off;
+    gAv = fabs(__dsub_rn(A[x], A[v]));
+    gBv = fabs(__dsub_rn(B[x], B[v]));
+  }
+  const double den = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(gAu, gAv), gBu), gBv), 2.220446049250313e-16);
+  return __ddiv_rn(__dadd_rn(Du, Dv), den);
+}
+
+// topology byte of an inner voxel: bits 0..5 = the neighbour in direction dir is an inner voxel,
+// bit 6 = direction 4 (+cut axis) leads into the sink slice, bit 7 = checkerboard colour
+constexpr unsigned kToSink = 64u, kColour = 128u;
+
+__global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* tasks) {
+  const CutTask T = tasks[blockIdx.x];
+  const int n0 = T.n0, n1 = T.n1, L = T.L;
+  const int P = n0 * n1, nfree = (L - 2) * P;
+  const double* __restrict__ A = T.A;
+  const double* __restrict__ B = T.B;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* r = reinterpret_cast<double*>(smraw);          // [6][nfree]
+  double* e = r + 6 * (size_t)nfree;                     // [nfree]
+  int* h = reinterpret_cast<int*>(e + nfree);            // [nfree]
+  unsigned char* topo = reinterpret_cast<unsigned char*>(h + nfree);  // [nfree]
+  const int rows = n1 * (L - 2), m7 = (n0 + 6) / 7, items = rows * m7;
+  unsigned short* clist = reinterpret_cast<unsigned short*>(topo + ((nfree + 3) & ~3));  // [7][items] voxel of item or 0xffff
+  const int tid = threadIdx.x;
+  const int HMAX = nfree + 2;
+  const int off[6] = {1, -1, n0, -n0, P, -P};
+
+  // ---- capacities, topology and initial preflow (arcs out of the source slice are saturated) ----
+  for (int i = tid; i < nfree; i += kCutThreads) {
+    const int u = i + P;
+    const int a = i % n0, b = (i / n0) % n1, k = i / P + 1;
+    const int c3[3] = {a, b, k}, sz3[3] = {n0, n1, L};
+    double ex = 0.0;
+    unsigned tp = ((a + b + k) & 1) ? kColour : 0u;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double cp = 0.0;  // arc towards +d
+      if (c3[d] + 1 < sz3[d]) cp = edge_cap(A, B, u, off[2 * d], c3[d] + 2 < sz3[d]);
+      r[(2 * d) * nfree + i] = cp;
+      double cm = 0.0;  // arc towards -d (capacity defined from the lower voxel)
+      if (c3[d] > 0) cm = edge_cap(A, B, u - off[2 * d], off[2 * d], c3[d] + 1 < sz3[d]);
+      if (d == 2 && k == 1) { ex = cm; cm = 0.0; }  // from the source slice: saturated, never pushed back
+      r[(2 * d + 1) * nfree + i] = cm;
+      if (d < 2) {
+        if (c3[d] + 1 < sz3[d]) tp |= 1u << (2 * d);
+        if (c3[d] > 0) tp |= 1u << (2 * d + 1);
+      } else {
+        if (k + 1 < L - 1) tp |= 1u << 4; else tp |= kToSink;
+        if (k > 1) tp |= 1u << 5;
+      }
+    }
+    e[i] = ex;
+    h[i] = HMAX;
+    topo[i] = (unsigned char)tp;
+  }
+  // work items of colour c: voxels with (a + 2b + 3k) mod 7 == c, enumerated row by row
+  for (int w = tid; w < 7 * items; w += kCutThreads) {
+    const int colour = w / items, ww = w - colour * items;
+    const int row = ww / m7, j = ww - row * m7;
+    const int b = row % n1, kk = row / n1;
+    const int a = (((colour - 2 * b - 3 * kk) % 7) + 7) % 7 + 7 * j;
+    clist[w] = (a < n0) ? (unsigned short)(row * n0 + a) : (unsigned short)0xffff;
+  }
+  __syncthreads();
+
+  // Exact heights = BFS distance to the sink slice over residual arcs i -> v, computed as the fixed point of
+  // h[i] = min(h[i], 1 + min_v h[v]) by chaotic in-place relaxation (the fixed point is unique, so the result
+  // does not depend on the update order; in-place updates propagate several levels per pass).
+  auto global_relabel = [&]() {
+    for (int i = tid; i < nfree; i += kCutThreads) h[i] = ((topo[i] & kToSink) && r[4 * nfree + i] > 0.0) ? 1 : HMAX;
+    __syncthreads();
+    for (;;) {
+      int changed = 0;
+      for (int i = tid; i < nfree; i += kCutThreads) {
+        const unsigned tp = topo[i];
+        int best = h[i];
+#pragma unroll
+        for (int dir = 0; dir < 6; ++dir)
+          if ((tp >> dir) & 1u) {
+            if (r[dir * nfree + i] > 0.0) best = min(best, ((volatile int*)h)[i + off[dir]] + 1);
+          }
+        if (best < h[i]) { ((volatile int*)h)[i] = best; changed = 1; }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+  };
+#ifdef IQ_CUT_PROFILE
+  long long t_push = 0, t_rel = 0, t_glob = 0, t0 = clock64();
+  int nglob = 1;
+#endif
+  global_relabel();
+#ifdef IQ_CUT_PROFILE
+  t_glob += clock64() - t0;
+#endif
+
+  int iter = 0;
+  const int max_iter = 200000;
+  // 7-colouring (a + 2b + 3k) mod 7: a voxel and its six neighbours all have different colours, so two voxels
+  // of one colour never share a neighbour.  All voxels of a colour can therefore be DISCHARGED at once (push
+  // along every admissible arc, then relabel if excess is left) without atomics and with a result that does
+  // not depend on thread scheduling; colours are processed one after the other (Gauss-Seidel across colours).
+  for (;; ++iter) {
+#ifdef IQ_CUT_PROFILE
+    long long ta = clock64();
+#endif
+    int active = 0;
+#pragma unroll 1
+    for (int colour = 0; colour < 7; ++colour) {
+      const unsigned short* cl = clist + colour * items;
+      for (int w = tid; w < items; w += kCutThreads) {
+        const int i = cl[w];
+        if (i == 0xffff) continue;
+        double ex = e[i];
+        if (!(ex > 0.0)) continue;
+        int hi = h[i];
+        if (hi >= HMAX) continue;
+        const unsigned tp = topo[i];
+        // fetch the six residuals and neighbour heights first (independent loads), then discharge from registers
+        double rc[6];
+        int hv[6];
+#pragma unroll
+        for (int dir = 0; dir < 6; ++dir) {
+          const bool inner = (tp >> dir) & 1u;
+          const bool sink = (dir == 4) && (tp & kToSink);
+          rc[dir] = (inner || sink) ? r[dir * nfree + i] : 0.0;
+          hv[dir] = sink ? 0 : (inner ? h[i + off[dir]] : HMAX);
+        }
+        int mh = HMAX;  // lowest neighbour over the arcs that still have residual capacity after the pushes
+#pragma unroll
+        for (int dir = 0; dir < 6; ++dir) {
+          if (!(rc[dir] > 0.0)) continue;
+          if (ex > 0.0 && hi == hv[dir] + 1) {
+            const double d = fmin(ex, rc[dir]);
+            rc[dir] = __dsub_rn(rc[dir], d);
+            ex = __dsub_rn(ex, d);
+            r[dir * nfree + i] = rc[dir];
+            if (!((dir == 4) && (tp & kToSink))) {
+              const int v = i + off[dir];
+              r[(dir ^ 1) * nfree + v] = __dadd_rn(r[(dir ^ 1) * nfree + v], d);
+              e[v] = __dadd_rn(e[v], d);
+            }
+          }
+          if (rc[dir] > 0.0) mh = min(mh, hv[dir]);
+        }
+        e[i] = ex;
+        if (ex > 0.0) {
+          if (mh + 1 > hi) hi = min(mh + 1, HMAX);
+          h[i] = hi;
+          if (hi < HMAX) active = 1;
+        }
+      }
+      __syncthreads();
+    }
+#ifdef IQ_CUT_PROFILE
+    long long tb = clock64(); t_push += tb - ta;
+#endif
+    // excess may also sit on voxels that received it after their own colour was processed
+    for (int i = tid; i < nfree && !active; i += kCutThreads)
+      if (e[i] > 0.0 && h[i] < HMAX) active = 1;
+    const int any = __syncthreads_or(active);
+#ifdef IQ_CUT_PROFILE
+    long long tc = clock64(); t_rel += tc - tb;
+#endif
+    if (!any || iter >= max_iter) break;
+    if ((iter & 31) == 31) {
+      global_relabel();
+#ifdef IQ_CUT_PROFILE
+      t_glob += clock64() - tc; ++nglob;
+#endif
+    }
+  }
+  global_relabel();
+
+  // ---- keep mask in the kernel's layout: source slice 1, sink slice 0, inner voxels = cannot reach the sink ----
+  unsigned char* keep = T.keep;
+  for (int i = tid; i < P; i += kCutThreads) {
+    keep[i] = 1;
+    keep[(L - 1) * P + i] = 0;
+  }
+  for (int i = tid; i < nfree; i += kCutThreads) keep[P + i] = (h[i] >= HMAX) ? 1 : 0;
+  if (tid == 0 && T.iters) *T.iters = (iter >= max_iter) ? -1 : iter;
+#ifdef IQ_CUT_PROFILE
+  if (tid == 0 && blockIdx.x == 0) printf("cut nfree %d sweeps %d: cycles push %lld relabel %lld global %lld (n=%d) total %lld\n", nfree, iter, t_push, t_rel, t_glob, nglob, clock64() - t0);
+#endif
+}
+
+size_t graphcut_smem(int n0, int n1, int L) {
+  const size_t nfree = (size_t)(L - 2) * n0 * n1;
+  const size_t items = (size_t)n1 * (L - 2) * ((n0 + 6) / 7);
+  return nfree * (kCutBytesPerNode - 1) + ((nfree + 3) & ~(size_t)3) + 7 * items * sizeof(unsigned short) + 16;
+}
+
+cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s) {
+  cudaError_t err = cudaFuncSetAttribute(k_graphcut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  k_graphcut<<<ntask, kCutThreads, smem, s>>>(d_tasks);
+  return cudaGetLastError();
+}
+
+}  // namespace iq

@@ -129,6 +129,8 @@ struct Group {
   std::vector<int64_t> picked;
   std::vector<double> ustep;
   std::vector<std::vector<uint8_t>> keepbuf;
+  std::vector<std::vector<double>> slabA, slabB;  // device cut: gathered slabs
+  std::vector<iq_cut_task> cut_tasks;
   std::unique_ptr<Latch> latch{new Latch()};
   std::atomic<int> cuts_left{0}, pastes_left{0};
   clk::time_point cut_t0;
@@ -388,6 +390,44 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
         }
       });
   };
+  // few host threads per GPU (multi-GPU nodes): the cuts of a step run on the device instead
+  const bool device_cut = D->cut_mode == 2 || (D->cut_mode == 0 && nthreads < 6);
+  std::atomic<int> cut_error{IQ_OK};
+  auto device_cut_job = [&](Group& g) {
+    const int nslab = (int)g.slabs.size();
+    const int ntask = g.R * nslab;
+    if ((int)g.slabA.size() < ntask) { g.slabA.resize(ntask); g.slabB.resize(ntask); }
+    g.cut_tasks.resize(ntask);
+    const int* start = g.start;
+    for (int task = 0; task < ntask; ++task) {
+      const int r = task / nslab;
+      const Slab& s = g.slabs[task % nslab];
+      const double* grid = out_grids + (size_t)(g.r0 + r) * G.padvol;
+      const int64_t rind = g.picked[r];
+      const int rs[3] = {(int)(rind % G.dist[0]), (int)((rind / G.dist[0]) % G.dist[1]),
+                         (int)(rind / ((long long)G.dist[0] * G.dist[1]))};
+      const int nv = s.sz[0] * s.sz[1] * s.sz[2];
+      g.slabA[task].resize(nv);
+      g.slabB[task].resize(nv);
+      g.keepbuf[task].resize(nv);
+      int i = 0;
+      for (int z = 0; z < s.sz[2]; ++z)
+        for (int y = 0; y < s.sz[1]; ++y) {
+          const int qy = s.lo[1] + y, qz = s.lo[2] + z;
+          const double* ga = grid + ((long long)(start[2] + qz) * pad[1] + (start[1] + qy)) * pad[0] + start[0] + s.lo[0];
+          const double* gb = D->ti + ((long long)(rs[2] + qz) * n[1] + (rs[1] + qy)) * n[0] + rs[0] + s.lo[0];
+          for (int x = 0; x < s.sz[0]; ++x, ++i) { g.slabA[task][i] = ga[x]; g.slabB[task][i] = gb[x]; }
+        }
+      iq_cut_task& T = g.cut_tasks[task];
+      T.A = g.slabA[task].data();
+      T.B = g.slabB[task].data();
+      T.sz[0] = s.sz[0]; T.sz[1] = s.sz[1]; T.sz[2] = s.sz[2];
+      T.dim = s.d;
+      T.keep = g.keepbuf[task].data();
+    }
+    const int rcc = iq_cut_batch(g.ctx, g.cut_tasks.data(), ntask, nullptr);
+    if (rcc != IQ_OK) cut_error.store(rcc);
+  };
   auto submit_cut = [&](Group& g) {
     const int nslab = (int)g.slabs.size();
     const int ntask = g.R * nslab;
@@ -396,6 +436,13 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     g.cut_t0 = clk::now();
     Group* gp = &g;
     if (ntask == 0) { start_pastes(gp); return; }
+    if (device_cut) {
+      pool.push([&, gp](int) {
+        device_cut_job(*gp);
+        start_pastes(gp);
+      });
+      return;
+    }
     g.cuts_left.store(ntask);
     for (int task = 0; task < ntask; ++task)
       pool.push([&, gp, task](int tid) {
@@ -416,6 +463,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     }
   }
   for (auto& g : groups) g.latch->wait();
+  if (rc == IQ_OK && cut_error.load() != IQ_OK) rc = cut_error.load();
   double search_ms = 0, search_dev_ms = 0, cut_ms = 0, dist_ms = 0;
   int64_t launches = 0, dist_launches = 0, ncand = 0;
   for (auto& g : groups) {

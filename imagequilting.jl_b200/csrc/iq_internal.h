@@ -85,6 +85,17 @@ struct PickJob {
   long long cap;
 };
 
+// One boundary cut for the device kernel (iq_cutgpu.cu): slabs laid out with the cut dimension slowest.
+struct CutTask {
+  const double* A;      // already pasted content, [L][n1][n0]
+  const double* B;      // new patch, same layout
+  unsigned char* keep;  // out: 1 = keep the already pasted voxel
+  int n0, n1, L;
+  int* iters;           // out (optional): push-relabel sweeps used, -1 = iteration cap hit
+};
+size_t graphcut_smem(int n0, int n1, int L);
+cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s);
+
 // ---- launch wrappers (iq_kernels.cu) -------------------------------------------------
 cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
 cudaError_t launch_dist_flat(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);

@@ -122,6 +122,21 @@ int32_t iq_distance(iq_ctx* ctx, int32_t which, const uint8_t* ovlmask, const iq
  * distance map (view_kernel, src/utils.jl:63-67). */
 int32_t iq_fetch_tile(iq_ctx* ctx, int64_t pos, float* out_tile);
 
+/* Optional device boundary cut (the reference keeps graphcut on the host, src/graphcut.jl:5-84; this entry
+ * exists because a multi-GPU node has few host cores per GPU).  Each task is one overlap slab: A = content
+ * already pasted, B = new patch, both column-major with size sz (unused dims = 1), cut along `dim`;
+ * keep[i] = 1 where the pasted voxel is kept (exactly graphcut(A, B, dim), same answer as the host routine
+ * iqh_graphcut on well-conditioned slabs).  Slabs too large for the shared-memory kernel are cut on the host.
+ * iters (may be NULL) receives the number of push-relabel sweeps per task (0 = host path). */
+typedef struct iq_cut_task {
+  const double* A;
+  const double* B;
+  int32_t sz[3];
+  int32_t dim;
+  uint8_t* keep;
+} iq_cut_task;
+int32_t iq_cut_batch(iq_ctx* ctx, const iq_cut_task* tasks, int32_t ntask, int32_t* iters);
+
 /* Timing hooks for benchmarks: device time (ms, CUDA events on the context's stream) and number
  * of kernels launched by the most recent iq_search* call. */
 int32_t iq_last_search_stats(const iq_ctx* ctx, double* device_ms, int64_t* kernel_launches);

@@ -48,6 +48,7 @@ typedef struct iqh_desc {
   int32_t batch;               /* realizations per iq_search_pick call (<= nreal); 0 = all */
   int32_t nthreads;            /* host threads for cut + paste; 0 = hardware concurrency */
   int32_t ngroups;             /* lockstep groups pipelined against the host cuts; 0 = auto */
+  int32_t cut_mode;            /* boundary cuts: 0 = auto (device when fewer than 6 host threads), 1 = host, 2 = device */
   int32_t fft_mode;            /* -1 never, 0 auto crossover, 1 always: distance path selection */
 } iqh_desc;
 

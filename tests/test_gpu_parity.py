@@ -324,3 +324,44 @@ def test_tau_model_device_equals_host_and_oracle(tol):
     assert out[0][0]["picked"] == out[1][0]["picked"] == int(ref["patterndb"][O.sample_weighted(0.3, ref["probs"])])
     if tol == 1.0:
         assert ref["patterndb"].size > 16384, ref["patterndb"].size  # exercises the host fallback
+
+
+def test_device_cut_equals_host_cut():
+    """iq_cut_batch (deterministic shared-memory push-relabel) returns the keep-mask of the host routine /
+    the oracle on slabs of every orientation, including a slab too large for shared memory (host path)."""
+    r = np.random.default_rng(5)
+    field = synth.gaussian_field((90, 80, 40), (12, 12, 5), 3).astype(np.float64)
+    slabs = []
+    for shape, dim in [((7, 40, 16), 0), ((40, 7, 16), 1), ((40, 40, 3), 2), ((8, 48), 0), ((48, 8), 1), ((5, 30, 12), 0),
+                       ((2, 10, 10), 0), ((30, 30, 4), 2), ((12, 60, 40), 0)]:
+        for _ in range(2):
+            p = [int(r.integers(0, s - t + 1)) for s, t in zip(field.shape, shape + (1,) * (3 - len(shape)))]
+            q = [int(r.integers(0, s - t + 1)) for s, t in zip(field.shape, shape + (1,) * (3 - len(shape)))]
+            sl = lambda o: tuple(slice(a, a + b) for a, b in zip(o, shape + (1,) * (3 - len(shape))))
+            A = field[sl(p)].reshape(shape)
+            B = field[sl(q)].reshape(shape)
+            slabs.append((A, B, dim))
+    with api.SearchContext(np.zeros((16, 16), np.float32), (4, 4)) as ctx:
+        keeps, iters = ctx.cut_batch(slabs)
+        keeps2, iters2 = ctx.cut_batch(slabs)
+    assert iters == iters2  # deterministic schedule
+    for (A, B, dim), k, k2, it in zip(slabs, keeps, keeps2, iters):
+        assert np.array_equal(k, k2)
+        assert np.array_equal(k, iqb200.graphcut(A, B, dim)), (A.shape, dim, it)
+    assert iters[-1] == 0 and max(iters[:-2]) > 0  # last slab (12x60x40) exceeds shared memory -> host
+    for (A, B, dim), k in list(zip(slabs, keeps))[:6]:
+        assert np.array_equal(k, O.graphcut(A, B, dim))
+
+
+def test_iqsim_device_cut_equals_host_cut():
+    """cut="device" (iq_cut_batch) and cut="host" (BK on the host) give the same realizations."""
+    cfg = synth.config(2, scale=0.25)
+    a = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=3, rng=np.random.default_rng(4), cut="host")
+    b = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=3, rng=np.random.default_rng(4), cut="device")
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    ti = synth.gaussian_field((48, 40, 20), (6, 6, 3), 9)
+    a = iqb200.iqsim(ti, (16, 12, 8), nreal=2, rng=np.random.default_rng(5), cut="host", overlap=(0.25, 0.25, 0.25))
+    b = iqb200.iqsim(ti, (16, 12, 8), nreal=2, rng=np.random.default_rng(5), cut="device", overlap=(0.25, 0.25, 0.25))
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
