@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
     long long tc = clock64(); t_rel += tc - tb;
 #endif
     if (!any || iter >= max_iter) break;
-    if ((iter & 31) == 31) {
+    if ((iter & 7) == 7 || iter == 3) {
       global_relabel();
 #ifdef IQ_CUT_PROFILE
       t_glob += clock64() - tc; ++nglob;
