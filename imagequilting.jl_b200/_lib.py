@@ -73,6 +73,11 @@ SYMBOLS = {
                                    C.POINTER(IqResult)]),
     "iq_distance": (C.c_int32, [C.c_void_p, C.c_int32, c_u8_p, C.POINTER(IqTile), c_float_p]),
     "iq_fetch_tile": (C.c_int32, [C.c_void_p, C.c_int64, c_float_p]),
+    "iq_slice_distance": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqTile), C.c_int32, c_float_p]),
+    "iq_slice_select": (C.c_int32, [C.c_void_p, C.c_double, c_float_p, c_i64_p]),
+    "iq_slice_candidates": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(c_i64_p), C.POINTER(c_float_p)]),
+    "iq_taumodel": (C.c_int32, [C.c_int64, C.c_int32, c_float_p, c_double_p]),
+    "iq_sample": (C.c_int32, [c_double_p, C.c_int64, C.c_double, c_i64_p]),
     "iq_cut_batch": (C.c_int32, [C.c_void_p, C.POINTER(IqCutTask), C.c_int32, c_i32_p]),
     "iq_last_search_stats": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
     "iq_last_search_path": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p, c_double_p, c_double_p]),

@@ -112,6 +112,23 @@ def _dilate(grid):
     return out
 
 
+def _overlap_slabs(tileind, pasted, geo):
+    """(dim, 'prev'|'next', slices) of the overlaps with already pasted neighbours (src/iqsim.jl:188-205)."""
+    tilesize, ovlsize, spacing = geo["tilesize"], geo["ovlsize"], geo["spacing"]
+    N = len(tilesize)
+    out = []
+    for d in range(N):
+        if ovlsize[d] <= 1:
+            continue
+        prev = tuple(t - 1 if i == d else t for i, t in enumerate(tileind))
+        nxt = tuple(t + 1 if i == d else t for i, t in enumerate(tileind))
+        if prev in pasted:
+            out.append((d, "prev", tuple(slice(0, ovlsize[i]) if i == d else slice(0, tilesize[i]) for i in range(N))))
+        if nxt in pasted:
+            out.append((d, "next", tuple(slice(spacing[i], tilesize[i]) if i == d else slice(0, tilesize[i]) for i in range(N))))
+    return out
+
+
 def _genpath(rng, extent, kind, datainds):
     """src/utils.jl:158-204 with a numpy Generator: raster / random (randperm) / dilation, or the
     data-first dilation path when hard data exists."""
@@ -434,6 +451,34 @@ class SearchContext:
                             dmin=float(res[i].dmin)))
         return out
 
+    def slice_distance(self, ovlmask, simdevs):
+        """Phase 1 of a position-slice search: overlap distances of the local positions -> local minima."""
+        m = _f(np.asarray(ovlmask).astype(np.uint8), np.uint8)
+        n = len(simdevs)
+        arr = (IqTile * n)()
+        keep = []
+        for i, sd in enumerate(simdevs):
+            t, k = self._tile(sd)
+            arr[i] = t
+            keep.append(k)
+        out = np.zeros(n, dtype=np.float32)
+        check(lib().iq_slice_distance(self._h, _ptr(m, c_u8_p), arr, n, _ptr(out, c_float_p)))
+        return out
+
+    def slice_select(self, tol, dmin_global):
+        """Phase 2: threshold rule with the GLOBAL minimum -> [(local idx, values)] per tile."""
+        g = np.ascontiguousarray(dmin_global, dtype=np.float32)
+        counts = np.zeros(g.size, dtype=np.int64)
+        check(lib().iq_slice_select(self._h, float(tol), _ptr(g, c_float_p), _ptr(counts, c_i64_p)))
+        out = []
+        for t in range(g.size):
+            pi, pv = c_i64_p(), c_float_p()
+            check(lib().iq_slice_candidates(self._h, t, C.byref(pi), C.byref(pv)))
+            n = int(counts[t])
+            out.append((np.ctypeslib.as_array(pi, shape=(n,)).copy() if n else np.zeros(0, np.int64),
+                        np.ctypeslib.as_array(pv, shape=(n,)).copy() if n else np.zeros(0, np.float32)))
+        return out
+
     def cut_batch(self, slabs):
         """Device boundary cuts (iq_cut_batch): slabs = [(A, B, dim), ...] -> ([keep masks], [sweeps])."""
         n = len(slabs)
@@ -471,6 +516,22 @@ class SearchContext:
         nd, nf, fb, fm = C.c_int64(), C.c_int64(), C.c_double(), C.c_double()
         check(lib().iq_last_search_path(self._h, C.byref(nd), C.byref(nf), C.byref(fb), C.byref(fm)))
         return nd.value, nf.value, fb.value, fm.value
+
+
+def taumodel(vals):
+    """Host tau model of the library (src/taumodel.jl:5-45); vals: (nsrc, n) float32 distances of the candidates."""
+    v = np.ascontiguousarray(np.atleast_2d(vals), dtype=np.float32)
+    prob = np.zeros(v.shape[1], dtype=np.float64)
+    check(lib().iq_taumodel(v.shape[1], v.shape[0], _ptr(v, c_float_p), _ptr(prob, c_double_p)))
+    return prob
+
+
+def sample(prob, u):
+    """StatsBase.sample's cumulative walk (src/iqsim.jl:243): position of the chosen candidate."""
+    p = np.ascontiguousarray(prob, dtype=np.float64)
+    pos = C.c_int64()
+    check(lib().iq_sample(_ptr(p, c_double_p), p.size, float(u), C.byref(pos)))
+    return pos.value
 
 
 def fma_peak(device=0, packed=False):

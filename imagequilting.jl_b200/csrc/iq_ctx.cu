@@ -194,6 +194,10 @@ struct iq_ctx {
   double* d_prob = nullptr;               // [max_batch][kTauMax]
   double* h_prob = nullptr;               // pinned mirror
   int tau_device = 1;                     // 0 = always evaluate the tau model on the host
+  // position-slice mode (iq_slice_*): candidates of the last select call
+  std::vector<std::vector<int64_t>> slice_idx;
+  std::vector<std::vector<float>> slice_val;
+  int slice_ntile = 0;
   char* h_cut = nullptr;  // pinned staging of the device boundary cut (slabs, masks, task records)
   char* d_cut = nullptr;
   size_t cut_cap = 0;
@@ -1210,6 +1214,122 @@ int32_t iq_fetch_tile(iq_ctx* c, int64_t pos, float* out_tile) {
   c->launches++;
   CK(cudaMemcpyAsync(out_tile, c->d_fetch, (size_t)c->tilevol * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return IQ_OK;
+}
+
+int32_t iq_slice_distance(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int32_t ntile, float* dmin_local) {
+  if (!c || !ovlmask || !tiles || !dmin_local || ntile <= 0) return fail(IQ_ERR_INVALID, "iq_slice_distance: bad argument");
+  if (ntile > c->max_batch) return fail(IQ_ERR_INVALID, "iq_slice_distance: ntile exceeds max_batch");
+  if (c->nsoft > 0) return fail(IQ_ERR_INVALID, "position-slice mode supports the threshold path only (no soft data)");
+  for (int i = 0; i < ntile; ++i)
+    if (!tiles[i].simdev || tiles[i].hard_nnz > 0) return fail(IQ_ERR_INVALID, "position-slice mode: simdev required, hard data unsupported");
+  CK(cudaSetDevice(c->device));
+  MaskEntry* e = nullptr;
+  int rc = get_mask(c, ovlmask, &e);
+  if (rc) return rc;
+  const int rb = pick_rb(c, ntile);
+  const int ngrp = (ntile + rb - 1) / rb;
+  rc = stage_reserve(c, 8192 + (size_t)ngrp * rb * e->tmpl_floats * sizeof(float) + (size_t)ntile * (c->tilevol * sizeof(float) + 64));
+  if (rc) return rc;
+  c->stage_used = 0;
+  c->dist_ev_used = 0;
+  CK(iq::launch_fill_u32(c->d_minmax, 0x7f800000u, c->max_batch, c->stream));
+  CK(iq::launch_fill_u32(c->d_minmax + c->max_batch, 0u, c->max_batch, c->stream));
+  c->launches += 2;
+  std::vector<const float*> kern(ntile);
+  for (int r = 0; r < ntile; ++r) kern[r] = tiles[r].simdev;
+  rc = run_dense(c, e, -1, kern.data(), ntile, c->d_Dovl, 0);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, (size_t)2 * c->max_batch * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < ntile; ++r) std::memcpy(&dmin_local[r], &c->h_minmax[r], 4);
+  c->slice_ntile = ntile;
+  return IQ_OK;
+}
+
+int32_t iq_slice_select(iq_ctx* c, double tol, const float* dmin_global, int64_t* counts) {
+  if (!c || !dmin_global || !counts) return fail(IQ_ERR_INVALID, "iq_slice_select: NULL argument");
+  if (c->slice_ntile <= 0) return fail(IQ_ERR_STATE, "iq_slice_select without a preceding iq_slice_distance");
+  if (!(tol > 0.0 && tol <= 1.0)) return fail(IQ_ERR_INVALID, "tolerance must be in range (0,1]");
+  CK(cudaSetDevice(c->device));
+  const int R = c->slice_ntile;
+  for (int r = 0; r < R; ++r) std::memcpy(&c->h_minmax[r], &dmin_global[r], 4);
+  CK(cudaMemcpyAsync(c->d_minmax, c->h_minmax, (size_t)R * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+  const int maxS = c->max_src;
+  for (int r = 0; r < R; ++r) {
+    iq::PickJob& J = c->h_pick[r];
+    std::memset(&J, 0, sizeof J);
+    J.mode = 0;
+    J.nsrc = 1;
+    J.src[0] = c->d_Dovl + (size_t)r * c->npos;
+    J.sel = c->d_sel + (size_t)r * maxS;
+    J.tol = tol;
+    J.minbits = c->d_minmax + r;
+    J.blockcount = c->d_blockcount + (size_t)r * iq::pick_nblk(c->npos);
+    J.total = c->d_total + r;
+    J.cand_idx = c->d_cand_idx + (size_t)r * c->npos;
+    J.cand_val = c->d_cand_val + (size_t)r * maxS * c->npos;
+    J.cap = c->npos;
+  }
+  CK(cudaMemcpyAsync(c->d_pick, c->h_pick, (size_t)R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+  CK(iq::launch_pick_count(c->d_pick, R, c->npos, c->stream));
+  CK(iq::launch_pick_write(c->d_pick, R, c->npos, c->stream));
+  c->launches += 2;
+  CK(cudaMemcpyAsync(c->h_total, c->d_total, (size_t)R * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  size_t tot = 0;
+  for (int r = 0; r < R; ++r) tot += c->h_total[r];
+  if (tot > c->h_cand_cap) {
+    if (c->h_cand_idx) cudaFreeHost(c->h_cand_idx);
+    if (c->h_cand_val) cudaFreeHost(c->h_cand_val);
+    c->h_cand_idx = nullptr; c->h_cand_val = nullptr;
+    const size_t cap = std::max<size_t>(tot * 2, 1 << 16);
+    CK(cudaMallocHost((void**)&c->h_cand_idx, cap * sizeof(unsigned)));
+    CK(cudaMallocHost((void**)&c->h_cand_val, cap * maxS * sizeof(float)));
+    c->h_cand_cap = cap;
+  }
+  size_t o = 0;
+  for (int r = 0; r < R; ++r) {
+    const size_t n = c->h_total[r];
+    if (n) {
+      CK(cudaMemcpyAsync(c->h_cand_idx + o, c->d_cand_idx + (size_t)r * c->npos, n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(c->h_cand_val + o, c->d_cand_val + (size_t)r * maxS * c->npos, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    o += n;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  c->slice_idx.resize(R);
+  c->slice_val.resize(R);
+  o = 0;
+  for (int r = 0; r < R; ++r) {
+    const size_t n = c->h_total[r];
+    c->slice_idx[r].resize(n);
+    c->slice_val[r].assign(c->h_cand_val + o, c->h_cand_val + o + n);
+    for (size_t i = 0; i < n; ++i) c->slice_idx[r][i] = (int64_t)c->h_cand_idx[o + i];
+    counts[r] = (int64_t)n;
+    o += n;
+  }
+  return IQ_OK;
+}
+
+int32_t iq_slice_candidates(const iq_ctx* c, int32_t tile, const int64_t** idx, const float** val) {
+  if (!c || tile < 0 || tile >= (int)c->slice_idx.size()) return fail(IQ_ERR_INVALID, "iq_slice_candidates: bad tile index");
+  if (idx) *idx = c->slice_idx[tile].data();
+  if (val) *val = c->slice_val[tile].data();
+  return IQ_OK;
+}
+
+int32_t iq_taumodel(int64_t n, int32_t nsrc, const float* vals, double* prob) {
+  if (n <= 0 || nsrc <= 0 || !vals || !prob) return fail(IQ_ERR_INVALID, "iq_taumodel: bad argument");
+  std::vector<double> p;
+  taumodel(n, nsrc, vals, p);
+  std::memcpy(prob, p.data(), (size_t)n * sizeof(double));
+  return IQ_OK;
+}
+
+int32_t iq_sample(const double* prob, int64_t n, double u, int64_t* pos) {
+  if (!prob || n <= 0 || !pos) return fail(IQ_ERR_INVALID, "iq_sample: bad argument");
+  *pos = sample_walk(prob, n, u);
   return IQ_OK;
 }
 

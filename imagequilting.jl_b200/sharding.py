@@ -63,3 +63,131 @@ def iqsim_sharded(trainimg, tilesize, simsize=None, *, nreal=1, seed=0, run_fn=N
             else:
                 reals.append(np.ma.masked_invalid(a))
     return reals
+
+
+# --------------------------------------------------------------------------------------
+# position-slice mode (second axis): ONE realization at a time, the candidate
+# positions of every tile search split over the ranks along the slowest distance-map axis
+# --------------------------------------------------------------------------------------
+class GpuSliceBackend:
+    """Local slab of the search on this rank's GPU (iq_slice_distance / iq_slice_select)."""
+
+    def __init__(self, ti_crop, tilesize, disabled_crop, device):
+        from .api import SearchContext
+        self.ctx = SearchContext(ti_crop, tilesize, disabled=disabled_crop, device=device, max_batch=1)
+
+    def distance(self, mask, simdev):
+        return float(self.ctx.slice_distance(mask, [simdev])[0])
+
+    def select(self, tol, gmin):
+        return self.ctx.slice_select(tol, [gmin])[0]
+
+    def close(self):
+        self.ctx.close()
+
+
+def slab(nlast, world, rank):
+    """Contiguous block [z0, z1) of the slowest distance-map axis owned by `rank`."""
+    return nlast * rank // world, nlast * (rank + 1) // world
+
+
+def iqsim_sliced(trainimg, tilesize, simsize=None, *, overlap=None, tol=0.1, path="raster", nreal=1, seed=0,
+                 device=0, backend_factory=None):
+    """Image quilting with every tile search split over the ranks by candidate position.
+
+    The training image is replicated on the host of every rank; each rank uploads only the slab of it that
+    its patch positions need.  Per tile: local distances + local minimum -> all-reduce(min) -> local threshold
+    selection -> all-gather of the (short) candidate lists -> tau model, sampling, boundary cut and paste
+    replicated on every rank (identical state everywhere, so no further exchange is needed).  Threshold path
+    only (no soft / hard data).  Returns the same realizations as `iqsim(..., rng=default_rng(seed))`."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    timg = np.asarray(trainimg)
+    N = timg.ndim
+    tilesize = tuple(int(t) for t in tilesize)
+    geo = api.geometry(timg.shape, tilesize, simsize, overlap)
+    TI, nanmask = api._prepare(timg)
+    disabled = api._finddisabled(nanmask, geo)
+    distsize, ntiles, spacing, padsize = geo["distsize"], geo["ntiles"], geo["spacing"], geo["padsize"]
+    z0, z1 = slab(distsize[-1], world, rank)
+    crop = (slice(None),) * (N - 1) + (slice(z0, z1 + tilesize[-1] - 1),)
+    dcrop = (slice(None),) * (N - 1) + (slice(z0, z1),)
+    plane = int(np.prod(distsize[:-1], dtype=np.int64))
+    backend = None
+    if z1 > z0:
+        factory = backend_factory or (lambda t, ts, d: GpuSliceBackend(t, ts, d, device))
+        backend = factory(np.asfortranarray(TI[crop], dtype=np.float32), tilesize,
+                          None if disabled is None else np.asfortranarray(disabled[dcrop]))
+    enabled = None  # global list of enabled positions for the empty-mask tiles
+
+    rng = np.random.default_rng(seed)
+    simpath = api._genpath(rng, ntiles, path, [])
+    skipped = {lin for lin in range(int(np.prod(ntiles)))
+               if any(int(t) * sp >= sz for t, sp, sz in zip(np.unravel_index(lin, ntiles, order="F"), spacing, geo["simsize"]))}
+    visited = [p for p in simpath if p not in skipped]
+    u_all = rng.random(nreal * len(visited)).reshape(nreal, len(visited))
+
+    def allreduce_min(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float32)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
+    def allgather(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    reals = []
+    for real in range(nreal):
+        simgrid = np.zeros(padsize, dtype=TI.dtype, order="F")
+        pasted = set()
+        for step, ind in enumerate(visited):
+            tileind = tuple(int(v) for v in np.unravel_index(ind, ntiles, order="F"))
+            start = tuple(t * sp for t, sp in zip(tileind, spacing))
+            tile = tuple(slice(s, s + t) for s, t in zip(start, tilesize))
+            simdev = simgrid[tile]
+            slabs = api._overlap_slabs(tileind, pasted, geo)
+            mask = np.zeros(tilesize, dtype=bool)
+            for _, _, sl in slabs:
+                mask[sl] = True
+            u = float(u_all[real, step])
+            if not mask.any():  # every enabled patch, equal weights (first tile of a realization)
+                if enabled is None:
+                    enabled = (np.arange(plane * distsize[-1], dtype=np.int64) if disabled is None
+                               else np.flatnonzero(~disabled.astype(bool).ravel(order="F")).astype(np.int64))
+                n = enabled.size
+                dn = float(n)
+                x0 = (1.0 - 1.0 / dn) / (1.0 / dn) if n > 1 else 0.0
+                Pi = dn / (dn * dn) if n > 1 else 1.0
+                pc = 1.0 / (1.0 + x0 * (((1.0 - Pi) / Pi) / x0)) if n > 1 else 1.0
+                rind = int(enabled[api.sample(np.full(n, pc), u)])
+            else:
+                lmin = backend.distance(mask, simdev) if backend is not None else float("inf")
+                gmin = allreduce_min(lmin)
+                idx, val = backend.select(tol, gmin) if backend is not None else (np.zeros(0, np.int64), np.zeros(0, np.float32))
+                parts = allgather((idx + z0 * plane, val))
+                gidx = np.concatenate([p[0] for p in parts])
+                gval = np.concatenate([p[1] for p in parts]).astype(np.float32)
+                prob = api.taumodel(gval[None, :]) if gidx.size > 1 else np.ones(1)
+                rind = int(gidx[api.sample(prob, u)])
+            rstart = tuple(int(v) for v in np.unravel_index(rind, distsize, order="F"))
+            TIdev = TI[tuple(slice(s, s + t) for s, t in zip(rstart, tilesize))]
+            cutmask = np.zeros(tilesize, dtype=bool)
+            for d, which, sl in slabs:
+                keep = api.graphcut(simdev[sl], TIdev[sl], d)
+                cutmask[sl] |= keep if which == "prev" else ~keep
+            simdev[~cutmask] = TIdev[~cutmask]
+            pasted.add(tileind)
+        reals.append(np.array(simgrid[tuple(slice(0, s) for s in geo["simsize"])], copy=True))
+    if backend is not None and hasattr(backend, "close"):
+        backend.close()
+    return reals

@@ -122,6 +122,21 @@ int32_t iq_distance(iq_ctx* ctx, int32_t which, const uint8_t* ovlmask, const iq
  * distance map (view_kernel, src/utils.jl:63-67). */
 int32_t iq_fetch_tile(iq_ctx* ctx, int64_t pos, float* out_tile);
 
+/* Position-slice mode (second axis): for ONE large realization every rank holds a slab of the
+ * training image (its context is created on the cropped image) and owns the patch positions of that slab.
+ * A tile search becomes: iq_slice_distance on every rank (overlap distance + local minimum) -> the host
+ * all-reduces the minimum -> iq_slice_select with the global minimum (threshold rule of src/iqsim.jl:237 on the
+ * local positions) -> the host all-gathers the short candidate lists (local index + offset of the slab) and
+ * evaluates the tau model (iq_taumodel) and the sampling walk (iq_sample) on the merged list.  Threshold path only
+ * (no soft / hard data).  Buffers handed out by iq_slice_candidates stay valid until the next iq_slice_* call. */
+int32_t iq_slice_distance(iq_ctx* ctx, const uint8_t* ovlmask, const iq_tile* tiles, int32_t ntile, float* dmin_local);
+int32_t iq_slice_select(iq_ctx* ctx, double tol, const float* dmin_global, int64_t* counts);
+int32_t iq_slice_candidates(const iq_ctx* ctx, int32_t tile, const int64_t** idx, const float** val);
+/* Host FP64 pieces exposed for hosts that merge candidate lists themselves: taumodel (src/taumodel.jl:5-45) on
+ * vals[source][candidate] and the StatsBase.sample walk (src/iqsim.jl:243). */
+int32_t iq_taumodel(int64_t n, int32_t nsrc, const float* vals, double* prob);
+int32_t iq_sample(const double* prob, int64_t n, double u, int64_t* pos);
+
 /* Optional device boundary cut (the reference keeps graphcut on the host, src/graphcut.jl:5-84; this entry
  * exists because a multi-GPU node has few host cores per GPU).  Each task is one overlap slab: A = content
  * already pasted, B = new patch, both column-major with size sz (unused dims = 1), cut along `dim`;
