@@ -14,8 +14,9 @@
 //     voxels of one colour never share a neighbour.  A sweep discharges the active voxels colour by colour
 //     (push along every admissible arc, relabel if excess is left): no two concurrent voxels touch the same
 //     state, so there are no atomics and the floating-point result is independent of thread scheduling;
-//   * every 32 sweeps an exact global relabel (BFS distances to the sink slice as the fixed point of a
-//     chaotic relaxation), which also parks voxels that cannot reach the sink;
+//   * the voxels of a colour that hold excess are first compacted into a list (dense warps), then discharged;
+//   * every 8 sweeps an exact global relabel (frontier BFS from the sink slice in shared memory), which also
+//     parks voxels that cannot reach the sink;
 //   * the final global relabel IS the answer: height < HMAX <=> can reach the sink.
 // FP64 throughout, capacities computed with the reference's formula and operation order
 // ((Du+Dv)/(gAu+gAv+gBu+gBv+eps), graphcut.jl:52) with explicit round-to-nearest intrinsics (no contraction).
@@ -62,6 +63,9 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
   unsigned char* topo = reinterpret_cast<unsigned char*>(h + nfree);  // [nfree]
   const int rows = n1 * (L - 2), m7 = (n0 + 6) / 7, items = rows * m7;
   unsigned short* clist = reinterpret_cast<unsigned short*>(topo + ((nfree + 3) & ~3));  // [7][items] voxel of item or 0xffff
+  unsigned short* fr0 = clist + 7 * items;   // [nfree] BFS frontier (ping) / active list of a colour phase
+  unsigned short* fr1 = fr0 + nfree;         // [nfree] BFS frontier (pong)
+  __shared__ int s_cnt[2];
   const int tid = threadIdx.x;
   const int HMAX = nfree + 2;
   const int off[6] = {1, -1, n0, -n0, P, -P};
@@ -104,25 +108,45 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
   }
   __syncthreads();
 
-  // Exact heights = BFS distance to the sink slice over residual arcs i -> v, computed as the fixed point of
-  // h[i] = min(h[i], 1 + min_v h[v]) by chaotic in-place relaxation (the fixed point is unique, so the result
-  // does not depend on the update order; in-place updates propagate several levels per pass).
+  // Exact heights = BFS distance to the sink slice over residual arcs x -> v, level by level with explicit
+  // frontiers in shared memory (every voxel is expanded once; levels are unique, so the result does not depend
+  // on the order in which a frontier is filled).  Voxels that cannot reach the sink keep HMAX.
   auto global_relabel = [&]() {
-    for (int i = tid; i < nfree; i += kCutThreads) h[i] = ((topo[i] & kToSink) && r[4 * nfree + i] > 0.0) ? 1 : HMAX;
+    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
     __syncthreads();
-    for (;;) {
-      int changed = 0;
-      for (int i = tid; i < nfree; i += kCutThreads) {
-        const unsigned tp = topo[i];
-        int best = h[i];
-#pragma unroll
-        for (int dir = 0; dir < 6; ++dir)
-          if ((tp >> dir) & 1u) {
-            if (r[dir * nfree + i] > 0.0) best = min(best, ((volatile int*)h)[i + off[dir]] + 1);
-          }
-        if (best < h[i]) { ((volatile int*)h)[i] = best; changed = 1; }
+    for (int i0 = 0; i0 < nfree; i0 += kCutThreads) {
+      const int i = i0 + tid;
+      const bool first = i < nfree && (topo[i] & kToSink) && r[4 * nfree + i] > 0.0;
+      if (i < nfree) h[i] = first ? 1 : HMAX;
+      const unsigned bal = __ballot_sync(0xffffffffu, first);
+      if (bal) {
+        int base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(&s_cnt[0], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (first) fr0[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned short)i;
       }
-      if (!__syncthreads_or(changed)) break;
+    }
+    __syncthreads();
+    unsigned short* cur = fr0;
+    unsigned short* nxt = fr1;
+    int which = 0;
+    for (int level = 1;; ++level) {
+      const int n = s_cnt[which];
+      if (n == 0) break;
+      // 6 threads per frontier voxel: one per direction
+      for (int t = tid; t < n * 6; t += kCutThreads) {
+        const int v = cur[t / 6], dir = t % 6;
+        if (!((topo[v] >> dir) & 1u)) continue;
+        const int x = v + off[dir];
+        if (h[x] != HMAX) continue;
+        if (!(r[(dir ^ 1) * nfree + x] > 0.0)) continue;  // arc x -> v must have residual capacity
+        if (atomicCAS(&h[x], HMAX, level + 1) == HMAX) nxt[atomicAdd(&s_cnt[which ^ 1], 1)] = (unsigned short)x;
+      }
+      __syncthreads();
+      if (tid == 0) s_cnt[which] = 0;
+      which ^= 1;
+      unsigned short* tsw = cur; cur = nxt; nxt = tsw;
+      __syncthreads();
     }
   };
 #ifdef IQ_CUT_PROFILE
@@ -145,43 +169,56 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
     long long ta = clock64();
 #endif
     int active = 0;
+    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+    __syncthreads();
 #pragma unroll 1
     for (int colour = 0; colour < 7; ++colour) {
       const unsigned short* cl = clist + colour * items;
-      for (int w = tid; w < items; w += kCutThreads) {
-        const int i = cl[w];
-        if (i == 0xffff) continue;
+      const int wq = colour & 1;
+      // pass 1: compact the voxels of this colour that hold excess (dense warps in pass 2)
+      for (int w0 = 0; w0 < items; w0 += kCutThreads) {
+        const int w = w0 + tid;
+        int i = 0xffff;
+        if (w < items) i = cl[w];
+        const bool act = (i != 0xffff) && e[i] > 0.0 && h[i] < HMAX;
+        const unsigned bal = __ballot_sync(0xffffffffu, act);
+        if (bal) {
+          int base = 0;
+          if ((tid & 31) == 0) base = atomicAdd(&s_cnt[wq], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (act) fr0[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned short)i;
+        }
+      }
+      __syncthreads();
+      const int nact = s_cnt[wq];
+      if (tid == 0) s_cnt[wq ^ 1] = 0;
+      // pass 2: discharge (push along every admissible arc, relabel if excess is left)
+      for (int j = tid; j < nact; j += kCutThreads) {
+        const int i = fr0[j];
         double ex = e[i];
-        if (!(ex > 0.0)) continue;
         int hi = h[i];
-        if (hi >= HMAX) continue;
         const unsigned tp = topo[i];
-        // fetch the six residuals and neighbour heights first (independent loads), then discharge from registers
-        double rc[6];
-        int hv[6];
+        int mh = HMAX;  // lowest neighbour over the arcs that still have residual capacity after the pushes
 #pragma unroll
         for (int dir = 0; dir < 6; ++dir) {
           const bool inner = (tp >> dir) & 1u;
           const bool sink = (dir == 4) && (tp & kToSink);
-          rc[dir] = (inner || sink) ? r[dir * nfree + i] : 0.0;
-          hv[dir] = sink ? 0 : (inner ? h[i + off[dir]] : HMAX);
-        }
-        int mh = HMAX;  // lowest neighbour over the arcs that still have residual capacity after the pushes
-#pragma unroll
-        for (int dir = 0; dir < 6; ++dir) {
-          if (!(rc[dir] > 0.0)) continue;
-          if (ex > 0.0 && hi == hv[dir] + 1) {
-            const double d = fmin(ex, rc[dir]);
-            rc[dir] = __dsub_rn(rc[dir], d);
+          if (!inner && !sink) continue;
+          double rc = r[dir * nfree + i];
+          if (!(rc > 0.0)) continue;
+          const int v = i + off[dir];
+          const int hv = sink ? 0 : h[v];
+          if (ex > 0.0 && hi == hv + 1) {
+            const double d = fmin(ex, rc);
+            rc = __dsub_rn(rc, d);
             ex = __dsub_rn(ex, d);
-            r[dir * nfree + i] = rc[dir];
-            if (!((dir == 4) && (tp & kToSink))) {
-              const int v = i + off[dir];
+            r[dir * nfree + i] = rc;
+            if (!sink) {
               r[(dir ^ 1) * nfree + v] = __dadd_rn(r[(dir ^ 1) * nfree + v], d);
               e[v] = __dadd_rn(e[v], d);
             }
           }
-          if (rc[dir] > 0.0) mh = min(mh, hv[dir]);
+          if (rc > 0.0) mh = min(mh, hv);
         }
         e[i] = ex;
         if (ex > 0.0) {
@@ -228,7 +265,7 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
 size_t graphcut_smem(int n0, int n1, int L) {
   const size_t nfree = (size_t)(L - 2) * n0 * n1;
   const size_t items = (size_t)n1 * (L - 2) * ((n0 + 6) / 7);
-  return nfree * (kCutBytesPerNode - 1) + ((nfree + 3) & ~(size_t)3) + 7 * items * sizeof(unsigned short) + 16;
+  return nfree * (kCutBytesPerNode - 1) + ((nfree + 3) & ~(size_t)3) + (7 * items + 2 * nfree) * sizeof(unsigned short) + 16;
 }
 
 cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s) {
