@@ -42,6 +42,15 @@ class IqCutTask(C.Structure):
     _fields_ = [("A", c_double_p), ("B", c_double_p), ("sz", C.c_int32 * 3), ("dim", C.c_int32), ("keep", c_u8_p)]
 
 
+class IqSimDesc(C.Structure):
+    _fields_ = [("pad_size", C.c_int64 * 3), ("ovl_size", C.c_int64 * 3), ("nreal", C.c_int32), ("ti64", c_double_p),
+                ("u", c_double_p), ("npath", C.c_int64), ("tol", C.c_double), ("debug", C.c_int32)]
+
+
+class IqSimSlab(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("prev", C.c_int32), ("lo", C.c_int32 * 3), ("sz", C.c_int32 * 3)]
+
+
 class IqhDesc(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("ti_size", C.c_int64 * 3), ("tile_size", C.c_int64 * 3),
                 ("ovl_size", C.c_int64 * 3), ("ntiles", C.c_int64 * 3), ("pad_size", C.c_int64 * 3),
@@ -49,7 +58,9 @@ class IqhDesc(C.Structure):
                 ("aux", C.POINTER(c_float_p)), ("auxti", C.POINTER(c_float_p)),
                 ("hard_has", c_u8_p), ("hard_val", c_float_p), ("path", c_i64_p), ("npath", C.c_int64),
                 ("tol", C.c_double), ("nreal", C.c_int32), ("u", c_double_p), ("debug", C.c_int32),
-                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32), ("ngroups", C.c_int32), ("cut_mode", C.c_int32), ("fft_mode", C.c_int32)]
+                ("device", C.c_int32), ("batch", C.c_int32), ("nthreads", C.c_int32), ("ngroups", C.c_int32),
+                ("cut_mode", C.c_int32), ("fft_mode", C.c_int32), ("pipeline", C.c_int32),
+                ("out_real", C.POINTER(C.c_void_p)), ("out_real_f32", C.c_int32), ("sim_size", C.c_int64 * 3)]
 
 
 class IqhStats(C.Structure):
@@ -57,7 +68,9 @@ class IqhStats(C.Structure):
                 ("total_ms", C.c_double), ("searches", C.c_int64), ("kernel_launches", C.c_int64),
                 ("candidates", C.c_int64), ("setup_ms", C.c_double), ("dist_kernel_ms", C.c_double),
                 ("dist_launches", C.c_int64), ("fft_searches", C.c_int64), ("direct_searches", C.c_int64),
-                ("fft_bytes", C.c_double), ("fft_ms", C.c_double)]
+                ("fft_bytes", C.c_double), ("fft_ms", C.c_double), ("resident", C.c_int32),
+                ("resident_status", C.c_int32), ("device_ms", C.c_double), ("select_ms", C.c_double),
+                ("cut_device_ms", C.c_double), ("fetch_ms", C.c_double)]
 
 
 # every symbol include/*.h declares: name -> (restype, argtypes)
@@ -79,6 +92,13 @@ SYMBOLS = {
     "iq_taumodel": (C.c_int32, [C.c_int64, C.c_int32, c_float_p, c_double_p]),
     "iq_sample": (C.c_int32, [c_double_p, C.c_int64, C.c_double, c_i64_p]),
     "iq_cut_batch": (C.c_int32, [C.c_void_p, C.POINTER(IqCutTask), C.c_int32, c_i32_p]),
+    "iq_sim_begin": (C.c_int32, [C.c_void_p, C.POINTER(IqSimDesc)]),
+    "iq_sim_step": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32]),
+    "iq_sim_sync": (C.c_int32, [C.c_void_p, c_i64_p, c_i32_p]),
+    "iq_sim_fetch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_i64_p, C.c_void_p]),
+    "iq_sim_fetch_cut": (C.c_int32, [C.c_void_p, C.c_int32, c_u8_p]),
+    "iq_sim_times": (C.c_int32, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "iq_sim_end": (C.c_int32, [C.c_void_p]),
     "iq_last_search_stats": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
     "iq_last_search_path": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p, c_double_p, c_double_p]),
     "iq_last_search_kernel_ms": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),

@@ -167,7 +167,8 @@ def _genpath(rng, extent, kind, datainds):
 # iqsim
 # --------------------------------------------------------------------------------------
 def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None, tol=0.1, path="raster", nreal=1,
-          debug=False, showprogress=False, rng=None, device=0, batch=0, nthreads=0, ngroups=0, fft=0, cut="auto", return_stats=False,
+          debug=False, showprogress=False, rng=None, device=0, batch=0, nthreads=0, ngroups=0, fft=0, cut="auto",
+          pipeline="auto", return_stats=False,
           return_picks=False, _path_override=None, _uniforms=None, _real_range=None):
     """Image quilting simulation with the GPU distance search (see module docstring)."""
     timg = trainimg if isinstance(trainimg, np.ma.MaskedArray) else np.asarray(trainimg)
@@ -258,7 +259,14 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     u = np.ascontiguousarray(u, dtype=np.float64)
 
     padvol = int(np.prod(padsize, dtype=np.int64))
-    grids = np.zeros((nreal, padvol), dtype=np.float64)
+    # the native driver writes the realizations, already cropped to simsize (src/iqsim.jl:303), straight into
+    # the arrays that are returned (element type of the prepared training image, src/utils.jl:96-102)
+    final_dtype = out_dtype
+    real_f32 = out_dtype == np.float32
+    if out_dtype not in (np.float32, np.float64):  # e.g. longdouble: simulated as FP64, converted at the end
+        out_dtype = np.dtype(np.float64)
+    reals = [np.zeros(simsize, dtype=out_dtype, order="F") for _ in range(nreal)]
+    real_ptrs = (C.c_void_p * nreal)(*[a.ctypes.data for a in reals])
     cuts = np.zeros((nreal, padvol), dtype=np.uint8) if debug else None
     picks = np.full((nreal, max(nvis, 1)), -1, dtype=np.int64)
 
@@ -282,24 +290,27 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     d.ngroups = int(ngroups)
     d.cut_mode = {"auto": 0, "host": 1, "device": 2}[cut]  # where the boundary cuts run (host = reference behaviour)
     d.fft_mode = int(fft)  # distance path: -1 direct kernels only, 0 measured crossover, 1 FFT whenever possible
+    # where the grids live: "resident" = on the device for the whole simulation (iq_sim_*), "staged" = on the host
+    # (one iq_search_pick per step), "auto" = resident whenever the simulation qualifies (no soft / hard data)
+    d.pipeline = {"auto": 0, "staged": 1, "resident": 2}[pipeline]
+    d.out_real, d.out_real_f32, d.sim_size = real_ptrs, int(real_f32), _i64x3(simsize)
     stats = IqhStats()
     if nvis > 0:
-        check(lib().iqh_run(C.byref(d), _ptr(grids, c_double_p), _ptr(cuts, c_u8_p) if debug else None,
-                            _ptr(picks, c_i64_p), C.byref(stats)))
+        check(lib().iqh_run(C.byref(d), None, _ptr(cuts, c_u8_p) if debug else None, _ptr(picks, c_i64_p),
+                            C.byref(stats)))
 
-    # post-processing (src/iqsim.jl:287-308)
+    # post-processing (src/iqsim.jl:287-308); hard-data coordinates lie inside simsize (asserted above)
     crop = tuple(slice(0, s) for s in simsize)
     realizations, boundarycuts, voxs = [], [], []
     for r in range(nreal):
-        simgrid = grids[r].reshape(padsize, order="F").astype(out_dtype)
+        res = reals[r] if final_dtype == out_dtype else reals[r].astype(final_dtype)
         cutgrid = cuts[r].reshape(padsize, order="F").astype(np.float64) if debug else None
         if debug:
             voxs.append(float(cutgrid.sum()) / geo["ovlvol"])
         for coord, val in hard.items():
-            simgrid[tuple(coord)] = val
+            res[tuple(coord)] = val
             if debug and _isnan(val):
                 cutgrid[tuple(coord)] = val
-        res = np.array(simgrid[crop], copy=True)
         realizations.append(res if is_float else np.ma.masked_invalid(res))
         if debug:
             boundarycuts.append(np.array(cutgrid[crop], copy=True))

@@ -22,7 +22,9 @@
 #include "iq_fft.h"
 #include "iq_cut.h"
 
-namespace {
+#include "iq_ctx.h"
+
+namespace iqimpl {
 
 thread_local std::string g_err;
 
@@ -35,34 +37,6 @@ int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
-
-#define CK(call)                                                                                      \
-  do {                                                                                                \
-    cudaError_t e__ = (call);                                                                         \
-    if (e__ != cudaSuccess)                                                                           \
-      return fail(IQ_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
-  } while (0)
-
-using iq::BoxDesc;
-
-struct MaskEntry {
-  std::vector<uint8_t> mask;
-  uint64_t hash = 0;
-  std::vector<BoxDesc> boxes;
-  BoxDesc* d_boxes = nullptr;
-  long long nnz = 0;
-  long long tmpl_floats = 0;           // packed template floats per tile
-  std::map<int, float*> a2;            // image id (-1 = TI, s = aux s) -> A2 map
-  int WX = 1, WY = 1;
-};
-
-struct TileResult {
-  std::vector<int64_t> idx;
-  std::vector<double> prob;
-  const int64_t* idx_ptr = nullptr;
-  const double* prob_ptr = nullptr;
-  int64_t count = 0;
-};
 
 uint64_t fnv1a(const uint8_t* p, size_t n) {
   uint64_t h = 1469598103934665603ull;
@@ -139,94 +113,6 @@ void taumodel(int64_t n, int nsrc, const float* vals, std::vector<double>& prob)
   for (int64_t i = 0; i < n; ++i) prob[(size_t)i] = 1.0 / (1.0 + x0 * prod[(size_t)i]);
 }
 
-}  // namespace
-
-struct iq_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int ndim = 3;
-  int nx = 1, ny = 1, nz = 1, tx = 1, ty = 1, tz = 1, nxo = 1, nyo = 1, nzo = 1;
-  long long npos = 0, tilevol = 0, nenabled = 0;
-  int nsoft = 0, max_batch = 1;
-  int rb_opt = 0;  // 0 = auto
-  int fft_mode = 0;   // 0 = auto (estimated crossover), 1 = always FFT for non-empty masks, -1 = never
-  iqfft::Plan* fft = nullptr;
-  bool fft_failed = false;
-  std::map<int, bool> image_is_int;  // image id -> every voxel is integer-valued (exact rounding of AB)
-  double last_fft_bytes = 0.0;
-  int64_t last_fft_searches = 0, last_direct_searches = 0;
-  int variant = 0; // 0 = flat kernel (default), 1 = tiled kernel, 2 = flat kernel with packed FMAs (experimental: slower)
-
-  float* d_ti = nullptr;
-  std::vector<float*> d_aux;
-  double* d_sat_ti = nullptr;
-  std::vector<double*> d_sat_aux;
-  uint8_t* d_disabled = nullptr;
-  std::vector<uint8_t> h_disabled;
-
-  float* d_Dovl = nullptr;
-  float* d_Dhard = nullptr;
-  std::vector<float*> d_Dsoft;
-  unsigned* d_minmax = nullptr;  // [kind][2][max_batch], kind 0 = ovl, 1 = hard, 2+s = soft
-  unsigned* h_minmax = nullptr;
-
-  // bump-allocated staging (pinned host + device mirror)
-  char* h_stage = nullptr;
-  char* d_stage = nullptr;
-  size_t stage_cap = 0, stage_used = 0;
-
-  iq::SelJob* d_sel = nullptr;
-  iq::SelJob* h_sel = nullptr;
-  iq::PickJob* d_pick = nullptr;
-  iq::PickJob* h_pick = nullptr;
-  unsigned* d_blockcount = nullptr;
-  unsigned* d_total = nullptr;
-  unsigned* h_total = nullptr;
-  unsigned* d_cand_idx = nullptr;
-  float* d_cand_val = nullptr;
-  int max_src = 1;
-  unsigned* h_cand_idx = nullptr;
-  float* h_cand_val = nullptr;
-  size_t h_cand_cap = 0;
-  unsigned* d_rank = nullptr;             // [max_batch][max_src][kTauMax] dense ranks (device tau model)
-  unsigned long long* d_colsum = nullptr; // [max_batch][max_src]
-  double* d_prob = nullptr;               // [max_batch][kTauMax]
-  double* h_prob = nullptr;               // pinned mirror
-  int tau_device = 1;                     // 0 = always evaluate the tau model on the host
-  // position-slice mode (iq_slice_*): candidates of the last select call
-  std::vector<std::vector<int64_t>> slice_idx;
-  std::vector<std::vector<float>> slice_val;
-  int slice_ntile = 0;
-  char* h_cut = nullptr;  // pinned staging of the device boundary cut (slabs, masks, task records)
-  char* d_cut = nullptr;
-  size_t cut_cap = 0;
-  iqcut::Work cut_work;   // host fallback scratch
-  int* d_shifts = nullptr;
-  int nshift = 0;
-  float* d_fetch = nullptr;
-
-  std::vector<std::unique_ptr<MaskEntry>> masks;
-  MaskEntry* full_mask = nullptr;
-
-  std::vector<TileResult> res;
-  // cached "every enabled patch, uniform weights" answer of an empty overlap mask
-  std::vector<int64_t> enabled_idx;
-  std::vector<double> uniform_prob, uniform_cum;
-  double uniform_sum = 0.0;
-
-  double last_ms = 0.0;
-  int64_t last_launches = 0;
-  std::vector<cudaEvent_t> dist_ev;  // start/stop pairs around every distance computation of a search
-  std::vector<char> dist_ev_fft;     // per pair: 1 = FFT path
-  double last_fft_ms = 0.0;
-  size_t dist_ev_used = 0;
-  double last_dist_ms = 0.0;
-  int64_t last_dist_launches = 0;
-  int64_t launches = 0;
-};
-
-namespace {
 
 int stage_reserve(iq_ctx* c, size_t bytes) {
   if (bytes <= c->stage_cap) return IQ_OK;
@@ -363,6 +249,9 @@ int get_mask(iq_ctx* c, const uint8_t* mask, MaskEntry** out) {
     CK(cudaMemcpyAsync(e->d_boxes, e->boxes.data(), e->boxes.size() * sizeof(BoxDesc), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
+  CK(cudaMalloc((void**)&e->d_mask, (size_t)c->tilevol));
+  CK(cudaMemcpyAsync(e->d_mask, e->mask.data(), (size_t)c->tilevol, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   choose_shape(c, e->boxes, 1, std::max(1, c->max_batch), &e->WX, &e->WY);
   *out = e.get();
   c->masks.push_back(std::move(e));
@@ -400,10 +289,11 @@ void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* ker
   const long long gstride = e->tmpl_floats * rb;
   std::memset(dst, 0, (size_t)ngrp * gstride * sizeof(float));
   const uint8_t* m = e->mask.data();
+  std::vector<float> dense((size_t)c->tilevol);
   for (int r = 0; r < R; ++r) {
     const int g = r / rb, ri = r % rb;
     const float* k = kern[r];
-    double s = 0.0;
+    for (long long i = 0; i < c->tilevol; ++i) dense[(size_t)i] = m[i] ? k[i] : 0.f;
     for (const BoxDesc& b : e->boxes) {
       float* base = dst + g * gstride + (long long)b.tmpl_off * rb;
       for (int qz = 0; qz < b.d; ++qz)
@@ -414,12 +304,28 @@ void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* ker
             const float v = m[trow + x] ? k[trow + x] : 0.f;
             if (tap_major) drow[(x >> 3) * 8 * rb + (x & 7) * rb + ri] = v;
             else drow[(x >> 3) * 8 * rb + ri * 8 + (x & 7)] = v;
-            s += (double)v * (double)v;
           }
         }
     }
-    b2[r] = s;
+    b2[r] = b2_ordered(dense.data(), c->tx, c->ty, c->tz);
   }
+}
+
+double b2_ordered(const float* v, int tx, int ty, int tz) {
+  // per z plane: 256 strided partial sums (element i goes to partial i mod 256, increasing i), a fixed binary
+  // tree over the partials, then the plane sums are added in z order -- exactly what k_sim_templates does
+  const int plane = tx * ty;
+  double total = 0.0;
+  for (int z = 0; z < tz; ++z) {
+    double part[256];
+    for (int j = 0; j < 256; ++j) part[j] = 0.0;
+    const float* p = v + (size_t)z * plane;
+    for (int i = 0; i < plane; ++i) part[i & 255] += (double)p[i] * (double)p[i];
+    for (int o = 128; o > 0; o >>= 1)
+      for (int j = 0; j < o; ++j) part[j] += part[j + o];
+    total = (z == 0) ? part[0] : total + part[0];
+  }
+  return total;
 }
 
 bool all_integer(const float* v, long long n) {
@@ -441,7 +347,24 @@ bool want_fft(const iq_ctx* c, const MaskEntry* e, int R) {
   return fft < direct;
 }
 
-int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R, float* d_out, int kind) {
+// Records a start/stop event pair around one distance computation (per-search kernel timing for benchmarks).
+static int dist_events(iq_ctx* c, cudaEvent_t* a, cudaEvent_t* b, bool fft) {
+  if (c->dist_ev_used + 2 > c->dist_ev.size()) {
+    cudaEvent_t x, y;
+    CK(cudaEventCreate(&x));
+    CK(cudaEventCreate(&y));
+    c->dist_ev.push_back(x);
+    c->dist_ev.push_back(y);
+  }
+  *a = c->dist_ev[c->dist_ev_used];
+  *b = c->dist_ev[c->dist_ev_used + 1];
+  if (c->dist_ev_fft.size() < c->dist_ev.size() / 2) c->dist_ev_fft.resize(c->dist_ev.size() / 2, 0);
+  c->dist_ev_fft[c->dist_ev_used / 2] = fft ? 1 : 0;
+  c->dist_ev_used += 2;
+  return IQ_OK;
+}
+
+int ensure_fft(iq_ctx* c, int image) {
   if (!c->fft) {
     cudaError_t ce = iqfft::plan_create(&c->fft, c->nx, c->ny, c->nz, c->tx, c->ty, c->tz, c->max_batch, c->stream);
     if (ce != cudaSuccess) {
@@ -452,6 +375,39 @@ int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R,
   }
   const float* d_img = image < 0 ? c->d_ti : c->d_aux[image];
   CK(iqfft::plan_set_image(c->fft, image, d_img, c->stream));
+  return IQ_OK;
+}
+
+// FFT correlation of R dense masked templates that already sit in device memory.
+int launch_fft(iq_ctx* c, MaskEntry* e, int image, const float* d_tmpl, const double* d_b2, int R, bool tint, float* d_out,
+               int kind) {
+  const float* a2 = nullptr;
+  int rc = get_a2(c, e, image, &a2);
+  if (rc) return rc;
+  iqfft::Epilogue ep{};
+  ep.a2 = a2;
+  ep.b2 = d_b2;
+  ep.disabled = c->d_disabled;
+  ep.out = d_out;
+  ep.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch;
+  ep.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch;
+  ep.round_to_int = tint ? 1 : 0;
+  cudaEvent_t ea, eb;
+  rc = dist_events(c, &ea, &eb, true);
+  if (rc) return rc;
+  int nl = 0;
+  CK(cudaEventRecord(ea, c->stream));
+  CK(iqfft::correlate(c->fft, image, d_tmpl, R, ep, c->stream, &nl));
+  CK(cudaEventRecord(eb, c->stream));
+  c->launches += nl;
+  c->last_fft_bytes += iqfft::correlate_bytes(c->fft, R);
+  c->last_fft_searches += R;
+  return IQ_OK;
+}
+
+int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R, float* d_out, int kind) {
+  int rc = ensure_fft(c, image);
+  if (rc) return rc;
   const size_t tbytes = (size_t)R * c->tilevol * sizeof(float);
   const size_t off_t = stage_alloc(c, tbytes);
   const size_t off_b = stage_alloc(c, (size_t)R * sizeof(double));
@@ -461,66 +417,20 @@ int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R,
   const uint8_t* m = e->mask.data();
   bool tint = c->image_is_int[image];
   for (int r = 0; r < R; ++r) {
-    double sum = 0.0;
     float* dst = wk + (size_t)r * c->tilevol;
     const float* k = kern[r];
-    for (long long i = 0; i < c->tilevol; ++i) {
-      const float v = m[i] ? k[i] : 0.f;
-      dst[i] = v;
-      sum += (double)v * (double)v;
-    }
-    b2[r] = sum;
+    for (long long i = 0; i < c->tilevol; ++i) dst[i] = m[i] ? k[i] : 0.f;
+    b2[r] = b2_ordered(dst, c->tx, c->ty, c->tz);
     if (tint) tint = all_integer(dst, c->tilevol);
   }
   CK(cudaMemcpyAsync(c->d_stage + off_t, c->h_stage + off_t, (off_b + R * sizeof(double)) - off_t, cudaMemcpyHostToDevice,
                      c->stream));
-  const float* a2 = nullptr;
-  int rc = get_a2(c, e, image, &a2);
-  if (rc) return rc;
-  iqfft::Epilogue ep{};
-  ep.a2 = a2;
-  ep.b2 = (const double*)(c->d_stage + off_b);
-  ep.disabled = c->d_disabled;
-  ep.out = d_out;
-  ep.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch;
-  ep.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch;
-  ep.round_to_int = tint ? 1 : 0;
-  if (c->dist_ev_used + 2 > c->dist_ev.size()) {
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a));
-    CK(cudaEventCreate(&b));
-    c->dist_ev.push_back(a);
-    c->dist_ev.push_back(b);
-  }
-  int nl = 0;
-  CK(cudaEventRecord(c->dist_ev[c->dist_ev_used], c->stream));
-  CK(iqfft::correlate(c->fft, image, (const float*)(c->d_stage + off_t), R, ep, c->stream, &nl));
-  CK(cudaEventRecord(c->dist_ev[c->dist_ev_used + 1], c->stream));
-  if (c->dist_ev_fft.size() < c->dist_ev.size() / 2) c->dist_ev_fft.resize(c->dist_ev.size() / 2, 0);
-  c->dist_ev_fft[c->dist_ev_used / 2] = 1;
-  c->dist_ev_used += 2;
-  c->launches += nl;
-  c->last_fft_bytes += iqfft::correlate_bytes(c->fft, R);
-  c->last_fft_searches += R;
-  return IQ_OK;
+  return launch_fft(c, e, image, (const float*)(c->d_stage + off_t), (const double*)(c->d_stage + off_b), R, tint, d_out, kind);
 }
 
-int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R, float* d_out, int kind) {
-  if (want_fft(c, e, R)) {
-    const int rcf = run_fft(c, e, image, kern, R, d_out, kind);
-    if (!(rcf == IQ_ERR_STATE && c->fft_failed)) return rcf;
-  }
-  c->last_direct_searches += R;
-  const int rb = pick_rb(c, R);
-  const int ngrp = (R + rb - 1) / rb;
-  const size_t tbytes = (size_t)ngrp * e->tmpl_floats * rb * sizeof(float);
-  const size_t off_t = stage_alloc(c, std::max<size_t>(tbytes, 16));
-  const size_t off_b = stage_alloc(c, (size_t)R * sizeof(double));
-  if (c->stage_used > c->stage_cap) return fail(IQ_ERR_STATE, "staging overflow (internal)");
-  const bool packed = (c->variant == 2 && rb >= 2);  // experimental FFMA2 kernel
-  pack_templates(c, e, kern, R, rb, packed, (float*)(c->h_stage + off_t), (double*)(c->h_stage + off_b));
-  CK(cudaMemcpyAsync(c->d_stage + off_t, c->h_stage + off_t, (off_b + R * sizeof(double)) - off_t, cudaMemcpyHostToDevice,
-                     c->stream));
+// Direct correlation kernel on R templates already packed in device memory ([grp][box][qz][qy][chunk][r(rb)][8]).
+int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, const double* d_b2, int R, int rb, bool packed,
+                  float* d_out, int kind) {
   const float* a2 = nullptr;
   int rc = get_a2(c, e, image, &a2);
   if (rc) return rc;
@@ -531,10 +441,10 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
   p.npos = c->npos;
   p.nbox = (int)e->boxes.size();
   p.boxes = e->d_boxes;
-  p.tmpl = (const float*)(c->d_stage + off_t);
+  p.tmpl = d_packed;
   p.tmpl_grp_stride = e->tmpl_floats * rb;
   p.a2 = a2;
-  p.b2 = (const double*)(c->d_stage + off_b);
+  p.b2 = d_b2;
   p.disabled = c->d_disabled;
   p.out = d_out;
   p.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch;
@@ -561,22 +471,49 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
   } else {
     smem = iq::dist_boxes_smem(e->boxes.data(), p.nbox, p.WX, p.WY, rb, &p.pitch_max, &p.patch_floats);
   }
-  if (c->dist_ev_used + 2 > c->dist_ev.size()) {
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a));
-    CK(cudaEventCreate(&b));
-    c->dist_ev.push_back(a);
-    c->dist_ev.push_back(b);
-  }
-  CK(cudaEventRecord(c->dist_ev[c->dist_ev_used], c->stream));
+  cudaEvent_t ea, eb;
+  rc = dist_events(c, &ea, &eb, false);
+  if (rc) return rc;
+  CK(cudaEventRecord(ea, c->stream));
   if (packed) CK(iq::launch_dist_flat2(p, rb, std::max<size_t>(smem, 64), c->stream));
   else if (c->variant != 1) CK(iq::launch_dist_flat(p, rb, std::max<size_t>(smem, 64), c->stream));
   else CK(iq::launch_dist_boxes(p, rb, std::max<size_t>(smem, 64), c->stream));
-  CK(cudaEventRecord(c->dist_ev[c->dist_ev_used + 1], c->stream));
-  if (c->dist_ev_fft.size() < c->dist_ev.size() / 2) c->dist_ev_fft.resize(c->dist_ev.size() / 2, 0);
-  c->dist_ev_fft[c->dist_ev_used / 2] = 0;
-  c->dist_ev_used += 2;
+  CK(cudaEventRecord(eb, c->stream));
   c->launches++;
+  c->last_direct_searches += R;
+  return IQ_OK;
+}
+
+int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R, float* d_out, int kind) {
+  if (want_fft(c, e, R)) {
+    const int rcf = run_fft(c, e, image, kern, R, d_out, kind);
+    if (!(rcf == IQ_ERR_STATE && c->fft_failed)) return rcf;
+  }
+  const int rb = pick_rb(c, R);
+  const int ngrp = (R + rb - 1) / rb;
+  const size_t tbytes = (size_t)ngrp * e->tmpl_floats * rb * sizeof(float);
+  const size_t off_t = stage_alloc(c, std::max<size_t>(tbytes, 16));
+  const size_t off_b = stage_alloc(c, (size_t)R * sizeof(double));
+  if (c->stage_used > c->stage_cap) return fail(IQ_ERR_STATE, "staging overflow (internal)");
+  const bool packed = (c->variant == 2 && rb >= 2);  // experimental FFMA2 kernel
+  pack_templates(c, e, kern, R, rb, packed, (float*)(c->h_stage + off_t), (double*)(c->h_stage + off_b));
+  CK(cudaMemcpyAsync(c->d_stage + off_t, c->h_stage + off_t, (off_b + R * sizeof(double)) - off_t, cudaMemcpyHostToDevice,
+                     c->stream));
+  return launch_direct(c, e, image, (const float*)(c->d_stage + off_t), (const double*)(c->d_stage + off_b), R, rb, packed,
+                       d_out, kind);
+}
+
+// Sums the event pairs recorded since dist_ev_used was last reset into last_dist_ms / last_fft_ms.
+int collect_dist_times(iq_ctx* c) {
+  c->last_dist_ms = 0.0;
+  c->last_fft_ms = 0.0;
+  c->last_dist_launches = (int64_t)(c->dist_ev_used / 2);
+  for (size_t i = 0; i + 1 < c->dist_ev_used; i += 2) {
+    float dm = 0.f;
+    CK(cudaEventElapsedTime(&dm, c->dist_ev[i], c->dist_ev[i + 1]));
+    c->last_dist_ms += dm;
+    if (c->dist_ev_fft[i / 2]) c->last_fft_ms += dm;
+  }
   return IQ_OK;
 }
 
@@ -915,19 +852,12 @@ int do_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int ntile
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->last_ms = ms;
   c->last_launches = c->launches - l0;
-  c->last_dist_ms = 0.0;
-  c->last_fft_ms = 0.0;
-  c->last_dist_launches = (int64_t)(c->dist_ev_used / 2);
-  for (size_t i = 0; i + 1 < c->dist_ev_used; i += 2) {
-    float dm = 0.f;
-    CK(cudaEventElapsedTime(&dm, c->dist_ev[i], c->dist_ev[i + 1]));
-    c->last_dist_ms += dm;
-    if (c->dist_ev_fft[i / 2]) c->last_fft_ms += dm;
-  }
-  return IQ_OK;
+  return collect_dist_times(c);
 }
 
-}  // namespace
+}  // namespace iqimpl
+
+using namespace iqimpl;
 
 // ================================================================================================
 // exported ABI
@@ -979,8 +909,11 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   cudaFree(c->d_colsum);
   cudaFree(c->d_prob);
   if (c->h_prob) cudaFreeHost(c->h_prob);
+  sim_destroy(c);
   for (auto& e : c->masks) {
     cudaFree(e->d_boxes);
+    cudaFree(e->d_mask);
+    cudaFree(e->d_cut_tasks);
     for (auto& kv : e->a2) cudaFree(kv.second);
   }
   iqfft::plan_destroy(c->fft);

@@ -150,8 +150,180 @@ extern "C" int32_t iqh_graphcut(const double* A, const double* B, int32_t ndim, 
   return IQ_OK;
 }
 
+
+namespace {
+
+// Overlap slabs of tile `ind` with its already pasted neighbours (iqsim.jl:188-205) and the overlap mask.
+void tile_slabs(const Geo& G, const std::vector<uint8_t>& pasted, int64_t ind, std::vector<Slab>& slabs, std::vector<uint8_t>& mask,
+                int start[3]) {
+  const int* t = G.t;
+  const int ti3[3] = {(int)(ind % G.nt[0]), (int)((ind / G.nt[0]) % G.nt[1]), (int)(ind / ((long long)G.nt[0] * G.nt[1]))};
+  for (int i = 0; i < 3; ++i) start[i] = ti3[i] * G.sp[i];
+  const long long tstride[3] = {1, G.nt[0], (long long)G.nt[0] * G.nt[1]};
+  slabs.clear();
+  for (int d = 0; d < G.N; ++d) {
+    if (G.ov[d] <= 1) continue;
+    if (ti3[d] > 0 && pasted[(size_t)(ind - tstride[d])]) {
+      Slab s{d, true, {0, 0, 0}, {t[0], t[1], t[2]}};
+      s.sz[d] = G.ov[d];
+      slabs.push_back(s);
+    }
+    if (ti3[d] + 1 < G.nt[d] && pasted[(size_t)(ind + tstride[d])]) {
+      Slab s{d, false, {0, 0, 0}, {t[0], t[1], t[2]}};
+      s.lo[d] = G.sp[d];
+      s.sz[d] = t[d] - G.sp[d];
+      slabs.push_back(s);
+    }
+  }
+  std::fill(mask.begin(), mask.end(), 0);
+  for (const Slab& s : slabs)
+    for (int z = s.lo[2]; z < s.lo[2] + s.sz[2]; ++z)
+      for (int y = s.lo[1]; y < s.lo[1] + s.sz[1]; ++y)
+        std::memset(&mask[((size_t)z * t[1] + y) * t[0] + s.lo[0]], 1, (size_t)s.sz[0]);
+}
+
+// Device-resident pipeline: every lockstep group owns a context whose stream carries the whole simulation of its
+// realizations (iq_sim_*); this thread only enqueues.  Returns IQ_ERR_STATE when the simulation does not qualify
+// (the caller then runs host-staged), `*status` != 0 when a data-dependent condition invalidated the result.
+int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats,
+                 int* status) {
+  *status = 0;
+  if (D->nsoft > 0 || D->hard_has) return IQ_ERR_STATE;
+  const auto t_start = clk::now();
+  const int R = D->nreal;
+  int ngroups = D->ngroups > 0 ? D->ngroups : (R >= 16 ? 2 : 1);
+  ngroups = std::max(1, std::min(ngroups, R));
+  struct RG { iq_ctx* ctx = nullptr; int r0 = 0, R = 0; };
+  std::vector<RG> groups(ngroups);
+  auto destroy_all = [&] {
+    for (auto& g : groups)
+      if (g.ctx) { iq_ctx_destroy(g.ctx); g.ctx = nullptr; }
+  };
+  const auto t_setup = clk::now();
+  int rc = IQ_OK;
+  for (int gi = 0; gi < ngroups && rc == IQ_OK; ++gi) {
+    RG& g = groups[gi];
+    g.r0 = (int)((long long)R * gi / ngroups);
+    g.R = (int)((long long)R * (gi + 1) / ngroups) - g.r0;
+    iq_ctx_desc cd{};
+    cd.ndim = G.N;
+    for (int i = 0; i < 3; ++i) { cd.ti_size[i] = G.n[i]; cd.tile_size[i] = G.t[i]; }
+    cd.ti = D->ti_f32;
+    cd.disabled = D->disabled;
+    cd.nsoft = 0;
+    cd.device = D->device;
+    cd.max_batch = g.R;
+    rc = iq_ctx_create(&g.ctx, &cd);
+    if (rc != IQ_OK) break;
+    iq_ctx_set_option(g.ctx, "fft", D->fft_mode);
+    iq_sim_desc sd{};
+    for (int i = 0; i < 3; ++i) { sd.pad_size[i] = G.pad[i]; sd.ovl_size[i] = G.ov[i]; }
+    sd.nreal = g.R;
+    sd.ti64 = D->ti;
+    sd.u = D->u + (size_t)g.r0 * D->npath;
+    sd.npath = D->npath;
+    sd.tol = D->tol;
+    sd.debug = D->debug;
+    rc = iq_sim_begin(g.ctx, &sd);
+  }
+  if (rc != IQ_OK) { destroy_all(); return rc; }
+  const double setup_ms = ms_since(t_setup);
+
+  std::vector<uint8_t> pasted((size_t)G.ntile_total, 0), mask((size_t)G.tilevol);
+  std::vector<Slab> slabs;
+  std::vector<iq_sim_slab> sl;
+  int64_t launches = 0;
+  const auto t_enq = clk::now();
+  for (int64_t step = 0; step < D->npath && rc == IQ_OK; ++step) {
+    const int64_t ind = D->path[step];
+    if (ind < 0 || ind >= G.ntile_total) { rc = IQ_ERR_INVALID; break; }
+    int start[3];
+    tile_slabs(G, pasted, ind, slabs, mask, start);
+    sl.resize(slabs.size());
+    for (size_t k = 0; k < slabs.size(); ++k) {
+      sl[k].dim = slabs[k].d;
+      sl[k].prev = slabs[k].prev ? 1 : 0;
+      for (int i = 0; i < 3; ++i) { sl[k].lo[i] = slabs[k].lo[i]; sl[k].sz[i] = slabs[k].sz[i]; }
+    }
+    const int64_t st64[3] = {start[0], start[1], start[2]};
+    for (auto& g : groups) {
+      rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size());
+      if (rc != IQ_OK) break;
+      double dms = 0;
+      int64_t nl = 0;
+      iq_last_search_stats(g.ctx, &dms, &nl);
+      launches += nl;
+    }
+    pasted[(size_t)ind] = 1;
+  }
+  const double enqueue_ms = ms_since(t_enq);
+  double device_ms = 0, dist_ms = 0, select_ms = 0, cut_ms = 0, fft_bytes = 0, fft_ms = 0;
+  int64_t nfft = 0, ndirect = 0, dist_launches = 0;
+  for (auto& g : groups) {
+    if (rc != IQ_OK) break;
+    int32_t st = 0;
+    rc = iq_sim_sync(g.ctx, out_picks ? out_picks + (size_t)g.r0 * D->npath : nullptr, &st);
+    if (rc != IQ_OK) break;
+    *status |= st;
+    double a = 0, b = 0, c2 = 0, d2 = 0;
+    iq_sim_times(g.ctx, &a, &b, &c2, &d2);
+    device_ms = std::max(device_ms, a);
+    dist_ms += b; select_ms += c2; cut_ms += d2;
+    int64_t nd = 0, nf = 0;
+    double fb = 0, fm = 0;
+    iq_last_search_path(g.ctx, &nd, &nf, &fb, &fm);
+    ndirect += nd; nfft += nf; fft_bytes += fb; fft_ms += fm;
+    double dm = 0;
+    int64_t dl = 0;
+    iq_last_search_kernel_ms(g.ctx, &dm, &dl);
+    dist_launches += dl;
+  }
+  const double run_ms = ms_since(t_enq);
+  const auto t_fetch = clk::now();
+  if (rc == IQ_OK && *status == 0) {
+    const int64_t padc[3] = {G.pad[0], G.pad[1], G.pad[2]};
+    for (auto& g : groups) {
+      for (int r = 0; r < g.R && rc == IQ_OK; ++r) {
+        if (D->out_real) rc = iq_sim_fetch(g.ctx, r, D->out_real_f32 ? 1 : 0, D->sim_size, D->out_real[g.r0 + r]);
+        if (rc == IQ_OK && out_grids) rc = iq_sim_fetch(g.ctx, r, 0, padc, out_grids + (size_t)(g.r0 + r) * G.padvol);
+        if (rc == IQ_OK && D->debug) rc = iq_sim_fetch_cut(g.ctx, r, out_cuts + (size_t)(g.r0 + r) * G.padvol);
+      }
+      if (rc != IQ_OK) break;
+    }
+  }
+  const double fetch_ms = ms_since(t_fetch);
+  destroy_all();
+  if (rc != IQ_OK) return rc;
+  if (stats && *status == 0) {
+    std::memset(stats, 0, sizeof *stats);
+    stats->resident = 1;
+    stats->search_ms = enqueue_ms;        // wall time this thread spent enqueueing
+    stats->search_device_ms = dist_ms;
+    stats->cut_ms = 0.0;
+    stats->total_ms = ms_since(t_start);
+    stats->searches = (int64_t)R * D->npath;
+    stats->kernel_launches = launches;
+    stats->setup_ms = setup_ms;
+    stats->dist_kernel_ms = dist_ms;
+    stats->dist_launches = dist_launches;
+    stats->fft_searches = nfft;
+    stats->direct_searches = ndirect;
+    stats->fft_bytes = fft_bytes;
+    stats->fft_ms = fft_ms;
+    stats->device_ms = device_ms;
+    stats->select_ms = select_ms;
+    stats->cut_device_ms = cut_ms;
+    stats->fetch_ms = fetch_ms;
+    (void)run_ms;
+  }
+  return IQ_OK;
+}
+
+}  // namespace
+
 extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats) {
-  if (!D || !out_grids || !D->ti || !D->ti_f32 || !D->path || !D->u) return IQ_ERR_INVALID;
+  if (!D || !D->ti || !D->ti_f32 || !D->path || !D->u) return IQ_ERR_INVALID;
+  if (!out_grids && !D->out_real) return IQ_ERR_INVALID;
   if (D->debug && !out_cuts) return IQ_ERR_INVALID;
   const auto t_start = clk::now();
   Geo G{};
@@ -171,6 +343,20 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
   const int* n = G.n;
   const int* t = G.t;
   const int* pad = G.pad;
+  if (D->pipeline < 0 || D->pipeline > 2) return IQ_ERR_INVALID;
+
+  int resident_status = 0;
+  if (D->pipeline != 1) {
+    const int rcr = run_resident(D, G, out_grids, out_cuts, out_picks, stats, &resident_status);
+    if (rcr == IQ_OK && resident_status == 0) return IQ_OK;
+    if (rcr != IQ_OK && !(rcr == IQ_ERR_STATE && D->pipeline == 0)) return rcr;  // explicit request or a real error
+    // otherwise: does not qualify (or a data-dependent bail-out): host-staged below, still on the GPU
+  }
+  std::vector<double> own_grids;
+  if (!out_grids) {
+    own_grids.resize((size_t)G.padvol * R);
+    out_grids = own_grids.data();
+  }
 
   // one core stays with the thread that drives the GPU; the rest form the cut/paste team
   const int hw = std::max(1, (int)std::thread::hardware_concurrency());
@@ -472,7 +658,28 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
   }
   destroy_all();
   if (rc != IQ_OK) return rc;
+  if (D->out_real) {
+    int cs[3] = {1, 1, 1};
+    for (int i = 0; i < G.N; ++i) cs[i] = (int)std::min<int64_t>(D->sim_size[i], pad[i]);
+    for (int r = 0; r < R; ++r) {
+      const double* g = out_grids + (size_t)r * G.padvol;
+      size_t o = 0;
+      for (int z = 0; z < cs[2]; ++z)
+        for (int y = 0; y < cs[1]; ++y) {
+          const double* src = g + ((size_t)z * pad[1] + y) * pad[0];
+          if (D->out_real_f32) {
+            float* dst = (float*)D->out_real[r] + o;
+            for (int x = 0; x < cs[0]; ++x) dst[x] = (float)src[x];
+          } else {
+            std::memcpy((double*)D->out_real[r] + o, src, sizeof(double) * cs[0]);
+          }
+          o += cs[0];
+        }
+    }
+  }
   if (stats) {
+    std::memset(stats, 0, sizeof *stats);
+    stats->resident_status = resident_status;
     stats->search_ms = search_ms;
     stats->search_device_ms = search_dev_ms;
     stats->cut_ms = cut_ms;

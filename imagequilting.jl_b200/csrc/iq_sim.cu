@@ -1,0 +1,638 @@
+// iq_sim.cu -- device-resident simulation: the grids of all realizations of a context stay in device memory and a
+// whole path step is enqueued on the context's stream without any host synchronisation (include/iqb200.h,
+// iq_sim_*).  SURVEY.md 8(f) rank 2 ("tile paste / simgrid on device + realization-lockstep driver").
+//
+// Restated reference code (relative to /root/reference/):
+//   tile view of the simulation grid        src/iqsim.jl:185          -> k_sim_templates
+//   overlap distance + threshold selection  src/iqsim.jl:187-237      -> existing distance / pick kernels
+//   tau model                               src/taumodel.jl:5-45      -> k_tau_rank / k_tau_prob
+//   sample(rng, patterndb, weights(p))      src/iqsim.jl:243          -> k_sim_sample (pre-drawn uniforms)
+//   boundary cut per overlap slab           src/iqsim.jl:251-275, src/graphcut.jl:5-84 -> k_sim_slabs + k_graphcut
+//   simdev[.!cutmask] = TIdev[.!cutmask]    src/iqsim.jl:278          -> k_sim_paste
+// The host only decides what depends on the path alone (tile origin, overlap mask, slabs) and enqueues kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "iq_ctx.h"
+
+namespace iqimpl {
+
+struct SlabDev {
+  int dim, prev;
+  int lo[3], sz[3];
+  int n0, n1, L;        // cut layout: [L][n1][n0], cut dimension slowest
+  int st_a, st_b, st_k; // strides (in tile voxels) of the layout axes inside the tile
+};
+struct SlabSet {
+  int n;
+  SlabDev s[6];
+};
+
+struct SimState {
+  int R = 0;
+  int pad[3] = {1, 1, 1};
+  long long padvol = 0;
+  int64_t npath = 0;
+  double tol = 0.1;
+  int debug = 0;
+  double* d_grid = nullptr;       // [R][padvol]
+  uint8_t* d_cutgrid = nullptr;   // [R][padvol] (debug)
+  double* d_ti64 = nullptr;       // [nimg]
+  double* d_u = nullptr;          // [R][npath]
+  std::vector<double> h_u;
+  float* d_tmpl = nullptr;        // [R][tilevol] dense masked templates
+  float* d_pack = nullptr;        // packed templates of the direct kernel
+  size_t pack_cap = 0;
+  double* d_b2 = nullptr;         // [R]
+  double* d_plane = nullptr;      // [R][tz] plane sums of B2
+  unsigned* d_ticket = nullptr;   // [R]
+  long long* d_picked = nullptr;  // [R] pattern chosen in the current step
+  long long* d_picks = nullptr;   // [R][npath]
+  long long* h_pickstage = nullptr;  // pinned [npath][R]: picks of empty-mask steps (computed on the host)
+  int* d_status = nullptr;
+  double* d_cutA = nullptr;
+  double* d_cutB = nullptr;
+  uint8_t* d_keep = nullptr;
+  int* d_cut_iters = nullptr;
+  size_t maxslab = 0;             // voxels of the largest slab
+  int maxslabs = 0;               // slabs per tile at most
+  void* d_export = nullptr;       // cropped realization in the output type
+  size_t export_cap = 0;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> ev;    // per step: select start, select stop (= cut start), cut stop
+  size_t ev_used = 0;
+  double total_ms = 0, dist_ms = 0, select_ms = 0, cut_ms = 0;
+  bool synced = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+// Dense masked templates (zeros outside the overlap mask) of every realization + B2 = sum of their squares in the
+// library's fixed order (b2_ordered in iq_ctx.cu): one CTA per (z plane, realization).
+__global__ void __launch_bounds__(256) k_sim_templates(const double* __restrict__ grid, long long padvol, int p0, int p1,
+                                                       int sx, int sy, int sz, const uint8_t* __restrict__ mask, int tx,
+                                                       int ty, int tz, float* __restrict__ tmpl, double* __restrict__ plane,
+                                                       double* __restrict__ b2, unsigned* __restrict__ ticket) {
+  const int z = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;
+  const int pl = tx * ty;
+  const double* g = grid + (long long)r * padvol + ((long long)(sz + z) * p1 + sy) * p0 + sx;
+  const uint8_t* m = mask + (long long)z * pl;
+  float* out = tmpl + ((long long)r * tz + z) * pl;
+  double acc = 0.0;
+  for (int i = tid; i < pl; i += 256) {
+    const int y = i / tx, x = i - y * tx;
+    const float v = m[i] ? (float)g[(long long)y * p0 + x] : 0.f;
+    out[i] = v;
+    acc = __dadd_rn(acc, __dmul_rn((double)v, (double)v));
+  }
+  __shared__ double s[256];
+  __shared__ int s_last;
+  s[tid] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) s[tid] = __dadd_rn(s[tid], s[tid + o]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    plane[(long long)r * tz + z] = s[0];
+    __threadfence();
+    s_last = (atomicAdd(&ticket[r], 1u) == (unsigned)(tz - 1));
+  }
+  __syncthreads();
+  if (!s_last || tid != 0) return;
+  __threadfence();
+  const volatile double* pv = plane + (long long)r * tz;
+  double tot = pv[0];
+  for (int k = 1; k < tz; ++k) tot = __dadd_rn(tot, pv[k]);
+  b2[r] = tot;
+  ticket[r] = 0u;
+}
+
+// Dense masked templates -> layout of the direct kernel [grp][box][qz][qy][chunk][r(rb)][8] (zero padded).
+__global__ void __launch_bounds__(256) k_sim_pack(const float* __restrict__ tmpl, long long tilevol, int tx, int ty,
+                                                  const iq::BoxDesc* __restrict__ boxes, int nbox, long long tmpl_floats,
+                                                  int rb, int R, long long total, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const long long gstride = tmpl_floats * rb;
+  const int g = (int)(i / gstride);
+  long long w = i - (long long)g * gstride;
+  int b = nbox - 1;
+  while (b > 0 && (long long)boxes[b].tmpl_off * rb > w) --b;
+  const iq::BoxDesc B = boxes[b];
+  w -= (long long)B.tmpl_off * rb;
+  const int tap = (int)(w & 7);
+  long long q = w >> 3;
+  const int ri = (int)(q % rb); q /= rb;
+  const int ch = (int)(q % B.nch); q /= B.nch;
+  const int qy = (int)(q % B.h);
+  const int qz = (int)(q / B.h);
+  const int x = ch * 8 + tap, r = g * rb + ri;
+  float v = 0.f;
+  if (r < R && x < B.w) v = tmpl[(long long)r * tilevol + ((long long)(B.z0 + qz) * ty + (B.y0 + qy)) * tx + B.x0 + x];
+  out[i] = v;
+}
+
+// Base.sum's pairwise reduction (Base.mapreduce_impl, block 1024), as julia_sum in iq_ctx.cu.
+__device__ double dev_julia_sum(const double* w, int lo, int hi) {
+  if (hi - lo < 1024) {
+    double v = w[lo];
+    for (int i = lo + 1; i <= hi; ++i) v = __dadd_rn(v, w[i]);
+    return v;
+  }
+  const int mid = lo + ((hi - lo) >> 1);
+  return __dadd_rn(dev_julia_sum(w, lo, mid), dev_julia_sum(w, mid + 1, hi));
+}
+
+// StatsBase.sample walk (iqsim.jl:243) on the candidate list of every realization; one thread each.
+// status bits: 1 = candidate set outside 1..kTauMax, 2 = a boundary cut hit its iteration cap.
+__global__ void k_sim_sample(const iq::PickJob* __restrict__ jobs, const double* __restrict__ prob,
+                             const double* __restrict__ u, long long npath, long long step, int R,
+                             long long* __restrict__ picked, long long* __restrict__ picks, int* __restrict__ status) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const iq::PickJob& J = jobs[r];
+  const unsigned n = *J.total;
+  long long pos = 0;
+  if (n == 0u || n > (unsigned)iq::kTauMax) {
+    atomicOr(status, 1);
+  } else if (n > 1u) {
+    const double* p = prob + (long long)r * iq::kTauMax;
+    const double t = __dmul_rn(u[(long long)r * npath + step], dev_julia_sum(p, 0, (int)n - 1));
+    double cw = p[0];
+    unsigned i = 0;
+    while (cw < t && i < n - 1u) { ++i; cw = __dadd_rn(cw, p[i]); }
+    pos = i;
+  }
+  const long long pk = (n == 0u) ? 0 : (long long)J.cand_idx[pos];
+  picked[r] = pk;
+  picks[(long long)r * npath + step] = pk;
+}
+
+__global__ void k_sim_store_picks(const long long* __restrict__ picked, long long* __restrict__ picks, long long npath,
+                                  long long step, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) picks[(long long)r * npath + step] = picked[r];
+}
+
+// Overlap slabs of every realization in the cut kernel's layout: A = pasted content, B = chosen patch.
+__global__ void __launch_bounds__(256) k_sim_slabs(const double* __restrict__ grid, long long padvol, int p0, int p1, int sx,
+                                                   int sy, int sz, const double* __restrict__ ti, int nx, int ny, int nxo,
+                                                   int nyo, const long long* __restrict__ picked, int tx, int ty,
+                                                   const SlabSet S, double* __restrict__ A, double* __restrict__ B,
+                                                   long long maxslab) {
+  const int task = blockIdx.x, r = task / S.n;
+  const SlabDev& s = S.s[task - r * S.n];
+  const long long pk = picked[r];
+  const int rx = (int)(pk % nxo), ry = (int)((pk / nxo) % nyo), rz = (int)(pk / ((long long)nxo * nyo));
+  const double* g = grid + (long long)r * padvol;
+  double* a = A + (long long)task * maxslab;
+  double* b = B + (long long)task * maxslab;
+  const int nv = s.n0 * s.n1 * s.L;
+  const int q0 = (s.lo[2] * ty + s.lo[1]) * tx + s.lo[0];
+  for (int o = threadIdx.x; o < nv; o += 256) {
+    const int aa = o % s.n0, t = o / s.n0, bb = t % s.n1, kk = t / s.n1;
+    const int q = q0 + aa * s.st_a + bb * s.st_b + kk * s.st_k;  // voxel inside the tile
+    const int qx = q % tx, qt = q / tx, qy = qt % ty, qz = qt / ty;
+    a[o] = g[((long long)(sz + qz) * p1 + (sy + qy)) * p0 + sx + qx];
+    b[o] = ti[((long long)(rz + qz) * ny + (ry + qy)) * nx + rx + qx];
+  }
+}
+
+// cutmask = OR over the slabs of (prev ? keep : !keep) (iqsim.jl:264,273); simdev[.!cutmask] = TIdev[.!cutmask].
+__global__ void __launch_bounds__(256) k_sim_paste(double* __restrict__ grid, uint8_t* __restrict__ cutgrid, long long padvol,
+                                                   int p0, int p1, int sx, int sy, int sz, const double* __restrict__ ti,
+                                                   int nx, int ny, int nxo, int nyo, const long long* __restrict__ picked,
+                                                   int tx, int ty, int tz, const SlabSet S, const uint8_t* __restrict__ keep,
+                                                   long long maxslab, const int* __restrict__ cut_iters,
+                                                   int* __restrict__ status) {
+  const int r = blockIdx.y;
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q == 0 && S.n > 0) {
+    bool bad = false;
+    for (int k = 0; k < S.n; ++k) bad |= cut_iters[r * S.n + k] < 0;
+    if (bad) atomicOr(status, 2);
+  }
+  if (q >= tx * ty * tz) return;
+  const int qx = q % tx, qt = q / tx, qy = qt % ty, qz = qt / ty;
+  unsigned cm = 0;
+  for (int k = 0; k < S.n; ++k) {
+    const SlabDev& s = S.s[k];
+    const int lx = qx - s.lo[0], ly = qy - s.lo[1], lz = qz - s.lo[2];
+    if (lx < 0 || ly < 0 || lz < 0 || lx >= s.sz[0] || ly >= s.sz[1] || lz >= s.sz[2]) continue;
+    const int l[3] = {lx, ly, lz};
+    const int da = s.dim == 0 ? 1 : 0, db = s.dim == 2 ? 1 : 2;
+    const int o = (l[s.dim] * s.n1 + l[db]) * s.n0 + l[da];
+    const unsigned kv = keep[(long long)(r * S.n + k) * maxslab + o];
+    cm |= s.prev ? kv : (kv ^ 1u);
+  }
+  const long long pk = picked[r];
+  const int rx = (int)(pk % nxo), ry = (int)((pk / nxo) % nyo), rz = (int)(pk / ((long long)nxo * nyo));
+  const long long gi = (long long)r * padvol + ((long long)(sz + qz) * p1 + (sy + qy)) * p0 + sx + qx;
+  if (!cm) grid[gi] = ti[((long long)(rz + qz) * ny + (ry + qy)) * nx + rx + qx];
+  if (cutgrid) cutgrid[gi] = (uint8_t)cm;
+}
+
+template <typename OT>
+__global__ void __launch_bounds__(256) k_sim_export(const double* __restrict__ grid, int p0, int p1, int c0, int c1, int c2,
+                                                    OT* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long n = (long long)c0 * c1 * c2;
+  if (i >= n) return;
+  const int x = (int)(i % c0);
+  const long long t = i / c0;
+  const int y = (int)(t % c1), z = (int)(t / c1);
+  out[i] = (OT)grid[((long long)z * p1 + y) * p0 + x];
+}
+
+void sim_destroy(iq_ctx* c) {
+  SimState* s = c->sim;
+  if (!s) return;
+  cudaFree(s->d_grid); cudaFree(s->d_cutgrid); cudaFree(s->d_ti64); cudaFree(s->d_u); cudaFree(s->d_tmpl);
+  cudaFree(s->d_pack); cudaFree(s->d_b2); cudaFree(s->d_plane); cudaFree(s->d_ticket); cudaFree(s->d_picked);
+  cudaFree(s->d_picks); cudaFree(s->d_status); cudaFree(s->d_cutA); cudaFree(s->d_cutB); cudaFree(s->d_keep);
+  cudaFree(s->d_cut_iters); cudaFree(s->d_export);
+  if (s->h_pickstage) cudaFreeHost(s->h_pickstage);
+  for (auto e : s->ev) cudaEventDestroy(e);
+  if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+  if (s->ev_end) cudaEventDestroy(s->ev_end);
+  delete s;
+  c->sim = nullptr;
+  // the task records cached per mask point into the freed slab buffers
+  for (auto& e : c->masks) {
+    cudaFree(e->d_cut_tasks);
+    e->d_cut_tasks = nullptr;
+    e->cut_ntask = 0;
+  }
+}
+
+namespace {
+
+constexpr size_t kCutSmemLimit = 220 * 1024;
+
+bool slab_fits(int n0, int n1, int L) {
+  if (L < 2) return false;
+  if (L == 2) return true;  // no inner voxel: the kernel only writes the source / sink slices
+  return iq::graphcut_smem(n0, n1, L) <= kCutSmemLimit && (long long)(L - 2) * n0 * n1 <= 4096;
+}
+
+int sim_events(SimState* s, cudaEvent_t* out, int n) {
+  while (s->ev_used + n > s->ev.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    s->ev.push_back(e);
+  }
+  for (int i = 0; i < n; ++i) out[i] = s->ev[s->ev_used + i];
+  s->ev_used += n;
+  return IQ_OK;
+}
+
+}  // namespace
+}  // namespace iqimpl
+
+using namespace iqimpl;
+
+extern "C" {
+
+int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
+  if (!c || !d || !d->ti64 || !d->u) return fail(IQ_ERR_INVALID, "iq_sim_begin: NULL argument");
+  if (d->nreal < 1 || d->nreal > c->max_batch) return fail(IQ_ERR_INVALID, "iq_sim_begin: nreal must be in 1..max_batch");
+  if (d->npath < 0) return fail(IQ_ERR_INVALID, "iq_sim_begin: npath < 0");
+  if (!(d->tol > 0.0 && d->tol <= 1.0)) return fail(IQ_ERR_INVALID, "tolerance must be in range (0,1]");
+  if (c->nsoft > 0) return fail(IQ_ERR_STATE, "resident simulation covers the threshold path only (context has soft data)");
+  CK(cudaSetDevice(c->device));
+  sim_destroy(c);
+  const int t[3] = {c->tx, c->ty, c->tz};
+  int pad[3] = {1, 1, 1}, ov[3] = {1, 1, 1};
+  for (int i = 0; i < c->ndim; ++i) {
+    pad[i] = (int)d->pad_size[i];
+    ov[i] = (int)d->ovl_size[i];
+    if (pad[i] < t[i] || ov[i] < 0 || ov[i] >= t[i] + 1) return fail(IQ_ERR_INVALID, "iq_sim_begin: bad pad_size / ovl_size");
+  }
+  size_t maxslab = 1;
+  int maxslabs = 0;
+  for (int dd = 0; dd < c->ndim; ++dd) {
+    if (ov[dd] <= 1) continue;
+    const int da = dd == 0 ? 1 : 0, db = dd == 2 ? 1 : 2;
+    if (!slab_fits(t[da], t[db], ov[dd]))
+      return fail(IQ_ERR_STATE, "overlap slab %d x %d x %d does not fit the shared-memory cut kernel", t[da], t[db], ov[dd]);
+    maxslab = std::max(maxslab, (size_t)t[da] * t[db] * ov[dd]);
+    maxslabs += 2;
+  }
+  SimState* s = new SimState();
+  c->sim = s;
+  s->R = d->nreal;
+  for (int i = 0; i < 3; ++i) s->pad[i] = pad[i];
+  s->padvol = (long long)pad[0] * pad[1] * pad[2];
+  s->npath = d->npath;
+  s->tol = d->tol;
+  s->debug = d->debug;
+  s->maxslab = maxslab;
+  s->maxslabs = std::max(maxslabs, 1);
+  const size_t R = (size_t)s->R, nimg = (size_t)c->nx * c->ny * c->nz, np = (size_t)std::max<int64_t>(d->npath, 1);
+  CK(cudaMalloc((void**)&s->d_grid, R * s->padvol * sizeof(double)));
+  CK(cudaMemsetAsync(s->d_grid, 0, R * s->padvol * sizeof(double), c->stream));  // simgrid = zeros (iqsim.jl:165)
+  if (s->debug) {
+    CK(cudaMalloc((void**)&s->d_cutgrid, R * s->padvol));
+    CK(cudaMemsetAsync(s->d_cutgrid, 0, R * s->padvol, c->stream));
+  }
+  CK(cudaMalloc((void**)&s->d_ti64, nimg * sizeof(double)));
+  CK(cudaMemcpyAsync(s->d_ti64, d->ti64, nimg * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  s->h_u.assign(d->u, d->u + R * (size_t)d->npath);
+  CK(cudaMalloc((void**)&s->d_u, R * np * sizeof(double)));
+  if (d->npath > 0)
+    CK(cudaMemcpyAsync(s->d_u, d->u, R * (size_t)d->npath * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMalloc((void**)&s->d_tmpl, R * c->tilevol * sizeof(float)));
+  CK(cudaMalloc((void**)&s->d_b2, R * sizeof(double)));
+  CK(cudaMalloc((void**)&s->d_plane, R * c->tz * sizeof(double)));
+  CK(cudaMalloc((void**)&s->d_ticket, R * sizeof(unsigned)));
+  CK(cudaMemsetAsync(s->d_ticket, 0, R * sizeof(unsigned), c->stream));
+  CK(cudaMalloc((void**)&s->d_picked, R * sizeof(long long)));
+  CK(cudaMalloc((void**)&s->d_picks, R * np * sizeof(long long)));
+  CK(cudaMemsetAsync(s->d_picks, 0xff, R * np * sizeof(long long), c->stream));
+  CK(cudaMallocHost((void**)&s->h_pickstage, R * np * sizeof(long long)));
+  CK(cudaMalloc((void**)&s->d_status, sizeof(int)));
+  CK(cudaMemsetAsync(s->d_status, 0, sizeof(int), c->stream));
+  const size_t ntask = R * s->maxslabs;
+  CK(cudaMalloc((void**)&s->d_cutA, ntask * maxslab * sizeof(double)));
+  CK(cudaMalloc((void**)&s->d_cutB, ntask * maxslab * sizeof(double)));
+  CK(cudaMalloc((void**)&s->d_keep, ntask * maxslab));
+  CK(cudaMalloc((void**)&s->d_cut_iters, ntask * sizeof(int)));
+  CK(cudaMemsetAsync(s->d_cut_iters, 0, ntask * sizeof(int), c->stream));
+  // selection jobs never change during the simulation: threshold rule on the overlap distance of realization r
+  for (int r = 0; r < s->R; ++r) {
+    iq::PickJob& J = c->h_pick[r];
+    std::memset(&J, 0, sizeof J);
+    J.mode = 0;
+    J.nsrc = 1;
+    J.src[0] = c->d_Dovl + (size_t)r * c->npos;
+    J.sel = c->d_sel + (size_t)r * c->max_src;
+    J.tol = s->tol;
+    J.minbits = c->d_minmax + r;
+    J.blockcount = c->d_blockcount + (size_t)r * iq::pick_nblk(c->npos);
+    J.total = c->d_total + r;
+    J.cand_idx = c->d_cand_idx + (size_t)r * c->npos;
+    J.cand_val = c->d_cand_val + (size_t)r * c->max_src * c->npos;
+    J.cap = c->npos;
+  }
+  CK(cudaMemcpyAsync(c->d_pick, c->h_pick, R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventCreate(&s->ev_begin));
+  CK(cudaEventCreate(&s->ev_end));
+  CK(cudaStreamSynchronize(c->stream));
+  c->dist_ev_used = 0;
+  c->last_fft_bytes = 0.0;
+  c->last_fft_searches = c->last_direct_searches = 0;
+  CK(cudaEventRecord(s->ev_begin, c->stream));
+  return IQ_OK;
+}
+
+int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
+                    int32_t nslab) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step: no simulation open on this context");
+  SimState* s = c->sim;
+  if (!start || !ovlmask || nslab < 0 || nslab > 6 || (nslab > 0 && !slabs)) return fail(IQ_ERR_INVALID, "iq_sim_step: bad argument");
+  if (step < 0 || step >= s->npath) return fail(IQ_ERR_INVALID, "iq_sim_step: step out of range");
+  CK(cudaSetDevice(c->device));
+  const int t[3] = {c->tx, c->ty, c->tz};
+  int st3[3] = {0, 0, 0};
+  for (int i = 0; i < c->ndim; ++i) {
+    st3[i] = (int)start[i];
+    if (st3[i] < 0 || st3[i] + t[i] > s->pad[i]) return fail(IQ_ERR_INVALID, "iq_sim_step: tile outside the padded grid");
+  }
+  const int R = s->R;
+  s->synced = false;
+  MaskEntry* e = nullptr;
+  int rc = get_mask(c, ovlmask, &e);
+  if (rc) return rc;
+  const int64_t l0 = c->launches;
+  cudaEvent_t ev[3];
+  rc = sim_events(s, ev, 3);
+  if (rc) return rc;
+
+  // ---- slab geometry (host side of iqsim.jl:251-275) ----
+  SlabSet S{};
+  S.n = nslab;
+  size_t smem = 0;
+  for (int k = 0; k < nslab; ++k) {
+    const iq_sim_slab& in = slabs[k];
+    SlabDev& o = S.s[k];
+    if (in.dim < 0 || in.dim >= c->ndim) return fail(IQ_ERR_INVALID, "iq_sim_step: slab %d: bad dim", k);
+    o.dim = in.dim;
+    o.prev = in.prev ? 1 : 0;
+    for (int i = 0; i < 3; ++i) {
+      o.lo[i] = i < c->ndim ? in.lo[i] : 0;
+      o.sz[i] = i < c->ndim ? in.sz[i] : 1;
+      if (o.lo[i] < 0 || o.sz[i] < 1 || o.lo[i] + o.sz[i] > t[i]) return fail(IQ_ERR_INVALID, "iq_sim_step: slab %d outside the tile", k);
+    }
+    const int da = o.dim == 0 ? 1 : 0, db = o.dim == 2 ? 1 : 2;
+    const int tst[3] = {1, t[0], t[0] * t[1]};
+    o.n0 = o.sz[da]; o.n1 = o.sz[db]; o.L = o.sz[o.dim];
+    o.st_a = tst[da]; o.st_b = tst[db]; o.st_k = tst[o.dim];
+    if ((size_t)o.n0 * o.n1 * o.L > s->maxslab || !slab_fits(o.n0, o.n1, o.L))
+      return fail(IQ_ERR_INVALID, "iq_sim_step: slab %d is larger than the overlap declared at iq_sim_begin", k);
+    if (o.L > 2) smem = std::max(smem, iq::graphcut_smem(o.n0, o.n1, o.L));
+  }
+  if (nslab > s->maxslabs) return fail(IQ_ERR_INVALID, "iq_sim_step: too many slabs");
+
+  const unsigned gR = (unsigned)((R + 127) / 128);
+  if (e->nnz == 0) {
+    // nothing pasted around the tile: every enabled patch with equal probability (iqsim.jl:237 on an all-zero map);
+    // the walk is evaluated on the host from the cached cumulative weights
+    rc = build_uniform(c);
+    if (rc) return rc;
+    const int64_t n = (int64_t)c->enabled_idx.size();
+    if (n == 0) return fail(IQ_ERR_INVALID, "all patches of the training image are disabled");
+    long long* hp = s->h_pickstage + (size_t)step * R;
+    for (int r = 0; r < R; ++r) {
+      const double tt = s->h_u[(size_t)r * s->npath + step] * c->uniform_sum;
+      const auto it = std::lower_bound(c->uniform_cum.begin(), c->uniform_cum.end() - 1, tt);
+      hp[r] = c->enabled_idx[(size_t)(it - c->uniform_cum.begin())];
+    }
+    CK(cudaEventRecord(ev[0], c->stream));
+    CK(cudaMemcpyAsync(s->d_picked, hp, (size_t)R * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    k_sim_store_picks<<<gR, 128, 0, c->stream>>>(s->d_picked, s->d_picks, s->npath, step, R);
+    CK(cudaGetLastError());
+    c->launches++;
+  } else {
+    CK(iq::launch_fill_u32(c->d_minmax + 0, 0x7f800000u, c->max_batch, c->stream));
+    CK(iq::launch_fill_u32(c->d_minmax + (size_t)c->max_batch, 0u, c->max_batch, c->stream));
+    k_sim_templates<<<dim3((unsigned)c->tz, (unsigned)R), 256, 0, c->stream>>>(
+        s->d_grid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], e->d_mask, c->tx, c->ty, c->tz, s->d_tmpl,
+        s->d_plane, s->d_b2, s->d_ticket);
+    CK(cudaGetLastError());
+    c->launches += 3;
+    bool done = false;
+    if (want_fft(c, e, R)) {
+      rc = ensure_fft(c, -1);
+      if (rc == IQ_OK) {
+        // templates are copies of training-image voxels (or zeros): integer-valued whenever the image is
+        rc = launch_fft(c, e, -1, s->d_tmpl, s->d_b2, R, c->image_is_int[-1], c->d_Dovl, 0);
+        if (rc) return rc;
+        done = true;
+      } else if (!(rc == IQ_ERR_STATE && c->fft_failed)) {
+        return rc;
+      }
+    }
+    if (!done) {
+      const int rb = pick_rb(c, R);
+      const int ngrp = (R + rb - 1) / rb;
+      const long long total = (long long)ngrp * e->tmpl_floats * rb;
+      if ((size_t)total > s->pack_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(s->d_pack);
+        s->d_pack = nullptr;
+        s->pack_cap = 0;
+        CK(cudaMalloc((void**)&s->d_pack, (size_t)total * 2 * sizeof(float)));
+        s->pack_cap = (size_t)total * 2;
+      }
+      k_sim_pack<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(s->d_tmpl, c->tilevol, c->tx, c->ty, e->d_boxes,
+                                                                          (int)e->boxes.size(), e->tmpl_floats, rb, R, total,
+                                                                          s->d_pack);
+      CK(cudaGetLastError());
+      c->launches++;
+      rc = launch_direct(c, e, -1, s->d_pack, s->d_b2, R, rb, false, c->d_Dovl, 0);
+      if (rc) return rc;
+    }
+    CK(cudaEventRecord(ev[0], c->stream));
+    CK(iq::launch_pick_count(c->d_pick, R, c->npos, c->stream));
+    CK(iq::launch_pick_write(c->d_pick, R, c->npos, c->stream));
+    CK(iq::launch_tau(c->d_pick, R, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
+    k_sim_sample<<<gR, 128, 0, c->stream>>>(c->d_pick, c->d_prob, s->d_u, s->npath, step, R, s->d_picked, s->d_picks,
+                                            s->d_status);
+    CK(cudaGetLastError());
+    c->launches += 5;
+  }
+  CK(cudaEventRecord(ev[1], c->stream));
+
+  // ---- boundary cuts ----
+  if (nslab > 0) {
+    const int ntask = R * nslab;
+    k_sim_slabs<<<ntask, 256, 0, c->stream>>>(s->d_grid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], s->d_ti64,
+                                              c->nx, c->ny, c->nxo, c->nyo, s->d_picked, c->tx, c->ty, S, s->d_cutA, s->d_cutB,
+                                              (long long)s->maxslab);
+    CK(cudaGetLastError());
+    // task records depend on the slab set only: cached with the mask
+    if (!e->d_cut_tasks || e->cut_ntask != ntask) {
+      std::vector<iq::CutTask> recs((size_t)ntask);
+      for (int k = 0; k < ntask; ++k) {
+        const SlabDev& o = S.s[k % nslab];
+        recs[k].A = s->d_cutA + (size_t)k * s->maxslab;
+        recs[k].B = s->d_cutB + (size_t)k * s->maxslab;
+        recs[k].keep = s->d_keep + (size_t)k * s->maxslab;
+        recs[k].n0 = o.n0; recs[k].n1 = o.n1; recs[k].L = o.L;
+        recs[k].iters = s->d_cut_iters + k;
+      }
+      CK(cudaStreamSynchronize(c->stream));
+      cudaFree(e->d_cut_tasks);
+      e->d_cut_tasks = nullptr;
+      CK(cudaMalloc((void**)&e->d_cut_tasks, recs.size() * sizeof(iq::CutTask)));
+      CK(cudaMemcpy(e->d_cut_tasks, recs.data(), recs.size() * sizeof(iq::CutTask), cudaMemcpyHostToDevice));
+      e->cut_ntask = ntask;
+      e->cut_smem = smem;
+    }
+    CK(iq::launch_graphcut(e->d_cut_tasks, ntask, std::max<size_t>(e->cut_smem, 64), c->stream));
+    c->launches += 2;
+  }
+  CK(cudaEventRecord(ev[2], c->stream));
+  k_sim_paste<<<dim3((unsigned)((c->tilevol + 255) / 256), (unsigned)R), 256, 0, c->stream>>>(
+      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], s->d_ti64, c->nx, c->ny, c->nxo, c->nyo,
+      s->d_picked, c->tx, c->ty, c->tz, S, s->d_keep, (long long)s->maxslab, s->d_cut_iters, s->d_status);
+  CK(cudaGetLastError());
+  c->launches++;
+  c->last_launches = c->launches - l0;
+  return IQ_OK;
+}
+
+int32_t iq_sim_sync(iq_ctx* c, int64_t* picks, int32_t* status) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_sync: no simulation open on this context");
+  SimState* s = c->sim;
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(s->ev_end, c->stream));
+  int st = 0;
+  CK(cudaMemcpyAsync(&st, s->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (picks && s->npath > 0)
+    CK(cudaMemcpyAsync(picks, s->d_picks, (size_t)s->R * s->npath * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (status) *status = st;
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, s->ev_begin, s->ev_end));
+  s->total_ms = ms;
+  int rc = collect_dist_times(c);
+  if (rc) return rc;
+  s->dist_ms = c->last_dist_ms;
+  s->select_ms = s->cut_ms = 0.0;
+  for (size_t i = 0; i + 3 <= s->ev_used; i += 3) {
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, s->ev[i], s->ev[i + 1]));
+    CK(cudaEventElapsedTime(&b, s->ev[i + 1], s->ev[i + 2]));
+    s->select_ms += a;
+    s->cut_ms += b;
+  }
+  s->synced = true;
+  return IQ_OK;
+}
+
+int32_t iq_sim_fetch(iq_ctx* c, int32_t r, int32_t dtype, const int64_t* crop, void* out) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_fetch: no simulation open on this context");
+  SimState* s = c->sim;
+  if (r < 0 || r >= s->R || !crop || !out || (dtype != 0 && dtype != 1)) return fail(IQ_ERR_INVALID, "iq_sim_fetch: bad argument");
+  CK(cudaSetDevice(c->device));
+  int cr[3] = {1, 1, 1};
+  for (int i = 0; i < c->ndim; ++i) {
+    cr[i] = (int)crop[i];
+    if (cr[i] < 1 || cr[i] > s->pad[i]) return fail(IQ_ERR_INVALID, "iq_sim_fetch: crop outside the padded grid");
+  }
+  const size_t n = (size_t)cr[0] * cr[1] * cr[2], bytes = n * (dtype == 0 ? sizeof(double) : sizeof(float));
+  if (bytes > s->export_cap) {
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(s->d_export);
+    s->d_export = nullptr;
+    s->export_cap = 0;
+    CK(cudaMalloc(&s->d_export, bytes));
+    s->export_cap = bytes;
+  }
+  const double* g = s->d_grid + (size_t)r * s->padvol;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  if (dtype == 0) k_sim_export<double><<<nb, 256, 0, c->stream>>>(g, s->pad[0], s->pad[1], cr[0], cr[1], cr[2], (double*)s->d_export);
+  else k_sim_export<float><<<nb, 256, 0, c->stream>>>(g, s->pad[0], s->pad[1], cr[0], cr[1], cr[2], (float*)s->d_export);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, s->d_export, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return IQ_OK;
+}
+
+int32_t iq_sim_fetch_cut(iq_ctx* c, int32_t r, uint8_t* out) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_fetch_cut: no simulation open on this context");
+  SimState* s = c->sim;
+  if (r < 0 || r >= s->R || !out) return fail(IQ_ERR_INVALID, "iq_sim_fetch_cut: bad argument");
+  if (!s->d_cutgrid) return fail(IQ_ERR_STATE, "iq_sim_fetch_cut: simulation was not opened with debug");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(out, s->d_cutgrid + (size_t)r * s->padvol, (size_t)s->padvol, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return IQ_OK;
+}
+
+int32_t iq_sim_times(const iq_ctx* c, double* total_ms, double* dist_ms, double* select_ms, double* cut_ms) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_times: no simulation open on this context");
+  if (!c->sim->synced) return fail(IQ_ERR_STATE, "iq_sim_times: call iq_sim_sync first");
+  if (total_ms) *total_ms = c->sim->total_ms;
+  if (dist_ms) *dist_ms = c->sim->dist_ms;
+  if (select_ms) *select_ms = c->sim->select_ms;
+  if (cut_ms) *cut_ms = c->sim->cut_ms;
+  return IQ_OK;
+}
+
+int32_t iq_sim_end(iq_ctx* c) {
+  if (!c) return fail(IQ_ERR_INVALID, "NULL context");
+  if (!c->sim) return IQ_OK;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  sim_destroy(c);
+  return IQ_OK;
+}
+
+}  // extern "C"

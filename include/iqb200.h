@@ -152,6 +152,49 @@ typedef struct iq_cut_task {
 } iq_cut_task;
 int32_t iq_cut_batch(iq_ctx* ctx, const iq_cut_task* tasks, int32_t ntask, int32_t* iters);
 
+/* Device-resident simulation (simulation grids, tile paste and boundary cuts on the device).
+ * The grids of `nreal` realizations live in device memory for the whole simulation; every path step is enqueued
+ * on the context's stream WITHOUT any host synchronisation:
+ *     template gather from the grids (iqsim.jl:185) -> overlap distance (utils.jl:5-13) -> threshold selection
+ *     (iqsim.jl:237) -> tau model (taumodel.jl:5-45) -> StatsBase.sample walk with the pre-drawn uniform
+ *     (iqsim.jl:243) -> boundary cuts (graphcut.jl:5-84, device kernel of iq_cut_batch) -> paste (iqsim.jl:278).
+ * Scope: the threshold path (no soft / hard data on the context) with overlap slabs that fit the shared-memory cut
+ * kernel; iq_sim_begin returns IQ_ERR_STATE otherwise and the caller uses iq_search_pick + its own paste instead.
+ * A data-dependent condition the device path does not cover (a candidate set larger than 16 384 entries on a
+ * non-empty mask) is reported by iq_sim_sync through `status` != 0; the grids are then invalid and the caller
+ * reruns the simulation through iq_search_pick.  While a simulation is open the context must not be used for
+ * iq_search* / iq_distance / iq_slice_* calls. */
+typedef struct iq_sim_desc {
+  int64_t pad_size[3];   /* padded simulation grid (src/iqsim.jl:106), unused dims = 1 */
+  int64_t ovl_size[3];   /* overlap size per dimension (src/iqsim.jl:92): fixes the largest cut slab */
+  int32_t nreal;         /* realizations held by this context (<= max_batch of the context) */
+  const double* ti64;    /* training image in FP64 (the values that are pasted and cut), ti_size doubles */
+  const double* u;       /* [nreal][npath] uniforms in the reference's draw order (src/iqsim.jl:243) */
+  int64_t npath;         /* number of path steps */
+  double tol;
+  int32_t debug;         /* nonzero: also keep the boundary-cut grids (src/iqsim.jl:281) */
+} iq_sim_desc;
+typedef struct iq_sim_slab {   /* one overlap slab of the current tile, in tile coordinates */
+  int32_t dim;           /* dimension of the overlap */
+  int32_t prev;          /* 1 = overlap with the previous tile along dim, 0 = with the next one */
+  int32_t lo[3], sz[3];
+} iq_sim_slab;
+int32_t iq_sim_begin(iq_ctx* ctx, const iq_sim_desc* desc);
+/* Enqueues one path step for all realizations: tile origin `start` (0-based voxel coordinates in the padded grid),
+ * the overlap mask of the step and the slabs whose union it is (nslab may be 0: nothing pasted around the tile). */
+int32_t iq_sim_step(iq_ctx* ctx, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
+                    int32_t nslab);
+/* Waits for the enqueued steps.  picks (may be NULL): [nreal][npath] chosen patterns; status: 0 = ok. */
+int32_t iq_sim_sync(iq_ctx* ctx, int64_t* picks, int32_t* status);
+/* Copies realization r, cropped to crop[3] (unused dims = 1), to the host as FP64 (dtype 0) or FP32 (dtype 1). */
+int32_t iq_sim_fetch(iq_ctx* ctx, int32_t r, int32_t dtype, const int64_t* crop, void* out);
+/* Copies the boundary-cut grid of realization r (pad_size bytes; debug simulations only). */
+int32_t iq_sim_fetch_cut(iq_ctx* ctx, int32_t r, uint8_t* out);
+/* Device time (ms, CUDA events on the context's stream) of the simulation since iq_sim_begin: whole stream, the
+ * distance computations, the selection + tau + sampling kernels, the boundary cuts.  Valid after iq_sim_sync. */
+int32_t iq_sim_times(const iq_ctx* ctx, double* total_ms, double* dist_ms, double* select_ms, double* cut_ms);
+int32_t iq_sim_end(iq_ctx* ctx);
+
 /* Timing hooks for benchmarks: device time (ms, CUDA events on the context's stream) and number
  * of kernels launched by the most recent iq_search* call. */
 int32_t iq_last_search_stats(const iq_ctx* ctx, double* device_ms, int64_t* kernel_launches);

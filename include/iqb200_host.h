@@ -9,9 +9,11 @@
  * (imagequilting.jl_b200/api.py) calls iqh_run; a Julia host would keep its own loop and ccall
  * iq_search instead.
  *
- * All realizations advance in lockstep along the (shared) simulation path: one iq_search_pick call per
- * path step carries the templates of every realization, then the cuts/pastes of that step run on host
- * threads, one realization each.
+ * All realizations advance in lockstep along the (shared) simulation path.  Two pipelines:
+ *   host-staged     one iq_search_pick call per path step carries the templates of every realization of a group,
+ *                   then the cuts/pastes of that step run on host threads (or iq_cut_batch);
+ *   device-resident the grids stay on the device and every step is enqueued through iq_sim_step without any host
+ *                   synchronisation (threshold path: no soft / hard data).
  */
 #ifndef IQB200_HOST_H
 #define IQB200_HOST_H
@@ -50,6 +52,13 @@ typedef struct iqh_desc {
   int32_t ngroups;             /* lockstep groups pipelined against the host cuts; 0 = auto */
   int32_t cut_mode;            /* boundary cuts: 0 = auto (device when fewer than 6 host threads), 1 = host, 2 = device */
   int32_t fft_mode;            /* -1 never, 0 auto crossover, 1 always: distance path selection */
+  int32_t pipeline;            /* 0 = auto (device-resident whenever the simulation qualifies), 1 = host-staged (grids,
+                                  cuts and paste on the host, one iq_search_pick per step), 2 = device-resident
+                                  (iq_sim_*: grids, cuts and paste on the device; error if it does not qualify) */
+  void* const* out_real;       /* optional: nreal pointers to sim_size-shaped column-major arrays that receive the
+                                  realizations cropped to sim_size (src/iqsim.jl:303); out_grids may then be NULL */
+  int32_t out_real_f32;        /* element type of out_real: 0 = FP64, 1 = FP32 */
+  int64_t sim_size[3];         /* crop of out_real (unused dims = 1) */
 } iqh_desc;
 
 typedef struct iqh_stats {
@@ -67,10 +76,16 @@ typedef struct iqh_stats {
   int64_t direct_searches;
   double fft_bytes;            /* algorithmic bytes moved by the FFT passes */
   double fft_ms;               /* device time inside the FFT passes */
+  int32_t resident;            /* 1 = the device-resident pipeline produced the result */
+  int32_t resident_status;     /* status word of a resident attempt that had to be redone host-staged (0 = none) */
+  double device_ms;            /* resident: device time of the whole simulation (max over the lockstep groups) */
+  double select_ms;            /* resident: device time of selection + tau model + sampling (sum over groups) */
+  double cut_device_ms;        /* resident: device time of the boundary cuts (sum over groups) */
+  double fetch_ms;             /* resident: wall time of exporting the realizations to the host */
 } iqh_stats;
 
 /* Runs the whole simulation.  `out_grids` receives nreal padded grids (pad_size doubles each,
- * column-major); `out_cuts` (may be NULL unless debug) nreal pad_size byte grids with the boundary-cut
+ * column-major; may be NULL when desc->out_real is given); `out_cuts` (may be NULL unless debug) nreal pad_size byte grids with the boundary-cut
  * masks (src/iqsim.jl:281); `out_picks` (may be NULL) the chosen pattern per realization and step,
  * [nreal][npath], for parity tests.  Returns IQ_OK or an IQ_ERR_* code (message: iq_last_error()). */
 int32_t iqh_run(const iqh_desc* desc, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats);

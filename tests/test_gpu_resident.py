@@ -1,0 +1,90 @@
+"""GPU tests of the device-resident pipeline (iq_sim_*: grids, cuts and paste on the device, no host
+synchronisation per step).  Bar: bit-identical picks, realizations and boundary-cut grids to the host-staged
+pipeline of the same library (which the other GPU tests pin against the oracle), plus direct oracle checks."""
+import numpy as np
+import pytest
+
+import iqb200
+from iqb200 import _lib, synth
+from oracle import iq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def both(ti, tile, seed, **kw):
+    a, ea = iqb200.iqsim(ti, tile, rng=np.random.default_rng(seed), pipeline="staged", cut="host", return_picks=True,
+                         return_stats=True, **kw)
+    b, eb = iqb200.iqsim(ti, tile, rng=np.random.default_rng(seed), pipeline="resident", return_picks=True,
+                         return_stats=True, **kw)
+    assert ea["stats"]["resident"] == 0 and eb["stats"]["resident"] == 1
+    return a, ea, b, eb
+
+
+def same(a, ea, b, eb, debug=False):
+    assert np.array_equal(ea["picks"], eb["picks"])
+    ra, rb = (a[0], b[0]) if debug else (a, b)
+    for x, y in zip(ra, rb):
+        assert x.dtype == y.dtype and x.shape == y.shape
+        assert np.array_equal(x, y, equal_nan=True)
+    if debug:
+        for x, y in zip(a[1], b[1]):
+            assert np.array_equal(x, y, equal_nan=True)
+        assert a[2] == b[2]
+
+
+@pytest.mark.parametrize("fft", [-1, 1])
+def test_resident_equals_staged_2d_continuous(fft):
+    cfg = synth.config(2, scale=0.25)  # 128x128 Gaussian field, 48x48 tiles
+    same(*both(cfg["trainimg"], cfg["tilesize"], 4, nreal=3, fft=fft, debug=True), debug=True)
+
+
+@pytest.mark.parametrize("fft", [-1, 1])
+def test_resident_equals_staged_3d_continuous(fft):
+    ti = synth.gaussian_field((48, 40, 20), (6, 6, 3), 9)
+    same(*both(ti, (16, 12, 8), 5, nreal=3, fft=fft, overlap=(0.25, 0.25, 0.25), simsize=(50, 44, 22)))
+
+
+@pytest.mark.parametrize("path", ["random", "dilation"])
+def test_resident_equals_staged_other_paths(path):
+    ti = synth.gaussian_field((64, 56), (5, 5), 3).astype(np.float64)
+    same(*both(ti, (16, 14), 6, nreal=4, path=path, overlap=(0.25, 0.3), simsize=(70, 60), debug=True), debug=True)
+
+
+def test_resident_thin_overlap_and_disabled_patches():
+    """ovlsize = 2 along one axis (no inner layer in the cut) and NaN voxels in the training image."""
+    ti = synth.gaussian_field((40, 36, 12), (5, 5, 2), 1).astype(np.float64)
+    ti[3:6, 30:33, 2] = np.nan
+    same(*both(ti, (12, 12, 6), 8, nreal=2, overlap=(0.25, 0.25, 0.3)))
+
+
+def test_resident_config1_matches_oracle():
+    cfg = synth.config(1)
+    got, ex = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(42), pipeline="resident",
+                           return_picks=True, nreal=2, **{k: v for k, v in cfg["kwargs"].items() if k != "nreal"})
+    trace = []
+    want = O.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(42), method="direct", trace=trace, nreal=2,
+                   cut_fn=iqb200.graphcut, **{k: v for k, v in cfg["kwargs"].items() if k != "nreal"})
+    picks_ref = np.array([t["rind"] for t in trace]).reshape(2, -1)
+    assert np.array_equal(ex["picks"], picks_ref)
+    for g, w in zip(got, want):
+        assert g.dtype == w.dtype and np.array_equal(g, w)
+
+
+def test_resident_refuses_soft_data_and_auto_falls_back():
+    cfg = synth.config(3, scale=0.4)
+    ti = cfg["trainimg"]
+    aux = np.asfortranarray(synth.box_mean(ti, (3, 3, 3)))
+    with pytest.raises(_lib.IqError):
+        iqb200.iqsim(ti, cfg["tilesize"], nreal=1, soft=[(aux, aux)], pipeline="resident", rng=np.random.default_rng(0))
+    out, ex = iqb200.iqsim(ti, cfg["tilesize"], nreal=1, soft=[(aux, aux)], pipeline="auto", rng=np.random.default_rng(0),
+                           return_stats=True)
+    assert ex["stats"]["resident"] == 0 and out[0].shape == ti.shape
+
+
+def test_resident_many_realizations_groups():
+    """Group split (two streams) does not change any realization."""
+    cfg = synth.config(2, scale=0.25)
+    a = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=6, rng=np.random.default_rng(2), pipeline="resident", ngroups=1)
+    b = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=6, rng=np.random.default_rng(2), pipeline="resident", ngroups=3)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
