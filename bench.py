@@ -8,9 +8,10 @@
 A "step" is one complete iqsim call (all tiles of `nreal-per-gpu` realizations on every rank) on the
 synthetic training image of the chosen config (default: config 5, the 250x250x100 volume the scaling
 target is quoted on).  Realizations are sharded over ranks with no data-path collective (weak scaling:
-fixed realizations per GPU; N = 8 with 8 per GPU is exactly the nreal = 64 config).
+fixed realizations per GPU; the default 64 per GPU makes N = 1 exactly BASELINE config 5, nreal = 64).
 
-  value  = voxels/s with the training image already resident in HBM (context set-up excluded)
+  value  = voxels/s with the training image already resident in HBM (context set-up excluded; on the
+           device-resident pipeline the realizations are left in HBM, their export is part of e2e)
   e2e    = voxels/s of the public call iqb200.iqsim(host arrays) -> host arrays, everything included
   roofline: FP32-FMA roofline of the dominant kernel k_dist_boxes (algorithmic FMAs = nnz(mask) x npos per
             tile search, SURVEY.md 8(d)) against the FFMA rate measured on this GPU by iq_bench_fma_peak;
@@ -176,7 +177,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=5)
-    ap.add_argument("--nreal-per-gpu", type=int, default=8)
+    ap.add_argument("--nreal-per-gpu", type=int, default=64)
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "staged", "resident"])
+    ap.add_argument("--ngroups", type=int, default=0)
     ap.add_argument("--cpu-tiles", type=int, default=0, help="tiles in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rb", type=int, default=0)
@@ -244,7 +247,7 @@ def main():
     def step(i):
         t0 = time.perf_counter()
         out, ex = iqb200.iqsim(ti, tilesize, rng=np.random.default_rng(seed0 + i), device=local, nthreads=nthreads, fft=args.fft, cut=args.cut,
-                               return_stats=True, return_picks=True, **kw)
+                               pipeline=args.pipeline, ngroups=args.ngroups, return_stats=True, return_picks=True, **kw)
         chk = float(sum(float(r[0, 0, 0] if r.ndim == 3 else r[0, 0]) for r in out))  # touch the result on the host
         return time.perf_counter() - t0, ex, chk
 
@@ -265,7 +268,9 @@ def main():
 
     geo = stats[0]["stats"]["geo"]
     vox_per_step = float(np.prod(geo["simsize"], dtype=np.float64)) * args.nreal_per_gpu
-    resident_s = sum((s["stats"]["total_ms"] - s["stats"]["setup_ms"]) for s in stats) / 1e3
+    # `value`: inputs already in HBM (context set-up / uploads excluded) and, on the device-resident pipeline, results
+    # left in HBM (the export to host arrays is part of e2e only)
+    resident_s = sum((s["stats"]["total_ms"] - s["stats"]["setup_ms"] - s["stats"]["fetch_ms"]) for s in stats) / 1e3
     t = torch.tensor([t_total, resident_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -285,8 +290,16 @@ def main():
     # algorithmic bytes per launch: image once + R distance maps written + templates (mask voxels x 2 x 4 B)
     bytes_total = args.steps * nsearch * (4.0 * nti + args.nreal_per_gpu * 4.0 * npos) + 8.0 * fma_total / max(npos, 1)
     achieved_gbs = bytes_total / (dist_ms * 1e-3) / 1e9 if dist_ms > 0 else 0.0
-    h2d = sum(s["stats"]["searches"] for s in stats) / args.steps * float(np.prod(tilesize)) * 4.0 + nti * 4.0
-    d2h = sum(s["stats"]["candidates"] for s in stats) / args.steps * 8.0
+    is_resident = all(s["stats"]["resident"] for s in stats)
+    out_bytes = float(np.prod(geo["simsize"], dtype=np.float64)) * args.nreal_per_gpu * ti.dtype.itemsize
+    npath = len(stats[0]["path"])
+    if is_resident:
+        # uploads: FP32 + FP64 training image and the uniforms; downloads: the cropped realizations and the picks
+        h2d = nti * 12.0 + args.nreal_per_gpu * npath * 8.0
+        d2h = out_bytes + args.nreal_per_gpu * npath * 8.0
+    else:
+        h2d = sum(s["stats"]["searches"] for s in stats) / args.steps * float(np.prod(tilesize)) * 4.0 + nti * 4.0
+        d2h = sum(s["stats"]["candidates"] for s in stats) / args.steps * 8.0
 
     fft_ms = sum(s["stats"]["fft_ms"] for s in stats)
     fft_bytes = sum(s["stats"]["fft_bytes"] for s in stats)
@@ -328,8 +341,10 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(sum(s["stats"]["kernel_launches"] for s in stats)),
         "roofline": roof,
+        "pipeline": "device-resident (iq_sim_*)" if is_resident else "host-staged (iq_search_pick per step)",
         "breakdown_ms_per_step": {k: sum(s["stats"][k] for s in stats) / args.steps
-                                  for k in ("search_ms", "search_device_ms", "cut_ms", "setup_ms", "total_ms")},
+                                  for k in ("search_ms", "search_device_ms", "cut_ms", "setup_ms", "total_ms", "device_ms",
+                                            "select_ms", "cut_device_ms", "fetch_ms")},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -96,6 +96,7 @@ SYMBOLS = {
     "iq_sim_step": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32]),
     "iq_sim_sync": (C.c_int32, [C.c_void_p, c_i64_p, c_i32_p]),
     "iq_sim_fetch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_i64_p, C.c_void_p]),
+    "iq_sim_fetch_all": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, C.POINTER(C.c_void_p), C.c_int32]),
     "iq_sim_fetch_cut": (C.c_int32, [C.c_void_p, C.c_int32, c_u8_p]),
     "iq_sim_times": (C.c_int32, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "iq_sim_end": (C.c_int32, [C.c_void_p]),

@@ -125,7 +125,7 @@ int stage_reserve(iq_ctx* c, size_t bytes) {
   c->d_stage = nullptr;
   c->stage_cap = 0;
   CK(cudaMallocHost((void**)&c->h_stage, cap));
-  CK(cudaMalloc((void**)&c->d_stage, cap));
+  CK(iq::dmalloc((void**)&c->d_stage, cap));
   c->stage_cap = cap;
   return IQ_OK;
 }
@@ -245,11 +245,11 @@ int get_mask(iq_ctx* c, const uint8_t* mask, MaskEntry** out) {
   }
   e->tmpl_floats = off;
   if (!e->boxes.empty()) {
-    CK(cudaMalloc((void**)&e->d_boxes, e->boxes.size() * sizeof(BoxDesc)));
+    CK(iq::dmalloc((void**)&e->d_boxes, e->boxes.size() * sizeof(BoxDesc)));
     CK(cudaMemcpyAsync(e->d_boxes, e->boxes.data(), e->boxes.size() * sizeof(BoxDesc), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
-  CK(cudaMalloc((void**)&e->d_mask, (size_t)c->tilevol));
+  CK(iq::dmalloc((void**)&e->d_mask, (size_t)c->tilevol));
   CK(cudaMemcpyAsync(e->d_mask, e->mask.data(), (size_t)c->tilevol, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   choose_shape(c, e->boxes, 1, std::max(1, c->max_batch), &e->WX, &e->WY);
@@ -263,7 +263,7 @@ int get_a2(iq_ctx* c, MaskEntry* e, int image, const float** out) {
   auto it = e->a2.find(image);
   if (it != e->a2.end()) { *out = it->second; return IQ_OK; }
   float* d = nullptr;
-  CK(cudaMalloc((void**)&d, (size_t)c->npos * sizeof(float)));
+  CK(iq::dmalloc((void**)&d, (size_t)c->npos * sizeof(float)));
   const double* sat = image < 0 ? c->d_sat_ti : c->d_sat_aux[image];
   CK(iq::launch_a2map(sat, c->nx, c->ny, c->nz, e->d_boxes, (int)e->boxes.size(), d, c->nxo, c->nyo, c->nzo, c->stream));
   c->launches++;
@@ -392,6 +392,13 @@ int launch_fft(iq_ctx* c, MaskEntry* e, int image, const float* d_tmpl, const do
   ep.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch;
   ep.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch;
   ep.round_to_int = tint ? 1 : 0;
+  if (kind == 0) {
+    const int rows = iqfft::final_chunk_rows(c->fft);
+    c->chunk_len = rows * c->nxo;
+    c->chunk_n = (c->nyo * c->nzo + rows - 1) / rows;
+    c->chunk_valid = c->chunk_n <= c->chunk_stride;
+    if (c->chunk_valid) { ep.chunkmin = c->d_chunkmin; ep.chunk_pitch = c->chunk_stride; }
+  }
   cudaEvent_t ea, eb;
   rc = dist_events(c, &ea, &eb, true);
   if (rc) return rc;
@@ -481,6 +488,17 @@ int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, con
   CK(cudaEventRecord(eb, c->stream));
   c->launches++;
   c->last_direct_searches += R;
+  if (kind == 0) c->chunk_valid = false;
+  return IQ_OK;
+}
+
+int ensure_chunkmin(iq_ctx* c, int R) {
+  if (c->chunk_valid) return IQ_OK;
+  c->chunk_len = 4096;
+  c->chunk_n = (int)((c->npos + 4095) / 4096);
+  CK(iq::launch_chunkmin(c->d_Dovl, R, c->npos, c->chunk_len, c->chunk_n, c->d_chunkmin, c->chunk_stride, c->stream));
+  c->launches++;
+  c->chunk_valid = true;
   return IQ_OK;
 }
 
@@ -667,6 +685,7 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
     J.cand_idx = c->d_cand_idx + (size_t)r * c->npos;
     J.cand_val = c->d_cand_val + (size_t)r * c->max_src * c->npos;
     J.cap = c->npos;
+    J.chunkmin = c->d_chunkmin + (size_t)r * c->chunk_stride;
     any_relax |= n > 1;
   }
 
@@ -694,7 +713,20 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
   // ---- selection ----
   const int maxS = c->max_src;
   bool first_round = true;
-  for (;;) {
+  bool by_chunks = !any_relax;  // threshold rule on the overlap distance: scan only chunks that can hold candidates
+  if (by_chunks) {
+    rc = ensure_chunkmin(c, R);
+    if (rc) return rc;
+    for (int r = 0; r < R; ++r) c->h_pick[r].sel = c->d_sel + (size_t)r * maxS;
+    CK(cudaMemcpyAsync(c->d_pick, c->h_pick, (size_t)R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+    CK(iq::launch_pick_chunks(c->d_pick, R, c->npos, c->chunk_len, c->chunk_n, c->stream));
+    c->launches++;
+    CK(cudaMemcpyAsync(c->h_total, c->d_total, (size_t)R * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < R; ++r)
+      if (c->h_total[r] == iq::kPickOverflow) by_chunks = false;  // too many chunks qualify: generic two-pass path
+  }
+  for (; !by_chunks;) {
     int njobs = 0;
     if (any_relax) {
       for (int r = 0; r < R; ++r) {
@@ -753,8 +785,10 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
     if (!again) break;
   }
 
-  CK(iq::launch_pick_write(c->d_pick, R, c->npos, c->stream));
-  c->launches++;
+  if (!by_chunks) {
+    CK(iq::launch_pick_write(c->d_pick, R, c->npos, c->stream));
+    c->launches++;
+  }
   if (c->tau_device) {
     CK(iq::launch_tau(c->d_pick, R, maxS, c->d_rank, c->d_colsum, c->d_prob, c->stream));
     c->launches += 2;
@@ -896,6 +930,7 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   if (c->h_pick) cudaFreeHost(c->h_pick);
   cudaFree(c->d_blockcount);
   cudaFree(c->d_total);
+  cudaFree(c->d_chunkmin);
   if (c->h_total) cudaFreeHost(c->h_total);
   cudaFree(c->d_cand_idx);
   cudaFree(c->d_cand_val);
@@ -945,10 +980,10 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   const size_t nsat = (size_t)(c->nx + 1) * (c->ny + 1) * (c->nz + 1);
   const size_t slack = 64;  // floats of zeroed slack after each image
   auto upload = [&](const float* src, float** dimg, double** dsat) -> int {
-    CK(cudaMalloc((void**)dimg, (nimg + slack) * sizeof(float)));
+    CK(iq::dmalloc((void**)dimg, (nimg + slack) * sizeof(float)));
     CK(cudaMemsetAsync(*dimg, 0, (nimg + slack) * sizeof(float), c->stream));
     CK(cudaMemcpyAsync(*dimg, src, nimg * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMalloc((void**)dsat, nsat * sizeof(double)));
+    CK(iq::dmalloc((void**)dsat, nsat * sizeof(double)));
     CK(cudaMemsetAsync(*dsat, 0, nsat * sizeof(double), c->stream));
     CK(iq::launch_sat_build(*dimg, *dsat, c->nx, c->ny, c->nz, c->stream));
     c->launches += 3;
@@ -973,7 +1008,7 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
     for (long long p = 0; p < c->npos; ++p) nd += c->h_disabled[p] ? 1 : 0;
     c->nenabled = c->npos - nd;
     if (nd > 0) {
-      CK(cudaMalloc((void**)&c->d_disabled, (size_t)c->npos));
+      CK(iq::dmalloc((void**)&c->d_disabled, (size_t)c->npos));
       CK(cudaMemcpyAsync(c->d_disabled, c->h_disabled.data(), (size_t)c->npos, cudaMemcpyHostToDevice, c->stream));
     } else {
       c->h_disabled.clear();
@@ -981,27 +1016,29 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   }
   const size_t B = (size_t)c->max_batch;
   c->max_src = 2 + c->nsoft;
-  CK(cudaMalloc((void**)&c->d_Dovl, B * c->npos * sizeof(float)));
-  CK(cudaMalloc((void**)&c->d_Dhard, B * c->npos * sizeof(float)));
+  CK(iq::dmalloc((void**)&c->d_Dovl, B * c->npos * sizeof(float)));
+  CK(iq::dmalloc((void**)&c->d_Dhard, B * c->npos * sizeof(float)));
   c->d_Dsoft.assign(c->nsoft, nullptr);
-  for (int s = 0; s < c->nsoft; ++s) CK(cudaMalloc((void**)&c->d_Dsoft[s], B * c->npos * sizeof(float)));
+  for (int s = 0; s < c->nsoft; ++s) CK(iq::dmalloc((void**)&c->d_Dsoft[s], B * c->npos * sizeof(float)));
   const size_t nmm = (size_t)(2 + c->nsoft) * 2 * B;
-  CK(cudaMalloc((void**)&c->d_minmax, nmm * sizeof(unsigned)));
+  CK(iq::dmalloc((void**)&c->d_minmax, nmm * sizeof(unsigned)));
   CK(cudaMallocHost((void**)&c->h_minmax, nmm * sizeof(unsigned)));
-  CK(cudaMalloc((void**)&c->d_sel, B * c->max_src * sizeof(iq::SelJob)));
+  CK(iq::dmalloc((void**)&c->d_sel, B * c->max_src * sizeof(iq::SelJob)));
   CK(cudaMallocHost((void**)&c->h_sel, B * c->max_src * sizeof(iq::SelJob)));
   CK(cudaMemsetAsync(c->d_sel, 0, B * c->max_src * sizeof(iq::SelJob), c->stream));
-  CK(cudaMalloc((void**)&c->d_pick, B * sizeof(iq::PickJob)));
+  CK(iq::dmalloc((void**)&c->d_pick, B * sizeof(iq::PickJob)));
   CK(cudaMallocHost((void**)&c->h_pick, B * sizeof(iq::PickJob)));
-  CK(cudaMalloc((void**)&c->d_blockcount, B * iq::pick_nblk(c->npos) * sizeof(unsigned)));
-  CK(cudaMalloc((void**)&c->d_total, B * sizeof(unsigned)));
+  CK(iq::dmalloc((void**)&c->d_blockcount, B * iq::pick_nblk(c->npos) * sizeof(unsigned)));
+  c->chunk_stride = c->npos / std::min<long long>(4096, std::max(4 * c->nxo, 1)) + 2;
+  CK(iq::dmalloc((void**)&c->d_chunkmin, B * c->chunk_stride * sizeof(unsigned)));
+  CK(iq::dmalloc((void**)&c->d_total, B * sizeof(unsigned)));
   CK(cudaMallocHost((void**)&c->h_total, B * sizeof(unsigned)));
-  CK(cudaMalloc((void**)&c->d_cand_idx, B * c->npos * sizeof(unsigned)));
-  CK(cudaMalloc((void**)&c->d_cand_val, B * c->max_src * c->npos * sizeof(float)));
-  CK(cudaMalloc((void**)&c->d_fetch, (size_t)c->tilevol * sizeof(float)));
-  CK(cudaMalloc((void**)&c->d_rank, B * c->max_src * iq::kTauMax * sizeof(unsigned)));
-  CK(cudaMalloc((void**)&c->d_colsum, B * c->max_src * sizeof(unsigned long long)));
-  CK(cudaMalloc((void**)&c->d_prob, B * iq::kTauMax * sizeof(double)));
+  CK(iq::dmalloc((void**)&c->d_cand_idx, B * c->npos * sizeof(unsigned)));
+  CK(iq::dmalloc((void**)&c->d_cand_val, B * c->max_src * c->npos * sizeof(float)));
+  CK(iq::dmalloc((void**)&c->d_fetch, (size_t)c->tilevol * sizeof(float)));
+  CK(iq::dmalloc((void**)&c->d_rank, B * c->max_src * iq::kTauMax * sizeof(unsigned)));
+  CK(iq::dmalloc((void**)&c->d_colsum, B * c->max_src * sizeof(unsigned long long)));
+  CK(iq::dmalloc((void**)&c->d_prob, B * iq::kTauMax * sizeof(double)));
   CK(cudaMallocHost((void**)&c->h_prob, B * iq::kTauMax * sizeof(double)));
   // radix-select schedule: 4 value bytes, then only the index bytes that can be non-zero
   std::vector<int> shifts = {56, 48, 40, 32};
@@ -1009,7 +1046,7 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   while (nib < 4 && ((unsigned long long)(c->npos - 1) >> (8 * nib)) != 0) ++nib;
   for (int b = nib - 1; b >= 0; --b) shifts.push_back(8 * b);
   c->nshift = (int)shifts.size();
-  CK(cudaMalloc((void**)&c->d_shifts, shifts.size() * sizeof(int)));
+  CK(iq::dmalloc((void**)&c->d_shifts, shifts.size() * sizeof(int)));
   CK(cudaMemcpyAsync(c->d_shifts, shifts.data(), shifts.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   // the all-ones mask of the soft-data distance (fastdistance default weights, src/utils.jl:5)
@@ -1303,7 +1340,7 @@ int32_t iq_cut_batch(iq_ctx* c, const iq_cut_task* tasks, int32_t ntask, int32_t
       c->h_cut = nullptr; c->d_cut = nullptr; c->cut_cap = 0;
       const size_t cap = off * 2;
       CK(cudaMallocHost((void**)&c->h_cut, cap));
-      CK(cudaMalloc((void**)&c->d_cut, cap));
+      CK(iq::dmalloc((void**)&c->d_cut, cap));
       c->cut_cap = cap;
     }
     iq::CutTask* recs = (iq::CutTask*)c->h_cut;
@@ -1405,7 +1442,7 @@ static int32_t bench_fma_impl(int32_t device, int packed, double* tfma) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   float* d = nullptr;
-  CK(cudaMalloc((void**)&d, 64));
+  CK(iq::dmalloc((void**)&d, 64));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));

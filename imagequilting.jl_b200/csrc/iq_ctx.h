@@ -94,6 +94,10 @@ struct iq_ctx {
   iq::PickJob* d_pick = nullptr;
   iq::PickJob* h_pick = nullptr;
   unsigned* d_blockcount = nullptr;
+  unsigned* d_chunkmin = nullptr;  // [max_batch][chunk_stride] chunk minima of the overlap distance maps
+  long long chunk_stride = 0;
+  int chunk_len = 0, chunk_n = 0;  // chunking of the most recent overlap-distance computation
+  bool chunk_valid = false;        // d_chunkmin already filled (by the FFT epilogue)
   unsigned* d_total = nullptr;
   unsigned* h_total = nullptr;
   unsigned* d_cand_idx = nullptr;
@@ -154,6 +158,8 @@ int launch_fft(iq_ctx* c, MaskEntry* e, int image, const float* d_tmpl, const do
 int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, const double* d_b2, int R, int rb, bool packed,
                   float* d_out, int kind);
 int collect_dist_times(iq_ctx* c);
+// Makes sure d_chunkmin describes the R overlap-distance maps in d_Dovl (FFT epilogue, or one extra pass).
+int ensure_chunkmin(iq_ctx* c, int R);
 // B2 = sum of the squared (masked) template values in the library's fixed summation order, shared by the
 // host-staged path and the device kernel k_sim_templates so that both produce the same bits.
 double b2_ordered(const float* v, int tx, int ty, int tz);

@@ -19,10 +19,12 @@
 // 16 (then 8/4/2) with the butterflies in registers, lines in shared memory with a 1-in-16 padding that
 // makes every pass and every global<->shared copy bank-conflict free.
 #include "iq_fft.h"
+#include "iq_internal.h"
 
 #include <math_constants.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -328,6 +330,59 @@ __global__ void __launch_bounds__(kThreads) k_fft_strided(const StridedArgs A) {
   }
 }
 
+// ---- pass B': direct correlation along z in the (kx, ky) frequency domain ----------------------------------
+// out[pr][z][ky][kx] = sum_{q < tz} Sxy[z + q][ky][kx] * T[pr][q][ky][kx],  z < nzo,
+// where Sxy is the 2-D (x, y) spectrum of every image plane and T the 2-D spectrum of the (flipped) template
+// planes.  A template is only tz planes deep, so the z axis needs no transform at all: tz complex MACs per output
+// beat the padded forward FFT + product + inverse FFT of the fused kernel below for tz <= 24, the image spectrum
+// shrinks from Nz to nz planes, and everything is plain FP32 FMAs on coalesced streams (one thread per (kx, ky)
+// column, a sliding window of W spectrum planes in registers).
+struct ZDirectArgs {
+  const float2* sxy;     // [nz][Ny][Nx]
+  const float2* tmpl;    // [npair][tz][Ny][Nx]
+  float2* out;           // [npair][nzo][Ny][Nx]
+  long long plane;       // Ny*Nx
+  long long tmpl_batch, out_batch;
+  int nz, tz, nzo;
+};
+template <int W>
+__global__ void __launch_bounds__(256) k_fft_zdirect(const ZDirectArgs A) {
+  const long long col = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (col >= A.plane) return;
+  const float2* __restrict__ S = A.sxy + col;
+  const float2* __restrict__ T = A.tmpl + (long long)blockIdx.y * A.tmpl_batch + col;
+  float2* __restrict__ O = A.out + (long long)blockIdx.y * A.out_batch + col;
+  const float2 zero = make_float2(0.f, 0.f);
+  float2 t[W], s[W];
+#pragma unroll
+  for (int q = 0; q < W; ++q) t[q] = q < A.tz ? T[(long long)q * A.plane] : zero;
+#pragma unroll
+  for (int j = 0; j < W - 1; ++j) s[j] = j < A.nz ? S[(long long)j * A.plane] : zero;
+  s[W - 1] = zero;
+  for (int z0 = 0; z0 < A.nzo; z0 += W) {
+    float2 nxt[W];
+#pragma unroll
+    for (int m = 0; m < W; ++m) {
+      const int zz = z0 + m + W - 1;
+      nxt[m] = zz < A.nz ? S[(long long)zz * A.plane] : zero;
+    }
+#pragma unroll
+    for (int m = 0; m < W; ++m) {
+      s[(m + W - 1) % W] = nxt[m];
+      float ax = 0.f, ay = 0.f;
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        const float2 sv = s[(m + q) % W], tv = t[q];
+        ax = fmaf(sv.x, tv.x, ax);
+        ax = fmaf(-sv.y, tv.y, ax);
+        ay = fmaf(sv.x, tv.y, ay);
+        ay = fmaf(sv.y, tv.x, ay);
+      }
+      if (z0 + m < A.nzo) O[(long long)(z0 + m) * A.plane] = make_float2(ax, ay);
+    }
+  }
+}
+
 // ---- pass C: last inverse pass along x + distance epilogue --------------------------------------------
 struct FinalArgs {
   const float2* in;     // [npair][nlines][N]
@@ -393,6 +448,9 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_final(const FinalArgs A) {
     __syncthreads();
     if (threadIdx.x == 0) { atomicMin(A.ep.minbits + r0, s_min[0]); atomicMax(A.ep.maxbits + r0, s_max[0]); }
     if (threadIdx.x == 1 && has1) { atomicMin(A.ep.minbits + r1, s_min[1]); atomicMax(A.ep.maxbits + r1, s_max[1]); }
+    // minimum of this CTA's chunk of LPB x-rows: lets the selection kernel skip chunks without candidates
+    if (A.ep.chunkmin && threadIdx.x < 2 && (threadIdx.x == 0 || has1))
+      A.ep.chunkmin[(long long)(threadIdx.x ? r1 : r0) * A.ep.chunk_pitch + blockIdx.x] = s_min[threadIdx.x];
   }
 }
 
@@ -418,7 +476,9 @@ struct Plan {
   float2 *twx = nullptr, *twy = nullptr, *twz = nullptr;
   float2 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
   long long w1_stride = 0, w2_stride = 0, w3_stride = 0, w4_stride = 0;  // float2 per pair
-  std::map<int, float2*> spectrum;
+  std::map<int, float2*> spectrum;   // full 3-D (2-D problems: 2-D) spectrum, scaled by 1/N
+  std::map<int, float2*> sxy;        // 3-D problems with the direct z pass: (x, y) spectrum of every plane, scaled by 1/(Nx Ny)
+  bool zdirect = false;              // direct correlation along z instead of the fused z transforms (tz <= 24)
   size_t workspace = 0;
 };
 
@@ -478,17 +538,37 @@ static cudaError_t launch_final(const FinalArgs& a, int log2n, int npair, cudaSt
   return cudaGetLastError();
 }
 
+static cudaError_t launch_zdirect(const ZDirectArgs& a, int npair, cudaStream_t s) {
+  dim3 grid((unsigned)((a.plane + 255) / 256), npair);
+  const int w = (a.tz + 3) / 4 * 4;
+  switch (w) {
+    case 4: k_fft_zdirect<4><<<grid, 256, 0, s>>>(a); break;
+    case 8: k_fft_zdirect<8><<<grid, 256, 0, s>>>(a); break;
+    case 12: k_fft_zdirect<12><<<grid, 256, 0, s>>>(a); break;
+    case 16: k_fft_zdirect<16><<<grid, 256, 0, s>>>(a); break;
+    case 20: k_fft_zdirect<20><<<grid, 256, 0, s>>>(a); break;
+    case 24: k_fft_zdirect<24><<<grid, 256, 0, s>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 static cudaError_t make_twiddles(float2** out, int N, cudaStream_t s) {
   std::vector<float2> h(N);
   for (int k = 0; k < N; ++k) {
     const double ang = -2.0 * M_PI * (double)k / (double)N;
     h[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
   }
-  cudaError_t e = cudaMalloc((void**)out, N * sizeof(float2));
+  cudaError_t e = iq::dmalloc((void**)out, N * sizeof(float2));
   if (e != cudaSuccess) return e;
   e = cudaMemcpyAsync(*out, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
   return cudaStreamSynchronize(s);
+}
+
+static bool zdirect_enabled() {
+  const char* ev = std::getenv("IQB200_FFT_ZDIRECT");  // experiments: 0 forces the fused z transforms
+  return !(ev && ev[0] == '0');
 }
 
 cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int tz, int max_templates, cudaStream_t s) {
@@ -502,6 +582,7 @@ cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int 
   p->Nx = 1 << p->lx; p->Ny = 1 << p->ly; p->Nz = 1 << p->lz;
   if (p->lx > 10 || p->ly > 10 || p->lz > 10) { delete p; return cudaErrorInvalidValue; }
   p->max_pairs = (max_templates + 1) / 2;
+  p->zdirect = p->lz > 0 && tz >= 2 && tz <= 24 && zdirect_enabled();
   cudaError_t e;
   if ((e = make_twiddles(&p->twx, p->Nx, s)) != cudaSuccess) { plan_destroy(p); return e; }
   if ((e = make_twiddles(&p->twy, p->Ny, s)) != cudaSuccess) { plan_destroy(p); return e; }
@@ -514,11 +595,11 @@ cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int 
     p->w3_stride = (long long)p->nzo * Ny * Nx;
   }
   const size_t mp = (size_t)p->max_pairs;
-  if ((e = cudaMalloc((void**)&p->w1, mp * p->w1_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
-  if ((e = cudaMalloc((void**)&p->w4, mp * p->w4_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+  if ((e = iq::dmalloc((void**)&p->w1, mp * p->w1_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+  if ((e = iq::dmalloc((void**)&p->w4, mp * p->w4_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
   if (p->lz > 0) {
-    if ((e = cudaMalloc((void**)&p->w2, mp * p->w2_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
-    if ((e = cudaMalloc((void**)&p->w3, mp * p->w3_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+    if ((e = iq::dmalloc((void**)&p->w2, mp * p->w2_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+    if ((e = iq::dmalloc((void**)&p->w3, mp * p->w3_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
   }
   p->workspace = mp * (p->w1_stride + p->w2_stride + p->w3_stride + p->w4_stride) * sizeof(float2);
   *out = p;
@@ -530,23 +611,24 @@ void plan_destroy(Plan* p) {
   cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->twz);
   cudaFree(p->w1); cudaFree(p->w2); cudaFree(p->w3); cudaFree(p->w4);
   for (auto& kv : p->spectrum) cudaFree(kv.second);
+  for (auto& kv : p->sxy) cudaFree(kv.second);
   delete p;
 }
 
 size_t plan_workspace_bytes(const Plan* p) { return p->workspace; }
 
 cudaError_t plan_set_image(Plan* p, int id, const float* d_img, cudaStream_t s) {
-  if (p->spectrum.count(id)) return cudaSuccess;
+  if (p->spectrum.count(id) || p->sxy.count(id)) return cudaSuccess;
   const long long Nx = p->Nx, Ny = p->Ny, Nz = p->Nz;
   float2 *t1 = nullptr, *t2 = nullptr, *spec = nullptr;
   cudaError_t e;
   // x pass: [nz][ny][Nx]
-  if ((e = cudaMalloc((void**)&t1, (size_t)p->nz * p->ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+  if ((e = iq::dmalloc((void**)&t1, (size_t)p->nz * p->ny * Nx * sizeof(float2))) != cudaSuccess) return e;
   RealPassArgs ra{d_img, t1, p->nx, p->nz * p->ny, p->twx};
   if ((e = launch_real(ra, p->lx, s)) != cudaSuccess) return e;
   const float scale = (float)(1.0 / ((double)Nx * (double)Ny * (double)Nz));
   if (p->lz == 0) {
-    if ((e = cudaMalloc((void**)&spec, (size_t)Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+    if ((e = iq::dmalloc((void**)&spec, (size_t)Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
     StridedArgs a{};
     a.in = t1; a.out = spec;
     a.in_sb = 0; a.in_se = Nx; a.in_batch = 0;
@@ -554,13 +636,23 @@ cudaError_t plan_set_image(Plan* p, int id, const float* d_img, cudaStream_t s) 
     a.nin = p->ny; a.flip = 0; a.nout = (int)Ny; a.na = (int)Nx; a.nb = 1; a.tw = p->twy; a.scale = scale;
     if ((e = launch_strided<0>(a, p->ly, 1, s)) != cudaSuccess) return e;
   } else {
-    if ((e = cudaMalloc((void**)&t2, (size_t)p->nz * Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&spec, (size_t)Nz * Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+    if ((e = iq::dmalloc((void**)&t2, (size_t)p->nz * Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+    if ((e = iq::dmalloc((void**)&spec, (size_t)Nz * Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
     StridedArgs a{};
     a.in = t1; a.out = t2;  // y pass: lines (x, z<nz)
     a.in_sb = (long long)p->ny * Nx; a.in_se = Nx;
     a.out_sb = Ny * Nx; a.out_se = Nx;
     a.nin = p->ny; a.flip = 0; a.nout = (int)Ny; a.na = (int)Nx; a.nb = p->nz; a.tw = p->twy; a.scale = 1.f;
+    if (p->zdirect) {
+      // direct z pass: keep the (x, y) spectrum of every plane, scaled for the two remaining inverse transforms
+      cudaFree(spec);
+      a.scale = (float)(1.0 / ((double)Nx * (double)Ny));
+      if ((e = launch_strided<0>(a, p->ly, 1, s)) != cudaSuccess) return e;
+      if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+      cudaFree(t1);
+      p->sxy[id] = t2;
+      return cudaSuccess;
+    }
     if ((e = launch_strided<0>(a, p->ly, 1, s)) != cudaSuccess) return e;
     StridedArgs b{};
     b.in = t2; b.out = spec;  // z pass: lines (x, y)
@@ -577,9 +669,16 @@ cudaError_t plan_set_image(Plan* p, int id, const float* d_img, cudaStream_t s) 
 }
 
 cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogue& ep, cudaStream_t s, int* launches) {
-  auto it = p->spectrum.find(id);
-  if (it == p->spectrum.end()) return cudaErrorInvalidValue;
-  const float2* spec = it->second;
+  const float2* spec = nullptr;
+  if (p->zdirect) {
+    auto it = p->sxy.find(id);
+    if (it == p->sxy.end()) return cudaErrorInvalidValue;
+    spec = it->second;
+  } else {
+    auto it = p->spectrum.find(id);
+    if (it == p->spectrum.end()) return cudaErrorInvalidValue;
+    spec = it->second;
+  }
   const int npair = (R + 1) / 2;
   if (npair > p->max_pairs) return cudaErrorInvalidValue;
   const long long Nx = p->Nx, Ny = p->Ny;
@@ -604,13 +703,21 @@ cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogu
     a.out_sb = Ny * Nx; a.out_se = Nx; a.out_batch = p->w2_stride;
     a.nin = p->ty; a.flip = 1; a.nout = (int)Ny; a.na = (int)Nx; a.nb = p->tz; a.tw = p->twy; a.scale = 1.f;
     if ((e = launch_strided<0>(a, p->ly, npair, s)) != cudaSuccess) return e;
-    StridedArgs b{};  // fused z: lines (x, y)
-    b.in = p->w2; b.out = p->w3;
-    b.in_sb = Nx; b.in_se = Ny * Nx; b.in_batch = p->w2_stride;
-    b.out_sb = Nx; b.out_se = Ny * Nx; b.out_batch = p->w3_stride;
-    b.nin = p->tz; b.flip = 1; b.nout = p->nzo; b.na = (int)Nx; b.nb = (int)Ny;
-    b.mul = spec; b.mul_sb = Nx; b.mul_se = Ny * Nx; b.tw = p->twz; b.scale = 1.f;
-    if ((e = launch_strided<1>(b, p->lz, npair, s)) != cudaSuccess) return e;
+    if (p->zdirect) {
+      ZDirectArgs z{};
+      z.sxy = spec; z.tmpl = p->w2; z.out = p->w3;
+      z.plane = Ny * Nx; z.tmpl_batch = p->w2_stride; z.out_batch = p->w3_stride;
+      z.nz = p->nz; z.tz = p->tz; z.nzo = p->nzo;
+      if ((e = launch_zdirect(z, npair, s)) != cudaSuccess) return e;
+    } else {
+      StridedArgs b{};  // fused z: lines (x, y)
+      b.in = p->w2; b.out = p->w3;
+      b.in_sb = Nx; b.in_se = Ny * Nx; b.in_batch = p->w2_stride;
+      b.out_sb = Nx; b.out_se = Ny * Nx; b.out_batch = p->w3_stride;
+      b.nin = p->tz; b.flip = 1; b.nout = p->nzo; b.na = (int)Nx; b.nb = (int)Ny;
+      b.mul = spec; b.mul_sb = Nx; b.mul_se = Ny * Nx; b.tw = p->twz; b.scale = 1.f;
+      if ((e = launch_strided<1>(b, p->lz, npair, s)) != cudaSuccess) return e;
+    }
     StridedArgs c{};  // inverse y: lines (x, z<nzo)
     c.in = p->w3; c.out = p->w4;
     c.in_sb = Ny * Nx; c.in_se = Nx; c.in_batch = p->w3_stride;
@@ -626,6 +733,8 @@ cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogu
   return cudaSuccess;
 }
 
+int final_chunk_rows(const Plan* p) { return lines_per_block(p->lx); }
+
 double correlate_bytes(const Plan* p, int R) {
   const double npair = (R + 1) / 2, c = sizeof(float2);
   const double Nx = p->Nx, Ny = p->Ny, Nz = p->Nz;
@@ -634,7 +743,7 @@ double correlate_bytes(const Plan* p, int R) {
     b += npair * c * (p->ty * Nx + p->nyo * Nx) + c * Ny * Nx;                             // fused y (+ spectrum once)
   } else {
     b += npair * c * (p->tz * p->ty * Nx + p->tz * Ny * Nx);                               // forward y
-    b += npair * c * (p->tz * Ny * Nx + p->nzo * Ny * Nx) + c * Nz * Ny * Nx;              // fused z (+ spectrum once)
+    b += npair * c * (p->tz * Ny * Nx + p->nzo * Ny * Nx) + c * (p->zdirect ? p->nz : Nz) * Ny * Nx;  // z pass (+ spectrum once)
     b += npair * c * (p->nzo * Ny * Nx + (double)p->nzo * p->nyo * Nx);                    // inverse y
   }
   b += npair * c * (double)p->nzo * p->nyo * Nx + (double)R * 4.0 * p->npos + 4.0 * p->npos;  // final + maps + A2

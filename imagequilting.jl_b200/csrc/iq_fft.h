@@ -16,6 +16,9 @@ struct Epilogue {
   float* out;               // [R][npos]
   unsigned* minbits;        // [R]
   unsigned* maxbits;        // [R]
+  unsigned* chunkmin;       // [R][nchunk] float bits of the minimum over enabled positions of every chunk of
+                            // final_chunk_rows(plan) consecutive x-rows (nchunk = ceil(nyo*nzo / rows)), or nullptr
+  long long chunk_pitch;    // entries between the chunk minima of consecutive templates (>= nchunk)
   int round_to_int;         // 1: image and templates are integer-valued -> AB is rounded (exact result)
 };
 
@@ -30,5 +33,7 @@ cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogu
 // Bytes moved through global memory by one correlate call with R templates (algorithmic, for the roofline).
 double correlate_bytes(const Plan* p, int R);
 size_t plan_workspace_bytes(const Plan* p);
+// x-rows of the distance map handled by one CTA of the last pass (granularity of Epilogue::chunkmin).
+int final_chunk_rows(const Plan* p);
 
 }  // namespace iqfft

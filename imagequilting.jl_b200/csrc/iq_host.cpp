@@ -13,6 +13,7 @@
 // other group(s), so the host cut hides behind the device search (or vice versa).
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -189,9 +190,21 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
                  int* status) {
   *status = 0;
   if (D->nsoft > 0 || D->hard_has) return IQ_ERR_STATE;
+  if (D->pipeline == 0) {
+    // Integer-valued (categorical) images make the cut capacities of graphcut.jl:52 degenerate (division by eps next
+    // to O(1) terms): equal-cost cuts abound and which one comes out depends on the max-flow algorithm's rounding.
+    // The reference's choice is Boykov-Kolmogorov on the host, so "auto" keeps such images on the host-staged
+    // pipeline (host cuts); continuous images have a unique minimum cut and go device-resident.
+    const long long nvox = (long long)G.n[0] * G.n[1] * G.n[2];
+    bool integer = true;
+    for (long long i = 0; i < nvox && integer; ++i) integer = D->ti_f32[i] == std::nearbyint(D->ti_f32[i]);
+    if (integer) return IQ_ERR_STATE;
+  }
   const auto t_start = clk::now();
   const int R = D->nreal;
-  int ngroups = D->ngroups > 0 ? D->ngroups : (R >= 16 ? 2 : 1);
+  // one lockstep group: a launch already carries every realization (FFT pairs, one cut CTA per slab), and a second
+  // stream only makes the kernels of the two groups fight for the same SMs (measured: 8-10 % slower on config 5)
+  int ngroups = D->ngroups > 0 ? D->ngroups : 1;
   ngroups = std::max(1, std::min(ngroups, R));
   struct RG { iq_ctx* ctx = nullptr; int r0 = 0, R = 0; };
   std::vector<RG> groups(ngroups);
@@ -282,9 +295,11 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   const auto t_fetch = clk::now();
   if (rc == IQ_OK && *status == 0) {
     const int64_t padc[3] = {G.pad[0], G.pad[1], G.pad[2]};
+    const int hw = std::max(1, (int)std::thread::hardware_concurrency());
+    const int nth = std::max(1, std::min(D->nthreads > 0 ? D->nthreads : hw, 8));
     for (auto& g : groups) {
+      if (D->out_real) rc = iq_sim_fetch_all(g.ctx, D->out_real_f32 ? 1 : 0, D->sim_size, D->out_real + g.r0, nth);
       for (int r = 0; r < g.R && rc == IQ_OK; ++r) {
-        if (D->out_real) rc = iq_sim_fetch(g.ctx, r, D->out_real_f32 ? 1 : 0, D->sim_size, D->out_real[g.r0 + r]);
         if (rc == IQ_OK && out_grids) rc = iq_sim_fetch(g.ctx, r, 0, padc, out_grids + (size_t)(g.r0 + r) * G.padvol);
         if (rc == IQ_OK && D->debug) rc = iq_sim_fetch_cut(g.ctx, r, out_cuts + (size_t)(g.r0 + r) * G.padvol);
       }

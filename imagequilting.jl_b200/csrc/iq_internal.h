@@ -83,6 +83,7 @@ struct PickJob {
   unsigned* cand_idx;            // [cap]
   float* cand_val;               // [nsrc][cap]
   long long cap;
+  const unsigned* chunkmin;      // mode 0, optional: float bits of the minimum of every chunk of src[0] (k_pick_chunks)
 };
 
 // One boundary cut for the device kernel (iq_cutgpu.cu): slabs laid out with the cut dimension slowest.
@@ -95,6 +96,11 @@ struct CutTask {
 };
 size_t graphcut_smem(int n0, int n1, int L);
 cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s);
+
+// Device allocation from the stream-ordered default memory pool with the release threshold lifted: memory freed by
+// one simulation (cudaFree returns it to the pool) is handed to the next without a trip to the driver's slow
+// cudaMalloc path.  The pointer is ready for every stream on return.
+cudaError_t dmalloc(void** p, size_t bytes);
 
 // ---- launch wrappers (iq_kernels.cu) -------------------------------------------------
 cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
@@ -111,6 +117,14 @@ cudaError_t launch_select_pass(SelJob* jobs, int njobs, long long npos, const in
                                cudaStream_t s);
 cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
 cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
+// Threshold selection driven by chunk minima (chunk = chunklen consecutive positions): only chunks whose minimum
+// passes the threshold are scanned.  total = kPickOverflow when more than kPickMaxChunks chunks qualify (the caller
+// falls back to count/write).
+constexpr int kPickMaxChunks = 2048;
+constexpr unsigned kPickOverflow = 0xffffffffu;
+cudaError_t launch_pick_chunks(PickJob* jobs, int njobs, long long npos, int chunklen, int nchunk, cudaStream_t s);
+cudaError_t launch_chunkmin(const float* maps, int njobs, long long npos, int chunklen, int nchunk, unsigned* chunkmin,
+                            long long pitch, cudaStream_t s);
 cudaError_t launch_fetch_tile(const float* img, int nx, int ny, int nz, int tx, int ty, int tz,
                               long long x0, long long y0, long long z0, float* out, cudaStream_t s);
 int pick_nblk(long long npos);

@@ -774,6 +774,22 @@ __global__ void k_fill_u32(unsigned* p, unsigned v, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+cudaError_t dmalloc(void** p, size_t bytes) {
+  static thread_local int configured = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (configured != dev) {
+    cudaMemPool_t pool;
+    if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
+    unsigned long long thr = ~0ull;
+    if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr)) != cudaSuccess) return e;
+    configured = dev;
+  }
+  if ((e = cudaMallocAsync(p, bytes ? bytes : 1, cudaStreamPerThread)) != cudaSuccess) return e;
+  return cudaStreamSynchronize(cudaStreamPerThread);
+}
+
 cudaError_t launch_fill_u32(unsigned* p, unsigned v, long long n, cudaStream_t s) {
   k_fill_u32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, v, n);
   return cudaGetLastError();
@@ -968,6 +984,131 @@ __global__ void __launch_bounds__(256) k_pick_write(PickJob* jobs, long long npo
     running += all;
     __syncthreads();
   }
+}
+
+// Threshold rule (iqsim.jl:237) driven by chunk minima: one CTA per tile.  Phase 1 compacts, in ascending order, the
+// chunks whose minimum passes the threshold; phase 2 counts the passing entries of those chunks (one warp per
+// chunk); phase 3 writes the candidates in ascending linear index.  A map is read only where candidates can be.
+__global__ void __launch_bounds__(1024) k_pick_chunks(PickJob* jobs, long long npos, int chunklen, int nchunk) {
+  PickJob& J = jobs[blockIdx.x];
+  if (J.mode != 0 || !J.chunkmin) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double thr = (1.0 + J.tol) * (double)__uint_as_float(*J.minbits);
+  __shared__ unsigned s_rows[kPickMaxChunks];
+  __shared__ unsigned s_cnt[kPickMaxChunks];
+  __shared__ unsigned s_w[32];
+  __shared__ unsigned s_nq;
+  if (tid == 0) s_nq = 0;
+  __syncthreads();
+  for (int base = 0; base < nchunk; base += 1024) {
+    const int ch = base + tid;
+    const bool q = ch < nchunk && (double)__uint_as_float(J.chunkmin[ch]) <= thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, q);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    unsigned before = 0, all = 0;
+    for (int w = 0; w < 32; ++w) {
+      const unsigned c = s_w[w];
+      if (w < warp) before += c;
+      all += c;
+    }
+    const unsigned nq0 = s_nq;
+    if (q) {
+      const unsigned slot = nq0 + before + __popc(bal & ((1u << lane) - 1u));
+      if (slot < (unsigned)kPickMaxChunks) s_rows[slot] = (unsigned)ch;
+    }
+    __syncthreads();
+    if (tid == 0) s_nq = nq0 + all;
+    __syncthreads();
+  }
+  const unsigned nq = s_nq;
+  if (nq > (unsigned)kPickMaxChunks) {
+    if (tid == 0) *J.total = kPickOverflow;
+    return;
+  }
+  const float* map = J.src[0];
+  for (unsigned k = warp; k < nq; k += 32) {
+    const long long p0 = (long long)s_rows[k] * chunklen;
+    const int len = (int)min((long long)chunklen, npos - p0);
+    unsigned c = 0;
+    for (int x = lane; x < len; x += 32) c += ((double)map[p0 + x] <= thr) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_cnt[k] = c;
+  }
+  __syncthreads();
+  // exclusive scan of the chunk counts (nq <= 2048: two entries per thread)
+  {
+    const unsigned a0 = (2u * tid < nq) ? s_cnt[2 * tid] : 0u, a1 = (2u * tid + 1u < nq) ? s_cnt[2 * tid + 1] : 0u;
+    unsigned incl = a0 + a1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned v = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      s_w[lane] = v;
+    }
+    __syncthreads();
+    const unsigned excl = incl - (a0 + a1) + (warp > 0 ? s_w[warp - 1] : 0u);
+    if (2u * tid < nq) s_cnt[2 * tid] = excl;
+    if (2u * tid + 1u < nq) s_cnt[2 * tid + 1] = excl + a0;
+    if (tid == 1023) *J.total = s_w[31];
+  }
+  __syncthreads();
+  for (unsigned k = warp; k < nq; k += 32) {
+    const long long p0 = (long long)s_rows[k] * chunklen;
+    const int len = (int)min((long long)chunklen, npos - p0);
+    unsigned off = s_cnt[k];
+    for (int x0 = 0; x0 < len; x0 += 32) {
+      const int x = x0 + lane;
+      const float v = x < len ? map[p0 + x] : 0.f;
+      const bool ok = x < len && (double)v <= thr;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const long long slot = (long long)off + __popc(bal & ((1u << lane) - 1u));
+        if (slot < J.cap) {
+          J.cand_idx[slot] = (unsigned)(p0 + x);
+          J.cand_val[slot] = v;
+        }
+      }
+      off += __popc(bal);
+    }
+  }
+}
+
+cudaError_t launch_pick_chunks(PickJob* jobs, int njobs, long long npos, int chunklen, int nchunk, cudaStream_t s) {
+  k_pick_chunks<<<njobs, 1024, 0, s>>>(jobs, npos, chunklen, nchunk);
+  return cudaGetLastError();
+}
+
+// Chunk minima (float bits) of njobs maps stored [job][npos]: one warp per chunk.  +Inf (disabled) entries never win.
+__global__ void __launch_bounds__(256) k_chunkmin(const float* __restrict__ maps, long long npos, int chunklen, int nchunk,
+                                                  unsigned* __restrict__ chunkmin, long long pitch) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (ch >= nchunk) return;
+  const long long p0 = (long long)ch * chunklen;
+  const int len = (int)min((long long)chunklen, npos - p0);
+  const float* m = maps + (long long)blockIdx.y * npos + p0;
+  unsigned mn = 0x7f800000u;
+  for (int x = lane; x < len; x += 32) mn = min(mn, __float_as_uint(m[x]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if (lane == 0) chunkmin[(long long)blockIdx.y * pitch + ch] = mn;
+}
+
+cudaError_t launch_chunkmin(const float* maps, int njobs, long long npos, int chunklen, int nchunk, unsigned* chunkmin,
+                            long long pitch, cudaStream_t s) {
+  k_chunkmin<<<dim3((unsigned)((nchunk + 7) / 8), njobs), 256, 0, s>>>(maps, npos, chunklen, nchunk, chunkmin, pitch);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStream_t s) {

@@ -60,6 +60,10 @@ struct SimState {
   int maxslabs = 0;               // slabs per tile at most
   void* d_export = nullptr;       // cropped realization in the output type
   size_t export_cap = 0;
+  char* h_export[2] = {nullptr, nullptr};  // pinned double buffer of iq_sim_fetch_all
+  void* d_export2[2] = {nullptr, nullptr};
+  size_t export2_cap = 0;
+  cudaEvent_t ev_export[2] = {nullptr, nullptr};
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev;    // per step: select start, select stop (= cut start), cut stop
   size_t ev_used = 0;
@@ -257,6 +261,11 @@ void sim_destroy(iq_ctx* c) {
   cudaFree(s->d_picks); cudaFree(s->d_status); cudaFree(s->d_cutA); cudaFree(s->d_cutB); cudaFree(s->d_keep);
   cudaFree(s->d_cut_iters); cudaFree(s->d_export);
   if (s->h_pickstage) cudaFreeHost(s->h_pickstage);
+  for (int i = 0; i < 2; ++i) {
+    if (s->h_export[i]) cudaFreeHost(s->h_export[i]);
+    cudaFree(s->d_export2[i]);
+    if (s->ev_export[i]) cudaEventDestroy(s->ev_export[i]);
+  }
   for (auto e : s->ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
   if (s->ev_end) cudaEventDestroy(s->ev_end);
@@ -334,34 +343,34 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   s->maxslab = maxslab;
   s->maxslabs = std::max(maxslabs, 1);
   const size_t R = (size_t)s->R, nimg = (size_t)c->nx * c->ny * c->nz, np = (size_t)std::max<int64_t>(d->npath, 1);
-  CK(cudaMalloc((void**)&s->d_grid, R * s->padvol * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_grid, R * s->padvol * sizeof(double)));
   CK(cudaMemsetAsync(s->d_grid, 0, R * s->padvol * sizeof(double), c->stream));  // simgrid = zeros (iqsim.jl:165)
   if (s->debug) {
-    CK(cudaMalloc((void**)&s->d_cutgrid, R * s->padvol));
+    CK(iq::dmalloc((void**)&s->d_cutgrid, R * s->padvol));
     CK(cudaMemsetAsync(s->d_cutgrid, 0, R * s->padvol, c->stream));
   }
-  CK(cudaMalloc((void**)&s->d_ti64, nimg * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_ti64, nimg * sizeof(double)));
   CK(cudaMemcpyAsync(s->d_ti64, d->ti64, nimg * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   s->h_u.assign(d->u, d->u + R * (size_t)d->npath);
-  CK(cudaMalloc((void**)&s->d_u, R * np * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_u, R * np * sizeof(double)));
   if (d->npath > 0)
     CK(cudaMemcpyAsync(s->d_u, d->u, R * (size_t)d->npath * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMalloc((void**)&s->d_tmpl, R * c->tilevol * sizeof(float)));
-  CK(cudaMalloc((void**)&s->d_b2, R * sizeof(double)));
-  CK(cudaMalloc((void**)&s->d_plane, R * c->tz * sizeof(double)));
-  CK(cudaMalloc((void**)&s->d_ticket, R * sizeof(unsigned)));
+  CK(iq::dmalloc((void**)&s->d_tmpl, R * c->tilevol * sizeof(float)));
+  CK(iq::dmalloc((void**)&s->d_b2, R * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_plane, R * c->tz * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_ticket, R * sizeof(unsigned)));
   CK(cudaMemsetAsync(s->d_ticket, 0, R * sizeof(unsigned), c->stream));
-  CK(cudaMalloc((void**)&s->d_picked, R * sizeof(long long)));
-  CK(cudaMalloc((void**)&s->d_picks, R * np * sizeof(long long)));
+  CK(iq::dmalloc((void**)&s->d_picked, R * sizeof(long long)));
+  CK(iq::dmalloc((void**)&s->d_picks, R * np * sizeof(long long)));
   CK(cudaMemsetAsync(s->d_picks, 0xff, R * np * sizeof(long long), c->stream));
   CK(cudaMallocHost((void**)&s->h_pickstage, R * np * sizeof(long long)));
-  CK(cudaMalloc((void**)&s->d_status, sizeof(int)));
+  CK(iq::dmalloc((void**)&s->d_status, sizeof(int)));
   CK(cudaMemsetAsync(s->d_status, 0, sizeof(int), c->stream));
   const size_t ntask = R * s->maxslabs;
-  CK(cudaMalloc((void**)&s->d_cutA, ntask * maxslab * sizeof(double)));
-  CK(cudaMalloc((void**)&s->d_cutB, ntask * maxslab * sizeof(double)));
-  CK(cudaMalloc((void**)&s->d_keep, ntask * maxslab));
-  CK(cudaMalloc((void**)&s->d_cut_iters, ntask * sizeof(int)));
+  CK(iq::dmalloc((void**)&s->d_cutA, ntask * maxslab * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_cutB, ntask * maxslab * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_keep, ntask * maxslab));
+  CK(iq::dmalloc((void**)&s->d_cut_iters, ntask * sizeof(int)));
   CK(cudaMemsetAsync(s->d_cut_iters, 0, ntask * sizeof(int), c->stream));
   // selection jobs never change during the simulation: threshold rule on the overlap distance of realization r
   for (int r = 0; r < s->R; ++r) {
@@ -378,6 +387,7 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     J.cand_idx = c->d_cand_idx + (size_t)r * c->npos;
     J.cand_val = c->d_cand_val + (size_t)r * c->max_src * c->npos;
     J.cap = c->npos;
+    J.chunkmin = c->d_chunkmin + (size_t)r * c->chunk_stride;
   }
   CK(cudaMemcpyAsync(c->d_pick, c->h_pick, R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventCreate(&s->ev_begin));
@@ -486,7 +496,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
         cudaFree(s->d_pack);
         s->d_pack = nullptr;
         s->pack_cap = 0;
-        CK(cudaMalloc((void**)&s->d_pack, (size_t)total * 2 * sizeof(float)));
+        CK(iq::dmalloc((void**)&s->d_pack, (size_t)total * 2 * sizeof(float)));
         s->pack_cap = (size_t)total * 2;
       }
       k_sim_pack<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(s->d_tmpl, c->tilevol, c->tx, c->ty, e->d_boxes,
@@ -498,13 +508,14 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       if (rc) return rc;
     }
     CK(cudaEventRecord(ev[0], c->stream));
-    CK(iq::launch_pick_count(c->d_pick, R, c->npos, c->stream));
-    CK(iq::launch_pick_write(c->d_pick, R, c->npos, c->stream));
+    rc = ensure_chunkmin(c, R);
+    if (rc) return rc;
+    CK(iq::launch_pick_chunks(c->d_pick, R, c->npos, c->chunk_len, c->chunk_n, c->stream));
     CK(iq::launch_tau(c->d_pick, R, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
     k_sim_sample<<<gR, 128, 0, c->stream>>>(c->d_pick, c->d_prob, s->d_u, s->npath, step, R, s->d_picked, s->d_picks,
                                             s->d_status);
     CK(cudaGetLastError());
-    c->launches += 5;
+    c->launches += 4;
   }
   CK(cudaEventRecord(ev[1], c->stream));
 
@@ -529,7 +540,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       CK(cudaStreamSynchronize(c->stream));
       cudaFree(e->d_cut_tasks);
       e->d_cut_tasks = nullptr;
-      CK(cudaMalloc((void**)&e->d_cut_tasks, recs.size() * sizeof(iq::CutTask)));
+      CK(iq::dmalloc((void**)&e->d_cut_tasks, recs.size() * sizeof(iq::CutTask)));
       CK(cudaMemcpy(e->d_cut_tasks, recs.data(), recs.size() * sizeof(iq::CutTask), cudaMemcpyHostToDevice));
       e->cut_ntask = ntask;
       e->cut_smem = smem;
@@ -592,7 +603,7 @@ int32_t iq_sim_fetch(iq_ctx* c, int32_t r, int32_t dtype, const int64_t* crop, v
     cudaFree(s->d_export);
     s->d_export = nullptr;
     s->export_cap = 0;
-    CK(cudaMalloc(&s->d_export, bytes));
+    CK(iq::dmalloc(&s->d_export, bytes));
     s->export_cap = bytes;
   }
   const double* g = s->d_grid + (size_t)r * s->padvol;
@@ -602,6 +613,65 @@ int32_t iq_sim_fetch(iq_ctx* c, int32_t r, int32_t dtype, const int64_t* crop, v
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, s->d_export, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return IQ_OK;
+}
+
+int32_t iq_sim_fetch_all(iq_ctx* c, int32_t dtype, const int64_t* crop, void* const* out, int32_t nthreads) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_fetch_all: no simulation open on this context");
+  SimState* s = c->sim;
+  if (!crop || !out || (dtype != 0 && dtype != 1)) return fail(IQ_ERR_INVALID, "iq_sim_fetch_all: bad argument");
+  for (int r = 0; r < s->R; ++r)
+    if (!out[r]) return fail(IQ_ERR_INVALID, "iq_sim_fetch_all: out[%d] is NULL", r);
+  CK(cudaSetDevice(c->device));
+  int cr[3] = {1, 1, 1};
+  for (int i = 0; i < c->ndim; ++i) {
+    cr[i] = (int)crop[i];
+    if (cr[i] < 1 || cr[i] > s->pad[i]) return fail(IQ_ERR_INVALID, "iq_sim_fetch_all: crop outside the padded grid");
+  }
+  const size_t n = (size_t)cr[0] * cr[1] * cr[2], bytes = n * (dtype == 0 ? sizeof(double) : sizeof(float));
+  if (bytes > s->export2_cap) {
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2; ++i) {
+      if (s->h_export[i]) cudaFreeHost(s->h_export[i]);
+      cudaFree(s->d_export2[i]);
+      s->h_export[i] = nullptr;
+      s->d_export2[i] = nullptr;
+      CK(cudaMallocHost((void**)&s->h_export[i], bytes));
+      CK(iq::dmalloc(&s->d_export2[i], bytes));
+      if (!s->ev_export[i]) CK(cudaEventCreateWithFlags(&s->ev_export[i], cudaEventDisableTiming));
+    }
+    s->export2_cap = bytes;
+  }
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  auto enqueue = [&](int r) -> int {
+    const int b = r & 1;
+    const double* g = s->d_grid + (size_t)r * s->padvol;
+    if (dtype == 0) k_sim_export<double><<<nb, 256, 0, c->stream>>>(g, s->pad[0], s->pad[1], cr[0], cr[1], cr[2], (double*)s->d_export2[b]);
+    else k_sim_export<float><<<nb, 256, 0, c->stream>>>(g, s->pad[0], s->pad[1], cr[0], cr[1], cr[2], (float*)s->d_export2[b]);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s->h_export[b], s->d_export2[b], bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(s->ev_export[b], c->stream));
+    return IQ_OK;
+  };
+  // realization r+1 is exported and copied into the other pinned buffer while the host moves realization r
+  const int nt = std::max(1, std::min(nthreads > 0 ? nthreads : 4, 16));
+  int rc = enqueue(0);
+  if (rc) return rc;
+  for (int r = 0; r < s->R; ++r) {
+    if (r + 1 < s->R) {
+      rc = enqueue(r + 1);
+      if (rc) return rc;
+    }
+    CK(cudaEventSynchronize(s->ev_export[r & 1]));
+    const char* src = s->h_export[r & 1];
+    char* dst = (char*)out[r];
+    const size_t chunk = (bytes + nt - 1) / nt;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int k = 0; k < nt; ++k) {
+      const size_t o = (size_t)k * chunk;
+      if (o < bytes) std::memcpy(dst + o, src + o, std::min(chunk, bytes - o));
+    }
+  }
   return IQ_OK;
 }
 

@@ -188,6 +188,9 @@ int32_t iq_sim_step(iq_ctx* ctx, int64_t step, const int64_t* start, const uint8
 int32_t iq_sim_sync(iq_ctx* ctx, int64_t* picks, int32_t* status);
 /* Copies realization r, cropped to crop[3] (unused dims = 1), to the host as FP64 (dtype 0) or FP32 (dtype 1). */
 int32_t iq_sim_fetch(iq_ctx* ctx, int32_t r, int32_t dtype, const int64_t* crop, void* out);
+/* Same for all realizations of the context: out[r] receives realization r.  Export kernel, device->host copy into a
+ * pinned double buffer and the host copy into out[r] (nthreads host threads, 0 = 4) are pipelined. */
+int32_t iq_sim_fetch_all(iq_ctx* ctx, int32_t dtype, const int64_t* crop, void* const* out, int32_t nthreads);
 /* Copies the boundary-cut grid of realization r (pad_size bytes; debug simulations only). */
 int32_t iq_sim_fetch_cut(iq_ctx* ctx, int32_t r, uint8_t* out);
 /* Device time (ms, CUDA events on the context's stream) of the simulation since iq_sim_begin: whole stream, the
