@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libiqb200.so")
+LIB_PATH = os.environ.get("IQB200_LIB") or os.path.join(_HERE, "libiqb200.so")  # IQB200_LIB: kernel-variant experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 IQ_OK = 0

@@ -28,7 +28,13 @@
 
 namespace iq {
 
-constexpr int kCutThreads = 1024;
+#ifndef IQ_CUT_THREADS
+#define IQ_CUT_THREADS 512
+#endif
+#ifndef IQ_CUT_RELABEL
+#define IQ_CUT_RELABEL 8
+#endif
+constexpr int kCutThreads = IQ_CUT_THREADS;
 constexpr int kCutBytesPerNode = 6 * 8 + 8 + 4 + 1;  // residuals, excess, height, topology byte
 
 __device__ __forceinline__ double edge_cap(const double* __restrict__ A, const double* __restrict__ B, int lo, int off,
@@ -172,9 +178,17 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
     if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
     __syncthreads();
 #pragma unroll 1
-    for (int colour = 0; colour < 7; ++colour) {
+    for (int cstep = 0; cstep < 7; ++cstep) {
+#ifndef IQ_CUT_ORDER_NATURAL
+      // colours visited with stride 3: the neighbour of a voxel along the cut axis (+k changes the colour by 3) is
+      // discharged in the very next phase, so flow injected next to the source slice can cross every inner layer
+      // within one sweep (Gauss-Seidel wavefront along the flow direction)
+      const int colour = (3 * cstep) % 7;
+#else
+      const int colour = cstep;
+#endif
       const unsigned short* cl = clist + colour * items;
-      const int wq = colour & 1;
+      const int wq = cstep & 1;
       // pass 1: compact the voxels of this colour that hold excess (dense warps in pass 2)
       for (int w0 = 0; w0 < items; w0 += kCutThreads) {
         const int w = w0 + tid;
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
     long long tc = clock64(); t_rel += tc - tb;
 #endif
     if (!any || iter >= max_iter) break;
-    if ((iter & 7) == 7 || iter == 3) {
+    if ((iter % IQ_CUT_RELABEL) == IQ_CUT_RELABEL - 1 || iter == 3) {
       global_relabel();
 #ifdef IQ_CUT_PROFILE
       t_glob += clock64() - tc; ++nglob;

@@ -38,6 +38,15 @@ __host__ __device__ constexpr int lines_per_block(int log2n) { return log2n >= 1
 // line-fastest global<->shared copies is bank-conflict free.
 __host__ __device__ constexpr int line_stride(int log2n) { return (1 << log2n) + ((1 << log2n) >> 4) + 1; }
 __device__ __forceinline__ int PI(int i) { return i + (i >> 4); }
+// In-place passes: when every pass of a transform is a single sweep of the CTA (lines_per_block * N / radix <= kThreads)
+// each thread holds all its inputs in registers before anything is written, so source and destination can be the
+// same buffer (one extra barrier per pass).  Halving the shared memory doubles the resident CTAs per SM, which is
+// what these streaming kernels need to keep enough loads in flight.
+__host__ __device__ constexpr bool inplace_ok(int log2n) {
+  const int rem = log2n % 4;
+  const int rmin = rem > 0 ? (1 << rem) : 16;
+  return log2n >= 1 && lines_per_block(log2n) * ((1 << log2n) / rmin) <= kThreads;
+}
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -113,23 +122,29 @@ __device__ __forceinline__ void dft_reg(float2 (&v)[R]) {
 // MUL: the inputs are multiplied by the spectrum tile `spec` (same layout) while they are read -- the
 // spectrum product of the fused forward/inverse kernel costs no extra pass.
 template <int LOG2N, int R, bool INV, bool MUL>
-__device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, float2* __restrict__ dst,
+__device__ __forceinline__ void stockham_pass(const float2* src, float2* dst,
                                               const float2* __restrict__ tw, const float2* __restrict__ spec,
                                               int nlines, int n, int ls) {
   constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), NB = N / R;
+  constexpr bool INPLACE = inplace_ok(LOG2N);  // src == dst: one sweep per thread, barrier between reads and writes
   const int s = 1 << ls, m = n / R, step = N / n;
-  for (int idx = threadIdx.x; idx < nlines * NB; idx += kThreads) {
-    const int line = idx / NB, b = idx - line * NB;
+  for (int idx = threadIdx.x; idx < (INPLACE ? kThreads : nlines * NB); idx += kThreads) {
+    const bool live = idx < nlines * NB;
+    const int line = live ? idx / NB : 0, b = live ? idx - line * NB : 0;
     const int p = b >> ls, q = b & (s - 1);
     const float2* xb = src + line * LS;
     float2* yb = dst + line * LS;
     float2 v[R];
+    if (live) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int i = PI(q + s * (p + j * m));
-      v[j] = xb[i];
-      if (MUL) v[j] = cmul(v[j], spec[line * LS + i]);
+      for (int j = 0; j < R; ++j) {
+        const int i = PI(q + s * (p + j * m));
+        v[j] = xb[i];
+        if (MUL) v[j] = cmul(v[j], spec[line * LS + i]);
+      }
     }
+    if (INPLACE) __syncthreads();
+    if (!live) continue;
     dft_reg<R, INV>(v);
     if (m > 1) {  // twiddles w_n^(p k): one table read, the powers by (shallow) repeated multiplication
       float2 w1 = tw[p * step];
@@ -165,6 +180,7 @@ __device__ float2* fft_lines(float2* src, float2* dst, const float2* __restrict_
   constexpr int n16 = LOG2N / 4, rem = LOG2N % 4;
   int n = N, ls = 0;
   bool first = true;
+  if constexpr (inplace_ok(LOG2N)) dst = src;
   if constexpr (n16 > 0) {
 #pragma unroll
     for (int i = 0; i < n16; ++i) {
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_tmpl(const TmplPassArgs A) {
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
   float2* b1 = sm + LPB * LS;
-  float2* tw = sm + 2 * LPB * LS;
+  float2* tw = sm + (inplace_ok(LOG2N) ? 1 : 2) * LPB * LS;
   const int pr = blockIdx.y, l0 = blockIdx.x * LPB;
   const int nl = min(LPB, A.nlines - l0);
   load_twiddles<LOG2N>(tw, A.tw);
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_real(const RealPassArgs A) {
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
   float2* b1 = sm + LPB * LS;
-  float2* tw = sm + 2 * LPB * LS;
+  float2* tw = sm + (inplace_ok(LOG2N) ? 1 : 2) * LPB * LS;
   const int l0 = blockIdx.x * LPB;
   const int nl = min(LPB, A.nlines - l0);
   load_twiddles<LOG2N>(tw, A.tw);
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_strided(const StridedArgs A) {
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
   float2* b1 = sm + LPB * LS;
-  float2* tw = sm + 2 * LPB * LS;
+  float2* tw = sm + (inplace_ok(LOG2N) ? 1 : 2) * LPB * LS;
   float2* spec = tw + N;  // MODE 1 only
   const int a0 = blockIdx.x * LPB, b = blockIdx.y;
   const int nl = min(LPB, A.na - a0);
@@ -347,11 +363,13 @@ struct ZDirectArgs {
 };
 template <int W>
 __global__ void __launch_bounds__(256) k_fft_zdirect(const ZDirectArgs A) {
-  const long long col = (long long)blockIdx.x * 256 + threadIdx.x;
+  // blockIdx.x = template pair (fastest): the CTAs that read the same spectrum columns are scheduled together, so the
+  // spectrum comes from DRAM once per launch and from L2 for every other pair
+  const long long col = (long long)blockIdx.y * 256 + threadIdx.x;
   if (col >= A.plane) return;
   const float2* __restrict__ S = A.sxy + col;
-  const float2* __restrict__ T = A.tmpl + (long long)blockIdx.y * A.tmpl_batch + col;
-  float2* __restrict__ O = A.out + (long long)blockIdx.y * A.out_batch + col;
+  const float2* __restrict__ T = A.tmpl + (long long)blockIdx.x * A.tmpl_batch + col;
+  float2* __restrict__ O = A.out + (long long)blockIdx.x * A.out_batch + col;
   const float2 zero = make_float2(0.f, 0.f);
   float2 t[W], s[W];
 #pragma unroll
@@ -398,7 +416,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_final(const FinalArgs A) {
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
   float2* b1 = sm + LPB * LS;
-  float2* tw = sm + 2 * LPB * LS;
+  float2* tw = sm + (inplace_ok(LOG2N) ? 1 : 2) * LPB * LS;
   __shared__ unsigned s_min[2], s_max[2];
   const int pr = blockIdx.y, l0 = blockIdx.x * LPB;
   const int nl = min(LPB, A.nlines - l0);
@@ -464,7 +482,8 @@ static int ilog2_ceil(int n) {
 }
 static size_t smem_bytes(int log2n, bool with_spectrum = false) {
   const int N = 1 << log2n;
-  return (size_t)((with_spectrum ? 3 : 2) * lines_per_block(log2n) * line_stride(log2n) + N) * sizeof(float2);
+  const int nbuf = (inplace_ok(log2n) ? 1 : 2) + (with_spectrum ? 1 : 0);
+  return (size_t)(nbuf * lines_per_block(log2n) * line_stride(log2n) + N) * sizeof(float2);
 }
 
 struct Plan {
@@ -539,7 +558,7 @@ static cudaError_t launch_final(const FinalArgs& a, int log2n, int npair, cudaSt
 }
 
 static cudaError_t launch_zdirect(const ZDirectArgs& a, int npair, cudaStream_t s) {
-  dim3 grid((unsigned)((a.plane + 255) / 256), npair);
+  dim3 grid(npair, (unsigned)((a.plane + 255) / 256));
   const int w = (a.tz + 3) / 4 * 4;
   switch (w) {
     case 4: k_fft_zdirect<4><<<grid, 256, 0, s>>>(a); break;
