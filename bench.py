@@ -224,6 +224,10 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ B200 arm
+    # keep stdout for the ONE JSON line: libraries (NCCL prints its version banner) write to stderr meanwhile
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import iqb200
@@ -352,7 +356,9 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": ncores, "kind": "port",
                                 "sample": f"first {mt} of {nt} tiles of 1 realization ({dt:.1f} s), SciPy-FFT restatement "
                                           f"(FP64, workers={ncores}), boundary cut skipped; not Julia"}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     return 0
 
 

@@ -23,6 +23,7 @@
 
 #include <math_constants.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -121,7 +122,11 @@ __device__ __forceinline__ void dft_reg(float2 (&v)[R]) {
 // registers:  y[q + s (R p + k)] = w_n^(p k) * sum_j x[q + s (p + j n/R)] w_R^(j k).
 // MUL: the inputs are multiplied by the spectrum tile `spec` (same layout) while they are read -- the
 // spectrum product of the fused forward/inverse kernel costs no extra pass.
-template <int LOG2N, int R, bool INV, bool MUL>
+// LIN (in-place transforms only): the input of this pass is NOT in the padded line layout but where a bulk (TMA)
+// copy dropped it: LIN = 1 lines of N consecutive elements, N apart; LIN = 2 element-major tiles
+// [element][line] of LPB lines (threads then take the line index fastest so that the reads stay conflict free).
+// The pass writes the padded layout, so every later pass is the ordinary one.
+template <int LOG2N, int R, bool INV, bool MUL, int LIN = 0>
 __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst,
                                               const float2* __restrict__ tw, const float2* __restrict__ spec,
                                               int nlines, int n, int ls) {
@@ -129,8 +134,12 @@ __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst,
   constexpr bool INPLACE = inplace_ok(LOG2N);  // src == dst: one sweep per thread, barrier between reads and writes
   const int s = 1 << ls, m = n / R, step = N / n;
   for (int idx = threadIdx.x; idx < (INPLACE ? kThreads : nlines * NB); idx += kThreads) {
+    static_assert(LIN == 0 || (inplace_ok(LOG2N) && !MUL), "bulk-copy layouts need the in-place transform");
+    constexpr int LPBC = lines_per_block(LOG2N);
     const bool live = idx < nlines * NB;
-    const int line = live ? idx / NB : 0, b = live ? idx - line * NB : 0;
+    int line, b;
+    if (LIN == 2) { line = idx % LPBC; b = idx / LPBC; if (!live) { line = 0; b = 0; } }
+    else { line = live ? idx / NB : 0; b = live ? idx - line * NB : 0; }
     const int p = b >> ls, q = b & (s - 1);
     const float2* xb = src + line * LS;
     float2* yb = dst + line * LS;
@@ -138,9 +147,14 @@ __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst,
     if (live) {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        const int i = PI(q + s * (p + j * m));
-        v[j] = xb[i];
-        if (MUL) v[j] = cmul(v[j], spec[line * LS + i]);
+        const int e = q + s * (p + j * m);
+        if (LIN == 1) v[j] = src[line * N + e];
+        else if (LIN == 2) v[j] = src[e * LPBC + line];
+        else {
+          const int i = PI(e);
+          v[j] = xb[i];
+          if (MUL) v[j] = cmul(v[j], spec[line * LS + i]);
+        }
       }
     }
     if (INPLACE) __syncthreads();
@@ -173,7 +187,7 @@ __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst,
 
 // Full transform of `nlines` lines (ping-pong between two buffers); returns the buffer holding the result.
 // Radix schedule: 16 while >= 4 bits remain, then 8 / 4 / 2 for the rest.
-template <int LOG2N, bool INV, bool MUL>
+template <int LOG2N, bool INV, bool MUL, int LIN = 0>
 __device__ float2* fft_lines(float2* src, float2* dst, const float2* __restrict__ tw, const float2* __restrict__ spec,
                              int nlines) {
   constexpr int N = 1 << LOG2N;
@@ -185,6 +199,7 @@ __device__ float2* fft_lines(float2* src, float2* dst, const float2* __restrict_
 #pragma unroll
     for (int i = 0; i < n16; ++i) {
       if (MUL && first) stockham_pass<LOG2N, 16, INV, true>(src, dst, tw, spec, nlines, n, ls);
+      else if (LIN != 0 && first) stockham_pass<LOG2N, 16, INV, false, LIN>(src, dst, tw, spec, nlines, n, ls);
       else stockham_pass<LOG2N, 16, INV, false>(src, dst, tw, spec, nlines, n, ls);
       first = false;
       float2* t = src; src = dst; dst = t;
@@ -194,6 +209,7 @@ __device__ float2* fft_lines(float2* src, float2* dst, const float2* __restrict_
   if constexpr (rem > 0) {
     constexpr int R = 1 << rem;
     if (MUL && first) stockham_pass<LOG2N, R, INV, true>(src, dst, tw, spec, nlines, n, ls);
+    else if (LIN != 0 && first) stockham_pass<LOG2N, R, INV, false, LIN>(src, dst, tw, spec, nlines, n, ls);
     else stockham_pass<LOG2N, R, INV, false>(src, dst, tw, spec, nlines, n, ls);
     float2* t = src; src = dst; dst = t;
   }
@@ -377,13 +393,18 @@ __global__ void __launch_bounds__(256) k_fft_zdirect(const ZDirectArgs A) {
 #pragma unroll
   for (int j = 0; j < W - 1; ++j) s[j] = j < A.nz ? S[(long long)j * A.plane] : zero;
   s[W - 1] = zero;
+  const float2* __restrict__ sp = S + (long long)(W - 1) * A.plane;  // next spectrum plane to enter the window
+  float2* __restrict__ op = O;
+  const long long step = A.plane;
   for (int z0 = 0; z0 < A.nzo; z0 += W) {
     float2 nxt[W];
+    const int navail = A.nz - (z0 + W - 1);  // spectrum planes left for this block of W outputs
 #pragma unroll
     for (int m = 0; m < W; ++m) {
-      const int zz = z0 + m + W - 1;
-      nxt[m] = zz < A.nz ? S[(long long)zz * A.plane] : zero;
+      nxt[m] = m < navail ? *sp : zero;
+      sp += step;
     }
+    const int nout = A.nzo - z0;
 #pragma unroll
     for (int m = 0; m < W; ++m) {
       s[(m + W - 1) % W] = nxt[m];
@@ -396,7 +417,8 @@ __global__ void __launch_bounds__(256) k_fft_zdirect(const ZDirectArgs A) {
         ay = fmaf(sv.x, tv.y, ay);
         ay = fmaf(sv.y, tv.x, ay);
       }
-      if (z0 + m < A.nzo) O[(long long)(z0 + m) * A.plane] = make_float2(ax, ay);
+      if (m < nout) *op = make_float2(ax, ay);
+      op += step;
     }
   }
 }
@@ -410,45 +432,43 @@ struct FinalArgs {
   Epilogue ep;
   const float2* tw;
 };
+// Distance epilogue of the last pass for the nl lines of tile `blk` of template pair `pr` (result lines in `res`,
+// padded layout): |A2 - 2 AB + B2|, disabled -> +Inf, min / max of the map and the minimum of the tile (chunk).
 template <int LOG2N>
-__global__ void __launch_bounds__(kThreads) k_fft_x_final(const FinalArgs A) {
-  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
-  extern __shared__ __align__(16) float2 sm[];
-  float2* b0 = sm;
-  float2* b1 = sm + LPB * LS;
-  float2* tw = sm + (inplace_ok(LOG2N) ? 1 : 2) * LPB * LS;
-  __shared__ unsigned s_min[2], s_max[2];
-  const int pr = blockIdx.y, l0 = blockIdx.x * LPB;
-  const int nl = min(LPB, A.nlines - l0);
-  load_twiddles<LOG2N>(tw, A.tw);
-  if (threadIdx.x < 2) { s_min[threadIdx.x] = 0x7f800000u; s_max[threadIdx.x] = 0u; }
-  const float2* in = A.in + ((long long)pr * A.nlines + l0) * N;
-  for (int i = threadIdx.x; i < nl * N; i += kThreads) {
-    const int line = i >> LOG2N, e = i & (N - 1);
-    b0[line * LS + PI(e)] = in[(long long)line * N + e];
-  }
-  __syncthreads();
-  const float2* res = fft_lines<LOG2N, true, false>(b0, b1, tw, nullptr, nl);
+__device__ __forceinline__ void final_epilogue(const FinalArgs& A, const float2* res, int pr, int blk, int l0, int nl,
+                                               unsigned* s_min, unsigned* s_max) {
+  constexpr int LS = line_stride(LOG2N);
   const int r0 = 2 * pr, r1 = 2 * pr + 1;
   const bool has1 = r1 < A.R;
   const double b20 = A.ep.b2[r0], b21 = has1 ? A.ep.b2[r1] : 0.0;
   unsigned mn0 = 0x7f800000u, mx0 = 0u, mn1 = 0x7f800000u, mx1 = 0u;
-  for (int i = threadIdx.x; i < nl * A.nxo; i += kThreads) {
-    const int line = i / A.nxo, x = i - line * A.nxo;
-    const long long p = (long long)(l0 + line) * A.nxo + x;
-    float2 ab = res[line * LS + PI(x)];
-    if (A.ep.round_to_int) { ab.x = rintf(ab.x); ab.y = rintf(ab.y); }
-    const double a2 = A.ep.a2 ? (double)__ldg(A.ep.a2 + p) : 0.0;
-    const bool dis = A.ep.disabled && A.ep.disabled[p];
-    float d0 = (float)fabs(a2 - 2.0 * (double)ab.x + b20);
-    if (dis) d0 = CUDART_INF_F;
-    A.ep.out[(long long)r0 * A.npos + p] = d0;
-    if (!dis) { const unsigned u = __float_as_uint(d0); mn0 = min(mn0, u); mx0 = max(mx0, u); }
-    if (has1) {
-      float d1 = (float)fabs(a2 - 2.0 * (double)ab.y + b21);
-      if (dis) d1 = CUDART_INF_F;
-      A.ep.out[(long long)r1 * A.npos + p] = d1;
-      if (!dis) { const unsigned u = __float_as_uint(d1); mn1 = min(mn1, u); mx1 = max(mx1, u); }
+  // one x column per thread, walked down the lines of the tile: no index division, unit-stride pointers (the profile
+  // of the first version showed this epilogue, not the transform, saturating the integer pipe)
+  const bool rnd = A.ep.round_to_int != 0;
+  for (int x = threadIdx.x; x < A.nxo; x += kThreads) {
+    const float2* rp = res + PI(x);
+    long long p = (long long)l0 * A.nxo + x;
+    const float* a2p = A.ep.a2 ? A.ep.a2 + p : nullptr;
+    const uint8_t* dp = A.ep.disabled ? A.ep.disabled + p : nullptr;
+    float* o0 = A.ep.out + (long long)r0 * A.npos + p;
+    float* o1 = A.ep.out + (long long)r1 * A.npos + p;
+#pragma unroll 2
+    for (int line = 0; line < nl; ++line) {
+      float2 ab = rp[line * LS];
+      if (rnd) { ab.x = rintf(ab.x); ab.y = rintf(ab.y); }
+      const long long off = (long long)line * A.nxo;
+      const double a2 = a2p ? (double)__ldg(a2p + off) : 0.0;
+      const bool dis = dp && dp[off];
+      float d0 = (float)fabs(a2 - 2.0 * (double)ab.x + b20);
+      if (dis) d0 = CUDART_INF_F;
+      o0[off] = d0;
+      if (!dis) { const unsigned u = __float_as_uint(d0); mn0 = min(mn0, u); mx0 = max(mx0, u); }
+      if (has1) {
+        float d1 = (float)fabs(a2 - 2.0 * (double)ab.y + b21);
+        if (dis) d1 = CUDART_INF_F;
+        o1[off] = d1;
+        if (!dis) { const unsigned u = __float_as_uint(d1); mn1 = min(mn1, u); mx1 = max(mx1, u); }
+      }
     }
   }
   if (A.ep.minbits) {
@@ -466,9 +486,103 @@ __global__ void __launch_bounds__(kThreads) k_fft_x_final(const FinalArgs A) {
     __syncthreads();
     if (threadIdx.x == 0) { atomicMin(A.ep.minbits + r0, s_min[0]); atomicMax(A.ep.maxbits + r0, s_max[0]); }
     if (threadIdx.x == 1 && has1) { atomicMin(A.ep.minbits + r1, s_min[1]); atomicMax(A.ep.maxbits + r1, s_max[1]); }
-    // minimum of this CTA's chunk of LPB x-rows: lets the selection kernel skip chunks without candidates
+    // minimum of this tile's chunk of LPB x-rows: lets the selection kernel skip chunks without candidates
     if (A.ep.chunkmin && threadIdx.x < 2 && (threadIdx.x == 0 || has1))
-      A.ep.chunkmin[(long long)(threadIdx.x ? r1 : r0) * A.ep.chunk_pitch + blockIdx.x] = s_min[threadIdx.x];
+      A.ep.chunkmin[(long long)(threadIdx.x ? r1 : r0) * A.ep.chunk_pitch + blk] = s_min[threadIdx.x];
+  }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads, 4) k_fft_x_final(const FinalArgs A) {
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
+  extern __shared__ __align__(16) float2 sm[];
+  float2* b0 = sm;
+  float2* b1 = sm + LPB * LS;
+  float2* tw = sm + (inplace_ok(LOG2N) ? 1 : 2) * LPB * LS;
+  __shared__ unsigned s_min[2], s_max[2];
+  const int pr = blockIdx.y, l0 = blockIdx.x * LPB;
+  const int nl = min(LPB, A.nlines - l0);
+  load_twiddles<LOG2N>(tw, A.tw);
+  if (threadIdx.x < 2) { s_min[threadIdx.x] = 0x7f800000u; s_max[threadIdx.x] = 0u; }
+  const float2* in = A.in + ((long long)pr * A.nlines + l0) * N;
+  for (int i = threadIdx.x; i < nl * N; i += kThreads) {
+    const int line = i >> LOG2N, e = i & (N - 1);
+    b0[line * LS + PI(e)] = in[(long long)line * N + e];
+  }
+  __syncthreads();
+  const float2* res = fft_lines<LOG2N, true, false>(b0, b1, tw, nullptr, nl);
+  final_epilogue<LOG2N>(A, res, pr, blockIdx.x, l0, nl, s_min, s_max);
+}
+
+// ---- TMA helpers (bulk asynchronous copies global -> shared, completion on an mbarrier) -------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// orders earlier generic-proxy accesses to shared memory before later asynchronous-proxy (TMA) writes
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- pass C, streaming version: persistent CTAs, the next tile of LPB lines (one contiguous block of global
+//      memory) is fetched by ONE bulk TMA copy into the other half of a double buffer while the current tile is
+//      transformed in place and written out.  The first pass reads the unpadded lines the copy delivered.
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads, 3) k_fft_x_final_tma(const FinalArgs A, int ntile, int total) {
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
+  static_assert(inplace_ok(LOG2N), "streaming kernels need the in-place transform");
+  extern __shared__ __align__(16) float2 sm[];
+  float2* const buf0 = sm;
+  float2* const buf1 = sm + LPB * LS;
+  float2* tw = sm + 2 * LPB * LS;
+  __shared__ unsigned s_min[2], s_max[2];
+  __shared__ __align__(8) unsigned long long bar[2];
+  load_twiddles<LOG2N>(tw, A.tw);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t, int b) {  // thread 0 only
+    const int pr = t / ntile, blk = t - pr * ntile;
+    const int l0 = blk * LPB, nl = min(LPB, A.nlines - l0);
+    const unsigned bytes = (unsigned)(nl * N * sizeof(float2));
+    fence_async_smem();
+    mbar_expect_tx(&bar[b], bytes);
+    bulk_g2s(b ? buf1 : buf0, A.in + ((long long)pr * A.nlines + l0) * N, bytes, &bar[b]);
+  };
+  int t = blockIdx.x;
+  if (threadIdx.x == 0 && t < total) issue(t, 0);
+  for (int it = 0; t < total; t += gridDim.x, ++it) {
+    const int b = it & 1;
+    const int tn = t + gridDim.x;
+    if (threadIdx.x == 0 && tn < total) issue(tn, b ^ 1);  // the other buffer was released by the barrier below
+    if (threadIdx.x < 2) { s_min[threadIdx.x] = 0x7f800000u; s_max[threadIdx.x] = 0u; }
+    mbar_wait(&bar[b], (unsigned)((it >> 1) & 1));
+    const int pr = t / ntile, blk = t - pr * ntile;
+    const int l0 = blk * LPB, nl = min(LPB, A.nlines - l0);
+    float2* cur = b ? buf1 : buf0;
+    const float2* res = fft_lines<LOG2N, true, false, 1>(cur, cur, tw, nullptr, nl);
+    final_epilogue<LOG2N>(A, res, pr, blk, l0, nl, s_min, s_max);
+    __syncthreads();  // everybody is done with buf[b] and s_min before they are reused
   }
 }
 
@@ -548,7 +662,42 @@ static cudaError_t launch_strided(const StridedArgs& a_in, int log2n, int batch,
                         k_fft_strided<L, MODE><<<grid, kThreads, sm, s>>>(a); });
   return cudaGetLastError();
 }
+static bool tma_enabled() {
+  // Experimental (IQB200_FFT_TMA=1): persistent CTAs with a TMA-fed double buffer.  Bit-identical results, but on
+  // config 5 it is slower than one tile per CTA (1.19 ms vs 0.77 ms per 32 template pairs): the pass is bound by
+  // instruction issue, not by load latency, and the double buffer costs a resident CTA per SM.
+  const char* ev = std::getenv("IQB200_FFT_TMA");
+  return ev && ev[0] == '1';
+}
+
+template <int L>
+static cudaError_t launch_final_tma(const FinalArgs& a, int npair, cudaStream_t s) {
+  if constexpr (inplace_ok(L)) {
+    constexpr int LPB = lines_per_block(L);
+    const size_t sm = (size_t)(2 * LPB * line_stride(L) + (1 << L)) * sizeof(float2);
+    cudaError_t e = set_smem(k_fft_x_final_tma<L>, sm);
+    if (e != cudaSuccess) return e;
+    static int ctas_per_sm = 0, nsm = 0;
+    if (!nsm) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fft_x_final_tma<L>, kThreads, sm);
+    if (e != cudaSuccess) return e;
+    const int ntile = (a.nlines + LPB - 1) / LPB, total = ntile * npair;
+    const int grid = std::max(1, std::min(total, nsm * std::max(ctas_per_sm, 1)));
+    k_fft_x_final_tma<L><<<grid, kThreads, sm, s>>>(a, ntile, total);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;
+  }
+}
+
 static cudaError_t launch_final(const FinalArgs& a, int log2n, int npair, cudaStream_t s) {
+  if (tma_enabled() && inplace_ok(log2n) && log2n >= 4) {
+    FFT_DISPATCH(log2n, { return launch_final_tma<L>(a, npair, s); });
+  }
   const size_t sm = smem_bytes(log2n);
   const int LPB = lines_per_block(log2n);
   dim3 grid((a.nlines + LPB - 1) / LPB, npair);

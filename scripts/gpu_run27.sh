@@ -1,0 +1,4 @@
+timeout 900 python bench.py > gpurun_out/bench_r01_resident.json 2> gpurun_out/bench_r01_resident.err; tail -c 2500 gpurun_out/bench_r01_resident.json; tail -3 gpurun_out/bench_r01_resident.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fft_x_final|k_fft_strided|k_fft_zdirect|k_graphcut" -s 600 -c 5 -o gpurun_out/prof_resident_r01 python scripts/resident_bench.py --config 5 --nreal 64 --ngroups 1 --reps 1 > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
