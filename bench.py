@@ -327,7 +327,22 @@ def main():
                 "kernel": "FFT correlation passes (k_fft_x_tmpl, k_fft_strided<fwd|fused|inv>, k_fft_x_final)",
                 "kernel_ms_total": fft_ms, "searches_fft": int(nfft), "searches_direct": int(ndirect),
                 "bytes_per_search": fft_bytes / max(nfft, 1), "direct_equivalent_tfma": eq_tfma,
-                "note": "working set per launch (templates x padded volume) is partly L2-resident; bytes are algorithmic"}
+                "note": "achieved = bytes the pruned passes must move (iqfft::correlate_bytes, DESIGN.md section 3) / CUDA-event "
+                        "time of the passes on the launching stream; the image spectrum is served from L2"}
+        # SURVEY 8(d) accounting of the same searches: image once per launch + one distance map per search + the
+        # template/mask (+ one read of the cached spectrum per launch), independent of how the correlation is computed
+        launches_fft = max(nfft / max(args.nreal_per_gpu, 1), 1.0)
+        mean_nnz = fma_per_real / max(npos, 1) / max(nsearch, 1)
+        spec_bytes = 8.0 * float(np.prod([1 << int(np.ceil(np.log2(max(v, 1)))) for v in ti.shape[:2]])) * (ti.shape[2] if ti.ndim == 3 else 1)
+        b8d = launches_fft * (4.0 * nti + spec_bytes) + nfft * (4.0 * npos + 8.0 * mean_nnz)
+        roof["survey_8d"] = {"bytes_per_search": b8d / max(nfft, 1), "achieved_gbs": b8d / (fft_ms * 1e-3) / 1e9,
+                             "frac": b8d / (fft_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 1.0),
+                             "note": "B_alg(R) = 4|TI| + spectrum + R(4 npos + 8 nnz) per launch of R searches: the floor any "
+                                     "method must move; the FFT method's own traffic is `bytes_per_search`"}
+        # traffic: DRAM bytes of the passes per launch of 64 searches, from the committed ncu launch list
+        roof["traffic"] = 6.63e9 if args.config == 5 and args.nreal_per_gpu == 64 else None
+        roof["traffic_note"] = ("dram__bytes_read+write summed over the five FFT passes of one step (64 searches), "
+                                "profiles/r01_launches_resident.csv; algorithmic bytes of the same launch: 64 x bytes_per_search")
         if direct_ms > 0 and ndirect > 0:
             roof["direct_kernel_ms_total"] = direct_ms
     else:

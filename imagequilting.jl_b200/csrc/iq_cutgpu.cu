@@ -71,10 +71,12 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
   unsigned short* clist = reinterpret_cast<unsigned short*>(topo + ((nfree + 3) & ~3));  // [7][items] voxel of item or 0xffff
   unsigned short* fr0 = clist + 7 * items;   // [nfree] BFS frontier (ping) / active list of a colour phase
   unsigned short* fr1 = fr0 + nfree;         // [nfree] BFS frontier (pong)
-  __shared__ int s_cnt[2];
+  __shared__ int s_cnt[3];
+  __shared__ int offs[6];  // neighbour offsets for the dynamically indexed BFS (a register array would live in local memory)
   const int tid = threadIdx.x;
   const int HMAX = nfree + 2;
   const int off[6] = {1, -1, n0, -n0, P, -P};
+  if (tid < 6) offs[tid] = off[tid];
 
   // ---- capacities, topology and initial preflow (arcs out of the source slice are saturated) ----
   for (int i = tid; i < nfree; i += kCutThreads) {
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
   // frontiers in shared memory (every voxel is expanded once; levels are unique, so the result does not depend
   // on the order in which a frontier is filled).  Voxels that cannot reach the sink keep HMAX.
   auto global_relabel = [&]() {
-    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+    if (tid < 3) s_cnt[tid] = 0;
     __syncthreads();
     for (int i0 = 0; i0 < nfree; i0 += kCutThreads) {
       const int i = i0 + tid;
@@ -133,27 +135,30 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
       }
     }
     __syncthreads();
+    // three rotating counters: level L reads s_cnt[L % 3], fills s_cnt[(L + 1) % 3] and clears s_cnt[(L + 2) % 3]
+    // (the input of level L - 1, dead by now) -- one barrier per level
     unsigned short* cur = fr0;
     unsigned short* nxt = fr1;
-    int which = 0;
+    int ci = 0;
     for (int level = 1;; ++level) {
-      const int n = s_cnt[which];
+      const int n = s_cnt[ci];
       if (n == 0) break;
+      const int cn = ci == 2 ? 0 : ci + 1, cz = cn == 2 ? 0 : cn + 1;
+      if (tid == 0) s_cnt[cz] = 0;
       // 6 threads per frontier voxel: one per direction
       for (int t = tid; t < n * 6; t += kCutThreads) {
         const int v = cur[t / 6], dir = t % 6;
         if (!((topo[v] >> dir) & 1u)) continue;
-        const int x = v + off[dir];
+        const int x = v + offs[dir];
         if (h[x] != HMAX) continue;
         if (!(r[(dir ^ 1) * nfree + x] > 0.0)) continue;  // arc x -> v must have residual capacity
-        if (atomicCAS(&h[x], HMAX, level + 1) == HMAX) nxt[atomicAdd(&s_cnt[which ^ 1], 1)] = (unsigned short)x;
+        if (atomicCAS(&h[x], HMAX, level + 1) == HMAX) nxt[atomicAdd(&s_cnt[cn], 1)] = (unsigned short)x;
       }
       __syncthreads();
-      if (tid == 0) s_cnt[which] = 0;
-      which ^= 1;
+      ci = cn;
       unsigned short* tsw = cur; cur = nxt; nxt = tsw;
-      __syncthreads();
     }
+    __syncthreads();
   };
 #ifdef IQ_CUT_PROFILE
   long long t_push = 0, t_rel = 0, t_glob = 0, t0 = clock64();
@@ -175,8 +180,6 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
     long long ta = clock64();
 #endif
     int active = 0;
-    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-    __syncthreads();
 #pragma unroll 1
     for (int cstep = 0; cstep < 7; ++cstep) {
 #ifndef IQ_CUT_ORDER_NATURAL
@@ -188,51 +191,46 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
       const int colour = cstep;
 #endif
       const unsigned short* cl = clist + colour * items;
-      const int wq = cstep & 1;
-      // pass 1: compact the voxels of this colour that hold excess (dense warps in pass 2)
-      for (int w0 = 0; w0 < items; w0 += kCutThreads) {
-        const int w = w0 + tid;
-        int i = 0xffff;
-        if (w < items) i = cl[w];
-        const bool act = (i != 0xffff) && e[i] > 0.0 && h[i] < HMAX;
-        const unsigned bal = __ballot_sync(0xffffffffu, act);
-        if (bal) {
-          int base = 0;
-          if ((tid & 31) == 0) base = atomicAdd(&s_cnt[wq], __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (act) fr0[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned short)i;
-        }
-      }
-      __syncthreads();
-      const int nact = s_cnt[wq];
-      if (tid == 0) s_cnt[wq ^ 1] = 0;
-      // pass 2: discharge (push along every admissible arc, relabel if excess is left)
-      for (int j = tid; j < nact; j += kCutThreads) {
-        const int i = fr0[j];
+      // Every thread owns the voxels cl[tid], cl[tid + T], ... of this colour and discharges those that hold excess:
+      // push along every admissible arc, relabel if excess is left.  No voxel of this colour shares a neighbour with
+      // another one, so everything a discharge reads (own arcs, neighbour heights, reverse arcs, neighbour excesses)
+      // is private to it during the phase: its 12 residuals / neighbour heights are loaded up front and the push logic
+      // runs in registers (the first version interleaved loads and stores per direction and spent the phase in
+      // shared-memory latency).
+      for (int w = tid; w < items; w += kCutThreads) {
+        const int i = cl[w];
+        if (i == 0xffff) continue;
         double ex = e[i];
         int hi = h[i];
+        if (!(ex > 0.0) || hi >= HMAX) continue;
         const unsigned tp = topo[i];
-        int mh = HMAX;  // lowest neighbour over the arcs that still have residual capacity after the pushes
+        double rc[6];
+        int hv[6];
 #pragma unroll
         for (int dir = 0; dir < 6; ++dir) {
           const bool inner = (tp >> dir) & 1u;
           const bool sink = (dir == 4) && (tp & kToSink);
-          if (!inner && !sink) continue;
-          double rc = r[dir * nfree + i];
-          if (!(rc > 0.0)) continue;
-          const int v = i + off[dir];
-          const int hv = sink ? 0 : h[v];
-          if (ex > 0.0 && hi == hv + 1) {
-            const double d = fmin(ex, rc);
-            rc = __dsub_rn(rc, d);
+          rc[dir] = (inner || sink) ? r[dir * nfree + i] : 0.0;
+          hv[dir] = sink ? 0 : (inner ? h[i + off[dir]] : HMAX);
+        }
+        int mh = HMAX;  // lowest neighbour over the arcs that still have residual capacity after the pushes
+#pragma unroll
+        for (int dir = 0; dir < 6; ++dir) {
+          double rcd = rc[dir];
+          if (!(rcd > 0.0)) continue;
+          if (ex > 0.0 && hi == hv[dir] + 1) {
+            const double d = fmin(ex, rcd);
+            rcd = __dsub_rn(rcd, d);
             ex = __dsub_rn(ex, d);
-            r[dir * nfree + i] = rc;
-            if (!sink) {
-              r[(dir ^ 1) * nfree + v] = __dadd_rn(r[(dir ^ 1) * nfree + v], d);
+            r[dir * nfree + i] = rcd;
+            if (!((dir == 4) && (tp & kToSink))) {
+              const int v = i + off[dir];
+              r[(dir ^ 1) * nfree + v] = __dadd_rn(r[(dir ^ 1) * nfree + v], d);  // only the few admissible arcs pay these
               e[v] = __dadd_rn(e[v], d);
+              active = 1;  // v sits one level below: it can push on
             }
           }
-          if (rc > 0.0) mh = min(mh, hv);
+          if (rcd > 0.0) mh = min(mh, hv[dir]);
         }
         e[i] = ex;
         if (ex > 0.0) {
@@ -246,9 +244,7 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
 #ifdef IQ_CUT_PROFILE
     long long tb = clock64(); t_push += tb - ta;
 #endif
-    // excess may also sit on voxels that received it after their own colour was processed
-    for (int i = tid; i < nfree && !active; i += kCutThreads)
-      if (e[i] > 0.0 && h[i] < HMAX) active = 1;
+    // (a voxel that received excess after its own colour was processed was flagged by the pusher)
     const int any = __syncthreads_or(active);
 #ifdef IQ_CUT_PROFILE
     long long tc = clock64(); t_rel += tc - tb;

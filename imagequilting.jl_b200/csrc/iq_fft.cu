@@ -311,6 +311,8 @@ struct StridedArgs {
   long long mul_sb, mul_se;
   const float2* tw;
   float scale;                         // applied on store
+  long long out_sa;                    // 0: lines are 1 apart in the output (default); else stride between lines and the
+                                       // store loop runs element-fastest (transposed output for the fused z/y kernel)
 };
 template <int LOG2N, int MODE>
 __global__ void __launch_bounds__(kThreads) k_fft_strided(const StridedArgs A) {
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_strided(const StridedArgs A) {
   const int p0 = (MODE == 1) ? 0 : blockIdx.z, p1 = (MODE == 1) ? A.batch : blockIdx.z + 1;
   for (int pr = p0; pr < p1; ++pr) {
     const float2* in = A.in + (long long)pr * A.in_batch + (long long)b * A.in_sb + a0;
-    float2* out = A.out + (long long)pr * A.out_batch + (long long)b * A.out_sb + a0;
+    float2* out = A.out + (long long)pr * A.out_batch + (long long)b * A.out_sb + (long long)a0 * (A.out_sa ? A.out_sa : 1);
     __syncthreads();  // previous pair fully stored / twiddles + spectrum visible
     if (A.nin < N) zero_lines<LOG2N>(b0, LPB);
     __syncthreads();
@@ -350,13 +352,23 @@ __global__ void __launch_bounds__(kThreads) k_fft_strided(const StridedArgs A) {
       float2* other = (res == b0) ? b1 : b0;
       res = fft_lines<LOG2N, true, true>(res, other, tw, spec, LPB);
     }
-    for (int i = threadIdx.x; i < LPB * A.nout; i += kThreads) {
-      const int al = i % LPB, e = i / LPB;
-      if (al < nl) {
+    if (A.out_sa) {
+      for (int i = threadIdx.x; i < nl * A.nout; i += kThreads) {
+        const int al = i / A.nout, e = i - al * A.nout;  // element fastest: one contiguous run per line
         float2 v = res[al * LS + PI(e)];
         v.x *= A.scale;
         v.y *= A.scale;
-        out[al + (long long)e * A.out_se] = v;
+        out[(long long)al * A.out_sa + (long long)e * A.out_se] = v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < LPB * A.nout; i += kThreads) {
+        const int al = i % LPB, e = i / LPB;
+        if (al < nl) {
+          float2 v = res[al * LS + PI(e)];
+          v.x *= A.scale;
+          v.y *= A.scale;
+          out[al + (long long)e * A.out_se] = v;
+        }
       }
     }
   }
@@ -423,9 +435,91 @@ __global__ void __launch_bounds__(256) k_fft_zdirect(const ZDirectArgs A) {
   }
 }
 
+// ---- pass B'': direct z correlation FUSED with the inverse y transform --------------------------------------
+// One CTA per (template pair, kx): thread ky keeps the sliding window of its (kx, ky) column in registers exactly as
+// k_fft_zdirect does, but 16 consecutive output planes go straight into 16 shared-memory lines (ky along the line),
+// are inverse-transformed along y in place and only the valid rows leave the SM.  The (nzo x Ny x Nx) intermediate
+// of the separate kernels (44.6 MB per pair on config 5, written once and read once) never exists.  Needs ky on
+// the fast axis: transposed image spectrum sxy_t[kx][z][ky], transposed template spectrum [pair][kx][q][ky]
+// (k_fft_strided's element-fastest store) and a transposed result [pair][kx][z][y] (read by k_fft_x_final<.,true>).
+struct ZYArgs {
+  const float2* sxy_t;   // [Nx][nz][Ny]
+  const float2* tmpl_t;  // [npair][Nx][tz][Ny]
+  float2* out_t;         // [npair][Nx][nzo][nyo]
+  long long tmpl_batch, out_batch;
+  int nz, tz, nzo, nyo;
+  const float2* tw;      // twiddles of the y transform
+};
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads, 2) k_fft_zy(const ZYArgs A) {
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N), W = 16;
+  static_assert(N == kThreads && LPB == W && inplace_ok(LOG2N), "one thread per ky, 16 planes per transform batch");
+  extern __shared__ __align__(16) float2 sm[];
+  float2* buf = sm;
+  float2* tw = sm + LPB * LS;
+  const int pr = blockIdx.x, kx = blockIdx.y, ky = threadIdx.x;
+  load_twiddles<LOG2N>(tw, A.tw);
+  const float2* __restrict__ S = A.sxy_t + (long long)kx * A.nz * N + ky;
+  const float2* __restrict__ T = A.tmpl_t + (long long)pr * A.tmpl_batch + (long long)kx * A.tz * N + ky;
+  float2* __restrict__ O = A.out_t + (long long)pr * A.out_batch + (long long)kx * A.nzo * A.nyo;
+  const float2 zero = make_float2(0.f, 0.f);
+  float2 t[W], s[W];
+#pragma unroll
+  for (int q = 0; q < W; ++q) t[q] = q < A.tz ? T[q * N] : zero;
+#pragma unroll
+  for (int j = 0; j < W - 1; ++j) s[j] = j < A.nz ? S[j * N] : zero;
+  s[W - 1] = zero;
+  const float2* __restrict__ sp = S + (W - 1) * N;
+  const int pky = PI(ky);
+  __syncthreads();  // twiddles
+  for (int z0 = 0; z0 < A.nzo; z0 += W) {
+    float2 nxt[W];
+    const int navail = A.nz - (z0 + W - 1);
+#pragma unroll
+    for (int m = 0; m < W; ++m) {
+      nxt[m] = m < navail ? *sp : zero;
+      sp += N;
+    }
+#pragma unroll
+    for (int m = 0; m < W; ++m) {
+      s[(m + W - 1) % W] = nxt[m];
+      float ax = 0.f, ay = 0.f;
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        const float2 sv = s[(m + q) % W], tv = t[q];
+        ax = fmaf(sv.x, tv.x, ax);
+        ax = fmaf(-sv.y, tv.y, ax);
+        ay = fmaf(sv.x, tv.y, ay);
+        ay = fmaf(sv.y, tv.x, ay);
+      }
+      buf[m * LS + pky] = make_float2(ax, ay);
+    }
+    __syncthreads();
+    const int nl = min(W, A.nzo - z0);
+    const float2* res = fft_lines<LOG2N, true, false>(buf, buf, tw, nullptr, nl);
+    if (ky < A.nyo) {
+      float2* op = O + (long long)z0 * A.nyo + ky;
+      for (int line = 0; line < nl; ++line) op[(long long)line * A.nyo] = res[line * LS + pky];
+    }
+    __syncthreads();  // the lines are refilled by the next batch
+  }
+}
+
+// out[x][z][y] = in[z][y][x] (set-up only: transposed image spectrum)
+__global__ void __launch_bounds__(256) k_transpose_xzy(const float2* __restrict__ in, float2* __restrict__ out, int nx, int ny,
+                                                       int nz) {
+  __shared__ float2 tile[16][17];
+  const int z = blockIdx.z, x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (x0 + tx < nx && y0 + ty < ny) tile[ty][tx] = in[((long long)z * ny + y0 + ty) * nx + x0 + tx];
+  __syncthreads();
+  if (x0 + ty < nx && y0 + tx < ny) out[((long long)(x0 + ty) * nz + z) * ny + y0 + tx] = tile[tx][ty];
+}
+
 // ---- pass C: last inverse pass along x + distance epilogue --------------------------------------------
 struct FinalArgs {
-  const float2* in;     // [npair][nlines][N]
+  const float2* in;     // [npair][nlines][N], or (transposed) [npair][N][nlines]
+  long long in_batch;   // transposed input: float2 per pair
   int nlines, nxo;      // nlines = nyo*nzo; output position p = line*nxo + x
   long long npos;
   int R;
@@ -492,7 +586,7 @@ __device__ __forceinline__ void final_epilogue(const FinalArgs& A, const float2*
   }
 }
 
-template <int LOG2N>
+template <int LOG2N, bool TIN>
 __global__ void __launch_bounds__(kThreads, 4) k_fft_x_final(const FinalArgs A) {
   constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
   extern __shared__ __align__(16) float2 sm[];
@@ -504,10 +598,19 @@ __global__ void __launch_bounds__(kThreads, 4) k_fft_x_final(const FinalArgs A) 
   const int nl = min(LPB, A.nlines - l0);
   load_twiddles<LOG2N>(tw, A.tw);
   if (threadIdx.x < 2) { s_min[threadIdx.x] = 0x7f800000u; s_max[threadIdx.x] = 0u; }
-  const float2* in = A.in + ((long long)pr * A.nlines + l0) * N;
-  for (int i = threadIdx.x; i < nl * N; i += kThreads) {
-    const int line = i >> LOG2N, e = i & (N - 1);
-    b0[line * LS + PI(e)] = in[(long long)line * N + e];
+  if (TIN) {
+    // transposed input [kx][line]: LPB consecutive lines of one kx are contiguous (128-byte runs for LPB = 16)
+    const float2* in = A.in + (long long)pr * A.in_batch + l0;
+    for (int i = threadIdx.x; i < LPB * N; i += kThreads) {
+      const int al = i % LPB, e = i / LPB;
+      if (al < nl) b0[al * LS + PI(e)] = in[(long long)e * A.nlines + al];
+    }
+  } else {
+    const float2* in = A.in + ((long long)pr * A.nlines + l0) * N;
+    for (int i = threadIdx.x; i < nl * N; i += kThreads) {
+      const int line = i >> LOG2N, e = i & (N - 1);
+      b0[line * LS + PI(e)] = in[(long long)line * N + e];
+    }
   }
   __syncthreads();
   const float2* res = fft_lines<LOG2N, true, false>(b0, b1, tw, nullptr, nl);
@@ -612,6 +715,8 @@ struct Plan {
   std::map<int, float2*> spectrum;   // full 3-D (2-D problems: 2-D) spectrum, scaled by 1/N
   std::map<int, float2*> sxy;        // 3-D problems with the direct z pass: (x, y) spectrum of every plane, scaled by 1/(Nx Ny)
   bool zdirect = false;              // direct correlation along z instead of the fused z transforms (tz <= 24)
+  bool zyfused = false;              // ... fused with the inverse y transform (k_fft_zy: Ny == 256, tz <= 16)
+  std::map<int, float2*> sxy_t;      // transposed (x, y) spectrum [Nx][nz][Ny] of the fused kernel
   size_t workspace = 0;
 };
 
@@ -695,14 +800,19 @@ static cudaError_t launch_final_tma(const FinalArgs& a, int npair, cudaStream_t 
 }
 
 static cudaError_t launch_final(const FinalArgs& a, int log2n, int npair, cudaStream_t s) {
-  if (tma_enabled() && inplace_ok(log2n) && log2n >= 4) {
+  if (tma_enabled() && inplace_ok(log2n) && log2n >= 4 && a.in_batch == 0) {
     FFT_DISPATCH(log2n, { return launch_final_tma<L>(a, npair, s); });
   }
   const size_t sm = smem_bytes(log2n);
   const int LPB = lines_per_block(log2n);
   dim3 grid((a.nlines + LPB - 1) / LPB, npair);
-  FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_x_final<L>, sm); if (e != cudaSuccess) return e;
-                        k_fft_x_final<L><<<grid, kThreads, sm, s>>>(a); });
+  if (a.in_batch > 0) {
+    FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_x_final<L, true>, sm); if (e != cudaSuccess) return e;
+                          k_fft_x_final<L, true><<<grid, kThreads, sm, s>>>(a); });
+  } else {
+    FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_x_final<L, false>, sm); if (e != cudaSuccess) return e;
+                          k_fft_x_final<L, false><<<grid, kThreads, sm, s>>>(a); });
+  }
   return cudaGetLastError();
 }
 
@@ -739,6 +849,14 @@ static bool zdirect_enabled() {
   return !(ev && ev[0] == '0');
 }
 
+static bool zyfused_enabled() {
+  // Experimental (IQB200_FFT_ZYFUSED=1).  Bit-identical results and 42 % less traffic, but 5 % SLOWER on config 5
+  // (FFT passes 1.155 s vs 1.099 s per 512 steps): both halves are bound by instruction issue, and the fused kernel
+  // (128 registers, 2 CTAs per SM) overlaps its barrier phases worse than two separate kernels do.
+  const char* ev = std::getenv("IQB200_FFT_ZYFUSED");
+  return ev && ev[0] == '1';
+}
+
 cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int tz, int max_templates, cudaStream_t s) {
   *out = nullptr;
   if (ny < 2 || nx < 2) return cudaErrorInvalidValue;
@@ -751,6 +869,7 @@ cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int 
   if (p->lx > 10 || p->ly > 10 || p->lz > 10) { delete p; return cudaErrorInvalidValue; }
   p->max_pairs = (max_templates + 1) / 2;
   p->zdirect = p->lz > 0 && tz >= 2 && tz <= 24 && zdirect_enabled();
+  p->zyfused = p->zdirect && tz <= 16 && p->Ny == kThreads && lines_per_block(p->ly) == 16 && zyfused_enabled();
   cudaError_t e;
   if ((e = make_twiddles(&p->twx, p->Nx, s)) != cudaSuccess) { plan_destroy(p); return e; }
   if ((e = make_twiddles(&p->twy, p->Ny, s)) != cudaSuccess) { plan_destroy(p); return e; }
@@ -767,7 +886,7 @@ cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int 
   if ((e = iq::dmalloc((void**)&p->w4, mp * p->w4_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
   if (p->lz > 0) {
     if ((e = iq::dmalloc((void**)&p->w2, mp * p->w2_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
-    if ((e = iq::dmalloc((void**)&p->w3, mp * p->w3_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
+    if (!p->zyfused && (e = iq::dmalloc((void**)&p->w3, mp * p->w3_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
   }
   p->workspace = mp * (p->w1_stride + p->w2_stride + p->w3_stride + p->w4_stride) * sizeof(float2);
   *out = p;
@@ -780,6 +899,7 @@ void plan_destroy(Plan* p) {
   cudaFree(p->w1); cudaFree(p->w2); cudaFree(p->w3); cudaFree(p->w4);
   for (auto& kv : p->spectrum) cudaFree(kv.second);
   for (auto& kv : p->sxy) cudaFree(kv.second);
+  for (auto& kv : p->sxy_t) cudaFree(kv.second);
   delete p;
 }
 
@@ -816,6 +936,14 @@ cudaError_t plan_set_image(Plan* p, int id, const float* d_img, cudaStream_t s) 
       cudaFree(spec);
       a.scale = (float)(1.0 / ((double)Nx * (double)Ny));
       if ((e = launch_strided<0>(a, p->ly, 1, s)) != cudaSuccess) return e;
+      if (p->zyfused) {
+        float2* tt = nullptr;
+        if ((e = iq::dmalloc((void**)&tt, (size_t)p->nz * Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
+        dim3 tg((unsigned)((Nx + 15) / 16), (unsigned)((Ny + 15) / 16), (unsigned)p->nz);
+        k_transpose_xzy<<<tg, 256, 0, s>>>(t2, tt, (int)Nx, (int)Ny, p->nz);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        p->sxy_t[id] = tt;
+      }
       if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
       cudaFree(t1);
       p->sxy[id] = t2;
@@ -870,7 +998,26 @@ cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogu
     a.in_sb = (long long)p->ty * Nx; a.in_se = Nx; a.in_batch = p->w1_stride;
     a.out_sb = Ny * Nx; a.out_se = Nx; a.out_batch = p->w2_stride;
     a.nin = p->ty; a.flip = 1; a.nout = (int)Ny; a.na = (int)Nx; a.nb = p->tz; a.tw = p->twy; a.scale = 1.f;
+    if (p->zyfused) {  // transposed template spectrum [pair][kx][qz][ky]
+      a.out_sa = (long long)p->tz * Ny; a.out_sb = Ny; a.out_se = 1;
+    }
     if ((e = launch_strided<0>(a, p->ly, npair, s)) != cudaSuccess) return e;
+    if (p->zyfused) {
+      auto itt = p->sxy_t.find(id);
+      if (itt == p->sxy_t.end()) return cudaErrorInvalidValue;
+      ZYArgs z{};
+      z.sxy_t = itt->second; z.tmpl_t = p->w2; z.out_t = p->w4;
+      z.tmpl_batch = p->w2_stride; z.out_batch = p->w4_stride;
+      z.nz = p->nz; z.tz = p->tz; z.nzo = p->nzo; z.nyo = p->nyo; z.tw = p->twy;
+      const size_t zsm = (size_t)(lines_per_block(8) * line_stride(8) + 256) * sizeof(float2);
+      if ((e = set_smem(k_fft_zy<8>, zsm)) != cudaSuccess) return e;
+      k_fft_zy<8><<<dim3(npair, (unsigned)Nx), kThreads, zsm, s>>>(z);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      FinalArgs fz{p->w4, p->w4_stride, p->nyo * p->nzo, p->nxo, p->npos, R, ep, p->twx};
+      if ((e = launch_final(fz, p->lx, npair, s)) != cudaSuccess) return e;
+      if (launches) *launches = nl + 3;
+      return cudaSuccess;
+    }
     if (p->zdirect) {
       ZDirectArgs z{};
       z.sxy = spec; z.tmpl = p->w2; z.out = p->w3;
@@ -894,7 +1041,7 @@ cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogu
     if ((e = launch_strided<2>(c, p->ly, npair, s)) != cudaSuccess) return e;
     nl += 3;
   }
-  FinalArgs fa{p->w4, p->nyo * p->nzo, p->nxo, p->npos, R, ep, p->twx};
+  FinalArgs fa{p->w4, 0, p->nyo * p->nzo, p->nxo, p->npos, R, ep, p->twx};
   if ((e = launch_final(fa, p->lx, npair, s)) != cudaSuccess) return e;
   ++nl;
   if (launches) *launches = nl;
@@ -913,6 +1060,7 @@ double correlate_bytes(const Plan* p, int R) {
     b += npair * c * (p->tz * p->ty * Nx + p->tz * Ny * Nx);                               // forward y
     b += npair * c * (p->tz * Ny * Nx + p->nzo * Ny * Nx) + c * (p->zdirect ? p->nz : Nz) * Ny * Nx;  // z pass (+ spectrum once)
     b += npair * c * (p->nzo * Ny * Nx + (double)p->nzo * p->nyo * Nx);                    // inverse y
+    if (p->zyfused) b -= 2.0 * npair * c * p->nzo * Ny * Nx;                               // fused: the z-pass output never leaves the SM
   }
   b += npair * c * (double)p->nzo * p->nyo * Nx + (double)R * 4.0 * p->npos + 4.0 * p->npos;  // final + maps + A2
   return b;

@@ -528,14 +528,24 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
     CK(cudaGetLastError());
     // task records depend on the slab set only: cached with the mask
     if (!e->d_cut_tasks || e->cut_ntask != ntask) {
+      // Launch order = longest first: the slabs with the most inner voxels of ALL realizations lead, the cheap ones
+      // (e.g. the one-layer z slabs) come last and fill the second wave (one CTA per SM: 192 cuts on 148 SMs), so the
+      // tail of the launch is made of short cuts.  Only the order of the records changes, not where a task's data is.
+      std::vector<int> sorder(nslab);
+      for (int i = 0; i < nslab; ++i) sorder[i] = i;
+      std::stable_sort(sorder.begin(), sorder.end(), [&](int a, int b) {
+        return (long long)(S.s[a].L - 2) * S.s[a].n0 * S.s[a].n1 > (long long)(S.s[b].L - 2) * S.s[b].n0 * S.s[b].n1;
+      });
       std::vector<iq::CutTask> recs((size_t)ntask);
-      for (int k = 0; k < ntask; ++k) {
+      for (int b = 0; b < ntask; ++b) {
+        const int k = (b % R) * nslab + sorder[b / R];  // task whose record sits at launch position b
         const SlabDev& o = S.s[k % nslab];
-        recs[k].A = s->d_cutA + (size_t)k * s->maxslab;
-        recs[k].B = s->d_cutB + (size_t)k * s->maxslab;
-        recs[k].keep = s->d_keep + (size_t)k * s->maxslab;
-        recs[k].n0 = o.n0; recs[k].n1 = o.n1; recs[k].L = o.L;
-        recs[k].iters = s->d_cut_iters + k;
+        iq::CutTask& rec = recs[b];
+        rec.A = s->d_cutA + (size_t)k * s->maxslab;
+        rec.B = s->d_cutB + (size_t)k * s->maxslab;
+        rec.keep = s->d_keep + (size_t)k * s->maxslab;
+        rec.n0 = o.n0; rec.n1 = o.n1; rec.L = o.L;
+        rec.iters = s->d_cut_iters + k;
       }
       CK(cudaStreamSynchronize(c->stream));
       cudaFree(e->d_cut_tasks);

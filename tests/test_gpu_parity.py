@@ -365,3 +365,45 @@ def test_iqsim_device_cut_equals_host_cut():
     b = iqb200.iqsim(ti, (16, 12, 8), nreal=2, rng=np.random.default_rng(5), cut="device", overlap=(0.25, 0.25, 0.25))
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("env", [{"IQB200_FFT_ZYFUSED": "1"}, {"IQB200_FFT_TMA": "1"}, {"IQB200_FFT_ZDIRECT": "0"}])
+def test_experimental_fft_variants_give_the_same_maps(env):
+    """The opt-in FFT variants (fused z/y kernel, TMA double-buffered last pass, z transforms instead of the direct z
+    pass) are alternative schedules of the same arithmetic: their distance maps must match the default path within
+    FP32 rounding of the different summation orders, and the oracle within the usual tolerance."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, json, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from iqb200 import api, synth\n"
+        "ti = synth.gaussian_field((250, 256, 40), (8, 8, 4), 3)\n"
+        "tile = (24, 20, 12)\n"
+        "m = np.zeros(tile, bool); m[:4] = True; m[:, :4] = True; m[:, :, :2] = True\n"
+        "r = np.random.default_rng(0)\n"
+        "sims = [ti[5:29, 7:27, 3:15] + 0.1 * r.standard_normal(tile).astype(np.float32) for _ in range(3)]\n"
+        "with api.SearchContext(ti, tile, max_batch=3) as ctx:\n"
+        "    ctx.set_option('fft', 1)\n"
+        "    res = ctx.search(m, [dict(simdev=s) for s in sims], tol=0.1, u=[0.3, 0.6, 0.9])\n"
+        "    d = ctx.distance(-1, m, sims[0])\n"
+        "np.save(sys.argv[1], d)\n"
+        "print(json.dumps([[int(x) for x in q['idx']] for q in res]))\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for extra in ({}, env):
+        e = dict(os.environ)
+        for k in ("IQB200_FFT_ZYFUSED", "IQB200_FFT_TMA", "IQB200_FFT_ZDIRECT"):
+            e.pop(k, None)
+        e.update(extra)
+        path = os.path.join("/tmp", "iq_variant_%d_%s.npy" % (os.getpid(), "x" if extra else "d"))
+        p = subprocess.run([sys.executable, "-c", code, path], env=e, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append((np.load(path), json.loads(p.stdout.strip().splitlines()[-1])))
+        os.unlink(path)
+    (d0, c0), (d1, c1) = outs
+    scale = float(np.abs(d0).max())
+    assert np.allclose(d0, d1, rtol=1e-4, atol=1e-6 * scale)
+    for a, b in zip(c0, c1):  # candidate sets identical except for a tie at the threshold inside that tolerance
+        assert len(set(a) ^ set(b)) <= 1
