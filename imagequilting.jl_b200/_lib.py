@@ -44,7 +44,8 @@ class IqCutTask(C.Structure):
 
 class IqSimDesc(C.Structure):
     _fields_ = [("pad_size", C.c_int64 * 3), ("ovl_size", C.c_int64 * 3), ("nreal", C.c_int32), ("ti64", c_double_p),
-                ("u", c_double_p), ("npath", C.c_int64), ("tol", C.c_double), ("debug", C.c_int32)]
+                ("u", c_double_p), ("npath", C.c_int64), ("tol", C.c_double), ("debug", C.c_int32),
+                ("aux", C.POINTER(c_float_p))]
 
 
 class IqSimSlab(C.Structure):
@@ -70,7 +71,7 @@ class IqhStats(C.Structure):
                 ("dist_launches", C.c_int64), ("fft_searches", C.c_int64), ("direct_searches", C.c_int64),
                 ("fft_bytes", C.c_double), ("fft_ms", C.c_double), ("resident", C.c_int32),
                 ("resident_status", C.c_int32), ("device_ms", C.c_double), ("select_ms", C.c_double),
-                ("cut_device_ms", C.c_double), ("fetch_ms", C.c_double)]
+                ("cut_device_ms", C.c_double), ("fetch_ms", C.c_double), ("max_candidates", C.c_int64)]
 
 
 # every symbol include/*.h declares: name -> (restype, argtypes)
@@ -94,6 +95,7 @@ SYMBOLS = {
     "iq_cut_batch": (C.c_int32, [C.c_void_p, C.POINTER(IqCutTask), C.c_int32, c_i32_p]),
     "iq_sim_begin": (C.c_int32, [C.c_void_p, C.POINTER(IqSimDesc)]),
     "iq_sim_step": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32]),
+    "iq_sim_step_picked": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_i64_p]),
     "iq_sim_sync": (C.c_int32, [C.c_void_p, c_i64_p, c_i32_p]),
     "iq_sim_fetch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_i64_p, C.c_void_p]),
     "iq_sim_fetch_all": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, C.POINTER(C.c_void_p), C.c_int32]),

@@ -871,9 +871,14 @@ int do_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int ntile
   if (rc) return rc;
   if ((int)c->res.size() < ntile) c->res.resize(ntile);
   const int64_t l0 = c->launches;
-  c->dist_ev_used = 0;
-  c->last_fft_bytes = 0.0;
-  c->last_fft_searches = c->last_direct_searches = 0;
+  // a search between the steps of an open resident simulation joins the simulation's accumulated timing (its
+  // distance events are summed by iq_sim_sync) instead of resetting it
+  const bool in_sim = c->sim != nullptr;
+  if (!in_sim) {
+    c->dist_ev_used = 0;
+    c->last_fft_bytes = 0.0;
+    c->last_fft_searches = c->last_direct_searches = 0;
+  }
   CK(cudaEventRecord(c->ev0, c->stream));
   for (int base = 0; base < ntile; base += c->max_batch) {
     const int R = std::min(c->max_batch, ntile - base);
@@ -886,6 +891,7 @@ int do_search(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int ntile
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->last_ms = ms;
   c->last_launches = c->launches - l0;
+  if (in_sim) return IQ_OK;
   return collect_dist_times(c);
 }
 

@@ -136,7 +136,7 @@ struct Group {
   std::atomic<int> cuts_left{0}, pastes_left{0};
   clk::time_point cut_t0;
   double search_ms = 0, search_dev_ms = 0, cut_ms = 0, dist_ms = 0, fft_bytes = 0, fft_ms = 0;
-  int64_t launches = 0, dist_launches = 0, ncand = 0, nfft = 0, ndirect = 0;
+  int64_t launches = 0, dist_launches = 0, ncand = 0, nfft = 0, ndirect = 0, maxcand = 0;
 };
 
 }  // namespace
@@ -189,7 +189,8 @@ void tile_slabs(const Geo& G, const std::vector<uint8_t>& pasted, int64_t ind, s
 int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats,
                  int* status) {
   *status = 0;
-  if (D->nsoft > 0 || D->hard_has) return IQ_ERR_STATE;
+  if (D->hard_has) return IQ_ERR_STATE;  // hard data: relaxation with the sparse hard distance, host-staged only
+  const int S = D->nsoft;
   if (D->pipeline == 0) {
     // Integer-valued (categorical) images make the cut capacities of graphcut.jl:52 degenerate (division by eps next
     // to O(1) terms): equal-cost cuts abound and which one comes out depends on the max-flow algorithm's rounding.
@@ -223,7 +224,8 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     for (int i = 0; i < 3; ++i) { cd.ti_size[i] = G.n[i]; cd.tile_size[i] = G.t[i]; }
     cd.ti = D->ti_f32;
     cd.disabled = D->disabled;
-    cd.nsoft = 0;
+    cd.nsoft = S;
+    cd.auxti = D->auxti;
     cd.device = D->device;
     cd.max_batch = g.R;
     rc = iq_ctx_create(&g.ctx, &cd);
@@ -237,6 +239,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     sd.npath = D->npath;
     sd.tol = D->tol;
     sd.debug = D->debug;
+    sd.aux = S ? D->aux : nullptr;
     rc = iq_sim_begin(g.ctx, &sd);
   }
   if (rc != IQ_OK) { destroy_all(); return rc; }
@@ -245,6 +248,9 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   std::vector<uint8_t> pasted((size_t)G.ntile_total, 0), mask((size_t)G.tilevol);
   std::vector<Slab> slabs;
   std::vector<iq_sim_slab> sl;
+  std::vector<float> zero_tile((size_t)G.tilevol, 0.f);
+  std::vector<std::vector<float>> soft_tile((size_t)S, std::vector<float>((size_t)G.tilevol));
+  std::vector<const float*> soft_ptr((size_t)S, nullptr);
   int64_t launches = 0;
   const auto t_enq = clk::now();
   for (int64_t step = 0; step < D->npath && rc == IQ_OK; ++step) {
@@ -259,8 +265,40 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
       for (int i = 0; i < 3; ++i) { sl[k].lo[i] = slabs[k].lo[i]; sl[k].sz[i] = slabs[k].sz[i]; }
     }
     const int64_t st64[3] = {start[0], start[1], start[2]};
+    const bool host_pick = S > 0 && slabs.empty();
+    if (host_pick) {
+      // Soft data and nothing pasted around the tile: the candidate set is a tenth of all patterns (relaxation.jl:11,20),
+      // far above the device tau model.  One search (the tile is the same for every realization), the sampling walk
+      // per realization on the host, and the picks handed to the device (iq_sim_step_picked).
+      std::fill(zero_tile.begin(), zero_tile.end(), 0.f);
+      for (int s = 0; s < S; ++s) {
+        for (int z = 0; z < G.t[2]; ++z)
+          for (int y = 0; y < G.t[1]; ++y) {
+            const long long gi = ((long long)(start[2] + z) * G.pad[1] + (start[1] + y)) * G.pad[0] + start[0];
+            std::memcpy(&soft_tile[s][((size_t)z * G.t[1] + y) * G.t[0]], D->aux[s] + gi, sizeof(float) * G.t[0]);
+          }
+        soft_ptr[s] = soft_tile[s].data();
+      }
+    }
     for (auto& g : groups) {
-      rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size());
+      if (host_pick) {
+        iq_tile tile{};
+        tile.simdev = zero_tile.data();
+        tile.softdev = soft_ptr.data();
+        iq_result res{};
+        rc = iq_search(g.ctx, mask.data(), &tile, 1, D->tol, &res);
+        if (rc != IQ_OK) break;
+        if (res.count <= 0) { rc = IQ_ERR_STATE; break; }
+        std::vector<int64_t> pk((size_t)g.R);
+        for (int r = 0; r < g.R && rc == IQ_OK; ++r) {
+          int64_t pos = 0;
+          rc = iq_sample(res.prob, res.count, D->u[(size_t)(g.r0 + r) * D->npath + step], &pos);
+          pk[(size_t)r] = res.idx[pos];
+        }
+        if (rc == IQ_OK) rc = iq_sim_step_picked(g.ctx, step, st64, pk.data());
+      } else {
+        rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size());
+      }
       if (rc != IQ_OK) break;
       double dms = 0;
       int64_t nl = 0;
@@ -511,6 +549,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     }
     for (int r = 0; r < g.R; ++r) {
       g.ncand += g.results[r].count;
+      g.maxcand = std::max<int64_t>(g.maxcand, g.results[r].count);
       g.picked[r] = g.results[r].picked;
       if (out_picks) out_picks[(size_t)(g.r0 + r) * D->npath + step] = g.picked[r];
       if (g.picked[r] < 0) return IQ_ERR_STATE;
@@ -708,6 +747,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     stats->fft_searches = stats->direct_searches = 0;
     stats->fft_bytes = stats->fft_ms = 0;
     for (auto& g : groups) {
+      stats->max_candidates = std::max(stats->max_candidates, g.maxcand);
       stats->fft_searches += g.nfft; stats->direct_searches += g.ndirect;
       stats->fft_bytes += g.fft_bytes; stats->fft_ms += g.fft_ms;
     }

@@ -6,7 +6,7 @@
 
 namespace iq {
 
-constexpr int kTauMax = 16384; // largest candidate set ranked on the device (shared-memory bitonic sort)
+constexpr int kTauMax = 32768; // largest candidate set ranked on the device (shared-memory bitonic sort)
 constexpr int kT = 8;           // outputs per thread along x (register tile)
 constexpr int kWarpX = 32;      // outputs per warp along x  (4 lanes x 8)
 constexpr int kWarpY = 8;       // outputs per warp along y  (8 lanes)
@@ -84,6 +84,7 @@ struct PickJob {
   float* cand_val;               // [nsrc][cap]
   long long cap;
   const unsigned* chunkmin;      // mode 0, optional: float bits of the minimum of every chunk of src[0] (k_pick_chunks)
+  const int* pending;            // optional: the count / write kernels skip the job unless *pending != 0
 };
 
 // One boundary cut for the device kernel (iq_cutgpu.cu): slabs laid out with the cut dimension slowest.

@@ -897,6 +897,7 @@ __device__ __forceinline__ bool pick_pred(const PickJob& J, long long p, double 
 
 __global__ void __launch_bounds__(256) k_pick_count(PickJob* jobs, long long npos) {
   PickJob& J = jobs[blockIdx.y];
+  if (J.pending && *J.pending == 0) return;
   const int tid = threadIdx.x;
   const double thr = (J.mode == 0) ? (1.0 + J.tol) * (double)__uint_as_float(*J.minbits) : 0.0;
   const long long base = (long long)blockIdx.x * kPickChunk;
@@ -1134,15 +1135,21 @@ __global__ void __launch_bounds__(1024) k_tau_rank(const PickJob* jobs, unsigned
   const int s = blockIdx.x;
   const unsigned n = *J.total;
   if (s >= J.nsrc || n < 2u || n > (unsigned)kTauMax) return;
-  extern __shared__ __align__(16) unsigned long long keys[];
+  // value bits (keys) and candidate slots (payload) in separate arrays: 6 bytes per entry, 32 768 entries in 192 KB.
+  // Ties need no tie-break: equal values share a dense rank whatever their order.
+  extern __shared__ __align__(16) unsigned char tau_sm[];
+  unsigned* keys = reinterpret_cast<unsigned*>(tau_sm);
+  unsigned short* slot = reinterpret_cast<unsigned short*>(keys + kTauMax);
   __shared__ unsigned s_part[32];
   __shared__ unsigned long long s_sum;
   unsigned NP = 2;
   while (NP < n) NP <<= 1;
   const int tid = threadIdx.x;
   const float* vals = J.cand_val + (long long)s * J.cap;
-  for (unsigned i = tid; i < NP; i += 1024)
-    keys[i] = i < n ? (((unsigned long long)__float_as_uint(vals[i]) << 32) | i) : ~0ull;
+  for (unsigned i = tid; i < NP; i += 1024) {
+    keys[i] = i < n ? __float_as_uint(vals[i]) : 0xffffffffu;
+    slot[i] = (unsigned short)i;
+  }
   if (tid == 0) s_sum = 0ull;
   __syncthreads();
   for (unsigned k = 2; k <= NP; k <<= 1) {
@@ -1151,8 +1158,12 @@ __global__ void __launch_bounds__(1024) k_tau_rank(const PickJob* jobs, unsigned
         const unsigned i = 2 * t - (t & (j - 1));
         const unsigned ixj = i + j;
         const bool up = (i & k) == 0;
-        const unsigned long long a = keys[i], b = keys[ixj];
-        if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        const unsigned a = keys[i], b = keys[ixj];
+        if ((a > b) == up && a != b) {
+          keys[i] = b; keys[ixj] = a;
+          const unsigned short sa = slot[i];
+          slot[i] = slot[ixj]; slot[ixj] = sa;
+        }
       }
       __syncthreads();
     }
@@ -1161,7 +1172,7 @@ __global__ void __launch_bounds__(1024) k_tau_rank(const PickJob* jobs, unsigned
   const unsigned seg = (NP + 1023) / 1024;
   const unsigned k0 = tid * seg, k1 = min(k0 + seg, n);
   unsigned local = 0;
-  for (unsigned k = k0; k < k1; ++k) local += (k == 0 || (unsigned)(keys[k] >> 32) != (unsigned)(keys[k - 1] >> 32)) ? 1u : 0u;
+  for (unsigned k = k0; k < k1; ++k) local += (k == 0 || keys[k] != keys[k - 1]) ? 1u : 0u;
   unsigned incl = local;
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -1185,8 +1196,8 @@ __global__ void __launch_bounds__(1024) k_tau_rank(const PickJob* jobs, unsigned
   unsigned long long mysum = 0ull;
   unsigned* ro = rank_out + ((long long)blockIdx.y * maxS + s) * kTauMax;
   for (unsigned k = k0; k < k1; ++k) {
-    if (k == 0 || (unsigned)(keys[k] >> 32) != (unsigned)(keys[k - 1] >> 32)) ++r;
-    ro[(unsigned)(keys[k] & 0xffffffffull)] = r;
+    if (k == 0 || keys[k] != keys[k - 1]) ++r;
+    ro[slot[k]] = r;
     mysum += (unsigned long long)(n - r + 1u);
   }
   atomicAdd(&s_sum, mysum);
@@ -1218,7 +1229,7 @@ __global__ void __launch_bounds__(256) k_tau_prob(const PickJob* jobs, const uns
 
 cudaError_t launch_tau(const PickJob* jobs, int njobs, int maxS, unsigned* rank, unsigned long long* colsum, double* prob,
                        cudaStream_t s) {
-  const size_t smem = (size_t)kTauMax * sizeof(unsigned long long);
+  const size_t smem = (size_t)kTauMax * (sizeof(unsigned) + sizeof(unsigned short));
   cudaError_t e = cudaFuncSetAttribute(k_tau_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k_tau_rank<<<dim3(maxS, njobs), 1024, smem, s>>>(jobs, rank, colsum, maxS);

@@ -52,6 +52,15 @@ struct SimState {
   long long* d_picks = nullptr;   // [R][npath]
   long long* h_pickstage = nullptr;  // pinned [npath][R]: picks of empty-mask steps (computed on the host)
   int* d_status = nullptr;
+  // soft data (relaxation path)
+  int S = 0;
+  std::vector<float*> d_aux_pad;     // [S] padded auxiliary grids
+  float* d_soft_tmpl = nullptr;      // [tilevol] soft template of the step (the same for every realization)
+  double* d_soft_b2 = nullptr;
+  double* d_soft_plane = nullptr;    // [tz]
+  unsigned* d_soft_ticket = nullptr;
+  iq::PickJob* d_pickjobs = nullptr; // [R] selection jobs of the simulation (the context's own array serves iq_search)
+  int* d_pending = nullptr;          // [R] relaxation: realization still without candidates (next round needed)
   double* d_cutA = nullptr;
   double* d_cutB = nullptr;
   uint8_t* d_keep = nullptr;
@@ -77,13 +86,14 @@ struct SimState {
 
 // Dense masked templates (zeros outside the overlap mask) of every realization + B2 = sum of their squares in the
 // library's fixed order (b2_ordered in iq_ctx.cu): one CTA per (z plane, realization).
-__global__ void __launch_bounds__(256) k_sim_templates(const double* __restrict__ grid, long long padvol, int p0, int p1,
+template <typename GT>
+__global__ void __launch_bounds__(256) k_sim_templates(const GT* __restrict__ grid, long long padvol, int p0, int p1,
                                                        int sx, int sy, int sz, const uint8_t* __restrict__ mask, int tx,
                                                        int ty, int tz, float* __restrict__ tmpl, double* __restrict__ plane,
                                                        double* __restrict__ b2, unsigned* __restrict__ ticket) {
   const int z = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;
   const int pl = tx * ty;
-  const double* g = grid + (long long)r * padvol + ((long long)(sz + z) * p1 + sy) * p0 + sx;
+  const GT* g = grid + (long long)r * padvol + ((long long)(sz + z) * p1 + sy) * p0 + sx;
   const uint8_t* m = mask + (long long)z * pl;
   float* out = tmpl + ((long long)r * tz + z) * pl;
   double acc = 0.0;
@@ -177,6 +187,61 @@ __global__ void k_sim_sample(const iq::PickJob* __restrict__ jobs, const double*
   picks[(long long)r * npath + step] = pk;
 }
 
+// Relaxation rounds (src/relaxation.jl:7-36) of every realization on the device.  Round 0: radix-select jobs for the
+// dbsize smallest keys of the primary map and the softk = ceil(frac * npatterns) smallest of every auxiliary map, with
+// dbsize = all(D .== 0) ? npatterns : ceil(tol * npatterns) and frac = 0.1 * dbsize / npatterns; round j > 0 (only for
+// realizations whose intersection was empty): frac = min(frac + 0.1, 1), auxiliary maps re-selected -- the same FP64
+// operations as the host driver of iq_search.  The auxiliary maps are shared by all realizations, so a realization
+// whose k equals realization 0's only copies its thresholds (k_sim_copykth).  One block per realization, one thread
+// per source.
+__global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* __restrict__ pick, int maxS,
+                              const unsigned* __restrict__ maxbits, double tol, long long npatterns, long long npos,
+                              int round, int* __restrict__ pending) {
+  const int r = blockIdx.x, s = threadIdx.x;
+  if (s >= maxS) return;
+  if (round > 0 && pending[r] == 0) return;  // candidates found: its jobs stay finished
+  if (round > 0 && s == 0) return;           // primary threshold already known
+  iq::SelJob& J = jobs[(long long)r * maxS + s];
+  const iq::PickJob& P = pick[r];
+  J.k = 0; J.prefix = 0; J.mask = 0; J.kth = 0; J.pass = 0; J.active = 0; J.ticket = 0;
+  for (int i = 0; i < 256; ++i) J.hist[i] = 0;
+  if (s == 0 && round == 0) pending[r] = 1;
+  if (s >= P.nsrc) return;
+  const bool allzero = maxbits[r] == 0u, allzero0 = maxbits[0] == 0u;
+  const long long dbsize = allzero ? npatterns : (long long)ceil(__dmul_rn(tol, (double)npatterns));
+  double frac = __dmul_rn(0.1, __ddiv_rn((double)dbsize, (double)npatterns));
+  for (int j = 0; j < round; ++j) frac = fmin(__dadd_rn(frac, 0.1), 1.0);  // relaxation.jl:35, once per empty round
+  const long long softk = (long long)ceil(__dmul_rn(frac, (double)npatterns));
+  long long k = s == 0 ? dbsize : softk;
+  k = max(1ll, min(k, npos));
+  J.map = P.src[s];
+  J.k = (unsigned long long)k;
+  // shared auxiliary map and the same k as realization 0, which runs its selection in this round: copy afterwards.
+  // (k depends on the all-zero flag and the round only; pending[] is not written during rounds > 0.)
+  const bool same_as_first = s > 0 && r > 0 && allzero == allzero0 && (round == 0 || pending[0] != 0);
+  J.active = same_as_first ? 0 : 1;
+  J.ticket = same_as_first ? 0xffffffffu : 0u;  // marker read by k_sim_copykth
+}
+
+// Thresholds of the shared auxiliary maps for the realizations that did not run their own selection.
+__global__ void k_sim_copykth(iq::SelJob* __restrict__ jobs, int maxS) {
+  const int r = blockIdx.x, s = threadIdx.x;
+  if (r == 0 || s == 0 || s >= maxS) return;
+  iq::SelJob& J = jobs[(long long)r * maxS + s];
+  if (J.ticket != 0xffffffffu) return;
+  J.kth = jobs[s].kth;
+  J.ticket = 0u;
+}
+
+// After a round: a realization stays pending iff its intersection is empty; `left` counts them at the last round.
+__global__ void k_sim_relax_check(const iq::PickJob* __restrict__ pick, int R, int* __restrict__ pending, int last,
+                                  int* __restrict__ status) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R || pending[r] == 0) return;
+  if (*pick[r].total > 0u) pending[r] = 0;
+  else if (last) atomicOr(status, 4);  // still empty after the rounds run on the device
+}
+
 __global__ void k_sim_store_picks(const long long* __restrict__ picked, long long* __restrict__ picks, long long npath,
                                   long long step, int R) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,6 +325,9 @@ void sim_destroy(iq_ctx* c) {
   cudaFree(s->d_pack); cudaFree(s->d_b2); cudaFree(s->d_plane); cudaFree(s->d_ticket); cudaFree(s->d_picked);
   cudaFree(s->d_picks); cudaFree(s->d_status); cudaFree(s->d_cutA); cudaFree(s->d_cutB); cudaFree(s->d_keep);
   cudaFree(s->d_cut_iters); cudaFree(s->d_export);
+  for (auto p : s->d_aux_pad) cudaFree(p);
+  cudaFree(s->d_soft_tmpl); cudaFree(s->d_soft_b2); cudaFree(s->d_soft_plane); cudaFree(s->d_soft_ticket);
+  cudaFree(s->d_pickjobs); cudaFree(s->d_pending);
   if (s->h_pickstage) cudaFreeHost(s->h_pickstage);
   for (int i = 0; i < 2; ++i) {
     if (s->h_export[i]) cudaFreeHost(s->h_export[i]);
@@ -312,7 +380,9 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   if (d->nreal < 1 || d->nreal > c->max_batch) return fail(IQ_ERR_INVALID, "iq_sim_begin: nreal must be in 1..max_batch");
   if (d->npath < 0) return fail(IQ_ERR_INVALID, "iq_sim_begin: npath < 0");
   if (!(d->tol > 0.0 && d->tol <= 1.0)) return fail(IQ_ERR_INVALID, "tolerance must be in range (0,1]");
-  if (c->nsoft > 0) return fail(IQ_ERR_STATE, "resident simulation covers the threshold path only (context has soft data)");
+  if (c->nsoft > 0 && !d->aux) return fail(IQ_ERR_INVALID, "iq_sim_begin: the context has soft data but desc.aux is NULL");
+  for (int i = 0; i < c->nsoft; ++i)
+    if (!d->aux[i]) return fail(IQ_ERR_INVALID, "iq_sim_begin: aux[%d] is NULL", i);
   CK(cudaSetDevice(c->device));
   sim_destroy(c);
   const int t[3] = {c->tx, c->ty, c->tz};
@@ -372,12 +442,30 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   CK(iq::dmalloc((void**)&s->d_keep, ntask * maxslab));
   CK(iq::dmalloc((void**)&s->d_cut_iters, ntask * sizeof(int)));
   CK(cudaMemsetAsync(s->d_cut_iters, 0, ntask * sizeof(int), c->stream));
-  // selection jobs never change during the simulation: threshold rule on the overlap distance of realization r
+  s->S = c->nsoft;
+  s->d_aux_pad.assign(s->S, nullptr);
+  for (int i = 0; i < s->S; ++i) {
+    CK(iq::dmalloc((void**)&s->d_aux_pad[i], (size_t)s->padvol * sizeof(float)));
+    CK(cudaMemcpyAsync(s->d_aux_pad[i], d->aux[i], (size_t)s->padvol * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (s->S > 0) {
+    CK(iq::dmalloc((void**)&s->d_soft_tmpl, (size_t)c->tilevol * sizeof(float)));
+    CK(iq::dmalloc((void**)&s->d_soft_b2, sizeof(double)));
+    CK(iq::dmalloc((void**)&s->d_soft_plane, (size_t)c->tz * sizeof(double)));
+    CK(iq::dmalloc((void**)&s->d_soft_ticket, sizeof(unsigned)));
+    CK(cudaMemsetAsync(s->d_soft_ticket, 0, sizeof(unsigned), c->stream));
+  }
+  CK(iq::dmalloc((void**)&s->d_pickjobs, R * sizeof(iq::PickJob)));
+  CK(iq::dmalloc((void**)&s->d_pending, R * sizeof(int)));
+  // selection jobs never change during the simulation: threshold rule on the overlap distance of realization r, or
+  // (soft data) the intersection of the radix-select thresholds of the overlap map and the shared soft maps
   for (int r = 0; r < s->R; ++r) {
     iq::PickJob& J = c->h_pick[r];
     std::memset(&J, 0, sizeof J);
-    J.mode = 0;
-    J.nsrc = 1;
+    J.mode = s->S > 0 ? 1 : 0;
+    J.nsrc = 1 + s->S;
+    for (int i = 0; i < s->S; ++i) J.src[1 + i] = c->d_Dsoft[i];  // one soft map per step serves every realization
+    J.pending = s->S > 0 ? s->d_pending + r : nullptr;
     J.src[0] = c->d_Dovl + (size_t)r * c->npos;
     J.sel = c->d_sel + (size_t)r * c->max_src;
     J.tol = s->tol;
@@ -389,7 +477,7 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     J.cap = c->npos;
     J.chunkmin = c->d_chunkmin + (size_t)r * c->chunk_stride;
   }
-  CK(cudaMemcpyAsync(c->d_pick, c->h_pick, R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(s->d_pickjobs, c->h_pick, R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventCreate(&s->ev_begin));
   CK(cudaEventCreate(&s->ev_end));
   CK(cudaStreamSynchronize(c->stream));
@@ -449,7 +537,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
   if (nslab > s->maxslabs) return fail(IQ_ERR_INVALID, "iq_sim_step: too many slabs");
 
   const unsigned gR = (unsigned)((R + 127) / 128);
-  if (e->nnz == 0) {
+  if (e->nnz == 0 && s->S == 0) {
     // nothing pasted around the tile: every enabled patch with equal probability (iqsim.jl:237 on an all-zero map);
     // the walk is evaluated on the host from the cached cumulative weights
     rc = build_uniform(c);
@@ -468,13 +556,39 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
     CK(cudaGetLastError());
     c->launches++;
   } else {
-    CK(iq::launch_fill_u32(c->d_minmax + 0, 0x7f800000u, c->max_batch, c->stream));
-    CK(iq::launch_fill_u32(c->d_minmax + (size_t)c->max_batch, 0u, c->max_batch, c->stream));
-    k_sim_templates<<<dim3((unsigned)c->tz, (unsigned)R), 256, 0, c->stream>>>(
+    for (int kind = 0; kind < 2 + s->S; ++kind) {
+      if (kind == 1) continue;  // hard distance: not part of resident simulations
+      CK(iq::launch_fill_u32(c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch, 0x7f800000u, c->max_batch, c->stream));
+      CK(iq::launch_fill_u32(c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch, 0u, c->max_batch, c->stream));
+      c->launches += 2;
+    }
+    // direct kernel on `nt` dense templates: pack into its layout (shared scratch, stream ordered) and launch
+    auto direct = [&](MaskEntry* me, int image, const float* d_dense, const double* d_b2, int nt, float* d_out, int kind) -> int {
+      const int rb = pick_rb(c, nt);
+      const int ngrp = (nt + rb - 1) / rb;
+      const long long total = (long long)ngrp * me->tmpl_floats * rb;
+      if ((size_t)total > s->pack_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(s->d_pack);
+        s->d_pack = nullptr;
+        s->pack_cap = 0;
+        CK(iq::dmalloc((void**)&s->d_pack, (size_t)total * 2 * sizeof(float)));
+        s->pack_cap = (size_t)total * 2;
+      }
+      if (total > 0) {
+        k_sim_pack<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_dense, c->tilevol, c->tx, c->ty, me->d_boxes,
+                                                                            (int)me->boxes.size(), me->tmpl_floats, rb, nt, total,
+                                                                            s->d_pack);
+        CK(cudaGetLastError());
+        c->launches++;
+      }
+      return launch_direct(c, me, image, s->d_pack, d_b2, nt, rb, false, d_out, kind);
+    };
+    k_sim_templates<double><<<dim3((unsigned)c->tz, (unsigned)R), 256, 0, c->stream>>>(
         s->d_grid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], e->d_mask, c->tx, c->ty, c->tz, s->d_tmpl,
         s->d_plane, s->d_b2, s->d_ticket);
     CK(cudaGetLastError());
-    c->launches += 3;
+    c->launches += 1;
     bool done = false;
     if (want_fft(c, e, R)) {
       rc = ensure_fft(c, -1);
@@ -488,34 +602,64 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       }
     }
     if (!done) {
-      const int rb = pick_rb(c, R);
-      const int ngrp = (R + rb - 1) / rb;
-      const long long total = (long long)ngrp * e->tmpl_floats * rb;
-      if ((size_t)total > s->pack_cap) {
-        CK(cudaStreamSynchronize(c->stream));
-        cudaFree(s->d_pack);
-        s->d_pack = nullptr;
-        s->pack_cap = 0;
-        CK(iq::dmalloc((void**)&s->d_pack, (size_t)total * 2 * sizeof(float)));
-        s->pack_cap = (size_t)total * 2;
-      }
-      k_sim_pack<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(s->d_tmpl, c->tilevol, c->tx, c->ty, e->d_boxes,
-                                                                          (int)e->boxes.size(), e->tmpl_floats, rb, R, total,
-                                                                          s->d_pack);
-      CK(cudaGetLastError());
-      c->launches++;
-      rc = launch_direct(c, e, -1, s->d_pack, s->d_b2, R, rb, false, c->d_Dovl, 0);
+      rc = direct(e, -1, s->d_tmpl, s->d_b2, R, c->d_Dovl, 0);
       if (rc) return rc;
     }
+    // soft-data distances (iqsim.jl:222-227): the auxiliary tile is the same for every realization -> one map per step
+    for (int si = 0; si < s->S; ++si) {
+      k_sim_templates<float><<<dim3((unsigned)c->tz, 1u), 256, 0, c->stream>>>(
+          s->d_aux_pad[si], 0, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], c->full_mask->d_mask, c->tx, c->ty, c->tz,
+          s->d_soft_tmpl, s->d_soft_plane, s->d_soft_b2, s->d_soft_ticket);
+      CK(cudaGetLastError());
+      c->launches++;
+      bool sdone = false;
+      if (want_fft(c, c->full_mask, 1)) {
+        rc = ensure_fft(c, si);
+        if (rc == IQ_OK) {
+          rc = launch_fft(c, c->full_mask, si, s->d_soft_tmpl, s->d_soft_b2, 1, false, c->d_Dsoft[si], 2 + si);
+          if (rc) return rc;
+          sdone = true;
+        } else if (!(rc == IQ_ERR_STATE && c->fft_failed)) {
+          return rc;
+        }
+      }
+      if (!sdone) {
+        rc = direct(c->full_mask, si, s->d_soft_tmpl, s->d_soft_b2, 1, c->d_Dsoft[si], 2 + si);
+        if (rc) return rc;
+      }
+    }
     CK(cudaEventRecord(ev[0], c->stream));
-    rc = ensure_chunkmin(c, R);
-    if (rc) return rc;
-    CK(iq::launch_pick_chunks(c->d_pick, R, c->npos, c->chunk_len, c->chunk_n, c->stream));
-    CK(iq::launch_tau(c->d_pick, R, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
-    k_sim_sample<<<gR, 128, 0, c->stream>>>(c->d_pick, c->d_prob, s->d_u, s->npath, step, R, s->d_picked, s->d_picks,
+    if (s->S == 0) {
+      rc = ensure_chunkmin(c, R);
+      if (rc) return rc;
+      CK(iq::launch_pick_chunks(s->d_pickjobs, R, c->npos, c->chunk_len, c->chunk_n, c->stream));
+      c->launches += 1;
+    } else {
+      // relaxation rounds on the device: kRelaxRounds rounds are enqueued unconditionally, the kernels of a round
+      // return at once for realizations that already have candidates; a realization still empty after the last
+      // round raises the status word (the caller then reruns host-staged, where the round count is unbounded)
+      constexpr int kRelaxRounds = 3;
+      for (int round = 0; round < kRelaxRounds; ++round) {
+        k_sim_seljobs<<<R, 32, 0, c->stream>>>(c->d_sel, s->d_pickjobs, c->max_src, c->d_minmax + (size_t)c->max_batch, s->tol,
+                                              c->nenabled, c->npos, round, s->d_pending);
+        CK(cudaGetLastError());
+        for (int pass = 0; pass < c->nshift; ++pass)
+          CK(iq::launch_select_pass(c->d_sel, R * c->max_src, c->npos, c->d_shifts, c->nshift, c->stream));
+        k_sim_copykth<<<R, 32, 0, c->stream>>>(c->d_sel, c->max_src);
+        CK(cudaGetLastError());
+        CK(iq::launch_pick_count(s->d_pickjobs, R, c->npos, c->stream));
+        k_sim_relax_check<<<gR, 128, 0, c->stream>>>(s->d_pickjobs, R, s->d_pending, round == kRelaxRounds - 1 ? 1 : 0, s->d_status);
+        CK(cudaGetLastError());
+        c->launches += 4 + c->nshift;
+      }
+      CK(iq::launch_pick_write(s->d_pickjobs, R, c->npos, c->stream));
+      c->launches += 1;
+    }
+    CK(iq::launch_tau(s->d_pickjobs, R, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
+    k_sim_sample<<<gR, 128, 0, c->stream>>>(s->d_pickjobs, c->d_prob, s->d_u, s->npath, step, R, s->d_picked, s->d_picks,
                                             s->d_status);
     CK(cudaGetLastError());
-    c->launches += 4;
+    c->launches += 3;
   }
   CK(cudaEventRecord(ev[1], c->stream));
 
@@ -565,6 +709,39 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
   CK(cudaGetLastError());
   c->launches++;
   c->last_launches = c->launches - l0;
+  return IQ_OK;
+}
+
+int32_t iq_sim_step_picked(iq_ctx* c, int64_t step, const int64_t* start, const int64_t* picks) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step_picked: no simulation open on this context");
+  SimState* s = c->sim;
+  if (!start || !picks) return fail(IQ_ERR_INVALID, "iq_sim_step_picked: NULL argument");
+  if (step < 0 || step >= s->npath) return fail(IQ_ERR_INVALID, "iq_sim_step_picked: step out of range");
+  CK(cudaSetDevice(c->device));
+  const int t[3] = {c->tx, c->ty, c->tz};
+  int st3[3] = {0, 0, 0};
+  for (int i = 0; i < c->ndim; ++i) {
+    st3[i] = (int)start[i];
+    if (st3[i] < 0 || st3[i] + t[i] > s->pad[i]) return fail(IQ_ERR_INVALID, "iq_sim_step_picked: tile outside the padded grid");
+  }
+  const int R = s->R;
+  s->synced = false;
+  long long* hp = s->h_pickstage + (size_t)step * R;
+  for (int r = 0; r < R; ++r) {
+    if (picks[r] < 0 || picks[r] >= c->npos) return fail(IQ_ERR_INVALID, "iq_sim_step_picked: pick %d out of range", r);
+    hp[r] = picks[r];
+  }
+  const unsigned gR = (unsigned)((R + 127) / 128);
+  CK(cudaMemcpyAsync(s->d_picked, hp, (size_t)R * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  k_sim_store_picks<<<gR, 128, 0, c->stream>>>(s->d_picked, s->d_picks, s->npath, step, R);
+  CK(cudaGetLastError());
+  SlabSet S{};
+  k_sim_paste<<<dim3((unsigned)((c->tilevol + 255) / 256), (unsigned)R), 256, 0, c->stream>>>(
+      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], s->d_ti64, c->nx, c->ny, c->nxo, c->nyo,
+      s->d_picked, c->tx, c->ty, c->tz, S, s->d_keep, (long long)s->maxslab, s->d_cut_iters, s->d_status);
+  CK(cudaGetLastError());
+  c->launches += 2;
+  c->last_launches = 2;
   return IQ_OK;
 }
 

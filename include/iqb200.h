@@ -158,12 +158,17 @@ int32_t iq_cut_batch(iq_ctx* ctx, const iq_cut_task* tasks, int32_t ntask, int32
  *     template gather from the grids (iqsim.jl:185) -> overlap distance (utils.jl:5-13) -> threshold selection
  *     (iqsim.jl:237) -> tau model (taumodel.jl:5-45) -> StatsBase.sample walk with the pre-drawn uniform
  *     (iqsim.jl:243) -> boundary cuts (graphcut.jl:5-84, device kernel of iq_cut_batch) -> paste (iqsim.jl:278).
- * Scope: the threshold path (no soft / hard data on the context) with overlap slabs that fit the shared-memory cut
- * kernel; iq_sim_begin returns IQ_ERR_STATE otherwise and the caller uses iq_search_pick + its own paste instead.
- * A data-dependent condition the device path does not cover (a candidate set larger than 16 384 entries on a
- * non-empty mask) is reported by iq_sim_sync through `status` != 0; the grids are then invalid and the caller
- * reruns the simulation through iq_search_pick.  While a simulation is open the context must not be used for
- * iq_search* / iq_distance / iq_slice_* calls. */
+ * Scope: no hard data; overlap slabs that fit the shared-memory cut kernel (iq_sim_begin returns IQ_ERR_STATE
+ * otherwise and the caller uses iq_search_pick + its own paste instead).  With soft data every step runs the first
+ * relaxation round (src/relaxation.jl:5-39: radix select of the dbsize / softk smallest keys per source, intersection)
+ * on the device.  Steps whose overlap mask is empty on a context with soft data (their candidate set is a tenth of
+ * all patterns, far above the device tau model's 32 768 entries) are done by the caller through iq_search +
+ * iq_sample and handed over with iq_sim_step_picked.
+ * A data-dependent condition the device path does not cover (a candidate set of more than 32 768 entries on a
+ * non-empty mask, an empty first relaxation round, a cut hitting its iteration cap) is reported by iq_sim_sync
+ * through `status` != 0; the grids are then invalid and the caller reruns the simulation through iq_search_pick.
+ * While a simulation is open the context may be used for iq_search / iq_distance between steps (they wait for the
+ * enqueued steps), nothing else. */
 typedef struct iq_sim_desc {
   int64_t pad_size[3];   /* padded simulation grid (src/iqsim.jl:106), unused dims = 1 */
   int64_t ovl_size[3];   /* overlap size per dimension (src/iqsim.jl:92): fixes the largest cut slab */
@@ -173,6 +178,8 @@ typedef struct iq_sim_desc {
   int64_t npath;         /* number of path steps */
   double tol;
   int32_t debug;         /* nonzero: also keep the boundary-cut grids (src/iqsim.jl:281) */
+  const float* const* aux; /* contexts with soft data: ctx.nsoft padded auxiliary grids (pad_size floats each,
+                              symmetric-padded, NaN -> 0; src/utils.jl:74-89), else NULL */
 } iq_sim_desc;
 typedef struct iq_sim_slab {   /* one overlap slab of the current tile, in tile coordinates */
   int32_t dim;           /* dimension of the overlap */
@@ -184,6 +191,9 @@ int32_t iq_sim_begin(iq_ctx* ctx, const iq_sim_desc* desc);
  * the overlap mask of the step and the slabs whose union it is (nslab may be 0: nothing pasted around the tile). */
 int32_t iq_sim_step(iq_ctx* ctx, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
                     int32_t nslab);
+/* A step whose patterns the caller chose itself (picks[r] = 0-based linear index of the pattern of realization r):
+ * the whole tile is pasted (no pasted neighbour, hence no cut).  Used for empty-mask steps of soft-data simulations. */
+int32_t iq_sim_step_picked(iq_ctx* ctx, int64_t step, const int64_t* start, const int64_t* picks);
 /* Waits for the enqueued steps.  picks (may be NULL): [nreal][npath] chosen patterns; status: 0 = ok. */
 int32_t iq_sim_sync(iq_ctx* ctx, int64_t* picks, int32_t* status);
 /* Copies realization r, cropped to crop[3] (unused dims = 1), to the host as FP64 (dtype 0) or FP32 (dtype 1). */

@@ -82,6 +82,7 @@ typedef struct iqh_stats {
   double select_ms;            /* resident: device time of selection + tau model + sampling (sum over groups) */
   double cut_device_ms;        /* resident: device time of the boundary cuts (sum over groups) */
   double fetch_ms;             /* resident: wall time of exporting the realizations to the host */
+  int64_t max_candidates;      /* host-staged: largest candidate set of any tile search */
 } iqh_stats;
 
 /* Runs the whole simulation.  `out_grids` receives nreal padded grids (pad_size doubles each,

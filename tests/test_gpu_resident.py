@@ -70,15 +70,38 @@ def test_resident_config1_matches_oracle():
         assert g.dtype == w.dtype and np.array_equal(g, w)
 
 
-def test_resident_refuses_soft_data_and_auto_falls_back():
+def test_resident_refuses_hard_data_and_auto_falls_back():
     cfg = synth.config(3, scale=0.4)
     ti = cfg["trainimg"]
-    aux = np.asfortranarray(synth.box_mean(ti, (3, 3, 3)))
+    hard = cfg["kwargs"]["hard"]
     with pytest.raises(_lib.IqError):
-        iqb200.iqsim(ti, cfg["tilesize"], nreal=1, soft=[(aux, aux)], pipeline="resident", rng=np.random.default_rng(0))
-    out, ex = iqb200.iqsim(ti, cfg["tilesize"], nreal=1, soft=[(aux, aux)], pipeline="auto", rng=np.random.default_rng(0),
+        iqb200.iqsim(ti, cfg["tilesize"], nreal=1, hard=hard, pipeline="resident", rng=np.random.default_rng(0))
+    out, ex = iqb200.iqsim(ti, cfg["tilesize"], nreal=1, hard=hard, pipeline="auto", rng=np.random.default_rng(0),
                            return_stats=True)
     assert ex["stats"]["resident"] == 0 and out[0].shape == ti.shape
+
+
+@pytest.mark.parametrize("fft", [-1, 1])
+def test_resident_soft_data_equals_staged(fft):
+    """Soft data: the first relaxation round (radix select per source + intersection), the tau model with two
+    sources and the sampling walk run on the device; the empty-mask first tile goes through iq_search + iq_sample."""
+    ti = synth.gaussian_field((48, 40, 20), (6, 6, 3), 9)
+    auxti = np.asfortranarray(synth.box_mean(ti, (5, 5, 3)).astype(np.float32))
+    other = synth.gaussian_field((48, 40, 20), (6, 6, 3), 10)
+    aux = np.asfortranarray(synth.box_mean(other, (5, 5, 3)).astype(np.float32))
+    a, ea, b, eb = both(ti, (16, 12, 8), 7, nreal=3, fft=fft, overlap=(0.25, 0.25, 0.25), soft=[(aux, auxti)])
+    same(a, ea, b, eb)
+
+
+def test_resident_soft_data_2d_two_variables():
+    ti = synth.gaussian_field((96, 80), (6, 6), 4)
+    auxti1 = np.asfortranarray(synth.box_mean(ti, (7, 7)).astype(np.float32))
+    auxti2 = np.asfortranarray(synth.box_mean(ti, (3, 9)).astype(np.float32))
+    tgt = synth.gaussian_field((96, 80), (6, 6), 5)
+    aux1 = np.asfortranarray(synth.box_mean(tgt, (7, 7)).astype(np.float32))
+    aux2 = np.asfortranarray(synth.box_mean(tgt, (3, 9)).astype(np.float32))
+    a, ea, b, eb = both(ti, (24, 20), 8, nreal=4, soft=[(aux1, auxti1), (aux2, auxti2)], debug=True)
+    same(a, ea, b, eb, debug=True)
 
 
 def test_resident_many_realizations_groups():
