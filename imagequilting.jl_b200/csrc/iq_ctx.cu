@@ -739,6 +739,8 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
           sj.map = c->h_pick[r].src[s];
           sj.k = (unsigned long long)std::max<long long>(1, std::min<long long>(s == 0 ? dbsize[r] : softk, c->npos));
           sj.active = 1;
+          sj.cbuf = c->d_selbuf + ((size_t)r * maxS + s) * c->sel_cap;
+          sj.ccap = c->sel_cap;
           ++njobs;
         }
         iters[r]++;
@@ -757,9 +759,10 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
                                (size_t)(nsrc[r] - 1) * sizeof(iq::SelJob), cudaMemcpyHostToDevice, c->stream));
           }
         }
-        for (int pass = 0; pass < c->nshift; ++pass) {
-          CK(iq::launch_select_pass(c->d_sel, R * maxS, c->npos, c->d_shifts, c->nshift, c->stream));
-          c->launches++;
+        {
+          int nl = 0;
+          CK(iq::launch_select_all(c->d_sel, R * maxS, c->npos, c->d_shifts, c->nshift, c->stream, &nl));
+          c->launches += nl;
         }
       }
     }
@@ -931,6 +934,7 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   cudaFree(c->d_stage);
   cudaFree(c->d_sel);
+  cudaFree(c->d_selbuf);
   if (c->h_sel) cudaFreeHost(c->h_sel);
   cudaFree(c->d_pick);
   if (c->h_pick) cudaFreeHost(c->h_pick);
@@ -1029,6 +1033,8 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   const size_t nmm = (size_t)(2 + c->nsoft) * 2 * B;
   CK(iq::dmalloc((void**)&c->d_minmax, nmm * sizeof(unsigned)));
   CK(cudaMallocHost((void**)&c->h_minmax, nmm * sizeof(unsigned)));
+  c->sel_cap = (unsigned)std::max<long long>(c->npos / 16, 4096);
+  CK(iq::dmalloc((void**)&c->d_selbuf, B * c->max_src * (size_t)c->sel_cap * sizeof(unsigned long long)));
   CK(iq::dmalloc((void**)&c->d_sel, B * c->max_src * sizeof(iq::SelJob)));
   CK(cudaMallocHost((void**)&c->h_sel, B * c->max_src * sizeof(iq::SelJob)));
   CK(cudaMemsetAsync(c->d_sel, 0, B * c->max_src * sizeof(iq::SelJob), c->stream));

@@ -89,6 +89,8 @@ struct iq_ctx {
   char* d_stage = nullptr;
   size_t stage_cap = 0, stage_used = 0;
 
+  unsigned long long* d_selbuf = nullptr;  // [max_batch][max_src][sel_cap] survivor lists of the radix select
+  unsigned sel_cap = 0;
   iq::SelJob* d_sel = nullptr;
   iq::SelJob* h_sel = nullptr;
   iq::PickJob* d_pick = nullptr;

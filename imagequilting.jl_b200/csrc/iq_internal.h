@@ -67,6 +67,12 @@ struct SelJob {
   int active;                    // 0 = done / skip
   unsigned ticket;               // last-block detection
   unsigned hist[256];
+  // After the first two passes (16 value bits decided) the keys that still match the prefix -- typically ~1 % of the
+  // map -- are copied to `cbuf`, and the remaining passes scan that list instead of the whole map.
+  unsigned long long* cbuf;      // [ccap] scratch of this job (or nullptr: never compact)
+  unsigned ccap;
+  unsigned ccount;               // keys in cbuf
+  int compact;                   // 1 = cbuf holds the surviving keys (set by the pass that decides it, filled by k_select_compact)
 };
 
 // Candidate predicate + outputs for one tile.
@@ -116,6 +122,9 @@ cudaError_t launch_a2map(const double* sat, int nx, int ny, int nz, const BoxDes
 cudaError_t launch_fill_u32(unsigned* p, unsigned v, long long n, cudaStream_t s);
 cudaError_t launch_select_pass(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift,
                                cudaStream_t s);
+// All passes of a radix select (k_select_pass x nshift, with the compaction of the survivors after the second pass).
+cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s,
+                              int* launches);
 cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
 cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
 // Threshold selection driven by chunk minima (chunk = chunklen consecutive positions): only chunks whose minimum

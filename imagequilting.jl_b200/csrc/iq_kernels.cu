@@ -12,6 +12,8 @@
 //                  the Perm ordering (relaxation.jl:12,27)
 //   k_pick_count / k_pick_write   ordered compaction of the candidate set = findall (iqsim.jl:237)
 //                  and fastintersect (relaxation.jl:41-48)
+#include <algorithm>
+
 #include "iq_internal.h"
 
 #include <math_constants.h>
@@ -804,80 +806,147 @@ __device__ __forceinline__ unsigned long long make_key(float v, long long p) {
   return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)p;
 }
 
-__global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, long long npos, const int* __restrict__ shifts,
+// Grid = (blocks per job, jobs).  Inactive jobs (finished early, later relaxation rounds) return at once; the launcher
+// keeps the blocks per job low when there are many jobs so that such rows stay cheap.
+__global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, long long npos, const int* __restrict__ shifts,
                                                      int nshift) {
-  SelJob* J = jobs + blockIdx.y;
   __shared__ unsigned h[256];
   __shared__ int s_active, s_pass, s_last;
   __shared__ unsigned long long s_prefix, s_mask;
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    s_active = J->active;
-    s_pass = J->pass;
-    s_prefix = J->prefix;
-    s_mask = J->mask;
+  for (int q = 0; q < 1; ++q) {
+    SelJob* J = jobs + blockIdx.y;
+    __syncthreads();  // previous job's shared state fully consumed
+    if (tid == 0) {
+      s_active = J->active;
+      s_pass = J->pass;
+      s_prefix = J->prefix;
+      s_mask = J->mask;
+    }
+    h[tid] = 0;
+    __syncthreads();
+    if (!s_active) continue;
+    const int shift = shifts[s_pass];
+    const unsigned long long prefix = s_prefix, mask = s_mask;
+    const float* __restrict__ map = J->map;
+    const bool comp = J->compact != 0;  // scan the compacted survivors instead of the map
+    const unsigned long long* __restrict__ cbuf = J->cbuf;
+    const long long n = comp ? (long long)J->ccount : npos;
+    // warp-aggregated histogram: distance values cluster in a few exponent bins, so per-lane shared-memory
+    // atomics would serialise 32-way; lanes with the same bin elect one leader that adds their count
+    const int lane = tid & 31;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+      const long long i = i0 + lane;
+      unsigned bin = 0xffffffffu;
+      if (i < n) {
+        const unsigned long long key = comp ? cbuf[i] : make_key(map[i], i);
+        if ((key & mask) == prefix) bin = (unsigned)(key >> shift) & 255u;
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (h[tid]) atomicAdd(&J->hist[tid], h[tid]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) continue;
+    if (tid == 0) {
+      __threadfence();
+      volatile unsigned* gh = J->hist;
+      unsigned long long k = J->k, cum = 0, c = 0;
+      int b = 0;
+      for (; b < 256; ++b) {
+        c = gh[b];
+        if (cum + c >= k) break;
+        cum += c;
+      }
+      if (b == 256) { b = 255; }  // k beyond the population: clamp (host never asks for this)
+      k -= cum;
+      const unsigned long long np = prefix | ((unsigned long long)b << shift);
+      const bool exact = (c == k);  // every key sharing the new prefix is selected
+      if (exact || s_pass + 1 == nshift) {
+        J->kth = exact ? (np | ((shift == 0) ? 0ull : ((1ull << shift) - 1ull))) : np;
+        J->active = 0;
+      } else {
+        const int ns = shifts[s_pass + 1];
+        J->mask = ~((1ull << (ns + 8)) - 1ull);
+        J->pass = s_pass + 1;
+        // second pass done: c keys share the decided 16 bits; if they fit, k_select_compact gathers them next
+        if (s_pass == 1 && nshift > 3 && J->cbuf && c <= (unsigned long long)J->ccap) { J->compact = 2; J->ccount = 0; }
+      }
+      J->prefix = np;
+      J->k = k;
+      for (int i = 0; i < 256; ++i) gh[i] = 0;
+      J->ticket = 0;
+      __threadfence();
+    }
   }
-  h[tid] = 0;
-  __syncthreads();
-  if (!s_active) return;
-  const int shift = shifts[s_pass];
-  const unsigned long long prefix = s_prefix, mask = s_mask;
+}
+
+// Gathers the keys that match the decided prefix of every job marked by the second pass (compact == 2) into its
+// scratch list (order is irrelevant: keys are unique) and switches the job to list mode (compact = 1).
+__global__ void __launch_bounds__(256) k_select_compact(SelJob* jobs, int njobs, long long npos) {
+ for (int q = 0; q < 1; ++q) {
+  SelJob* J = jobs + blockIdx.y;
+  if (!J->active || J->compact != 2) continue;
+  const unsigned long long prefix = J->prefix, mask = J->mask;
   const float* __restrict__ map = J->map;
-  // warp-aggregated histogram: distance values cluster in a few exponent bins, so per-lane shared-memory
-  // atomics would serialise 32-way; lanes with the same bin elect one leader that adds their count
-  const int lane = tid & 31;
+  unsigned long long* __restrict__ cbuf = J->cbuf;
+  const int tid = threadIdx.x, lane = tid & 31;
   for (long long i0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); i0 < npos; i0 += (long long)gridDim.x * blockDim.x) {
     const long long i = i0 + lane;
-    unsigned bin = 0xffffffffu;
+    unsigned long long key = 0;
+    bool hit = false;
     if (i < npos) {
-      const unsigned long long key = make_key(map[i], i);
-      if ((key & mask) == prefix) bin = (unsigned)(key >> shift) & 255u;
+      key = make_key(map[i], i);
+      hit = (key & mask) == prefix;
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (bal) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&J->ccount, (unsigned)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hit) cbuf[base + __popc(bal & ((1u << lane) - 1u))] = key;
+    }
   }
-  __syncthreads();
-  if (h[tid]) atomicAdd(&J->hist[tid], h[tid]);
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  if (tid == 0) {
-    __threadfence();
-    volatile unsigned* gh = J->hist;
-    unsigned long long k = J->k, cum = 0, c = 0;
-    int b = 0;
-    for (; b < 256; ++b) {
-      c = gh[b];
-      if (cum + c >= k) break;
-      cum += c;
+ }
+}
+// one thread per job flips compact 2 -> 1 after the gather (a separate launch orders it after every block above)
+__global__ void k_select_compact_done(SelJob* jobs, int njobs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < njobs && jobs[j].compact == 2) jobs[j].compact = 1;
+}
+
+cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s,
+                              int* launches) {
+  long long nb = (npos + 256 * 8 - 1) / (256 * 8);
+  const long long cap = njobs >= 16 ? 148 : 148 * 4;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  int nl = 0;
+  for (int pass = 0; pass < nshift; ++pass) {
+    cudaError_t e = launch_select_pass(jobs, njobs, npos, shifts, nshift, s);
+    if (e != cudaSuccess) return e;
+    ++nl;
+    if (pass == 1 && nshift > 3) {
+      k_select_compact<<<dim3((unsigned)nb, njobs), 256, 0, s>>>(jobs, njobs, npos);
+      k_select_compact_done<<<(njobs + 127) / 128, 128, 0, s>>>(jobs, njobs);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      nl += 2;
     }
-    if (b == 256) { b = 255; }  // k beyond the population: clamp (host never asks for this)
-    k -= cum;
-    const unsigned long long np = prefix | ((unsigned long long)b << shift);
-    const bool exact = (c == k);  // every key sharing the new prefix is selected
-    if (exact || s_pass + 1 == nshift) {
-      J->kth = exact ? (np | ((shift == 0) ? 0ull : ((1ull << shift) - 1ull))) : np;
-      J->active = 0;
-    } else {
-      const int ns = shifts[s_pass + 1];
-      J->mask = ~((1ull << (ns + 8)) - 1ull);
-      J->pass = s_pass + 1;
-    }
-    J->prefix = np;
-    J->k = k;
-    for (int i = 0; i < 256; ++i) gh[i] = 0;
-    J->ticket = 0;
-    __threadfence();
   }
+  if (launches) *launches += nl;
+  return cudaSuccess;
 }
 
 cudaError_t launch_select_pass(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s) {
   long long nb = (npos + 256 * 8 - 1) / (256 * 8);
-  if (nb > 148 * 4) nb = 148 * 4;
+  const long long cap = njobs >= 16 ? 148 : 148 * 4;
+  if (nb > cap) nb = cap;
   if (nb < 1) nb = 1;
-  k_select_pass<<<dim3((unsigned)nb, njobs), 256, 0, s>>>(jobs, npos, shifts, nshift);
+  k_select_pass<<<dim3((unsigned)nb, njobs), 256, 0, s>>>(jobs, njobs, npos, shifts, nshift);
   return cudaGetLastError();
 }
 

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256) k_sim_pack(const float* __restrict__ tmpl
   out[i] = v;
 }
 
-// Base.sum's pairwise reduction (Base.mapreduce_impl, block 1024), as julia_sum in iq_ctx.cu.
+// Base.sum's pairwise reduction (Base.mapreduce_impl, block 1024), as julia_sum in iq_ctx.cu: sequential inside a
+// leaf (hi - lo < 1024), left + right above.
 __device__ double dev_julia_sum(const double* w, int lo, int hi) {
   if (hi - lo < 1024) {
     double v = w[lo];
@@ -162,29 +163,82 @@ __device__ double dev_julia_sum(const double* w, int lo, int hi) {
   return __dadd_rn(dev_julia_sum(w, lo, mid), dev_julia_sum(w, mid + 1, hi));
 }
 
-// StatsBase.sample walk (iqsim.jl:243) on the candidate list of every realization; one thread each.
-// status bits: 1 = candidate set outside 1..kTauMax, 2 = a boundary cut hit its iteration cap.
-__global__ void k_sim_sample(const iq::PickJob* __restrict__ jobs, const double* __restrict__ prob,
-                             const double* __restrict__ u, long long npath, long long step, int R,
-                             long long* __restrict__ picked, long long* __restrict__ picks, int* __restrict__ status) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// The same sum by one warp, bit for bit: lane l walks down the recursion tree following the bits of l (most
+// significant first) for at most 5 levels; a node that is a leaf before level 5 belongs to the lane whose remaining
+// bits are zero, the other lanes below it own nothing.  Every owner sums its sub-range with the sequential/recursive
+// routine, then the tree is folded upwards: a parent is left + right when both halves exist, else the half that does.
+__device__ double warp_julia_sum(const double* w, int n, int lane) {
+  int lo = 0, hi = n - 1;
+  bool owner = true;
+#pragma unroll
+  for (int level = 4; level >= 0; --level) {
+    if (hi - lo < 1024) {                       // leaf reached early
+      if (lane & ((2 << level) - 1)) owner = false;  // only the lane with all remaining bits clear keeps it
+      break;
+    }
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((lane >> level) & 1) lo = mid + 1; else hi = mid;
+  }
+  double v = owner ? dev_julia_sum(w, lo, hi) : 0.0;
+  int have = owner ? 1 : 0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, v, o);
+    const int oh = __shfl_down_sync(0xffffffffu, have, o);
+    if ((lane & (2 * o - 1)) == 0) {            // left child of a level-o pair
+      if (have && oh) v = __dadd_rn(v, ov);
+      else if (oh) { v = ov; have = 1; }
+    }
+  }
+  return __shfl_sync(0xffffffffu, v, 0);
+}
+
+// StatsBase.sample walk (iqsim.jl:243) on the candidate list of every realization; one WARP each: the total is the
+// pairwise sum above, the cumulative walk is inherently sequential in FP64 (cw += p[i]) -- the lanes fetch 32
+// consecutive weights with one coalesced load (next batch prefetched) and lane 0's running sum is fed by shuffles,
+// so the chain costs one DADD latency per candidate instead of a dependent global load.
+// status bits: 1 = candidate set outside 1..kTauMax, 2 = a boundary cut hit its iteration cap, 4 = relaxation rounds.
+__global__ void __launch_bounds__(128) k_sim_sample(const iq::PickJob* __restrict__ jobs, const double* __restrict__ prob,
+                                                    const double* __restrict__ u, long long npath, long long step, int R,
+                                                    long long* __restrict__ picked, long long* __restrict__ picks,
+                                                    int* __restrict__ status) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= R) return;
   const iq::PickJob& J = jobs[r];
   const unsigned n = *J.total;
-  long long pos = 0;
+  unsigned pos = 0;
   if (n == 0u || n > (unsigned)iq::kTauMax) {
-    atomicOr(status, 1);
+    if (lane == 0) atomicOr(status, 1);
   } else if (n > 1u) {
     const double* p = prob + (long long)r * iq::kTauMax;
-    const double t = __dmul_rn(u[(long long)r * npath + step], dev_julia_sum(p, 0, (int)n - 1));
-    double cw = p[0];
-    unsigned i = 0;
-    while (cw < t && i < n - 1u) { ++i; cw = __dadd_rn(cw, p[i]); }
-    pos = i;
+    const double t = __dmul_rn(u[(long long)r * npath + step], warp_julia_sum(p, (int)n, lane));
+    // first i with cw_i >= t among i < n-1, else n-1, where cw_0 = p[0], cw_i = fl(cw_{i-1} + p[i])
+    // Every lane carries the same running sum (the only dependent chain: one DADD per candidate, cw_0 = 0 + p[0]
+    // exactly); lane j keeps the value after candidate base + j and the crossing test runs once per batch of 32.
+    double cw = 0.0;
+    bool found = false;
+    double cur = lane < n ? p[lane] : 0.0;
+    for (unsigned base = 0; base < n && !found; base += 32) {
+      const unsigned nb = base + 32;
+      const double nxt = (nb + lane < n) ? p[nb + lane] : 0.0;  // prefetch the next batch
+      double mine = 0.0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        cw = __dadd_rn(cw, __shfl_sync(0xffffffffu, cur, j));
+        if (lane == j) mine = cw;
+      }
+      const unsigned i = base + lane;
+      const bool hit = i < n && (!(mine < t) || i == n - 1u);
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) { pos = base + (unsigned)(__ffs(bal) - 1); found = true; }
+      cur = nxt;
+    }
   }
-  const long long pk = (n == 0u) ? 0 : (long long)J.cand_idx[pos];
-  picked[r] = pk;
-  picks[(long long)r * npath + step] = pk;
+  if (lane == 0) {
+    const long long pk = (n == 0u) ? 0 : (long long)J.cand_idx[pos];
+    picked[r] = pk;
+    picks[(long long)r * npath + step] = pk;
+  }
 }
 
 // Relaxation rounds (src/relaxation.jl:7-36) of every realization on the device.  Round 0: radix-select jobs for the
@@ -196,7 +250,7 @@ __global__ void k_sim_sample(const iq::PickJob* __restrict__ jobs, const double*
 // per source.
 __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* __restrict__ pick, int maxS,
                               const unsigned* __restrict__ maxbits, double tol, long long npatterns, long long npos,
-                              int round, int* __restrict__ pending) {
+                              int round, int* __restrict__ pending, unsigned long long* __restrict__ selbuf, unsigned selcap) {
   const int r = blockIdx.x, s = threadIdx.x;
   if (s >= maxS) return;
   if (round > 0 && pending[r] == 0) return;  // candidates found: its jobs stay finished
@@ -204,6 +258,7 @@ __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* 
   iq::SelJob& J = jobs[(long long)r * maxS + s];
   const iq::PickJob& P = pick[r];
   J.k = 0; J.prefix = 0; J.mask = 0; J.kth = 0; J.pass = 0; J.active = 0; J.ticket = 0;
+  J.cbuf = selbuf + ((long long)r * maxS + s) * selcap; J.ccap = selcap; J.ccount = 0; J.compact = 0;
   for (int i = 0; i < 256; ++i) J.hist[i] = 0;
   if (s == 0 && round == 0) pending[r] = 1;
   if (s >= P.nsrc) return;
@@ -641,23 +696,26 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       constexpr int kRelaxRounds = 3;
       for (int round = 0; round < kRelaxRounds; ++round) {
         k_sim_seljobs<<<R, 32, 0, c->stream>>>(c->d_sel, s->d_pickjobs, c->max_src, c->d_minmax + (size_t)c->max_batch, s->tol,
-                                              c->nenabled, c->npos, round, s->d_pending);
+                                              c->nenabled, c->npos, round, s->d_pending, c->d_selbuf, c->sel_cap);
         CK(cudaGetLastError());
-        for (int pass = 0; pass < c->nshift; ++pass)
-          CK(iq::launch_select_pass(c->d_sel, R * c->max_src, c->npos, c->d_shifts, c->nshift, c->stream));
+        {
+          int nl = 0;
+          CK(iq::launch_select_all(c->d_sel, R * c->max_src, c->npos, c->d_shifts, c->nshift, c->stream, &nl));
+          c->launches += nl;
+        }
         k_sim_copykth<<<R, 32, 0, c->stream>>>(c->d_sel, c->max_src);
         CK(cudaGetLastError());
         CK(iq::launch_pick_count(s->d_pickjobs, R, c->npos, c->stream));
         k_sim_relax_check<<<gR, 128, 0, c->stream>>>(s->d_pickjobs, R, s->d_pending, round == kRelaxRounds - 1 ? 1 : 0, s->d_status);
         CK(cudaGetLastError());
-        c->launches += 4 + c->nshift;
+        c->launches += 4;
       }
       CK(iq::launch_pick_write(s->d_pickjobs, R, c->npos, c->stream));
       c->launches += 1;
     }
     CK(iq::launch_tau(s->d_pickjobs, R, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
-    k_sim_sample<<<gR, 128, 0, c->stream>>>(s->d_pickjobs, c->d_prob, s->d_u, s->npath, step, R, s->d_picked, s->d_picks,
-                                            s->d_status);
+    k_sim_sample<<<(unsigned)((R + 3) / 4), 128, 0, c->stream>>>(s->d_pickjobs, c->d_prob, s->d_u, s->npath, step, R,
+                                                                 s->d_picked, s->d_picks, s->d_status);
     CK(cudaGetLastError());
     c->launches += 3;
   }
