@@ -245,7 +245,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    nthreads = max(1, ncores // max(world, 1) - 2)  # per rank: leave the GPU-driving thread and the sampler a core
+    # host threads per rank: cut/paste pool of the host-staged pipeline (which leaves the GPU-driving thread and the clock
+    # sampler a core), export threads of the device-resident one (the driving thread is idle by then)
+    nthreads = max(1, ncores // max(world, 1) - (2 if args.pipeline == "staged" else 0))
     seed0 = 1234 + 1000 * rank
 
     def step(i):
@@ -340,7 +342,7 @@ def main():
                              "note": "B_alg(R) = 4|TI| + spectrum + R(4 npos + 8 nnz) per launch of R searches: the floor any "
                                      "method must move; the FFT method's own traffic is `bytes_per_search`"}
         # traffic: DRAM bytes of the passes per launch of 64 searches, from the committed ncu launch list
-        roof["traffic"] = 6.63e9 if args.config == 5 and args.nreal_per_gpu == 64 else None
+        roof["traffic"] = 6.72e9 if args.config == 5 and args.nreal_per_gpu == 64 else None
         roof["traffic_note"] = ("dram__bytes_read+write summed over the five FFT passes of one step (64 searches), "
                                 "profiles/r01_launches_resident.csv; algorithmic bytes of the same launch: 64 x bytes_per_search")
         if direct_ms > 0 and ndirect > 0:

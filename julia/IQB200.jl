@@ -105,4 +105,62 @@ function search(ctx::Context, ovlmask::AbstractArray{Bool}, simdevs::Vector; har
   out
 end
 
+# ---- device-resident simulation (iq_sim_*): grids, sampling, boundary cuts and paste on the device -----------------
+struct SimDesc          # == iq_sim_desc
+  pad_size::NTuple{3,Int64}
+  ovl_size::NTuple{3,Int64}
+  nreal::Int32
+  ti64::Ptr{Float64}
+  u::Ptr{Float64}
+  npath::Int64
+  tol::Float64
+  debug::Int32
+  aux::Ptr{Ptr{Float32}}
+end
+
+struct SimSlab          # == iq_sim_slab (tile coordinates, 0-based)
+  dim::Int32
+  prev::Int32
+  lo::NTuple{3,Int32}
+  sz::NTuple{3,Int32}
+end
+
+"""
+    simulate!(outs, ctx, TI, padsize, ovlsize, steps, U; tol=0.1, aux=[])
+
+Runs a whole simulation on the device.  `steps` is the path as a vector of
+`(start0::NTuple{3,Int}, ovlmask::Array{Bool}, slabs::Vector{SimSlab})` (what src/iqsim.jl:177-205 derives from
+`simpath` and `pasted`), `U` the `nreal x length(steps)` uniforms drawn in the reference's order, `outs` the
+preallocated `Float32` realizations (cropped to `size(outs[1])`).  Returns the status word (0 = ok; otherwise fall
+back to `search` + host cut/paste).  Steps with an empty mask on a context with soft data must be done with
+`search` + `sample` and handed over through `iq_sim_step_picked` (not wrapped here).
+"""
+function simulate!(outs::Vector{<:Array{Float32}}, ctx::Context, TI::AbstractArray{<:Real,N}, padsize::Dims{N},
+                   ovlsize::Dims{N}, steps, U::Matrix{Float64}; tol=0.1, aux=[]) where {N}
+  ti64 = Array{Float64}(TI)
+  u = permutedims(U)                       # library layout: [nreal][npath], row-major
+  auxs = [Array{Float32}(a) for a in aux]
+  auxptr = [pointer(a) for a in auxs]
+  status = Ref{Int32}(0)
+  GC.@preserve ti64 u auxs auxptr outs begin
+    desc = SimDesc(pad3(padsize), pad3(ovlsize), length(outs), pointer(ti64), pointer(u), length(steps), tol, 0,
+                   isempty(auxs) ? Ptr{Ptr{Float32}}(C_NULL) : pointer(auxptr))
+    check(ccall((:iq_sim_begin, lib), Int32, (Ptr{Cvoid}, Ref{SimDesc}), ctx.handle, desc))
+    for (k, (start0, ovlmask, slabs)) in enumerate(steps)
+      st = Int64[start0...]; mask = Array{UInt8}(vec(ovlmask))
+      check(ccall((:iq_sim_step, lib), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}, Ptr{SimSlab}, Int32),
+                  ctx.handle, k - 1, st, mask, slabs, length(slabs)))
+    end
+    check(ccall((:iq_sim_sync, lib), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ref{Int32}), ctx.handle, C_NULL, status))
+    if status[] == 0
+      crop = Int64[pad3(size(outs[1]))...]
+      ptrs = [Ptr{Cvoid}(pointer(o)) for o in outs]
+      check(ccall((:iq_sim_fetch_all, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Int32),
+                  ctx.handle, 1, crop, ptrs, 0))
+    end
+    check(ccall((:iq_sim_end, lib), Int32, (Ptr{Cvoid},), ctx.handle))
+  end
+  status[]
+end
+
 end # module
