@@ -814,9 +814,8 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
   __shared__ int s_active, s_pass, s_last;
   __shared__ unsigned long long s_prefix, s_mask;
   const int tid = threadIdx.x;
-  for (int q = 0; q < 1; ++q) {
+  {
     SelJob* J = jobs + blockIdx.y;
-    __syncthreads();  // previous job's shared state fully consumed
     if (tid == 0) {
       s_active = J->active;
       s_pass = J->pass;
@@ -825,7 +824,7 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
     }
     h[tid] = 0;
     __syncthreads();
-    if (!s_active) continue;
+    if (!s_active) return;
     const int shift = shifts[s_pass];
     const unsigned long long prefix = s_prefix, mask = s_mask;
     const float* __restrict__ map = J->map;
@@ -851,7 +850,7 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (!s_last) continue;
+    if (!s_last) return;
     if (tid == 0) {
       __threadfence();
       volatile unsigned* gh = J->hist;
@@ -888,9 +887,9 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
 // Gathers the keys that match the decided prefix of every job marked by the second pass (compact == 2) into its
 // scratch list (order is irrelevant: keys are unique) and switches the job to list mode (compact = 1).
 __global__ void __launch_bounds__(256) k_select_compact(SelJob* jobs, int njobs, long long npos) {
- for (int q = 0; q < 1; ++q) {
+ {
   SelJob* J = jobs + blockIdx.y;
-  if (!J->active || J->compact != 2) continue;
+  if (!J->active || J->compact != 2) return;
   const unsigned long long prefix = J->prefix, mask = J->mask;
   const float* __restrict__ map = J->map;
   unsigned long long* __restrict__ cbuf = J->cbuf;
