@@ -45,7 +45,7 @@ class IqCutTask(C.Structure):
 class IqSimDesc(C.Structure):
     _fields_ = [("pad_size", C.c_int64 * 3), ("ovl_size", C.c_int64 * 3), ("nreal", C.c_int32), ("ti64", c_double_p),
                 ("u", c_double_p), ("npath", C.c_int64), ("tol", C.c_double), ("debug", C.c_int32),
-                ("aux", C.POINTER(c_float_p))]
+                ("aux", C.POINTER(c_float_p)), ("hard_has", c_u8_p), ("hard_val", c_float_p)]
 
 
 class IqSimSlab(C.Structure):
@@ -94,7 +94,7 @@ SYMBOLS = {
     "iq_sample": (C.c_int32, [c_double_p, C.c_int64, C.c_double, c_i64_p]),
     "iq_cut_batch": (C.c_int32, [C.c_void_p, C.POINTER(IqCutTask), C.c_int32, c_i32_p]),
     "iq_sim_begin": (C.c_int32, [C.c_void_p, C.POINTER(IqSimDesc)]),
-    "iq_sim_step": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32]),
+    "iq_sim_step": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32, C.c_int32]),
     "iq_sim_step_picked": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_i64_p]),
     "iq_sim_sync": (C.c_int32, [C.c_void_p, c_i64_p, c_i32_p]),
     "iq_sim_fetch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_i64_p, C.c_void_p]),

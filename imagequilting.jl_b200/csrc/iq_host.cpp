@@ -189,7 +189,6 @@ void tile_slabs(const Geo& G, const std::vector<uint8_t>& pasted, int64_t ind, s
 int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats,
                  int* status) {
   *status = 0;
-  if (D->hard_has) return IQ_ERR_STATE;  // hard data: relaxation with the sparse hard distance, host-staged only
   const int S = D->nsoft;
   if (D->pipeline == 0) {
     // Integer-valued (categorical) images make the cut capacities of graphcut.jl:52 degenerate (division by eps next
@@ -240,6 +239,8 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     sd.tol = D->tol;
     sd.debug = D->debug;
     sd.aux = S ? D->aux : nullptr;
+    sd.hard_has = D->hard_has;
+    sd.hard_val = D->hard_has ? D->hard_val : nullptr;
     rc = iq_sim_begin(g.ctx, &sd);
   }
   if (rc != IQ_OK) { destroy_all(); return rc; }
@@ -265,7 +266,17 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
       for (int i = 0; i < 3; ++i) { sl[k].lo[i] = slabs[k].lo[i]; sl[k].sz[i] = slabs[k].sz[i]; }
     }
     const int64_t st64[3] = {start[0], start[1], start[2]};
-    const bool host_pick = S > 0 && slabs.empty();
+    // does the tile contain hard data?  (indicator!, utils.jl:31-36: the same for every realization)
+    bool hard_tile = false;
+    if (D->hard_has) {
+      for (int z = 0; z < G.t[2] && !hard_tile; ++z)
+        for (int y = 0; y < G.t[1] && !hard_tile; ++y) {
+          const uint8_t* row = D->hard_has + ((long long)(start[2] + z) * G.pad[1] + (start[1] + y)) * G.pad[0] + start[0];
+          for (int x = 0; x < G.t[0]; ++x)
+            if (row[x]) { hard_tile = true; break; }
+        }
+    }
+    const bool host_pick = S > 0 && slabs.empty() && !hard_tile;
     if (host_pick) {
       // Soft data and nothing pasted around the tile: the candidate set is a tenth of all patterns (relaxation.jl:11,20),
       // far above the device tau model.  One search (the tile is the same for every realization), the sampling walk
@@ -297,7 +308,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
         }
         if (rc == IQ_OK) rc = iq_sim_step_picked(g.ctx, step, st64, pk.data());
       } else {
-        rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size());
+        rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size(), hard_tile ? 1 : 0);
       }
       if (rc != IQ_OK) break;
       double dms = 0;

@@ -60,6 +60,13 @@ struct SimState {
   double* d_soft_plane = nullptr;    // [tz]
   unsigned* d_soft_ticket = nullptr;
   iq::PickJob* d_pickjobs = nullptr; // [R] selection jobs of the simulation (the context's own array serves iq_search)
+  // hard data (tiles that contain data: hard distance primary, overlap distance first auxiliary; iqsim.jl:230-231)
+  uint8_t* d_hard_has = nullptr;     // [padvol]
+  float* d_hard_val = nullptr;       // [padvol]
+  int* d_hard_ptr = nullptr;         // [2] CSR row of the step's tile
+  long long* d_hard_off = nullptr;   // [tilevol] image offsets of the data voxels relative to the patch origin
+  float* d_hard_list = nullptr;      // [tilevol] their values
+  iq::PickJob* d_pickjobs_hard = nullptr;  // [R] selection jobs of hard tiles
   int* d_pending = nullptr;          // [R] relaxation: realization still without candidates (next round needed)
   double* d_cutA = nullptr;
   double* d_cutB = nullptr;
@@ -249,8 +256,9 @@ __global__ void __launch_bounds__(128) k_sim_sample(const iq::PickJob* __restric
 // whose k equals realization 0's only copies its thresholds (k_sim_copykth).  One block per realization, one thread
 // per source.
 __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* __restrict__ pick, int maxS,
-                              const unsigned* __restrict__ maxbits, double tol, long long npatterns, long long npos,
-                              int round, int* __restrict__ pending, unsigned long long* __restrict__ selbuf, unsigned selcap) {
+                              const unsigned* __restrict__ maxbits, int maxbits_stride, unsigned shared_mask, double tol,
+                              long long npatterns, long long npos, int round, int* __restrict__ pending,
+                              unsigned long long* __restrict__ selbuf, unsigned selcap) {
   const int r = blockIdx.x, s = threadIdx.x;
   if (s >= maxS) return;
   if (round > 0 && pending[r] == 0) return;  // candidates found: its jobs stay finished
@@ -262,7 +270,7 @@ __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* 
   for (int i = 0; i < 256; ++i) J.hist[i] = 0;
   if (s == 0 && round == 0) pending[r] = 1;
   if (s >= P.nsrc) return;
-  const bool allzero = maxbits[r] == 0u, allzero0 = maxbits[0] == 0u;
+  const bool allzero = maxbits[(long long)r * maxbits_stride] == 0u, allzero0 = maxbits[0] == 0u;
   const long long dbsize = allzero ? npatterns : (long long)ceil(__dmul_rn(tol, (double)npatterns));
   double frac = __dmul_rn(0.1, __ddiv_rn((double)dbsize, (double)npatterns));
   for (int j = 0; j < round; ++j) frac = fmin(__dadd_rn(frac, 0.1), 1.0);  // relaxation.jl:35, once per empty round
@@ -271,9 +279,10 @@ __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* 
   k = max(1ll, min(k, npos));
   J.map = P.src[s];
   J.k = (unsigned long long)k;
-  // shared auxiliary map and the same k as realization 0, which runs its selection in this round: copy afterwards.
-  // (k depends on the all-zero flag and the round only; pending[] is not written during rounds > 0.)
-  const bool same_as_first = s > 0 && r > 0 && allzero == allzero0 && (round == 0 || pending[0] != 0);
+  // map shared by all realizations (bit s of shared_mask) and the same k as realization 0, which runs its selection
+  // in this round: copy afterwards.  (k depends on the all-zero flag and the round only; pending[] is not written
+  // during rounds > 0.)
+  const bool same_as_first = ((shared_mask >> s) & 1u) && r > 0 && allzero == allzero0 && (round == 0 || pending[0] != 0);
   J.active = same_as_first ? 0 : 1;
   J.ticket = same_as_first ? 0xffffffffu : 0u;  // marker read by k_sim_copykth
 }
@@ -281,7 +290,7 @@ __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* 
 // Thresholds of the shared auxiliary maps for the realizations that did not run their own selection.
 __global__ void k_sim_copykth(iq::SelJob* __restrict__ jobs, int maxS) {
   const int r = blockIdx.x, s = threadIdx.x;
-  if (r == 0 || s == 0 || s >= maxS) return;
+  if (r == 0 || s >= maxS) return;
   iq::SelJob& J = jobs[(long long)r * maxS + s];
   if (J.ticket != 0xffffffffu) return;
   J.kth = jobs[s].kth;
@@ -295,6 +304,46 @@ __global__ void k_sim_relax_check(const iq::PickJob* __restrict__ pick, int R, i
   if (r >= R || pending[r] == 0) return;
   if (*pick[r].total > 0u) pending[r] = 0;
   else if (last) atomicOr(status, 4);  // still empty after the rounds run on the device
+}
+
+// Hard data of the step's tile (indicator! / event!, utils.jl:18-36) as the sparse list k_dist_sparse consumes, in
+// ascending tile offset (the order the host driver builds it in: the FP32 accumulation order of the distance).
+__global__ void __launch_bounds__(256) k_sim_hardlist(const uint8_t* __restrict__ has, const float* __restrict__ val, int p0,
+                                                      int p1, int sx, int sy, int sz, int tx, int ty, int tz, int nx, int ny,
+                                                      int* __restrict__ ptr, long long* __restrict__ off,
+                                                      float* __restrict__ list) {
+  __shared__ unsigned s_w[8];
+  __shared__ unsigned s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tv = tx * ty * tz;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < tv; q0 += 256) {
+    const int q = q0 + tid;
+    bool hit = false;
+    long long gi = 0;
+    int qx = 0, qy = 0, qz = 0;
+    if (q < tv) {
+      qx = q % tx; const int qt = q / tx; qy = qt % ty; qz = qt / ty;
+      gi = ((long long)(sz + qz) * p1 + (sy + qy)) * p0 + sx + qx;
+      hit = has[gi] != 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    unsigned before = 0, all = 0;
+    for (int w = 0; w < 8; ++w) { const unsigned c = s_w[w]; if (w < warp) before += c; all += c; }
+    const unsigned base = s_base;
+    if (hit) {
+      const unsigned slot = base + before + __popc(bal & ((1u << lane) - 1u));
+      off[slot] = ((long long)qz * ny + qy) * nx + qx;
+      list[slot] = val[gi];
+    }
+    __syncthreads();
+    if (tid == 0) s_base = base + all;
+    __syncthreads();
+  }
+  if (tid == 0) { ptr[0] = 0; ptr[1] = (int)s_base; }
 }
 
 __global__ void k_sim_store_picks(const long long* __restrict__ picked, long long* __restrict__ picks, long long npath,
@@ -383,6 +432,8 @@ void sim_destroy(iq_ctx* c) {
   for (auto p : s->d_aux_pad) cudaFree(p);
   cudaFree(s->d_soft_tmpl); cudaFree(s->d_soft_b2); cudaFree(s->d_soft_plane); cudaFree(s->d_soft_ticket);
   cudaFree(s->d_pickjobs); cudaFree(s->d_pending);
+  cudaFree(s->d_hard_has); cudaFree(s->d_hard_val); cudaFree(s->d_hard_ptr); cudaFree(s->d_hard_off);
+  cudaFree(s->d_hard_list); cudaFree(s->d_pickjobs_hard);
   if (s->h_pickstage) cudaFreeHost(s->h_pickstage);
   for (int i = 0; i < 2; ++i) {
     if (s->h_export[i]) cudaFreeHost(s->h_export[i]);
@@ -533,6 +584,39 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     J.chunkmin = c->d_chunkmin + (size_t)r * c->chunk_stride;
   }
   CK(cudaMemcpyAsync(s->d_pickjobs, c->h_pick, R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+  if (d->hard_has) {
+    if (!d->hard_val) return fail(IQ_ERR_INVALID, "iq_sim_begin: hard_has without hard_val");
+    CK(cudaStreamSynchronize(c->stream));  // h_pick is rewritten below
+    CK(iq::dmalloc((void**)&s->d_hard_has, (size_t)s->padvol));
+    CK(iq::dmalloc((void**)&s->d_hard_val, (size_t)s->padvol * sizeof(float)));
+    CK(cudaMemcpyAsync(s->d_hard_has, d->hard_has, (size_t)s->padvol, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(s->d_hard_val, d->hard_val, (size_t)s->padvol * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(iq::dmalloc((void**)&s->d_hard_ptr, 2 * sizeof(int)));
+    CK(iq::dmalloc((void**)&s->d_hard_off, (size_t)c->tilevol * sizeof(long long)));
+    CK(iq::dmalloc((void**)&s->d_hard_list, (size_t)c->tilevol * sizeof(float)));
+    CK(iq::dmalloc((void**)&s->d_pickjobs_hard, R * sizeof(iq::PickJob)));
+    if (!s->d_pending) CK(iq::dmalloc((void**)&s->d_pending, R * sizeof(int)));
+    // hard tiles: sources = [hard distance (one map for all realizations), overlap distance, soft maps...]
+    for (int r = 0; r < s->R; ++r) {
+      iq::PickJob& J = c->h_pick[r];
+      std::memset(&J, 0, sizeof J);
+      J.mode = 1;
+      J.nsrc = 2 + s->S;
+      J.src[0] = c->d_Dhard;
+      J.src[1] = c->d_Dovl + (size_t)r * c->npos;
+      for (int i = 0; i < s->S; ++i) J.src[2 + i] = c->d_Dsoft[i];
+      J.pending = s->d_pending + r;
+      J.sel = c->d_sel + (size_t)r * c->max_src;
+      J.tol = s->tol;
+      J.minbits = c->d_minmax + (size_t)(1 * 2 + 0) * c->max_batch;
+      J.blockcount = c->d_blockcount + (size_t)r * iq::pick_nblk(c->npos);
+      J.total = c->d_total + r;
+      J.cand_idx = c->d_cand_idx + (size_t)r * c->npos;
+      J.cand_val = c->d_cand_val + (size_t)r * c->max_src * c->npos;
+      J.cap = c->npos;
+    }
+    CK(cudaMemcpyAsync(s->d_pickjobs_hard, c->h_pick, R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+  }
   CK(cudaEventCreate(&s->ev_begin));
   CK(cudaEventCreate(&s->ev_end));
   CK(cudaStreamSynchronize(c->stream));
@@ -544,11 +628,13 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
 }
 
 int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
-                    int32_t nslab) {
+                    int32_t nslab, int32_t hard_tile) {
   if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step: no simulation open on this context");
   SimState* s = c->sim;
   if (!start || !ovlmask || nslab < 0 || nslab > 6 || (nslab > 0 && !slabs)) return fail(IQ_ERR_INVALID, "iq_sim_step: bad argument");
   if (step < 0 || step >= s->npath) return fail(IQ_ERR_INVALID, "iq_sim_step: step out of range");
+  if (hard_tile && !s->d_hard_has) return fail(IQ_ERR_INVALID, "iq_sim_step: hard_tile on a simulation opened without hard data");
+  const bool hardt = hard_tile != 0;
   CK(cudaSetDevice(c->device));
   const int t[3] = {c->tx, c->ty, c->tz};
   int st3[3] = {0, 0, 0};
@@ -592,7 +678,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
   if (nslab > s->maxslabs) return fail(IQ_ERR_INVALID, "iq_sim_step: too many slabs");
 
   const unsigned gR = (unsigned)((R + 127) / 128);
-  if (e->nnz == 0 && s->S == 0) {
+  if (e->nnz == 0 && s->S == 0 && !hardt) {
     // nothing pasted around the tile: every enabled patch with equal probability (iqsim.jl:237 on an all-zero map);
     // the walk is evaluated on the host from the cached cumulative weights
     rc = build_uniform(c);
@@ -612,7 +698,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
     c->launches++;
   } else {
     for (int kind = 0; kind < 2 + s->S; ++kind) {
-      if (kind == 1) continue;  // hard distance: not part of resident simulations
+      if (kind == 1 && !hardt) continue;
       CK(iq::launch_fill_u32(c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch, 0x7f800000u, c->max_batch, c->stream));
       CK(iq::launch_fill_u32(c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch, 0u, c->max_batch, c->stream));
       c->launches += 2;
@@ -660,6 +746,26 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       rc = direct(e, -1, s->d_tmpl, s->d_b2, R, c->d_Dovl, 0);
       if (rc) return rc;
     }
+    // hard-data distance (iqsim.jl:210-219): the data are the same for every realization -> one map per step
+    if (hardt) {
+      k_sim_hardlist<<<1, 256, 0, c->stream>>>(s->d_hard_has, s->d_hard_val, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], c->tx,
+                                               c->ty, c->tz, c->nx, c->ny, s->d_hard_ptr, s->d_hard_off, s->d_hard_list);
+      CK(cudaGetLastError());
+      iq::SparseParams sp{};
+      sp.img = c->d_ti;
+      sp.nx = c->nx; sp.ny = c->ny; sp.nz = c->nz; sp.nxo = c->nxo; sp.nyo = c->nyo; sp.nzo = c->nzo;
+      sp.npos = c->npos;
+      sp.ptr = s->d_hard_ptr;
+      sp.off = s->d_hard_off;
+      sp.val = s->d_hard_list;
+      sp.disabled = c->d_disabled;
+      sp.out = c->d_Dhard;
+      sp.minbits = c->d_minmax + (size_t)(1 * 2 + 0) * c->max_batch;
+      sp.maxbits = c->d_minmax + (size_t)(1 * 2 + 1) * c->max_batch;
+      sp.R = 1;
+      CK(iq::launch_dist_sparse(sp, c->stream));
+      c->launches += 2;
+    }
     // soft-data distances (iqsim.jl:222-227): the auxiliary tile is the same for every realization -> one map per step
     for (int si = 0; si < s->S; ++si) {
       k_sim_templates<float><<<dim3((unsigned)c->tz, 1u), 256, 0, c->stream>>>(
@@ -684,19 +790,29 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       }
     }
     CK(cudaEventRecord(ev[0], c->stream));
-    if (s->S == 0) {
+    iq::PickJob* pj = hardt ? s->d_pickjobs_hard : s->d_pickjobs;
+    if (s->S == 0 && !hardt) {
       rc = ensure_chunkmin(c, R);
       if (rc) return rc;
-      CK(iq::launch_pick_chunks(s->d_pickjobs, R, c->npos, c->chunk_len, c->chunk_n, c->stream));
+      CK(iq::launch_pick_chunks(pj, R, c->npos, c->chunk_len, c->chunk_n, c->stream));
       c->launches += 1;
     } else {
+      // sources shared by all realizations: the hard map (source 0 of a hard tile) and every soft map
+      const int nsrc = 1 + (hardt ? 1 : 0) + s->S;
+      unsigned shared_mask = 0;
+      for (int i = 0; i < nsrc; ++i)
+        if (hardt ? (i != 1) : (i != 0)) shared_mask |= 1u << i;
+      const unsigned* pmax = hardt ? c->d_minmax + (size_t)(1 * 2 + 1) * c->max_batch : c->d_minmax + (size_t)c->max_batch;
+      const int pmax_stride = hardt ? 0 : 1;
       // relaxation rounds on the device: kRelaxRounds rounds are enqueued unconditionally, the kernels of a round
       // return at once for realizations that already have candidates; a realization still empty after the last
       // round raises the status word (the caller then reruns host-staged, where the round count is unbounded)
-      constexpr int kRelaxRounds = 3;
+      // (3 rounds normally; tiles with hard data or an empty overlap mask often need many -- an all-zero overlap map
+      // selects an index prefix -- and get all 11, after which frac = 1 guarantees a non-empty intersection)
+      const int kRelaxRounds = (hardt || e->nnz == 0) ? 11 : 3;
       for (int round = 0; round < kRelaxRounds; ++round) {
-        k_sim_seljobs<<<R, 32, 0, c->stream>>>(c->d_sel, s->d_pickjobs, c->max_src, c->d_minmax + (size_t)c->max_batch, s->tol,
-                                              c->nenabled, c->npos, round, s->d_pending, c->d_selbuf, c->sel_cap);
+        k_sim_seljobs<<<R, 32, 0, c->stream>>>(c->d_sel, pj, c->max_src, pmax, pmax_stride, shared_mask, s->tol, c->nenabled,
+                                              c->npos, round, s->d_pending, c->d_selbuf, c->sel_cap);
         CK(cudaGetLastError());
         {
           int nl = 0;
@@ -705,16 +821,16 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
         }
         k_sim_copykth<<<R, 32, 0, c->stream>>>(c->d_sel, c->max_src);
         CK(cudaGetLastError());
-        CK(iq::launch_pick_count(s->d_pickjobs, R, c->npos, c->stream));
-        k_sim_relax_check<<<gR, 128, 0, c->stream>>>(s->d_pickjobs, R, s->d_pending, round == kRelaxRounds - 1 ? 1 : 0, s->d_status);
+        CK(iq::launch_pick_count(pj, R, c->npos, c->stream));
+        k_sim_relax_check<<<gR, 128, 0, c->stream>>>(pj, R, s->d_pending, round == kRelaxRounds - 1 ? 1 : 0, s->d_status);
         CK(cudaGetLastError());
         c->launches += 4;
       }
-      CK(iq::launch_pick_write(s->d_pickjobs, R, c->npos, c->stream));
+      CK(iq::launch_pick_write(pj, R, c->npos, c->stream));
       c->launches += 1;
     }
-    CK(iq::launch_tau(s->d_pickjobs, R, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
-    k_sim_sample<<<(unsigned)((R + 3) / 4), 128, 0, c->stream>>>(s->d_pickjobs, c->d_prob, s->d_u, s->npath, step, R,
+    CK(iq::launch_tau(pj, R, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
+    k_sim_sample<<<(unsigned)((R + 3) / 4), 128, 0, c->stream>>>(pj, c->d_prob, s->d_u, s->npath, step, R,
                                                                  s->d_picked, s->d_picks, s->d_status);
     CK(cudaGetLastError());
     c->launches += 3;

@@ -158,10 +158,10 @@ int32_t iq_cut_batch(iq_ctx* ctx, const iq_cut_task* tasks, int32_t ntask, int32
  *     template gather from the grids (iqsim.jl:185) -> overlap distance (utils.jl:5-13) -> threshold selection
  *     (iqsim.jl:237) -> tau model (taumodel.jl:5-45) -> StatsBase.sample walk with the pre-drawn uniform
  *     (iqsim.jl:243) -> boundary cuts (graphcut.jl:5-84, device kernel of iq_cut_batch) -> paste (iqsim.jl:278).
- * Scope: no hard data; overlap slabs that fit the shared-memory cut kernel (iq_sim_begin returns IQ_ERR_STATE
- * otherwise and the caller uses iq_search_pick + its own paste instead).  With soft data every step runs the first
- * relaxation round (src/relaxation.jl:5-39: radix select of the dbsize / softk smallest keys per source, intersection)
- * on the device.  Steps whose overlap mask is empty on a context with soft data (their candidate set is a tenth of
+ * Scope: overlap slabs that fit the shared-memory cut kernel (iq_sim_begin returns IQ_ERR_STATE otherwise and the
+ * caller uses iq_search_pick + its own paste instead).  With soft data, and on tiles with hard data, every step runs
+ * up to three relaxation rounds (src/relaxation.jl:5-39: radix select of the dbsize / softk smallest keys per source,
+ * intersection) on the device.  Steps whose overlap mask is empty on a context with soft data (their candidate set is a tenth of
  * all patterns, far above the device tau model's 32 768 entries) are done by the caller through iq_search +
  * iq_sample and handed over with iq_sim_step_picked.
  * A data-dependent condition the device path does not cover (a candidate set of more than 32 768 entries on a
@@ -180,6 +180,9 @@ typedef struct iq_sim_desc {
   int32_t debug;         /* nonzero: also keep the boundary-cut grids (src/iqsim.jl:281) */
   const float* const* aux; /* contexts with soft data: ctx.nsoft padded auxiliary grids (pad_size floats each,
                               symmetric-padded, NaN -> 0; src/utils.jl:74-89), else NULL */
+  const uint8_t* hard_has; /* hard data (src/utils.jl:18-36): pad_size bytes, nonzero = voxel carries a non-NaN datum;
+                              NULL = no hard data */
+  const float* hard_val;   /* pad_size floats: the datum where hard_has */
 } iq_sim_desc;
 typedef struct iq_sim_slab {   /* one overlap slab of the current tile, in tile coordinates */
   int32_t dim;           /* dimension of the overlap */
@@ -188,9 +191,11 @@ typedef struct iq_sim_slab {   /* one overlap slab of the current tile, in tile 
 } iq_sim_slab;
 int32_t iq_sim_begin(iq_ctx* ctx, const iq_sim_desc* desc);
 /* Enqueues one path step for all realizations: tile origin `start` (0-based voxel coordinates in the padded grid),
- * the overlap mask of the step and the slabs whose union it is (nslab may be 0: nothing pasted around the tile). */
+ * the overlap mask of the step and the slabs whose union it is (nslab may be 0: nothing pasted around the tile).
+ * hard_tile != 0: the tile contains hard data (the caller knows: it owns the grids it passed to iq_sim_begin); the
+ * hard distance then is the primary source and the overlap distance the first auxiliary one (src/iqsim.jl:230-231). */
 int32_t iq_sim_step(iq_ctx* ctx, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
-                    int32_t nslab);
+                    int32_t nslab, int32_t hard_tile);
 /* A step whose patterns the caller chose itself (picks[r] = 0-based linear index of the pattern of realization r):
  * the whole tile is pasted (no pasted neighbour, hence no cut).  Used for empty-mask steps of soft-data simulations. */
 int32_t iq_sim_step_picked(iq_ctx* ctx, int64_t step, const int64_t* start, const int64_t* picks);

@@ -116,6 +116,8 @@ struct SimDesc          # == iq_sim_desc
   tol::Float64
   debug::Int32
   aux::Ptr{Ptr{Float32}}
+  hard_has::Ptr{UInt8}
+  hard_val::Ptr{Float32}
 end
 
 struct SimSlab          # == iq_sim_slab (tile coordinates, 0-based)
@@ -144,12 +146,12 @@ function simulate!(outs::Vector{<:Array{Float32}}, ctx::Context, TI::AbstractArr
   status = Ref{Int32}(0)
   GC.@preserve ti64 u auxs auxptr outs begin
     desc = SimDesc(pad3(padsize), pad3(ovlsize), length(outs), pointer(ti64), pointer(u), length(steps), tol, 0,
-                   isempty(auxs) ? Ptr{Ptr{Float32}}(C_NULL) : pointer(auxptr))
+                   isempty(auxs) ? Ptr{Ptr{Float32}}(C_NULL) : pointer(auxptr), Ptr{UInt8}(C_NULL), Ptr{Float32}(C_NULL))
     check(ccall((:iq_sim_begin, lib), Int32, (Ptr{Cvoid}, Ref{SimDesc}), ctx.handle, desc))
     for (k, (start0, ovlmask, slabs)) in enumerate(steps)
       st = Int64[start0...]; mask = Array{UInt8}(vec(ovlmask))
-      check(ccall((:iq_sim_step, lib), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}, Ptr{SimSlab}, Int32),
-                  ctx.handle, k - 1, st, mask, slabs, length(slabs)))
+      check(ccall((:iq_sim_step, lib), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}, Ptr{SimSlab}, Int32, Int32),
+                  ctx.handle, k - 1, st, mask, slabs, length(slabs), 0))
     end
     check(ccall((:iq_sim_sync, lib), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ref{Int32}), ctx.handle, C_NULL, status))
     if status[] == 0

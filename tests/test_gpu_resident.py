@@ -70,15 +70,40 @@ def test_resident_config1_matches_oracle():
         assert g.dtype == w.dtype and np.array_equal(g, w)
 
 
-def test_resident_refuses_hard_data_and_auto_falls_back():
+def test_resident_auto_keeps_categorical_images_host_staged():
+    """pipeline="auto": integer-valued images stay on the host-staged pipeline (host Boykov-Kolmogorov cuts: their cut
+    capacities are degenerate and the cut depends on the max-flow algorithm's rounding)."""
     cfg = synth.config(3, scale=0.4)
-    ti = cfg["trainimg"]
-    hard = cfg["kwargs"]["hard"]
-    with pytest.raises(_lib.IqError):
-        iqb200.iqsim(ti, cfg["tilesize"], nreal=1, hard=hard, pipeline="resident", rng=np.random.default_rng(0))
-    out, ex = iqb200.iqsim(ti, cfg["tilesize"], nreal=1, hard=hard, pipeline="auto", rng=np.random.default_rng(0),
-                           return_stats=True)
-    assert ex["stats"]["resident"] == 0 and out[0].shape == ti.shape
+    out, ex = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=1, hard=cfg["kwargs"]["hard"], pipeline="auto",
+                           rng=np.random.default_rng(0), return_stats=True)
+    assert ex["stats"]["resident"] == 0 and out[0].shape == cfg["trainimg"].shape
+
+
+def _hard_from(field, n, seed):
+    r = np.random.default_rng(seed)
+    flat = r.choice(field.size, size=n, replace=False)
+    coords = np.array(np.unravel_index(flat, field.shape)).T
+    return {tuple(int(v) for v in c): float(field[tuple(c)]) for c in coords}
+
+
+@pytest.mark.parametrize("with_soft", [False, True])
+def test_resident_hard_data_equals_staged(with_soft):
+    """Hard data on a continuous image: data-first dilation path, sparse hard distance as the primary source on tiles
+    that contain data, relaxation rounds on the device; realizations honour the data."""
+    ti = synth.gaussian_field((48, 40, 20), (6, 6, 3), 9)
+    other = synth.gaussian_field((48, 40, 20), (6, 6, 3), 12)
+    hard = _hard_from(other, 30, 1)
+    hard[(2, 3, 1)] = float("nan")
+    kw = dict(nreal=3, overlap=(0.25, 0.25, 0.25), hard=hard)
+    if with_soft:
+        auxti = np.asfortranarray(synth.box_mean(ti, (5, 5, 3)).astype(np.float32))
+        aux = np.asfortranarray(synth.box_mean(other, (5, 5, 3)).astype(np.float32))
+        kw["soft"] = [(aux, auxti)]
+    a, ea, b, eb = both(ti, (16, 12, 8), 11, **kw)
+    same(a, ea, b, eb)
+    for real in b:
+        for coord, val in hard.items():
+            assert (np.isnan(real[coord]) and np.isnan(val)) or real[coord] == np.float32(val)
 
 
 @pytest.mark.parametrize("fft", [-1, 1])
