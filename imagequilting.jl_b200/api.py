@@ -339,6 +339,38 @@ def voxelreuse(trainimg, tilesize, *, overlap=None, nreal=10, **kwargs):
     return mu, sigma
 
 
+def voxelreuse_sweep(trainimg, *, tmin=None, tmax=None, overlap=None, nreal=10, rng=None, **kwargs):
+    """The data behind `voxelreuseplot` (ext/ImageQuiltingMakieExt.jl:23-80) without the Makie recipe: mean voxel reuse
+    and its standard deviation for every template size tmin..tmax (cubic tiles along the non-singleton dimensions),
+    and the range [t-, t+] spanned by the five best sizes (the dashed lines of the plot).
+
+    As in the reference (`:46`) every size is evaluated with overlap 1/6 per dimension; the `overlap` attribute is
+    accepted for signature compatibility.  Returns dict(ts, mu, sigma, best=(t-, t+))."""
+    timg = trainimg if isinstance(trainimg, np.ma.MaskedArray) else np.asarray(trainimg)
+    dims = timg.shape
+    idx = [d > 1 for d in dims]
+    if tmin is None:
+        tmin = 7
+    if tmax is None:
+        tmax = min(100, min(d for d, i in zip(dims, idx) if i))
+    if not tmin > 0:
+        raise ValueError("`tmin` must be positive")
+    if not tmin < tmax:
+        raise ValueError("`tmin` must be smaller than `tmax`")
+    rng = np.random.default_rng() if rng is None else rng
+    N = timg.ndim
+    ts = list(range(int(tmin), int(tmax) + 1))
+    mus, sigmas = [], []
+    for tsz in ts:
+        tilesize = tuple(tsz if i else 1 for i in idx)
+        mu, sigma = voxelreuse(timg, tilesize, overlap=(1.0 / 6.0,) * N, nreal=nreal, rng=rng, **kwargs)
+        mus.append(mu)
+        sigmas.append(sigma)
+    rank = np.argsort(-np.asarray(mus), kind="stable")
+    best = [ts[i] for i in rank[:min(5, len(ts))]]
+    return dict(ts=np.asarray(ts), mu=np.asarray(mus), sigma=np.asarray(sigmas), best=(min(best), max(best)))
+
+
 def graphcut(A, B, dim):
     """Boundary cut keep-mask through the native host routine (src/graphcut.jl:5-84)."""
     A = _f(A, np.float64)

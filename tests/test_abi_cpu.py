@@ -99,3 +99,13 @@ def test_uniform_stream_matches_scalar_draws():
     g = np.random.default_rng(5)
     b = np.array([g.random() for _ in range(7)])
     assert np.array_equal(a, b)
+
+
+def test_voxelreuse_sweep_argument_checks():
+    """tminmax of the reference's plot recipe (ext/ImageQuiltingMakieExt.jl:62-80): same defaults and errors."""
+    import iqb200
+    ti = np.zeros((20, 30))
+    with pytest.raises(ValueError, match="`tmin` must be positive"):
+        iqb200.voxelreuse_sweep(ti, tmin=0, tmax=5)
+    with pytest.raises(ValueError, match="`tmin` must be smaller than `tmax`"):
+        iqb200.voxelreuse_sweep(ti, tmin=9, tmax=9)

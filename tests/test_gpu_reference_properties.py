@@ -98,3 +98,18 @@ def test_assertions_match_reference_messages():  # src/iqsim.jl:69-89
         ss = kwargs.pop("simsize", None)
         with pytest.raises(AssertionError, match=msg.replace("(", r"\(").replace(")", r"\)").replace("]", r"\]")):
             iqb200.iqsim(TI, ts, ss, **kwargs)
+
+
+def test_voxelreuse_sweep_matches_single_calls():
+    """The sweep behind voxelreuseplot (ext/ImageQuiltingMakieExt.jl:41-58) is one voxelreuse call per template size
+    on a shared RNG stream, cubic tiles along the non-singleton dimensions, five best sizes -> [t-, t+]."""
+    from iqb200 import synth
+    ti = synth.gaussian_field((40, 36, 1), (5, 5, 1), 3)
+    out = iqb200.voxelreuse_sweep(ti, tmin=7, tmax=12, nreal=2, rng=np.random.default_rng(5))
+    r = np.random.default_rng(5)
+    want = [iqb200.voxelreuse(ti, (t, t, 1), overlap=(1 / 6,) * 3, nreal=2, rng=r) for t in range(7, 13)]
+    assert out["ts"].tolist() == list(range(7, 13))
+    assert np.allclose(out["mu"], [w[0] for w in want]) and np.allclose(out["sigma"], [w[1] for w in want])
+    assert np.all((out["mu"] >= 0) & (out["mu"] <= 1))
+    order = np.argsort(-out["mu"], kind="stable")[:5]
+    assert out["best"] == (int(out["ts"][order].min()), int(out["ts"][order].max()))
