@@ -315,7 +315,7 @@ struct StridedArgs {
                                        // store loop runs element-fastest (transposed output for the fused z/y kernel)
 };
 template <int LOG2N, int MODE>
-__global__ void __launch_bounds__(kThreads) k_fft_strided(const StridedArgs A) {
+__global__ void __launch_bounds__(kThreads, 5) k_fft_strided(const StridedArgs A) {
   constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
   extern __shared__ __align__(16) float2 sm[];
   float2* b0 = sm;
