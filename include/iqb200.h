@@ -12,7 +12,9 @@
  *         taumodel src/taumodel.jl:5-45
  * What stays with the caller: RNG and sampling (src/iqsim.jl:243) unless the caller asks
  * for a fused pick and supplies the uniform itself; the boundary cut (src/graphcut.jl) and
- * the paste (src/iqsim.jl:251-278).
+ * the paste (src/iqsim.jl:251-278) -- unless the caller opts into the device-resident
+ * simulation (iq_sim_*, below), which keeps the grids of all realizations on the device and
+ * runs sampling (pre-drawn uniforms), cut and paste there as well.
  *
  * Conventions
  *   - All arrays are column-major (Julia layout, first index fastest), densely packed.
