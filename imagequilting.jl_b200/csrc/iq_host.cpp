@@ -202,8 +202,9 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   }
   const auto t_start = clk::now();
   const int R = D->nreal;
-  // one lockstep group: a launch already carries every realization (FFT pairs, one cut CTA per slab), and a second
-  // stream only makes the kernels of the two groups fight for the same SMs (measured: 8-10 % slower on config 5)
+  // one lockstep group by default: a launch already carries every realization (FFT pairs, one cut CTA per slab).
+  // Several groups (streams) overlap one group's cut tail with another's FFT passes: -10 % device time with 4 groups
+  // of 16 on config 5, at the price of per-kernel timings that no longer describe a kernel alone.
   int ngroups = D->ngroups > 0 ? D->ngroups : 1;
   ngroups = std::max(1, std::min(ngroups, R));
   struct RG { iq_ctx* ctx = nullptr; int r0 = 0, R = 0; };
