@@ -577,6 +577,11 @@ def sample(prob, u):
     return pos.value
 
 
+def release_device_memory(device=0):
+    """Return the library's cached (currently unused) device memory on `device` to the driver."""
+    check(lib().iq_release_device_memory(int(device)))
+
+
 def fma_peak(device=0, packed=False):
     """Measured FP32 FMA rate of the device in TFMA/s (iq_bench_fma_peak / iq_bench_fma2_peak)."""
     out = C.c_double()

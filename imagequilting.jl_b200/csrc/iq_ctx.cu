@@ -1477,6 +1477,20 @@ static int32_t bench_fma_impl(int32_t device, int packed, double* tfma) {
   return IQ_OK;
 }
 
+int32_t iq_release_device_memory(int32_t device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(IQ_ERR_NO_DEVICE, "no such CUDA device");
+  }
+  CK(cudaSetDevice(device));
+  CK(cudaDeviceSynchronize());
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, device));
+  CK(cudaMemPoolTrimTo(pool, 0));
+  return IQ_OK;
+}
+
 int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return fail(IQ_ERR_INVALID, "NULL argument");
   if (std::strcmp(key, "rb") == 0) {

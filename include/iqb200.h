@@ -234,6 +234,11 @@ int32_t iq_bench_fma_peak(int32_t device, double* tfma_per_s);
 /* Same with the packed fma.rn.f32x2 instruction (two FMAs per issue slot on sm_100). */
 int32_t iq_bench_fma2_peak(int32_t device, double* tfma_per_s);
 
+/* Device buffers are taken from the device's stream-ordered memory pool with the release threshold lifted, so the
+ * memory of a destroyed context / finished simulation is reused by the next one instead of going back to the driver.
+ * iq_release_device_memory returns everything that is currently unused on `device` to the driver. */
+int32_t iq_release_device_memory(int32_t device);
+
 /* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 0 = auto,
  * 1, 2, 4), "variant" (0 flat kernel, 1 tiled, 2 packed-FMA), "fft" (-1 never, 0 auto crossover, 1 always). */
 int32_t iq_ctx_set_option(iq_ctx* ctx, const char* key, int64_t value);

@@ -123,3 +123,13 @@ def test_full_size_config5_realization_is_a_quilt_of_training_values():
         assert a.shape == cfg["trainimg"].shape and a.dtype == np.float32
         assert np.isin(a, vals).all()
     assert ex["stats"]["fft_searches"] > 0 and ex["stats"]["searches"] == 2 * 512
+
+
+def test_release_device_memory_keeps_results_reproducible():
+    """The pooled device allocations can be handed back to the driver between simulations."""
+    from iqb200 import api
+    cfg = synth.config(2, scale=0.25)
+    a = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=2, rng=np.random.default_rng(1))
+    api.release_device_memory(0)
+    b = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=2, rng=np.random.default_rng(1))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
