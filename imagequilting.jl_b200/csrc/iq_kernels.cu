@@ -841,8 +841,13 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
         const unsigned long long key = comp ? cbuf[i] : make_key(map[i], i);
         if ((key & mask) == prefix) bin = (unsigned)(key >> shift) & 255u;
       }
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+      if (s_pass == 0) {
+        // first digit (sign + high exponent bits): nearly every key falls into one or two bins -- aggregate per warp
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+      } else if (bin != 0xffffffffu) {
+        atomicAdd(&h[bin], 1u);  // later digits spread over the bins: plain shared-memory atomics are cheaper than the vote
+      }
     }
     __syncthreads();
     if (h[tid]) atomicAdd(&J->hist[tid], h[tid]);
@@ -958,8 +963,11 @@ int pick_nblk(long long npos) { return (int)((npos + kPickChunk - 1) / kPickChun
 
 __device__ __forceinline__ bool pick_pred(const PickJob& J, long long p, double thr) {
   if (J.mode == 0) return (double)J.src[0][p] <= thr;
+  // most selective source first: the auxiliary sets hold a tenth of the primary one (relaxation.jl:20-22), and the
+  // auxiliary maps of a resident simulation are shared by all realizations (L2 hits) -- the per-realization primary
+  // map is then read only where the auxiliary tests pass
   bool ok = true;
-  for (int s = 0; s < J.nsrc; ++s) ok = ok && (make_key(J.src[s][p], p) <= J.sel[s].kth);
+  for (int s = J.nsrc - 1; s >= 0 && ok; --s) ok = make_key(J.src[s][p], p) <= J.sel[s].kth;
   return ok;
 }
 
