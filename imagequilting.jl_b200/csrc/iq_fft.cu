@@ -144,6 +144,13 @@ __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst,
     const float2* xb = src + line * LS;
     float2* yb = dst + line * LS;
     float2 v[R];
+    // Padded index of input j: e_j = (q + s p) + NBR j with q + s p < NBR = N / R.  When NBR is a multiple of 16 the
+    // padding term grows by exactly NBR / 16 per j, so PI(e_j) = PI(q + s p) + (NBR + NBR / 16) j: one add, and the
+    // j-dependent part folds into the load's immediate offset (the profile showed the index arithmetic of these passes
+    // next to the butterflies in instruction count).
+    constexpr int NBR = N / R;
+    constexpr bool kInLinear = (NBR % 16) == 0;
+    const int pin = PI(q + s * p);
     if (live) {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
@@ -151,7 +158,7 @@ __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst,
         if (LIN == 1) v[j] = src[line * N + e];
         else if (LIN == 2) v[j] = src[e * LPBC + line];
         else {
-          const int i = PI(e);
+          const int i = kInLinear ? pin + (NBR + NBR / 16) * j : PI(e);
           v[j] = xb[i];
           if (MUL) v[j] = cmul(v[j], spec[line * LS + i]);
         }
@@ -179,8 +186,20 @@ __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst,
 #pragma unroll
       for (int k = 1; k < R; ++k) v[k] = cmul(v[k], w[k]);
     }
+    // outputs k: e_k = (q + s R p) + s k.  s a multiple of 16: PI grows by s + s / 16 per k; s = 1 with R = 16: the base
+    // is a multiple of 16 and k < 16, so PI(e_k) = PI(base) + k.
+    const int pout = PI(q + s * R * p);
+    if ((s & 15) == 0) {
+      const int os = s + (s >> 4);
 #pragma unroll
-    for (int k = 0; k < R; ++k) yb[PI(q + s * (R * p + k))] = v[k];
+      for (int k = 0; k < R; ++k) yb[pout + os * k] = v[k];
+    } else if (s == 1 && R == 16) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) yb[pout + k] = v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) yb[PI(q + s * (R * p + k))] = v[k];
+    }
   }
   __syncthreads();
 }
@@ -539,28 +558,29 @@ __device__ __forceinline__ void final_epilogue(const FinalArgs& A, const float2*
   // one x column per thread, walked down the lines of the tile: no index division, unit-stride pointers (the profile
   // of the first version showed this epilogue, not the transform, saturating the integer pipe)
   const bool rnd = A.ep.round_to_int != 0;
+  // uniform 64-bit bases + one 32-bit position per thread (npos < 2^32): the loads / stores use base + u32 addressing
+  // instead of a 64-bit add per pointer and line
+  const float* __restrict__ a2b = A.ep.a2;
+  const uint8_t* __restrict__ disb = A.ep.disabled;
+  float* __restrict__ o0b = A.ep.out + (long long)r0 * A.npos;
+  float* __restrict__ o1b = A.ep.out + (long long)r1 * A.npos;
   for (int x = threadIdx.x; x < A.nxo; x += kThreads) {
     const float2* rp = res + PI(x);
-    long long p = (long long)l0 * A.nxo + x;
-    const float* a2p = A.ep.a2 ? A.ep.a2 + p : nullptr;
-    const uint8_t* dp = A.ep.disabled ? A.ep.disabled + p : nullptr;
-    float* o0 = A.ep.out + (long long)r0 * A.npos + p;
-    float* o1 = A.ep.out + (long long)r1 * A.npos + p;
+    unsigned p = (unsigned)((long long)l0 * A.nxo + x);
 #pragma unroll 2
-    for (int line = 0; line < nl; ++line) {
+    for (int line = 0; line < nl; ++line, p += (unsigned)A.nxo) {
       float2 ab = rp[line * LS];
       if (rnd) { ab.x = rintf(ab.x); ab.y = rintf(ab.y); }
-      const long long off = (long long)line * A.nxo;
-      const double a2 = a2p ? (double)__ldg(a2p + off) : 0.0;
-      const bool dis = dp && dp[off];
+      const double a2 = a2b ? (double)__ldg(a2b + p) : 0.0;
+      const bool dis = disb && disb[p];
       float d0 = (float)fabs(a2 - 2.0 * (double)ab.x + b20);
       if (dis) d0 = CUDART_INF_F;
-      o0[off] = d0;
+      o0b[p] = d0;
       if (!dis) { const unsigned u = __float_as_uint(d0); mn0 = min(mn0, u); mx0 = max(mx0, u); }
       if (has1) {
         float d1 = (float)fabs(a2 - 2.0 * (double)ab.y + b21);
         if (dis) d1 = CUDART_INF_F;
-        o1[off] = d1;
+        o1b[p] = d1;
         if (!dis) { const unsigned u = __float_as_uint(d1); mn1 = min(mn1, u); mx1 = max(mx1, u); }
       }
     }
