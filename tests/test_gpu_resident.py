@@ -136,3 +136,14 @@ def test_resident_many_realizations_groups():
     b = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=6, rng=np.random.default_rng(2), pipeline="resident", ngroups=3)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_resident_soft_data_random_path():
+    """Random path with soft data: many tiles have no pasted neighbour (empty overlap mask) and go through
+    iq_search + iq_sample on the host, interleaved with device steps on the same context."""
+    ti = synth.gaussian_field((72, 60), (6, 6), 14)
+    auxti = np.asfortranarray(synth.box_mean(ti, (7, 7)).astype(np.float32))
+    tgt = synth.gaussian_field((72, 60), (6, 6), 15)
+    aux = np.asfortranarray(synth.box_mean(tgt, (7, 7)).astype(np.float32))
+    a, ea, b, eb = both(ti, (18, 15), 9, nreal=3, path="random", soft=[(aux, auxti)])
+    same(a, ea, b, eb)
