@@ -108,6 +108,7 @@ SYMBOLS = {
     "iq_bench_fma_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "iq_bench_fma2_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "iq_release_device_memory": (C.c_int32, [C.c_int32]),
+    "iq_device_free_memory": (C.c_int32, [C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "iq_ctx_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
     "iqh_run": (C.c_int32, [C.POINTER(IqhDesc), c_double_p, c_u8_p, c_i64_p, C.POINTER(IqhStats)]),
     "iqh_graphcut": (C.c_int32, [c_double_p, c_double_p, C.c_int32, c_i64_p, C.c_int32, c_u8_p]),

@@ -1491,6 +1491,27 @@ int32_t iq_release_device_memory(int32_t device) {
   return IQ_OK;
 }
 
+int32_t iq_device_free_memory(int32_t device, size_t* free_bytes, size_t* total_bytes) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(IQ_ERR_NO_DEVICE, "no such CUDA device");
+  }
+  CK(cudaSetDevice(device));
+  size_t f = 0, t = 0;
+  CK(cudaMemGetInfo(&f, &t));
+  // memory parked in the pool is handed out again by iq::dmalloc: count it as free
+  cudaMemPool_t pool;
+  unsigned long long reserved = 0, used = 0;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess &&
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+    f += (size_t)(reserved - used);
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return IQ_OK;
+}
+
 int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return fail(IQ_ERR_INVALID, "NULL argument");
   if (std::strcmp(key, "rb") == 0) {

@@ -17,6 +17,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -384,6 +385,53 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   return IQ_OK;
 }
 
+// Realizations are independent, so a simulation whose resident state would not fit in device memory is run as
+// consecutive waves of at most `rmax` realizations (each wave a complete run_resident on its rows of the uniform
+// stream).  rmax comes from the free device memory and a per-realization estimate (FP64 grid, distance maps,
+// candidate lists, FFT work space, cut slabs); IQB200_MAX_RESIDENT_REAL overrides it (tests).
+int run_resident_waves(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats,
+                       int* status) {
+  const int R = D->nreal;
+  const double npos = (double)G.dist[0] * G.dist[1] * G.dist[2];
+  auto p2 = [](int n) { double v = 1; while (v < n) v *= 2; return v; };
+  const double fftws = 8.0 * p2(G.n[0]) * ((double)G.t[2] * G.t[1] + (G.n[2] > 1 ? (double)G.t[2] * p2(G.n[1]) + 2.0 * G.dist[2] * p2(G.n[1]) : 0.0) +
+                                            (double)G.dist[2] * G.dist[1]) / 2.0;  // per template (two per transform)
+  const double per_real = 8.0 * G.padvol * (D->debug ? 1.125 : 1.0) + npos * 4.0 * (2.0 + 1.0 + (2.0 + D->nsoft)) +
+                          npos / 16.0 * 8.0 * (2.0 + D->nsoft) + fftws + 6.0 * 17.0 * G.tilevol;
+  size_t free_b = 0, total_b = 0;
+  int rmax = R;
+  if (iq_device_free_memory(D->device, &free_b, &total_b) == IQ_OK && per_real > 0)
+    rmax = (int)std::max(1.0, std::min((double)R, 0.7 * (double)free_b / per_real));
+  if (const char* ev = std::getenv("IQB200_MAX_RESIDENT_REAL")) rmax = std::max(1, std::min(R, std::atoi(ev)));
+  if (rmax >= R) return run_resident(D, G, out_grids, out_cuts, out_picks, stats, status);
+  iqh_stats acc{};
+  *status = 0;
+  for (int r0 = 0; r0 < R; r0 += rmax) {
+    const int n = std::min(rmax, R - r0);
+    iqh_desc sub = *D;
+    sub.nreal = n;
+    sub.u = D->u + (size_t)r0 * D->npath;
+    sub.out_real = D->out_real ? D->out_real + r0 : nullptr;
+    iqh_stats st{};
+    int wst = 0;
+    const int rc = run_resident(&sub, G, out_grids ? out_grids + (size_t)r0 * G.padvol : nullptr,
+                                out_cuts ? out_cuts + (size_t)r0 * G.padvol : nullptr,
+                                out_picks ? out_picks + (size_t)r0 * D->npath : nullptr, &st, &wst);
+    if (rc != IQ_OK) return rc;
+    *status |= wst;
+    if (wst) return IQ_OK;  // the caller redoes everything host-staged
+    acc.resident = 1;
+    acc.search_ms += st.search_ms; acc.search_device_ms += st.search_device_ms; acc.total_ms += st.total_ms;
+    acc.searches += st.searches; acc.kernel_launches += st.kernel_launches; acc.setup_ms += st.setup_ms;
+    acc.dist_kernel_ms += st.dist_kernel_ms; acc.dist_launches += st.dist_launches; acc.fft_searches += st.fft_searches;
+    acc.direct_searches += st.direct_searches; acc.fft_bytes += st.fft_bytes; acc.fft_ms += st.fft_ms;
+    acc.device_ms += st.device_ms; acc.select_ms += st.select_ms; acc.cut_device_ms += st.cut_device_ms;
+    acc.fetch_ms += st.fetch_ms;
+  }
+  if (stats) *stats = acc;
+  return IQ_OK;
+}
+
 }  // namespace
 
 extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats) {
@@ -412,7 +460,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
 
   int resident_status = 0;
   if (D->pipeline != 1) {
-    const int rcr = run_resident(D, G, out_grids, out_cuts, out_picks, stats, &resident_status);
+    const int rcr = run_resident_waves(D, G, out_grids, out_cuts, out_picks, stats, &resident_status);
     if (rcr == IQ_OK && resident_status == 0) return IQ_OK;
     if (rcr != IQ_OK && !(rcr == IQ_ERR_STATE && D->pipeline == 0)) return rcr;  // explicit request or a real error
     // otherwise: does not qualify (or a data-dependent bail-out): host-staged below, still on the GPU

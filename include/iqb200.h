@@ -35,6 +35,7 @@
 #ifndef IQB200_H
 #define IQB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -238,6 +239,8 @@ int32_t iq_bench_fma2_peak(int32_t device, double* tfma_per_s);
  * memory of a destroyed context / finished simulation is reused by the next one instead of going back to the driver.
  * iq_release_device_memory returns everything that is currently unused on `device` to the driver. */
 int32_t iq_release_device_memory(int32_t device);
+/* Free / total memory of `device` in bytes (cudaMemGetInfo), counting the library's cached pool memory as free. */
+int32_t iq_device_free_memory(int32_t device, size_t* free_bytes, size_t* total_bytes);
 
 /* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 0 = auto,
  * 1, 2, 4), "variant" (0 flat kernel, 1 tiled, 2 packed-FMA), "fft" (-1 never, 0 auto crossover, 1 always). */

@@ -147,3 +147,18 @@ def test_resident_soft_data_random_path():
     aux = np.asfortranarray(synth.box_mean(tgt, (7, 7)).astype(np.float32))
     a, ea, b, eb = both(ti, (18, 15), 9, nreal=3, path="random", soft=[(aux, auxti)])
     same(a, ea, b, eb)
+
+
+def test_resident_waves_when_memory_is_short(monkeypatch):
+    """More realizations than fit on the device at once are simulated in consecutive waves (rows of the uniform
+    stream), with the same result; IQB200_MAX_RESIDENT_REAL forces the situation."""
+    cfg = synth.config(2, scale=0.25)
+    a, ea = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=5, rng=np.random.default_rng(3), pipeline="resident",
+                         return_picks=True, return_stats=True)
+    monkeypatch.setenv("IQB200_MAX_RESIDENT_REAL", "2")
+    b, eb = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=5, rng=np.random.default_rng(3), pipeline="resident",
+                         return_picks=True, return_stats=True)
+    assert eb["stats"]["resident"] == 1 and np.array_equal(ea["picks"], eb["picks"])
+    assert eb["stats"]["searches"] == ea["stats"]["searches"]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
