@@ -1,21 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- iqsim voxels/s on the BASELINE.json configs, one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 5] [--nreal-per-gpu 8]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 5] [--scaling auto|strong|weak]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...   # the CPU restatement of the reference on the host cores
 
-A "step" is one complete iqsim call (all tiles of `nreal-per-gpu` realizations on every rank) on the
-synthetic training image of the chosen config (default: config 5, the 250x250x100 volume the scaling
-target is quoted on).  Realizations are sharded over ranks with no data-path collective (weak scaling:
-fixed realizations per GPU; the default 64 per GPU makes N = 1 exactly BASELINE config 5, nreal = 64).
+A "step" is one complete iqsim call on the synthetic training image of the chosen config (default: config 5, the
+250x250x100 volume with nreal = 64 the scaling target is quoted on).  Realizations are sharded over ranks with no
+data-path collective.  Scaling mode: "strong" (default for N > 1) keeps BASELINE's nreal = 64 in TOTAL, 64/N per rank,
+every rank taking its rows of the one shared uniform stream -- the union of the shards is exactly the N = 1 job;
+"weak" keeps --nreal-per-gpu realizations on every rank.  N = 1 is config 5 as BASELINE.json states it either way.
 
   value  = voxels/s with the training image already resident in HBM (context set-up excluded; on the
            device-resident pipeline the realizations are left in HBM, their export is part of e2e)
   e2e    = voxels/s of the public call iqb200.iqsim(host arrays) -> host arrays, everything included
-  roofline: FP32-FMA roofline of the dominant kernel k_dist_boxes (algorithmic FMAs = nnz(mask) x npos per
-            tile search) against the FFMA rate measured on this GPU by iq_bench_fma_peak;
-            the HBM term (algorithmic bytes / measured copy bandwidth) is reported next to it.
+  roofline: the dominant distance path of the run.  FFT passes: HBM roofline, `achieved` = ALGORITHMIC bytes of
+            SURVEY.md 8(d) (image + cached spectrum once per launch, one distance map + template per search) over the
+            CUDA-event time of the passes; the passes' own multi-pass traffic over the same time is reported beside it
+            as `dram_utilisation`.  Direct kernel k_dist_flat: FP32-FMA roofline (nnz(mask) x npos FMAs per search)
+            against the FFMA rate measured in the run by iq_bench_fma_peak.
 """
 from __future__ import annotations
 
@@ -152,22 +155,28 @@ def algorithmic_work(geo, path):
     return total_nnz * npos, npos, nsearch
 
 
-def cpu_sample(cfg, max_tiles, workers):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_sample(cfg, ntiles, workers):
     """Bounded sample of the restated reference (SciPy FFT form, FP64, per-tile recomputation exactly as
-    src/utils.jl:5-13 does) on the host cores.  The boundary cut is replaced by a no-op so that only the
-    hot path is timed -- this favours the CPU figure."""
+    src/utils.jl:5-13 does; relaxation / tau model / sampling on the host; boundary cut by the C restatement of
+    src/graphcut.jl) on the host cores: the first `ntiles` visited tiles of realization 1 (and on into the next
+    realizations when ntiles exceeds one path).  Returns the wall-clock stamp after every tile."""
     from oracle import iq_oracle as O
     kw = dict(cfg["kwargs"])
-    kw["nreal"] = 1
     geo = O.geometry(cfg["trainimg"].shape, cfg["tilesize"], None, kw.get("overlap"))
     nt = int(np.prod(geo["ntiles"]))
-    max_tiles = min(max_tiles, nt)
-    t0 = time.perf_counter()
+    kw["nreal"] = max(1, -(-ntiles // nt))
+    stamps = [time.perf_counter()]
     O.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(0), method="fft", workers=workers,
-            cut_fn=lambda A, B, d: np.ones(A.shape, dtype=bool), max_tiles=max_tiles, **kw)
-    dt = time.perf_counter() - t0
-    vox = float(np.prod(geo["simsize"], dtype=np.float64)) * max_tiles / nt
-    return vox / dt, dt, max_tiles, nt
+            cut_fn=O.graphcut_c, max_tiles=ntiles, on_tile=lambda n: stamps.append(time.perf_counter()), **kw)
+    vox_per_tile = float(np.prod(geo["simsize"], dtype=np.float64)) / nt
+    return np.array(stamps), vox_per_tile, nt
 
 
 def main():
@@ -177,7 +186,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=5)
-    ap.add_argument("--nreal-per-gpu", type=int, default=64)
+    ap.add_argument("--nreal-per-gpu", type=int, default=0, help="weak scaling: realizations per rank (default 64)")
+    ap.add_argument("--nreal", type=int, default=0, help="strong scaling: realizations in total (default: the config's, 64 on config 5)")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"])
     ap.add_argument("--pipeline", default="auto", choices=["auto", "staged", "resident"])
     ap.add_argument("--ngroups", type=int, default=0)
     ap.add_argument("--cpu-tiles", type=int, default=0, help="tiles in the CPU sample (0 = auto)")
@@ -190,33 +201,52 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    ncores = os.cpu_count() or 1
+    ncores = host_cores()
 
     from iqb200 import synth
     cfg = synth.config(args.config)
     ti, tilesize = cfg["trainimg"], cfg["tilesize"]
     kw = dict(cfg["kwargs"])
-    kw["nreal"] = args.nreal_per_gpu
-    workload = f"{cfg['name'].split(' nreal')[0]}; {args.nreal_per_gpu} realizations per GPU"
-    cpu_tiles = args.cpu_tiles or {1: 16, 2: 169, 3: 120, 4: 24, 5: 24}[args.config]
+    # scaling mode and realization counts
+    scaling = args.scaling
+    if scaling == "auto":
+        scaling = "weak" if (args.nreal_per_gpu > 0 or world == 1) else "strong"
+    if scaling == "strong":
+        nreal_total = args.nreal or int(kw.get("nreal", 1))
+        r0, r1 = nreal_total * rank // world, nreal_total * (rank + 1) // world
+    else:
+        per = args.nreal_per_gpu or args.nreal or int(kw.get("nreal", 1))
+        nreal_total = per * world
+        r0, r1 = per * rank, per * (rank + 1)
+    nreal_local = r1 - r0
+    kw["nreal"] = nreal_total
+    workload = (f"{cfg['name'].split(' nreal')[0]}; nreal = {nreal_total} in total"
+                + (f", {nreal_total // world if scaling == 'strong' else nreal_local} per GPU ({scaling} scaling)" if world > 1 else ""))
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        for _ in range(max(args.warmup, 0)):
-            cpu_sample(cfg, max(2, cpu_tiles // 4), ncores)
-        vals, dts = [], []
-        for _ in range(args.steps):
-            v, dt, mt, nt = cpu_sample(cfg, cpu_tiles, ncores)
-            vals.append(v)
-            dts.append(dt)
-        value = float(np.sum([v * d for v, d in zip(vals, dts)]) / np.sum(dts))
-        sample = (f"first {mt} of {nt} tiles of 1 realization per step, SciPy-FFT restatement of src/utils.jl:5-13 + "
-                  f"src/imfilter.jl:5-7 (FP64, workers={ncores}), selection+taumodel on host, boundary cut skipped; not Julia")
+        # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the restatement's parallelism is SciPy's own
+        # FFT worker pool (the reference: FFTW threads = physical cores, src/iqsim.jl:66) + the OpenMP C pieces
+        os.environ["OMP_NUM_THREADS"] = str(ncores)
+        tiles_per_step = args.cpu_tiles or {1: 16, 2: 169, 3: 40, 4: 12, 5: 22}[args.config]
+        W, K = max(args.warmup, 0), max(args.steps, 1)
+        stamps, vox_per_tile, nt = cpu_sample(cfg, (W + K) * tiles_per_step, ncores)
+        ntile = len(stamps) - 1
+        K = min(K, max(1, ntile // tiles_per_step - W))
+        t0 = stamps[W * tiles_per_step]
+        t1 = stamps[min((W + K) * tiles_per_step, ntile)]
+        done = min((W + K) * tiles_per_step, ntile) - W * tiles_per_step
+        value = done * vox_per_tile / (t1 - t0)
+        sample = (f"{tiles_per_step} consecutive tiles per step, {W} warm-up + {K} timed steps walking on through the path "
+                  f"({done} of {nt} tiles of a realization timed); SciPy-FFT restatement of src/utils.jl:5-13 + "
+                  f"src/imfilter.jl:5-7 in FP64 with workers={ncores}, selection / tau model / sampling on the host, boundary cut "
+                  f"by the C restatement of src/graphcut.jl (included); voxels/s = timed tiles x (simsize voxels / tiles per "
+                  f"realization) / time; not Julia")
         line = {"impl": "reference", "metric": "iqsim voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "steps": K, "warmup": W, "ms_per_step": 1e3 * (t1 - t0) / K, "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload},
                 "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": ncores, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -248,12 +278,15 @@ def main():
     # host threads per rank: cut/paste pool of the host-staged pipeline (which leaves the GPU-driving thread and the clock
     # sampler a core), export threads of the device-resident one (the driving thread is idle by then)
     nthreads = max(1, ncores // max(world, 1) - (2 if args.pipeline == "staged" else 0))
-    seed0 = 1234 + 1000 * rank
+    seed0 = 1234
 
     def step(i):
+        # every rank draws the same path and the same nreal_total x nvisited uniforms from the same seed and simulates
+        # rows r0:r1 of that stream (sharding.py): the union of the ranks' realizations is the single-GPU job
         t0 = time.perf_counter()
-        out, ex = iqb200.iqsim(ti, tilesize, rng=np.random.default_rng(seed0 + i), device=local, nthreads=nthreads, fft=args.fft, cut=args.cut,
-                               pipeline=args.pipeline, ngroups=args.ngroups, return_stats=True, return_picks=True, **kw)
+        out, ex = iqb200.iqsim(ti, tilesize, rng=np.random.default_rng(seed0 + i), device=local, nthreads=nthreads, fft=args.fft,
+                               cut=args.cut, pipeline=args.pipeline, ngroups=args.ngroups, return_stats=True, return_picks=True,
+                               _real_range=(r0, r1), **kw)
         chk = float(sum(float(r[0, 0, 0] if r.ndim == 3 else r[0, 0]) for r in out))  # touch the result on the host
         return time.perf_counter() - t0, ex, chk
 
@@ -273,7 +306,8 @@ def main():
     clocks = sampler.stop() if sampler is not None else None
 
     geo = stats[0]["stats"]["geo"]
-    vox_per_step = float(np.prod(geo["simsize"], dtype=np.float64)) * args.nreal_per_gpu
+    simvox = float(np.prod(geo["simsize"], dtype=np.float64))
+    vox_per_step = simvox * nreal_total          # whole job, all ranks
     # `value`: inputs already in HBM (context set-up / uploads excluded) and, on the device-resident pipeline, results
     # left in HBM (the export to host arrays is part of e2e only)
     resident_s = sum((s["stats"]["total_ms"] - s["stats"]["setup_ms"] - s["stats"]["fetch_ms"]) for s in stats) / 1e3
@@ -289,20 +323,18 @@ def main():
     fma_per_real, npos, nsearch = algorithmic_work(geo, stats[0]["path"])
     dist_ms = sum(s["stats"]["dist_kernel_ms"] for s in stats)
     dist_launches = sum(s["stats"]["dist_launches"] for s in stats)
-    fma_total = fma_per_real * args.nreal_per_gpu * args.steps
+    fma_total = fma_per_real * nreal_local * args.steps
     achieved_tfma = fma_total / (dist_ms * 1e-3) / 1e12 if dist_ms > 0 else 0.0
     peaks, peak_kind = measured_peaks()
     nti = int(ti.size)
-    # algorithmic bytes per launch: image once + R distance maps written + templates (mask voxels x 2 x 4 B)
-    bytes_total = args.steps * nsearch * (4.0 * nti + args.nreal_per_gpu * 4.0 * npos) + 8.0 * fma_total / max(npos, 1)
-    achieved_gbs = bytes_total / (dist_ms * 1e-3) / 1e9 if dist_ms > 0 else 0.0
+    mean_nnz = fma_per_real / max(npos, 1) / max(nsearch, 1)
     is_resident = all(s["stats"]["resident"] for s in stats)
-    out_bytes = float(np.prod(geo["simsize"], dtype=np.float64)) * args.nreal_per_gpu * ti.dtype.itemsize
+    out_bytes = simvox * nreal_local * ti.dtype.itemsize
     npath = len(stats[0]["path"])
     if is_resident:
         # uploads: FP32 + FP64 training image and the uniforms; downloads: the cropped realizations and the picks
-        h2d = nti * 12.0 + args.nreal_per_gpu * npath * 8.0
-        d2h = out_bytes + args.nreal_per_gpu * npath * 8.0
+        h2d = nti * 12.0 + nreal_local * npath * 8.0
+        d2h = out_bytes + nreal_local * npath * 8.0
     else:
         h2d = sum(s["stats"]["searches"] for s in stats) / args.steps * float(np.prod(tilesize)) * 4.0 + nti * 4.0
         d2h = sum(s["stats"]["candidates"] for s in stats) / args.steps * 8.0
@@ -312,53 +344,62 @@ def main():
     nfft = sum(s["stats"]["fft_searches"] for s in stats)
     ndirect = sum(s["stats"]["direct_searches"] for s in stats)
     direct_ms = max(dist_ms - fft_ms, 0.0)
+    hbm = float(peaks.get("hbm_gbs", 1.0))
+    # SURVEY 8(d) bytes of the direct kernel: image once per launch + R distance maps + templates
+    b_direct = args.steps * nsearch * (4.0 * nti + nreal_local * (4.0 * npos + 8.0 * mean_nnz))
     fma_roof = {"bound": "fp32_fma", "achieved": 2 * achieved_tfma, "peak": 2 * fma_peak, "unit": "TFLOP/s",
-                "frac": achieved_tfma / fma_peak if fma_peak else None, "traffic": 129.1e6,
+                "frac": achieved_tfma / fma_peak if fma_peak else None, "traffic": None,
                 "kernel": "k_dist_flat", "launches": int(dist_launches), "kernel_ms_total": dist_ms,
                 "peak_source": "iq_bench_fma_peak measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
-                "traffic_note": "dram read+write per launch from profiles/r01_k_dist_flat_ncu.txt (8 templates, config 5)",
-                "hbm_term": {"achieved_gbs": achieved_gbs, "peak_gbs": peaks.get("hbm_gbs"), "of": peak_kind,
-                             "frac": achieved_gbs / peaks.get("hbm_gbs", 1.0)}}
+                "algorithmic": "F = nnz(mask) x npos FMAs per search (SURVEY 8(d)), AB term only: the sum of P^2 comes from the table",
+                "hbm_term": {"achieved_gbs": b_direct / (dist_ms * 1e-3) / 1e9 if dist_ms > 0 else 0.0, "peak_gbs": hbm,
+                             "of": peak_kind, "frac": (b_direct / (dist_ms * 1e-3) / 1e9 / hbm) if dist_ms > 0 else 0.0}}
     if fft_ms > direct_ms:
-        # the FFT passes dominate: byte-bound roofline, algorithmic bytes from iqfft::correlate_bytes
-        gbs = fft_bytes / (fft_ms * 1e-3) / 1e9
-        # direct-equivalent FMA rate of the same searches (reported, NOT used for `achieved`)
-        eq_tfma = fma_total * (nfft / max(nfft + ndirect, 1)) / (fft_ms * 1e-3) / 1e12
-        roof = {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                "frac": gbs / peaks.get("hbm_gbs", 1.0), "of": peak_kind, "traffic": None,
-                "kernel": "FFT correlation passes (k_fft_x_tmpl, k_fft_strided<fwd|fused|inv>, k_fft_x_final)",
-                "kernel_ms_total": fft_ms, "searches_fft": int(nfft), "searches_direct": int(ndirect),
-                "bytes_per_search": fft_bytes / max(nfft, 1), "direct_equivalent_tfma": eq_tfma,
-                "note": "achieved = bytes the pruned passes must move (iqfft::correlate_bytes, DESIGN.md section 3) / CUDA-event "
-                        "time of the passes on the launching stream; the image spectrum is served from L2"}
-        # SURVEY 8(d) accounting of the same searches: image once per launch + one distance map per search + the
-        # template/mask (+ one read of the cached spectrum per launch), independent of how the correlation is computed
-        launches_fft = max(nfft / max(args.nreal_per_gpu, 1), 1.0)
-        mean_nnz = fma_per_real / max(npos, 1) / max(nsearch, 1)
+        # The FFT passes dominate: byte-bound.  `achieved` uses the ALGORITHMIC bytes of SURVEY 8(d): per launch of R
+        # searches the image and its cached spectrum once, per search one distance map written and the template + mask
+        # read -- the floor any method has to move -- over the CUDA-event time of the passes on the launching stream.
+        per_launch = stats[0]["stats"].get("searches_per_launch", 0) or nreal_local
+        launches_fft = max(nfft / max(per_launch, 1), 1.0)
         spec_bytes = 8.0 * float(np.prod([1 << int(np.ceil(np.log2(max(v, 1)))) for v in ti.shape[:2]])) * (ti.shape[2] if ti.ndim == 3 else 1)
         b8d = launches_fft * (4.0 * nti + spec_bytes) + nfft * (4.0 * npos + 8.0 * mean_nnz)
-        roof["survey_8d"] = {"bytes_per_search": b8d / max(nfft, 1), "achieved_gbs": b8d / (fft_ms * 1e-3) / 1e9,
-                             "frac": b8d / (fft_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 1.0),
-                             "note": "B_alg(R) = 4|TI| + spectrum + R(4 npos + 8 nnz) per launch of R searches: the floor any "
-                                     "method must move; the FFT method's own traffic is `bytes_per_search`"}
-        # traffic: DRAM bytes of the passes per launch of 64 searches, from the committed ncu launch list
-        roof["traffic"] = 6.72e9 if args.config == 5 and args.nreal_per_gpu == 64 else None
-        roof["traffic_note"] = ("dram__bytes_read+write summed over the five FFT passes of one step (64 searches), "
-                                "profiles/r01_launches_resident.csv; algorithmic bytes of the same launch: 64 x bytes_per_search")
+        gbs8d = b8d / (fft_ms * 1e-3) / 1e9
+        gbs_own = fft_bytes / (fft_ms * 1e-3) / 1e9
+        eq_tfma = fma_total * (nfft / max(nfft + ndirect, 1)) / (fft_ms * 1e-3) / 1e12
+        prof = os.path.join(ROOT, "profiles", "r02_launches_resident.csv")
+        traffic, traffic_note = None, "no committed ncu launch list for this configuration"
+        meta = os.path.join(ROOT, "profiles", "r02_fft_traffic.json")
+        if os.path.exists(meta) and args.config == 5:
+            try:
+                with open(meta) as f:
+                    tm = json.load(f)
+                traffic, traffic_note = tm["dram_bytes_per_launch"], tm["note"]
+            except Exception:
+                pass
+        roof = {"bound": "hbm", "achieved": gbs8d, "peak": hbm, "unit": "GB/s", "frac": gbs8d / hbm, "of": peak_kind,
+                "traffic": traffic, "traffic_note": traffic_note,
+                "kernel": "FFT correlation passes (k_fft_x_tmpl, k_fft_strided<fwd>, k_fft_zdirect / fused, k_fft_strided<inv>, k_fft_x_final)",
+                "kernel_ms_total": fft_ms, "searches_fft": int(nfft), "searches_direct": int(ndirect),
+                "algorithmic_bytes_per_search": b8d / max(nfft, 1), "searches_per_launch": per_launch,
+                "algorithmic": "B_alg(R) = 4|TI| + cached spectrum + R (4 npos + 8 nnz) per launch of R searches (SURVEY 8(d))",
+                "dram_utilisation": {"bytes_per_search": fft_bytes / max(nfft, 1), "achieved_gbs": gbs_own, "frac": gbs_own / hbm,
+                                     "note": "the passes' OWN multi-pass traffic (iqfft::correlate_bytes) over the same time: how "
+                                             "busy the memory system is, not a roofline fraction"},
+                "direct_equivalent_tfma": eq_tfma}
         if direct_ms > 0 and ndirect > 0:
             roof["direct_kernel_ms_total"] = direct_ms
     else:
         roof = fma_roof
 
     line = {
-        "metric": "iqsim voxels/sec", "value": world * vox_per_step * args.steps / resident_max, "unit": "voxels/s",
+        "metric": "iqsim voxels/sec", "value": vox_per_step * args.steps / resident_max, "unit": "voxels/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "tilesize": list(tilesize), "trainimg": list(ti.shape),
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "tilesize": list(tilesize), "trainimg": list(ti.shape), "nreal_total": nreal_total,
+                   "nreal_per_gpu": nreal_local,
                    "l2": "whole-job steps: every search reads fresh templates and writes R x npos distance maps (> L2 at "
                          "R >= 8 on config 5); the training image / its spectrum stay L2-resident by design, no flush applies",
                    "host_threads_per_rank": nthreads, "host_cores": ncores, "distance_path": {-1: "direct", 0: "auto", 1: "fft"}[args.fft]},
-        "e2e": {"value": world * vox_per_step * args.steps / t_total_max, "unit": "voxels/s",
+        "e2e": {"value": vox_per_step * args.steps / t_total_max, "unit": "voxels/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(sum(s["stats"]["kernel_launches"] for s in stats)),
         "roofline": roof,
@@ -369,10 +410,15 @@ def main():
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
-        v, dt, mt, nt = cpu_sample(cfg, cpu_tiles, ncores)
-        line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": ncores, "kind": "port",
-                                "sample": f"first {mt} of {nt} tiles of 1 realization ({dt:.1f} s), SciPy-FFT restatement "
-                                          f"(FP64, workers={ncores}), boundary cut skipped; not Julia"}
+        os.environ["OMP_NUM_THREADS"] = str(ncores)
+        ntile = args.cpu_tiles or {1: 16, 2: 169, 3: 120, 4: 40, 5: 60}[args.config]
+        stamps, vox_per_tile, nt = cpu_sample(cfg, ntile, ncores)
+        dt = float(stamps[-1] - stamps[0])
+        done = len(stamps) - 1
+        line["cpu_baseline"] = {"value": done * vox_per_tile / dt, "unit": "voxels/s", "cores": ncores, "kind": "port",
+                                "sample": f"first {done} of {nt} tiles of 1 realization ({dt:.1f} s), SciPy-FFT restatement "
+                                          f"(FP64, workers={ncores}) incl. selection, tau model and the boundary cut (C restatement); "
+                                          f"not Julia"}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)

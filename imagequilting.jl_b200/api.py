@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import sys
+import warnings
 
 import numpy as np
 
@@ -42,6 +44,12 @@ def _i64x3(vals):
     for i, v in enumerate(vals):
         out[i] = int(v)
     return out
+
+
+def _require(cond, msg):
+    """The reference's @assert (src/iqsim.jl:69-89): AssertionError with the same message, not stripped by -O."""
+    if not cond:
+        raise AssertionError(msg)
 
 
 def _isnan(v):
@@ -81,6 +89,17 @@ def _prepare(img):
     nan = np.isnan(out)
     out[nan] = 0
     return out, nan
+
+
+def _unprepare_nonfloat(res, dtype):
+    """NaN -> missing and back to the input element type: Array{Union{Missing,T}} (src/utils.jl:104-113) as a numpy
+    masked array of dtype T."""
+    nan = np.isnan(res)
+    if np.issubdtype(dtype, np.integer) or np.issubdtype(dtype, np.bool_):
+        data = np.where(nan, 0, res).astype(dtype)
+    else:
+        data = res
+    return np.ma.array(data, mask=nan)
 
 
 def _window_any(flag, win):
@@ -173,8 +192,23 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     """Image quilting simulation with the GPU distance search (see module docstring)."""
     timg = trainimg if isinstance(trainimg, np.ma.MaskedArray) else np.asarray(trainimg)
     N = timg.ndim
+    if N == 1:
+        # a 1-D image is a 2-D one with a singleton second dimension (tile 1, overlap size 1: never overlapped)
+        def col(a):
+            return a.reshape(a.shape[0], 1) if isinstance(a, np.ma.MaskedArray) else np.asarray(a).reshape(-1, 1)
+        out = iqsim(col(timg), (int(tilesize[0]), 1), None if simsize is None else (int(simsize[0]), 1),
+                    overlap=None if overlap is None else (overlap[0], 0.5), soft=[(col(a), col(b)) for a, b in soft],
+                    hard=None if not hard else {(int(tuple(k)[0]), 0): v for k, v in hard.items()}, tol=tol, path=path, nreal=nreal,
+                    debug=debug, showprogress=showprogress, rng=rng, device=device, batch=batch, nthreads=nthreads,
+                    ngroups=ngroups, fft=fft, cut=cut, pipeline=pipeline, return_stats=return_stats, return_picks=return_picks,
+                    _path_override=_path_override, _uniforms=_uniforms, _real_range=_real_range)
+        res, extras = out if (return_stats or return_picks) else (out, None)
+        flat = (lambda lst: [a.reshape(a.shape[0]) for a in lst])
+        res = (flat(res[0]), flat(res[1]), res[2]) if debug else flat(res)
+        return (res, extras) if extras is not None else res
     if N not in (2, 3):
-        raise NotImplementedError("only 2-D and 3-D training images are supported by the B200 path")
+        raise NotImplementedError("the B200 path handles 1-D, 2-D and 3-D training images (the reference is generic in N, "
+                                  "src/iqsim.jl:50; its documented use is 2-D/3-D grids)")
     tilesize = tuple(int(t) for t in tilesize)
     simsize = tuple(timg.shape) if simsize is None else tuple(int(s) for s in simsize)
     overlap = (1.0 / 6.0,) * N if overlap is None else tuple(overlap)
@@ -182,27 +216,33 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     soft = list(soft)
     rng = np.random.default_rng() if rng is None else rng
 
-    # sanity checks, messages as in src/iqsim.jl:69-89
-    assert len(tilesize) == N and all(0 < t <= s for t, s in zip(tilesize, timg.shape)), "invalid tile size"
-    assert len(simsize) == N and all(s >= t for s, t in zip(simsize, tilesize)), "invalid grid size"
-    assert all(0 < o < 1 for o in overlap), "overlaps must be in range (0,1)"
-    assert 0 < tol <= 1, "tolerance must be in range (0,1]"
-    assert path in ("raster", "dilation", "random"), "invalid simulation path"
-    assert nreal > 0, "invalid number of realizations"
-    for aux, auxTI in soft:
-        assert all(a >= s for a, s in zip(np.shape(aux), simsize)), "soft data size < grid size"
-        assert np.shape(auxTI) == timg.shape, "auxiliary TI must have the same size as TI"
+    # sanity checks, messages as in src/iqsim.jl:69-89 (raised explicitly: they must survive `python -O`)
+    _require(len(tilesize) == N and all(0 < t <= s for t, s in zip(tilesize, timg.shape)), "invalid tile size")
+    _require(len(simsize) == N and all(s >= t for s, t in zip(simsize, tilesize)), "invalid grid size")
+    _require(len(overlap) == N and all(0 < o < 1 for o in overlap), "overlaps must be in range (0,1)")
+    _require(0 < tol <= 1, "tolerance must be in range (0,1]")
+    _require(path in ("raster", "dilation", "random"), "invalid simulation path")
+    _require(nreal > 0, "invalid number of realizations")
+    for pair in soft:
+        _require(len(pair) == 2, "soft data must be (aux, auxTI) pairs")
+        aux, auxTI = pair
+        _require(np.ndim(aux) == N and all(a >= s for a, s in zip(np.shape(aux), simsize)), "soft data size < grid size")
+        _require(np.shape(auxTI) == timg.shape, "auxiliary TI must have the same size as TI")
     if hard:
+        _require(all(len(tuple(k)) == N for k in hard.keys()), "hard data coordinates must have one index per dimension")
         coords = np.array([tuple(k) for k in hard.keys()], dtype=np.int64)
-        assert np.all(coords.max(axis=0) <= np.array(simsize) - 1), "hard data coordinates outside of grid"
-        assert np.all(coords.min(axis=0) >= 0), "hard data coordinates must be positive indices"
+        _require(np.all(coords.max(axis=0) <= np.array(simsize) - 1), "hard data coordinates outside of grid")
+        _require(np.all(coords.min(axis=0) >= 0), "hard data coordinates must be positive indices")
 
     geo = geometry(timg.shape, tilesize, simsize, overlap)
     ntiles, spacing, padsize = geo["ntiles"], geo["spacing"], geo["padsize"]
+    if any(t > 1 and o == 1 for t, o in zip(tilesize, geo["ovlsize"])):  # src/iqsim.jl:95-97
+        warnings.warn("Overlaps with only 1 voxel, check tilesize/overlap configuration")
 
     # pre-processing (src/utils.jl:69-92)
     TI, nanmask = _prepare(timg)
-    is_float = np.issubdtype(np.asarray(timg).dtype, np.floating)
+    in_dtype = np.asarray(timg).dtype
+    is_float = np.issubdtype(in_dtype, np.floating)
     out_dtype = TI.dtype
     ti64 = _f(TI, np.float64)
     ti32 = _f(TI, np.float32)
@@ -291,14 +331,20 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     d.cut_mode = {"auto": 0, "host": 1, "device": 2}[cut]  # where the boundary cuts run (host = reference behaviour)
     d.fft_mode = int(fft)  # distance path: -1 direct kernels only, 0 measured crossover, 1 FFT whenever possible
     # where the grids live: "resident" = on the device for the whole simulation (iq_sim_*), "staged" = on the host
-    # (one iq_search_pick per step), "auto" = resident whenever the simulation qualifies (no soft / hard data)
+    # (one iq_search_pick per step), "auto" = resident whenever the simulation qualifies (slabs that fit the device cut;
+    # soft and hard data included; integer-valued images stay host-staged)
     d.pipeline = {"auto": 0, "staged": 1, "resident": 2}[pipeline]
     d.out_real, d.out_real_f32, d.sim_size = real_ptrs, int(real_f32), _i64x3(simsize)
     stats = IqhStats()
+    if showprogress:  # the reference shows a ProgressMeter bar per realization (src/iqsim.jl:142,311); the native driver
+        # advances all realizations together, so there is one line before and one after the run
+        print(f"iqsim: {nreal} realization(s) x {nvis} tiles on device {device}", file=sys.stderr, flush=True)
     if nvis > 0:
         check(lib().iqh_run(C.byref(d), None, _ptr(cuts, c_u8_p) if debug else None, _ptr(picks, c_i64_p),
                             C.byref(stats)))
 
+    if showprogress:
+        print(f"iqsim: done in {stats.total_ms / 1e3:.2f} s", file=sys.stderr, flush=True)
     # post-processing (src/iqsim.jl:287-308); hard-data coordinates lie inside simsize (asserted above)
     crop = tuple(slice(0, s) for s in simsize)
     realizations, boundarycuts, voxs = [], [], []
@@ -311,7 +357,7 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
             res[tuple(coord)] = val
             if debug and _isnan(val):
                 cutgrid[tuple(coord)] = val
-        realizations.append(res if is_float else np.ma.masked_invalid(res))
+        realizations.append(res if is_float else _unprepare_nonfloat(res, in_dtype))
         if debug:
             boundarycuts.append(np.array(cutgrid[crop], copy=True))
     out = (realizations, boundarycuts, voxs) if debug else realizations

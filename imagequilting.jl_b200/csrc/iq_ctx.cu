@@ -916,6 +916,9 @@ int32_t iq_device_count(void) {
 }
 
 const char* iq_last_error(void) { return g_err.c_str(); }
+// Host driver (iq_host.cpp): an entry point that failed on a pool thread left its message in THAT thread's string;
+// the driver copies it and re-posts it on the thread that returns the error to the caller.
+void iq_post_error(const char* msg) { g_err = msg ? msg : ""; }
 
 int32_t iq_ctx_destroy(iq_ctx* c) {
   if (!c) return IQ_OK;

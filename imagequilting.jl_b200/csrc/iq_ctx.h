@@ -39,6 +39,7 @@ struct MaskEntry {
   iq::CutTask* d_cut_tasks = nullptr;  // resident simulation: cut task records of this mask's slabs
   int cut_ntask = 0;
   size_t cut_smem = 0;
+  std::vector<int> cut_sig;            // slab signature (R, nslab, dim/n0/n1/L per slab) the cached records were built for
 };
 
 struct TileResult {

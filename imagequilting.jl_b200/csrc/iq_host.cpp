@@ -22,12 +22,15 @@
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/iqb200.h"
 #include "../../include/iqb200_host.h"
 #include "iq_cut.h"
+
+extern "C" void iq_post_error(const char* msg);  // iq_ctx.cu: sets the calling thread's iq_last_error() string
 
 namespace {
 
@@ -184,6 +187,15 @@ void tile_slabs(const Geo& G, const std::vector<uint8_t>& pasted, int64_t ind, s
         std::memset(&mask[((size_t)z * t[1] + y) * t[0] + s.lo[0]], 1, (size_t)s.sz[0]);
 }
 
+// Integer-valued (categorical) training image?  Its cut capacities (graphcut.jl:52) are degenerate (division by eps next
+// to O(1) terms): equal-cost cuts abound and which one comes out depends on the max-flow algorithm's rounding.
+bool image_is_integer(const iqh_desc* D, const Geo& G) {
+  const long long nvox = (long long)G.n[0] * G.n[1] * G.n[2];
+  for (long long i = 0; i < nvox; ++i)
+    if (D->ti_f32[i] != std::nearbyint(D->ti_f32[i])) return false;
+  return true;
+}
+
 // Device-resident pipeline: every lockstep group owns a context whose stream carries the whole simulation of its
 // realizations (iq_sim_*); this thread only enqueues.  Returns IQ_ERR_STATE when the simulation does not qualify
 // (the caller then runs host-staged), `*status` != 0 when a data-dependent condition invalidated the result.
@@ -196,10 +208,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     // to O(1) terms): equal-cost cuts abound and which one comes out depends on the max-flow algorithm's rounding.
     // The reference's choice is Boykov-Kolmogorov on the host, so "auto" keeps such images on the host-staged
     // pipeline (host cuts); continuous images have a unique minimum cut and go device-resident.
-    const long long nvox = (long long)G.n[0] * G.n[1] * G.n[2];
-    bool integer = true;
-    for (long long i = 0; i < nvox && integer; ++i) integer = D->ti_f32[i] == std::nearbyint(D->ti_f32[i]);
-    if (integer) return IQ_ERR_STATE;
+    if (image_is_integer(D, G)) return IQ_ERR_STATE;
   }
   const auto t_start = clk::now();
   const int R = D->nreal;
@@ -385,6 +394,13 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   return IQ_OK;
 }
 
+bool is_oom(int rc) {
+  if (rc == IQ_ERR_NOMEM) return true;
+  if (rc != IQ_ERR_CUDA) return false;
+  const std::string m = iq_last_error();
+  return m.find("out of memory") != std::string::npos;
+}
+
 // Realizations are independent, so a simulation whose resident state would not fit in device memory is run as
 // consecutive waves of at most `rmax` realizations (each wave a complete run_resident on its rows of the uniform
 // stream).  rmax comes from the free device memory and a per-realization estimate (FP64 grid, distance maps,
@@ -403,7 +419,14 @@ int run_resident_waves(const iqh_desc* D, const Geo& G, double* out_grids, uint8
   if (iq_device_free_memory(D->device, &free_b, &total_b) == IQ_OK && per_real > 0)
     rmax = (int)std::max(1.0, std::min((double)R, 0.7 * (double)free_b / per_real));
   if (const char* ev = std::getenv("IQB200_MAX_RESIDENT_REAL")) rmax = std::max(1, std::min(R, std::atoi(ev)));
-  if (rmax >= R) return run_resident(D, G, out_grids, out_cuts, out_picks, stats, status);
+  // The estimate is a heuristic (it ignores the per-context fixed costs and the pinned buffers): a wave that runs out
+  // of device memory is retried with half as many realizations instead of failing the call.
+  if (rmax >= R) {
+    const int rc = run_resident(D, G, out_grids, out_cuts, out_picks, stats, status);
+    if (!is_oom(rc) || R < 2) return rc;
+    iq_release_device_memory(D->device);
+    rmax = (R + 1) / 2;
+  }
   iqh_stats acc{};
   *status = 0;
   for (int r0 = 0; r0 < R; r0 += rmax) {
@@ -417,6 +440,12 @@ int run_resident_waves(const iqh_desc* D, const Geo& G, double* out_grids, uint8
     const int rc = run_resident(&sub, G, out_grids ? out_grids + (size_t)r0 * G.padvol : nullptr,
                                 out_cuts ? out_cuts + (size_t)r0 * G.padvol : nullptr,
                                 out_picks ? out_picks + (size_t)r0 * D->npath : nullptr, &st, &wst);
+    if (is_oom(rc) && rmax > 1) {  // redo this wave (and the rest) with smaller waves
+      iq_release_device_memory(D->device);
+      rmax = (rmax + 1) / 2;
+      r0 -= rmax;  // the loop increment brings r0 back to the start of the failed wave
+      continue;
+    }
     if (rc != IQ_OK) return rc;
     *status |= wst;
     if (wst) return IQ_OK;  // the caller redoes everything host-staged
@@ -462,7 +491,9 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
   if (D->pipeline != 1) {
     const int rcr = run_resident_waves(D, G, out_grids, out_cuts, out_picks, stats, &resident_status);
     if (rcr == IQ_OK && resident_status == 0) return IQ_OK;
-    if (rcr != IQ_OK && !(rcr == IQ_ERR_STATE && D->pipeline == 0)) return rcr;  // explicit request or a real error
+    // explicit request or a real error; in auto mode "does not qualify" includes "does not fit in device memory"
+    if (rcr != IQ_OK && !((rcr == IQ_ERR_STATE || is_oom(rcr)) && D->pipeline == 0)) return rcr;
+    if (rcr != IQ_OK && is_oom(rcr)) iq_release_device_memory(D->device);
     // otherwise: does not qualify (or a data-dependent bail-out): host-staged below, still on the GPU
   }
   std::vector<double> own_grids;
@@ -690,9 +721,13 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
         }
       });
   };
-  // few host threads per GPU (multi-GPU nodes): the cuts of a step run on the device instead
-  const bool device_cut = D->cut_mode == 2 || (D->cut_mode == 0 && nthreads < 6);
+  // few host threads per GPU (multi-GPU nodes): the cuts of a step run on the device instead -- but never by default
+  // on integer-valued (categorical) images, whose degenerate capacities make the cut depend on the max-flow algorithm
+  // (same rule as run_resident): the result must not depend on the host's core count or the nthreads argument
+  const bool device_cut = D->cut_mode == 2 || (D->cut_mode == 0 && nthreads < 6 && !image_is_integer(D, G));
   std::atomic<int> cut_error{IQ_OK};
+  std::mutex cut_error_m;
+  std::string cut_error_msg;
   auto device_cut_job = [&](Group& g) {
     const int nslab = (int)g.slabs.size();
     const int ntask = g.R * nslab;
@@ -726,7 +761,11 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
       T.keep = g.keepbuf[task].data();
     }
     const int rcc = iq_cut_batch(g.ctx, g.cut_tasks.data(), ntask, nullptr);
-    if (rcc != IQ_OK) cut_error.store(rcc);
+    if (rcc != IQ_OK) {
+      std::lock_guard<std::mutex> l(cut_error_m);
+      if (cut_error.load() == IQ_OK) cut_error_msg = iq_last_error();  // thread-local on this pool thread
+      cut_error.store(rcc);
+    }
   };
   auto submit_cut = [&](Group& g) {
     const int nslab = (int)g.slabs.size();
@@ -763,7 +802,10 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     }
   }
   for (auto& g : groups) g.latch->wait();
-  if (rc == IQ_OK && cut_error.load() != IQ_OK) rc = cut_error.load();
+  if (rc == IQ_OK && cut_error.load() != IQ_OK) {
+    rc = cut_error.load();
+    iq_post_error(cut_error_msg.c_str());
+  }
   double search_ms = 0, search_dev_ms = 0, cut_ms = 0, dist_ms = 0;
   int64_t launches = 0, dist_launches = 0, ncand = 0;
   for (auto& g : groups) {

@@ -807,9 +807,9 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       // relaxation rounds on the device: kRelaxRounds rounds are enqueued unconditionally, the kernels of a round
       // return at once for realizations that already have candidates; a realization still empty after the last
       // round raises the status word (the caller then reruns host-staged, where the round count is unbounded)
-      // (3 rounds normally; tiles with hard data or an empty overlap mask often need many -- an all-zero overlap map
+      // (5 rounds normally, frac up to 0.4 + 0.1 tol; tiles with hard data or an empty overlap mask often need many -- an all-zero overlap map
       // selects an index prefix -- and get all 11, after which frac = 1 guarantees a non-empty intersection)
-      const int kRelaxRounds = (hardt || e->nnz == 0) ? 11 : 3;
+      const int kRelaxRounds = (hardt || e->nnz == 0) ? 11 : 5;
       for (int round = 0; round < kRelaxRounds; ++round) {
         k_sim_seljobs<<<R, 32, 0, c->stream>>>(c->d_sel, pj, c->max_src, pmax, pmax_stride, shared_mask, s->tol, c->nenabled,
                                               c->npos, round, s->d_pending, c->d_selbuf, c->sel_cap);
@@ -844,8 +844,15 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
                                               c->nx, c->ny, c->nxo, c->nyo, s->d_picked, c->tx, c->ty, S, s->d_cutA, s->d_cutB,
                                               (long long)s->maxslab);
     CK(cudaGetLastError());
-    // task records depend on the slab set only: cached with the mask
-    if (!e->d_cut_tasks || e->cut_ntask != ntask) {
+    // task records depend on the slab set (dimension and extent of every slab) and R only; they are cached with the
+    // mask, but the mask alone does not determine the slabs (overlap >= 0.5: {px,nx,py} and {px,py,ny} cover the same
+    // voxels with different slab shapes), so the cache is keyed on the slab signature
+    std::vector<int> sig;
+    sig.reserve(2 + 4 * (size_t)nslab);
+    sig.push_back(R);
+    sig.push_back(nslab);
+    for (int k = 0; k < nslab; ++k) { sig.push_back(S.s[k].dim); sig.push_back(S.s[k].n0); sig.push_back(S.s[k].n1); sig.push_back(S.s[k].L); }
+    if (!e->d_cut_tasks || e->cut_ntask != ntask || e->cut_sig != sig) {
       // Launch order = longest first: the slabs with the most inner voxels of ALL realizations lead, the cheap ones
       // (e.g. the one-layer z slabs) come last and fill the second wave (one CTA per SM: 192 cuts on 148 SMs), so the
       // tail of the launch is made of short cuts.  Only the order of the records changes, not where a task's data is.
@@ -872,6 +879,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       CK(cudaMemcpy(e->d_cut_tasks, recs.data(), recs.size() * sizeof(iq::CutTask), cudaMemcpyHostToDevice));
       e->cut_ntask = ntask;
       e->cut_smem = smem;
+      e->cut_sig = sig;
     }
     CK(iq::launch_graphcut(e->d_cut_tasks, ntask, std::max<size_t>(e->cut_smem, 64), c->stream));
     c->launches += 2;

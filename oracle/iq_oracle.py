@@ -41,7 +41,7 @@ __all__ = [
     "prepare", "unprepare", "imagepreproc", "finddisabled", "findskipped", "genpath",
     "overlap_mask", "indicator", "event", "activation", "relaxation", "fastintersect",
     "taumodel", "julia_sum", "sample_weighted", "graphcut", "iqsim", "voxelreuse",
-    "search_tile",
+    "search_tile", "build_c", "graphcut_c", "fastdistance_c", "decision_gaps", "relaxation_thresholds",
 ]
 
 
@@ -100,6 +100,8 @@ def fastdistance(img, kern, weights=None, method="fft", workers=None):
         AB = imfilter_valid_fft(img, wkern, workers)  # src/utils.jl:9
         B2 = float(np.sum(wkern * kern))  # src/utils.jl:10
         return np.abs(A2 - 2.0 * AB + B2)  # src/utils.jl:12
+    if method == "c":  # same definition as "direct", evaluated by oracle/iq_oracle_c.c
+        return fastdistance_c(img, kern, weights)
     if method == "direct":
         final = tuple(a - b + 1 for a, b in zip(img.shape, kern.shape))
         out = np.zeros(final, dtype=np.float64)
@@ -146,12 +148,15 @@ def prepare(img):
     return fimg
 
 
-def unprepare(is_float, fimg):
-    """Float input -> array returned as is; otherwise NaN -> missing (masked) and cast back
-    (src/utils.jl:104-113).  Masked arrays stand in for Union{Missing,T}."""
+def unprepare(is_float, fimg, dtype=None):
+    """Float input -> array returned as is; otherwise NaN -> missing (masked) and cast back to the
+    input element type (src/utils.jl:104-113).  Masked arrays stand in for Union{Missing,T}."""
     if is_float:
         return np.array(fimg, copy=True)
-    return np.ma.masked_invalid(np.array(fimg, copy=True))
+    nan = np.isnan(fimg)
+    if dtype is not None and (np.issubdtype(dtype, np.integer) or np.issubdtype(dtype, np.bool_)):
+        return np.ma.array(np.where(nan, 0, fimg).astype(dtype), mask=nan)
+    return np.ma.array(np.array(fimg, copy=True), mask=nan)
 
 
 def imagepreproc(trainimg, soft, geo):
@@ -392,6 +397,39 @@ def relaxation(distance, auxdistances, cutoff):
     return np.sort(np.asarray(patterndb, dtype=np.int64))
 
 
+def relaxation_thresholds(distance, auxdistances, cutoff):
+    """Test diagnostics for `relaxation`: the k-th smallest value of every source at the round that produced the
+    result -> (rounds, [kth of the primary, kth of aux 1, ...]).  A position belongs to the result iff its
+    (value, index) key is <= the k-th key of every source (src/relaxation.jl:12,27,29), so an FP32 distance path may
+    legitimately differ from the FP64 result only at positions whose value is within rounding of one of these."""
+    distance = np.asarray(distance, dtype=np.float64)
+    enabled = ~np.isinf(distance)
+    npatterns = int(enabled.sum())
+    allzero = bool(np.all(distance[enabled] == 0))
+    dbsize = npatterns if allzero else int(math.ceil(cutoff * npatterns))
+    frac = 0.1 * (dbsize / npatterns)
+    kth0 = float(np.partition(distance, dbsize - 1)[dbsize - 1])
+    ovl = np.zeros(distance.size, dtype=bool)
+    ovl[_partialsortperm(distance, dbsize)] = True
+    rounds = 0
+    while True:
+        rounds += 1
+        k = int(math.ceil(frac * npatterns))
+        sel = ovl.copy()
+        kths = []
+        for a in auxdistances:
+            a = np.asarray(a, dtype=np.float64)
+            m = np.zeros(distance.size, dtype=bool)
+            m[_partialsortperm(a, k)] = True
+            kths.append(float(np.partition(a, k - 1)[k - 1]))
+            sel &= m
+            if not sel.any():
+                break
+        if sel.any():
+            return rounds, [kth0] + kths
+        frac = min(frac + 0.1, 1)
+
+
 # --------------------------------------------------------------------------------------
 # taumodel (src/taumodel.jl:5-45)
 # --------------------------------------------------------------------------------------
@@ -576,6 +614,70 @@ def _maxflow_sink_side(nvox, us, vs, caps, src_nodes, snk_nodes):
 
 
 # --------------------------------------------------------------------------------------
+# plain-C twins (oracle/iq_oracle_c.c) of the two pieces that are too slow in NumPy / pure Python at
+# BASELINE.json's full sizes.  Same semantics as graphcut / fastdistance(method="direct") above;
+# tests/test_oracle_c.py holds them against each other.
+# --------------------------------------------------------------------------------------
+_CLIB = None
+
+
+def build_c(verbose=False):
+    """Compile oracle/iq_oracle_c.c into oracle/_build/libiqoracle.so (gcc; make -C oracle)."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run(["make", "-C", here], check=True, stdout=None if verbose else subprocess.DEVNULL)
+    return os.path.join(here, "_build", "libiqoracle.so")
+
+
+def _clib():
+    global _CLIB
+    if _CLIB is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libiqoracle.so")
+        if not os.path.exists(path):
+            build_c()
+        _CLIB = ctypes.CDLL(path)
+        _CLIB.iqo_graphcut.restype = ctypes.c_int
+        _CLIB.iqo_fastdistance.restype = ctypes.c_int
+    return _CLIB
+
+
+def graphcut_c(A, B, dim):
+    """graphcut(A, B, dim) (src/graphcut.jl:5-84) through the C restatement (Dinic in C)."""
+    import ctypes
+    A = np.asfortranarray(A, dtype=np.float64)
+    B = np.asfortranarray(B, dtype=np.float64)
+    assert A.shape == B.shape, "arrays must have the same size for cut"
+    sz = np.array(A.shape, dtype=np.int64)
+    keep = np.zeros(A.shape, dtype=np.uint8, order="F")
+    rc = _clib().iqo_graphcut(A.ctypes.data_as(ctypes.c_void_p), B.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(A.ndim),
+                              sz.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(int(dim)), keep.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError("iqo_graphcut failed: %d" % rc)
+    return keep.astype(bool)
+
+
+def fastdistance_c(img, kern, weights=None):
+    """fastdistance by its definition (FP64, src/utils.jl:5-13) through the C restatement (OpenMP over rows)."""
+    import ctypes
+    img = np.asfortranarray(img, dtype=np.float64)
+    kern = np.asfortranarray(kern, dtype=np.float64)
+    w = None if weights is None else np.asfortranarray(weights, dtype=np.float64)
+    isz = np.array(img.shape, dtype=np.int64)
+    ksz = np.array(kern.shape, dtype=np.int64)
+    out = np.zeros(tuple(a - b + 1 for a, b in zip(img.shape, kern.shape)), dtype=np.float64, order="F")
+    rc = _clib().iqo_fastdistance(img.ctypes.data_as(ctypes.c_void_p), isz.ctypes.data_as(ctypes.c_void_p),
+                                  kern.ctypes.data_as(ctypes.c_void_p),
+                                  w.ctypes.data_as(ctypes.c_void_p) if w is not None else None,
+                                  ksz.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(img.ndim), out.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError("iqo_fastdistance failed: %d" % rc)
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # per-tile search = src/iqsim.jl:187-240 (the hot path)
 # --------------------------------------------------------------------------------------
 def search_tile(TI, simdev, ovlmask, disabled, tol, hard=None, soft=None, method="direct", workers=None):
@@ -610,15 +712,40 @@ def search_tile(TI, simdev, ovlmask, disabled, tol, hard=None, soft=None, method
     return dict(patterndb=patterndb, probs=probs, D=Dv, Ds=Dsv)
 
 
+def decision_gaps(D, Ds, patterndb, tol):
+    """How close the FP64 decision of one tile search is to flipping (test diagnostics, no reference counterpart):
+    thr_gap  = smallest relative distance of any map value to the selection threshold (1+tol)*min D of the threshold
+               path (inf on the relaxation path or when the threshold is 0: exact zeros only);
+    rank_gap = smallest relative difference between two distinct consecutive candidate distances of any source (a
+               smaller FP32 rounding error can swap their tau-model ranks).
+    An FP32 distance path with relative error eps may legitimately decide differently only where a gap <= ~2 eps."""
+    thr_gap = np.inf
+    if not Ds:
+        fin = D[np.isfinite(D)]
+        thr = (1 + tol) * fin.min()
+        if thr > 0:
+            thr_gap = float(np.min(np.abs(fin - thr)) / thr)
+    rank_gap = np.inf
+    if patterndb.size > 1:
+        for src in [D] + list(Ds):
+            v = np.sort(src[patterndb])
+            dv = np.diff(v)
+            pos = dv > 0
+            if pos.any():
+                rank_gap = min(rank_gap, float(np.min(dv[pos] / np.maximum(v[1:][pos], 1e-300))))
+    return thr_gap, rank_gap
+
+
 # --------------------------------------------------------------------------------------
 # iqsim (src/iqsim.jl:50-315)
 # --------------------------------------------------------------------------------------
 def iqsim(trainimg, tilesize, simsize=None, overlap=None, soft=(), hard=None, tol=0.1,
           path="raster", nreal=1, debug=False, rng=None, method="direct", workers=None,
-          cut_fn=None, trace=None, max_tiles=None):
+          cut_fn=None, trace=None, max_tiles=None, on_tile=None):
     """Restatement of the whole driver.  `cut_fn(A, B, dim)` overrides the boundary cut
     (tests use it to isolate search parity); `trace` (a list) receives one dict per
-    visited tile for parity tests."""
+    visited tile for parity tests; `max_tiles` stops after that many visited tiles (over all
+    realizations) and `on_tile(n)` is called after every visited tile (bounded benchmark samples)."""
     trainimg_in = trainimg
     trainimg = np.asarray(trainimg) if not isinstance(trainimg, np.ma.MaskedArray) else trainimg
     N = trainimg.ndim
@@ -692,9 +819,12 @@ def iqsim(trainimg, tilesize, simsize=None, overlap=None, soft=(), hard=None, to
             TIdev = TI[tuple(slice(s, s + t) for s, t in zip(rstart, tilesize))]
 
             if trace is not None:
+                thr_gap, rank_gap = decision_gaps(res["D"], res["Ds"], patterndb, tol)
                 trace.append(dict(real=real, ind=ind, u=u, rind=rind, ncand=int(patterndb.size),
                                   patterndb=patterndb.copy(), probs=np.array(probs, copy=True),
-                                  simdev=np.array(simdev, copy=True), ovlmask=ovlmask.copy()))
+                                  simdev=np.array(simdev, copy=True), ovlmask=ovlmask.copy(), start=start,
+                                  thr_gap=thr_gap, rank_gap=rank_gap,
+                                  hard=hardarg, softdev=[np.array(sd, copy=True) for _, sd in softarg]))
 
             # boundary cut mask (:251-275)
             cutmask = np.zeros(tilesize, dtype=bool)
@@ -709,6 +839,8 @@ def iqsim(trainimg, tilesize, simsize=None, overlap=None, soft=(), hard=None, to
             if debug:
                 cutgrid[tile] = cutmask  # :281
             pasted.add(tileind)
+            if on_tile is not None:
+                on_tile(nvisited_total)  # benchmarks: wall-clock stamp per visited tile
 
         if debug:
             voxelreuse_out.append(float(cutgrid.sum()) / geo["ovlvol"])  # :288
@@ -720,7 +852,7 @@ def iqsim(trainimg, tilesize, simsize=None, overlap=None, soft=(), hard=None, to
                     if _isnan(val):
                         cutgrid[tuple(coord)] = val
         crop = tuple(slice(0, s) for s in simsize)  # :303
-        realizations.append(unprepare(is_float, simgrid[crop]))
+        realizations.append(unprepare(is_float, simgrid[crop], np.asarray(trainimg_in).dtype))
         if debug:
             boundarycuts.append(np.array(cutgrid[crop], copy=True))
     if debug:
