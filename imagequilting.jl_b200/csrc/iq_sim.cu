@@ -30,8 +30,16 @@ struct SlabSet {
   SlabDev s[6];
 };
 
+// One tile of a (multi-tile) step: origin in the padded grid and the path step it belongs to (index of its uniform /
+// pick).  A step launch carries ntile x R jobs: job j = tile j / R of realization j % R.
+struct TileInfo { int sx, sy, sz, step; };
+
 struct SimState {
   int R = 0;
+  int J = 0;                      // job slots of one launch (= max_batch of the context, a multiple of R)
+  TileInfo* d_tiles = nullptr;    // [npath] tile records in launch order (every path step is launched exactly once)
+  TileInfo* h_tiles = nullptr;    // pinned mirror
+  size_t tile_cursor = 0;         // tiles launched so far
   int pad[3] = {1, 1, 1};
   long long padvol = 0;
   int64_t npath = 0;
@@ -95,12 +103,15 @@ struct SimState {
 // library's fixed order (b2_ordered in iq_ctx.cu): one CTA per (z plane, realization).
 template <typename GT>
 __global__ void __launch_bounds__(256) k_sim_templates(const GT* __restrict__ grid, long long padvol, int p0, int p1,
-                                                       int sx, int sy, int sz, const uint8_t* __restrict__ mask, int tx,
+                                                       const TileInfo* __restrict__ tiles, int R,
+                                                       const uint8_t* __restrict__ mask, int tx,
                                                        int ty, int tz, float* __restrict__ tmpl, double* __restrict__ plane,
                                                        double* __restrict__ b2, unsigned* __restrict__ ticket) {
-  const int z = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;
+  const int z = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;  // r = job: tile r / R of realization r % R
   const int pl = tx * ty;
-  const GT* g = grid + (long long)r * padvol + ((long long)(sz + z) * p1 + sy) * p0 + sx;
+  const TileInfo T = tiles[r / R];
+  const int sx = T.sx, sy = T.sy, sz = T.sz;
+  const GT* g = grid + (long long)(r % R) * padvol + ((long long)(sz + z) * p1 + sy) * p0 + sx;
   const uint8_t* m = mask + (long long)z * pl;
   float* out = tmpl + ((long long)r * tz + z) * pl;
   double acc = 0.0;
@@ -206,11 +217,13 @@ __device__ double warp_julia_sum(const double* w, int n, int lane) {
 // so the chain costs one DADD latency per candidate instead of a dependent global load.
 // status bits: 1 = candidate set outside 1..kTauMax, 2 = a boundary cut hit its iteration cap, 4 = relaxation rounds.
 __global__ void __launch_bounds__(128) k_sim_sample(const iq::PickJob* __restrict__ jobs, const double* __restrict__ prob,
-                                                    const double* __restrict__ u, long long npath, long long step, int R,
+                                                    const double* __restrict__ u, long long npath,
+                                                    const TileInfo* __restrict__ tiles, int R, int njobs,
                                                     long long* __restrict__ picked, long long* __restrict__ picks,
                                                     int* __restrict__ status) {
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= R) return;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // r = job
+  if (r >= njobs) return;
+  const long long ustep = (long long)(r % R) * npath + tiles[r / R].step;  // uniform / pick slot of (realization, step)
   const iq::PickJob& J = jobs[r];
   const unsigned n = *J.total;
   unsigned pos = 0;
@@ -218,7 +231,7 @@ __global__ void __launch_bounds__(128) k_sim_sample(const iq::PickJob* __restric
     if (lane == 0) atomicOr(status, 1);
   } else if (n > 1u) {
     const double* p = prob + (long long)r * iq::kTauMax;
-    const double t = __dmul_rn(u[(long long)r * npath + step], warp_julia_sum(p, (int)n, lane));
+    const double t = __dmul_rn(u[ustep], warp_julia_sum(p, (int)n, lane));
     // first i with cw_i >= t among i < n-1, else n-1, where cw_0 = p[0], cw_i = fl(cw_{i-1} + p[i])
     // Every lane carries the same running sum (the only dependent chain: one DADD per candidate, cw_0 = 0 + p[0]
     // exactly); lane j keeps the value after candidate base + j and the crossing test runs once per batch of 32.
@@ -244,7 +257,7 @@ __global__ void __launch_bounds__(128) k_sim_sample(const iq::PickJob* __restric
   if (lane == 0) {
     const long long pk = (n == 0u) ? 0 : (long long)J.cand_idx[pos];
     picked[r] = pk;
-    picks[(long long)r * npath + step] = pk;
+    picks[ustep] = pk;
   }
 }
 
@@ -347,22 +360,25 @@ __global__ void __launch_bounds__(256) k_sim_hardlist(const uint8_t* __restrict_
 }
 
 __global__ void k_sim_store_picks(const long long* __restrict__ picked, long long* __restrict__ picks, long long npath,
-                                  long long step, int R) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R) picks[(long long)r * npath + step] = picked[r];
+                                  const TileInfo* __restrict__ tiles, int R, int njobs) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;  // job
+  if (r < njobs) picks[(long long)(r % R) * npath + tiles[r / R].step] = picked[r];
 }
 
 // Overlap slabs of every realization in the cut kernel's layout: A = pasted content, B = chosen patch.
-__global__ void __launch_bounds__(256) k_sim_slabs(const double* __restrict__ grid, long long padvol, int p0, int p1, int sx,
-                                                   int sy, int sz, const double* __restrict__ ti, int nx, int ny, int nxo,
+__global__ void __launch_bounds__(256) k_sim_slabs(const double* __restrict__ grid, long long padvol, int p0, int p1,
+                                                   const TileInfo* __restrict__ tiles, int R,
+                                                   const double* __restrict__ ti, int nx, int ny, int nxo,
                                                    int nyo, const long long* __restrict__ picked, int tx, int ty,
                                                    const SlabSet S, double* __restrict__ A, double* __restrict__ B,
                                                    long long maxslab) {
-  const int task = blockIdx.x, r = task / S.n;
+  const int task = blockIdx.x, r = task / S.n;  // r = job
   const SlabDev& s = S.s[task - r * S.n];
+  const TileInfo T = tiles[r / R];
+  const int sx = T.sx, sy = T.sy, sz = T.sz;
   const long long pk = picked[r];
   const int rx = (int)(pk % nxo), ry = (int)((pk / nxo) % nyo), rz = (int)(pk / ((long long)nxo * nyo));
-  const double* g = grid + (long long)r * padvol;
+  const double* g = grid + (long long)(r % R) * padvol;
   double* a = A + (long long)task * maxslab;
   double* b = B + (long long)task * maxslab;
   const int nv = s.n0 * s.n1 * s.L;
@@ -378,12 +394,15 @@ __global__ void __launch_bounds__(256) k_sim_slabs(const double* __restrict__ gr
 
 // cutmask = OR over the slabs of (prev ? keep : !keep) (iqsim.jl:264,273); simdev[.!cutmask] = TIdev[.!cutmask].
 __global__ void __launch_bounds__(256) k_sim_paste(double* __restrict__ grid, uint8_t* __restrict__ cutgrid, long long padvol,
-                                                   int p0, int p1, int sx, int sy, int sz, const double* __restrict__ ti,
+                                                   int p0, int p1, const TileInfo* __restrict__ tiles, int R,
+                                                   const double* __restrict__ ti,
                                                    int nx, int ny, int nxo, int nyo, const long long* __restrict__ picked,
                                                    int tx, int ty, int tz, const SlabSet S, const uint8_t* __restrict__ keep,
                                                    long long maxslab, const int* __restrict__ cut_iters,
                                                    int* __restrict__ status) {
-  const int r = blockIdx.y;
+  const int r = blockIdx.y;  // job
+  const TileInfo T = tiles[r / R];
+  const int sx = T.sx, sy = T.sy, sz = T.sz;
   const int q = blockIdx.x * 256 + threadIdx.x;
   if (q == 0 && S.n > 0) {
     bool bad = false;
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(256) k_sim_paste(double* __restrict__ grid, ui
   }
   const long long pk = picked[r];
   const int rx = (int)(pk % nxo), ry = (int)((pk / nxo) % nyo), rz = (int)(pk / ((long long)nxo * nyo));
-  const long long gi = (long long)r * padvol + ((long long)(sz + qz) * p1 + (sy + qy)) * p0 + sx + qx;
+  const long long gi = (long long)(r % R) * padvol + ((long long)(sz + qz) * p1 + (sy + qy)) * p0 + sx + qx;
   if (!cm) grid[gi] = ti[((long long)(rz + qz) * ny + (ry + qy)) * nx + rx + qx];
   if (cutgrid) cutgrid[gi] = (uint8_t)cm;
 }
@@ -435,6 +454,8 @@ void sim_destroy(iq_ctx* c) {
   cudaFree(s->d_hard_has); cudaFree(s->d_hard_val); cudaFree(s->d_hard_ptr); cudaFree(s->d_hard_off);
   cudaFree(s->d_hard_list); cudaFree(s->d_pickjobs_hard);
   if (s->h_pickstage) cudaFreeHost(s->h_pickstage);
+  cudaFree(s->d_tiles);
+  if (s->h_tiles) cudaFreeHost(s->h_tiles);
   for (int i = 0; i < 2; ++i) {
     if (s->h_export[i]) cudaFreeHost(s->h_export[i]);
     cudaFree(s->d_export2[i]);
@@ -484,6 +505,8 @@ extern "C" {
 int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   if (!c || !d || !d->ti64 || !d->u) return fail(IQ_ERR_INVALID, "iq_sim_begin: NULL argument");
   if (d->nreal < 1 || d->nreal > c->max_batch) return fail(IQ_ERR_INVALID, "iq_sim_begin: nreal must be in 1..max_batch");
+  if (c->max_batch % d->nreal != 0)
+    return fail(IQ_ERR_INVALID, "iq_sim_begin: max_batch of the context must be a multiple of nreal (job slots = tiles per step x nreal)");
   if (d->npath < 0) return fail(IQ_ERR_INVALID, "iq_sim_begin: npath < 0");
   if (!(d->tol > 0.0 && d->tol <= 1.0)) return fail(IQ_ERR_INVALID, "tolerance must be in range (0,1]");
   if (c->nsoft > 0 && !d->aux) return fail(IQ_ERR_INVALID, "iq_sim_begin: the context has soft data but desc.aux is NULL");
@@ -511,6 +534,7 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   SimState* s = new SimState();
   c->sim = s;
   s->R = d->nreal;
+  s->J = c->max_batch;
   for (int i = 0; i < 3; ++i) s->pad[i] = pad[i];
   s->padvol = (long long)pad[0] * pad[1] * pad[2];
   s->npath = d->npath;
@@ -518,7 +542,9 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   s->debug = d->debug;
   s->maxslab = maxslab;
   s->maxslabs = std::max(maxslabs, 1);
-  const size_t R = (size_t)s->R, nimg = (size_t)c->nx * c->ny * c->nz, np = (size_t)std::max<int64_t>(d->npath, 1);
+  const size_t R = (size_t)s->R, J = (size_t)s->J, nimg = (size_t)c->nx * c->ny * c->nz, np = (size_t)std::max<int64_t>(d->npath, 1);
+  CK(iq::dmalloc((void**)&s->d_tiles, np * sizeof(TileInfo)));
+  CK(cudaMallocHost((void**)&s->h_tiles, np * sizeof(TileInfo)));
   CK(iq::dmalloc((void**)&s->d_grid, R * s->padvol * sizeof(double)));
   CK(cudaMemsetAsync(s->d_grid, 0, R * s->padvol * sizeof(double), c->stream));  // simgrid = zeros (iqsim.jl:165)
   if (s->debug) {
@@ -531,18 +557,18 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   CK(iq::dmalloc((void**)&s->d_u, R * np * sizeof(double)));
   if (d->npath > 0)
     CK(cudaMemcpyAsync(s->d_u, d->u, R * (size_t)d->npath * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(iq::dmalloc((void**)&s->d_tmpl, R * c->tilevol * sizeof(float)));
-  CK(iq::dmalloc((void**)&s->d_b2, R * sizeof(double)));
-  CK(iq::dmalloc((void**)&s->d_plane, R * c->tz * sizeof(double)));
-  CK(iq::dmalloc((void**)&s->d_ticket, R * sizeof(unsigned)));
-  CK(cudaMemsetAsync(s->d_ticket, 0, R * sizeof(unsigned), c->stream));
-  CK(iq::dmalloc((void**)&s->d_picked, R * sizeof(long long)));
+  CK(iq::dmalloc((void**)&s->d_tmpl, J * c->tilevol * sizeof(float)));
+  CK(iq::dmalloc((void**)&s->d_b2, J * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_plane, J * c->tz * sizeof(double)));
+  CK(iq::dmalloc((void**)&s->d_ticket, J * sizeof(unsigned)));
+  CK(cudaMemsetAsync(s->d_ticket, 0, J * sizeof(unsigned), c->stream));
+  CK(iq::dmalloc((void**)&s->d_picked, J * sizeof(long long)));
   CK(iq::dmalloc((void**)&s->d_picks, R * np * sizeof(long long)));
   CK(cudaMemsetAsync(s->d_picks, 0xff, R * np * sizeof(long long), c->stream));
   CK(cudaMallocHost((void**)&s->h_pickstage, R * np * sizeof(long long)));
   CK(iq::dmalloc((void**)&s->d_status, sizeof(int)));
   CK(cudaMemsetAsync(s->d_status, 0, sizeof(int), c->stream));
-  const size_t ntask = R * s->maxslabs;
+  const size_t ntask = J * s->maxslabs;
   CK(iq::dmalloc((void**)&s->d_cutA, ntask * maxslab * sizeof(double)));
   CK(iq::dmalloc((void**)&s->d_cutB, ntask * maxslab * sizeof(double)));
   CK(iq::dmalloc((void**)&s->d_keep, ntask * maxslab));
@@ -561,11 +587,12 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     CK(iq::dmalloc((void**)&s->d_soft_ticket, sizeof(unsigned)));
     CK(cudaMemsetAsync(s->d_soft_ticket, 0, sizeof(unsigned), c->stream));
   }
-  CK(iq::dmalloc((void**)&s->d_pickjobs, R * sizeof(iq::PickJob)));
-  CK(iq::dmalloc((void**)&s->d_pending, R * sizeof(int)));
-  // selection jobs never change during the simulation: threshold rule on the overlap distance of realization r, or
-  // (soft data) the intersection of the radix-select thresholds of the overlap map and the shared soft maps
-  for (int r = 0; r < s->R; ++r) {
+  CK(iq::dmalloc((void**)&s->d_pickjobs, J * sizeof(iq::PickJob)));
+  CK(iq::dmalloc((void**)&s->d_pending, J * sizeof(int)));
+  // selection jobs never change during the simulation: threshold rule on the overlap distance of job slot r, or
+  // (soft data: one tile per step, slots 0..R-1) the intersection of the radix-select thresholds of the overlap map and
+  // the shared soft maps
+  for (int r = 0; r < s->J; ++r) {
     iq::PickJob& J = c->h_pick[r];
     std::memset(&J, 0, sizeof J);
     J.mode = s->S > 0 ? 1 : 0;
@@ -583,7 +610,7 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     J.cap = c->npos;
     J.chunkmin = c->d_chunkmin + (size_t)r * c->chunk_stride;
   }
-  CK(cudaMemcpyAsync(s->d_pickjobs, c->h_pick, R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(s->d_pickjobs, c->h_pick, J * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
   if (d->hard_has) {
     if (!d->hard_val) return fail(IQ_ERR_INVALID, "iq_sim_begin: hard_has without hard_val");
     CK(cudaStreamSynchronize(c->stream));  // h_pick is rewritten below

@@ -116,28 +116,37 @@ def test_config4_full_size_search_with_soft_variable(fft):
     m = slab_mask(tile, geo["ovlsize"], (1, 1, 1))
     r = np.random.default_rng(44)
     disabled = np.zeros(geo["distsize"], bool)
-    with api.SearchContext(ti, tile, auxti=[auxti], max_batch=2) as ctx:
+    with api.SearchContext(ti, tile, auxti=[auxti]) as ctx:
         ctx.set_option("fft", fft)
-        tiles, refs, scales = [], [], []
         for _ in range(2):
             p0 = tuple(int(r.integers(0, s)) for s in geo["distsize"])
             dev = ti[tuple(slice(a, a + b) for a, b in zip(p0, tile))].copy()
             q0 = tuple(int(r.integers(0, s)) for s in geo["distsize"])
             sdev = aux[tuple(slice(a, a + b) for a, b in zip(q0, tile))].copy()
-            tiles.append(dict(simdev=dev, softdev=[sdev]))
-            refs.append(O.search_tile(ti.astype(np.float64), dev.astype(np.float64), m, disabled, 0.1,
-                                      soft=[(auxti.astype(np.float64), sdev.astype(np.float64))], method="fft", workers=WORKERS))
-            scales.append([map_scale(ti, dev, m), map_scale(auxti, sdev, np.ones(tile, bool))])
-        u = r.random(2)
-        res = ctx.search(m, tiles, tol=0.1, u=u)
-        for i in range(2):
-            ndiff = assert_relaxation_band(res[i], refs[i], 0.1, scales[i])
-            assert res[i]["idx"].size > 100  # a real relaxation result, not a degenerate one
+            ref = O.search_tile(ti.astype(np.float64), dev.astype(np.float64), m, disabled, 0.1,
+                                soft=[(auxti.astype(np.float64), sdev.astype(np.float64))], method="fft", workers=WORKERS)
+            scales = [map_scale(ti, dev, m), map_scale(auxti, sdev, np.ones(tile, bool))]
+            u = float(r.random())
+            res = ctx.search(m, [dict(simdev=dev, softdev=[sdev])], tol=0.1, u=[u])[0]
+            ndiff = assert_relaxation_band(res, ref, 0.1, scales)
+            assert res["idx"].size > 100  # a real relaxation result, not a degenerate one
+            # tau model + sampling, exactly: the library's probabilities are src/taumodel.jl applied to the library's own
+            # (FP32) distance maps of the same launch shape, and the pick is StatsBase.sample's walk on them
+            dg = ctx.distance(-1, m, dev).astype(np.float64).ravel(order="F")
+            sg = ctx.distance(0, softdev=[sdev]).astype(np.float64).ravel(order="F")
+            check_map(dg, ref["D"], scales[0])
+            check_map(sg, ref["Ds"][0], scales[1])
+            own = O.taumodel(res["idx"], dg, [sg])
+            assert np.array_equal(res["prob"], own)
+            assert res["picked"] == int(res["idx"][O.sample_weighted(u, own)])
             if ndiff == 0:
-                # tau model: FP32 rounding can merge / swap ranks of candidates closer than the band, which moves a
-                # probability by O(1/n); everything else must agree
-                assert np.allclose(res[i]["prob"], refs[i]["probs"], rtol=2e-2, atol=0)
-                assert abs(res[i]["prob"].sum() - refs[i]["probs"].sum()) <= 1e-3 * refs[i]["probs"].sum()
+                # against the FP64 oracle: FP32 rounding merges the ranks of candidates closer than one ulp (ties share a
+                # rank, taumodel.jl:26-30), which shifts every later rank by the number of merges -- a change of O(merges / n)
+                # of the largest probability, not a relative one
+                assert np.abs(res["prob"] - ref["probs"]).max() <= 2e-2 * ref["probs"].max()
+                assert abs(res["prob"].sum() - ref["probs"].sum()) <= 2e-2 * ref["probs"].sum()
+                top = np.argsort(-ref["probs"])[:50]
+                assert np.allclose(res["prob"][top], ref["probs"][top], rtol=2e-2)
 
 
 # ---------------------------------------------------------------------------------------------------------------
