@@ -406,7 +406,8 @@ def main():
         "pipeline": "device-resident (iq_sim_*)" if is_resident else "host-staged (iq_search_pick per step)",
         "breakdown_ms_per_step": {k: sum(s["stats"][k] for s in stats) / args.steps
                                   for k in ("search_ms", "search_device_ms", "cut_ms", "setup_ms", "total_ms", "device_ms",
-                                            "select_ms", "cut_device_ms", "fetch_ms")},
+                                            "select_ms", "cut_device_ms", "fetch_ms", "run_ms", "teardown_ms")},
+        "schedule": {k: stats[0]["stats"][k] for k in ("dep_levels", "tiles_per_launch", "step_launches")},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -71,7 +71,9 @@ class IqhStats(C.Structure):
                 ("dist_launches", C.c_int64), ("fft_searches", C.c_int64), ("direct_searches", C.c_int64),
                 ("fft_bytes", C.c_double), ("fft_ms", C.c_double), ("resident", C.c_int32),
                 ("resident_status", C.c_int32), ("device_ms", C.c_double), ("select_ms", C.c_double),
-                ("cut_device_ms", C.c_double), ("fetch_ms", C.c_double), ("max_candidates", C.c_int64)]
+                ("cut_device_ms", C.c_double), ("fetch_ms", C.c_double), ("max_candidates", C.c_int64),
+                ("dep_levels", C.c_int32), ("tiles_per_launch", C.c_int32), ("step_launches", C.c_int64),
+                ("run_ms", C.c_double), ("teardown_ms", C.c_double)]
 
 
 # every symbol include/*.h declares: name -> (restype, argtypes)
@@ -95,6 +97,7 @@ SYMBOLS = {
     "iq_cut_batch": (C.c_int32, [C.c_void_p, C.POINTER(IqCutTask), C.c_int32, c_i32_p]),
     "iq_sim_begin": (C.c_int32, [C.c_void_p, C.POINTER(IqSimDesc)]),
     "iq_sim_step": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32, C.c_int32]),
+    "iq_sim_step_multi": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32]),
     "iq_sim_step_picked": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_i64_p]),
     "iq_sim_sync": (C.c_int32, [C.c_void_p, c_i64_p, c_i32_p]),
     "iq_sim_fetch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_i64_p, C.c_void_p]),
@@ -112,6 +115,7 @@ SYMBOLS = {
     "iq_ctx_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
     "iqh_run": (C.c_int32, [C.POINTER(IqhDesc), c_double_p, c_u8_p, c_i64_p, C.POINTER(IqhStats)]),
     "iqh_graphcut": (C.c_int32, [c_double_p, c_double_p, C.c_int32, c_i64_p, C.c_int32, c_u8_p]),
+    "iqh_dependency_levels": (C.c_int32, [C.c_int32, c_i64_p, c_i64_p, c_i64_p, c_i64_p, C.c_int64, c_i32_p, c_i32_p]),
 }
 
 _lib = None

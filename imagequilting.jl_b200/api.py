@@ -417,6 +417,21 @@ def voxelreuse_sweep(trainimg, *, tmin=None, tmax=None, overlap=None, nreal=10, 
     return dict(ts=np.asarray(ts), mu=np.asarray(mus), sigma=np.asarray(sigmas), best=(min(best), max(best)))
 
 
+def dependency_levels(tilesize, ovlsize, ntiles, path):
+    """Dependency level of every step of a simulation path (iqh_dependency_levels): steps of one level touch disjoint
+    windows of the simulation grid and are launched together by the device-resident pipeline."""
+    N = len(tilesize)
+    t = np.array(tilesize, dtype=np.int64)
+    o = np.array(ovlsize, dtype=np.int64)
+    n = np.array(ntiles, dtype=np.int64)
+    p = np.ascontiguousarray(path, dtype=np.int64)
+    lv = np.zeros(max(p.size, 1), dtype=np.int32)
+    nl = C.c_int32()
+    check(lib().iqh_dependency_levels(N, _ptr(t, c_i64_p), _ptr(o, c_i64_p), _ptr(n, c_i64_p), _ptr(p, c_i64_p), p.size,
+                                      _ptr(lv, c_i32_p), C.byref(nl)))
+    return lv[:p.size], nl.value
+
+
 def graphcut(A, B, dim):
     """Boundary cut keep-mask through the native host routine (src/graphcut.jl:5-84)."""
     A = _f(A, np.float64)

@@ -961,7 +961,7 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   for (auto& e : c->masks) {
     cudaFree(e->d_boxes);
     cudaFree(e->d_mask);
-    cudaFree(e->d_cut_tasks);
+    for (auto& ts : e->cut_sets) cudaFree(ts.d_tasks);
     for (auto& kv : e->a2) cudaFree(kv.second);
   }
   iqfft::plan_destroy(c->fft);

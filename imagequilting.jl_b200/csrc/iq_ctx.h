@@ -26,6 +26,14 @@ int fail(int code, const char* fmt, ...);
 
 using iq::BoxDesc;
 
+// Device cut task records for one (job count, slab set) of a mask.  The mask alone does not determine the slabs
+// (overlap >= 0.5: {px,nx,py} and {px,py,ny} cover the same voxels with different slab shapes), hence the signature.
+struct CutTaskSet {
+  std::vector<int> sig;                // jobs, nslab, then dim / n0 / n1 / L of every slab
+  iq::CutTask* d_tasks = nullptr;
+  size_t smem = 0;
+};
+
 struct MaskEntry {
   std::vector<uint8_t> mask;
   uint64_t hash = 0;
@@ -36,10 +44,7 @@ struct MaskEntry {
   long long tmpl_floats = 0;           // packed template floats per tile
   std::map<int, float*> a2;            // image id (-1 = TI, s = aux s) -> A2 map
   int WX = 1, WY = 1;
-  iq::CutTask* d_cut_tasks = nullptr;  // resident simulation: cut task records of this mask's slabs
-  int cut_ntask = 0;
-  size_t cut_smem = 0;
-  std::vector<int> cut_sig;            // slab signature (R, nslab, dim/n0/n1/L per slab) the cached records were built for
+  std::vector<CutTaskSet> cut_sets;    // resident simulation: cached cut task records of this mask's slab sets
 };
 
 struct TileResult {

@@ -158,6 +158,11 @@ extern "C" int32_t iqh_graphcut(const double* A, const double* B, int32_t ndim, 
 
 namespace {
 
+int fail_invalid(const char* msg) {
+  iq_post_error(msg);
+  return IQ_ERR_INVALID;
+}
+
 // Overlap slabs of tile `ind` with its already pasted neighbours (iqsim.jl:188-205) and the overlap mask.
 void tile_slabs(const Geo& G, const std::vector<uint8_t>& pasted, int64_t ind, std::vector<Slab>& slabs, std::vector<uint8_t>& mask,
                 int start[3]) {
@@ -196,6 +201,42 @@ bool image_is_integer(const iqh_desc* D, const Geo& G) {
   return true;
 }
 
+// Dependency levels of a simulation path.  A tile reads (template, slabs) and writes (paste) only its own window, so it
+// depends exactly on the tiles EARLIER IN THE PATH whose windows intersect its own: level = 1 + max level of those (0
+// without any).  Tiles of one level are mutually independent (two tiles with intersecting windows are ordered by the
+// path, hence on different levels), and running the levels in order -- each as one batch -- gives bit for bit the
+// result of the sequential path.  On a raster path the level of tile (i, j, k) is i + 2j + 4k (3-D) / i + 2j (2-D): 50
+// levels instead of 512 sequential steps on an 8 x 8 x 8 grid.  Returns the number of levels, -1 on a bad path.
+int dependency_levels(const Geo& G, const int64_t* path, int64_t npath, std::vector<int>& level) {
+  level.assign((size_t)npath, 0);
+  std::vector<int64_t> step_of((size_t)G.ntile_total, -1);
+  const long long tstride[3] = {1, G.nt[0], (long long)G.nt[0] * G.nt[1]};
+  int reach[3];  // windows of tiles up to `reach` indices apart along a dimension intersect
+  for (int d = 0; d < 3; ++d) reach[d] = G.sp[d] > 0 ? std::min(G.nt[d] - 1, (G.t[d] + G.sp[d] - 1) / G.sp[d] - 1) : G.nt[d] - 1;
+  int nlevels = 0;
+  for (int64_t step = 0; step < npath; ++step) {
+    const int64_t ind = path[step];
+    if (ind < 0 || ind >= G.ntile_total || step_of[(size_t)ind] >= 0) return -1;
+    const int ti3[3] = {(int)(ind % G.nt[0]), (int)((ind / G.nt[0]) % G.nt[1]), (int)(ind / ((long long)G.nt[0] * G.nt[1]))};
+    int lv = 0;
+    for (int dz = -reach[2]; dz <= reach[2]; ++dz)
+      for (int dy = -reach[1]; dy <= reach[1]; ++dy)
+        for (int dx = -reach[0]; dx <= reach[0]; ++dx) {
+          const int q[3] = {ti3[0] + dx, ti3[1] + dy, ti3[2] + dz};
+          if (q[0] < 0 || q[1] < 0 || q[2] < 0 || q[0] >= G.nt[0] || q[1] >= G.nt[1] || q[2] >= G.nt[2]) continue;
+          const int64_t so = step_of[(size_t)(q[0] * tstride[0] + q[1] * tstride[1] + q[2] * tstride[2])];
+          if (so < 0) continue;  // not visited yet (or skipped): no dependency
+          // windows [i * sp, i * sp + t) intersect along every dimension?
+          const bool apart = std::abs(dx) * G.sp[0] >= G.t[0] || std::abs(dy) * G.sp[1] >= G.t[1] || std::abs(dz) * G.sp[2] >= G.t[2];
+          if (!apart) lv = std::max(lv, level[(size_t)so] + 1);
+        }
+    level[(size_t)step] = lv;
+    nlevels = std::max(nlevels, lv + 1);
+    step_of[(size_t)ind] = step;
+  }
+  return nlevels;
+}
+
 // Device-resident pipeline: every lockstep group owns a context whose stream carries the whole simulation of its
 // realizations (iq_sim_*); this thread only enqueues.  Returns IQ_ERR_STATE when the simulation does not qualify
 // (the caller then runs host-staged), `*status` != 0 when a data-dependent condition invalidated the result.
@@ -217,6 +258,27 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   // of 16 on config 5, at the price of per-kernel timings that no longer describe a kernel alone.
   int ngroups = D->ngroups > 0 ? D->ngroups : 1;
   ngroups = std::max(1, std::min(ngroups, R));
+  // Tiles per launch (dependency-level batching, see below): a launch carries tiles x realizations jobs.  Soft data keep
+  // one tile per launch (one auxiliary map per source is kept).  IQB200_JOBS overrides the job slots per launch.
+  const int Rg = (R + ngroups - 1) / ngroups;
+  int tiles_per_launch = 1;
+  if (S == 0) {
+    int jobs_cap = 256;
+    if (const char* ev = std::getenv("IQB200_JOBS")) jobs_cap = std::max(1, std::atoi(ev));
+    tiles_per_launch = (int)std::max<long long>(1, std::min<long long>(jobs_cap / std::max(Rg, 1), G.ntile_total));
+    // device memory: every job slot holds an overlap map, a candidate list with values, radix-select scratch, its
+    // share of the FFT work space and its cut slabs
+    const double npos = (double)G.dist[0] * G.dist[1] * G.dist[2];
+    auto p2 = [](int n) { double v = 1; while (v < n) v *= 2; return v; };
+    const double fftws = 8.0 * p2(G.n[0]) * ((double)G.t[2] * G.t[1] + (G.n[2] > 1 ? (double)G.t[2] * p2(G.n[1]) + 2.0 * G.dist[2] * p2(G.n[1]) : 0.0) +
+                                              (double)G.dist[2] * G.dist[1]) / 2.0;
+    const double per_job = npos * 4.0 * 6.0 + npos / 16.0 * 8.0 * 2.0 + fftws + 6.0 * 17.0 * G.tilevol + 2.0 * 32768 * 12.0;
+    size_t free_b = 0, total_b = 0;
+    if (iq_device_free_memory(D->device, &free_b, &total_b) == IQ_OK) {
+      const double budget = 0.6 * (double)free_b - (double)R * 8.0 * G.padvol;
+      while (tiles_per_launch > 1 && (double)tiles_per_launch * Rg * ngroups * per_job > budget) --tiles_per_launch;
+    }
+  }
   struct RG { iq_ctx* ctx = nullptr; int r0 = 0, R = 0; };
   std::vector<RG> groups(ngroups);
   auto destroy_all = [&] {
@@ -237,7 +299,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     cd.nsoft = S;
     cd.auxti = D->auxti;
     cd.device = D->device;
-    cd.max_batch = g.R;
+    cd.max_batch = g.R * tiles_per_launch;
     rc = iq_ctx_create(&g.ctx, &cd);
     if (rc != IQ_OK) break;
     iq_ctx_set_option(g.ctx, "fft", D->fft_mode);
@@ -257,53 +319,122 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   if (rc != IQ_OK) { destroy_all(); return rc; }
   const double setup_ms = ms_since(t_setup);
 
+  // ---- what depends on the path alone, for every step (iqsim.jl:172-205): tile origin, slabs / overlap mask from the
+  //      neighbours pasted EARLIER IN THE PATH, hard-data flag ----
+  struct StepInfo {
+    int64_t ind;
+    int start[3];
+    unsigned key;      // bit 2d: overlap with the previous tile along d, bit 2d+1: with the next one (fixes slabs and mask)
+    bool hard_tile, host_pick;
+    int level;
+  };
+  std::vector<int> levels;
+  const int nlevels = dependency_levels(G, D->path, D->npath, levels);
+  if (nlevels < 0) { destroy_all(); return fail_invalid("iqh_run: path holds an out-of-range or repeated tile index"); }
+  std::vector<StepInfo> steps((size_t)D->npath);
   std::vector<uint8_t> pasted((size_t)G.ntile_total, 0), mask((size_t)G.tilevol);
   std::vector<Slab> slabs;
   std::vector<iq_sim_slab> sl;
+  for (int64_t step = 0; step < D->npath && rc == IQ_OK; ++step) {
+    const int64_t ind = D->path[step];
+    StepInfo& si = steps[(size_t)step];
+    si.ind = ind;
+    tile_slabs(G, pasted, ind, slabs, mask, si.start);
+    si.key = 0;
+    for (const Slab& sb : slabs) si.key |= 1u << (2 * sb.d + (sb.prev ? 0 : 1));
+    // does the tile contain hard data?  (indicator!, utils.jl:31-36: the same for every realization)
+    si.hard_tile = false;
+    if (D->hard_has) {
+      for (int z = 0; z < G.t[2] && !si.hard_tile; ++z)
+        for (int y = 0; y < G.t[1] && !si.hard_tile; ++y) {
+          const uint8_t* row = D->hard_has + ((long long)(si.start[2] + z) * G.pad[1] + (si.start[1] + y)) * G.pad[0] + si.start[0];
+          for (int x = 0; x < G.t[0]; ++x)
+            if (row[x]) { si.hard_tile = true; break; }
+        }
+    }
+    si.host_pick = S > 0 && slabs.empty() && !si.hard_tile;
+    si.level = levels[(size_t)step];
+    pasted[(size_t)ind] = 1;
+  }
+  // launch order: level by level; inside a level the tiles that share slabs / mask are batched (path order otherwise)
+  std::vector<int64_t> order((size_t)D->npath);
+  for (int64_t i = 0; i < D->npath; ++i) order[(size_t)i] = i;
+  const bool batching = tiles_per_launch > 1;
+  if (batching)
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      const StepInfo &x = steps[(size_t)a], &y = steps[(size_t)b];
+      if (x.level != y.level) return x.level < y.level;
+      return x.key < y.key;
+    });
   std::vector<float> zero_tile((size_t)G.tilevol, 0.f);
   std::vector<std::vector<float>> soft_tile((size_t)S, std::vector<float>((size_t)G.tilevol));
   std::vector<const float*> soft_ptr((size_t)S, nullptr);
-  int64_t launches = 0;
+  std::vector<int64_t> bsteps, bstarts;
+  int64_t launches = 0, nlaunch_steps = 0;
   const auto t_enq = clk::now();
-  for (int64_t step = 0; step < D->npath && rc == IQ_OK; ++step) {
-    const int64_t ind = D->path[step];
-    if (ind < 0 || ind >= G.ntile_total) { rc = IQ_ERR_INVALID; break; }
-    int start[3];
-    tile_slabs(G, pasted, ind, slabs, mask, start);
+  for (size_t oi = 0; oi < order.size() && rc == IQ_OK;) {
+    const StepInfo& si = steps[(size_t)order[oi]];
+    const int64_t step = order[oi];
+    // slabs and mask of this step, rebuilt from the key (all tiles of a batch share them)
+    slabs.clear();
+    for (int d = 0; d < G.N; ++d) {
+      if ((si.key >> (2 * d)) & 1u) {
+        Slab sb{d, true, {0, 0, 0}, {G.t[0], G.t[1], G.t[2]}};
+        sb.sz[d] = G.ov[d];
+        slabs.push_back(sb);
+      }
+      if ((si.key >> (2 * d + 1)) & 1u) {
+        Slab sb{d, false, {0, 0, 0}, {G.t[0], G.t[1], G.t[2]}};
+        sb.lo[d] = G.sp[d];
+        sb.sz[d] = G.t[d] - G.sp[d];
+        slabs.push_back(sb);
+      }
+    }
+    std::fill(mask.begin(), mask.end(), 0);
+    for (const Slab& sb : slabs)
+      for (int z = sb.lo[2]; z < sb.lo[2] + sb.sz[2]; ++z)
+        for (int y = sb.lo[1]; y < sb.lo[1] + sb.sz[1]; ++y)
+          std::memset(&mask[((size_t)z * G.t[1] + y) * G.t[0] + sb.lo[0]], 1, (size_t)sb.sz[0]);
     sl.resize(slabs.size());
     for (size_t k = 0; k < slabs.size(); ++k) {
       sl[k].dim = slabs[k].d;
       sl[k].prev = slabs[k].prev ? 1 : 0;
       for (int i = 0; i < 3; ++i) { sl[k].lo[i] = slabs[k].lo[i]; sl[k].sz[i] = slabs[k].sz[i]; }
     }
+    const int* start = si.start;
     const int64_t st64[3] = {start[0], start[1], start[2]};
-    // does the tile contain hard data?  (indicator!, utils.jl:31-36: the same for every realization)
-    bool hard_tile = false;
-    if (D->hard_has) {
-      for (int z = 0; z < G.t[2] && !hard_tile; ++z)
-        for (int y = 0; y < G.t[1] && !hard_tile; ++y) {
-          const uint8_t* row = D->hard_has + ((long long)(start[2] + z) * G.pad[1] + (start[1] + y)) * G.pad[0] + start[0];
-          for (int x = 0; x < G.t[0]; ++x)
-            if (row[x]) { hard_tile = true; break; }
-        }
+    // the batch: following steps of the same level and key (no hard / soft data)
+    size_t oe = oi + 1;
+    if (batching && !si.hard_tile && !si.host_pick && S == 0)
+      while (oe < order.size() && (int)(oe - oi) < tiles_per_launch) {
+        const StepInfo& o = steps[(size_t)order[oe]];
+        if (o.level != si.level || o.key != si.key || o.hard_tile) break;
+        ++oe;
+      }
+    const int ntile = (int)(oe - oi);
+    bsteps.resize((size_t)ntile);
+    bstarts.resize((size_t)ntile * 3);
+    for (int k = 0; k < ntile; ++k) {
+      const StepInfo& o = steps[(size_t)order[oi + k]];
+      bsteps[(size_t)k] = order[oi + k];
+      for (int i = 0; i < 3; ++i) bstarts[(size_t)k * 3 + i] = o.start[i];
     }
-    const bool host_pick = S > 0 && slabs.empty() && !hard_tile;
-    if (host_pick) {
+    if (si.host_pick) {
       // Soft data and nothing pasted around the tile: the candidate set is a tenth of all patterns (relaxation.jl:11,20),
       // far above the device tau model.  One search (the tile is the same for every realization), the sampling walk
       // per realization on the host, and the picks handed to the device (iq_sim_step_picked).
       std::fill(zero_tile.begin(), zero_tile.end(), 0.f);
-      for (int s = 0; s < S; ++s) {
+      for (int sidx = 0; sidx < S; ++sidx) {
         for (int z = 0; z < G.t[2]; ++z)
           for (int y = 0; y < G.t[1]; ++y) {
             const long long gi = ((long long)(start[2] + z) * G.pad[1] + (start[1] + y)) * G.pad[0] + start[0];
-            std::memcpy(&soft_tile[s][((size_t)z * G.t[1] + y) * G.t[0]], D->aux[s] + gi, sizeof(float) * G.t[0]);
+            std::memcpy(&soft_tile[sidx][((size_t)z * G.t[1] + y) * G.t[0]], D->aux[sidx] + gi, sizeof(float) * G.t[0]);
           }
-        soft_ptr[s] = soft_tile[s].data();
+        soft_ptr[sidx] = soft_tile[sidx].data();
       }
     }
     for (auto& g : groups) {
-      if (host_pick) {
+      if (si.host_pick) {
         iq_tile tile{};
         tile.simdev = zero_tile.data();
         tile.softdev = soft_ptr.data();
@@ -318,8 +449,10 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
           pk[(size_t)r] = res.idx[pos];
         }
         if (rc == IQ_OK) rc = iq_sim_step_picked(g.ctx, step, st64, pk.data());
+      } else if (ntile == 1) {
+        rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size(), si.hard_tile ? 1 : 0);
       } else {
-        rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size(), hard_tile ? 1 : 0);
+        rc = iq_sim_step_multi(g.ctx, ntile, bsteps.data(), bstarts.data(), mask.data(), sl.data(), (int32_t)sl.size());
       }
       if (rc != IQ_OK) break;
       double dms = 0;
@@ -327,7 +460,8 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
       iq_last_search_stats(g.ctx, &dms, &nl);
       launches += nl;
     }
-    pasted[(size_t)ind] = 1;
+    ++nlaunch_steps;
+    oi = oe;
   }
   const double enqueue_ms = ms_since(t_enq);
   double device_ms = 0, dist_ms = 0, select_ms = 0, cut_ms = 0, fft_bytes = 0, fft_ms = 0;
@@ -367,7 +501,9 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     }
   }
   const double fetch_ms = ms_since(t_fetch);
+  const auto t_down = clk::now();
   destroy_all();
+  const double teardown_ms = ms_since(t_down);
   if (rc != IQ_OK) return rc;
   if (stats && *status == 0) {
     std::memset(stats, 0, sizeof *stats);
@@ -389,7 +525,11 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     stats->select_ms = select_ms;
     stats->cut_device_ms = cut_ms;
     stats->fetch_ms = fetch_ms;
-    (void)run_ms;
+    stats->teardown_ms = teardown_ms;
+    stats->run_ms = run_ms;
+    stats->dep_levels = nlevels;
+    stats->tiles_per_launch = tiles_per_launch;
+    stats->step_launches = nlaunch_steps;
   }
   return IQ_OK;
 }
@@ -456,12 +596,32 @@ int run_resident_waves(const iqh_desc* D, const Geo& G, double* out_grids, uint8
     acc.direct_searches += st.direct_searches; acc.fft_bytes += st.fft_bytes; acc.fft_ms += st.fft_ms;
     acc.device_ms += st.device_ms; acc.select_ms += st.select_ms; acc.cut_device_ms += st.cut_device_ms;
     acc.fetch_ms += st.fetch_ms;
+    acc.teardown_ms += st.teardown_ms; acc.run_ms += st.run_ms;
+    acc.dep_levels = st.dep_levels; acc.tiles_per_launch = st.tiles_per_launch; acc.step_launches += st.step_launches;
   }
   if (stats) *stats = acc;
   return IQ_OK;
 }
 
 }  // namespace
+
+extern "C" int32_t iqh_dependency_levels(int32_t ndim, const int64_t* tile_size, const int64_t* ovl_size, const int64_t* ntiles,
+                                         const int64_t* path, int64_t npath, int32_t* levels, int32_t* nlevels) {
+  if (ndim < 1 || ndim > 3 || !tile_size || !ovl_size || !ntiles || (npath > 0 && (!path || !levels))) return IQ_ERR_INVALID;
+  Geo G{};
+  G.N = ndim;
+  for (int i = 0; i < 3; ++i) { G.t[i] = G.nt[i] = 1; G.ov[i] = 1; }
+  for (int i = 0; i < ndim; ++i) { G.t[i] = (int)tile_size[i]; G.ov[i] = (int)ovl_size[i]; G.nt[i] = (int)ntiles[i]; }
+  for (int i = 0; i < 3; ++i) G.sp[i] = G.t[i] - G.ov[i];
+  for (int i = ndim; i < 3; ++i) G.sp[i] = 1;
+  G.ntile_total = (long long)G.nt[0] * G.nt[1] * G.nt[2];
+  std::vector<int> lv;
+  const int n = dependency_levels(G, path, npath, lv);
+  if (n < 0) return fail_invalid("iqh_dependency_levels: path holds an out-of-range or repeated tile index");
+  for (int64_t i = 0; i < npath; ++i) levels[i] = lv[(size_t)i];
+  if (nlevels) *nlevels = n;
+  return IQ_OK;
+}
 
 extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats) {
   if (!D || !D->ti || !D->ti_f32 || !D->path || !D->u) return IQ_ERR_INVALID;

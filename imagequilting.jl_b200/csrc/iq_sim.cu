@@ -468,9 +468,8 @@ void sim_destroy(iq_ctx* c) {
   c->sim = nullptr;
   // the task records cached per mask point into the freed slab buffers
   for (auto& e : c->masks) {
-    cudaFree(e->d_cut_tasks);
-    e->d_cut_tasks = nullptr;
-    e->cut_ntask = 0;
+    for (auto& ts : e->cut_sets) cudaFree(ts.d_tasks);
+    e->cut_sets.clear();
   }
 }
 
@@ -654,22 +653,43 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   return IQ_OK;
 }
 
-int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
-                    int32_t nslab, int32_t hard_tile) {
-  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step: no simulation open on this context");
+// One launch of `ntile` mutually independent tiles (no two windows intersect) that share the overlap mask and the slab
+// set: ntile x R jobs, job j = tile j / R of realization j % R.  Tiles with hard data and contexts with soft data take
+// one tile per launch (their auxiliary maps belong to the tile, and one map per source is kept).
+static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64_t* starts, const uint8_t* ovlmask,
+                         const iq_sim_slab* slabs, int32_t nslab, int32_t hard_tile) {
   SimState* s = c->sim;
-  if (!start || !ovlmask || nslab < 0 || nslab > 6 || (nslab > 0 && !slabs)) return fail(IQ_ERR_INVALID, "iq_sim_step: bad argument");
-  if (step < 0 || step >= s->npath) return fail(IQ_ERR_INVALID, "iq_sim_step: step out of range");
-  if (hard_tile && !s->d_hard_has) return fail(IQ_ERR_INVALID, "iq_sim_step: hard_tile on a simulation opened without hard data");
   const bool hardt = hard_tile != 0;
+  const int R = s->R;
+  if (ntile < 1 || (long long)ntile * R > s->J)
+    return fail(IQ_ERR_INVALID, "iq_sim_step: %d tiles x %d realizations exceed the %d job slots (max_batch) of the context", ntile, R, s->J);
+  if ((hardt || s->S > 0) && ntile != 1)
+    return fail(IQ_ERR_INVALID, "iq_sim_step_multi: tiles with hard data / contexts with soft data take one tile per step");
+  if (s->tile_cursor + (size_t)ntile > (size_t)std::max<int64_t>(s->npath, 1))
+    return fail(IQ_ERR_STATE, "iq_sim_step: more tiles launched than path steps declared at iq_sim_begin");
   CK(cudaSetDevice(c->device));
   const int t[3] = {c->tx, c->ty, c->tz};
-  int st3[3] = {0, 0, 0};
-  for (int i = 0; i < c->ndim; ++i) {
-    st3[i] = (int)start[i];
-    if (st3[i] < 0 || st3[i] + t[i] > s->pad[i]) return fail(IQ_ERR_INVALID, "iq_sim_step: tile outside the padded grid");
+  TileInfo* ht = s->h_tiles + s->tile_cursor;
+  for (int k = 0; k < ntile; ++k) {
+    if (steps[k] < 0 || steps[k] >= s->npath) return fail(IQ_ERR_INVALID, "iq_sim_step: step out of range");
+    int st3[3] = {0, 0, 0};
+    for (int i = 0; i < c->ndim; ++i) {
+      st3[i] = (int)starts[3 * k + i];
+      if (st3[i] < 0 || st3[i] + t[i] > s->pad[i]) return fail(IQ_ERR_INVALID, "iq_sim_step: tile outside the padded grid");
+    }
+    ht[k].sx = st3[0]; ht[k].sy = st3[1]; ht[k].sz = st3[2]; ht[k].step = (int)steps[k];
+    for (int m = 0; m < k; ++m) {  // the tiles of one launch read and write disjoint windows
+      const bool apart = std::abs(ht[m].sx - st3[0]) >= t[0] || std::abs(ht[m].sy - st3[1]) >= t[1] || std::abs(ht[m].sz - st3[2]) >= t[2];
+      if (!apart) return fail(IQ_ERR_INVALID, "iq_sim_step_multi: tiles %d and %d overlap; only independent tiles can share a step", m, k);
+    }
   }
-  const int R = s->R;
+  const TileInfo* dt = s->d_tiles + s->tile_cursor;
+  CK(cudaMemcpyAsync(s->d_tiles + s->tile_cursor, ht, (size_t)ntile * sizeof(TileInfo), cudaMemcpyHostToDevice, c->stream));
+  const size_t cursor0 = s->tile_cursor;
+  s->tile_cursor += (size_t)ntile;
+  const int st3[3] = {ht[0].sx, ht[0].sy, ht[0].sz};  // single-tile paths (hard / soft data)
+  const int64_t step = steps[0];
+  const int NJ = ntile * R;  // jobs of this launch
   s->synced = false;
   MaskEntry* e = nullptr;
   int rc = get_mask(c, ovlmask, &e);
@@ -704,7 +724,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
   }
   if (nslab > s->maxslabs) return fail(IQ_ERR_INVALID, "iq_sim_step: too many slabs");
 
-  const unsigned gR = (unsigned)((R + 127) / 128);
+  const unsigned gJ = (unsigned)((NJ + 127) / 128);
   if (e->nnz == 0 && s->S == 0 && !hardt) {
     // nothing pasted around the tile: every enabled patch with equal probability (iqsim.jl:237 on an all-zero map);
     // the walk is evaluated on the host from the cached cumulative weights
@@ -712,15 +732,15 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
     if (rc) return rc;
     const int64_t n = (int64_t)c->enabled_idx.size();
     if (n == 0) return fail(IQ_ERR_INVALID, "all patches of the training image are disabled");
-    long long* hp = s->h_pickstage + (size_t)step * R;
-    for (int r = 0; r < R; ++r) {
-      const double tt = s->h_u[(size_t)r * s->npath + step] * c->uniform_sum;
+    long long* hp = s->h_pickstage + cursor0 * R;
+    for (int j = 0; j < NJ; ++j) {
+      const double tt = s->h_u[(size_t)(j % R) * s->npath + ht[j / R].step] * c->uniform_sum;
       const auto it = std::lower_bound(c->uniform_cum.begin(), c->uniform_cum.end() - 1, tt);
-      hp[r] = c->enabled_idx[(size_t)(it - c->uniform_cum.begin())];
+      hp[j] = c->enabled_idx[(size_t)(it - c->uniform_cum.begin())];
     }
     CK(cudaEventRecord(ev[0], c->stream));
-    CK(cudaMemcpyAsync(s->d_picked, hp, (size_t)R * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-    k_sim_store_picks<<<gR, 128, 0, c->stream>>>(s->d_picked, s->d_picks, s->npath, step, R);
+    CK(cudaMemcpyAsync(s->d_picked, hp, (size_t)NJ * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    k_sim_store_picks<<<gJ, 128, 0, c->stream>>>(s->d_picked, s->d_picks, s->npath, dt, R, NJ);
     CK(cudaGetLastError());
     c->launches++;
   } else {
@@ -752,17 +772,17 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       }
       return launch_direct(c, me, image, s->d_pack, d_b2, nt, rb, false, d_out, kind);
     };
-    k_sim_templates<double><<<dim3((unsigned)c->tz, (unsigned)R), 256, 0, c->stream>>>(
-        s->d_grid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], e->d_mask, c->tx, c->ty, c->tz, s->d_tmpl,
+    k_sim_templates<double><<<dim3((unsigned)c->tz, (unsigned)NJ), 256, 0, c->stream>>>(
+        s->d_grid, s->padvol, s->pad[0], s->pad[1], dt, R, e->d_mask, c->tx, c->ty, c->tz, s->d_tmpl,
         s->d_plane, s->d_b2, s->d_ticket);
     CK(cudaGetLastError());
     c->launches += 1;
     bool done = false;
-    if (want_fft(c, e, R)) {
+    if (want_fft(c, e, NJ)) {
       rc = ensure_fft(c, -1);
       if (rc == IQ_OK) {
         // templates are copies of training-image voxels (or zeros): integer-valued whenever the image is
-        rc = launch_fft(c, e, -1, s->d_tmpl, s->d_b2, R, c->image_is_int[-1], c->d_Dovl, 0);
+        rc = launch_fft(c, e, -1, s->d_tmpl, s->d_b2, NJ, c->image_is_int[-1], c->d_Dovl, 0);
         if (rc) return rc;
         done = true;
       } else if (!(rc == IQ_ERR_STATE && c->fft_failed)) {
@@ -770,7 +790,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       }
     }
     if (!done) {
-      rc = direct(e, -1, s->d_tmpl, s->d_b2, R, c->d_Dovl, 0);
+      rc = direct(e, -1, s->d_tmpl, s->d_b2, NJ, c->d_Dovl, 0);
       if (rc) return rc;
     }
     // hard-data distance (iqsim.jl:210-219): the data are the same for every realization -> one map per step
@@ -796,7 +816,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
     // soft-data distances (iqsim.jl:222-227): the auxiliary tile is the same for every realization -> one map per step
     for (int si = 0; si < s->S; ++si) {
       k_sim_templates<float><<<dim3((unsigned)c->tz, 1u), 256, 0, c->stream>>>(
-          s->d_aux_pad[si], 0, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], c->full_mask->d_mask, c->tx, c->ty, c->tz,
+          s->d_aux_pad[si], 0, s->pad[0], s->pad[1], dt, 1, c->full_mask->d_mask, c->tx, c->ty, c->tz,
           s->d_soft_tmpl, s->d_soft_plane, s->d_soft_b2, s->d_soft_ticket);
       CK(cudaGetLastError());
       c->launches++;
@@ -819,9 +839,9 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
     CK(cudaEventRecord(ev[0], c->stream));
     iq::PickJob* pj = hardt ? s->d_pickjobs_hard : s->d_pickjobs;
     if (s->S == 0 && !hardt) {
-      rc = ensure_chunkmin(c, R);
+      rc = ensure_chunkmin(c, NJ);
       if (rc) return rc;
-      CK(iq::launch_pick_chunks(pj, R, c->npos, c->chunk_len, c->chunk_n, c->stream));
+      CK(iq::launch_pick_chunks(pj, NJ, c->npos, c->chunk_len, c->chunk_n, c->stream));
       c->launches += 1;
     } else {
       // sources shared by all realizations: the hard map (source 0 of a hard tile) and every soft map
@@ -834,9 +854,11 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       // relaxation rounds on the device: kRelaxRounds rounds are enqueued unconditionally, the kernels of a round
       // return at once for realizations that already have candidates; a realization still empty after the last
       // round raises the status word (the caller then reruns host-staged, where the round count is unbounded)
-      // (5 rounds normally, frac up to 0.4 + 0.1 tol; tiles with hard data or an empty overlap mask often need many -- an all-zero overlap map
-      // selects an index prefix -- and get all 11, after which frac = 1 guarantees a non-empty intersection)
+      // (5 rounds normally, frac up to 0.4 + 0.1 tol; tiles with hard data or an empty overlap mask often need many -- an
+      // all-zero overlap map selects an index prefix -- and get all 11, after which frac = 1 guarantees a non-empty
+      // intersection)
       const int kRelaxRounds = (hardt || e->nnz == 0) ? 11 : 5;
+      const unsigned gR = (unsigned)((R + 127) / 128);
       for (int round = 0; round < kRelaxRounds; ++round) {
         k_sim_seljobs<<<R, 32, 0, c->stream>>>(c->d_sel, pj, c->max_src, pmax, pmax_stride, shared_mask, s->tol, c->nenabled,
                                               c->npos, round, s->d_pending, c->d_selbuf, c->sel_cap);
@@ -856,9 +878,9 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       CK(iq::launch_pick_write(pj, R, c->npos, c->stream));
       c->launches += 1;
     }
-    CK(iq::launch_tau(pj, R, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
-    k_sim_sample<<<(unsigned)((R + 3) / 4), 128, 0, c->stream>>>(pj, c->d_prob, s->d_u, s->npath, step, R,
-                                                                 s->d_picked, s->d_picks, s->d_status);
+    CK(iq::launch_tau(pj, NJ, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
+    k_sim_sample<<<(unsigned)((NJ + 3) / 4), 128, 0, c->stream>>>(pj, c->d_prob, s->d_u, s->npath, dt, R, NJ,
+                                                                  s->d_picked, s->d_picks, s->d_status);
     CK(cudaGetLastError());
     c->launches += 3;
   }
@@ -866,23 +888,26 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
 
   // ---- boundary cuts ----
   if (nslab > 0) {
-    const int ntask = R * nslab;
-    k_sim_slabs<<<ntask, 256, 0, c->stream>>>(s->d_grid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], s->d_ti64,
+    const int ntask = NJ * nslab;
+    k_sim_slabs<<<ntask, 256, 0, c->stream>>>(s->d_grid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_ti64,
                                               c->nx, c->ny, c->nxo, c->nyo, s->d_picked, c->tx, c->ty, S, s->d_cutA, s->d_cutB,
                                               (long long)s->maxslab);
     CK(cudaGetLastError());
-    // task records depend on the slab set (dimension and extent of every slab) and R only; they are cached with the
-    // mask, but the mask alone does not determine the slabs (overlap >= 0.5: {px,nx,py} and {px,py,ny} cover the same
-    // voxels with different slab shapes), so the cache is keyed on the slab signature
+    // Task records depend on the slab set (dimension and extent of every slab) and the job count only; they are cached
+    // with the mask, but the mask alone does not determine the slabs (overlap >= 0.5: {px,nx,py} and {px,py,ny} cover
+    // the same voxels with different slab shapes), so every cached set carries its slab signature.
     std::vector<int> sig;
     sig.reserve(2 + 4 * (size_t)nslab);
-    sig.push_back(R);
+    sig.push_back(NJ);
     sig.push_back(nslab);
     for (int k = 0; k < nslab; ++k) { sig.push_back(S.s[k].dim); sig.push_back(S.s[k].n0); sig.push_back(S.s[k].n1); sig.push_back(S.s[k].L); }
-    if (!e->d_cut_tasks || e->cut_ntask != ntask || e->cut_sig != sig) {
-      // Launch order = longest first: the slabs with the most inner voxels of ALL realizations lead, the cheap ones
-      // (e.g. the one-layer z slabs) come last and fill the second wave (one CTA per SM: 192 cuts on 148 SMs), so the
-      // tail of the launch is made of short cuts.  Only the order of the records changes, not where a task's data is.
+    CutTaskSet* ts = nullptr;
+    for (auto& cand : e->cut_sets)
+      if (cand.sig == sig) { ts = &cand; break; }
+    if (!ts) {
+      // Launch order = longest first: the slabs with the most inner voxels of ALL jobs lead, the cheap ones (e.g. the
+      // one-layer z slabs) come last and fill the tail of the launch.  Only the order of the records changes, not
+      // where a task's data is.
       std::vector<int> sorder(nslab);
       for (int i = 0; i < nslab; ++i) sorder[i] = i;
       std::stable_sort(sorder.begin(), sorder.end(), [&](int a, int b) {
@@ -890,7 +915,7 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
       });
       std::vector<iq::CutTask> recs((size_t)ntask);
       for (int b = 0; b < ntask; ++b) {
-        const int k = (b % R) * nslab + sorder[b / R];  // task whose record sits at launch position b
+        const int k = (b % NJ) * nslab + sorder[b / NJ];  // task whose record sits at launch position b
         const SlabDev& o = S.s[k % nslab];
         iq::CutTask& rec = recs[b];
         rec.A = s->d_cutA + (size_t)k * s->maxslab;
@@ -899,26 +924,43 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
         rec.n0 = o.n0; rec.n1 = o.n1; rec.L = o.L;
         rec.iters = s->d_cut_iters + k;
       }
-      CK(cudaStreamSynchronize(c->stream));
-      cudaFree(e->d_cut_tasks);
-      e->d_cut_tasks = nullptr;
-      CK(iq::dmalloc((void**)&e->d_cut_tasks, recs.size() * sizeof(iq::CutTask)));
-      CK(cudaMemcpy(e->d_cut_tasks, recs.data(), recs.size() * sizeof(iq::CutTask), cudaMemcpyHostToDevice));
-      e->cut_ntask = ntask;
-      e->cut_smem = smem;
-      e->cut_sig = sig;
+      e->cut_sets.emplace_back();
+      ts = &e->cut_sets.back();
+      ts->sig = sig;
+      ts->smem = smem;
+      CK(iq::dmalloc((void**)&ts->d_tasks, recs.size() * sizeof(iq::CutTask)));
+      // pageable source: the copy is staged before the call returns, and it is ordered on the stream before the launch
+      CK(cudaMemcpyAsync(ts->d_tasks, recs.data(), recs.size() * sizeof(iq::CutTask), cudaMemcpyHostToDevice, c->stream));
     }
-    CK(iq::launch_graphcut(e->d_cut_tasks, ntask, std::max<size_t>(e->cut_smem, 64), c->stream));
+    CK(iq::launch_graphcut(ts->d_tasks, ntask, std::max<size_t>(ts->smem, 64), c->stream));
     c->launches += 2;
   }
   CK(cudaEventRecord(ev[2], c->stream));
-  k_sim_paste<<<dim3((unsigned)((c->tilevol + 255) / 256), (unsigned)R), 256, 0, c->stream>>>(
-      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], s->d_ti64, c->nx, c->ny, c->nxo, c->nyo,
+  k_sim_paste<<<dim3((unsigned)((c->tilevol + 255) / 256), (unsigned)NJ), 256, 0, c->stream>>>(
+      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_ti64, c->nx, c->ny, c->nxo, c->nyo,
       s->d_picked, c->tx, c->ty, c->tz, S, s->d_keep, (long long)s->maxslab, s->d_cut_iters, s->d_status);
   CK(cudaGetLastError());
   c->launches++;
   c->last_launches = c->launches - l0;
+  (void)step;
   return IQ_OK;
+}
+
+int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
+                    int32_t nslab, int32_t hard_tile) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step: no simulation open on this context");
+  if (!start || !ovlmask || nslab < 0 || nslab > 6 || (nslab > 0 && !slabs)) return fail(IQ_ERR_INVALID, "iq_sim_step: bad argument");
+  if (hard_tile && !c->sim->d_hard_has) return fail(IQ_ERR_INVALID, "iq_sim_step: hard_tile on a simulation opened without hard data");
+  const int64_t st[3] = {start[0], c->ndim > 1 ? start[1] : 0, c->ndim > 2 ? start[2] : 0};
+  return sim_step_impl(c, 1, &step, st, ovlmask, slabs, nslab, hard_tile);
+}
+
+int32_t iq_sim_step_multi(iq_ctx* c, int32_t ntile, const int64_t* steps, const int64_t* starts, const uint8_t* ovlmask,
+                          const iq_sim_slab* slabs, int32_t nslab) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step_multi: no simulation open on this context");
+  if (!steps || !starts || !ovlmask || nslab < 0 || nslab > 6 || (nslab > 0 && !slabs))
+    return fail(IQ_ERR_INVALID, "iq_sim_step_multi: bad argument");
+  return sim_step_impl(c, ntile, steps, starts, ovlmask, slabs, nslab, 0);
 }
 
 int32_t iq_sim_step_picked(iq_ctx* c, int64_t step, const int64_t* start, const int64_t* picks) {
@@ -926,6 +968,8 @@ int32_t iq_sim_step_picked(iq_ctx* c, int64_t step, const int64_t* start, const 
   SimState* s = c->sim;
   if (!start || !picks) return fail(IQ_ERR_INVALID, "iq_sim_step_picked: NULL argument");
   if (step < 0 || step >= s->npath) return fail(IQ_ERR_INVALID, "iq_sim_step_picked: step out of range");
+  if (s->tile_cursor + 1 > (size_t)std::max<int64_t>(s->npath, 1))
+    return fail(IQ_ERR_STATE, "iq_sim_step_picked: more tiles launched than path steps declared at iq_sim_begin");
   CK(cudaSetDevice(c->device));
   const int t[3] = {c->tx, c->ty, c->tz};
   int st3[3] = {0, 0, 0};
@@ -935,18 +979,23 @@ int32_t iq_sim_step_picked(iq_ctx* c, int64_t step, const int64_t* start, const 
   }
   const int R = s->R;
   s->synced = false;
-  long long* hp = s->h_pickstage + (size_t)step * R;
+  long long* hp = s->h_pickstage + s->tile_cursor * R;
   for (int r = 0; r < R; ++r) {
     if (picks[r] < 0 || picks[r] >= c->npos) return fail(IQ_ERR_INVALID, "iq_sim_step_picked: pick %d out of range", r);
     hp[r] = picks[r];
   }
+  TileInfo* ht = s->h_tiles + s->tile_cursor;
+  ht->sx = st3[0]; ht->sy = st3[1]; ht->sz = st3[2]; ht->step = (int)step;
+  const TileInfo* dt = s->d_tiles + s->tile_cursor;
+  CK(cudaMemcpyAsync(s->d_tiles + s->tile_cursor, ht, sizeof(TileInfo), cudaMemcpyHostToDevice, c->stream));
+  s->tile_cursor += 1;
   const unsigned gR = (unsigned)((R + 127) / 128);
   CK(cudaMemcpyAsync(s->d_picked, hp, (size_t)R * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-  k_sim_store_picks<<<gR, 128, 0, c->stream>>>(s->d_picked, s->d_picks, s->npath, step, R);
+  k_sim_store_picks<<<gR, 128, 0, c->stream>>>(s->d_picked, s->d_picks, s->npath, dt, R, R);
   CK(cudaGetLastError());
   SlabSet S{};
   k_sim_paste<<<dim3((unsigned)((c->tilevol + 255) / 256), (unsigned)R), 256, 0, c->stream>>>(
-      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], s->d_ti64, c->nx, c->ny, c->nxo, c->nyo,
+      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_ti64, c->nx, c->ny, c->nxo, c->nyo,
       s->d_picked, c->tx, c->ty, c->tz, S, s->d_keep, (long long)s->maxslab, s->d_cut_iters, s->d_status);
   CK(cudaGetLastError());
   c->launches += 2;

@@ -175,7 +175,8 @@ int32_t iq_cut_batch(iq_ctx* ctx, const iq_cut_task* tasks, int32_t ntask, int32
 typedef struct iq_sim_desc {
   int64_t pad_size[3];   /* padded simulation grid (src/iqsim.jl:106), unused dims = 1 */
   int64_t ovl_size[3];   /* overlap size per dimension (src/iqsim.jl:92): fixes the largest cut slab */
-  int32_t nreal;         /* realizations held by this context (<= max_batch of the context) */
+  int32_t nreal;         /* realizations held by this context; max_batch of the context must be a multiple of it
+                            (max_batch / nreal = tiles one iq_sim_step_multi launch may carry) */
   const double* ti64;    /* training image in FP64 (the values that are pasted and cut), ti_size doubles */
   const double* u;       /* [nreal][npath] uniforms in the reference's draw order (src/iqsim.jl:243) */
   int64_t npath;         /* number of path steps */
@@ -199,6 +200,15 @@ int32_t iq_sim_begin(iq_ctx* ctx, const iq_sim_desc* desc);
  * hard distance then is the primary source and the overlap distance the first auxiliary one (src/iqsim.jl:230-231). */
 int32_t iq_sim_step(iq_ctx* ctx, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
                     int32_t nslab, int32_t hard_tile);
+/* Several MUTUALLY INDEPENDENT tiles in one launch (dependency-level batching): ntile tiles whose windows do not
+ * intersect (checked) and that share the overlap mask and the slab set, e.g. the tiles (i, j, k) of a raster path with
+ * equal i + 2j + 4k.  A tile only reads and writes its own window, so it depends exactly on the earlier path tiles whose
+ * windows intersect it; tiles that share a dependency level may run together and the result is bit for bit that of the
+ * sequential path (every (realization, step) keeps its own uniform u[r][steps[k]]).  steps[k] / starts[3k..3k+2] describe
+ * tile k; ntile * nreal must not exceed the max_batch of the context.  Not for tiles with hard data nor for contexts with
+ * soft data (their auxiliary distance maps belong to one tile): use iq_sim_step for those. */
+int32_t iq_sim_step_multi(iq_ctx* ctx, int32_t ntile, const int64_t* steps, const int64_t* starts, const uint8_t* ovlmask,
+                          const iq_sim_slab* slabs, int32_t nslab);
 /* A step whose patterns the caller chose itself (picks[r] = 0-based linear index of the pattern of realization r):
  * the whole tile is pasted (no pasted neighbour, hence no cut).  Used for empty-mask steps of soft-data simulations. */
 int32_t iq_sim_step_picked(iq_ctx* ctx, int64_t step, const int64_t* start, const int64_t* picks);

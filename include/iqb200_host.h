@@ -83,6 +83,11 @@ typedef struct iqh_stats {
   double cut_device_ms;        /* resident: device time of the boundary cuts (sum over groups) */
   double fetch_ms;             /* resident: wall time of exporting the realizations to the host */
   int64_t max_candidates;      /* host-staged: largest candidate set of any tile search */
+  int32_t dep_levels;          /* resident: dependency levels of the path (iqh_dependency_levels) */
+  int32_t tiles_per_launch;    /* resident: most tiles one step launch may carry (job slots / realizations per group) */
+  int64_t step_launches;       /* resident: step launches issued per lockstep group (npath without batching) */
+  double run_ms;               /* resident: wall time from the first enqueue to the end of iq_sim_sync */
+  double teardown_ms;          /* resident: wall time of destroying the contexts */
 } iqh_stats;
 
 /* Runs the whole simulation.  `out_grids` receives nreal padded grids (pad_size doubles each,
@@ -90,6 +95,16 @@ typedef struct iqh_stats {
  * masks (src/iqsim.jl:281); `out_picks` (may be NULL) the chosen pattern per realization and step,
  * [nreal][npath], for parity tests.  Returns IQ_OK or an IQ_ERR_* code (message: iq_last_error()). */
 int32_t iqh_run(const iqh_desc* desc, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats);
+
+/* Dependency levels of a simulation path (the schedule of the device-resident pipeline).  A tile only reads and writes
+ * its own window of the simulation grid (template src/iqsim.jl:185, cut slabs :251-275, paste :278), so step s depends
+ * exactly on the earlier steps whose tile windows intersect its own: levels[s] = 1 + max level of those, 0 without any.
+ * Steps of one level are mutually independent; executing the levels in order, each level as one batch, reproduces the
+ * sequential path bit for bit (the overlap masks are still those of the path order: which neighbours were pasted
+ * EARLIER IN THE PATH).  Raster paths: levels[tile (i,j,k)] = i + 2j + 4k.  path: npath distinct 0-based column-major
+ * tile indices; tile_size / ovl_size / ntiles: ndim entries. */
+int32_t iqh_dependency_levels(int32_t ndim, const int64_t* tile_size, const int64_t* ovl_size, const int64_t* ntiles,
+                              const int64_t* path, int64_t npath, int32_t* levels, int32_t* nlevels);
 
 /* The boundary cut alone: keep-mask (1 = keep the already pasted voxel) for overlap slabs A (old) and
  * B (new) of size sz (ndim entries, column-major) cut along `dim`.  Restates graphcut(A, B, dim). */

@@ -162,3 +162,53 @@ def test_resident_waves_when_memory_is_short(monkeypatch):
     assert eb["stats"]["searches"] == ea["stats"]["searches"]
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+# ---- dependency-level batching (iq_sim_step_multi): several independent tiles of a level in one launch ----------
+def _run_jobs(monkeypatch, jobs, ti, tile, seed, **kw):
+    if jobs is None:
+        monkeypatch.delenv("IQB200_JOBS", raising=False)
+    else:
+        monkeypatch.setenv("IQB200_JOBS", str(jobs))
+    return iqb200.iqsim(ti, tile, rng=np.random.default_rng(seed), pipeline="resident", return_picks=True, return_stats=True, **kw)
+
+
+@pytest.mark.parametrize("case", ["2d-raster", "3d-raster", "3d-random", "2d-dilation", "3d-fft"])
+def test_level_batching_equals_one_tile_per_launch(monkeypatch, case):
+    """The launch schedule (levels of mutually independent tiles, batched) must not change a single bit: compare with
+    one tile per launch (IQB200_JOBS = nreal, the lockstep schedule of round 1) and with the host-staged pipeline."""
+    kw = dict(nreal=3)
+    if case == "2d-raster":
+        ti, tile = synth.gaussian_field((200, 180), (8, 8), 41), (32, 28)
+    elif case == "3d-raster":
+        ti, tile = synth.gaussian_field((60, 56, 30), (6, 6, 3), 42), (16, 14, 8)
+        kw.update(overlap=(0.25, 0.25, 0.25), simsize=(70, 60, 34))
+    elif case == "3d-random":
+        ti, tile = synth.gaussian_field((48, 44, 24), (6, 6, 3), 43), (14, 12, 8)
+        kw.update(overlap=(0.25, 0.25, 0.25), path="random", simsize=(60, 50, 30), debug=True)
+    elif case == "2d-dilation":
+        ti, tile = synth.gaussian_field((160, 150), (7, 7), 44).astype(np.float64), (24, 20)
+        kw.update(path="dilation", overlap=(0.25, 0.3), debug=True)
+    else:
+        ti, tile = synth.gaussian_field((128, 128, 24), (8, 8, 3), 45), (24, 24, 8)
+        kw.update(fft=1, nreal=2)
+    a, ea = _run_jobs(monkeypatch, None, ti, tile, 5, **kw)
+    b, eb = _run_jobs(monkeypatch, kw["nreal"], ti, tile, 5, **kw)
+    assert ea["stats"]["resident"] == 1 and eb["stats"]["resident"] == 1
+    assert eb["stats"]["tiles_per_launch"] == 1 and eb["stats"]["step_launches"] == ea["stats"]["nvisited"]
+    assert ea["stats"]["tiles_per_launch"] > 1 and ea["stats"]["step_launches"] < ea["stats"]["nvisited"]
+    assert ea["stats"]["dep_levels"] == eb["stats"]["dep_levels"] <= ea["stats"]["step_launches"]
+    same(a, ea, b, eb, debug=kw.get("debug", False))
+    monkeypatch.delenv("IQB200_JOBS", raising=False)
+    c, ec = iqb200.iqsim(ti, tile, rng=np.random.default_rng(5), pipeline="staged", cut="host", return_picks=True,
+                         return_stats=True, **kw)
+    same(a, ea, c, ec, debug=kw.get("debug", False))
+
+
+def test_overlap_above_half_anisotropic_tile_random_path():
+    """Overlap >= 1/2 with a non-square tile on a random path: the slab SET is not determined by the overlap mask
+    ({prev x, next x, prev y} and {prev x, prev y, next y} cover the whole tile alike), so the cached cut task records
+    must follow the slab signature, and windows two tiles apart intersect (dependency reach 2)."""
+    ti = synth.gaussian_field((70, 64), (6, 6), 46).astype(np.float64)
+    kw = dict(nreal=2, overlap=(0.6, 0.55), path="random", simsize=(60, 50), debug=True)
+    same(*both(ti, (20, 12), 12, **kw), debug=True)

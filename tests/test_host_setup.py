@@ -100,3 +100,56 @@ def test_relaxation_thresholds_describe_the_relaxation_result():
         rounds, (k0, k1) = O.relaxation_thresholds(D, [Da], tol)
         assert rounds >= 1
         assert np.array_equal(db, np.flatnonzero((D <= k0) & (Da <= k1)))  # continuous values: no ties at the k-th key
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dependency levels of a path (schedule of the device-resident pipeline; host logic, no GPU)
+# ---------------------------------------------------------------------------------------------------------------
+def _windows_intersect(a, b, tile, spacing):
+    return all(abs(x - y) * sp < t for x, y, t, sp in zip(a, b, tile, spacing))
+
+
+def _check_levels(tile, ovl, ntiles, path, levels):
+    """Defining property, by brute force: level[s] = 1 + max level of the earlier steps whose windows intersect."""
+    spacing = [t - o for t, o in zip(tile, ovl)]
+    idx = [np.unravel_index(int(p), ntiles, order="F") for p in path]
+    for s in range(len(path)):
+        want = 0
+        for e in range(s):
+            if _windows_intersect(idx[s], idx[e], tile, spacing):
+                want = max(want, levels[e] + 1)
+        assert levels[s] == want, (s, levels[s], want)
+
+
+def test_dependency_levels_raster_is_the_skewed_wavefront():
+    # config 5 geometry: 8 x 8 x 8 tiles of 40 x 40 x 16 with overlaps 7, 7, 3 -> level(i, j, k) = i + 2j + 4k, 50 levels
+    lv, n = api.dependency_levels((40, 40, 16), (7, 7, 3), (8, 8, 8), np.arange(512))
+    i, j, k = np.unravel_index(np.arange(512), (8, 8, 8), order="F")
+    assert n == 50 and np.array_equal(lv, i + 2 * j + 4 * k)
+    # config 2 geometry: 13 x 13 tiles -> i + 2j, 37 levels
+    lv, n = api.dependency_levels((48, 48), (8, 8), (13, 13), np.arange(169))
+    i, j = np.unravel_index(np.arange(169), (13, 13), order="F")
+    assert n == 37 and np.array_equal(lv, i + 2 * j)
+
+
+def test_dependency_levels_any_path_and_large_overlaps():
+    r = np.random.default_rng(0)
+    cases = [((12, 10), (3, 2), (6, 5)), ((8, 8, 4), (2, 2, 2), (4, 3, 3)),
+             ((10, 10), (6, 7), (5, 4)),          # overlap > 1/2: windows two tiles apart still intersect
+             ((9, 7, 1), (3, 1, 1), (5, 4, 1))]   # singleton dimension, a 1-voxel overlap
+    for tile, ovl, ntiles in cases:
+        n = int(np.prod(ntiles))
+        for path in (np.arange(n), r.permutation(n), np.array(api._genpath(np.random.default_rng(1), ntiles, "dilation", [])),
+                     r.permutation(n)[: n // 2]):   # skipped tiles: the path visits only some of them
+            lv, nl = api.dependency_levels(tile, ovl, ntiles, path)
+            _check_levels(tile, ovl, ntiles, path, lv)
+            assert nl == (int(lv.max()) + 1 if len(path) else 0)
+
+
+def test_dependency_levels_rejects_bad_paths():
+    import pytest
+    from iqb200._lib import IqError
+    with pytest.raises(IqError):
+        api.dependency_levels((8, 8), (2, 2), (3, 3), [0, 1, 1])
+    with pytest.raises(IqError):
+        api.dependency_levels((8, 8), (2, 2), (3, 3), [0, 9])
