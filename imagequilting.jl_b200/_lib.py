@@ -83,6 +83,9 @@ SYMBOLS = {
     "iq_last_error": (C.c_char_p, []),
     "iq_ctx_create": (C.c_int32, [C.POINTER(C.c_void_p), C.POINTER(IqCtxDesc)]),
     "iq_ctx_destroy": (C.c_int32, [C.c_void_p]),
+    "iq_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "iq_host_free": (C.c_int32, [C.c_void_p]),
+    "iq_ctx_matches": (C.c_int32, [C.c_void_p, C.POINTER(IqCtxDesc), c_i32_p]),
     "iq_ctx_npos": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p]),
     "iq_search": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqTile), C.c_int32, C.c_double, C.POINTER(IqResult)]),
     "iq_search_pick": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqTile), C.c_int32, C.c_double, c_double_p,
@@ -97,7 +100,8 @@ SYMBOLS = {
     "iq_cut_batch": (C.c_int32, [C.c_void_p, C.POINTER(IqCutTask), C.c_int32, c_i32_p]),
     "iq_sim_begin": (C.c_int32, [C.c_void_p, C.POINTER(IqSimDesc)]),
     "iq_sim_step": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32, C.c_int32]),
-    "iq_sim_step_multi": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32]),
+    "iq_sim_define_shape": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32, c_i32_p]),
+    "iq_sim_step_multi": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p, c_i32_p]),
     "iq_sim_step_picked": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_i64_p]),
     "iq_sim_sync": (C.c_int32, [C.c_void_p, c_i64_p, c_i32_p]),
     "iq_sim_fetch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_i64_p, C.c_void_p]),
@@ -115,6 +119,7 @@ SYMBOLS = {
     "iq_ctx_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
     "iqh_run": (C.c_int32, [C.POINTER(IqhDesc), c_double_p, c_u8_p, c_i64_p, C.POINTER(IqhStats)]),
     "iqh_graphcut": (C.c_int32, [c_double_p, c_double_p, C.c_int32, c_i64_p, C.c_int32, c_u8_p]),
+    "iqh_cache_clear": (C.c_int32, []),
     "iqh_dependency_levels": (C.c_int32, [C.c_int32, c_i64_p, c_i64_p, c_i64_p, c_i64_p, C.c_int64, c_i32_p, c_i32_p]),
 }
 

@@ -59,6 +59,51 @@ def _isnan(v):
         return False
 
 
+class _PinnedPool:
+    """Page-locked host blocks for the arrays `iqsim` returns (iq_host_alloc): the native driver copies device -> host
+    straight into them.  A block goes back to the pool when the array that wraps it is garbage collected, so repeated
+    calls reuse the same memory (no page faults, no bounce copies); at most `cap` bytes stay pooled."""
+
+    def __init__(self, cap=8 << 30):
+        self.free, self.cap, self.pooled = {}, cap, 0
+
+    def array(self, shape, dtype):
+        import weakref
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        lst = self.free.get(n)
+        if lst:
+            ptr = lst.pop()
+            self.pooled -= n
+        else:
+            p = C.c_void_p()
+            check(lib().iq_host_alloc(n, C.byref(p)))
+            ptr = p.value
+        buf = (C.c_char * max(n, 1)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape, order="F")
+        weakref.finalize(buf, self._release, ptr, n)  # the ctypes buffer lives as long as any view of the array
+        return arr
+
+    def _release(self, ptr, n):
+        if self.pooled + n <= self.cap:
+            self.free.setdefault(n, []).append(ptr)
+            self.pooled += n
+        else:
+            try:
+                lib().iq_host_free(ptr)
+            except Exception:
+                pass
+
+    def clear(self):
+        for lst in self.free.values():
+            for ptr in lst:
+                lib().iq_host_free(ptr)
+        self.free, self.pooled = {}, 0
+
+
+_pinned = _PinnedPool()
+
+
 def geometry(TIsize, tilesize, simsize=None, overlap=None):
     """geoconfig of src/iqsim.jl:92-127."""
     TIsize = tuple(int(v) for v in TIsize)
@@ -305,7 +350,12 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     real_f32 = out_dtype == np.float32
     if out_dtype not in (np.float32, np.float64):  # e.g. longdouble: simulated as FP64, converted at the end
         out_dtype = np.dtype(np.float64)
-    reals = [np.zeros(simsize, dtype=out_dtype, order="F") for _ in range(nreal)]
+    # results live in pooled page-locked memory (device -> host copies land in them directly); the native driver writes
+    # every voxel of a visited realization, and a simulation without visited tiles returns zeros (src/iqsim.jl:165)
+    reals = [_pinned.array(simsize, out_dtype) for _ in range(nreal)]
+    if nvis == 0:
+        for a in reals:
+            a[...] = 0
     real_ptrs = (C.c_void_p * nreal)(*[a.ctypes.data for a in reals])
     cuts = np.zeros((nreal, padvol), dtype=np.uint8) if debug else None
     picks = np.full((nreal, max(nvis, 1)), -1, dtype=np.int64)
@@ -639,8 +689,11 @@ def sample(prob, u):
 
 
 def release_device_memory(device=0):
-    """Return the library's cached (currently unused) device memory on `device` to the driver."""
+    """Destroy the contexts parked by earlier `iqsim` calls and return the library's cached (currently unused) device
+    memory on `device` to the driver."""
+    check(lib().iqh_cache_clear())
     check(lib().iq_release_device_memory(int(device)))
+    _pinned.clear()
 
 
 def fma_peak(device=0, packed=False):

@@ -380,24 +380,28 @@ int ensure_fft(iq_ctx* c, int image) {
 
 // FFT correlation of R dense masked templates that already sit in device memory.
 int launch_fft(iq_ctx* c, MaskEntry* e, int image, const float* d_tmpl, const double* d_b2, int R, bool tint, float* d_out,
-               int kind) {
+               int kind, int job0, const float* const* a2_list) {
   const float* a2 = nullptr;
-  int rc = get_a2(c, e, image, &a2);
-  if (rc) return rc;
+  int rc = IQ_OK;
+  if (!a2_list) {
+    rc = get_a2(c, e, image, &a2);
+    if (rc) return rc;
+  }
   iqfft::Epilogue ep{};
   ep.a2 = a2;
+  ep.a2_list = a2_list;
   ep.b2 = d_b2;
   ep.disabled = c->d_disabled;
   ep.out = d_out;
-  ep.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch;
-  ep.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch;
+  ep.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch + job0;
+  ep.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch + job0;
   ep.round_to_int = tint ? 1 : 0;
   if (kind == 0) {
     const int rows = iqfft::final_chunk_rows(c->fft);
     c->chunk_len = rows * c->nxo;
     c->chunk_n = (c->nyo * c->nzo + rows - 1) / rows;
     c->chunk_valid = c->chunk_n <= c->chunk_stride;
-    if (c->chunk_valid) { ep.chunkmin = c->d_chunkmin; ep.chunk_pitch = c->chunk_stride; }
+    if (c->chunk_valid) { ep.chunkmin = c->d_chunkmin + (size_t)job0 * c->chunk_stride; ep.chunk_pitch = c->chunk_stride; }
   }
   cudaEvent_t ea, eb;
   rc = dist_events(c, &ea, &eb, true);
@@ -437,7 +441,7 @@ int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R,
 
 // Direct correlation kernel on R templates already packed in device memory ([grp][box][qz][qy][chunk][r(rb)][8]).
 int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, const double* d_b2, int R, int rb, bool packed,
-                  float* d_out, int kind) {
+                  float* d_out, int kind, int job0) {
   const float* a2 = nullptr;
   int rc = get_a2(c, e, image, &a2);
   if (rc) return rc;
@@ -454,8 +458,8 @@ int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, con
   p.b2 = d_b2;
   p.disabled = c->d_disabled;
   p.out = d_out;
-  p.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch;
-  p.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch;
+  p.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch + job0;
+  p.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch + job0;
   p.R = R;
   p.WX = e->WX;
   p.WY = e->WY;
@@ -961,7 +965,6 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   for (auto& e : c->masks) {
     cudaFree(e->d_boxes);
     cudaFree(e->d_mask);
-    for (auto& ts : e->cut_sets) cudaFree(ts.d_tasks);
     for (auto& kv : e->a2) cudaFree(kv.second);
   }
   iqfft::plan_destroy(c->fft);
@@ -1104,6 +1107,74 @@ int32_t iq_ctx_create(iq_ctx** out, const iq_ctx_desc* d) {
     return rc;
   }
   *out = c;
+  return IQ_OK;
+}
+
+// Bitwise comparison of two device arrays: *flag |= 1 when they differ.
+__global__ void __launch_bounds__(256) k_differs(const unsigned* __restrict__ a, const unsigned* __restrict__ b, long long n,
+                                                 int* __restrict__ flag) {
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  bool diff = false;
+  for (long long i = i0; i < n; i += (long long)gridDim.x * 256) diff |= a[i] != b[i];
+  if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+int32_t iq_ctx_matches(iq_ctx* c, const iq_ctx_desc* d, int32_t* same) {
+  if (!c || !d || !same || !d->ti) return fail(IQ_ERR_INVALID, "iq_ctx_matches: NULL argument");
+  *same = 0;
+  if (c->sim) return IQ_OK;  // a simulation is open on it
+  const int nz = d->ndim == 3 ? (int)d->ti_size[2] : 1, tz = d->ndim == 3 ? (int)d->tile_size[2] : 1;
+  if (d->ndim != c->ndim || d->device != c->device || d->nsoft != c->nsoft || std::max(1, d->max_batch) != c->max_batch ||
+      d->ti_size[0] != c->nx || d->ti_size[1] != c->ny || nz != c->nz || d->tile_size[0] != c->tx || d->tile_size[1] != c->ty ||
+      tz != c->tz)
+    return IQ_OK;
+  // disabled patches: host-side comparison with the copy the context keeps (empty = none disabled)
+  bool any = false;
+  if (d->disabled)
+    for (long long p = 0; p < c->npos && !any; ++p) any = d->disabled[p] != 0;
+  if (any != !c->h_disabled.empty()) return IQ_OK;
+  if (any && std::memcmp(d->disabled, c->h_disabled.data(), (size_t)c->npos) != 0) return IQ_OK;
+  // images: uploaded again (the caller's arrays may have changed since) and compared with the resident copies
+  CK(cudaSetDevice(c->device));
+  const size_t nimg = (size_t)c->nx * c->ny * c->nz;
+  float* d_new = nullptr;
+  int* d_flag = nullptr;
+  CK(iq::dmalloc((void**)&d_new, nimg * sizeof(float)));
+  CK(iq::dmalloc((void**)&d_flag, sizeof(int)));
+  CK(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+  for (int img = -1; img < c->nsoft; ++img) {
+    const float* src = img < 0 ? d->ti : (d->auxti ? d->auxti[img] : nullptr);
+    if (!src) { cudaFree(d_new); cudaFree(d_flag); return fail(IQ_ERR_INVALID, "iq_ctx_matches: auxti[%d] is NULL", img); }
+    CK(cudaMemcpyAsync(d_new, src, nimg * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    k_differs<<<1184, 256, 0, c->stream>>>((const unsigned*)d_new, (const unsigned*)(img < 0 ? c->d_ti : c->d_aux[img]),
+                                           (long long)nimg, d_flag);
+    CK(cudaGetLastError());
+  }
+  int flag = 1;
+  CK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_new);
+  cudaFree(d_flag);
+  *same = flag == 0 ? 1 : 0;
+  return IQ_OK;
+}
+
+int32_t iq_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(IQ_ERR_INVALID, "iq_host_alloc: NULL argument");
+  *out = nullptr;
+  if (cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return fail(IQ_ERR_NOMEM, "iq_host_alloc: cannot allocate %zu bytes of page-locked host memory", bytes);
+  }
+  return IQ_OK;
+}
+
+int32_t iq_host_free(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(IQ_ERR_INVALID, "iq_host_free: not a pointer returned by iq_host_alloc");
+  }
   return IQ_OK;
 }
 

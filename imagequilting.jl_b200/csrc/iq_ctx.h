@@ -26,14 +26,6 @@ int fail(int code, const char* fmt, ...);
 
 using iq::BoxDesc;
 
-// Device cut task records for one (job count, slab set) of a mask.  The mask alone does not determine the slabs
-// (overlap >= 0.5: {px,nx,py} and {px,py,ny} cover the same voxels with different slab shapes), hence the signature.
-struct CutTaskSet {
-  std::vector<int> sig;                // jobs, nslab, then dim / n0 / n1 / L of every slab
-  iq::CutTask* d_tasks = nullptr;
-  size_t smem = 0;
-};
-
 struct MaskEntry {
   std::vector<uint8_t> mask;
   uint64_t hash = 0;
@@ -44,7 +36,6 @@ struct MaskEntry {
   long long tmpl_floats = 0;           // packed template floats per tile
   std::map<int, float*> a2;            // image id (-1 = TI, s = aux s) -> A2 map
   int WX = 1, WY = 1;
-  std::vector<CutTaskSet> cut_sets;    // resident simulation: cached cut task records of this mask's slab sets
 };
 
 struct TileResult {
@@ -161,10 +152,13 @@ int pick_rb(const iq_ctx* c, int R);
 bool want_fft(const iq_ctx* c, const MaskEntry* e, int R);
 int build_uniform(iq_ctx* c);
 int ensure_fft(iq_ctx* c, int image);
+// job0: first batch slot the R templates occupy (offset into the per-slot min/max and chunk-minimum arrays; d_b2 and
+// d_out already point at that slot).  a2_list (FFT only): device array of one A2 map per template for launches that
+// mix masks (e may then be nullptr).
 int launch_fft(iq_ctx* c, MaskEntry* e, int image, const float* d_tmpl, const double* d_b2, int R, bool tint, float* d_out,
-               int kind);
+               int kind, int job0 = 0, const float* const* a2_list = nullptr);
 int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, const double* d_b2, int R, int rb, bool packed,
-                  float* d_out, int kind);
+                  float* d_out, int kind, int job0 = 0);
 int collect_dist_times(iq_ctx* c);
 // Makes sure d_chunkmin describes the R overlap-distance maps in d_Dovl (FFT epilogue, or one extra pass).
 int ensure_chunkmin(iq_ctx* c, int R);

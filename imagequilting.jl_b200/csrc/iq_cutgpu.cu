@@ -56,8 +56,7 @@ __device__ __forceinline__ double edge_cap(const double* __restrict__ A, const d
 // bit 6 = direction 4 (+cut axis) leads into the sink slice, bit 7 = checkerboard colour
 constexpr unsigned kToSink = 64u, kColour = 128u;
 
-__global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* tasks) {
-  const CutTask T = tasks[blockIdx.x];
+__device__ __forceinline__ void graphcut_body(const CutTask& T) {
   const int n0 = T.n0, n1 = T.n1, L = T.L;
   const int P = n0 * n1, nfree = (L - 2) * P;
   const double* __restrict__ A = T.A;
@@ -272,10 +271,41 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* task
 #endif
 }
 
+// explicit task list (iq_cut_batch)
+__global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* tasks) { graphcut_body(tasks[blockIdx.x]); }
+
+// Implicit task grid of the resident simulation: task (job, k) = slab k of job `job`, data at (job * maxslabs + k) * maxslab,
+// dims[task] = {n0, n1, L, -} written by the slab gather (L = 0: the job's tile has no slab k -> nothing to do).  Launch
+// position b -> slab index b / njobs, job b % njobs: the cuts of one slab kind (same size, similar cost) run side by
+// side, the first kinds (x, y overlaps: the thick ones) lead and the thin z overlaps fill the tail.
+__global__ void __launch_bounds__(kCutThreads, 1) k_graphcut_grid(const double* A, const double* B, unsigned char* keep, int* iters,
+                                                                  const int4* __restrict__ dims, long long maxslab,
+                                                                  int maxslabs, int njobs) {
+  const int k = blockIdx.x / njobs, job = blockIdx.x - k * njobs;
+  const int task = job * maxslabs + k;
+  const int4 d = dims[task];
+  if (d.z < 2) return;
+  CutTask T;
+  T.A = A + (long long)task * maxslab;
+  T.B = B + (long long)task * maxslab;
+  T.keep = keep + (long long)task * maxslab;
+  T.n0 = d.x; T.n1 = d.y; T.L = d.z;
+  T.iters = iters + task;
+  graphcut_body(T);
+}
+
 size_t graphcut_smem(int n0, int n1, int L) {
   const size_t nfree = (size_t)(L - 2) * n0 * n1;
   const size_t items = (size_t)n1 * (L - 2) * ((n0 + 6) / 7);
   return nfree * (kCutBytesPerNode - 1) + ((nfree + 3) & ~(size_t)3) + (7 * items + 2 * nfree) * sizeof(unsigned short) + 16;
+}
+
+cudaError_t launch_graphcut_grid(const double* A, const double* B, unsigned char* keep, int* iters, const int4* dims,
+                                 long long maxslab, int maxslabs, int nslab, int njobs, size_t smem, cudaStream_t s) {
+  cudaError_t err = cudaFuncSetAttribute(k_graphcut_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  k_graphcut_grid<<<nslab * njobs, kCutThreads, smem, s>>>(A, B, keep, iters, dims, maxslab, maxslabs, njobs);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s) {

@@ -560,7 +560,9 @@ __device__ __forceinline__ void final_epilogue(const FinalArgs& A, const float2*
   const bool rnd = A.ep.round_to_int != 0;
   // uniform 64-bit bases + one 32-bit position per thread (npos < 2^32): the loads / stores use base + u32 addressing
   // instead of a 64-bit add per pointer and line
-  const float* __restrict__ a2b = A.ep.a2;
+  const float* __restrict__ a2b = A.ep.a2_list ? A.ep.a2_list[r0] : A.ep.a2;
+  const float* __restrict__ a2c = A.ep.a2_list ? (has1 ? A.ep.a2_list[r1] : nullptr) : A.ep.a2;  // second template of the pair
+  const bool same_a2 = a2b == a2c;
   const uint8_t* __restrict__ disb = A.ep.disabled;
   float* __restrict__ o0b = A.ep.out + (long long)r0 * A.npos;
   float* __restrict__ o1b = A.ep.out + (long long)r1 * A.npos;
@@ -572,13 +574,14 @@ __device__ __forceinline__ void final_epilogue(const FinalArgs& A, const float2*
       float2 ab = rp[line * LS];
       if (rnd) { ab.x = rintf(ab.x); ab.y = rintf(ab.y); }
       const double a2 = a2b ? (double)__ldg(a2b + p) : 0.0;
+      const double a2s = same_a2 ? a2 : (a2c ? (double)__ldg(a2c + p) : 0.0);
       const bool dis = disb && disb[p];
       float d0 = (float)fabs(a2 - 2.0 * (double)ab.x + b20);
       if (dis) d0 = CUDART_INF_F;
       o0b[p] = d0;
       if (!dis) { const unsigned u = __float_as_uint(d0); mn0 = min(mn0, u); mx0 = max(mx0, u); }
       if (has1) {
-        float d1 = (float)fabs(a2 - 2.0 * (double)ab.y + b21);
+        float d1 = (float)fabs(a2s - 2.0 * (double)ab.y + b21);
         if (dis) d1 = CUDART_INF_F;
         o1b[p] = d1;
         if (!dis) { const unsigned u = __float_as_uint(d1); mn1 = min(mn1, u); mx1 = max(mx1, u); }

@@ -11,6 +11,8 @@ struct Plan;
 // Epilogue arguments: the last inverse pass writes the distance maps directly.
 struct Epilogue {
   const float* a2;          // [npos] sum of img^2 over the mask, or nullptr (= 0)
+  const float* const* a2_list;  // optional [R] device array: one a2 map (or nullptr) per template -- templates of
+                                // different masks in one call (mixed-shape launches of the resident pipeline)
   const double* b2;         // [R] sum of mask*kern^2
   const uint8_t* disabled;  // [npos] or nullptr
   float* out;               // [R][npos]

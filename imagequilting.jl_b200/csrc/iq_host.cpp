@@ -201,6 +201,56 @@ bool image_is_integer(const iqh_desc* D, const Geo& G) {
   return true;
 }
 
+// Contexts kept between iqh_run calls.  Building a context costs tens of milliseconds (summed-volume tables, pinned
+// staging, image spectra, work buffers) and destroying it more (pinned frees), which is a large share of a call on a
+// small shard (8 realizations per GPU).  A finished simulation parks its contexts here; the next call takes one back
+// if iq_ctx_matches says a fresh context would be identical (same geometry and job slots, bitwise the same images --
+// they are uploaded and compared every time, so the caller may change its arrays freely).  iqh_cache_clear empties it.
+struct CtxCache {
+  std::mutex m;
+  std::vector<iq_ctx*> parked;
+  static constexpr size_t kMax = 4;
+  iq_ctx* take(const iq_ctx_desc& cd) {
+    std::vector<iq_ctx*> cand;
+    {
+      std::lock_guard<std::mutex> l(m);
+      cand.swap(parked);
+    }
+    iq_ctx* hit = nullptr;
+    std::vector<iq_ctx*> rest;
+    for (iq_ctx* c : cand) {
+      int32_t same = 0;
+      if (!hit && iq_ctx_matches(c, &cd, &same) == IQ_OK && same) hit = c;
+      else rest.push_back(c);
+    }
+    std::lock_guard<std::mutex> l(m);
+    for (iq_ctx* c : rest) parked.push_back(c);
+    return hit;
+  }
+  void park(iq_ctx* c) {
+    iq_ctx* evict = nullptr;
+    {
+      std::lock_guard<std::mutex> l(m);
+      parked.push_back(c);
+      if (parked.size() > kMax) { evict = parked.front(); parked.erase(parked.begin()); }
+    }
+    if (evict) iq_ctx_destroy(evict);
+  }
+  void clear() {
+    std::vector<iq_ctx*> all;
+    {
+      std::lock_guard<std::mutex> l(m);
+      all.swap(parked);
+    }
+    for (iq_ctx* c : all) iq_ctx_destroy(c);
+  }
+};
+CtxCache g_cache;
+bool cache_enabled() {
+  const char* ev = std::getenv("IQB200_CTX_CACHE");
+  return !(ev && ev[0] == '0');
+}
+
 // Dependency levels of a simulation path.  A tile reads (template, slabs) and writes (paste) only its own window, so it
 // depends exactly on the tiles EARLIER IN THE PATH whose windows intersect its own: level = 1 + max level of those (0
 // without any).  Tiles of one level are mutually independent (two tiles with intersecting windows are ordered by the
@@ -281,9 +331,19 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   }
   struct RG { iq_ctx* ctx = nullptr; int r0 = 0, R = 0; };
   std::vector<RG> groups(ngroups);
+  const bool use_cache = cache_enabled();
   auto destroy_all = [&] {
     for (auto& g : groups)
       if (g.ctx) { iq_ctx_destroy(g.ctx); g.ctx = nullptr; }
+  };
+  // after a successful simulation the contexts are parked for the next call instead of destroyed
+  auto park_all = [&] {
+    for (auto& g : groups)
+      if (g.ctx) {
+        if (use_cache && iq_sim_end(g.ctx) == IQ_OK) g_cache.park(g.ctx);
+        else iq_ctx_destroy(g.ctx);
+        g.ctx = nullptr;
+      }
   };
   const auto t_setup = clk::now();
   int rc = IQ_OK;
@@ -300,7 +360,8 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     cd.auxti = D->auxti;
     cd.device = D->device;
     cd.max_batch = g.R * tiles_per_launch;
-    rc = iq_ctx_create(&g.ctx, &cd);
+    g.ctx = use_cache ? g_cache.take(cd) : nullptr;
+    if (!g.ctx) rc = iq_ctx_create(&g.ctx, &cd);
     if (rc != IQ_OK) break;
     iq_ctx_set_option(g.ctx, "fft", D->fft_mode);
     iq_sim_desc sd{};
@@ -370,20 +431,18 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   std::vector<std::vector<float>> soft_tile((size_t)S, std::vector<float>((size_t)G.tilevol));
   std::vector<const float*> soft_ptr((size_t)S, nullptr);
   std::vector<int64_t> bsteps, bstarts;
+  std::vector<int32_t> bshapes;
   int64_t launches = 0, nlaunch_steps = 0;
-  const auto t_enq = clk::now();
-  for (size_t oi = 0; oi < order.size() && rc == IQ_OK;) {
-    const StepInfo& si = steps[(size_t)order[oi]];
-    const int64_t step = order[oi];
-    // slabs and mask of this step, rebuilt from the key (all tiles of a batch share them)
+  // slabs / mask of an overlap key (bit 2d: previous tile along d pasted, bit 2d+1: next one)
+  auto key_shape = [&](unsigned key) {
     slabs.clear();
     for (int d = 0; d < G.N; ++d) {
-      if ((si.key >> (2 * d)) & 1u) {
+      if ((key >> (2 * d)) & 1u) {
         Slab sb{d, true, {0, 0, 0}, {G.t[0], G.t[1], G.t[2]}};
         sb.sz[d] = G.ov[d];
         slabs.push_back(sb);
       }
-      if ((si.key >> (2 * d + 1)) & 1u) {
+      if ((key >> (2 * d + 1)) & 1u) {
         Slab sb{d, false, {0, 0, 0}, {G.t[0], G.t[1], G.t[2]}};
         sb.lo[d] = G.sp[d];
         sb.sz[d] = G.t[d] - G.sp[d];
@@ -401,24 +460,25 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
       sl[k].prev = slabs[k].prev ? 1 : 0;
       for (int i = 0; i < 3; ++i) { sl[k].lo[i] = slabs[k].lo[i]; sl[k].sz[i] = slabs[k].sz[i]; }
     }
+  };
+  // shape ids per lockstep group and key (registered on first use)
+  std::vector<std::vector<int32_t>> shape_of(groups.size(), std::vector<int32_t>(64, -1));
+  const auto t_enq = clk::now();
+  for (size_t oi = 0; oi < order.size() && rc == IQ_OK;) {
+    const StepInfo& si = steps[(size_t)order[oi]];
+    const int64_t step = order[oi];
     const int* start = si.start;
     const int64_t st64[3] = {start[0], start[1], start[2]};
-    // the batch: following steps of the same level and key (no hard / soft data)
+    // the batch: the following steps of the same level (no hard / soft data); tiles without a pasted neighbour (key 0:
+    // the host samples them from the uniform distribution) only go with their like
     size_t oe = oi + 1;
     if (batching && !si.hard_tile && !si.host_pick && S == 0)
       while (oe < order.size() && (int)(oe - oi) < tiles_per_launch) {
         const StepInfo& o = steps[(size_t)order[oe]];
-        if (o.level != si.level || o.key != si.key || o.hard_tile) break;
+        if (o.level != si.level || o.hard_tile || (o.key == 0) != (si.key == 0)) break;
         ++oe;
       }
     const int ntile = (int)(oe - oi);
-    bsteps.resize((size_t)ntile);
-    bstarts.resize((size_t)ntile * 3);
-    for (int k = 0; k < ntile; ++k) {
-      const StepInfo& o = steps[(size_t)order[oi + k]];
-      bsteps[(size_t)k] = order[oi + k];
-      for (int i = 0; i < 3; ++i) bstarts[(size_t)k * 3 + i] = o.start[i];
-    }
     if (si.host_pick) {
       // Soft data and nothing pasted around the tile: the candidate set is a tenth of all patterns (relaxation.jl:11,20),
       // far above the device tau model.  One search (the tile is the same for every realization), the sampling walk
@@ -433,8 +493,10 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
         soft_ptr[sidx] = soft_tile[sidx].data();
       }
     }
-    for (auto& g : groups) {
+    for (size_t gi = 0; gi < groups.size() && rc == IQ_OK; ++gi) {
+      RG& g = groups[gi];
       if (si.host_pick) {
+        key_shape(si.key);
         iq_tile tile{};
         tile.simdev = zero_tile.data();
         tile.softdev = soft_ptr.data();
@@ -450,9 +512,24 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
         }
         if (rc == IQ_OK) rc = iq_sim_step_picked(g.ctx, step, st64, pk.data());
       } else if (ntile == 1) {
+        key_shape(si.key);
         rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size(), si.hard_tile ? 1 : 0);
       } else {
-        rc = iq_sim_step_multi(g.ctx, ntile, bsteps.data(), bstarts.data(), mask.data(), sl.data(), (int32_t)sl.size());
+        bsteps.resize((size_t)ntile);
+        bstarts.resize((size_t)ntile * 3);
+        bshapes.resize((size_t)ntile);
+        for (int k = 0; k < ntile && rc == IQ_OK; ++k) {
+          const StepInfo& o = steps[(size_t)order[oi + k]];
+          bsteps[(size_t)k] = order[oi + k];
+          for (int i = 0; i < 3; ++i) bstarts[(size_t)k * 3 + i] = o.start[i];
+          int32_t& sid = shape_of[gi][o.key & 63u];
+          if (sid < 0) {
+            key_shape(o.key);
+            rc = iq_sim_define_shape(g.ctx, mask.data(), sl.data(), (int32_t)sl.size(), &sid);
+          }
+          bshapes[(size_t)k] = sid;
+        }
+        if (rc == IQ_OK) rc = iq_sim_step_multi(g.ctx, ntile, bsteps.data(), bstarts.data(), bshapes.data());
       }
       if (rc != IQ_OK) break;
       double dms = 0;
@@ -502,7 +579,8 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   }
   const double fetch_ms = ms_since(t_fetch);
   const auto t_down = clk::now();
-  destroy_all();
+  if (rc == IQ_OK && *status == 0) park_all();
+  else destroy_all();
   const double teardown_ms = ms_since(t_down);
   if (rc != IQ_OK) return rc;
   if (stats && *status == 0) {
@@ -604,6 +682,11 @@ int run_resident_waves(const iqh_desc* D, const Geo& G, double* out_grids, uint8
 }
 
 }  // namespace
+
+extern "C" int32_t iqh_cache_clear(void) {
+  g_cache.clear();
+  return IQ_OK;
+}
 
 extern "C" int32_t iqh_dependency_levels(int32_t ndim, const int64_t* tile_size, const int64_t* ovl_size, const int64_t* ntiles,
                                          const int64_t* path, int64_t npath, int32_t* levels, int32_t* nlevels) {

@@ -32,7 +32,16 @@ struct SlabSet {
 
 // One tile of a (multi-tile) step: origin in the padded grid and the path step it belongs to (index of its uniform /
 // pick).  A step launch carries ntile x R jobs: job j = tile j / R of realization j % R.
-struct TileInfo { int sx, sy, sz, step; };
+struct TileInfo { int sx, sy, sz, step, shape; };
+
+// One overlap shape of the simulation: the mask, its A2 map (sum of img^2 over the mask per position) and the slabs
+// whose union the mask is.  Tiles of different shapes may share a launch (they only differ in these three).
+struct ShapeDev {
+  const uint8_t* mask;   // [tilevol]
+  const float* a2;       // [npos], nullptr for the empty mask
+  SlabSet S;
+};
+constexpr int kMaxShapes = 256;
 
 struct SimState {
   int R = 0;
@@ -40,6 +49,12 @@ struct SimState {
   TileInfo* d_tiles = nullptr;    // [npath] tile records in launch order (every path step is launched exactly once)
   TileInfo* h_tiles = nullptr;    // pinned mirror
   size_t tile_cursor = 0;         // tiles launched so far
+  ShapeDev* d_shapes = nullptr;   // [kMaxShapes] shape table (entries are written once, stream ordered)
+  ShapeDev* h_shapes = nullptr;   // pinned mirror
+  struct ShapeHost { MaskEntry* e; std::vector<int> sig; size_t smem; int nslab; };
+  std::vector<ShapeHost> shapes;
+  const float** d_a2list = nullptr;  // [J] A2 map of every job of the current launch (written by k_sim_templates)
+  int4* d_cutdims = nullptr;         // [J * maxslabs] {n0, n1, L, -} of every cut task of the current launch (L = 0: none)
   int pad[3] = {1, 1, 1};
   long long padvol = 0;
   int64_t npath = 0;
@@ -104,13 +119,18 @@ struct SimState {
 template <typename GT>
 __global__ void __launch_bounds__(256) k_sim_templates(const GT* __restrict__ grid, long long padvol, int p0, int p1,
                                                        const TileInfo* __restrict__ tiles, int R,
-                                                       const uint8_t* __restrict__ mask, int tx,
+                                                       const ShapeDev* __restrict__ shapes, const uint8_t* __restrict__ mask,
+                                                       const float** __restrict__ a2list, int tx,
                                                        int ty, int tz, float* __restrict__ tmpl, double* __restrict__ plane,
                                                        double* __restrict__ b2, unsigned* __restrict__ ticket) {
   const int z = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;  // r = job: tile r / R of realization r % R
   const int pl = tx * ty;
   const TileInfo T = tiles[r / R];
   const int sx = T.sx, sy = T.sy, sz = T.sz;
+  if (shapes) {  // the job's own overlap shape (else: the one mask passed in, e.g. the all-ones soft-data mask)
+    mask = shapes[T.shape].mask;
+    if (z == 0 && tid == 0 && a2list) a2list[r] = shapes[T.shape].a2;
+  }
   const GT* g = grid + (long long)(r % R) * padvol + ((long long)(sz + z) * p1 + sy) * p0 + sx;
   const uint8_t* m = mask + (long long)z * pl;
   float* out = tmpl + ((long long)r * tz + z) * pl;
@@ -365,16 +385,25 @@ __global__ void k_sim_store_picks(const long long* __restrict__ picked, long lon
   if (r < njobs) picks[(long long)(r % R) * npath + tiles[r / R].step] = picked[r];
 }
 
-// Overlap slabs of every realization in the cut kernel's layout: A = pasted content, B = chosen patch.
+// Overlap slabs of every job in the cut kernel's layout: A = pasted content, B = chosen patch.  One CTA per
+// (job, slab slot k < maxn); a job whose shape has fewer slabs marks the slot empty (dims.z = 0).
 __global__ void __launch_bounds__(256) k_sim_slabs(const double* __restrict__ grid, long long padvol, int p0, int p1,
                                                    const TileInfo* __restrict__ tiles, int R,
+                                                   const ShapeDev* __restrict__ shapes, int maxn, int maxslabs,
                                                    const double* __restrict__ ti, int nx, int ny, int nxo,
                                                    int nyo, const long long* __restrict__ picked, int tx, int ty,
-                                                   const SlabSet S, double* __restrict__ A, double* __restrict__ B,
+                                                   double* __restrict__ A, double* __restrict__ B, int4* __restrict__ dims,
                                                    long long maxslab) {
-  const int task = blockIdx.x, r = task / S.n;  // r = job
-  const SlabDev& s = S.s[task - r * S.n];
+  const int r = blockIdx.x / maxn, k = blockIdx.x - r * maxn;  // r = job
   const TileInfo T = tiles[r / R];
+  const SlabSet& S = shapes[T.shape].S;
+  const int task = r * maxslabs + k;
+  if (k >= S.n) {
+    if (threadIdx.x == 0) dims[task] = make_int4(0, 0, 0, 0);
+    return;
+  }
+  const SlabDev& s = S.s[k];
+  if (threadIdx.x == 0) dims[task] = make_int4(s.n0, s.n1, s.L, 0);
   const int sx = T.sx, sy = T.sy, sz = T.sz;
   const long long pk = picked[r];
   const int rx = (int)(pk % nxo), ry = (int)((pk / nxo) % nyo), rz = (int)(pk / ((long long)nxo * nyo));
@@ -395,31 +424,33 @@ __global__ void __launch_bounds__(256) k_sim_slabs(const double* __restrict__ gr
 // cutmask = OR over the slabs of (prev ? keep : !keep) (iqsim.jl:264,273); simdev[.!cutmask] = TIdev[.!cutmask].
 __global__ void __launch_bounds__(256) k_sim_paste(double* __restrict__ grid, uint8_t* __restrict__ cutgrid, long long padvol,
                                                    int p0, int p1, const TileInfo* __restrict__ tiles, int R,
+                                                   const ShapeDev* __restrict__ shapes, int maxslabs,
                                                    const double* __restrict__ ti,
                                                    int nx, int ny, int nxo, int nyo, const long long* __restrict__ picked,
-                                                   int tx, int ty, int tz, const SlabSet S, const uint8_t* __restrict__ keep,
+                                                   int tx, int ty, int tz, const uint8_t* __restrict__ keep,
                                                    long long maxslab, const int* __restrict__ cut_iters,
                                                    int* __restrict__ status) {
   const int r = blockIdx.y;  // job
   const TileInfo T = tiles[r / R];
   const int sx = T.sx, sy = T.sy, sz = T.sz;
+  const int nslab = shapes ? shapes[T.shape].S.n : 0;  // shapes == nullptr: the whole tile is pasted (no pasted neighbour)
   const int q = blockIdx.x * 256 + threadIdx.x;
-  if (q == 0 && S.n > 0) {
+  if (q == 0 && nslab > 0) {
     bool bad = false;
-    for (int k = 0; k < S.n; ++k) bad |= cut_iters[r * S.n + k] < 0;
+    for (int k = 0; k < nslab; ++k) bad |= cut_iters[r * maxslabs + k] < 0;
     if (bad) atomicOr(status, 2);
   }
   if (q >= tx * ty * tz) return;
   const int qx = q % tx, qt = q / tx, qy = qt % ty, qz = qt / ty;
   unsigned cm = 0;
-  for (int k = 0; k < S.n; ++k) {
-    const SlabDev& s = S.s[k];
+  for (int k = 0; k < nslab; ++k) {
+    const SlabDev& s = shapes[T.shape].S.s[k];
     const int lx = qx - s.lo[0], ly = qy - s.lo[1], lz = qz - s.lo[2];
     if (lx < 0 || ly < 0 || lz < 0 || lx >= s.sz[0] || ly >= s.sz[1] || lz >= s.sz[2]) continue;
     const int l[3] = {lx, ly, lz};
     const int da = s.dim == 0 ? 1 : 0, db = s.dim == 2 ? 1 : 2;
     const int o = (l[s.dim] * s.n1 + l[db]) * s.n0 + l[da];
-    const unsigned kv = keep[(long long)(r * S.n + k) * maxslab + o];
+    const unsigned kv = keep[(long long)(r * maxslabs + k) * maxslab + o];
     cm |= s.prev ? kv : (kv ^ 1u);
   }
   const long long pk = picked[r];
@@ -456,6 +487,10 @@ void sim_destroy(iq_ctx* c) {
   if (s->h_pickstage) cudaFreeHost(s->h_pickstage);
   cudaFree(s->d_tiles);
   if (s->h_tiles) cudaFreeHost(s->h_tiles);
+  cudaFree(s->d_shapes);
+  if (s->h_shapes) cudaFreeHost(s->h_shapes);
+  cudaFree(s->d_a2list);
+  cudaFree(s->d_cutdims);
   for (int i = 0; i < 2; ++i) {
     if (s->h_export[i]) cudaFreeHost(s->h_export[i]);
     cudaFree(s->d_export2[i]);
@@ -466,11 +501,6 @@ void sim_destroy(iq_ctx* c) {
   if (s->ev_end) cudaEventDestroy(s->ev_end);
   delete s;
   c->sim = nullptr;
-  // the task records cached per mask point into the freed slab buffers
-  for (auto& e : c->masks) {
-    for (auto& ts : e->cut_sets) cudaFree(ts.d_tasks);
-    e->cut_sets.clear();
-  }
 }
 
 namespace {
@@ -544,6 +574,10 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   const size_t R = (size_t)s->R, J = (size_t)s->J, nimg = (size_t)c->nx * c->ny * c->nz, np = (size_t)std::max<int64_t>(d->npath, 1);
   CK(iq::dmalloc((void**)&s->d_tiles, np * sizeof(TileInfo)));
   CK(cudaMallocHost((void**)&s->h_tiles, np * sizeof(TileInfo)));
+  CK(iq::dmalloc((void**)&s->d_shapes, kMaxShapes * sizeof(ShapeDev)));
+  CK(cudaMallocHost((void**)&s->h_shapes, kMaxShapes * sizeof(ShapeDev)));
+  CK(iq::dmalloc((void**)&s->d_a2list, J * sizeof(float*)));
+  CK(iq::dmalloc((void**)&s->d_cutdims, J * s->maxslabs * sizeof(int4)));
   CK(iq::dmalloc((void**)&s->d_grid, R * s->padvol * sizeof(double)));
   CK(cudaMemsetAsync(s->d_grid, 0, R * s->padvol * sizeof(double), c->stream));  // simgrid = zeros (iqsim.jl:165)
   if (s->debug) {
@@ -653,11 +687,65 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   return IQ_OK;
 }
 
-// One launch of `ntile` mutually independent tiles (no two windows intersect) that share the overlap mask and the slab
-// set: ntile x R jobs, job j = tile j / R of realization j % R.  Tiles with hard data and contexts with soft data take
-// one tile per launch (their auxiliary maps belong to the tile, and one map per source is kept).
-static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64_t* starts, const uint8_t* ovlmask,
-                         const iq_sim_slab* slabs, int32_t nslab, int32_t hard_tile) {
+// Registers (or finds) the overlap shape (mask + slab set) and returns its slot in the device shape table.
+static int sim_shape(iq_ctx* c, const uint8_t* ovlmask, const iq_sim_slab* slabs, int32_t nslab, int* slot) {
+  SimState* s = c->sim;
+  const int t[3] = {c->tx, c->ty, c->tz};
+  if (nslab < 0 || nslab > 6 || nslab > s->maxslabs || (nslab > 0 && !slabs)) return fail(IQ_ERR_INVALID, "iq_sim: bad slab list");
+  // ---- slab geometry (host side of iqsim.jl:251-275) ----
+  SlabSet S{};
+  S.n = nslab;
+  size_t smem = 0;
+  std::vector<int> sig;
+  for (int k = 0; k < nslab; ++k) {
+    const iq_sim_slab& in = slabs[k];
+    SlabDev& o = S.s[k];
+    if (in.dim < 0 || in.dim >= c->ndim) return fail(IQ_ERR_INVALID, "iq_sim: slab %d: bad dim", k);
+    o.dim = in.dim;
+    o.prev = in.prev ? 1 : 0;
+    for (int i = 0; i < 3; ++i) {
+      o.lo[i] = i < c->ndim ? in.lo[i] : 0;
+      o.sz[i] = i < c->ndim ? in.sz[i] : 1;
+      if (o.lo[i] < 0 || o.sz[i] < 1 || o.lo[i] + o.sz[i] > t[i]) return fail(IQ_ERR_INVALID, "iq_sim: slab %d outside the tile", k);
+    }
+    const int da = o.dim == 0 ? 1 : 0, db = o.dim == 2 ? 1 : 2;
+    const int tst[3] = {1, t[0], t[0] * t[1]};
+    o.n0 = o.sz[da]; o.n1 = o.sz[db]; o.L = o.sz[o.dim];
+    o.st_a = tst[da]; o.st_b = tst[db]; o.st_k = tst[o.dim];
+    if ((size_t)o.n0 * o.n1 * o.L > s->maxslab || !slab_fits(o.n0, o.n1, o.L))
+      return fail(IQ_ERR_INVALID, "iq_sim: slab %d is larger than the overlap declared at iq_sim_begin", k);
+    if (o.L > 2) smem = std::max(smem, iq::graphcut_smem(o.n0, o.n1, o.L));
+    for (int v : {o.dim, o.prev, o.lo[0], o.lo[1], o.lo[2], o.sz[0], o.sz[1], o.sz[2]}) sig.push_back(v);
+  }
+  MaskEntry* e = nullptr;
+  int rc = get_mask(c, ovlmask, &e);
+  if (rc) return rc;
+  // the mask alone does not determine the slabs (overlap >= 0.5: {px,nx,py} and {px,py,ny} cover the same voxels with
+  // different slabs), so a shape is (mask, slab list)
+  for (size_t i = 0; i < s->shapes.size(); ++i)
+    if (s->shapes[i].e == e && s->shapes[i].sig == sig) { *slot = (int)i; return IQ_OK; }
+  if ((int)s->shapes.size() >= kMaxShapes) return fail(IQ_ERR_STATE, "iq_sim: more than %d distinct overlap shapes", kMaxShapes);
+  const float* a2 = nullptr;
+  if (e->nnz > 0) {
+    rc = get_a2(c, e, -1, &a2);
+    if (rc) return rc;
+  }
+  const int id = (int)s->shapes.size();
+  s->shapes.push_back({e, sig, smem, nslab});
+  ShapeDev& h = s->h_shapes[id];  // written once, never modified: the pinned entry stays valid for the queued copy
+  h.mask = e->d_mask;
+  h.a2 = a2;
+  h.S = S;
+  CK(cudaMemcpyAsync(s->d_shapes + id, &h, sizeof(ShapeDev), cudaMemcpyHostToDevice, c->stream));
+  *slot = id;
+  return IQ_OK;
+}
+
+// One launch of `ntile` mutually independent tiles (no two windows intersect): ntile x R jobs, job j = tile j / R of
+// realization j % R; tile k has overlap shape shapes[k].  Tiles with hard data and contexts with soft data take one
+// tile per launch (their auxiliary maps belong to the tile, and one map per source is kept).
+static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64_t* starts, const int32_t* shapes,
+                         int32_t hard_tile) {
   SimState* s = c->sim;
   const bool hardt = hard_tile != 0;
   const int R = s->R;
@@ -670,62 +758,48 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
   CK(cudaSetDevice(c->device));
   const int t[3] = {c->tx, c->ty, c->tz};
   TileInfo* ht = s->h_tiles + s->tile_cursor;
+  int nempty = 0, maxn = 0;
+  size_t smem = 0;
+  const MaskEntry* ebig = nullptr;   // the shape with the most mask voxels (FFT / direct decision)
+  bool one_shape = true;
   for (int k = 0; k < ntile; ++k) {
     if (steps[k] < 0 || steps[k] >= s->npath) return fail(IQ_ERR_INVALID, "iq_sim_step: step out of range");
+    if (shapes[k] < 0 || shapes[k] >= (int)s->shapes.size()) return fail(IQ_ERR_INVALID, "iq_sim_step: unknown shape id");
     int st3[3] = {0, 0, 0};
     for (int i = 0; i < c->ndim; ++i) {
       st3[i] = (int)starts[3 * k + i];
       if (st3[i] < 0 || st3[i] + t[i] > s->pad[i]) return fail(IQ_ERR_INVALID, "iq_sim_step: tile outside the padded grid");
     }
-    ht[k].sx = st3[0]; ht[k].sy = st3[1]; ht[k].sz = st3[2]; ht[k].step = (int)steps[k];
+    ht[k].sx = st3[0]; ht[k].sy = st3[1]; ht[k].sz = st3[2]; ht[k].step = (int)steps[k]; ht[k].shape = shapes[k];
     for (int m = 0; m < k; ++m) {  // the tiles of one launch read and write disjoint windows
       const bool apart = std::abs(ht[m].sx - st3[0]) >= t[0] || std::abs(ht[m].sy - st3[1]) >= t[1] || std::abs(ht[m].sz - st3[2]) >= t[2];
       if (!apart) return fail(IQ_ERR_INVALID, "iq_sim_step_multi: tiles %d and %d overlap; only independent tiles can share a step", m, k);
     }
+    const SimState::ShapeHost& sh = s->shapes[(size_t)shapes[k]];
+    if (sh.e->nnz == 0) ++nempty;
+    maxn = std::max(maxn, sh.nslab);
+    smem = std::max(smem, sh.smem);
+    if (!ebig || sh.e->nnz > ebig->nnz) ebig = sh.e;
+    if (shapes[k] != shapes[0]) one_shape = false;
   }
+  if (nempty != 0 && nempty != ntile)
+    return fail(IQ_ERR_INVALID, "iq_sim_step_multi: tiles without any pasted neighbour cannot share a step with others");
   const TileInfo* dt = s->d_tiles + s->tile_cursor;
   CK(cudaMemcpyAsync(s->d_tiles + s->tile_cursor, ht, (size_t)ntile * sizeof(TileInfo), cudaMemcpyHostToDevice, c->stream));
   const size_t cursor0 = s->tile_cursor;
   s->tile_cursor += (size_t)ntile;
   const int st3[3] = {ht[0].sx, ht[0].sy, ht[0].sz};  // single-tile paths (hard / soft data)
-  const int64_t step = steps[0];
   const int NJ = ntile * R;  // jobs of this launch
   s->synced = false;
-  MaskEntry* e = nullptr;
-  int rc = get_mask(c, ovlmask, &e);
-  if (rc) return rc;
+  MaskEntry* e = s->shapes[(size_t)shapes[0]].e;
+  int rc = IQ_OK;
   const int64_t l0 = c->launches;
   cudaEvent_t ev[3];
   rc = sim_events(s, ev, 3);
   if (rc) return rc;
 
-  // ---- slab geometry (host side of iqsim.jl:251-275) ----
-  SlabSet S{};
-  S.n = nslab;
-  size_t smem = 0;
-  for (int k = 0; k < nslab; ++k) {
-    const iq_sim_slab& in = slabs[k];
-    SlabDev& o = S.s[k];
-    if (in.dim < 0 || in.dim >= c->ndim) return fail(IQ_ERR_INVALID, "iq_sim_step: slab %d: bad dim", k);
-    o.dim = in.dim;
-    o.prev = in.prev ? 1 : 0;
-    for (int i = 0; i < 3; ++i) {
-      o.lo[i] = i < c->ndim ? in.lo[i] : 0;
-      o.sz[i] = i < c->ndim ? in.sz[i] : 1;
-      if (o.lo[i] < 0 || o.sz[i] < 1 || o.lo[i] + o.sz[i] > t[i]) return fail(IQ_ERR_INVALID, "iq_sim_step: slab %d outside the tile", k);
-    }
-    const int da = o.dim == 0 ? 1 : 0, db = o.dim == 2 ? 1 : 2;
-    const int tst[3] = {1, t[0], t[0] * t[1]};
-    o.n0 = o.sz[da]; o.n1 = o.sz[db]; o.L = o.sz[o.dim];
-    o.st_a = tst[da]; o.st_b = tst[db]; o.st_k = tst[o.dim];
-    if ((size_t)o.n0 * o.n1 * o.L > s->maxslab || !slab_fits(o.n0, o.n1, o.L))
-      return fail(IQ_ERR_INVALID, "iq_sim_step: slab %d is larger than the overlap declared at iq_sim_begin", k);
-    if (o.L > 2) smem = std::max(smem, iq::graphcut_smem(o.n0, o.n1, o.L));
-  }
-  if (nslab > s->maxslabs) return fail(IQ_ERR_INVALID, "iq_sim_step: too many slabs");
-
   const unsigned gJ = (unsigned)((NJ + 127) / 128);
-  if (e->nnz == 0 && s->S == 0 && !hardt) {
+  if (nempty == ntile && s->S == 0 && !hardt) {
     // nothing pasted around the tile: every enabled patch with equal probability (iqsim.jl:237 on an all-zero map);
     // the walk is evaluated on the host from the cached cumulative weights
     rc = build_uniform(c);
@@ -750,8 +824,9 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
       CK(iq::launch_fill_u32(c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch, 0u, c->max_batch, c->stream));
       c->launches += 2;
     }
-    // direct kernel on `nt` dense templates: pack into its layout (shared scratch, stream ordered) and launch
-    auto direct = [&](MaskEntry* me, int image, const float* d_dense, const double* d_b2, int nt, float* d_out, int kind) -> int {
+    // direct kernel on `nt` dense templates of ONE mask starting at job slot job0: pack into its layout (scratch of the
+    // simulation, stream ordered) and launch
+    auto direct = [&](MaskEntry* me, int image, const float* d_dense, const double* d_b2, int nt, float* d_out, int kind, int job0) -> int {
       const int rb = pick_rb(c, nt);
       const int ngrp = (nt + rb - 1) / rb;
       const long long total = (long long)ngrp * me->tmpl_floats * rb;
@@ -770,19 +845,20 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
         CK(cudaGetLastError());
         c->launches++;
       }
-      return launch_direct(c, me, image, s->d_pack, d_b2, nt, rb, false, d_out, kind);
+      return launch_direct(c, me, image, s->d_pack, d_b2, nt, rb, false, d_out, kind, job0);
     };
     k_sim_templates<double><<<dim3((unsigned)c->tz, (unsigned)NJ), 256, 0, c->stream>>>(
-        s->d_grid, s->padvol, s->pad[0], s->pad[1], dt, R, e->d_mask, c->tx, c->ty, c->tz, s->d_tmpl,
+        s->d_grid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_shapes, nullptr, s->d_a2list, c->tx, c->ty, c->tz, s->d_tmpl,
         s->d_plane, s->d_b2, s->d_ticket);
     CK(cudaGetLastError());
     c->launches += 1;
     bool done = false;
-    if (want_fft(c, e, NJ)) {
+    if (want_fft(c, ebig, NJ)) {
       rc = ensure_fft(c, -1);
       if (rc == IQ_OK) {
-        // templates are copies of training-image voxels (or zeros): integer-valued whenever the image is
-        rc = launch_fft(c, e, -1, s->d_tmpl, s->d_b2, NJ, c->image_is_int[-1], c->d_Dovl, 0);
+        // templates are copies of training-image voxels (or zeros): integer-valued whenever the image is.  The FFT
+        // passes do not depend on the mask: one call serves every shape of the launch (A2 map per template).
+        rc = launch_fft(c, e, -1, s->d_tmpl, s->d_b2, NJ, c->image_is_int[-1], c->d_Dovl, 0, 0, one_shape ? nullptr : s->d_a2list);
         if (rc) return rc;
         done = true;
       } else if (!(rc == IQ_ERR_STATE && c->fft_failed)) {
@@ -790,8 +866,16 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
       }
     }
     if (!done) {
-      rc = direct(e, -1, s->d_tmpl, s->d_b2, NJ, c->d_Dovl, 0);
-      if (rc) return rc;
+      // the direct kernel is specialised on the mask (its box decomposition): one launch per run of equal shapes
+      for (int k0 = 0; k0 < ntile;) {
+        int k1 = k0 + 1;
+        while (k1 < ntile && shapes[k1] == shapes[k0]) ++k1;
+        const int job0 = k0 * R, nt = (k1 - k0) * R;
+        rc = direct(s->shapes[(size_t)shapes[k0]].e, -1, s->d_tmpl + (size_t)job0 * c->tilevol, s->d_b2 + job0, nt,
+                    c->d_Dovl + (size_t)job0 * c->npos, 0, job0);
+        if (rc) return rc;
+        k0 = k1;
+      }
     }
     // hard-data distance (iqsim.jl:210-219): the data are the same for every realization -> one map per step
     if (hardt) {
@@ -816,7 +900,7 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
     // soft-data distances (iqsim.jl:222-227): the auxiliary tile is the same for every realization -> one map per step
     for (int si = 0; si < s->S; ++si) {
       k_sim_templates<float><<<dim3((unsigned)c->tz, 1u), 256, 0, c->stream>>>(
-          s->d_aux_pad[si], 0, s->pad[0], s->pad[1], dt, 1, c->full_mask->d_mask, c->tx, c->ty, c->tz,
+          s->d_aux_pad[si], 0, s->pad[0], s->pad[1], dt, 1, nullptr, c->full_mask->d_mask, nullptr, c->tx, c->ty, c->tz,
           s->d_soft_tmpl, s->d_soft_plane, s->d_soft_b2, s->d_soft_ticket);
       CK(cudaGetLastError());
       c->launches++;
@@ -832,7 +916,7 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
         }
       }
       if (!sdone) {
-        rc = direct(c->full_mask, si, s->d_soft_tmpl, s->d_soft_b2, 1, c->d_Dsoft[si], 2 + si);
+        rc = direct(c->full_mask, si, s->d_soft_tmpl, s->d_soft_b2, 1, c->d_Dsoft[si], 2 + si, 0);
         if (rc) return rc;
       }
     }
@@ -886,81 +970,55 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
   }
   CK(cudaEventRecord(ev[1], c->stream));
 
-  // ---- boundary cuts ----
-  if (nslab > 0) {
-    const int ntask = NJ * nslab;
-    k_sim_slabs<<<ntask, 256, 0, c->stream>>>(s->d_grid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_ti64,
-                                              c->nx, c->ny, c->nxo, c->nyo, s->d_picked, c->tx, c->ty, S, s->d_cutA, s->d_cutB,
-                                              (long long)s->maxslab);
+  // ---- boundary cuts: one CTA per (job, slab) of an implicit task grid (iq_cutgpu.cu); jobs with fewer slabs than the
+  //      launch's maximum leave their extra slots empty ----
+  if (maxn > 0) {
+    k_sim_slabs<<<NJ * maxn, 256, 0, c->stream>>>(s->d_grid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_shapes, maxn,
+                                                  s->maxslabs, s->d_ti64, c->nx, c->ny, c->nxo, c->nyo, s->d_picked, c->tx, c->ty,
+                                                  s->d_cutA, s->d_cutB, s->d_cutdims, (long long)s->maxslab);
     CK(cudaGetLastError());
-    // Task records depend on the slab set (dimension and extent of every slab) and the job count only; they are cached
-    // with the mask, but the mask alone does not determine the slabs (overlap >= 0.5: {px,nx,py} and {px,py,ny} cover
-    // the same voxels with different slab shapes), so every cached set carries its slab signature.
-    std::vector<int> sig;
-    sig.reserve(2 + 4 * (size_t)nslab);
-    sig.push_back(NJ);
-    sig.push_back(nslab);
-    for (int k = 0; k < nslab; ++k) { sig.push_back(S.s[k].dim); sig.push_back(S.s[k].n0); sig.push_back(S.s[k].n1); sig.push_back(S.s[k].L); }
-    CutTaskSet* ts = nullptr;
-    for (auto& cand : e->cut_sets)
-      if (cand.sig == sig) { ts = &cand; break; }
-    if (!ts) {
-      // Launch order = longest first: the slabs with the most inner voxels of ALL jobs lead, the cheap ones (e.g. the
-      // one-layer z slabs) come last and fill the tail of the launch.  Only the order of the records changes, not
-      // where a task's data is.
-      std::vector<int> sorder(nslab);
-      for (int i = 0; i < nslab; ++i) sorder[i] = i;
-      std::stable_sort(sorder.begin(), sorder.end(), [&](int a, int b) {
-        return (long long)(S.s[a].L - 2) * S.s[a].n0 * S.s[a].n1 > (long long)(S.s[b].L - 2) * S.s[b].n0 * S.s[b].n1;
-      });
-      std::vector<iq::CutTask> recs((size_t)ntask);
-      for (int b = 0; b < ntask; ++b) {
-        const int k = (b % NJ) * nslab + sorder[b / NJ];  // task whose record sits at launch position b
-        const SlabDev& o = S.s[k % nslab];
-        iq::CutTask& rec = recs[b];
-        rec.A = s->d_cutA + (size_t)k * s->maxslab;
-        rec.B = s->d_cutB + (size_t)k * s->maxslab;
-        rec.keep = s->d_keep + (size_t)k * s->maxslab;
-        rec.n0 = o.n0; rec.n1 = o.n1; rec.L = o.L;
-        rec.iters = s->d_cut_iters + k;
-      }
-      e->cut_sets.emplace_back();
-      ts = &e->cut_sets.back();
-      ts->sig = sig;
-      ts->smem = smem;
-      CK(iq::dmalloc((void**)&ts->d_tasks, recs.size() * sizeof(iq::CutTask)));
-      // pageable source: the copy is staged before the call returns, and it is ordered on the stream before the launch
-      CK(cudaMemcpyAsync(ts->d_tasks, recs.data(), recs.size() * sizeof(iq::CutTask), cudaMemcpyHostToDevice, c->stream));
-    }
-    CK(iq::launch_graphcut(ts->d_tasks, ntask, std::max<size_t>(ts->smem, 64), c->stream));
+    CK(iq::launch_graphcut_grid(s->d_cutA, s->d_cutB, s->d_keep, s->d_cut_iters, s->d_cutdims, (long long)s->maxslab,
+                                s->maxslabs, maxn, NJ, std::max<size_t>(smem, 64), c->stream));
     c->launches += 2;
   }
   CK(cudaEventRecord(ev[2], c->stream));
   k_sim_paste<<<dim3((unsigned)((c->tilevol + 255) / 256), (unsigned)NJ), 256, 0, c->stream>>>(
-      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_ti64, c->nx, c->ny, c->nxo, c->nyo,
-      s->d_picked, c->tx, c->ty, c->tz, S, s->d_keep, (long long)s->maxslab, s->d_cut_iters, s->d_status);
+      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_shapes, s->maxslabs, s->d_ti64, c->nx, c->ny,
+      c->nxo, c->nyo, s->d_picked, c->tx, c->ty, c->tz, s->d_keep, (long long)s->maxslab, s->d_cut_iters, s->d_status);
   CK(cudaGetLastError());
   c->launches++;
   c->last_launches = c->launches - l0;
-  (void)step;
+  return IQ_OK;
+}
+
+int32_t iq_sim_define_shape(iq_ctx* c, const uint8_t* ovlmask, const iq_sim_slab* slabs, int32_t nslab, int32_t* shape) {
+  if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_define_shape: no simulation open on this context");
+  if (!ovlmask || !shape) return fail(IQ_ERR_INVALID, "iq_sim_define_shape: NULL argument");
+  CK(cudaSetDevice(c->device));
+  int slot = -1;
+  const int rc = sim_shape(c, ovlmask, slabs, nslab, &slot);
+  if (rc) return rc;
+  *shape = slot;
   return IQ_OK;
 }
 
 int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
                     int32_t nslab, int32_t hard_tile) {
   if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step: no simulation open on this context");
-  if (!start || !ovlmask || nslab < 0 || nslab > 6 || (nslab > 0 && !slabs)) return fail(IQ_ERR_INVALID, "iq_sim_step: bad argument");
+  if (!start || !ovlmask) return fail(IQ_ERR_INVALID, "iq_sim_step: bad argument");
   if (hard_tile && !c->sim->d_hard_has) return fail(IQ_ERR_INVALID, "iq_sim_step: hard_tile on a simulation opened without hard data");
+  CK(cudaSetDevice(c->device));
+  int32_t slot = -1;
+  const int rc = sim_shape(c, ovlmask, slabs, nslab, &slot);
+  if (rc) return rc;
   const int64_t st[3] = {start[0], c->ndim > 1 ? start[1] : 0, c->ndim > 2 ? start[2] : 0};
-  return sim_step_impl(c, 1, &step, st, ovlmask, slabs, nslab, hard_tile);
+  return sim_step_impl(c, 1, &step, st, &slot, hard_tile);
 }
 
-int32_t iq_sim_step_multi(iq_ctx* c, int32_t ntile, const int64_t* steps, const int64_t* starts, const uint8_t* ovlmask,
-                          const iq_sim_slab* slabs, int32_t nslab) {
+int32_t iq_sim_step_multi(iq_ctx* c, int32_t ntile, const int64_t* steps, const int64_t* starts, const int32_t* shapes) {
   if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step_multi: no simulation open on this context");
-  if (!steps || !starts || !ovlmask || nslab < 0 || nslab > 6 || (nslab > 0 && !slabs))
-    return fail(IQ_ERR_INVALID, "iq_sim_step_multi: bad argument");
-  return sim_step_impl(c, ntile, steps, starts, ovlmask, slabs, nslab, 0);
+  if (!steps || !starts || !shapes) return fail(IQ_ERR_INVALID, "iq_sim_step_multi: NULL argument");
+  return sim_step_impl(c, ntile, steps, starts, shapes, 0);
 }
 
 int32_t iq_sim_step_picked(iq_ctx* c, int64_t step, const int64_t* start, const int64_t* picks) {
@@ -985,7 +1043,7 @@ int32_t iq_sim_step_picked(iq_ctx* c, int64_t step, const int64_t* start, const 
     hp[r] = picks[r];
   }
   TileInfo* ht = s->h_tiles + s->tile_cursor;
-  ht->sx = st3[0]; ht->sy = st3[1]; ht->sz = st3[2]; ht->step = (int)step;
+  ht->sx = st3[0]; ht->sy = st3[1]; ht->sz = st3[2]; ht->step = (int)step; ht->shape = 0;
   const TileInfo* dt = s->d_tiles + s->tile_cursor;
   CK(cudaMemcpyAsync(s->d_tiles + s->tile_cursor, ht, sizeof(TileInfo), cudaMemcpyHostToDevice, c->stream));
   s->tile_cursor += 1;
@@ -993,10 +1051,9 @@ int32_t iq_sim_step_picked(iq_ctx* c, int64_t step, const int64_t* start, const 
   CK(cudaMemcpyAsync(s->d_picked, hp, (size_t)R * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
   k_sim_store_picks<<<gR, 128, 0, c->stream>>>(s->d_picked, s->d_picks, s->npath, dt, R, R);
   CK(cudaGetLastError());
-  SlabSet S{};
   k_sim_paste<<<dim3((unsigned)((c->tilevol + 255) / 256), (unsigned)R), 256, 0, c->stream>>>(
-      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_ti64, c->nx, c->ny, c->nxo, c->nyo,
-      s->d_picked, c->tx, c->ty, c->tz, S, s->d_keep, (long long)s->maxslab, s->d_cut_iters, s->d_status);
+      s->d_grid, s->d_cutgrid, s->padvol, s->pad[0], s->pad[1], dt, R, nullptr, s->maxslabs, s->d_ti64, c->nx, c->ny,
+      c->nxo, c->nyo, s->d_picked, c->tx, c->ty, c->tz, s->d_keep, (long long)s->maxslab, s->d_cut_iters, s->d_status);
   CK(cudaGetLastError());
   c->launches += 2;
   c->last_launches = 2;
@@ -1074,20 +1131,39 @@ int32_t iq_sim_fetch_all(iq_ctx* c, int32_t dtype, const int64_t* crop, void* co
     if (cr[i] < 1 || cr[i] > s->pad[i]) return fail(IQ_ERR_INVALID, "iq_sim_fetch_all: crop outside the padded grid");
   }
   const size_t n = (size_t)cr[0] * cr[1] * cr[2], bytes = n * (dtype == 0 ? sizeof(double) : sizeof(float));
-  if (bytes > s->export2_cap) {
+  // page-locked destinations (iq_host_alloc, cudaHostRegister): device -> host copies go straight into them
+  bool pinned = true;
+  for (int r = 0; r < s->R && pinned; ++r) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, out[r]) != cudaSuccess) { cudaGetLastError(); pinned = false; break; }
+    pinned = at.type == cudaMemoryTypeHost;
+  }
+  if (bytes > s->export2_cap || (!pinned && !s->h_export[0])) {
     CK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 2; ++i) {
       if (s->h_export[i]) cudaFreeHost(s->h_export[i]);
       cudaFree(s->d_export2[i]);
       s->h_export[i] = nullptr;
       s->d_export2[i] = nullptr;
-      CK(cudaMallocHost((void**)&s->h_export[i], bytes));
+      if (!pinned) CK(cudaMallocHost((void**)&s->h_export[i], bytes));
       CK(iq::dmalloc(&s->d_export2[i], bytes));
       if (!s->ev_export[i]) CK(cudaEventCreateWithFlags(&s->ev_export[i], cudaEventDisableTiming));
     }
     s->export2_cap = bytes;
   }
   const unsigned nb = (unsigned)((n + 255) / 256);
+  if (pinned) {
+    for (int r = 0; r < s->R; ++r) {
+      const int b = r & 1;  // two device buffers: the export of realization r + 1 does not wait for the copy of r - 1 ... r
+      const double* g = s->d_grid + (size_t)r * s->padvol;
+      if (dtype == 0) k_sim_export<double><<<nb, 256, 0, c->stream>>>(g, s->pad[0], s->pad[1], cr[0], cr[1], cr[2], (double*)s->d_export2[b]);
+      else k_sim_export<float><<<nb, 256, 0, c->stream>>>(g, s->pad[0], s->pad[1], cr[0], cr[1], cr[2], (float*)s->d_export2[b]);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(out[r], s->d_export2[b], bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return IQ_OK;
+  }
   auto enqueue = [&](int r) -> int {
     const int b = r & 1;
     const double* g = s->d_grid + (size_t)r * s->padvol;

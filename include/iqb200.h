@@ -99,6 +99,12 @@ const char* iq_last_error(void);
 int32_t iq_ctx_create(iq_ctx** out, const iq_ctx_desc* desc);
 int32_t iq_ctx_destroy(iq_ctx* ctx);
 int32_t iq_ctx_npos(const iq_ctx* ctx, int64_t* npos, int64_t* nenabled);
+/* Would iq_ctx_create(desc) build a context identical to `ctx`?  Same device, geometry, nsoft and max_batch, the same
+ * disabled patches, and bitwise the same images: desc's images are uploaded and compared with the resident copies on
+ * the device.  *same = 1 lets a caller that simulates again on the same training image keep the context -- its
+ * summed-volume tables, cached A2 maps, image spectra and work buffers -- instead of rebuilding it.  0 while a
+ * simulation is open on the context. */
+int32_t iq_ctx_matches(iq_ctx* ctx, const iq_ctx_desc* desc, int32_t* same);
 
 /* The hot path: for each of `ntile` tiles sharing `ovlmask` (tile-sized, nonzero = voxel belongs
  * to the overlap with an already pasted neighbour) compute the overlap / hard / soft distance maps,
@@ -200,15 +206,18 @@ int32_t iq_sim_begin(iq_ctx* ctx, const iq_sim_desc* desc);
  * hard distance then is the primary source and the overlap distance the first auxiliary one (src/iqsim.jl:230-231). */
 int32_t iq_sim_step(iq_ctx* ctx, int64_t step, const int64_t* start, const uint8_t* ovlmask, const iq_sim_slab* slabs,
                     int32_t nslab, int32_t hard_tile);
-/* Several MUTUALLY INDEPENDENT tiles in one launch (dependency-level batching): ntile tiles whose windows do not
- * intersect (checked) and that share the overlap mask and the slab set, e.g. the tiles (i, j, k) of a raster path with
- * equal i + 2j + 4k.  A tile only reads and writes its own window, so it depends exactly on the earlier path tiles whose
- * windows intersect it; tiles that share a dependency level may run together and the result is bit for bit that of the
- * sequential path (every (realization, step) keeps its own uniform u[r][steps[k]]).  steps[k] / starts[3k..3k+2] describe
- * tile k; ntile * nreal must not exceed the max_batch of the context.  Not for tiles with hard data nor for contexts with
- * soft data (their auxiliary distance maps belong to one tile): use iq_sim_step for those. */
-int32_t iq_sim_step_multi(iq_ctx* ctx, int32_t ntile, const int64_t* steps, const int64_t* starts, const uint8_t* ovlmask,
-                          const iq_sim_slab* slabs, int32_t nslab);
+/* Several MUTUALLY INDEPENDENT tiles in one launch (dependency-level batching).  A tile only reads and writes its own
+ * window of the simulation grid, so it depends exactly on the earlier path tiles whose windows intersect it; tiles that
+ * share a dependency level (iqh_dependency_levels in iqb200_host.h: i + 2j + 4k on a raster path) may run together and
+ * the result is bit for bit that of the sequential path -- every (realization, step) keeps its own uniform
+ * u[r][steps[k]].  iq_sim_define_shape registers an overlap shape (mask + the slabs whose union it is) once and returns
+ * its id; iq_sim_step_multi launches ntile tiles whose windows do not intersect (checked): tile k has path step
+ * steps[k], origin starts[3k..3k+2] and overlap shape shapes[k].  Shapes may be mixed freely, except that tiles without
+ * any pasted neighbour (empty mask) cannot share a launch with others.  ntile * nreal must not exceed the max_batch of the
+ * context.  Not for tiles with hard data nor for contexts with soft data (their auxiliary distance maps belong to one
+ * tile): use iq_sim_step for those. */
+int32_t iq_sim_define_shape(iq_ctx* ctx, const uint8_t* ovlmask, const iq_sim_slab* slabs, int32_t nslab, int32_t* shape);
+int32_t iq_sim_step_multi(iq_ctx* ctx, int32_t ntile, const int64_t* steps, const int64_t* starts, const int32_t* shapes);
 /* A step whose patterns the caller chose itself (picks[r] = 0-based linear index of the pattern of realization r):
  * the whole tile is pasted (no pasted neighbour, hence no cut).  Used for empty-mask steps of soft-data simulations. */
 int32_t iq_sim_step_picked(iq_ctx* ctx, int64_t step, const int64_t* start, const int64_t* picks);
@@ -251,6 +260,13 @@ int32_t iq_bench_fma2_peak(int32_t device, double* tfma_per_s);
 int32_t iq_release_device_memory(int32_t device);
 /* Free / total memory of `device` in bytes (cudaMemGetInfo), counting the library's cached pool memory as free. */
 int32_t iq_device_free_memory(int32_t device, size_t* free_bytes, size_t* total_bytes);
+
+/* Page-locked host memory for result arrays: iq_sim_fetch_all copies device -> host straight into destinations that
+ * are page-locked (cudaHostAlloc / cudaHostRegister memory: no bounce buffer, no host-side copy, full PCIe / C2C rate);
+ * pageable destinations go through the library's pinned double buffer.  A host language that wants the fast path
+ * allocates its result arrays here (the Python mirror pools them). */
+int32_t iq_host_alloc(size_t bytes, void** out);
+int32_t iq_host_free(void* p);
 
 /* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 0 = auto,
  * 1, 2, 4), "variant" (0 flat kernel, 1 tiled, 2 packed-FMA), "fft" (-1 never, 0 auto crossover, 1 always). */

@@ -96,6 +96,12 @@ typedef struct iqh_stats {
  * [nreal][npath], for parity tests.  Returns IQ_OK or an IQ_ERR_* code (message: iq_last_error()). */
 int32_t iqh_run(const iqh_desc* desc, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats);
 
+/* iqh_run parks the contexts of a finished device-resident simulation (up to 4) and reuses one when the next call
+ * would build an identical context (iq_ctx_matches: same geometry, same job slots, bitwise the same images -- they are
+ * uploaded and compared on every call).  The parked contexts keep their device buffers; iqh_cache_clear destroys them
+ * (IQB200_CTX_CACHE=0 disables the cache). */
+int32_t iqh_cache_clear(void);
+
 /* Dependency levels of a simulation path (the schedule of the device-resident pipeline).  A tile only reads and writes
  * its own window of the simulation grid (template src/iqsim.jl:185, cut slabs :251-275, paste :278), so step s depends
  * exactly on the earlier steps whose tile windows intersect its own: levels[s] = 1 + max level of those, 0 without any.
