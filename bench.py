@@ -333,7 +333,9 @@ def main():
     npath = len(stats[0]["path"])
     if is_resident:
         # uploads: FP32 + FP64 training image and the uniforms; downloads: the cropped realizations and the picks
-        h2d = nti * 12.0 + nreal_local * npath * 8.0
+        # uploads: the training image twice (FP32: once into the context or, when the context is reused, into the
+        # comparison buffer of iq_ctx_matches; + its FP64 copy unless the image is FP32) and the uniforms
+        h2d = nti * (8.0 if ti.dtype == np.float32 else 16.0) + nreal_local * npath * 8.0
         d2h = out_bytes + nreal_local * npath * 8.0
     else:
         h2d = sum(s["stats"]["searches"] for s in stats) / args.steps * float(np.prod(tilesize)) * 4.0 + nti * 4.0

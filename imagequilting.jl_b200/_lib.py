@@ -45,7 +45,7 @@ class IqCutTask(C.Structure):
 class IqSimDesc(C.Structure):
     _fields_ = [("pad_size", C.c_int64 * 3), ("ovl_size", C.c_int64 * 3), ("nreal", C.c_int32), ("ti64", c_double_p),
                 ("u", c_double_p), ("npath", C.c_int64), ("tol", C.c_double), ("debug", C.c_int32),
-                ("aux", C.POINTER(c_float_p)), ("hard_has", c_u8_p), ("hard_val", c_float_p)]
+                ("aux", C.POINTER(c_float_p)), ("hard_has", c_u8_p), ("hard_val", c_float_p), ("exact_cut", C.c_int32)]
 
 
 class IqSimSlab(C.Structure):
@@ -119,6 +119,7 @@ SYMBOLS = {
     "iq_ctx_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
     "iqh_run": (C.c_int32, [C.POINTER(IqhDesc), c_double_p, c_u8_p, c_i64_p, C.POINTER(IqhStats)]),
     "iqh_graphcut": (C.c_int32, [c_double_p, c_double_p, C.c_int32, c_i64_p, C.c_int32, c_u8_p]),
+    "iqh_graphcut_mode": (C.c_int32, [c_double_p, c_double_p, C.c_int32, c_i64_p, C.c_int32, C.c_int32, c_u8_p]),
     "iqh_cache_clear": (C.c_int32, []),
     "iqh_dependency_levels": (C.c_int32, [C.c_int32, c_i64_p, c_i64_p, c_i64_p, c_i64_p, C.c_int64, c_i32_p, c_i32_p]),
 }

@@ -130,6 +130,8 @@ def _prepare(img):
     else:
         base = np.asarray(img)
     F = base.dtype if np.issubdtype(base.dtype, np.floating) and base.dtype.itemsize >= 4 else np.float64
+    if base.dtype == F and base.flags.f_contiguous and not np.isnan(base).any():
+        return base, None  # nothing to replace: the caller's array is used as it is (it is only read)
     out = np.array(base, dtype=F, copy=True, order="F")
     nan = np.isnan(out)
     out[nan] = 0
@@ -160,7 +162,7 @@ def _window_any(flag, win):
 
 def _finddisabled(nanmask, geo):
     """src/utils.jl:115-129: a patch is disabled iff it contains an inactive (NaN) voxel."""
-    if not nanmask.any():
+    if nanmask is None or not nanmask.any():
         return None
     return np.asfortranarray(_window_any(nanmask, geo["tilesize"]).astype(np.uint8))
 
@@ -289,8 +291,10 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     in_dtype = np.asarray(timg).dtype
     is_float = np.issubdtype(in_dtype, np.floating)
     out_dtype = TI.dtype
-    ti64 = _f(TI, np.float64)
+    # the device searches in FP32; cut and paste use the image's own values in FP64.  An FP32 image is widened exactly
+    # on the device (no FP64 host copy, half the upload)
     ti32 = _f(TI, np.float32)
+    ti64 = None if TI.dtype == np.float32 else _f(TI, np.float64)
     disabled = _finddisabled(nanmask, geo)
     aux_pad, aux_ti = [], []
     for aux, auxTI in soft:
@@ -364,7 +368,7 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     d.ndim = N
     d.ti_size, d.tile_size = _i64x3(timg.shape), _i64x3(tilesize)
     d.ovl_size, d.ntiles, d.pad_size = _i64x3(geo["ovlsize"]), _i64x3(ntiles), _i64x3(padsize)
-    d.ti, d.ti_f32 = _ptr(ti64, c_double_p), _ptr(ti32, c_float_p)
+    d.ti, d.ti_f32 = (_ptr(ti64, c_double_p) if ti64 is not None else None), _ptr(ti32, c_float_p)
     d.disabled = _ptr(disabled, c_u8_p) if disabled is not None else None
     d.nsoft = len(soft)
     if soft:
@@ -482,15 +486,20 @@ def dependency_levels(tilesize, ovlsize, ntiles, path):
     return lv[:p.size], nl.value
 
 
-def graphcut(A, B, dim):
-    """Boundary cut keep-mask through the native host routine (src/graphcut.jl:5-84)."""
+def graphcut(A, B, dim, exact=None):
+    """Boundary cut keep-mask through the native host routine (src/graphcut.jl:5-84).  exact=None: integer-valued slabs
+    are cut in exact integer arithmetic (their capacities are degenerate; see include/iqb200_host.h), others in FP64."""
     A = _f(A, np.float64)
     B = _f(B, np.float64)
-    assert A.shape == B.shape, "arrays must have the same size for cut"
+    _require(A.shape == B.shape, "arrays must have the same size for cut")
     keep = np.zeros(A.shape, dtype=np.uint8, order="F")
     sz = np.array(A.shape, dtype=np.int64)
-    check(lib().iqh_graphcut(_ptr(A, c_double_p), _ptr(B, c_double_p), A.ndim, _ptr(sz, c_i64_p), int(dim),
-                             _ptr(keep, c_u8_p)))
+    if exact is None:
+        check(lib().iqh_graphcut(_ptr(A, c_double_p), _ptr(B, c_double_p), A.ndim, _ptr(sz, c_i64_p), int(dim),
+                                 _ptr(keep, c_u8_p)))
+    else:
+        check(lib().iqh_graphcut_mode(_ptr(A, c_double_p), _ptr(B, c_double_p), A.ndim, _ptr(sz, c_i64_p), int(dim),
+                                      int(bool(exact)), _ptr(keep, c_u8_p)))
     return keep.astype(bool)
 
 

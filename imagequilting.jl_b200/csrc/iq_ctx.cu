@@ -1409,7 +1409,7 @@ int32_t iq_cut_batch(iq_ctx* c, const iq_cut_task* tasks, int32_t ntask, int32_t
     P.db = T.dim == 2 ? 1 : 2;
     P.n0 = T.sz[P.da]; P.n1 = T.sz[P.db]; P.L = T.sz[T.dim];
     P.nv = (long long)T.sz[0] * T.sz[1] * T.sz[2];
-    const size_t need = P.L >= 3 ? iq::graphcut_smem(P.n0, P.n1, P.L) : 0;
+    const size_t need = P.L >= 3 ? iq::graphcut_smem(P.n0, P.n1, P.L, c->cut_exact != 0) : 0;
     P.dev = (P.L >= 3 && need <= smem_limit && (long long)(P.L - 2) * P.n0 * P.n1 <= 4096) ? 1 : 0;
     if (P.dev) {
       smem = std::max(smem, need);
@@ -1457,7 +1457,7 @@ int32_t iq_cut_batch(iq_ctx* c, const iq_cut_task* tasks, int32_t ntask, int32_t
       ++k;
     }
     CK(cudaMemcpyAsync(c->d_cut, c->h_cut, off, cudaMemcpyHostToDevice, c->stream));
-    CK(iq::launch_graphcut((const iq::CutTask*)c->d_cut, ndev, smem, c->stream));
+    CK(iq::launch_graphcut((const iq::CutTask*)c->d_cut, ndev, smem, c->stream, c->cut_exact != 0));
     c->launches++;
     CK(cudaMemcpyAsync(c->h_cut, c->d_cut, off, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1468,7 +1468,7 @@ int32_t iq_cut_batch(iq_ctx* c, const iq_cut_task* tasks, int32_t ntask, int32_t
       if (!P.dev) continue;
       const iq_cut_task& T = tasks[t];
       if (h_iters[k] < 0) {
-        P.dev = 0;  // iteration cap hit (never observed): recompute on the host below
+        P.dev = 0;  // iteration cap hit (never observed) / exact range exceeded: recompute on the host below
       } else {
         const unsigned char* kp = (const unsigned char*)(c->h_cut + P.offK);
         const long long st[3] = {1, T.sz[0], (long long)T.sz[0] * T.sz[1]};
@@ -1485,7 +1485,8 @@ int32_t iq_cut_batch(iq_ctx* c, const iq_cut_task* tasks, int32_t ntask, int32_t
     if (plan[t].dev) continue;
     const iq_cut_task& T = tasks[t];
     const int sz[3] = {T.sz[0], T.sz[1], T.sz[2]};
-    iqcut::graphcut(T.A, T.B, sz, T.dim, T.keep, c->cut_work);
+    if (!(c->cut_exact && iqcut::graphcut_exact(T.A, T.B, sz, T.dim, T.keep, c->cut_work)))
+      iqcut::graphcut(T.A, T.B, sz, T.dim, T.keep, c->cut_work);
     if (iters) iters[t] = 0;
   }
   return IQ_OK;
@@ -1600,6 +1601,10 @@ int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
   if (std::strcmp(key, "fft") == 0) {
     if (value < -1 || value > 1) return fail(IQ_ERR_INVALID, "fft must be -1 (never), 0 (auto) or 1 (always)");
     c->fft_mode = (int)value;
+    return IQ_OK;
+  }
+  if (std::strcmp(key, "cut_exact") == 0) {
+    c->cut_exact = value ? 1 : 0;
     return IQ_OK;
   }
   if (std::strcmp(key, "variant") == 0) {

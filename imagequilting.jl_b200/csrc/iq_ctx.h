@@ -110,6 +110,7 @@ struct iq_ctx {
   double* d_prob = nullptr;               // [max_batch][kTauMax]
   double* h_prob = nullptr;               // pinned mirror
   int tau_device = 1;                     // 0 = always evaluate the tau model on the host
+  int cut_exact = 0;                      // iq_cut_batch: exact integer arithmetic (option "cut_exact")
   // position-slice mode (iq_slice_*): candidates of the last select call
   std::vector<std::vector<int64_t>> slice_idx;
   std::vector<std::vector<float>> slice_val;

@@ -15,6 +15,7 @@
 // neighbours are found by index arithmetic.
 #include "iq_cut.h"
 
+#include <algorithm>
 #include <cmath>
 #include <limits>
 
@@ -24,11 +25,27 @@ namespace {
 constexpr int8_t kTerminal = 6, kNone = 7, kOrphan = 8;
 }
 
-void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_t* keep, Work& w) {
+// Capacity arithmetic of the two instantiations: FP64 (what an FP64 max-flow code computes) and unsigned 128-bit
+// integers (exact).
+template <typename T> struct Cap;
+template <> struct Cap<double> {
+  static double inf() { return std::numeric_limits<double>::infinity(); }
+  static bool pos(double c) { return c > 0.0; }
+};
+template <> struct Cap<u128> {
+  static u128 inf() { return ~(u128)0; }
+  static bool pos(u128 c) { return c != 0; }
+};
+
+// conv(c): the FP64 capacity of graphcut.jl:52 in the arithmetic of the cut
+template <typename T, typename Conv>
+static void graphcut_impl(const double* A, const double* B, const int sz[3], int dim, uint8_t* keep, Work& w,
+                          std::vector<NodeT<T>>& nodes, Conv conv) {
+  using Node = NodeT<T>;
   const int nvox = sz[0] * sz[1] * sz[2];
   const int off[6] = {1, -1, sz[0], -sz[0], sz[0] * sz[1], -sz[0] * sz[1]};
-  w.nodes.resize(nvox);
-  Node* nd = w.nodes.data();
+  nodes.resize(nvox);
+  Node* nd = nodes.data();
 
   // ---- topology + initial tree state: the two terminal slices are the roots ----
   {
@@ -45,7 +62,7 @@ void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_
           Node& n = nd[u];
           n.valid = v;
           n.term = c[dim] == 0 ? 1 : (c[dim] == sz[dim] - 1 ? 2 : 0);
-          for (int k = 0; k < 6; ++k) n.cap[k] = 0.0;
+          for (int k = 0; k < 6; ++k) n.cap[k] = 0;
           n.stamp = 0;
           n.tree = n.term;
           n.par = n.term ? kTerminal : kNone;
@@ -69,7 +86,7 @@ void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_
         gAv = std::fabs(A[x] - A[v]);
         gBv = std::fabs(B[x] - B[v]);
       }
-      const double c = (Du + Dv) / (gAu + gAv + gBu + gBv + eps);
+      const T c = conv((Du + Dv) / (gAu + gAv + gBu + gBv + eps));
       nd[u].cap[2 * d] = c;
       nd[v].cap[2 * d + 1] = c;
     }
@@ -80,9 +97,9 @@ void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_
     const int dd = 2 * dim;
     for (int u0 = 0; u0 < nvox; ++u0) {
       if (nd[u0].term != 1) continue;
-      double f = std::numeric_limits<double>::infinity();
-      for (int u = u0; nd[u].term != 2; u += off[dd]) f = std::fmin(f, nd[u].cap[dd]);
-      if (!(f > 0.0)) continue;
+      T f = Cap<T>::inf();
+      for (int u = u0; nd[u].term != 2; u += off[dd]) f = std::min(f, nd[u].cap[dd]);
+      if (!Cap<T>::pos(f)) continue;
       for (int u = u0; nd[u].term != 2;) {
         const int v = u + off[dd];
         nd[u].cap[dd] -= f;
@@ -133,8 +150,8 @@ void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_
         if (!(np.valid & (1 << dir))) continue;
         const int q = p + off[dir];
         Node& nq = nd[q];
-        const double rc = (tp == 1) ? np.cap[dir] : nq.cap[dir ^ 1];
-        if (rc <= 0.0) continue;
+        const T rc = (tp == 1) ? np.cap[dir] : nq.cap[dir ^ 1];
+        if (!Cap<T>::pos(rc)) continue;
         const uint8_t tq = nq.tree;
         if (!tq) {
           nq.tree = tp;
@@ -156,33 +173,33 @@ void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_
 
     // ---- augment along source-root .. s -> t .. sink-root ----
     const int t = s + off[sdir];
-    double f = nd[s].cap[sdir];
+    T f = nd[s].cap[sdir];
     for (int u = s; nd[u].par != kTerminal;) {
       const int pd = nd[u].par, v = u + off[pd];
-      f = std::fmin(f, nd[v].cap[pd ^ 1]);
+      f = std::min(f, nd[v].cap[pd ^ 1]);
       u = v;
     }
     for (int u = t; nd[u].par != kTerminal;) {
       const int pd = nd[u].par, v = u + off[pd];
-      f = std::fmin(f, nd[u].cap[pd]);
+      f = std::min(f, nd[u].cap[pd]);
       u = v;
     }
     nd[s].cap[sdir] -= f;
     nd[t].cap[sdir ^ 1] += f;
     for (int u = s; nd[u].par != kTerminal;) {
       const int pd = nd[u].par, v = u + off[pd];
-      double& c = nd[v].cap[pd ^ 1];
+      T& c = nd[v].cap[pd ^ 1];
       c -= f;
       nd[u].cap[pd] += f;
-      if (c <= 0.0) { nd[u].par = kOrphan; w.orphans.push_back(u); }
+      if (!Cap<T>::pos(c)) { nd[u].par = kOrphan; w.orphans.push_back(u); }
       u = v;
     }
     for (int u = t; nd[u].par != kTerminal;) {
       const int pd = nd[u].par, v = u + off[pd];
-      double& c = nd[u].cap[pd];
+      T& c = nd[u].cap[pd];
       c -= f;
       nd[v].cap[pd ^ 1] += f;
-      if (c <= 0.0) { nd[u].par = kOrphan; w.orphans.push_back(u); }
+      if (!Cap<T>::pos(c)) { nd[u].par = kOrphan; w.orphans.push_back(u); }
       u = v;
     }
 
@@ -198,8 +215,8 @@ void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_
         if (!(nu.valid & (1 << dir))) continue;
         const int q = u + off[dir];
         if (nd[q].tree != tr) continue;
-        const double rc = (tr == 1) ? nd[q].cap[dir ^ 1] : nu.cap[dir];
-        if (rc <= 0.0) continue;
+        const T rc = (tr == 1) ? nd[q].cap[dir ^ 1] : nu.cap[dir];
+        if (!Cap<T>::pos(rc)) continue;
         if (rooted(q)) { best = dir; break; }
       }
       if (best >= 0) {
@@ -211,8 +228,8 @@ void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_
         const int q = u + off[dir];
         Node& nq = nd[q];
         if (nq.tree != tr) continue;
-        const double rc = (tr == 1) ? nq.cap[dir ^ 1] : nu.cap[dir];
-        if (rc > 0.0) activate(q);
+        const T rc = (tr == 1) ? nq.cap[dir ^ 1] : nu.cap[dir];
+        if (Cap<T>::pos(rc)) activate(q);
         if (nq.par == (int8_t)(dir ^ 1)) { nq.par = kOrphan; w.orphans.push_back(q); }
       }
       nu.tree = 0;
@@ -232,10 +249,62 @@ void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_
       if (!(nd[v].valid & (1 << dir))) continue;
       const int x = v + off[dir];
       if (w.reach[x]) continue;
-      if (nd[x].cap[dir ^ 1] > 0.0) { w.reach[x] = 1; w.queue[qt++] = x; }
+      if (Cap<T>::pos(nd[x].cap[dir ^ 1])) { w.reach[x] = 1; w.queue[qt++] = x; }
     }
   }
   for (int u = 0; u < nvox; ++u) keep[u] = w.reach[u] ? 0 : 1;
+}
+
+void graphcut(const double* A, const double* B, const int sz[3], int dim, uint8_t* keep, Work& w) {
+  graphcut_impl<double>(A, B, sz, dim, keep, w, w.nodes, [](double c) { return c; });
+}
+
+bool integer_valued(const double* A, const double* B, int n) {
+  for (int i = 0; i < n; ++i)
+    if (A[i] != std::nearbyint(A[i]) || B[i] != std::nearbyint(B[i])) return false;
+  return true;
+}
+
+bool graphcut_exact(const double* A, const double* B, const int sz[3], int dim, uint8_t* keep, Work& w) {
+  // exponent range of the capacities (same formula and operation order as graphcut_impl)
+  const int nvox = sz[0] * sz[1] * sz[2];
+  const int off[3] = {1, sz[0], sz[0] * sz[1]};
+  const double eps = std::numeric_limits<double>::epsilon();
+  int emin = 1 << 30, emax = -(1 << 30);
+  for (int d = 0; d < 3; ++d) {
+    if (sz[d] < 2) continue;
+    for (int u = 0; u < nvox; ++u) {
+      const int cd = (u / off[d]) % sz[d];
+      if (cd + 1 >= sz[d]) continue;
+      const int v = u + off[d];
+      const double Du = std::fabs(A[u] - B[u]), Dv = std::fabs(A[v] - B[v]);
+      const double gAu = std::fabs(A[v] - A[u]), gBu = std::fabs(B[v] - B[u]);
+      double gAv = gAu, gBv = gBu;
+      if (cd + 2 < sz[d]) {
+        const int x = v + off[d];
+        gAv = std::fabs(A[x] - A[v]);
+        gBv = std::fabs(B[x] - B[v]);
+      }
+      const double c = (Du + Dv) / (gAu + gAv + gBu + gBv + eps);
+      if (!(c > 0.0)) continue;
+      if (!std::isfinite(c)) return false;
+      int ex;
+      std::frexp(c, &ex);
+      emin = std::min(emin, ex - 53);
+      emax = std::max(emax, ex - 53);
+    }
+  }
+  // every capacity < 2^(54 + emax - emin); sums over at most all 3 nvox arcs occur (pre-augmentation, path bottlenecks)
+  int sumbits = 1;
+  while ((1ll << sumbits) < 3ll * nvox + 1) ++sumbits;
+  if (emax >= emin && 54 + (emax - emin) + sumbits > 128) return false;
+  graphcut_impl<u128>(A, B, sz, dim, keep, w, w.nodes_x, [emin](double c) -> u128 {
+    if (!(c > 0.0)) return 0;
+    int ex;
+    const double fr = std::frexp(c, &ex);
+    return (u128)(uint64_t)std::ldexp(fr, 53) << (ex - 53 - emin);
+  });
+  return true;
 }
 
 }  // namespace iqcut

@@ -35,7 +35,6 @@ namespace iq {
 #define IQ_CUT_RELABEL 8
 #endif
 constexpr int kCutThreads = IQ_CUT_THREADS;
-constexpr int kCutBytesPerNode = 6 * 8 + 8 + 4 + 1;  // residuals, excess, height, topology byte
 
 __device__ __forceinline__ double edge_cap(const double* __restrict__ A, const double* __restrict__ B, int lo, int off,
                                            bool has_next) {
@@ -52,18 +51,48 @@ __device__ __forceinline__ double edge_cap(const double* __restrict__ A, const d
   return __ddiv_rn(__dadd_rn(Du, Dv), den);
 }
 
+// Flow arithmetic of the two instantiations: FP64 with explicit round-to-nearest operations (no contraction), and
+// unsigned 128-bit integers -- the FP64 capacities scaled to exact integers, no rounding at all: the cut of
+// integer-valued (categorical) slabs, whose degenerate capacities make an FP64 max-flow's answer depend on its
+// rounding (iq_cut.h, graphcut_exact).
+typedef unsigned __int128 u128;
+template <typename T> struct DCap;
+template <> struct DCap<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+  static __device__ __forceinline__ bool pos(double a) { return a > 0.0; }
+};
+template <> struct DCap<u128> {
+  static __device__ __forceinline__ u128 add(u128 a, u128 b) { return a + b; }
+  static __device__ __forceinline__ u128 sub(u128 a, u128 b) { return a - b; }
+  static __device__ __forceinline__ u128 mn(u128 a, u128 b) { return a < b ? a : b; }
+  static __device__ __forceinline__ bool pos(u128 a) { return a != 0; }
+};
+// FP64 capacity -> arithmetic of the cut (emin: exponent of the unit of the exact representation)
+template <typename T> __device__ __forceinline__ T cap_conv(double c, int emin);
+template <> __device__ __forceinline__ double cap_conv<double>(double c, int) { return c; }
+template <> __device__ __forceinline__ u128 cap_conv<u128>(double c, int emin) {
+  if (!(c > 0.0)) return 0;
+  int ex;
+  const double fr = frexp(c, &ex);
+  return (u128)(unsigned long long)ldexp(fr, 53) << (ex - 53 - emin);
+}
+
 // topology byte of an inner voxel: bits 0..5 = the neighbour in direction dir is an inner voxel,
 // bit 6 = direction 4 (+cut axis) leads into the sink slice, bit 7 = checkerboard colour
 constexpr unsigned kToSink = 64u, kColour = 128u;
 
+template <typename CT>
 __device__ __forceinline__ void graphcut_body(const CutTask& T) {
+  using C = DCap<CT>;
   const int n0 = T.n0, n1 = T.n1, L = T.L;
   const int P = n0 * n1, nfree = (L - 2) * P;
   const double* __restrict__ A = T.A;
   const double* __restrict__ B = T.B;
   extern __shared__ __align__(16) unsigned char smraw[];
-  double* r = reinterpret_cast<double*>(smraw);          // [6][nfree]
-  double* e = r + 6 * (size_t)nfree;                     // [nfree]
+  CT* r = reinterpret_cast<CT*>(smraw);                  // [6][nfree]
+  CT* e = r + 6 * (size_t)nfree;                         // [nfree]
   int* h = reinterpret_cast<int*>(e + nfree);            // [nfree]
   unsigned char* topo = reinterpret_cast<unsigned char*>(h + nfree);  // [nfree]
   const int rows = n1 * (L - 2), m7 = (n0 + 6) / 7, items = rows * m7;
@@ -77,21 +106,58 @@ __device__ __forceinline__ void graphcut_body(const CutTask& T) {
   const int off[6] = {1, -1, n0, -n0, P, -P};
   if (tid < 6) offs[tid] = off[tid];
 
+  // ---- exact arithmetic: exponent range of the capacities (unit 2^emin makes all of them integers) ----
+  __shared__ int s_erange[2];
+  int emin = 0;
+  if (sizeof(CT) > sizeof(double)) {
+    if (tid == 0) { s_erange[0] = 1 << 30; s_erange[1] = -(1 << 30); }
+    __syncthreads();
+    for (int i = tid; i < nfree; i += kCutThreads) {
+      const int u = i + P;
+      const int a = i % n0, b = (i / n0) % n1, k = i / P + 1;
+      const int c3[3] = {a, b, k}, sz3[3] = {n0, n1, L};
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double cv[2] = {0.0, 0.0};
+        if (c3[d] + 1 < sz3[d]) cv[0] = edge_cap(A, B, u, off[2 * d], c3[d] + 2 < sz3[d]);
+        if (c3[d] > 0) cv[1] = edge_cap(A, B, u - off[2 * d], off[2 * d], c3[d] + 1 < sz3[d]);
+        for (int q = 0; q < 2; ++q)
+          if (cv[q] > 0.0) {
+            int ex2;
+            frexp(cv[q], &ex2);
+            if (isinf(cv[q])) ex2 = 1 << 20;
+            atomicMin(&s_erange[0], ex2 - 53);
+            atomicMax(&s_erange[1], ex2 - 53);
+          }
+      }
+    }
+    __syncthreads();
+    emin = s_erange[0];
+    // every capacity < 2^(54 + emax - emin); an excess is at most the sum of the arcs out of the source slice (P of them),
+    // a residual at most twice a capacity: all of it must fit 128 bits
+    int sumbits = 1;
+    while ((1 << sumbits) < P + 1) ++sumbits;
+    if (s_erange[1] >= emin && 54 + (s_erange[1] - emin) + sumbits + 1 > 128) {
+      if (tid == 0 && T.iters) *T.iters = -2;
+      return;
+    }
+  }
+
   // ---- capacities, topology and initial preflow (arcs out of the source slice are saturated) ----
   for (int i = tid; i < nfree; i += kCutThreads) {
     const int u = i + P;
     const int a = i % n0, b = (i / n0) % n1, k = i / P + 1;
     const int c3[3] = {a, b, k}, sz3[3] = {n0, n1, L};
-    double ex = 0.0;
+    CT ex = 0;
     unsigned tp = ((a + b + k) & 1) ? kColour : 0u;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      double cp = 0.0;  // arc towards +d
-      if (c3[d] + 1 < sz3[d]) cp = edge_cap(A, B, u, off[2 * d], c3[d] + 2 < sz3[d]);
+      CT cp = 0;  // arc towards +d
+      if (c3[d] + 1 < sz3[d]) cp = cap_conv<CT>(edge_cap(A, B, u, off[2 * d], c3[d] + 2 < sz3[d]), emin);
       r[(2 * d) * nfree + i] = cp;
-      double cm = 0.0;  // arc towards -d (capacity defined from the lower voxel)
-      if (c3[d] > 0) cm = edge_cap(A, B, u - off[2 * d], off[2 * d], c3[d] + 1 < sz3[d]);
-      if (d == 2 && k == 1) { ex = cm; cm = 0.0; }  // from the source slice: saturated, never pushed back
+      CT cm = 0;  // arc towards -d (capacity defined from the lower voxel)
+      if (c3[d] > 0) cm = cap_conv<CT>(edge_cap(A, B, u - off[2 * d], off[2 * d], c3[d] + 1 < sz3[d]), emin);
+      if (d == 2 && k == 1) { ex = cm; cm = 0; }  // from the source slice: saturated, never pushed back
       r[(2 * d + 1) * nfree + i] = cm;
       if (d < 2) {
         if (c3[d] + 1 < sz3[d]) tp |= 1u << (2 * d);
@@ -123,7 +189,7 @@ __device__ __forceinline__ void graphcut_body(const CutTask& T) {
     __syncthreads();
     for (int i0 = 0; i0 < nfree; i0 += kCutThreads) {
       const int i = i0 + tid;
-      const bool first = i < nfree && (topo[i] & kToSink) && r[4 * nfree + i] > 0.0;
+      const bool first = i < nfree && (topo[i] & kToSink) && C::pos(r[4 * nfree + i]);
       if (i < nfree) h[i] = first ? 1 : HMAX;
       const unsigned bal = __ballot_sync(0xffffffffu, first);
       if (bal) {
@@ -150,7 +216,7 @@ __device__ __forceinline__ void graphcut_body(const CutTask& T) {
         if (!((topo[v] >> dir) & 1u)) continue;
         const int x = v + offs[dir];
         if (h[x] != HMAX) continue;
-        if (!(r[(dir ^ 1) * nfree + x] > 0.0)) continue;  // arc x -> v must have residual capacity
+        if (!C::pos(r[(dir ^ 1) * nfree + x])) continue;  // arc x -> v must have residual capacity
         if (atomicCAS(&h[x], HMAX, level + 1) == HMAX) nxt[atomicAdd(&s_cnt[cn], 1)] = (unsigned short)x;
       }
       __syncthreads();
@@ -199,40 +265,40 @@ __device__ __forceinline__ void graphcut_body(const CutTask& T) {
       for (int w = tid; w < items; w += kCutThreads) {
         const int i = cl[w];
         if (i == 0xffff) continue;
-        double ex = e[i];
+        CT ex = e[i];
         int hi = h[i];
-        if (!(ex > 0.0) || hi >= HMAX) continue;
+        if (!C::pos(ex) || hi >= HMAX) continue;
         const unsigned tp = topo[i];
-        double rc[6];
+        CT rc[6];
         int hv[6];
 #pragma unroll
         for (int dir = 0; dir < 6; ++dir) {
           const bool inner = (tp >> dir) & 1u;
           const bool sink = (dir == 4) && (tp & kToSink);
-          rc[dir] = (inner || sink) ? r[dir * nfree + i] : 0.0;
+          rc[dir] = (inner || sink) ? r[dir * nfree + i] : (CT)0;
           hv[dir] = sink ? 0 : (inner ? h[i + off[dir]] : HMAX);
         }
         int mh = HMAX;  // lowest neighbour over the arcs that still have residual capacity after the pushes
 #pragma unroll
         for (int dir = 0; dir < 6; ++dir) {
-          double rcd = rc[dir];
-          if (!(rcd > 0.0)) continue;
-          if (ex > 0.0 && hi == hv[dir] + 1) {
-            const double d = fmin(ex, rcd);
-            rcd = __dsub_rn(rcd, d);
-            ex = __dsub_rn(ex, d);
+          CT rcd = rc[dir];
+          if (!C::pos(rcd)) continue;
+          if (C::pos(ex) && hi == hv[dir] + 1) {
+            const CT d = C::mn(ex, rcd);
+            rcd = C::sub(rcd, d);
+            ex = C::sub(ex, d);
             r[dir * nfree + i] = rcd;
             if (!((dir == 4) && (tp & kToSink))) {
               const int v = i + off[dir];
-              r[(dir ^ 1) * nfree + v] = __dadd_rn(r[(dir ^ 1) * nfree + v], d);  // only the few admissible arcs pay these
-              e[v] = __dadd_rn(e[v], d);
+              r[(dir ^ 1) * nfree + v] = C::add(r[(dir ^ 1) * nfree + v], d);  // only the few admissible arcs pay these
+              e[v] = C::add(e[v], d);
               active = 1;  // v sits one level below: it can push on
             }
           }
-          if (rcd > 0.0) mh = min(mh, hv[dir]);
+          if (C::pos(rcd)) mh = min(mh, hv[dir]);
         }
         e[i] = ex;
-        if (ex > 0.0) {
+        if (C::pos(ex)) {
           if (mh + 1 > hi) hi = min(mh + 1, HMAX);
           h[i] = hi;
           if (hi < HMAX) active = 1;
@@ -272,12 +338,14 @@ __device__ __forceinline__ void graphcut_body(const CutTask& T) {
 }
 
 // explicit task list (iq_cut_batch)
-__global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* tasks) { graphcut_body(tasks[blockIdx.x]); }
+template <typename CT>
+__global__ void __launch_bounds__(kCutThreads, 1) k_graphcut(const CutTask* tasks) { graphcut_body<CT>(tasks[blockIdx.x]); }
 
 // Implicit task grid of the resident simulation: task (job, k) = slab k of job `job`, data at (job * maxslabs + k) * maxslab,
 // dims[task] = {n0, n1, L, -} written by the slab gather (L = 0: the job's tile has no slab k -> nothing to do).  Launch
 // position b -> slab index b / njobs, job b % njobs: the cuts of one slab kind (same size, similar cost) run side by
 // side, the first kinds (x, y overlaps: the thick ones) lead and the thin z overlaps fill the tail.
+template <typename CT>
 __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut_grid(const double* A, const double* B, unsigned char* keep, int* iters,
                                                                   const int4* __restrict__ dims, long long maxslab,
                                                                   int maxslabs, int njobs) {
@@ -291,27 +359,40 @@ __global__ void __launch_bounds__(kCutThreads, 1) k_graphcut_grid(const double* 
   T.keep = keep + (long long)task * maxslab;
   T.n0 = d.x; T.n1 = d.y; T.L = d.z;
   T.iters = iters + task;
-  graphcut_body(T);
+  graphcut_body<CT>(T);
 }
 
-size_t graphcut_smem(int n0, int n1, int L) {
+size_t graphcut_smem(int n0, int n1, int L, bool exact) {
   const size_t nfree = (size_t)(L - 2) * n0 * n1;
   const size_t items = (size_t)n1 * (L - 2) * ((n0 + 6) / 7);
-  return nfree * (kCutBytesPerNode - 1) + ((nfree + 3) & ~(size_t)3) + (7 * items + 2 * nfree) * sizeof(unsigned short) + 16;
+  const size_t flow = exact ? sizeof(u128) : sizeof(double);  // 6 residuals + the excess per voxel
+  return nfree * (7 * flow + 4) + ((nfree + 3) & ~(size_t)3) + (7 * items + 2 * nfree) * sizeof(unsigned short) + 16;
 }
 
 cudaError_t launch_graphcut_grid(const double* A, const double* B, unsigned char* keep, int* iters, const int4* dims,
-                                 long long maxslab, int maxslabs, int nslab, int njobs, size_t smem, cudaStream_t s) {
-  cudaError_t err = cudaFuncSetAttribute(k_graphcut_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return err;
-  k_graphcut_grid<<<nslab * njobs, kCutThreads, smem, s>>>(A, B, keep, iters, dims, maxslab, maxslabs, njobs);
+                                 long long maxslab, int maxslabs, int nslab, int njobs, size_t smem, bool exact, cudaStream_t s) {
+  if (exact) {
+    cudaError_t err = cudaFuncSetAttribute(k_graphcut_grid<u128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k_graphcut_grid<u128><<<nslab * njobs, kCutThreads, smem, s>>>(A, B, keep, iters, dims, maxslab, maxslabs, njobs);
+  } else {
+    cudaError_t err = cudaFuncSetAttribute(k_graphcut_grid<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k_graphcut_grid<double><<<nslab * njobs, kCutThreads, smem, s>>>(A, B, keep, iters, dims, maxslab, maxslabs, njobs);
+  }
   return cudaGetLastError();
 }
 
-cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s) {
-  cudaError_t err = cudaFuncSetAttribute(k_graphcut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return err;
-  k_graphcut<<<ntask, kCutThreads, smem, s>>>(d_tasks);
+cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s, bool exact) {
+  if (exact) {
+    cudaError_t err = cudaFuncSetAttribute(k_graphcut<u128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k_graphcut<u128><<<ntask, kCutThreads, smem, s>>>(d_tasks);
+  } else {
+    cudaError_t err = cudaFuncSetAttribute(k_graphcut<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k_graphcut<double><<<ntask, kCutThreads, smem, s>>>(d_tasks);
+  }
   return cudaGetLastError();
 }
 

@@ -34,6 +34,11 @@ extern "C" void iq_post_error(const char* msg);  // iq_ctx.cu: sets the calling 
 
 namespace {
 
+int fail_exact_range() {
+  iq_post_error("iqh_graphcut_mode: the capacities of this slab span more than 128 bits; no exact cut");
+  return IQ_ERR_INVALID;
+}
+
 using clk = std::chrono::steady_clock;
 double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
 
@@ -151,7 +156,24 @@ extern "C" int32_t iqh_graphcut(const double* A, const double* B, int32_t ndim, 
   for (int i = 0; i < ndim; ++i) sz[i] = (int)sz64[i];
   if (sz[dim] < 2) return IQ_ERR_INVALID;
   iqcut::Work w;
-  iqcut::graphcut(A, B, sz, dim, keep, w);
+  // integer-valued slabs: exact integer arithmetic (one well-defined cut), FP64 otherwise
+  if (!(iqcut::integer_valued(A, B, sz[0] * sz[1] * sz[2]) && iqcut::graphcut_exact(A, B, sz, dim, keep, w)))
+    iqcut::graphcut(A, B, sz, dim, keep, w);
+  return IQ_OK;
+}
+
+extern "C" int32_t iqh_graphcut_mode(const double* A, const double* B, int32_t ndim, const int64_t* sz64, int32_t dim, int32_t exact,
+                                     uint8_t* keep) {
+  if (!A || !B || !sz64 || !keep || ndim < 1 || ndim > 3 || dim < 0 || dim >= ndim) return IQ_ERR_INVALID;
+  int sz[3] = {1, 1, 1};
+  for (int i = 0; i < ndim; ++i) sz[i] = (int)sz64[i];
+  if (sz[dim] < 2) return IQ_ERR_INVALID;
+  iqcut::Work w;
+  if (exact) {
+    if (!iqcut::graphcut_exact(A, B, sz, dim, keep, w)) return fail_exact_range();
+  } else {
+    iqcut::graphcut(A, B, sz, dim, keep, w);
+  }
   return IQ_OK;
 }
 
@@ -294,13 +316,11 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
                  int* status) {
   *status = 0;
   const int S = D->nsoft;
-  if (D->pipeline == 0) {
-    // Integer-valued (categorical) images make the cut capacities of graphcut.jl:52 degenerate (division by eps next
-    // to O(1) terms): equal-cost cuts abound and which one comes out depends on the max-flow algorithm's rounding.
-    // The reference's choice is Boykov-Kolmogorov on the host, so "auto" keeps such images on the host-staged
-    // pipeline (host cuts); continuous images have a unique minimum cut and go device-resident.
-    if (image_is_integer(D, G)) return IQ_ERR_STATE;
-  }
+  // Integer-valued (categorical) images make the cut capacities of graphcut.jl:52 degenerate (division by eps next
+  // to O(1) terms): equal-cost cuts abound and which one an FP64 max-flow returns depends on its rounding.  Their cuts
+  // therefore run in exact integer arithmetic -- on the device here, on the host in the staged pipeline -- which has
+  // one well-defined answer; continuous images have a unique minimum cut with a margin and keep FP64.
+  const bool exact_cut = image_is_integer(D, G);
   const auto t_start = clk::now();
   const int R = D->nreal;
   // one lockstep group by default: a launch already carries every realization (FFT pairs, one cut CTA per slab).
@@ -375,6 +395,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     sd.aux = S ? D->aux : nullptr;
     sd.hard_has = D->hard_has;
     sd.hard_val = D->hard_has ? D->hard_val : nullptr;
+    sd.exact_cut = exact_cut ? 1 : 0;
     rc = iq_sim_begin(g.ctx, &sd);
   }
   if (rc != IQ_OK) { destroy_all(); return rc; }
@@ -707,7 +728,7 @@ extern "C" int32_t iqh_dependency_levels(int32_t ndim, const int64_t* tile_size,
 }
 
 extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cuts, int64_t* out_picks, iqh_stats* stats) {
-  if (!D || !D->ti || !D->ti_f32 || !D->path || !D->u) return IQ_ERR_INVALID;
+  if (!D || !D->ti_f32 || !D->path || !D->u) return IQ_ERR_INVALID;
   if (!out_grids && !D->out_real) return IQ_ERR_INVALID;
   if (D->debug && !out_cuts) return IQ_ERR_INVALID;
   const auto t_start = clk::now();
@@ -738,6 +759,15 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     if (rcr != IQ_OK && !((rcr == IQ_ERR_STATE || is_oom(rcr)) && D->pipeline == 0)) return rcr;
     if (rcr != IQ_OK && is_oom(rcr)) iq_release_device_memory(D->device);
     // otherwise: does not qualify (or a data-dependent bail-out): host-staged below, still on the GPU
+  }
+  // FP64 copy of the training image for the host-side cut and paste (exact: the image is FP32 when desc.ti is NULL)
+  std::vector<double> own_ti64;
+  const double* ti64 = D->ti;
+  if (!ti64) {
+    const size_t nimg = (size_t)G.n[0] * G.n[1] * G.n[2];
+    own_ti64.resize(nimg);
+    for (size_t i = 0; i < nimg; ++i) own_ti64[i] = (double)D->ti_f32[i];
+    ti64 = own_ti64.data();
   }
   std::vector<double> own_grids;
   if (!out_grids) {
@@ -896,6 +926,8 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
   //      slab) cut; the last cut to finish enqueues one paste task per realization; the last paste
   //      releases the group's latch ----
   Pool pool(nthreads);
+  // integer-valued images: exact integer cuts (see run_resident); iq_cut_batch is FP64, so never chosen for them by default
+  const bool exact_cuts = image_is_integer(D, G);
   auto cut_task = [&](Group& g, int task, int tid) {
     iqcut::Work& w = work[tid];
     const int nslab = (int)g.slabs.size();
@@ -915,10 +947,11 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
       for (int y = 0; y < s.sz[1]; ++y) {
         const int qy = s.lo[1] + y, qz = s.lo[2] + z;
         const double* ga = grid + ((long long)(start[2] + qz) * pad[1] + (start[1] + qy)) * pad[0] + start[0] + s.lo[0];
-        const double* gb = D->ti + ((long long)(rs[2] + qz) * n[1] + (rs[1] + qy)) * n[0] + rs[0] + s.lo[0];
+        const double* gb = ti64 + ((long long)(rs[2] + qz) * n[1] + (rs[1] + qy)) * n[0] + rs[0] + s.lo[0];
         for (int x = 0; x < s.sz[0]; ++x, ++i) { w.A[i] = ga[x]; w.B[i] = gb[x]; }
       }
-    iqcut::graphcut(w.A.data(), w.B.data(), s.sz, s.d, g.keepbuf[task].data(), w);
+    if (!(exact_cuts && iqcut::graphcut_exact(w.A.data(), w.B.data(), s.sz, s.d, g.keepbuf[task].data(), w)))
+      iqcut::graphcut(w.A.data(), w.B.data(), s.sz, s.d, g.keepbuf[task].data(), w);
   };
   auto paste_task = [&](Group& g, int r, int tid) {
     iqcut::Work& w = work[tid];
@@ -945,7 +978,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
     for (int z = 0; z < t[2]; ++z)
       for (int y = 0; y < t[1]; ++y) {
         const long long gi = ((long long)(start[2] + z) * pad[1] + (start[1] + y)) * pad[0] + start[0];
-        const double* src = D->ti + ((long long)(rs[2] + z) * n[1] + (rs[1] + y)) * n[0] + rs[0];
+        const double* src = ti64 + ((long long)(rs[2] + z) * n[1] + (rs[1] + y)) * n[0] + rs[0];
         const uint8_t* cm = &w.cutmask[((size_t)z * t[1] + y) * t[0]];
         for (int x = 0; x < t[0]; ++x) {
           if (!cm[x]) grid[gi + x] = src[x];
@@ -967,7 +1000,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
   // few host threads per GPU (multi-GPU nodes): the cuts of a step run on the device instead -- but never by default
   // on integer-valued (categorical) images, whose degenerate capacities make the cut depend on the max-flow algorithm
   // (same rule as run_resident): the result must not depend on the host's core count or the nthreads argument
-  const bool device_cut = D->cut_mode == 2 || (D->cut_mode == 0 && nthreads < 6 && !image_is_integer(D, G));
+  const bool device_cut = D->cut_mode == 2 || (D->cut_mode == 0 && nthreads < 6 && !exact_cuts);
   std::atomic<int> cut_error{IQ_OK};
   std::mutex cut_error_m;
   std::string cut_error_msg;
@@ -993,7 +1026,7 @@ extern "C" int32_t iqh_run(const iqh_desc* D, double* out_grids, uint8_t* out_cu
         for (int y = 0; y < s.sz[1]; ++y) {
           const int qy = s.lo[1] + y, qz = s.lo[2] + z;
           const double* ga = grid + ((long long)(start[2] + qz) * pad[1] + (start[1] + qy)) * pad[0] + start[0] + s.lo[0];
-          const double* gb = D->ti + ((long long)(rs[2] + qz) * n[1] + (rs[1] + qy)) * n[0] + rs[0] + s.lo[0];
+          const double* gb = ti64 + ((long long)(rs[2] + qz) * n[1] + (rs[1] + qy)) * n[0] + rs[0] + s.lo[0];
           for (int x = 0; x < s.sz[0]; ++x, ++i) { g.slabA[task][i] = ga[x]; g.slabB[task][i] = gb[x]; }
         }
       iq_cut_task& T = g.cut_tasks[task];

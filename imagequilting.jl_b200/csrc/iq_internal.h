@@ -101,12 +101,12 @@ struct CutTask {
   int n0, n1, L;
   int* iters;           // out (optional): push-relabel sweeps used, -1 = iteration cap hit
 };
-size_t graphcut_smem(int n0, int n1, int L);
-cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s);
+size_t graphcut_smem(int n0, int n1, int L, bool exact = false);
+cudaError_t launch_graphcut(const CutTask* d_tasks, int ntask, size_t smem, cudaStream_t s, bool exact = false);
 // Implicit task grid (resident simulation): nslab * njobs CTAs, task (job, k) at (job * maxslabs + k) * maxslab, skipped
 // when dims[task].z (L) < 2.
 cudaError_t launch_graphcut_grid(const double* A, const double* B, unsigned char* keep, int* iters, const int4* dims,
-                                 long long maxslab, int maxslabs, int nslab, int njobs, size_t smem, cudaStream_t s);
+                                 long long maxslab, int maxslabs, int nslab, int njobs, size_t smem, bool exact, cudaStream_t s);
 
 // Device allocation from the stream-ordered default memory pool with the release threshold lifted: memory freed by
 // one simulation (cudaFree returns it to the pool) is handed to the next without a trip to the driver's slow

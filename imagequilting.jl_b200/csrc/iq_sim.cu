@@ -60,6 +60,7 @@ struct SimState {
   int64_t npath = 0;
   double tol = 0.1;
   int debug = 0;
+  bool exact = false;             // boundary cuts in exact integer arithmetic (integer-valued images)
   double* d_grid = nullptr;       // [R][padvol]
   uint8_t* d_cutgrid = nullptr;   // [R][padvol] (debug)
   double* d_ti64 = nullptr;       // [nimg]
@@ -460,6 +461,11 @@ __global__ void __launch_bounds__(256) k_sim_paste(double* __restrict__ grid, ui
   if (cutgrid) cutgrid[gi] = (uint8_t)cm;
 }
 
+__global__ void __launch_bounds__(256) k_sim_widen(const float* __restrict__ in, double* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+
 template <typename OT>
 __global__ void __launch_bounds__(256) k_sim_export(const double* __restrict__ grid, int p0, int p1, int c0, int c1, int c2,
                                                     OT* __restrict__ out) {
@@ -507,10 +513,10 @@ namespace {
 
 constexpr size_t kCutSmemLimit = 220 * 1024;
 
-bool slab_fits(int n0, int n1, int L) {
+bool slab_fits(int n0, int n1, int L, bool exact) {
   if (L < 2) return false;
   if (L == 2) return true;  // no inner voxel: the kernel only writes the source / sink slices
-  return iq::graphcut_smem(n0, n1, L) <= kCutSmemLimit && (long long)(L - 2) * n0 * n1 <= 4096;
+  return iq::graphcut_smem(n0, n1, L, exact) <= kCutSmemLimit && (long long)(L - 2) * n0 * n1 <= 4096;
 }
 
 int sim_events(SimState* s, cudaEvent_t* out, int n) {
@@ -532,7 +538,7 @@ using namespace iqimpl;
 extern "C" {
 
 int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
-  if (!c || !d || !d->ti64 || !d->u) return fail(IQ_ERR_INVALID, "iq_sim_begin: NULL argument");
+  if (!c || !d || !d->u) return fail(IQ_ERR_INVALID, "iq_sim_begin: NULL argument");
   if (d->nreal < 1 || d->nreal > c->max_batch) return fail(IQ_ERR_INVALID, "iq_sim_begin: nreal must be in 1..max_batch");
   if (c->max_batch % d->nreal != 0)
     return fail(IQ_ERR_INVALID, "iq_sim_begin: max_batch of the context must be a multiple of nreal (job slots = tiles per step x nreal)");
@@ -555,7 +561,7 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   for (int dd = 0; dd < c->ndim; ++dd) {
     if (ov[dd] <= 1) continue;
     const int da = dd == 0 ? 1 : 0, db = dd == 2 ? 1 : 2;
-    if (!slab_fits(t[da], t[db], ov[dd]))
+    if (!slab_fits(t[da], t[db], ov[dd], d->exact_cut != 0))
       return fail(IQ_ERR_STATE, "overlap slab %d x %d x %d does not fit the shared-memory cut kernel", t[da], t[db], ov[dd]);
     maxslab = std::max(maxslab, (size_t)t[da] * t[db] * ov[dd]);
     maxslabs += 2;
@@ -569,6 +575,7 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
   s->npath = d->npath;
   s->tol = d->tol;
   s->debug = d->debug;
+  s->exact = d->exact_cut != 0;
   s->maxslab = maxslab;
   s->maxslabs = std::max(maxslabs, 1);
   const size_t R = (size_t)s->R, J = (size_t)s->J, nimg = (size_t)c->nx * c->ny * c->nz, np = (size_t)std::max<int64_t>(d->npath, 1);
@@ -585,7 +592,12 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     CK(cudaMemsetAsync(s->d_cutgrid, 0, R * s->padvol, c->stream));
   }
   CK(iq::dmalloc((void**)&s->d_ti64, nimg * sizeof(double)));
-  CK(cudaMemcpyAsync(s->d_ti64, d->ti64, nimg * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (d->ti64) {
+    CK(cudaMemcpyAsync(s->d_ti64, d->ti64, nimg * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    k_sim_widen<<<(unsigned)((nimg + 255) / 256), 256, 0, c->stream>>>(c->d_ti, s->d_ti64, (long long)nimg);
+    CK(cudaGetLastError());
+  }
   s->h_u.assign(d->u, d->u + R * (size_t)d->npath);
   CK(iq::dmalloc((void**)&s->d_u, R * np * sizeof(double)));
   if (d->npath > 0)
@@ -712,9 +724,9 @@ static int sim_shape(iq_ctx* c, const uint8_t* ovlmask, const iq_sim_slab* slabs
     const int tst[3] = {1, t[0], t[0] * t[1]};
     o.n0 = o.sz[da]; o.n1 = o.sz[db]; o.L = o.sz[o.dim];
     o.st_a = tst[da]; o.st_b = tst[db]; o.st_k = tst[o.dim];
-    if ((size_t)o.n0 * o.n1 * o.L > s->maxslab || !slab_fits(o.n0, o.n1, o.L))
+    if ((size_t)o.n0 * o.n1 * o.L > s->maxslab || !slab_fits(o.n0, o.n1, o.L, s->exact))
       return fail(IQ_ERR_INVALID, "iq_sim: slab %d is larger than the overlap declared at iq_sim_begin", k);
-    if (o.L > 2) smem = std::max(smem, iq::graphcut_smem(o.n0, o.n1, o.L));
+    if (o.L > 2) smem = std::max(smem, iq::graphcut_smem(o.n0, o.n1, o.L, s->exact));
     for (int v : {o.dim, o.prev, o.lo[0], o.lo[1], o.lo[2], o.sz[0], o.sz[1], o.sz[2]}) sig.push_back(v);
   }
   MaskEntry* e = nullptr;
@@ -978,7 +990,7 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
                                                   s->d_cutA, s->d_cutB, s->d_cutdims, (long long)s->maxslab);
     CK(cudaGetLastError());
     CK(iq::launch_graphcut_grid(s->d_cutA, s->d_cutB, s->d_keep, s->d_cut_iters, s->d_cutdims, (long long)s->maxslab,
-                                s->maxslabs, maxn, NJ, std::max<size_t>(smem, 64), c->stream));
+                                s->maxslabs, maxn, NJ, std::max<size_t>(smem, 64), s->exact, c->stream));
     c->launches += 2;
   }
   CK(cudaEventRecord(ev[2], c->stream));

@@ -183,7 +183,8 @@ typedef struct iq_sim_desc {
   int64_t ovl_size[3];   /* overlap size per dimension (src/iqsim.jl:92): fixes the largest cut slab */
   int32_t nreal;         /* realizations held by this context; max_batch of the context must be a multiple of it
                             (max_batch / nreal = tiles one iq_sim_step_multi launch may carry) */
-  const double* ti64;    /* training image in FP64 (the values that are pasted and cut), ti_size doubles */
+  const double* ti64;    /* training image in FP64 (the values that are pasted and cut), ti_size doubles; NULL = the
+                            context's FP32 image is exact (FP32 input) and is widened on the device */
   const double* u;       /* [nreal][npath] uniforms in the reference's draw order (src/iqsim.jl:243) */
   int64_t npath;         /* number of path steps */
   double tol;
@@ -193,6 +194,11 @@ typedef struct iq_sim_desc {
   const uint8_t* hard_has; /* hard data (src/utils.jl:18-36): pad_size bytes, nonzero = voxel carries a non-NaN datum;
                               NULL = no hard data */
   const float* hard_val;   /* pad_size floats: the datum where hard_has */
+  int32_t exact_cut;       /* nonzero: boundary cuts in exact integer arithmetic (the FP64 capacities of graphcut.jl:52 as
+                              128-bit integers: no rounding in the flow, one well-defined cut).  For integer-valued
+                              (categorical) images, whose degenerate capacities -- (Du+Dv)/eps next to O(1) terms -- make an
+                              FP64 max-flow return whichever equal-cost cut its rounding favours.  Needs twice the shared
+                              memory per slab voxel; a slab whose capacities span more than ~2^56 raises status bit 2. */
 } iq_sim_desc;
 typedef struct iq_sim_slab {   /* one overlap slab of the current tile, in tile coordinates */
   int32_t dim;           /* dimension of the overlap */
@@ -269,7 +275,8 @@ int32_t iq_host_alloc(size_t bytes, void** out);
 int32_t iq_host_free(void* p);
 
 /* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 0 = auto,
- * 1, 2, 4), "variant" (0 flat kernel, 1 tiled, 2 packed-FMA), "fft" (-1 never, 0 auto crossover, 1 always). */
+ * 1, 2, 4), "variant" (0 flat kernel, 1 tiled, 2 packed-FMA), "fft" (-1 never, 0 auto crossover, 1 always),
+ * "cut_exact" (iq_cut_batch in exact integer arithmetic, for integer-valued slabs; see iq_sim_desc.exact_cut). */
 int32_t iq_ctx_set_option(iq_ctx* ctx, const char* key, int64_t value);
 
 #ifdef __cplusplus

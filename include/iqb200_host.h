@@ -31,7 +31,8 @@ typedef struct iqh_desc {
   int64_t ovl_size[3];         /* ceil(overlap * tilesize), src/iqsim.jl:92 */
   int64_t ntiles[3];           /* src/iqsim.jl:103 */
   int64_t pad_size[3];         /* src/iqsim.jl:106 */
-  const double* ti;            /* prepared training image (NaN -> 0), FP64 copy used for pasting and cuts */
+  const double* ti;            /* prepared training image (NaN -> 0) in FP64: the values that are pasted and cut.  NULL = the
+                                  image IS FP32 (ti_f32 holds it exactly); the FP64 copy is then derived from ti_f32 */
   const float* ti_f32;         /* same image in FP32: what the device searches */
   const uint8_t* disabled;     /* distsize bytes or NULL (finddisabled, src/utils.jl:115-129) */
   int32_t nsoft;
@@ -50,7 +51,8 @@ typedef struct iqh_desc {
   int32_t batch;               /* realizations per iq_search_pick call (<= nreal); 0 = all */
   int32_t nthreads;            /* host threads for cut + paste; 0 = hardware concurrency */
   int32_t ngroups;             /* lockstep groups pipelined against the host cuts; 0 = auto */
-  int32_t cut_mode;            /* boundary cuts: 0 = auto (device when fewer than 6 host threads), 1 = host, 2 = device */
+  int32_t cut_mode;            /* host-staged boundary cuts: 0 = auto (iq_cut_batch on the device when fewer than 6 host
+                                  threads and the image is not integer-valued), 1 = host, 2 = device (FP64) */
   int32_t fft_mode;            /* -1 never, 0 auto crossover, 1 always: distance path selection */
   int32_t pipeline;            /* 0 = auto (device-resident whenever the simulation qualifies), 1 = host-staged (grids,
                                   cuts and paste on the host, one iq_search_pick per step), 2 = device-resident
@@ -115,6 +117,14 @@ int32_t iqh_dependency_levels(int32_t ndim, const int64_t* tile_size, const int6
 /* The boundary cut alone: keep-mask (1 = keep the already pasted voxel) for overlap slabs A (old) and
  * B (new) of size sz (ndim entries, column-major) cut along `dim`.  Restates graphcut(A, B, dim). */
 int32_t iqh_graphcut(const double* A, const double* B, int32_t ndim, const int64_t* sz, int32_t dim, uint8_t* keep);
+/* iqh_graphcut picks the arithmetic by the data: integer-valued slabs are cut in exact integer arithmetic (the FP64
+ * capacities of graphcut.jl:52 scaled to 128-bit integers; no rounding in the flow, hence the one "cannot reach the
+ * sink" set of those capacities whatever the max-flow algorithm), everything else in FP64.  On integer-valued
+ * (categorical) slabs the capacities are degenerate -- (Du+Dv)/eps next to O(1) terms, many equal-cost cuts -- and an
+ * FP64 max-flow, GraphsFlows' Boykov-Kolmogorov included, returns whichever cut its own rounding favours.
+ * iqh_graphcut_mode forces one or the other (exact != 0: IQ_ERR_INVALID when the capacities span more than 128 bits). */
+int32_t iqh_graphcut_mode(const double* A, const double* B, int32_t ndim, const int64_t* sz, int32_t dim, int32_t exact,
+                          uint8_t* keep);
 
 #ifdef __cplusplus
 }

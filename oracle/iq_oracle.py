@@ -42,6 +42,7 @@ __all__ = [
     "overlap_mask", "indicator", "event", "activation", "relaxation", "fastintersect",
     "taumodel", "julia_sum", "sample_weighted", "graphcut", "iqsim", "voxelreuse",
     "search_tile", "build_c", "graphcut_c", "fastdistance_c", "decision_gaps", "relaxation_thresholds",
+    "exact_capacities", "is_integer_valued",
 ]
 
 
@@ -498,14 +499,39 @@ def sample_weighted(u, probs):
 # --------------------------------------------------------------------------------------
 # graphcut (src/graphcut.jl:5-84; max-flow lives in GraphsFlows.jl 0.1, not vendored)
 # --------------------------------------------------------------------------------------
-def graphcut(A, B, dim):
+def exact_capacities(caps):
+    """The FP64 capacities as exact integers: every double is m * 2^e, so all of them are integers after scaling by
+    2^-emin.  A max-flow in integer arithmetic has no rounding at all, hence its 'can reach the sink' set is THE set of
+    the capacities the reference computes -- independent of the max-flow algorithm (see graphcut)."""
+    caps = np.asarray(caps, dtype=np.float64)
+    if caps.size == 0:
+        return []
+    m, e = np.frexp(caps)                      # caps = m * 2^e, 0.5 <= |m| < 1
+    mi = (m * 2.0 ** 53).astype(np.int64)      # exact 53-bit integers
+    ei = e.astype(np.int64) - 53
+    nz = mi != 0
+    emin = int(ei[nz].min()) if nz.any() else 0
+    return [int(a) << int(b - emin) if a else 0 for a, b in zip(mi.tolist(), ei.tolist())]
+
+
+def is_integer_valued(*arrays):
+    return all(bool(np.all(np.asarray(a) == np.rint(a))) for a in arrays)
+
+
+def graphcut(A, B, dim, exact=None):
     """Keep-mask M of the minimum boundary cut between overlap slabs A (already pasted) and
     B (new patch) along `dim` (0-based).  Capacities as in src/graphcut.jl:22-54; source =
     first slice along dim, sink = last slice (:56-70).  M = labels in {free, source tree}
     (:79-81) = complement of the sink tree at Boykov-Kolmogorov termination = complement of
     the set of voxels that can still reach the sink in the residual graph of a maximum
     flow -- a set that is the same for every maximum flow, so any exact max-flow algorithm
-    reproduces it (up to floating-point ties among equal-cost cuts).  Here: Dinic."""
+    reproduces it (up to floating-point ties among equal-cost cuts).  Here: Dinic.
+
+    exact: run the max-flow on the FP64 capacities as exact integers (no rounding in the flow arithmetic).  Integer-
+    valued (categorical) slabs make graphcut.jl:52 degenerate -- (Du+Dv)/eps next to O(1) terms, many equal-cost cuts --
+    and an FP64 max-flow then returns whichever of them its own rounding favours (GraphsFlows' Boykov-Kolmogorov included:
+    what a Julia run returns there is an accident of its augmentation order).  The exact result is the one well-defined
+    answer; default (None): exact iff A and B are integer-valued."""
     A = np.asarray(A, dtype=np.float64)
     B = np.asarray(B, dtype=np.float64)
     assert A.shape == B.shape, "arrays must have the same size for cut"
@@ -535,13 +561,16 @@ def graphcut(A, B, dim):
     caps = np.concatenate(caps) if caps else np.zeros(0)
     first = lin[tuple(slice(0, 1) if i == dim else slice(None) for i in range(N))].ravel()
     last = lin[tuple(slice(sz[dim] - 1, sz[dim]) if i == dim else slice(None) for i in range(N))].ravel()
-    can_reach_sink = _maxflow_sink_side(nvox, us, vs, caps, first, last)
+    if exact is None:
+        exact = is_integer_valued(A, B)
+    can_reach_sink = _maxflow_sink_side(nvox, us, vs, exact_capacities(caps) if exact else caps, first, last, exact)
     return (~can_reach_sink).reshape(sz, order="F")
 
 
-def _maxflow_sink_side(nvox, us, vs, caps, src_nodes, snk_nodes):
+def _maxflow_sink_side(nvox, us, vs, caps, src_nodes, snk_nodes, exact=False):
     """Dinic max-flow on the lattice (undirected capacities) with infinite terminal links;
-    returns the boolean vector 'this voxel can reach the sink in the residual graph'."""
+    returns the boolean vector 'this voxel can reach the sink in the residual graph'.
+    exact: `caps` are Python integers (arbitrary precision)."""
     s, t = nvox, nvox + 1
     n = nvox + 2
     head = [[] for _ in range(n)]
@@ -551,13 +580,15 @@ def _maxflow_sink_side(nvox, us, vs, caps, src_nodes, snk_nodes):
         head[u].append(len(to)); to.append(v); cap.append(c_uv)
         head[v].append(len(to)); to.append(u); cap.append(c_vu)
 
-    for u, v, c in zip(us.tolist(), vs.tolist(), caps.tolist()):
+    caps = caps if isinstance(caps, list) else caps.tolist()
+    for u, v, c in zip(us.tolist(), vs.tolist(), caps):
         add(u, v, c, c)
-    INF = float("inf")
+    INF = (sum(caps) + 1) if exact else float("inf")
+    zero = 0 if exact else 0.0
     for u in src_nodes.tolist():
-        add(s, u, INF, 0.0)
+        add(s, u, INF, zero)
     for v in snk_nodes.tolist():
-        add(v, t, INF, 0.0)
+        add(v, t, INF, zero)
 
     while True:
         level = [-1] * n
@@ -640,20 +671,27 @@ def _clib():
             build_c()
         _CLIB = ctypes.CDLL(path)
         _CLIB.iqo_graphcut.restype = ctypes.c_int
+        _CLIB.iqo_graphcut_exact.restype = ctypes.c_int
         _CLIB.iqo_fastdistance.restype = ctypes.c_int
     return _CLIB
 
 
-def graphcut_c(A, B, dim):
-    """graphcut(A, B, dim) (src/graphcut.jl:5-84) through the C restatement (Dinic in C)."""
+def graphcut_c(A, B, dim, exact=None):
+    """graphcut(A, B, dim) (src/graphcut.jl:5-84) through the C restatement (Dinic in C; exact = 128-bit integer
+    capacities, falling back to the arbitrary-precision Python routine when their dynamic range exceeds 128 bits)."""
     import ctypes
     A = np.asfortranarray(A, dtype=np.float64)
     B = np.asfortranarray(B, dtype=np.float64)
     assert A.shape == B.shape, "arrays must have the same size for cut"
+    if exact is None:
+        exact = is_integer_valued(A, B)
     sz = np.array(A.shape, dtype=np.int64)
     keep = np.zeros(A.shape, dtype=np.uint8, order="F")
-    rc = _clib().iqo_graphcut(A.ctypes.data_as(ctypes.c_void_p), B.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(A.ndim),
-                              sz.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(int(dim)), keep.ctypes.data_as(ctypes.c_void_p))
+    fn = _clib().iqo_graphcut_exact if exact else _clib().iqo_graphcut
+    rc = fn(A.ctypes.data_as(ctypes.c_void_p), B.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(A.ndim),
+            sz.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(int(dim)), keep.ctypes.data_as(ctypes.c_void_p))
+    if rc == -3 and exact:
+        return graphcut(A, B, dim, exact=True)
     if rc != 0:
         raise RuntimeError("iqo_graphcut failed: %d" % rc)
     return keep.astype(bool)

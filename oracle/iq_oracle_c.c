@@ -28,42 +28,11 @@
  * the sink in the residual graph of a maximum flow", which is the same set for every maximum flow.  Max-flow here:
  * Dinic (BFS levels + iterative blocking-flow DFS).
  * ------------------------------------------------------------------------------------------------------------- */
-typedef struct {
-  int n;        /* nodes incl. s, t */
-  int m;        /* arcs (2 per edge) */
-  int* head;    /* [n] first arc or -1 */
-  int* next;    /* [m] */
-  int* to;      /* [m] */
-  double* cap;  /* [m] residual */
-} Graph;
-
-static void add_edge(Graph* g, int u, int v, double cuv, double cvu) {
-  g->to[g->m] = v; g->cap[g->m] = cuv; g->next[g->m] = g->head[u]; g->head[u] = g->m++;
-  g->to[g->m] = u; g->cap[g->m] = cvu; g->next[g->m] = g->head[v]; g->head[v] = g->m++;
-}
-
-int iqo_graphcut(const double* A, const double* B, int ndim, const int64_t* sz64, int dim, uint8_t* keep) {
-  if (!A || !B || !sz64 || !keep || ndim < 1 || ndim > 3 || dim < 0 || dim >= ndim) return -1;
-  int sz[3] = {1, 1, 1};
-  for (int i = 0; i < ndim; ++i) sz[i] = (int)sz64[i];
-  const int nvox = sz[0] * sz[1] * sz[2];
+/* lattice capacities of graphcut.jl:22-54 in FP64, edge list (u, v, c) in the order d = 0, 1, 2 / column-major u */
+static int lattice_caps(const double* A, const double* B, int ndim, const int sz[3], int* eu, int* ev, double* ec) {
   const int stride[3] = {1, sz[0], sz[0] * sz[1]};
-  const int s = nvox, t = nvox + 1;
-  Graph g;
-  g.n = nvox + 2;
-  g.m = 0;
-  const int maxarcs = 2 * (3 * nvox + 2 * nvox);
-  g.head = (int*)malloc(sizeof(int) * g.n);
-  g.next = (int*)malloc(sizeof(int) * maxarcs);
-  g.to = (int*)malloc(sizeof(int) * maxarcs);
-  g.cap = (double*)malloc(sizeof(double) * maxarcs);
-  int* level = (int*)malloc(sizeof(int) * g.n);
-  int* it = (int*)malloc(sizeof(int) * g.n);
-  int* queue = (int*)malloc(sizeof(int) * g.n);
-  int* pathe = (int*)malloc(sizeof(int) * g.n);
-  if (!g.head || !g.next || !g.to || !g.cap || !level || !it || !queue || !pathe) return -2;
-  for (int i = 0; i < g.n; ++i) g.head[i] = -1;
   const double eps = 2.220446049250313e-16; /* eps(Float64) */
+  int ne = 0;
   for (int d = 0; d < ndim; ++d) {
     if (sz[d] < 2) continue;
     for (int z = 0; z < sz[2]; ++z)
@@ -80,82 +49,162 @@ int iqo_graphcut(const double* A, const double* B, int ndim, const int64_t* sz64
             gAv = fabs(A[w] - A[v]);
             gBv = fabs(B[w] - B[v]);
           }
-          const double cap = (Du + Dv) / (gAu + gAv + gBu + gBv + eps);
-          add_edge(&g, u, v, cap, cap);
+          eu[ne] = u; ev[ne] = v;
+          ec[ne] = (Du + Dv) / (gAu + gAv + gBu + gBv + eps);
+          ++ne;
         }
   }
-  for (int z = 0; z < sz[2]; ++z)
-    for (int y = 0; y < sz[1]; ++y)
-      for (int x = 0; x < sz[0]; ++x) {
-        const int c[3] = {x, y, z};
-        const int u = x + y * stride[1] + z * stride[2];
-        if (c[dim] == 0) add_edge(&g, s, u, INFINITY, 0.0);
-        if (c[dim] == sz[dim] - 1) add_edge(&g, u, t, INFINITY, 0.0);
-      }
-  for (;;) {
-    for (int i = 0; i < g.n; ++i) level[i] = -1;
-    int qh = 0, qt = 0;
-    level[s] = 0;
-    queue[qt++] = s;
-    while (qh < qt) {
-      const int u = queue[qh++];
-      for (int e = g.head[u]; e >= 0; e = g.next[e])
-        if (g.cap[e] > 0.0 && level[g.to[e]] < 0) {
-          level[g.to[e]] = level[u] + 1;
-          queue[qt++] = g.to[e];
-        }
-    }
-    if (level[t] < 0) break;
-    for (int i = 0; i < g.n; ++i) it[i] = g.head[i];
-    for (;;) { /* one augmenting path per round of the blocking flow */
-      int np = 0, u = s;
-      while (u != t) {
-        int adv = 0;
-        for (; it[u] >= 0; it[u] = g.next[it[u]]) {
-          const int e = it[u];
-          if (g.cap[e] > 0.0 && level[g.to[e]] == level[u] + 1) {
-            pathe[np++] = e;
-            u = g.to[e];
-            adv = 1;
-            break;
-          }
-        }
-        if (!adv) {
-          if (np == 0) break;
-          level[u] = -1; /* dead end */
-          const int e = pathe[--np];
-          u = g.to[e ^ 1];
-        }
-      }
-      if (u != t) break;
-      double f = INFINITY;
-      for (int i = 0; i < np; ++i)
-        if (g.cap[pathe[i]] < f) f = g.cap[pathe[i]];
-      for (int i = 0; i < np; ++i) {
-        g.cap[pathe[i]] -= f;
-        g.cap[pathe[i] ^ 1] += f;
-      }
-    }
+  return ne;
+}
+
+/* Dinic (BFS levels + iterative blocking-flow DFS) + reverse reachability from the sink, generic in the capacity type:
+ * double (what an FP64 max-flow code computes) or unsigned 128-bit integers (exact). */
+#define DEFINE_MAXFLOW(NAME, CAP_T)                                                                                   \
+  static int NAME(int nvox, int ne, const int* eu, const int* ev, const CAP_T* ec, CAP_T inf, int ndim,               \
+                  const int sz[3], int dim, uint8_t* keep) {                                                          \
+    const int stride[3] = {1, sz[0], sz[0] * sz[1]};                                                                  \
+    const int s = nvox, t = nvox + 1, n = nvox + 2;                                                                   \
+    const int maxarcs = 2 * (ne + 2 * nvox);                                                                          \
+    int* head = (int*)malloc(sizeof(int) * n);                                                                        \
+    int* next = (int*)malloc(sizeof(int) * maxarcs);                                                                  \
+    int* to = (int*)malloc(sizeof(int) * maxarcs);                                                                    \
+    CAP_T* cap = (CAP_T*)malloc(sizeof(CAP_T) * maxarcs);                                                             \
+    int* level = (int*)malloc(sizeof(int) * n);                                                                       \
+    int* it = (int*)malloc(sizeof(int) * n);                                                                          \
+    int* queue = (int*)malloc(sizeof(int) * n);                                                                       \
+    int* pathe = (int*)malloc(sizeof(int) * n);                                                                       \
+    char* reach = (char*)calloc((size_t)n, 1);                                                                        \
+    if (!head || !next || !to || !cap || !level || !it || !queue || !pathe || !reach) return -2;                      \
+    int m = 0;                                                                                                        \
+    for (int i = 0; i < n; ++i) head[i] = -1;                                                                         \
+    for (int i = 0; i < ne; ++i) {                                                                                    \
+      to[m] = ev[i]; cap[m] = ec[i]; next[m] = head[eu[i]]; head[eu[i]] = m++;                                        \
+      to[m] = eu[i]; cap[m] = ec[i]; next[m] = head[ev[i]]; head[ev[i]] = m++;                                        \
+    }                                                                                                                 \
+    (void)ndim;                                                                                                       \
+    for (int z = 0; z < sz[2]; ++z)                                                                                   \
+      for (int y = 0; y < sz[1]; ++y)                                                                                 \
+        for (int x = 0; x < sz[0]; ++x) {                                                                             \
+          const int c[3] = {x, y, z};                                                                                 \
+          const int u = x + y * stride[1] + z * stride[2];                                                            \
+          if (c[dim] == 0) {                                                                                          \
+            to[m] = u; cap[m] = inf; next[m] = head[s]; head[s] = m++;                                                \
+            to[m] = s; cap[m] = 0; next[m] = head[u]; head[u] = m++;                                                  \
+          }                                                                                                           \
+          if (c[dim] == sz[dim] - 1) {                                                                                \
+            to[m] = t; cap[m] = inf; next[m] = head[u]; head[u] = m++;                                                \
+            to[m] = u; cap[m] = 0; next[m] = head[t]; head[t] = m++;                                                  \
+          }                                                                                                           \
+        }                                                                                                             \
+    for (;;) {                                                                                                        \
+      for (int i = 0; i < n; ++i) level[i] = -1;                                                                      \
+      int qh = 0, qt = 0;                                                                                             \
+      level[s] = 0;                                                                                                   \
+      queue[qt++] = s;                                                                                                \
+      while (qh < qt) {                                                                                               \
+        const int u = queue[qh++];                                                                                    \
+        for (int e = head[u]; e >= 0; e = next[e])                                                                    \
+          if (cap[e] > 0 && level[to[e]] < 0) { level[to[e]] = level[u] + 1; queue[qt++] = to[e]; }                   \
+      }                                                                                                               \
+      if (level[t] < 0) break;                                                                                        \
+      for (int i = 0; i < n; ++i) it[i] = head[i];                                                                    \
+      for (;;) { /* one augmenting path per round of the blocking flow */                                            \
+        int np = 0, u = s;                                                                                            \
+        while (u != t) {                                                                                              \
+          int adv = 0;                                                                                                \
+          for (; it[u] >= 0; it[u] = next[it[u]]) {                                                                   \
+            const int e = it[u];                                                                                      \
+            if (cap[e] > 0 && level[to[e]] == level[u] + 1) { pathe[np++] = e; u = to[e]; adv = 1; break; }           \
+          }                                                                                                           \
+          if (!adv) {                                                                                                 \
+            if (np == 0) break;                                                                                       \
+            level[u] = -1; /* dead end */                                                                             \
+            const int e = pathe[--np];                                                                                \
+            u = to[e ^ 1];                                                                                            \
+          }                                                                                                           \
+        }                                                                                                             \
+        if (u != t) break;                                                                                            \
+        CAP_T f = inf;                                                                                                \
+        for (int i = 0; i < np; ++i)                                                                                  \
+          if (cap[pathe[i]] < f) f = cap[pathe[i]];                                                                   \
+        for (int i = 0; i < np; ++i) { cap[pathe[i]] -= f; cap[pathe[i] ^ 1] += f; }                                  \
+      }                                                                                                               \
+    }                                                                                                                 \
+    /* reverse reachability to t over arcs with residual capacity */                                                  \
+    int qh = 0, qt = 0;                                                                                               \
+    reach[t] = 1;                                                                                                     \
+    queue[qt++] = t;                                                                                                  \
+    while (qh < qt) {                                                                                                 \
+      const int v = queue[qh++];                                                                                      \
+      for (int e = head[v]; e >= 0; e = next[e]) {                                                                    \
+        const int u = to[e];                                                                                          \
+        if (!reach[u] && cap[e ^ 1] > 0) { reach[u] = 1; queue[qt++] = u; } /* arc u -> v is e^1 */                   \
+      }                                                                                                               \
+    }                                                                                                                 \
+    for (int i = 0; i < nvox; ++i) keep[i] = reach[i] ? 0 : 1;                                                        \
+    free(reach); free(head); free(next); free(to); free(cap); free(level); free(it); free(queue); free(pathe);        \
+    return 0;                                                                                                         \
   }
-  /* reverse reachability to t over arcs with residual capacity */
-  char* reach = (char*)calloc((size_t)g.n, 1);
-  if (!reach) return -2;
-  int qh = 0, qt = 0;
-  reach[t] = 1;
-  queue[qt++] = t;
-  while (qh < qt) {
-    const int v = queue[qh++];
-    for (int e = g.head[v]; e >= 0; e = g.next[e]) {
-      const int u = g.to[e];
-      if (!reach[u] && g.cap[e ^ 1] > 0.0) { /* arc u -> v is e^1 */
-        reach[u] = 1;
-        queue[qt++] = u;
-      }
+
+typedef unsigned __int128 u128;
+DEFINE_MAXFLOW(maxflow_f64, double)
+DEFINE_MAXFLOW(maxflow_u128, u128)
+
+static int graphcut_impl(const double* A, const double* B, int ndim, const int64_t* sz64, int dim, uint8_t* keep, int exact) {
+  if (!A || !B || !sz64 || !keep || ndim < 1 || ndim > 3 || dim < 0 || dim >= ndim) return -1;
+  int sz[3] = {1, 1, 1};
+  for (int i = 0; i < ndim; ++i) sz[i] = (int)sz64[i];
+  const int nvox = sz[0] * sz[1] * sz[2];
+  int* eu = (int*)malloc(sizeof(int) * 3 * (size_t)nvox);
+  int* ev = (int*)malloc(sizeof(int) * 3 * (size_t)nvox);
+  double* ec = (double*)malloc(sizeof(double) * 3 * (size_t)nvox);
+  if (!eu || !ev || !ec) return -2;
+  const int ne = lattice_caps(A, B, ndim, sz, eu, ev, ec);
+  int rc;
+  if (!exact) {
+    rc = maxflow_f64(nvox, ne, eu, ev, ec, INFINITY, ndim, sz, dim, keep);
+  } else {
+    /* every FP64 capacity is m * 2^e (m a 53-bit integer): scaled by 2^-emin they are all integers.  They must fit
+       128 bits together with the sum over all arcs (the "infinite" terminal capacity): 54 + (emax - emin) +
+       log2(arcs) <= 128, else -3 (the caller falls back to arbitrary precision). */
+    int emin = 1 << 30, emax = -(1 << 30);
+    for (int i = 0; i < ne; ++i) {
+      if (!(ec[i] > 0.0)) continue;
+      if (!isfinite(ec[i])) { free(eu); free(ev); free(ec); return -3; }
+      int ex;
+      frexp(ec[i], &ex);
+      if (ex - 53 < emin) emin = ex - 53;
+      if (ex - 53 > emax) emax = ex - 53;
     }
+    int sumbits = 1;
+    while ((1ll << sumbits) < (long long)ne + 2) ++sumbits;
+    if (emax >= emin && 54 + (emax - emin) + sumbits > 128) { free(eu); free(ev); free(ec); return -3; }
+    u128* ic = (u128*)malloc(sizeof(u128) * (size_t)(ne > 0 ? ne : 1));
+    if (!ic) return -2;
+    u128 total = 0;
+    for (int i = 0; i < ne; ++i) {
+      ic[i] = 0;
+      if (!(ec[i] > 0.0)) continue;
+      int ex;
+      const double fr = frexp(ec[i], &ex);
+      ic[i] = (u128)(uint64_t)ldexp(fr, 53) << (ex - 53 - emin);
+      total += ic[i];
+    }
+    rc = maxflow_u128(nvox, ne, eu, ev, ic, total + 1, ndim, sz, dim, keep);
+    free(ic);
   }
-  for (int i = 0; i < nvox; ++i) keep[i] = reach[i] ? 0 : 1;
-  free(reach); free(g.head); free(g.next); free(g.to); free(g.cap); free(level); free(it); free(queue); free(pathe);
-  return 0;
+  free(eu); free(ev); free(ec);
+  return rc;
+}
+
+int iqo_graphcut(const double* A, const double* B, int ndim, const int64_t* sz64, int dim, uint8_t* keep) {
+  return graphcut_impl(A, B, ndim, sz64, dim, keep, 0);
+}
+
+/* The same cut with the FP64 capacities taken as exact integers (no rounding in the flow arithmetic): the one
+ * well-defined answer on degenerate (integer-valued / categorical) slabs, see oracle/iq_oracle.py graphcut(exact=). */
+int iqo_graphcut_exact(const double* A, const double* B, int ndim, const int64_t* sz64, int dim, uint8_t* keep) {
+  return graphcut_impl(A, B, ndim, sz64, dim, keep, 1);
 }
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -63,6 +63,30 @@ def test_native_graphcut_equals_oracle(seed):
     assert np.array_equal(iqb200.graphcut(A, B, dim), O.graphcut(A, B, dim))
 
 
+def test_exact_cut_three_max_flow_codes_agree_on_categorical_slabs():
+    """Integer-valued slabs: capacities (Du+Dv)/eps ~ 1e16 next to O(1) ones and many equal-cost cuts -- an FP64 max-flow
+    returns whichever its rounding favours.  In exact integer arithmetic the answer is unique: the product's host
+    Boykov-Kolmogorov, the oracle's Python Dinic (arbitrary precision) and its C Dinic (128-bit) must coincide on every
+    slab; FP64 runs of different algorithms are allowed to differ (and do, on some)."""
+    r = np.random.default_rng(77)
+    fp64_differs = 0
+    for trial in range(40):
+        shape, dim = [((4, 20, 10), 0), ((20, 4, 10), 1), ((5, 30), 0), ((12, 12, 3), 2)][trial % 4]
+        ncat = [2, 3, 5, 9][(trial // 4) % 4]
+        A, B = r.integers(0, ncat, shape).astype(float), r.integers(0, ncat, shape).astype(float)
+        want = O.graphcut(A, B, dim, exact=True)
+        assert np.array_equal(iqb200.graphcut(A, B, dim), want)                 # default: exact on integer slabs
+        assert np.array_equal(iqb200.graphcut(A, B, dim, exact=True), want)
+        assert np.array_equal(O.graphcut_c(A, B, dim), want)
+        fp64_differs += not np.array_equal(iqb200.graphcut(A, B, dim, exact=False), O.graphcut(A, B, dim, exact=False))
+    # continuous slabs: exact and FP64 agree (unique minimum cut with a margin)
+    for trial in range(6):
+        A, B = r.standard_normal((4, 14, 6)), r.standard_normal((4, 14, 6))
+        assert np.array_equal(iqb200.graphcut(A, B, 0, exact=True), iqb200.graphcut(A, B, 0, exact=False))
+        assert np.array_equal(iqb200.graphcut(A, B, 0), O.graphcut_c(A, B, 0, exact=True))
+    print("FP64 max-flows (host BK vs Python Dinic) disagree on", fp64_differs, "of 40 categorical slabs")
+
+
 def test_native_graphcut_identical_slabs():
     A = np.ones((20, 20))
     C = iqb200.graphcut(A, A, 0)

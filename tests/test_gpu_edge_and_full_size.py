@@ -14,7 +14,7 @@ def test_tile_equal_to_training_image():
     """distsize = 1: a single patch position; every tile must be that patch."""
     ti = np.asfortranarray(np.random.default_rng(0).random((12, 9)).astype(np.float32))
     reals = iqb200.iqsim(ti, (12, 9), (30, 20), rng=np.random.default_rng(1), nreal=2)
-    want = O.iqsim(ti, (12, 9), (30, 20), rng=np.random.default_rng(1), nreal=2, cut_fn=iqb200.graphcut)
+    want = O.iqsim(ti, (12, 9), (30, 20), rng=np.random.default_rng(1), nreal=2, cut_fn=O.graphcut_c)
     for a, b in zip(reals, want):
         assert a.shape == (30, 20) and np.array_equal(a, b)
 
@@ -26,7 +26,7 @@ def test_ragged_grid_one_voxel_overlap_and_singleton_dim():
     ti = np.asfortranarray(r.integers(0, 3, (25, 14, 1)).astype(np.float64))
     kw = dict(overlap=(0.3, 0.1, 0.5), nreal=2, path="dilation")
     got = iqb200.iqsim(ti, (7, 5, 1), (33, 17, 1), rng=np.random.default_rng(3), **kw)
-    want = O.iqsim(ti, (7, 5, 1), (33, 17, 1), rng=np.random.default_rng(3), cut_fn=iqb200.graphcut, **kw)
+    want = O.iqsim(ti, (7, 5, 1), (33, 17, 1), rng=np.random.default_rng(3), cut_fn=O.graphcut_c, **kw)
     for a, b in zip(got, want):
         assert a.shape == (33, 17, 1) and np.array_equal(a, b)
 
@@ -46,7 +46,7 @@ def test_inactive_tiles_are_skipped_and_draw_no_uniform():
     hard = {(i, j): np.nan for i in range(0, 12) for j in range(0, 12)}
     hard[(20, 20)] = 1.0
     got = iqb200.iqsim(ti, (8, 8), hard=hard, overlap=(0.25, 0.25), rng=np.random.default_rng(5), nreal=2)
-    want = O.iqsim(ti, (8, 8), hard=hard, overlap=(0.25, 0.25), rng=np.random.default_rng(5), nreal=2, cut_fn=iqb200.graphcut)
+    want = O.iqsim(ti, (8, 8), hard=hard, overlap=(0.25, 0.25), rng=np.random.default_rng(5), nreal=2, cut_fn=O.graphcut_c)
     for a, b in zip(got, want):
         assert np.array_equal(a, b, equal_nan=True)
         assert np.isnan(a[:12, :12]).all() and a[20, 20] == 1.0
@@ -57,7 +57,7 @@ def test_more_realizations_than_batch_and_odd_counts():
     cfg = synth.config(1)
     for fft in (-1, 1):
         got = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=5, batch=2, fft=fft, rng=np.random.default_rng(6))
-        want = O.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=5, rng=np.random.default_rng(6), cut_fn=iqb200.graphcut)
+        want = O.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=5, rng=np.random.default_rng(6), cut_fn=O.graphcut_c)
         for a, b in zip(got, want):
             assert np.array_equal(a, b)
 

@@ -224,17 +224,16 @@ def test_fetch_tile():
 
 
 # ---- end-to-end: realizations bit-exact against the oracle on identical seeds -----------------------
-def run_both(cfg, seed, native_cut=False, **over):
-    """native_cut=True hands the product's host cut routine to the oracle so that the comparison isolates
-    the search: on categorical images the reference's capacities mix ~1e16 (division by eps) with O(1)
-    terms, equal-cost cuts abound and which one a max-flow code returns is decided by FP rounding (cut
-    parity on well-conditioned slabs is tested separately in tests/test_abi_cpu.py)."""
+def run_both(cfg, seed, **over):
+    """CUDA path vs the oracle with the ORACLE'S OWN boundary cut (C Dinic; exact integer arithmetic on integer-valued
+    slabs, where an FP64 max-flow's answer is an accident of its rounding -- the product uses exact cuts there too:
+    host Boykov-Kolmogorov on 128-bit integers / the u128 instantiation of the device push-relabel)."""
     kw = dict(cfg["kwargs"])
     kw.update(over)
     got, ex = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(seed), return_picks=True, **kw)
     trace = []
     want = O.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(seed), method="direct", trace=trace,
-                   cut_fn=iqb200.graphcut if native_cut else None, **kw)
+                   cut_fn=O.graphcut_c, **kw)
     return got, want, ex, trace
 
 
@@ -254,7 +253,7 @@ def test_iqsim_3d_categorical_hard_soft_bit_exact():
     aux = np.asfortranarray(np.round(synth.box_mean(ti, (3, 3, 3)) * 2) / 2)
     hard = {k: v for k, v in cfg["kwargs"]["hard"].items()}
     hard[(0, 0, 0)] = float("nan")
-    got, want, ex, trace = run_both(cfg, 7, native_cut=True, nreal=2, hard=hard, soft=[(aux, aux)], debug=True)
+    got, want, ex, trace = run_both(cfg, 7, nreal=2, hard=hard, soft=[(aux, aux)], debug=True)
     picks_ref = np.array([t["rind"] for t in trace]).reshape(2, -1)
     assert np.array_equal(ex["picks"], picks_ref)
     for a, b in zip(got[0], want[0]):
@@ -269,7 +268,7 @@ def test_iqsim_paths_bit_exact(path):
     r = np.random.default_rng(3)
     ti = np.asfortranarray(r.integers(0, 4, (36, 30)).astype(np.float64))
     cfg = dict(trainimg=ti, tilesize=(12, 10), kwargs=dict(path=path, nreal=3, overlap=(0.25, 0.3)))
-    got, want, ex, trace = run_both(cfg, 5, native_cut=True, simsize=(40, 33))
+    got, want, ex, trace = run_both(cfg, 5, simsize=(40, 33))
     for g, w in zip(got, want):
         assert g.dtype == np.float64 and np.array_equal(g, w)
 
@@ -351,6 +350,31 @@ def test_device_cut_equals_host_cut():
     assert iters[-1] == 0 and max(iters[:-2]) > 0  # last slab (12x60x40) exceeds shared memory -> host
     for (A, B, dim), k in list(zip(slabs, keeps))[:6]:
         assert np.array_equal(k, O.graphcut(A, B, dim))
+    for (A, B, dim), k in zip(slabs, keeps):
+        assert np.array_equal(k, O.graphcut_c(A, B, dim, exact=False))
+
+
+def test_device_exact_cut_equals_host_and_oracle_on_categorical_slabs():
+    """The u128 instantiation of the device push-relabel (option cut_exact): on integer-valued slabs the exact cut is
+    unique, so the device (push-relabel), the host (Boykov-Kolmogorov) and the oracle (Dinic) coincide -- every slab."""
+    r = np.random.default_rng(9)
+    slabs = []
+    for shape, dim in [((4, 20, 10), 0), ((20, 4, 10), 1), ((20, 20, 2), 2), ((5, 30), 0), ((30, 5), 1), ((3, 16, 8), 0)]:
+        for ncat in (2, 3, 4):
+            A = r.integers(0, ncat, shape).astype(np.float64)
+            B = r.integers(0, ncat, shape).astype(np.float64)
+            # realistic slabs: B agrees with A on most voxels (the search picked a matching patch)
+            same = r.random(shape) < 0.7
+            B[same] = A[same]
+            slabs.append((A, B, dim))
+    with api.SearchContext(np.zeros((16, 16), np.float32), (4, 4)) as ctx:
+        ctx.set_option("cut_exact", 1)
+        keeps, iters = ctx.cut_batch(slabs)
+    assert max(iters) > 0  # the device kernel ran
+    for (A, B, dim), k in zip(slabs, keeps):
+        want = O.graphcut_c(A, B, dim)   # exact (integer-valued)
+        assert np.array_equal(k, want), (A.shape, dim)
+        assert np.array_equal(iqb200.graphcut(A, B, dim), want)
 
 
 def test_iqsim_device_cut_equals_host_cut():

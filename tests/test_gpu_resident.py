@@ -63,20 +63,46 @@ def test_resident_config1_matches_oracle():
                            return_picks=True, nreal=2, **{k: v for k, v in cfg["kwargs"].items() if k != "nreal"})
     trace = []
     want = O.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(42), method="direct", trace=trace, nreal=2,
-                   cut_fn=iqb200.graphcut, **{k: v for k, v in cfg["kwargs"].items() if k != "nreal"})
+                   cut_fn=O.graphcut_c, **{k: v for k, v in cfg["kwargs"].items() if k != "nreal"})
     picks_ref = np.array([t["rind"] for t in trace]).reshape(2, -1)
     assert np.array_equal(ex["picks"], picks_ref)
     for g, w in zip(got, want):
         assert g.dtype == w.dtype and np.array_equal(g, w)
 
 
-def test_resident_auto_keeps_categorical_images_host_staged():
-    """pipeline="auto": integer-valued images stay on the host-staged pipeline (host Boykov-Kolmogorov cuts: their cut
-    capacities are degenerate and the cut depends on the max-flow algorithm's rounding)."""
+def test_categorical_images_run_resident_with_exact_cuts():
+    """pipeline="auto": integer-valued images go device-resident as well -- their boundary cuts run in exact integer
+    arithmetic on the device (u128 push-relabel), which has one well-defined answer, the same as the host's exact
+    Boykov-Kolmogorov (staged pipeline) and the oracle's exact Dinic."""
     cfg = synth.config(3, scale=0.4)
-    out, ex = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], nreal=1, hard=cfg["kwargs"]["hard"], pipeline="auto",
-                           rng=np.random.default_rng(0), return_stats=True)
-    assert ex["stats"]["resident"] == 0 and out[0].shape == cfg["trainimg"].shape
+    kw = dict(nreal=2, hard=cfg["kwargs"]["hard"])
+    a, ea, b, eb = both(cfg["trainimg"], cfg["tilesize"], 3, **kw)
+    same(a, ea, b, eb)
+    out, ex = iqb200.iqsim(cfg["trainimg"], cfg["tilesize"], pipeline="auto", rng=np.random.default_rng(3), return_stats=True,
+                           return_picks=True, **kw)
+    assert ex["stats"]["resident"] == 1
+    same(out, ex, b, eb)
+    trace = []
+    want = O.iqsim(cfg["trainimg"], cfg["tilesize"], rng=np.random.default_rng(3), method="direct", trace=trace,
+                   cut_fn=O.graphcut_c, **kw)
+    assert np.array_equal(ex["picks"], np.array([t["rind"] for t in trace]).reshape(2, -1))
+    for g, w in zip(out, want):
+        assert np.array_equal(g, w, equal_nan=True)
+
+
+def test_config3_full_size_resident_equals_staged_and_oracle():
+    """BASELINE config 3 at its full size (100 x 100 x 50 facies image, 20 x 20 x 10 tiles, 200 hard data): device-resident
+    == host-staged (2 realizations, picks and voxels), and realization 1 == the oracle end to end."""
+    cfg = synth.config(3)
+    ti, tile, hard = cfg["trainimg"], cfg["tilesize"], cfg["kwargs"]["hard"]
+    a, ea, b, eb = both(ti, tile, 31, nreal=2, hard=hard)
+    same(a, ea, b, eb)
+    trace = []
+    want = O.iqsim(ti, tile, rng=np.random.default_rng(31), method="c", trace=trace, cut_fn=O.graphcut_c, nreal=1, hard=hard)
+    assert np.array_equal(eb["picks"][0], np.array([t["rind"] for t in trace]))
+    assert np.array_equal(b[0], want[0], equal_nan=True)
+    for coord, val in hard.items():
+        assert b[0][coord] == np.float32(val)
 
 
 def _hard_from(field, n, seed):
