@@ -101,7 +101,7 @@ SYMBOLS = {
     "iq_sim_begin": (C.c_int32, [C.c_void_p, C.POINTER(IqSimDesc)]),
     "iq_sim_step": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32, C.c_int32]),
     "iq_sim_define_shape": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqSimSlab), C.c_int32, c_i32_p]),
-    "iq_sim_step_multi": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p, c_i32_p]),
+    "iq_sim_step_multi": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p, c_i32_p, C.c_int32]),
     "iq_sim_step_picked": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_i64_p]),
     "iq_sim_sync": (C.c_int32, [C.c_void_p, c_i64_p, c_i32_p]),
     "iq_sim_fetch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_i64_p, C.c_void_p]),

@@ -646,6 +646,7 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
     sp.nx = c->nx; sp.ny = c->ny; sp.nz = c->nz; sp.nxo = c->nxo; sp.nyo = c->nyo; sp.nzo = c->nzo;
     sp.npos = c->npos;
     sp.ptr = (const int*)(c->d_stage + off_ptr);
+    sp.ptr_stride = 1;
     sp.off = (const long long*)(c->d_stage + off_off);
     sp.val = (const float*)(c->d_stage + off_val);
     sp.disabled = c->d_disabled;
@@ -1236,6 +1237,7 @@ int32_t iq_distance(iq_ctx* c, int32_t which, const uint8_t* ovlmask, const iq_t
     sp.nx = c->nx; sp.ny = c->ny; sp.nz = c->nz; sp.nxo = c->nxo; sp.nyo = c->nyo; sp.nzo = c->nzo;
     sp.npos = c->npos;
     sp.ptr = (const int*)(c->d_stage + off_ptr);
+    sp.ptr_stride = 1;
     sp.off = (const long long*)(c->d_stage + off_off);
     sp.val = (const float*)(c->d_stage + off_val);
     sp.disabled = c->d_disabled;

@@ -332,7 +332,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   // one tile per launch (one auxiliary map per source is kept).  IQB200_JOBS overrides the job slots per launch.
   const int Rg = (R + ngroups - 1) / ngroups;
   int tiles_per_launch = 1;
-  if (S == 0) {
+  {
     int jobs_cap = 256;
     if (const char* ev = std::getenv("IQB200_JOBS")) jobs_cap = std::max(1, std::atoi(ev));
     tiles_per_launch = (int)std::max<long long>(1, std::min<long long>(jobs_cap / std::max(Rg, 1), G.ntile_total));
@@ -342,7 +342,8 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     auto p2 = [](int n) { double v = 1; while (v < n) v *= 2; return v; };
     const double fftws = 8.0 * p2(G.n[0]) * ((double)G.t[2] * G.t[1] + (G.n[2] > 1 ? (double)G.t[2] * p2(G.n[1]) + 2.0 * G.dist[2] * p2(G.n[1]) : 0.0) +
                                               (double)G.dist[2] * G.dist[1]) / 2.0;
-    const double per_job = npos * 4.0 * 6.0 + npos / 16.0 * 8.0 * 2.0 + fftws + 6.0 * 17.0 * G.tilevol + 2.0 * 32768 * 12.0;
+    const double per_job = npos * 4.0 * (6.0 + 2.0 * S) + npos / 16.0 * 8.0 * (2.0 + S) + fftws + 6.0 * 17.0 * G.tilevol +
+                           (2.0 + S) * 32768 * 12.0;
     size_t free_b = 0, total_b = 0;
     if (iq_device_free_memory(D->device, &free_b, &total_b) == IQ_OK) {
       const double budget = 0.6 * (double)free_b - (double)R * 8.0 * G.padvol;
@@ -446,6 +447,8 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
       const StepInfo &x = steps[(size_t)a], &y = steps[(size_t)b];
       if (x.level != y.level) return x.level < y.level;
+      if (x.hard_tile != y.hard_tile) return x.hard_tile < y.hard_tile;
+      if (x.host_pick != y.host_pick) return x.host_pick < y.host_pick;
       return x.key < y.key;
     });
   std::vector<float> zero_tile((size_t)G.tilevol, 0.f);
@@ -490,13 +493,14 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     const int64_t step = order[oi];
     const int* start = si.start;
     const int64_t st64[3] = {start[0], start[1], start[2]};
-    // the batch: the following steps of the same level (no hard / soft data); tiles without a pasted neighbour (key 0:
-    // the host samples them from the uniform distribution) only go with their like
+    // the batch: the following steps of the same level; tiles with hard data only go with their like (their primary
+    // source is the hard distance), and so do tiles without a pasted neighbour (key 0: sampled from the uniform
+    // distribution on the host, or -- with soft data -- searched on the host)
     size_t oe = oi + 1;
-    if (batching && !si.hard_tile && !si.host_pick && S == 0)
+    if (batching && !si.host_pick)
       while (oe < order.size() && (int)(oe - oi) < tiles_per_launch) {
         const StepInfo& o = steps[(size_t)order[oe]];
-        if (o.level != si.level || o.hard_tile || (o.key == 0) != (si.key == 0)) break;
+        if (o.level != si.level || o.hard_tile != si.hard_tile || o.host_pick || (o.key == 0) != (si.key == 0)) break;
         ++oe;
       }
     const int ntile = (int)(oe - oi);
@@ -536,6 +540,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
         key_shape(si.key);
         rc = iq_sim_step(g.ctx, step, st64, mask.data(), sl.data(), (int32_t)sl.size(), si.hard_tile ? 1 : 0);
       } else {
+        // (sort order inside a level: key, then hard flag -- see below)
         bsteps.resize((size_t)ntile);
         bstarts.resize((size_t)ntile * 3);
         bshapes.resize((size_t)ntile);
@@ -550,7 +555,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
           }
           bshapes[(size_t)k] = sid;
         }
-        if (rc == IQ_OK) rc = iq_sim_step_multi(g.ctx, ntile, bsteps.data(), bstarts.data(), bshapes.data());
+        if (rc == IQ_OK) rc = iq_sim_step_multi(g.ctx, ntile, bsteps.data(), bstarts.data(), bshapes.data(), si.hard_tile ? 1 : 0);
       }
       if (rc != IQ_OK) break;
       double dms = 0;

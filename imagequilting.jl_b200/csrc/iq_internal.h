@@ -46,7 +46,8 @@ struct SparseParams {
   const float* img;
   int nx, ny, nz, nxo, nyo, nzo;
   long long npos;
-  const int* ptr;              // [R+1] CSR row pointers
+  const int* ptr;              // row r holds entries ptr[r * ptr_stride] .. ptr[r * ptr_stride + 1] - 1
+  int ptr_stride;              // 1 = CSR row pointers [R+1]; 2 = one (begin, end) pair per row
   const long long* off;        // image offsets of the data voxels relative to the patch origin
   const float* val;            // data values
   const uint8_t* disabled;

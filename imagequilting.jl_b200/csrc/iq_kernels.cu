@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(256) k_dist_sparse(const SparseParams P) {
     const int y = (int)(q % P.nyo), z = (int)(q / P.nyo);
     const float* base = P.img + ((long long)z * P.ny + y) * P.nx + x;
     float sum = 0.f;
-    const int i0 = P.ptr[r], i1 = P.ptr[r + 1];
+    const int i0 = P.ptr[r * P.ptr_stride], i1 = P.ptr[r * P.ptr_stride + 1];
     for (int i = i0; i < i1; ++i) {
       const float diff = __ldg(base + P.off[i]) - __ldg(P.val + i);
       sum = fmaf(diff, diff, sum);

@@ -290,10 +290,12 @@ __global__ void __launch_bounds__(128) k_sim_sample(const iq::PickJob* __restric
 // whose k equals realization 0's only copies its thresholds (k_sim_copykth).  One block per realization, one thread
 // per source.
 __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* __restrict__ pick, int maxS,
-                              const unsigned* __restrict__ maxbits, int maxbits_stride, unsigned shared_mask, double tol,
+                              const unsigned* __restrict__ maxbits, int maxbits_stride, int maxbits_tile_stride, int R,
+                              unsigned shared_mask, double tol,
                               long long npatterns, long long npos, int round, int* __restrict__ pending,
                               unsigned long long* __restrict__ selbuf, unsigned selcap) {
-  const int r = blockIdx.x, s = threadIdx.x;
+  const int r = blockIdx.x, s = threadIdx.x;  // r = job; the jobs of one tile (r / R) share that tile's auxiliary maps
+  const int lead = (r / R) * R;               // first job of the tile: it runs the selection on the shared maps
   if (s >= maxS) return;
   if (round > 0 && pending[r] == 0) return;  // candidates found: its jobs stay finished
   if (round > 0 && s == 0) return;           // primary threshold already known
@@ -304,7 +306,9 @@ __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* 
   for (int i = 0; i < 256; ++i) J.hist[i] = 0;
   if (s == 0 && round == 0) pending[r] = 1;
   if (s >= P.nsrc) return;
-  const bool allzero = maxbits[(long long)r * maxbits_stride] == 0u, allzero0 = maxbits[0] == 0u;
+  const long long tileoff = (long long)(r / R) * maxbits_tile_stride;
+  const bool allzero = maxbits[(long long)r * maxbits_stride + tileoff] == 0u;
+  const bool allzero0 = maxbits[(long long)lead * maxbits_stride + tileoff] == 0u;
   const long long dbsize = allzero ? npatterns : (long long)ceil(__dmul_rn(tol, (double)npatterns));
   double frac = __dmul_rn(0.1, __ddiv_rn((double)dbsize, (double)npatterns));
   for (int j = 0; j < round; ++j) frac = fmin(__dadd_rn(frac, 0.1), 1.0);  // relaxation.jl:35, once per empty round
@@ -316,18 +320,19 @@ __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* 
   // map shared by all realizations (bit s of shared_mask) and the same k as realization 0, which runs its selection
   // in this round: copy afterwards.  (k depends on the all-zero flag and the round only; pending[] is not written
   // during rounds > 0.)
-  const bool same_as_first = ((shared_mask >> s) & 1u) && r > 0 && allzero == allzero0 && (round == 0 || pending[0] != 0);
+  const bool same_as_first = ((shared_mask >> s) & 1u) && r != lead && allzero == allzero0 && (round == 0 || pending[lead] != 0);
   J.active = same_as_first ? 0 : 1;
   J.ticket = same_as_first ? 0xffffffffu : 0u;  // marker read by k_sim_copykth
 }
 
 // Thresholds of the shared auxiliary maps for the realizations that did not run their own selection.
-__global__ void k_sim_copykth(iq::SelJob* __restrict__ jobs, int maxS) {
+__global__ void k_sim_copykth(iq::SelJob* __restrict__ jobs, int maxS, int R) {
   const int r = blockIdx.x, s = threadIdx.x;
-  if (r == 0 || s >= maxS) return;
+  const int lead = (r / R) * R;
+  if (r == lead || s >= maxS) return;
   iq::SelJob& J = jobs[(long long)r * maxS + s];
   if (J.ticket != 0xffffffffu) return;
-  J.kth = jobs[s].kth;
+  J.kth = jobs[(long long)lead * maxS + s].kth;
   J.ticket = 0u;
 }
 
@@ -343,13 +348,20 @@ __global__ void k_sim_relax_check(const iq::PickJob* __restrict__ pick, int R, i
 // Hard data of the step's tile (indicator! / event!, utils.jl:18-36) as the sparse list k_dist_sparse consumes, in
 // ascending tile offset (the order the host driver builds it in: the FP32 accumulation order of the distance).
 __global__ void __launch_bounds__(256) k_sim_hardlist(const uint8_t* __restrict__ has, const float* __restrict__ val, int p0,
-                                                      int p1, int sx, int sy, int sz, int tx, int ty, int tz, int nx, int ny,
-                                                      int* __restrict__ ptr, long long* __restrict__ off,
+                                                      int p1, const TileInfo* __restrict__ tiles, int tx, int ty, int tz,
+                                                      int nx, int ny, int* __restrict__ ptr, long long* __restrict__ off,
                                                       float* __restrict__ list) {
   __shared__ unsigned s_w[8];
   __shared__ unsigned s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tv = tx * ty * tz;
+  // one CTA per tile of the launch: its list occupies the segment [tile * tv, tile * tv + count), ptr holds the pair
+  const TileInfo T = tiles[blockIdx.x];
+  const int sx = T.sx, sy = T.sy, sz = T.sz;
+  off += (long long)blockIdx.x * tv;
+  list += (long long)blockIdx.x * tv;
+  ptr += 2 * blockIdx.x;
+  const int seg0 = blockIdx.x * tv;
   if (tid == 0) s_base = 0;
   __syncthreads();
   for (int q0 = 0; q0 < tv; q0 += 256) {
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(256) k_sim_hardlist(const uint8_t* __restrict_
     if (tid == 0) s_base = base + all;
     __syncthreads();
   }
-  if (tid == 0) { ptr[0] = 0; ptr[1] = (int)s_base; }
+  if (tid == 0) { ptr[0] = seg0; ptr[1] = seg0 + (int)s_base; }
 }
 
 __global__ void k_sim_store_picks(const long long* __restrict__ picked, long long* __restrict__ picks, long long npath,
@@ -625,12 +637,13 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     CK(iq::dmalloc((void**)&s->d_aux_pad[i], (size_t)s->padvol * sizeof(float)));
     CK(cudaMemcpyAsync(s->d_aux_pad[i], d->aux[i], (size_t)s->padvol * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
+  const size_t T = J / R;  // tiles one launch may carry: the auxiliary (soft / hard) maps belong to a tile, one set per tile
   if (s->S > 0) {
-    CK(iq::dmalloc((void**)&s->d_soft_tmpl, (size_t)c->tilevol * sizeof(float)));
-    CK(iq::dmalloc((void**)&s->d_soft_b2, sizeof(double)));
-    CK(iq::dmalloc((void**)&s->d_soft_plane, (size_t)c->tz * sizeof(double)));
-    CK(iq::dmalloc((void**)&s->d_soft_ticket, sizeof(unsigned)));
-    CK(cudaMemsetAsync(s->d_soft_ticket, 0, sizeof(unsigned), c->stream));
+    CK(iq::dmalloc((void**)&s->d_soft_tmpl, T * c->tilevol * sizeof(float)));
+    CK(iq::dmalloc((void**)&s->d_soft_b2, T * sizeof(double)));
+    CK(iq::dmalloc((void**)&s->d_soft_plane, T * c->tz * sizeof(double)));
+    CK(iq::dmalloc((void**)&s->d_soft_ticket, T * sizeof(unsigned)));
+    CK(cudaMemsetAsync(s->d_soft_ticket, 0, T * sizeof(unsigned), c->stream));
   }
   CK(iq::dmalloc((void**)&s->d_pickjobs, J * sizeof(iq::PickJob)));
   CK(iq::dmalloc((void**)&s->d_pending, J * sizeof(int)));
@@ -642,7 +655,7 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     std::memset(&J, 0, sizeof J);
     J.mode = s->S > 0 ? 1 : 0;
     J.nsrc = 1 + s->S;
-    for (int i = 0; i < s->S; ++i) J.src[1 + i] = c->d_Dsoft[i];  // one soft map per step serves every realization
+    for (int i = 0; i < s->S; ++i) J.src[1 + i] = c->d_Dsoft[i] + (size_t)(r / s->R) * c->npos;  // one soft map per tile serves every realization
     J.pending = s->S > 0 ? s->d_pending + r : nullptr;
     J.src[0] = c->d_Dovl + (size_t)r * c->npos;
     J.sel = c->d_sel + (size_t)r * c->max_src;
@@ -663,31 +676,31 @@ int32_t iq_sim_begin(iq_ctx* c, const iq_sim_desc* d) {
     CK(iq::dmalloc((void**)&s->d_hard_val, (size_t)s->padvol * sizeof(float)));
     CK(cudaMemcpyAsync(s->d_hard_has, d->hard_has, (size_t)s->padvol, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(s->d_hard_val, d->hard_val, (size_t)s->padvol * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CK(iq::dmalloc((void**)&s->d_hard_ptr, 2 * sizeof(int)));
-    CK(iq::dmalloc((void**)&s->d_hard_off, (size_t)c->tilevol * sizeof(long long)));
-    CK(iq::dmalloc((void**)&s->d_hard_list, (size_t)c->tilevol * sizeof(float)));
-    CK(iq::dmalloc((void**)&s->d_pickjobs_hard, R * sizeof(iq::PickJob)));
-    if (!s->d_pending) CK(iq::dmalloc((void**)&s->d_pending, R * sizeof(int)));
-    // hard tiles: sources = [hard distance (one map for all realizations), overlap distance, soft maps...]
-    for (int r = 0; r < s->R; ++r) {
+    CK(iq::dmalloc((void**)&s->d_hard_ptr, 2 * T * sizeof(int)));
+    CK(iq::dmalloc((void**)&s->d_hard_off, T * c->tilevol * sizeof(long long)));
+    CK(iq::dmalloc((void**)&s->d_hard_list, T * c->tilevol * sizeof(float)));
+    CK(iq::dmalloc((void**)&s->d_pickjobs_hard, J * sizeof(iq::PickJob)));
+    // hard tiles: sources = [hard distance (one map per tile, for all realizations), overlap distance, soft maps...]
+    for (int r = 0; r < s->J; ++r) {
+      const size_t tl = (size_t)(r / s->R);
       iq::PickJob& J = c->h_pick[r];
       std::memset(&J, 0, sizeof J);
       J.mode = 1;
       J.nsrc = 2 + s->S;
-      J.src[0] = c->d_Dhard;
+      J.src[0] = c->d_Dhard + tl * c->npos;
       J.src[1] = c->d_Dovl + (size_t)r * c->npos;
-      for (int i = 0; i < s->S; ++i) J.src[2 + i] = c->d_Dsoft[i];
+      for (int i = 0; i < s->S; ++i) J.src[2 + i] = c->d_Dsoft[i] + tl * c->npos;
       J.pending = s->d_pending + r;
       J.sel = c->d_sel + (size_t)r * c->max_src;
       J.tol = s->tol;
-      J.minbits = c->d_minmax + (size_t)(1 * 2 + 0) * c->max_batch;
+      J.minbits = c->d_minmax + (size_t)(1 * 2 + 0) * c->max_batch + tl;
       J.blockcount = c->d_blockcount + (size_t)r * iq::pick_nblk(c->npos);
       J.total = c->d_total + r;
       J.cand_idx = c->d_cand_idx + (size_t)r * c->npos;
       J.cand_val = c->d_cand_val + (size_t)r * c->max_src * c->npos;
       J.cap = c->npos;
     }
-    CK(cudaMemcpyAsync(s->d_pickjobs_hard, c->h_pick, R * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(s->d_pickjobs_hard, c->h_pick, J * sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
   }
   CK(cudaEventCreate(&s->ev_begin));
   CK(cudaEventCreate(&s->ev_end));
@@ -763,8 +776,6 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
   const int R = s->R;
   if (ntile < 1 || (long long)ntile * R > s->J)
     return fail(IQ_ERR_INVALID, "iq_sim_step: %d tiles x %d realizations exceed the %d job slots (max_batch) of the context", ntile, R, s->J);
-  if ((hardt || s->S > 0) && ntile != 1)
-    return fail(IQ_ERR_INVALID, "iq_sim_step_multi: tiles with hard data / contexts with soft data take one tile per step");
   if (s->tile_cursor + (size_t)ntile > (size_t)std::max<int64_t>(s->npath, 1))
     return fail(IQ_ERR_STATE, "iq_sim_step: more tiles launched than path steps declared at iq_sim_begin");
   CK(cudaSetDevice(c->device));
@@ -800,7 +811,6 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
   CK(cudaMemcpyAsync(s->d_tiles + s->tile_cursor, ht, (size_t)ntile * sizeof(TileInfo), cudaMemcpyHostToDevice, c->stream));
   const size_t cursor0 = s->tile_cursor;
   s->tile_cursor += (size_t)ntile;
-  const int st3[3] = {ht[0].sx, ht[0].sy, ht[0].sz};  // single-tile paths (hard / soft data)
   const int NJ = ntile * R;  // jobs of this launch
   s->synced = false;
   MaskEntry* e = s->shapes[(size_t)shapes[0]].e;
@@ -889,38 +899,39 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
         k0 = k1;
       }
     }
-    // hard-data distance (iqsim.jl:210-219): the data are the same for every realization -> one map per step
+    // hard-data distance (iqsim.jl:210-219): the data are the same for every realization -> one map per tile
     if (hardt) {
-      k_sim_hardlist<<<1, 256, 0, c->stream>>>(s->d_hard_has, s->d_hard_val, s->pad[0], s->pad[1], st3[0], st3[1], st3[2], c->tx,
-                                               c->ty, c->tz, c->nx, c->ny, s->d_hard_ptr, s->d_hard_off, s->d_hard_list);
+      k_sim_hardlist<<<ntile, 256, 0, c->stream>>>(s->d_hard_has, s->d_hard_val, s->pad[0], s->pad[1], dt, c->tx,
+                                                   c->ty, c->tz, c->nx, c->ny, s->d_hard_ptr, s->d_hard_off, s->d_hard_list);
       CK(cudaGetLastError());
       iq::SparseParams sp{};
       sp.img = c->d_ti;
       sp.nx = c->nx; sp.ny = c->ny; sp.nz = c->nz; sp.nxo = c->nxo; sp.nyo = c->nyo; sp.nzo = c->nzo;
       sp.npos = c->npos;
       sp.ptr = s->d_hard_ptr;
+      sp.ptr_stride = 2;
       sp.off = s->d_hard_off;
       sp.val = s->d_hard_list;
       sp.disabled = c->d_disabled;
       sp.out = c->d_Dhard;
       sp.minbits = c->d_minmax + (size_t)(1 * 2 + 0) * c->max_batch;
       sp.maxbits = c->d_minmax + (size_t)(1 * 2 + 1) * c->max_batch;
-      sp.R = 1;
+      sp.R = ntile;
       CK(iq::launch_dist_sparse(sp, c->stream));
       c->launches += 2;
     }
-    // soft-data distances (iqsim.jl:222-227): the auxiliary tile is the same for every realization -> one map per step
+    // soft-data distances (iqsim.jl:222-227): the auxiliary tile is the same for every realization -> one map per tile
     for (int si = 0; si < s->S; ++si) {
-      k_sim_templates<float><<<dim3((unsigned)c->tz, 1u), 256, 0, c->stream>>>(
+      k_sim_templates<float><<<dim3((unsigned)c->tz, (unsigned)ntile), 256, 0, c->stream>>>(
           s->d_aux_pad[si], 0, s->pad[0], s->pad[1], dt, 1, nullptr, c->full_mask->d_mask, nullptr, c->tx, c->ty, c->tz,
           s->d_soft_tmpl, s->d_soft_plane, s->d_soft_b2, s->d_soft_ticket);
       CK(cudaGetLastError());
       c->launches++;
       bool sdone = false;
-      if (want_fft(c, c->full_mask, 1)) {
+      if (want_fft(c, c->full_mask, ntile)) {
         rc = ensure_fft(c, si);
         if (rc == IQ_OK) {
-          rc = launch_fft(c, c->full_mask, si, s->d_soft_tmpl, s->d_soft_b2, 1, false, c->d_Dsoft[si], 2 + si);
+          rc = launch_fft(c, c->full_mask, si, s->d_soft_tmpl, s->d_soft_b2, ntile, false, c->d_Dsoft[si], 2 + si);
           if (rc) return rc;
           sdone = true;
         } else if (!(rc == IQ_ERR_STATE && c->fft_failed)) {
@@ -928,7 +939,7 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
         }
       }
       if (!sdone) {
-        rc = direct(c->full_mask, si, s->d_soft_tmpl, s->d_soft_b2, 1, c->d_Dsoft[si], 2 + si, 0);
+        rc = direct(c->full_mask, si, s->d_soft_tmpl, s->d_soft_b2, ntile, c->d_Dsoft[si], 2 + si, 0);
         if (rc) return rc;
       }
     }
@@ -945,33 +956,33 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
       unsigned shared_mask = 0;
       for (int i = 0; i < nsrc; ++i)
         if (hardt ? (i != 1) : (i != 0)) shared_mask |= 1u << i;
+      // all-zero test of the primary map (relaxation.jl:11): per job (overlap map) or per tile (hard map)
       const unsigned* pmax = hardt ? c->d_minmax + (size_t)(1 * 2 + 1) * c->max_batch : c->d_minmax + (size_t)c->max_batch;
-      const int pmax_stride = hardt ? 0 : 1;
+      const int pmax_stride = hardt ? 0 : 1, pmax_tile_stride = hardt ? 1 : 0;
       // relaxation rounds on the device: kRelaxRounds rounds are enqueued unconditionally, the kernels of a round
       // return at once for realizations that already have candidates; a realization still empty after the last
       // round raises the status word (the caller then reruns host-staged, where the round count is unbounded)
       // (5 rounds normally, frac up to 0.4 + 0.1 tol; tiles with hard data or an empty overlap mask often need many -- an
       // all-zero overlap map selects an index prefix -- and get all 11, after which frac = 1 guarantees a non-empty
       // intersection)
-      const int kRelaxRounds = (hardt || e->nnz == 0) ? 11 : 5;
-      const unsigned gR = (unsigned)((R + 127) / 128);
+      const int kRelaxRounds = (hardt || nempty > 0) ? 11 : 5;
       for (int round = 0; round < kRelaxRounds; ++round) {
-        k_sim_seljobs<<<R, 32, 0, c->stream>>>(c->d_sel, pj, c->max_src, pmax, pmax_stride, shared_mask, s->tol, c->nenabled,
-                                              c->npos, round, s->d_pending, c->d_selbuf, c->sel_cap);
+        k_sim_seljobs<<<NJ, 32, 0, c->stream>>>(c->d_sel, pj, c->max_src, pmax, pmax_stride, pmax_tile_stride, R, shared_mask,
+                                               s->tol, c->nenabled, c->npos, round, s->d_pending, c->d_selbuf, c->sel_cap);
         CK(cudaGetLastError());
         {
           int nl = 0;
-          CK(iq::launch_select_all(c->d_sel, R * c->max_src, c->npos, c->d_shifts, c->nshift, c->stream, &nl));
+          CK(iq::launch_select_all(c->d_sel, NJ * c->max_src, c->npos, c->d_shifts, c->nshift, c->stream, &nl));
           c->launches += nl;
         }
-        k_sim_copykth<<<R, 32, 0, c->stream>>>(c->d_sel, c->max_src);
+        k_sim_copykth<<<NJ, 32, 0, c->stream>>>(c->d_sel, c->max_src, R);
         CK(cudaGetLastError());
-        CK(iq::launch_pick_count(pj, R, c->npos, c->stream));
-        k_sim_relax_check<<<gR, 128, 0, c->stream>>>(pj, R, s->d_pending, round == kRelaxRounds - 1 ? 1 : 0, s->d_status);
+        CK(iq::launch_pick_count(pj, NJ, c->npos, c->stream));
+        k_sim_relax_check<<<gJ, 128, 0, c->stream>>>(pj, NJ, s->d_pending, round == kRelaxRounds - 1 ? 1 : 0, s->d_status);
         CK(cudaGetLastError());
         c->launches += 4;
       }
-      CK(iq::launch_pick_write(pj, R, c->npos, c->stream));
+      CK(iq::launch_pick_write(pj, NJ, c->npos, c->stream));
       c->launches += 1;
     }
     CK(iq::launch_tau(pj, NJ, c->max_src, c->d_rank, c->d_colsum, c->d_prob, c->stream));
@@ -1027,10 +1038,12 @@ int32_t iq_sim_step(iq_ctx* c, int64_t step, const int64_t* start, const uint8_t
   return sim_step_impl(c, 1, &step, st, &slot, hard_tile);
 }
 
-int32_t iq_sim_step_multi(iq_ctx* c, int32_t ntile, const int64_t* steps, const int64_t* starts, const int32_t* shapes) {
+int32_t iq_sim_step_multi(iq_ctx* c, int32_t ntile, const int64_t* steps, const int64_t* starts, const int32_t* shapes,
+                          int32_t hard_tiles) {
   if (!c || !c->sim) return fail(IQ_ERR_STATE, "iq_sim_step_multi: no simulation open on this context");
   if (!steps || !starts || !shapes) return fail(IQ_ERR_INVALID, "iq_sim_step_multi: NULL argument");
-  return sim_step_impl(c, ntile, steps, starts, shapes, 0);
+  if (hard_tiles && !c->sim->d_hard_has) return fail(IQ_ERR_INVALID, "iq_sim_step_multi: hard_tiles on a simulation opened without hard data");
+  return sim_step_impl(c, ntile, steps, starts, shapes, hard_tiles);
 }
 
 int32_t iq_sim_step_picked(iq_ctx* c, int64_t step, const int64_t* start, const int64_t* picks) {

@@ -220,10 +220,12 @@ int32_t iq_sim_step(iq_ctx* ctx, int64_t step, const int64_t* start, const uint8
  * its id; iq_sim_step_multi launches ntile tiles whose windows do not intersect (checked): tile k has path step
  * steps[k], origin starts[3k..3k+2] and overlap shape shapes[k].  Shapes may be mixed freely, except that tiles without
  * any pasted neighbour (empty mask) cannot share a launch with others.  ntile * nreal must not exceed the max_batch of the
- * context.  Not for tiles with hard data nor for contexts with soft data (their auxiliary distance maps belong to one
- * tile): use iq_sim_step for those. */
+ * context.  hard_tiles != 0: EVERY tile of the launch contains hard data (hard distance primary, src/iqsim.jl:230-231);
+ * tiles with and without data go in separate launches.  Soft data: one auxiliary distance map per tile and source is
+ * computed and shared by the realizations of that tile. */
 int32_t iq_sim_define_shape(iq_ctx* ctx, const uint8_t* ovlmask, const iq_sim_slab* slabs, int32_t nslab, int32_t* shape);
-int32_t iq_sim_step_multi(iq_ctx* ctx, int32_t ntile, const int64_t* steps, const int64_t* starts, const int32_t* shapes);
+int32_t iq_sim_step_multi(iq_ctx* ctx, int32_t ntile, const int64_t* steps, const int64_t* starts, const int32_t* shapes,
+                          int32_t hard_tiles);
 /* A step whose patterns the caller chose itself (picks[r] = 0-based linear index of the pattern of realization r):
  * the whole tile is pasted (no pasted neighbour, hence no cut).  Used for empty-mask steps of soft-data simulations. */
 int32_t iq_sim_step_picked(iq_ctx* ctx, int64_t step, const int64_t* start, const int64_t* picks);

@@ -199,7 +199,7 @@ def _run_jobs(monkeypatch, jobs, ti, tile, seed, **kw):
     return iqb200.iqsim(ti, tile, rng=np.random.default_rng(seed), pipeline="resident", return_picks=True, return_stats=True, **kw)
 
 
-@pytest.mark.parametrize("case", ["2d-raster", "3d-raster", "3d-random", "2d-dilation", "3d-fft"])
+@pytest.mark.parametrize("case", ["2d-raster", "3d-raster", "3d-random", "2d-dilation", "3d-fft", "3d-soft", "3d-hard-soft"])
 def test_level_batching_equals_one_tile_per_launch(monkeypatch, case):
     """The launch schedule (levels of mutually independent tiles, batched) must not change a single bit: compare with
     one tile per launch (IQB200_JOBS = nreal, the lockstep schedule of round 1) and with the host-staged pipeline."""
@@ -215,9 +215,19 @@ def test_level_batching_equals_one_tile_per_launch(monkeypatch, case):
     elif case == "2d-dilation":
         ti, tile = synth.gaussian_field((160, 150), (7, 7), 44).astype(np.float64), (24, 20)
         kw.update(path="dilation", overlap=(0.25, 0.3), debug=True)
-    else:
+    elif case == "3d-fft":
         ti, tile = synth.gaussian_field((128, 128, 24), (8, 8, 3), 45), (24, 24, 8)
         kw.update(fft=1, nreal=2)
+    else:
+        # soft data (one auxiliary map per tile of the launch, relaxation rounds on the device) and hard data (tiles
+        # with data: their own launches, hard distance primary) batched by dependency level as well
+        ti, tile = synth.gaussian_field((60, 52, 24), (6, 6, 3), 47), (16, 12, 8)
+        other = synth.gaussian_field((60, 52, 24), (6, 6, 3), 48)
+        auxti = np.asfortranarray(synth.box_mean(ti, (5, 5, 3)).astype(np.float32))
+        aux = np.asfortranarray(synth.box_mean(other, (5, 5, 3)).astype(np.float32))
+        kw.update(overlap=(0.25, 0.25, 0.25), soft=[(aux, auxti)])
+        if case == "3d-hard-soft":
+            kw.update(hard=_hard_from(other, 40, 2))
     a, ea = _run_jobs(monkeypatch, None, ti, tile, 5, **kw)
     b, eb = _run_jobs(monkeypatch, kw["nreal"], ti, tile, 5, **kw)
     assert ea["stats"]["resident"] == 1 and eb["stats"]["resident"] == 1
