@@ -334,16 +334,26 @@ bool all_integer(const float* v, long long n) {
   return true;
 }
 
-// Estimated cost model for the direct / FFT choice (seconds); constants measured on B200.
+// Direct kernel or FFT path?  Cost model (milliseconds) fitted to the measured sweep profiles/r02_crossover.csv
+// (scripts/crossover_sweep.py on one B200: 8 image / tile geometries x 3 masks x R = 1, 8, 64; CUDA-event times of the
+// distance kernels alone).  The model picks the measured winner in 70 of the 72 cases; the two misses are 2-D searches
+// of < 0.06 ms where both paths are within launch latency of each other (regret 0.04 ms over the whole sweep).
+//   direct: 16 us + nnz * npos * R / eff,  eff = 30 TFMA/s * nnz / (nnz + n0) (n0 = 1500 voxels in 3-D, 300 in 2-D: small
+//           masks amortise the staging of the image brick badly), x 0.63 / 0.8 for R = 1 / 2-3 (fewer templates per pass);
+//   FFT:    24 us + pairs * Nx * Ny * nz * 11 ps in 3-D (x, y padded to powers of two; z direct);
+//           24 us + pairs * (4.2 us + Nx * Ny * 17 ps) in 2-D (the fused y pass walks the pairs inside a CTA).
 bool want_fft(const iq_ctx* c, const MaskEntry* e, int R) {
   if (c->fft_mode < 0 || c->fft_failed || e->nnz == 0) return false;
   if (c->ny < 2 || c->nx < 2) return false;
   if (c->fft_mode > 0) return true;
-  const double direct = (double)e->nnz * (double)c->npos * R / (0.62 * 36.2e12) + 6e-6;
+  const bool three_d = c->nz > 1;
+  const double nnz = (double)e->nnz;
+  const double eff = 30e12 * nnz / (nnz + (three_d ? 1500.0 : 300.0)) * (R >= 4 ? 1.0 : (R >= 2 ? 0.8 : 0.63));
+  const double direct = 0.016 + nnz * (double)c->npos * R / eff * 1e3;
   auto p2 = [](int n) { double v = 1; while (v < n) v *= 2; return v; };
-  const double vol = p2(c->nx) * p2(c->ny) * (c->nz > 1 ? p2(c->nz) : 1.0);
+  const double plane = p2(c->nx) * p2(c->ny);
   const double pairs = (R + 1) / 2;
-  const double fft = pairs * vol * 8.0 * 5.0 / 2.2e12 + 30e-6;  // ~5 volume sweeps per pair at ~2.2 TB/s
+  const double fft = three_d ? 0.024 + pairs * plane * c->nz * 1.1e-8 : 0.024 + pairs * (0.0042 + plane * 1.7e-8);
   return fft < direct;
 }
 

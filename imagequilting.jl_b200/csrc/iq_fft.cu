@@ -358,11 +358,23 @@ __global__ void __launch_bounds__(kThreads, 5) k_fft_strided(const StridedArgs A
     __syncthreads();  // previous pair fully stored / twiddles + spectrum visible
     if (A.nin < N) zero_lines<LOG2N>(b0, LPB);
     __syncthreads();
-    for (int i = threadIdx.x; i < LPB * A.nin; i += kThreads) {
-      const int al = i % LPB, e = i / LPB;  // a fastest: coalesced
-      if (al < nl) {
-        const int slot = A.flip ? ((N - e) & (N - 1)) : e;
-        b0[al * LS + PI(slot)] = in[al + (long long)e * A.in_se];
+    if (nl == LPB && (LPB & 1) == 0 && ((A.in_se | A.in_sb | A.in_batch) & 1) == 0) {
+      // full tile: two adjacent lines per 16-byte load (half the load instructions, twice the bytes in flight)
+      constexpr int H = LPB / 2;
+      for (int i = threadIdx.x; i < H * A.nin; i += kThreads) {
+        const int ap = i % H, e = i / H;
+        const float4 v = *reinterpret_cast<const float4*>(in + 2 * ap + (long long)e * A.in_se);
+        const int slot = PI(A.flip ? ((N - e) & (N - 1)) : e);
+        b0[(2 * ap) * LS + slot] = make_float2(v.x, v.y);
+        b0[(2 * ap + 1) * LS + slot] = make_float2(v.z, v.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < LPB * A.nin; i += kThreads) {
+        const int al = i % LPB, e = i / LPB;  // a fastest: coalesced
+        if (al < nl) {
+          const int slot = A.flip ? ((N - e) & (N - 1)) : e;
+          b0[al * LS + PI(slot)] = in[al + (long long)e * A.in_se];
+        }
       }
     }
     __syncthreads();
@@ -378,6 +390,15 @@ __global__ void __launch_bounds__(kThreads, 5) k_fft_strided(const StridedArgs A
         v.x *= A.scale;
         v.y *= A.scale;
         out[(long long)al * A.out_sa + (long long)e * A.out_se] = v;
+      }
+    } else if (nl == LPB && (LPB & 1) == 0 && ((A.out_se | A.out_sb | A.out_batch) & 1) == 0) {
+      constexpr int H = LPB / 2;
+      for (int i = threadIdx.x; i < H * A.nout; i += kThreads) {
+        const int ap = i % H, e = i / H;
+        const int slot = PI(e);
+        const float2 v0 = res[(2 * ap) * LS + slot], v1 = res[(2 * ap + 1) * LS + slot];
+        *reinterpret_cast<float4*>(out + 2 * ap + (long long)e * A.out_se) =
+            make_float4(v0.x * A.scale, v0.y * A.scale, v1.x * A.scale, v1.y * A.scale);
       }
     } else {
       for (int i = threadIdx.x; i < LPB * A.nout; i += kThreads) {
@@ -408,11 +429,15 @@ struct ZDirectArgs {
   long long tmpl_batch, out_batch;
   int nz, tz, nzo;
 };
+#ifndef IQ_ZD_THREADS
+#define IQ_ZD_THREADS 256
+#endif
+constexpr int kZdThreads = IQ_ZD_THREADS;
 template <int W>
-__global__ void __launch_bounds__(256) k_fft_zdirect(const ZDirectArgs A) {
+__global__ void __launch_bounds__(kZdThreads) k_fft_zdirect(const ZDirectArgs A) {
   // blockIdx.x = template pair (fastest): the CTAs that read the same spectrum columns are scheduled together, so the
   // spectrum comes from DRAM once per launch and from L2 for every other pair
-  const long long col = (long long)blockIdx.y * 256 + threadIdx.x;
+  const long long col = (long long)blockIdx.y * kZdThreads + threadIdx.x;
   if (col >= A.plane) return;
   const float2* __restrict__ S = A.sxy + col;
   const float2* __restrict__ T = A.tmpl + (long long)blockIdx.x * A.tmpl_batch + col;
@@ -630,9 +655,19 @@ __global__ void __launch_bounds__(kThreads, 4) k_fft_x_final(const FinalArgs A) 
     }
   } else {
     const float2* in = A.in + ((long long)pr * A.nlines + l0) * N;
-    for (int i = threadIdx.x; i < nl * N; i += kThreads) {
-      const int line = i >> LOG2N, e = i & (N - 1);
-      b0[line * LS + PI(e)] = in[(long long)line * N + e];
+    if (N >= 2) {  // two consecutive elements of a line per 16-byte load (PI(e) and PI(e + 1) are adjacent for even e)
+      for (int i = threadIdx.x; i < nl * (N / 2); i += kThreads) {
+        const int line = i / (N / 2), e = 2 * (i - line * (N / 2));
+        const float4 v = *reinterpret_cast<const float4*>(in + (long long)line * N + e);
+        float2* d = b0 + line * LS + PI(e);
+        d[0] = make_float2(v.x, v.y);
+        d[1] = make_float2(v.z, v.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < nl * N; i += kThreads) {
+        const int line = i >> LOG2N, e = i & (N - 1);
+        b0[line * LS + PI(e)] = in[(long long)line * N + e];
+      }
     }
   }
   __syncthreads();
@@ -840,15 +875,15 @@ static cudaError_t launch_final(const FinalArgs& a, int log2n, int npair, cudaSt
 }
 
 static cudaError_t launch_zdirect(const ZDirectArgs& a, int npair, cudaStream_t s) {
-  dim3 grid(npair, (unsigned)((a.plane + 255) / 256));
+  dim3 grid(npair, (unsigned)((a.plane + kZdThreads - 1) / kZdThreads));
   const int w = (a.tz + 3) / 4 * 4;
   switch (w) {
-    case 4: k_fft_zdirect<4><<<grid, 256, 0, s>>>(a); break;
-    case 8: k_fft_zdirect<8><<<grid, 256, 0, s>>>(a); break;
-    case 12: k_fft_zdirect<12><<<grid, 256, 0, s>>>(a); break;
-    case 16: k_fft_zdirect<16><<<grid, 256, 0, s>>>(a); break;
-    case 20: k_fft_zdirect<20><<<grid, 256, 0, s>>>(a); break;
-    case 24: k_fft_zdirect<24><<<grid, 256, 0, s>>>(a); break;
+    case 4: k_fft_zdirect<4><<<grid, kZdThreads, 0, s>>>(a); break;
+    case 8: k_fft_zdirect<8><<<grid, kZdThreads, 0, s>>>(a); break;
+    case 12: k_fft_zdirect<12><<<grid, kZdThreads, 0, s>>>(a); break;
+    case 16: k_fft_zdirect<16><<<grid, kZdThreads, 0, s>>>(a); break;
+    case 20: k_fft_zdirect<20><<<grid, kZdThreads, 0, s>>>(a); break;
+    case 24: k_fft_zdirect<24><<<grid, kZdThreads, 0, s>>>(a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
