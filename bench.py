@@ -360,8 +360,9 @@ def main():
         # The FFT passes dominate: byte-bound.  `achieved` uses the ALGORITHMIC bytes of SURVEY 8(d): per launch of R
         # searches the image and its cached spectrum once, per search one distance map written and the template + mask
         # read -- the floor any method has to move -- over the CUDA-event time of the passes on the launching stream.
-        per_launch = stats[0]["stats"].get("searches_per_launch", 0) or nreal_local
-        launches_fft = max(nfft / max(per_launch, 1), 1.0)
+        # distance launches of the run (every one an FFT correlate call when no search went to the direct kernel)
+        launches_fft = float(dist_launches) if ndirect == 0 and dist_launches > 0 else max(nfft / max(nreal_local, 1), 1.0)
+        per_launch = nfft / launches_fft
         spec_bytes = 8.0 * float(np.prod([1 << int(np.ceil(np.log2(max(v, 1)))) for v in ti.shape[:2]])) * (ti.shape[2] if ti.ndim == 3 else 1)
         b8d = launches_fft * (4.0 * nti + spec_bytes) + nfft * (4.0 * npos + 8.0 * mean_nnz)
         gbs8d = b8d / (fft_ms * 1e-3) / 1e9
@@ -374,7 +375,9 @@ def main():
             try:
                 with open(meta) as f:
                     tm = json.load(f)
-                traffic, traffic_note = tm["dram_bytes_per_launch"], tm["note"]
+                # the committed capture's launches carry tm["searches_per_launch"] searches: scale to this run's launches
+                traffic = tm["dram_bytes_per_launch"] * per_launch / tm["searches_per_launch"]
+                traffic_note = tm["note"]
             except Exception:
                 pass
         roof = {"bound": "hbm", "achieved": gbs8d, "peak": hbm, "unit": "GB/s", "frac": gbs8d / hbm, "of": peak_kind,

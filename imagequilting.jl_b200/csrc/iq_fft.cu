@@ -430,7 +430,7 @@ struct ZDirectArgs {
   int nz, tz, nzo;
 };
 #ifndef IQ_ZD_THREADS
-#define IQ_ZD_THREADS 256
+#define IQ_ZD_THREADS 128  // 949 vs 990 ms of FFT passes per config-5 simulation with 256 (finer CTA scheduling)
 #endif
 constexpr int kZdThreads = IQ_ZD_THREADS;
 template <int W>

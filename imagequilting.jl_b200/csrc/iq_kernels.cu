@@ -1035,31 +1035,37 @@ __global__ void __launch_bounds__(256) k_pick_write(PickJob* jobs, long long npo
   const PickJob& J = jobs[blockIdx.y];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double thr = (J.mode == 0) ? (1.0 + J.tol) * (double)__uint_as_float(*J.minbits) : 0.0;
-  const long long base = (long long)blockIdx.x * kPickChunk;
+  // every warp owns kPickChunk / 8 consecutive positions of the CTA's chunk: the predicate is evaluated once (one bit
+  // per iteration kept in a register), the warp totals are scanned with ONE barrier, then every warp writes its
+  // candidates in ascending position (the first version took two barriers per 256 positions)
+  constexpr int kPerWarp = kPickChunk / 8, kIters = kPerWarp / 32;
+  const long long base = (long long)blockIdx.x * kPickChunk + (long long)warp * kPerWarp;
   __shared__ unsigned s_w[8];
-  unsigned running = J.blockcount[blockIdx.x];
-  for (int it = 0; it < kPickChunk / 256; ++it) {
-    const long long p = base + it * 256 + tid;
+  unsigned mybits = 0, wcount = 0;
+#pragma unroll 4
+  for (int it = 0; it < kIters; ++it) {
+    const long long p = base + it * 32 + lane;
     const bool ok = (p < npos) && pick_pred(J, p, thr);
+    mybits |= (ok ? 1u : 0u) << it;
+    wcount += __popc(__ballot_sync(0xffffffffu, ok));
+  }
+  if (lane == 0) s_w[warp] = wcount;
+  __syncthreads();
+  unsigned running = J.blockcount[blockIdx.x];
+  for (int w = 0; w < warp; ++w) running += s_w[w];
+  if (wcount == 0) return;
+  for (int it = 0; it < kIters; ++it) {
+    const bool ok = (mybits >> it) & 1u;
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) s_w[warp] = __popc(bal);
-    __syncthreads();
-    unsigned before = 0, all = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const unsigned c = s_w[w];
-      if (w < warp) before += c;
-      all += c;
-    }
     if (ok) {
-      const long long slot = (long long)running + before + __popc(bal & ((1u << lane) - 1u));
+      const long long p = base + it * 32 + lane;
+      const long long slot = (long long)running + __popc(bal & ((1u << lane) - 1u));
       if (slot < J.cap) {
         J.cand_idx[slot] = (unsigned)p;
         for (int s = 0; s < J.nsrc; ++s) J.cand_val[(long long)s * J.cap + slot] = J.src[s][p];
       }
     }
-    running += all;
-    __syncthreads();
+    running += __popc(bal);
   }
 }
 

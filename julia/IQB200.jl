@@ -118,6 +118,7 @@ struct SimDesc          # == iq_sim_desc
   aux::Ptr{Ptr{Float32}}
   hard_has::Ptr{UInt8}
   hard_val::Ptr{Float32}
+  exact_cut::Int32      # 1: boundary cuts in exact 128-bit integer arithmetic (integer-valued / categorical images)
 end
 
 struct SimSlab          # == iq_sim_slab (tile coordinates, 0-based)
@@ -146,7 +147,8 @@ function simulate!(outs::Vector{<:Array{Float32}}, ctx::Context, TI::AbstractArr
   status = Ref{Int32}(0)
   GC.@preserve ti64 u auxs auxptr outs begin
     desc = SimDesc(pad3(padsize), pad3(ovlsize), length(outs), pointer(ti64), pointer(u), length(steps), tol, 0,
-                   isempty(auxs) ? Ptr{Ptr{Float32}}(C_NULL) : pointer(auxptr), Ptr{UInt8}(C_NULL), Ptr{Float32}(C_NULL))
+                   isempty(auxs) ? Ptr{Ptr{Float32}}(C_NULL) : pointer(auxptr), Ptr{UInt8}(C_NULL), Ptr{Float32}(C_NULL),
+                   all(isinteger, TI) ? 1 : 0)
     check(ccall((:iq_sim_begin, lib), Int32, (Ptr{Cvoid}, Ref{SimDesc}), ctx.handle, desc))
     for (k, (start0, ovlmask, slabs)) in enumerate(steps)
       st = Int64[start0...]; mask = Array{UInt8}(vec(ovlmask))
@@ -163,6 +165,22 @@ function simulate!(outs::Vector{<:Array{Float32}}, ctx::Context, TI::AbstractArr
     check(ccall((:iq_sim_end, lib), Int32, (Ptr{Cvoid},), ctx.handle))
   end
   status[]
+end
+
+"""
+    dependency_levels(tilesize, ovlsize, ntiles, path0) -> (levels, nlevels)
+
+Dependency level of every step of a simulation path (`path0`: 0-based column-major tile indices).  Steps of one level
+touch disjoint windows of the simulation grid and may be handed to `iq_sim_step_multi` together (after registering their
+overlap shapes with `iq_sim_define_shape`); running the levels in order reproduces the sequential loop of
+src/iqsim.jl:172-285 bit for bit.  Raster paths: level(i, j, k) = i + 2j + 4k.
+"""
+function dependency_levels(tilesize::Dims{N}, ovlsize::Dims{N}, ntiles::Dims{N}, path0::Vector{Int64}) where {N}
+  levels = Vector{Int32}(undef, length(path0)); nl = Ref{Int32}(0)
+  check(ccall((:iqh_dependency_levels, lib), Int32,
+              (Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Int32}, Ref{Int32}),
+              N, Int64[tilesize...], Int64[ovlsize...], Int64[ntiles...], path0, length(path0), levels, nl))
+  levels, nl[]
 end
 
 end # module
