@@ -776,7 +776,7 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
         }
         {
           int nl = 0;
-          CK(iq::launch_select_all(c->d_sel, R * maxS, c->npos, c->d_shifts, c->nshift, c->stream, &nl));
+          CK(iq::launch_select_all(c->d_sel, R * maxS, c->npos, c->d_shifts, c->nshift, c->stream, &nl, c->d_sel_list));
           c->launches += nl;
         }
       }
@@ -952,6 +952,7 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   cudaFree(c->d_stage);
   cudaFree(c->d_sel);
+  cudaFree(c->d_sel_list);
   cudaFree(c->d_selbuf);
   if (c->h_sel) cudaFreeHost(c->h_sel);
   cudaFree(c->d_pick);
@@ -1053,6 +1054,7 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   c->sel_cap = (unsigned)std::max<long long>(c->npos / 16, 4096);
   CK(iq::dmalloc((void**)&c->d_selbuf, B * c->max_src * (size_t)c->sel_cap * sizeof(unsigned long long)));
   CK(iq::dmalloc((void**)&c->d_sel, B * c->max_src * sizeof(iq::SelJob)));
+  CK(iq::dmalloc((void**)&c->d_sel_list, (B * c->max_src + 1) * sizeof(int)));
   CK(cudaMallocHost((void**)&c->h_sel, B * c->max_src * sizeof(iq::SelJob)));
   CK(cudaMemsetAsync(c->d_sel, 0, B * c->max_src * sizeof(iq::SelJob), c->stream));
   CK(iq::dmalloc((void**)&c->d_pick, B * sizeof(iq::PickJob)));

@@ -180,6 +180,24 @@ __device__ __forceinline__ void graphcut_body(const CutTask& T) {
     clist[w] = (a < n0) ? (unsigned short)(row * n0 + a) : (unsigned short)0xffff;
   }
   __syncthreads();
+#ifndef IQ_CUT_NO_PREAUG
+  // Straight-line pre-augmentation (as the host routine does): every column along the cut axis carries
+  // f = min(capacities along it) from the source slice to the sink slice before the push-relabel starts -- a valid
+  // flow that takes the bulk of the excess out of the first layer.  One thread per column, no conflicts.
+  for (int col = tid; col < (L > 2 ? P : 0); col += kCutThreads) {  // (L == 2: no inner layer, nothing to route)
+    CT f = e[col];  // capacity of the (saturated) arc source slice -> layer 1
+    for (int k = 0; k < L - 2; ++k) f = C::mn(f, r[4 * nfree + k * P + col]);
+    if (C::pos(f)) {
+      e[col] = C::sub(e[col], f);
+      for (int k = 0; k < L - 2; ++k) {
+        const int i = k * P + col;
+        r[4 * nfree + i] = C::sub(r[4 * nfree + i], f);
+        if (k + 1 < L - 2) r[5 * nfree + i + P] = C::add(r[5 * nfree + i + P], f);
+      }
+    }
+  }
+  __syncthreads();
+#endif
 
   // Exact heights = BFS distance to the sink slice over residual arcs x -> v, level by level with explicit
   // frontiers in shared memory (every voxel is expanded once; levels are unique, so the result does not depend
@@ -315,7 +333,14 @@ __device__ __forceinline__ void graphcut_body(const CutTask& T) {
     long long tc = clock64(); t_rel += tc - tb;
 #endif
     if (!any || iter >= max_iter) break;
-    if ((iter % IQ_CUT_RELABEL) == IQ_CUT_RELABEL - 1 || iter == 3) {
+#ifdef IQ_CUT_LATE
+    // experiment: exact heights more often once the bulk of the flow has settled (the long tail of sweeps is excess
+    // crawling along stale labels)
+    const bool relabel_now = iter >= 32 ? ((iter % IQ_CUT_LATE) == IQ_CUT_LATE - 1) : ((iter % IQ_CUT_RELABEL) == IQ_CUT_RELABEL - 1 || iter == 3);
+#else
+    const bool relabel_now = (iter % IQ_CUT_RELABEL) == IQ_CUT_RELABEL - 1 || iter == 3;
+#endif
+    if (relabel_now) {
       global_relabel();
 #ifdef IQ_CUT_PROFILE
       t_glob += clock64() - tc; ++nglob;

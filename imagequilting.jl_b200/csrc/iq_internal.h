@@ -74,6 +74,14 @@ struct SelJob {
   unsigned ccap;
   unsigned ccount;               // keys in cbuf
   int compact;                   // 1 = cbuf holds the surviving keys (set by the pass that decides it, filled by k_select_compact)
+  // Range-adaptive digits (optional, nv > 0): the map's finite values lie in [sub, sub + 2^t) as float bits (known from
+  // the distance epilogue), so the select runs on keys (bits - sub) << 32 | position and its FIRST digit is the top 8
+  // bits of that range instead of the float's sign / exponent byte, which hardly discriminates: the k-th key's bin then
+  // holds ~1 % of the map and the survivors are gathered after ONE full pass instead of two.  vshift = the value-digit
+  // shifts (the position digits follow from the context's schedule); 0 everywhere = the plain schedule.
+  unsigned sub;
+  int nv;
+  int vshift[4];
 };
 
 // Candidate predicate + outputs for one tile.
@@ -125,11 +133,10 @@ cudaError_t launch_sat_build(const float* img, double* sat, int nx, int ny, int 
 cudaError_t launch_a2map(const double* sat, int nx, int ny, int nz, const BoxDesc* boxes, int nbox,
                          float* a2, int nxo, int nyo, int nzo, cudaStream_t s);
 cudaError_t launch_fill_u32(unsigned* p, unsigned v, long long n, cudaStream_t s);
-cudaError_t launch_select_pass(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift,
-                               cudaStream_t s);
 // All passes of a radix select (k_select_pass x nshift, with the compaction of the survivors after the second pass).
+// scratch: njobs + 1 ints of device memory (job list + count of the pass being launched)
 cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s,
-                              int* launches);
+                              int* launches, int* scratch);
 cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
 cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
 // Threshold selection driven by chunk minima (chunk = chunklen consecutive positions): only chunks whose minimum

@@ -805,17 +805,48 @@ cudaError_t launch_fill_u32(unsigned* p, unsigned v, long long n, cudaStream_t s
 __device__ __forceinline__ unsigned long long make_key(float v, long long p) {
   return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)p;
 }
+// key of the range-adaptive select (SelJob::sub); values below sub do not occur, values above the range (+Inf of
+// disabled patches) keep high bits set and are filtered by the initial mask
+__device__ __forceinline__ unsigned long long make_key_sub(float v, long long p, unsigned sub) {
+  return ((unsigned long long)(__float_as_uint(v) - sub) << 32) | (unsigned long long)p;
+}
+// shift of pass `pass` of a job and its total number of passes (the context's schedule: 4 value bytes, then the
+// position bytes; an adaptive job replaces the value bytes by its own nv digits)
+__device__ __forceinline__ int job_shift(const SelJob* J, const int* __restrict__ shifts, int nshift, int pass, int* total) {
+  if (J->nv == 0) { *total = nshift; return shifts[pass]; }
+  *total = J->nv + (nshift - 4);
+  return pass < J->nv ? J->vshift[pass] : shifts[4 + pass - J->nv];
+}
 
 // Grid = (blocks per job, jobs).  Inactive jobs (finished early, later relaxation rounds) return at once; the launcher
 // keeps the blocks per job low when there are many jobs so that such rows stay cheap.
-__global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, long long npos, const int* __restrict__ shifts,
-                                                     int nshift) {
+// Snapshot of the jobs a pass has to visit (mode 0: active ones; mode 1: those marked for the gather, compact == 2).
+// A separate launch, so that every CTA of the pass works from the same list; most launches of the later relaxation
+// rounds find it empty and then cost a few microseconds instead of a grid of tens of thousands of idle CTAs.
+__global__ void k_select_list(const SelJob* __restrict__ jobs, int njobs, int mode, int* __restrict__ list, int* __restrict__ count) {
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < njobs; j0 += blockDim.x) {  // ascending job order within a chunk is not needed: any order works
+    const int j = j0 + threadIdx.x;
+    const bool on = j < njobs && (mode == 0 ? jobs[j].active != 0 : (jobs[j].active != 0 && jobs[j].compact == 2));
+    if (on) list[atomicAdd(&s_n, 1)] = j;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *count = s_n;
+}
+
+__global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, const int* __restrict__ list, const int* __restrict__ count,
+                                                     int nb, long long npos, const int* __restrict__ shifts, int nshift) {
   __shared__ unsigned h[256];
   __shared__ int s_active, s_pass, s_last;
   __shared__ unsigned long long s_prefix, s_mask;
   const int tid = threadIdx.x;
-  {
-    SelJob* J = jobs + blockIdx.y;
+  const int nwork = *count * nb;  // work item = (listed job, virtual block of nb)
+  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int vb = w % nb;
+    SelJob* J = jobs + list[w / nb];
+    __syncthreads();  // the previous item's shared state is dead
     if (tid == 0) {
       s_active = J->active;
       s_pass = J->pass;
@@ -824,8 +855,10 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
     }
     h[tid] = 0;
     __syncthreads();
-    if (!s_active) return;
-    const int shift = shifts[s_pass];
+    if (!s_active) continue;
+    int npass_job;
+    const int shift = job_shift(J, shifts, nshift, s_pass, &npass_job);
+    const unsigned sub = J->sub;
     const unsigned long long prefix = s_prefix, mask = s_mask;
     const float* __restrict__ map = J->map;
     const bool comp = J->compact != 0;  // scan the compacted survivors instead of the map
@@ -834,11 +867,11 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
     // warp-aggregated histogram: distance values cluster in a few exponent bins, so per-lane shared-memory
     // atomics would serialise 32-way; lanes with the same bin elect one leader that adds their count
     const int lane = tid & 31;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+    for (long long i0 = (long long)vb * blockDim.x + (tid & ~31); i0 < n; i0 += (long long)nb * blockDim.x) {
       const long long i = i0 + lane;
       unsigned bin = 0xffffffffu;
       if (i < n) {
-        const unsigned long long key = comp ? cbuf[i] : make_key(map[i], i);
+        const unsigned long long key = comp ? cbuf[i] : make_key_sub(map[i], i, sub);
         if ((key & mask) == prefix) bin = (unsigned)(key >> shift) & 255u;
       }
       if (s_pass == 0) {
@@ -853,9 +886,9 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
     if (h[tid]) atomicAdd(&J->hist[tid], h[tid]);
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == gridDim.x - 1);
+    if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == (unsigned)nb - 1u);
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) continue;
     if (tid == 0) {
       __threadfence();
       volatile unsigned* gh = J->hist;
@@ -870,15 +903,19 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
       k -= cum;
       const unsigned long long np = prefix | ((unsigned long long)b << shift);
       const bool exact = (c == k);  // every key sharing the new prefix is selected
-      if (exact || s_pass + 1 == nshift) {
-        J->kth = exact ? (np | ((shift == 0) ? 0ull : ((1ull << shift) - 1ull))) : np;
+      if (exact || s_pass + 1 == npass_job) {
+        // back to plain keys (float bits << 32 | position): that is what the pick kernels compare with
+        J->kth = (exact ? (np | ((shift == 0) ? 0ull : ((1ull << shift) - 1ull))) : np) + ((unsigned long long)sub << 32);
         J->active = 0;
       } else {
-        const int ns = shifts[s_pass + 1];
-        J->mask = ~((1ull << (ns + 8)) - 1ull);
+        J->mask = ~((1ull << shift) - 1ull);  // every bit from this digit upwards is decided
         J->pass = s_pass + 1;
-        // second pass done: c keys share the decided 16 bits; if they fit, k_select_compact gathers them next
-        if (s_pass == 1 && nshift > 3 && J->cbuf && c <= (unsigned long long)J->ccap) { J->compact = 2; J->ccount = 0; }
+        // c keys share the decided bits: once they fit (after the first pass of an adaptive job, after the second
+        // otherwise), k_select_compact gathers them and the remaining passes scan that list
+        if (J->compact == 0 && s_pass <= 1 && (J->nv > 0 || s_pass == 1) && npass_job > 3 && J->cbuf && c <= (unsigned long long)J->ccap) {
+          J->compact = 2;
+          J->ccount = 0;
+        }
       }
       J->prefix = np;
       J->k = k;
@@ -891,20 +928,24 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, lo
 
 // Gathers the keys that match the decided prefix of every job marked by the second pass (compact == 2) into its
 // scratch list (order is irrelevant: keys are unique) and switches the job to list mode (compact = 1).
-__global__ void __launch_bounds__(256) k_select_compact(SelJob* jobs, int njobs, long long npos) {
- {
-  SelJob* J = jobs + blockIdx.y;
-  if (!J->active || J->compact != 2) return;
+__global__ void __launch_bounds__(256) k_select_compact(SelJob* jobs, const int* __restrict__ list, const int* __restrict__ count,
+                                                        int nb, long long npos) {
+ const int nwork = *count * nb;
+ for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+  const int vb = w % nb;
+  SelJob* J = jobs + list[w / nb];
+  if (!J->active || J->compact != 2) continue;
   const unsigned long long prefix = J->prefix, mask = J->mask;
+  const unsigned sub = J->sub;
   const float* __restrict__ map = J->map;
   unsigned long long* __restrict__ cbuf = J->cbuf;
   const int tid = threadIdx.x, lane = tid & 31;
-  for (long long i0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); i0 < npos; i0 += (long long)gridDim.x * blockDim.x) {
+  for (long long i0 = (long long)vb * blockDim.x + (tid & ~31); i0 < npos; i0 += (long long)nb * blockDim.x) {
     const long long i = i0 + lane;
     unsigned long long key = 0;
     bool hit = false;
     if (i < npos) {
-      key = make_key(map[i], i);
+      key = make_key_sub(map[i], i, sub);
       hit = (key & mask) == prefix;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, hit);
@@ -923,35 +964,40 @@ __global__ void k_select_compact_done(SelJob* jobs, int njobs) {
   if (j < njobs && jobs[j].compact == 2) jobs[j].compact = 1;
 }
 
-cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s,
-                              int* launches) {
+// scratch of the select launches: job list + count (one per stream would be needed for concurrent selects on one
+// device from different contexts; the list lives next to the jobs: jobs[njobs] is followed by nothing we own, so the
+// caller provides it)
+static int select_nb(int njobs, long long npos) {
   long long nb = (npos + 256 * 8 - 1) / (256 * 8);
   const long long cap = njobs >= 16 ? 148 : 148 * 4;
   if (nb > cap) nb = cap;
   if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s,
+                              int* launches, int* scratch) {
+  const int nb = select_nb(njobs, npos);
+  int* list = scratch;
+  int* count = scratch + njobs;
+  const int grid = 148 * 4;  // persistent CTAs over (listed job, virtual block) work items
   int nl = 0;
   for (int pass = 0; pass < nshift; ++pass) {
-    cudaError_t e = launch_select_pass(jobs, njobs, npos, shifts, nshift, s);
+    k_select_list<<<1, 256, 0, s>>>(jobs, njobs, 0, list, count);
+    k_select_pass<<<grid, 256, 0, s>>>(jobs, list, count, nb, npos, shifts, nshift);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    ++nl;
-    if (pass == 1 && nshift > 3) {
-      k_select_compact<<<dim3((unsigned)nb, njobs), 256, 0, s>>>(jobs, njobs, npos);
+    nl += 2;
+    if (pass <= 1 && nshift > 3) {  // gather point of adaptive jobs (after pass 0) and of plain ones (after pass 1)
+      k_select_list<<<1, 256, 0, s>>>(jobs, njobs, 1, list, count);
+      k_select_compact<<<grid, 256, 0, s>>>(jobs, list, count, nb, npos);
       k_select_compact_done<<<(njobs + 127) / 128, 128, 0, s>>>(jobs, njobs);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
-      nl += 2;
+      nl += 3;
     }
   }
   if (launches) *launches += nl;
   return cudaSuccess;
-}
-
-cudaError_t launch_select_pass(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s) {
-  long long nb = (npos + 256 * 8 - 1) / (256 * 8);
-  const long long cap = njobs >= 16 ? 148 : 148 * 4;
-  if (nb > cap) nb = cap;
-  if (nb < 1) nb = 1;
-  k_select_pass<<<dim3((unsigned)nb, njobs), 256, 0, s>>>(jobs, njobs, npos, shifts, nshift);
-  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(128) k_sim_sample(const iq::PickJob* __restric
 // per source.
 __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* __restrict__ pick, int maxS,
                               const unsigned* __restrict__ maxbits, int maxbits_stride, int maxbits_tile_stride, int R,
-                              unsigned shared_mask, double tol,
+                              const unsigned* __restrict__ minmax, int B, int hard, unsigned shared_mask, double tol,
                               long long npatterns, long long npos, int round, int* __restrict__ pending,
                               unsigned long long* __restrict__ selbuf, unsigned selcap) {
   const int r = blockIdx.x, s = threadIdx.x;  // r = job; the jobs of one tile (r / R) share that tile's auxiliary maps
@@ -302,6 +302,7 @@ __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* 
   iq::SelJob& J = jobs[(long long)r * maxS + s];
   const iq::PickJob& P = pick[r];
   J.k = 0; J.prefix = 0; J.mask = 0; J.kth = 0; J.pass = 0; J.active = 0; J.ticket = 0;
+  J.sub = 0; J.nv = 0;
   J.cbuf = selbuf + ((long long)r * maxS + s) * selcap; J.ccap = selcap; J.ccount = 0; J.compact = 0;
   for (int i = 0; i < 256; ++i) J.hist[i] = 0;
   if (s == 0 && round == 0) pending[r] = 1;
@@ -317,6 +318,29 @@ __global__ void k_sim_seljobs(iq::SelJob* __restrict__ jobs, const iq::PickJob* 
   k = max(1ll, min(k, npos));
   J.map = P.src[s];
   J.k = (unsigned long long)k;
+  {
+    // range-adaptive digits: [min, max] of this source map over the enabled positions, written by its distance
+    // epilogue -- kind 0 = overlap map of job r, 1 = hard map of the tile, 2 + i = soft map i of the tile
+    const int tile = r / R;
+    int kind, slot;
+    if (hard) { kind = s == 0 ? 1 : (s == 1 ? 0 : s); slot = s == 1 ? r : tile; }
+    else { kind = s == 0 ? 0 : 1 + s; slot = s == 0 ? r : tile; }
+    const unsigned lo = minmax[(size_t)(kind * 2 + 0) * B + slot], hi = minmax[(size_t)(kind * 2 + 1) * B + slot];
+    if (lo <= hi && hi < 0x7f800000u) {
+      const unsigned range = hi - lo;
+      const int t = range ? 32 - __clz(range) : 1;  // the values span t bits
+      int sh = 32 + max(t - 8, 0), nv = 0;
+      for (;;) {
+        J.vshift[nv++] = sh;
+        if (sh == 32 || nv == 4) break;
+        sh = max(sh - 8, 32);
+      }
+      J.vshift[nv - 1] = 32;  // the last value digit always ends at the lowest value bit
+      J.nv = nv;
+      J.sub = lo;
+      J.mask = ~((1ull << (J.vshift[0] + 8)) - 1ull);  // in-range keys have nothing above the first digit; +Inf has
+    }
+  }
   // map shared by all realizations (bit s of shared_mask) and the same k as realization 0, which runs its selection
   // in this round: copy afterwards.  (k depends on the all-zero flag and the round only; pending[] is not written
   // during rounds > 0.)
@@ -967,12 +991,13 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
       // intersection)
       const int kRelaxRounds = (hardt || nempty > 0) ? 11 : 5;
       for (int round = 0; round < kRelaxRounds; ++round) {
-        k_sim_seljobs<<<NJ, 32, 0, c->stream>>>(c->d_sel, pj, c->max_src, pmax, pmax_stride, pmax_tile_stride, R, shared_mask,
-                                               s->tol, c->nenabled, c->npos, round, s->d_pending, c->d_selbuf, c->sel_cap);
+        k_sim_seljobs<<<NJ, 32, 0, c->stream>>>(c->d_sel, pj, c->max_src, pmax, pmax_stride, pmax_tile_stride, R, c->d_minmax,
+                                               c->max_batch, hardt ? 1 : 0, shared_mask, s->tol, c->nenabled, c->npos, round,
+                                               s->d_pending, c->d_selbuf, c->sel_cap);
         CK(cudaGetLastError());
         {
           int nl = 0;
-          CK(iq::launch_select_all(c->d_sel, NJ * c->max_src, c->npos, c->d_shifts, c->nshift, c->stream, &nl));
+          CK(iq::launch_select_all(c->d_sel, NJ * c->max_src, c->npos, c->d_shifts, c->nshift, c->stream, &nl, c->d_sel_list));
           c->launches += nl;
         }
         k_sim_copykth<<<NJ, 32, 0, c->stream>>>(c->d_sel, c->max_src, R);

@@ -139,12 +139,37 @@ def iqsim_sliced(trainimg, tilesize, simsize=None, *, overlap=None, tol=0.1, pat
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return float(t.item())
 
-    def allgather(obj):
+    # Candidate exchange: ONE fixed-size tensor all-gather per tile search (NCCL on device tensors, gloo on host
+    # tensors) -- no pickled Python objects.  A rank's record is [count, idx[0:cap], float bits of val[0:cap]] as int64;
+    # the capacity starts at 4096 candidates and doubles for the whole run when any rank's list does not fit (the search
+    # is then exchanged again with the larger records: counts are known to every rank, so all ranks take the same branch).
+    use_cuda = world > 1 and dist.get_backend() == "nccl"
+    state = {"cap": 4096}
+
+    def allgather(idx, val):
         if world == 1:
-            return [obj]
-        out = [None] * world
-        dist.all_gather_object(out, obj)
-        return out
+            return idx, val
+        while True:
+            cap = state["cap"]
+            rec = np.zeros(1 + 2 * cap, dtype=np.int64)
+            n = int(idx.size)
+            rec[0] = n
+            m = min(n, cap)
+            rec[1:1 + m] = idx[:m]
+            rec[1 + cap:1 + cap + m] = val[:m].astype(np.float32).view(np.int32).astype(np.int64)
+            t = torch.from_numpy(rec)
+            if use_cuda:
+                t = t.cuda()
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            parts = [o.cpu().numpy() for o in out]
+            nmax = max(int(pz[0]) for pz in parts)
+            if nmax <= cap:
+                gi = np.concatenate([pz[1:1 + int(pz[0])] for pz in parts])
+                gv = np.concatenate([pz[1 + cap:1 + cap + int(pz[0])].astype(np.int32).view(np.float32) for pz in parts])
+                return gi, gv
+            while state["cap"] < nmax:
+                state["cap"] *= 2
 
     reals = []
     for real in range(nreal):
@@ -174,9 +199,8 @@ def iqsim_sliced(trainimg, tilesize, simsize=None, *, overlap=None, tol=0.1, pat
                 lmin = backend.distance(mask, simdev) if backend is not None else float("inf")
                 gmin = allreduce_min(lmin)
                 idx, val = backend.select(tol, gmin) if backend is not None else (np.zeros(0, np.int64), np.zeros(0, np.float32))
-                parts = allgather((idx + z0 * plane, val))
-                gidx = np.concatenate([p[0] for p in parts])
-                gval = np.concatenate([p[1] for p in parts]).astype(np.float32)
+                gidx, gval = allgather(idx + z0 * plane, val)
+                gval = gval.astype(np.float32)
                 prob = api.taumodel(gval[None, :]) if gidx.size > 1 else np.ones(1)
                 rind = int(gidx[api.sample(prob, u)])
             rstart = tuple(int(v) for v in np.unravel_index(rind, distsize, order="F"))

@@ -1,0 +1,17 @@
+# round 2, call M: tests (adaptive select digits, cut pre-augmentation) + bench cfg 3/4/5 + pre-augmentation A/B
+timeout 2400 python -m pytest tests -q -m gpu -x 2>&1 | tail -3 > gpurun_out/r02_m_tests.log
+cat gpurun_out/r02_m_tests.log
+run() { # name lib cfg nreal
+  IQB200_LIB=$2 timeout 300 python bench.py --config $3 --steps 3 --warmup 2 --no-cpu-baseline --nreal $4 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); b = d['breakdown_ms_per_step']
+print('$1 cfg$3 nreal $4: value %.1fM e2e %.1fM ms %.0f device %.0f cut %.1f dist %.0f sel %.1f' % (d['value'] / 1e6, d['e2e']['value'] / 1e6, d['ms_per_step'], b['device_ms'], b['cut_device_ms'], b['search_device_ms'], b['select_ms']))"
+}
+L=imagequilting.jl_b200
+run preaug $L/libiqb200.so 5 64
+run nopreaug $L/libiqb200_nopreaug.so 5 64
+run preaug $L/libiqb200.so 5 8
+run nopreaug $L/libiqb200_nopreaug.so 5 8
+run preaug $L/libiqb200.so 4 8
+run preaug $L/libiqb200.so 3 8
+run preaug $L/libiqb200.so 2 16

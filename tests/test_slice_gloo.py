@@ -34,15 +34,24 @@ class OracleSliceBackend:
 
 def _worker(rank, world, port, ti, use_gpu, q):
     sys.path.insert(0, ROOT)
+    import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # two physical GPUs: one rank per GPU over NCCL (the candidate exchange runs on device tensors); otherwise gloo,
+    # both ranks sharing cuda:0 (or no GPU at all with the oracle-backed slab search)
+    nccl = use_gpu == "nccl"
+    device = rank if nccl else 0
+    if nccl:
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", device))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     import iqb200  # noqa: F401
     from iqb200 import sharding
     factory = None if use_gpu else (lambda t, ts, d: OracleSliceBackend(t, ts, d))
     reals = sharding.iqsim_sliced(ti, (8, 6, 4), None, overlap=(0.25, 0.34, 0.5), tol=0.1, path="random", nreal=2, seed=3,
-                                  device=0, backend_factory=factory)
+                                  device=device, backend_factory=factory)
     if rank == 0:
         q.put([np.asarray(r) for r in reals])
     dist.barrier()
@@ -84,7 +93,7 @@ def test_two_rank_position_slices_equal_oracle_iqsim():
     import iqb200
     ti, got = _run(use_gpu=False)
     want = O.iqsim(ti, (8, 6, 4), None, overlap=(0.25, 0.34, 0.5), tol=0.1, path="random", nreal=2,
-                   rng=np.random.default_rng(3), method="direct", cut_fn=iqb200.graphcut)
+                   rng=np.random.default_rng(3), method="direct", cut_fn=O.graphcut_c)
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
 
@@ -96,5 +105,21 @@ def test_two_rank_position_slices_equal_single_gpu_iqsim():
     ti, got = _run(use_gpu=True)
     want = iqb200.iqsim(ti, (8, 6, 4), None, overlap=(0.25, 0.34, 0.5), tol=0.1, path="random", nreal=2,
                         rng=np.random.default_rng(3), cut="host")
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_two_rank_position_slices_over_nccl_on_two_gpus():
+    """One rank per GPU, NCCL: all-reduce(min) of the local minima and the tensor all-gather of the candidate records
+    run on device tensors.  Needs two physical GPUs (skipped on a one-GPU box; run with `gpurun --gpus 2`)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import iqb200
+    ti, got = _run(use_gpu="nccl")
+    want = iqb200.iqsim(ti, (8, 6, 4), None, overlap=(0.25, 0.34, 0.5), tol=0.1, path="random", nreal=2,
+                        rng=np.random.default_rng(3))
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
