@@ -1051,10 +1051,11 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   const size_t nmm = (size_t)(2 + c->nsoft) * 2 * B;
   CK(iq::dmalloc((void**)&c->d_minmax, nmm * sizeof(unsigned)));
   CK(cudaMallocHost((void**)&c->h_minmax, nmm * sizeof(unsigned)));
-  c->sel_cap = (unsigned)std::max<long long>(c->npos / 16, 4096);
+  c->sel_cap = (unsigned)std::max<long long>(c->npos / 8, 4096);
   CK(iq::dmalloc((void**)&c->d_selbuf, B * c->max_src * (size_t)c->sel_cap * sizeof(unsigned long long)));
   CK(iq::dmalloc((void**)&c->d_sel, B * c->max_src * sizeof(iq::SelJob)));
-  CK(iq::dmalloc((void**)&c->d_sel_list, (B * c->max_src + 1) * sizeof(int)));
+  CK(iq::dmalloc((void**)&c->d_sel_list, (2 * B * c->max_src + 3) * sizeof(int)));
+  CK(cudaMemsetAsync(c->d_sel_list, 0, (2 * B * c->max_src + 3) * sizeof(int), c->stream));
   CK(cudaMallocHost((void**)&c->h_sel, B * c->max_src * sizeof(iq::SelJob)));
   CK(cudaMemsetAsync(c->d_sel, 0, B * c->max_src * sizeof(iq::SelJob), c->stream));
   CK(iq::dmalloc((void**)&c->d_pick, B * sizeof(iq::PickJob)));

@@ -89,7 +89,7 @@ struct iq_ctx {
   unsigned long long* d_selbuf = nullptr;  // [max_batch][max_src][sel_cap] survivor lists of the radix select
   unsigned sel_cap = 0;
   iq::SelJob* d_sel = nullptr;
-  int* d_sel_list = nullptr;               // [max_batch * max_src + 1] job list + count of the select pass being launched
+  int* d_sel_list = nullptr;               // [2 * max_batch * max_src + 3] job lists + counts of the select pass being launched
   iq::SelJob* h_sel = nullptr;
   iq::PickJob* d_pick = nullptr;
   iq::PickJob* h_pick = nullptr;

@@ -21,6 +21,7 @@
 #include "iq_fft.h"
 #include "iq_internal.h"
 
+#include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 #include <math_constants.h>
 
 #include <algorithm>
@@ -702,6 +703,88 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // orders earlier generic-proxy accesses to shared memory before later asynchronous-proxy (TMA) writes
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- pass B, inverse transform along a strided axis with TMA-fed double buffering ------------------------------------
+// The inverse y pass is bound by memory latency (ncu: 5 warps per issue slot waiting on the long scoreboard, DRAM at
+// 63 %): every CTA first pulls its 16 x N tile through registers (128-byte row chunks, 2 KB apart), then transforms, then
+// stores.  Here the CTAs are persistent and the NEXT tile is already in flight while the current one is transformed:
+// every thread issues one 128-byte bulk asynchronous copy (cp.async.bulk, the TMA engine; completion counted on an
+// mbarrier) of row e of the tile straight into shared memory -- no registers, no LSU issue slots -- in the
+// element-major layout [e][16 lines] that the first Stockham pass reads (LIN = 2).  Same arithmetic, same results.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// USE_MAP: ONE tensor-map request per tile (cp.async.bulk.tensor.2d: box of 16 elements x N rows of the work array seen
+// as a 2-D tensor [rows][Nx] of 8-byte elements) instead of N row copies.
+template <int LOG2N, bool USE_MAP>
+__global__ void __launch_bounds__(kThreads, 3) k_fft_strided_inv_tma(const StridedArgs A, int ntile_a, int total,
+                                                                     const __grid_constant__ CUtensorMap tmap, int rows_per_b,
+                                                                     int rows_per_pair) {
+  constexpr int N = 1 << LOG2N, LS = line_stride(LOG2N), LPB = lines_per_block(LOG2N);
+  static_assert(inplace_ok(LOG2N) && LPB == 16, "16 lines per tile, in-place transform");
+  extern __shared__ __align__(128) unsigned char smraw_[];
+  float2* sm = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(smraw_) + 127) & ~(uintptr_t)127);  // TMA boxes: 128-byte aligned
+  // buffer pitch: the padded lines (LPB * LS float2) rounded up to 128 bytes
+  constexpr int kBuf = ((LPB * LS * (int)sizeof(float2) + 127) / 128) * 128 / (int)sizeof(float2);
+  float2* const buf0 = sm;
+  float2* const buf1 = sm + kBuf;
+  float2* tw = sm + 2 * kBuf;
+  __shared__ __align__(8) unsigned long long bar[2];
+  load_twiddles<LOG2N>(tw, A.tw);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // tile t -> (pair, plane b, chunk of 16 lines): the chunks of one plane are consecutive, so that concurrently
+  // running CTAs read neighbouring 128-byte pieces of the same 2 KB rows
+  auto tile_src = [&](int t) -> const float2* {
+    const int ac = t % ntile_a, r = t / ntile_a, b = r % A.nb, pr = r / A.nb;
+    return A.in + (long long)pr * A.in_batch + (long long)b * A.in_sb + ac * LPB;
+  };
+  auto issue = [&](int t, int bsel) {  // all threads
+    float2* dst = bsel ? buf1 : buf0;
+    fence_async_smem();  // the buffer was last touched by ordinary loads / stores
+    if (USE_MAP) {
+      if (threadIdx.x == 0) {
+        const int ac = t % ntile_a, r = t / ntile_a, b = r % A.nb, pr = r / A.nb;
+        mbar_expect_tx(&bar[bsel], (unsigned)(N * LPB * sizeof(float2)));
+        tma_load_2d(dst, &tmap, ac * LPB, pr * rows_per_pair + b * rows_per_b, &bar[bsel]);
+      }
+    } else {
+      const float2* src = tile_src(t);
+      if (threadIdx.x == 0) mbar_expect_tx(&bar[bsel], (unsigned)(N * LPB * sizeof(float2)));
+      for (int e = threadIdx.x; e < N; e += kThreads)
+        bulk_g2s(dst + e * LPB, src + (long long)e * A.in_se, (unsigned)(LPB * sizeof(float2)), &bar[bsel]);
+    }
+  };
+  int t = blockIdx.x;
+  if (t < total) issue(t, 0);
+  for (int it = 0; t < total; t += gridDim.x, ++it) {
+    const int bsel = it & 1;
+    const int tn = t + gridDim.x;
+    if (tn < total) issue(tn, bsel ^ 1);  // the other buffer was released by the barrier at the end of the last round
+    mbar_wait(&bar[bsel], (unsigned)((it >> 1) & 1));
+    float2* cur = bsel ? buf1 : buf0;
+    const float2* res = fft_lines<LOG2N, true, false, 2>(cur, cur, tw, nullptr, LPB);
+    const int ac = t % ntile_a, r = t / ntile_a, b = r % A.nb, pr = r / A.nb;
+    float2* out = A.out + (long long)pr * A.out_batch + (long long)b * A.out_sb + ac * LPB;
+    constexpr int H = LPB / 2;
+    for (int i = threadIdx.x; i < H * A.nout; i += kThreads) {
+      const int ap = i % H, e = i / H;
+      const int slot = PI(e);
+      const float2 v0 = res[(2 * ap) * LS + slot], v1 = res[(2 * ap + 1) * LS + slot];
+      *reinterpret_cast<float4*>(out + 2 * ap + (long long)e * A.out_se) =
+          make_float4(v0.x * A.scale, v0.y * A.scale, v1.x * A.scale, v1.y * A.scale);
+    }
+    __syncthreads();  // everybody is done with this buffer before it is refilled
+  }
+}
+
 // ---- pass C, streaming version: persistent CTAs, the next tile of LPB lines (one contiguous block of global
 //      memory) is fetched by ONE bulk TMA copy into the other half of a double buffer while the current tile is
 //      transformed in place and written out.  The first pass reads the unpadded lines the copy delivered.
@@ -776,6 +859,8 @@ struct Plan {
   bool zyfused = false;              // ... fused with the inverse y transform (k_fft_zy: Ny == 256, tz <= 16)
   std::map<int, float2*> sxy_t;      // transposed (x, y) spectrum [Nx][nz][Ny] of the fused kernel
   size_t workspace = 0;
+  CUtensorMap w3_map;                // w3 as a 2-D tensor [max_pairs * nzo * Ny rows][Nx] of 8-byte elements, box 16 x Ny
+  bool w3_map_ok = false;
 };
 
 #define FFT_DISPATCH(LOG2N, ...)                                   \
@@ -814,8 +899,66 @@ static cudaError_t launch_real(const RealPassArgs& a, int log2n, cudaStream_t s)
                         k_fft_x_real<L><<<grid, kThreads, sm, s>>>(a); });
   return cudaGetLastError();
 }
+// inverse y pass: 0 = register-staged tiles (k_fft_strided<.,2>), 1 = TMA row copies (cp.async.bulk), 2 = one TMA
+// tensor-map request per tile (cp.async.bulk.tensor.2d), both double-buffered in persistent CTAs (IQB200_FFT_INV_TMA).
+// Measured on config 5 (FFT passes per simulation): 950 / 1005 / 963 ms -- the pass already moves 5.2 TB/s (ncu: DRAM
+// 63 % of its 8 TB/s scale, i.e. ~80 % of the measured copy bandwidth), so hiding the load latency buys nothing and the
+// persistent CTAs keep fewer tiles in flight than 5 resident register-staged CTAs.  Default: 0; bit-identical results.
+static int inv_tma_mode() {
+  const char* ev = std::getenv("IQB200_FFT_INV_TMA");
+  return ev ? std::atoi(ev) : 0;
+}
+
+// mode: 1 = N row copies per tile (cp.async.bulk), 2 = one tensor-map request per tile (cp.async.bulk.tensor.2d)
+template <int L, bool USE_MAP>
+static cudaError_t launch_strided_inv_tma_impl(const StridedArgs& a, int batch, const CUtensorMap& map, int rows_per_b,
+                                               int rows_per_pair, cudaStream_t s) {
+  constexpr int LPB = 16;
+  constexpr size_t kBuf = ((LPB * line_stride(L) * sizeof(float2) + 127) / 128) * 128;
+  const size_t sm = 2 * kBuf + (size_t)(1 << L) * sizeof(float2) + 128;
+  auto kern = k_fft_strided_inv_tma<L, USE_MAP>;
+  cudaError_t e = set_smem(kern, sm);
+  if (e != cudaSuccess) return e;
+  static int nsm = 0;
+  int ctas_per_sm = 0;
+  if (!nsm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kThreads, sm);
+  if (e != cudaSuccess) return e;
+  const int ntile_a = a.na / LPB;
+  const long long total = (long long)ntile_a * a.nb * batch;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(total, (long long)nsm * std::max(ctas_per_sm, 1)));
+  kern<<<grid, kThreads, sm, s>>>(a, ntile_a, (int)total, map, rows_per_b, rows_per_pair);
+  return cudaGetLastError();
+}
+
+template <int L>
+static cudaError_t launch_strided_inv_tma(const StridedArgs& a, int batch, int mode, const CUtensorMap* map, cudaStream_t s) {
+  if constexpr (inplace_ok(L) && lines_per_block(L) == 16) {
+    const int N = 1 << L;
+    if (mode == 2 && map) return launch_strided_inv_tma_impl<L, true>(a, batch, *map, (int)(a.in_sb / a.in_se), (int)(a.in_batch / a.in_se), s);
+    (void)N;
+    CUtensorMap none{};
+    return launch_strided_inv_tma_impl<L, false>(a, batch, none, 0, 0, s);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+}
+
 template <int MODE>
-static cudaError_t launch_strided(const StridedArgs& a_in, int log2n, int batch, cudaStream_t s) {
+static cudaError_t launch_strided(const StridedArgs& a_in, int log2n, int batch, cudaStream_t s, const CUtensorMap* map = nullptr) {
+  if (MODE == 2 && inv_tma_mode() > 0 && inplace_ok(log2n) && lines_per_block(log2n) == 16 && log2n >= 5 &&
+      a_in.nin == (1 << log2n) && a_in.flip == 0 && a_in.out_sa == 0 && a_in.na % 16 == 0 &&
+      ((a_in.in_se | a_in.in_sb | a_in.in_batch | a_in.out_se | a_in.out_sb | a_in.out_batch) & 1) == 0 &&
+      (long long)(a_in.na / 16) * a_in.nb * batch < (1ll << 31)) {
+    StridedArgs a = a_in;
+    a.batch = batch;
+    const int mode = (inv_tma_mode() == 2 && map && a.in_sb % a.in_se == 0 && a.in_batch % a.in_se == 0) ? 2 : 1;
+    FFT_DISPATCH(log2n, { return launch_strided_inv_tma<L>(a, batch, mode, map, s); });
+  }
   const size_t sm = smem_bytes(log2n, MODE == 1);
   const int LPB = lines_per_block(log2n);
   StridedArgs a = a_in;
@@ -947,6 +1090,27 @@ cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int 
     if (!p->zyfused && (e = iq::dmalloc((void**)&p->w3, mp * p->w3_stride * sizeof(float2))) != cudaSuccess) { plan_destroy(p); return e; }
   }
   p->workspace = mp * (p->w1_stride + p->w2_stride + p->w3_stride + p->w4_stride) * sizeof(float2);
+  // tensor map of w3 for the TMA-fed inverse y pass: rows = (pair, z, ky), 16-element boxes over all Ny rows of a plane
+  if (p->w3 && lines_per_block(p->ly) == 16 && p->Ny <= 256 && p->Nx % 16 == 0) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+        qres == cudaDriverEntryPointSuccess) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)Nx, (cuuint64_t)mp * (cuuint64_t)p->nzo * (cuuint64_t)Ny};
+      const cuuint64_t gstr[1] = {(cuuint64_t)Nx * sizeof(float2)};
+      const cuuint32_t box[2] = {16u, (cuuint32_t)Ny};
+      const cuuint32_t estr[2] = {1u, 1u};
+      const CUresult r = ((EncodeFn)fn)(&p->w3_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, p->w3, gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      p->w3_map_ok = (r == CUDA_SUCCESS);
+    } else {
+      cudaGetLastError();
+    }
+  }
   *out = p;
   return cudaSuccess;
 }
@@ -1096,7 +1260,7 @@ cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogu
     c.in_sb = Ny * Nx; c.in_se = Nx; c.in_batch = p->w3_stride;
     c.out_sb = (long long)p->nyo * Nx; c.out_se = Nx; c.out_batch = p->w4_stride;
     c.nin = (int)Ny; c.flip = 0; c.nout = p->nyo; c.na = (int)Nx; c.nb = p->nzo; c.tw = p->twy; c.scale = 1.f;
-    if ((e = launch_strided<2>(c, p->ly, npair, s)) != cudaSuccess) return e;
+    if ((e = launch_strided<2>(c, p->ly, npair, s, p->w3_map_ok ? &p->w3_map : nullptr)) != cudaSuccess) return e;
     nl += 3;
   }
   FinalArgs fa{p->w4, 0, p->nyo * p->nzo, p->nxo, p->npos, R, ep, p->twx};

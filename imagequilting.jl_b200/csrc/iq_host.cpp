@@ -342,7 +342,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     auto p2 = [](int n) { double v = 1; while (v < n) v *= 2; return v; };
     const double fftws = 8.0 * p2(G.n[0]) * ((double)G.t[2] * G.t[1] + (G.n[2] > 1 ? (double)G.t[2] * p2(G.n[1]) + 2.0 * G.dist[2] * p2(G.n[1]) : 0.0) +
                                               (double)G.dist[2] * G.dist[1]) / 2.0;
-    const double per_job = npos * 4.0 * (6.0 + 2.0 * S) + npos / 16.0 * 8.0 * (2.0 + S) + fftws + 6.0 * 17.0 * G.tilevol +
+    const double per_job = npos * 4.0 * (6.0 + 2.0 * S) + npos / 8.0 * 8.0 * (2.0 + S) + fftws + 6.0 * 17.0 * G.tilevol +
                            (2.0 + S) * 32768 * 12.0;
     size_t free_b = 0, total_b = 0;
     if (iq_device_free_memory(D->device, &free_b, &total_b) == IQ_OK) {

@@ -134,7 +134,7 @@ cudaError_t launch_a2map(const double* sat, int nx, int ny, int nz, const BoxDes
                          float* a2, int nxo, int nyo, int nzo, cudaStream_t s);
 cudaError_t launch_fill_u32(unsigned* p, unsigned v, long long n, cudaStream_t s);
 // All passes of a radix select (k_select_pass x nshift, with the compaction of the survivors after the second pass).
-// scratch: njobs + 1 ints of device memory (job list + count of the pass being launched)
+// scratch: 2 * njobs + 3 ints of device memory (job lists + counts of the pass being launched, zero-initialised)
 cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s,
                               int* launches, int* scratch);
 cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStream_t s);

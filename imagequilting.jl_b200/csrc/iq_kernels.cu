@@ -820,29 +820,43 @@ __device__ __forceinline__ int job_shift(const SelJob* J, const int* __restrict_
 
 // Grid = (blocks per job, jobs).  Inactive jobs (finished early, later relaxation rounds) return at once; the launcher
 // keeps the blocks per job low when there are many jobs so that such rows stay cheap.
-// Snapshot of the jobs a pass has to visit (mode 0: active ones; mode 1: those marked for the gather, compact == 2).
-// A separate launch, so that every CTA of the pass works from the same list; most launches of the later relaxation
-// rounds find it empty and then cost a few microseconds instead of a grid of tens of thousands of idle CTAs.
-__global__ void k_select_list(const SelJob* __restrict__ jobs, int njobs, int mode, int* __restrict__ list, int* __restrict__ count) {
-  __shared__ int s_n;
-  if (threadIdx.x == 0) s_n = 0;
+// Scratch of a select sequence: [0, njobs) active jobs, [njobs] their count, [njobs + 1, 2 njobs + 1) jobs marked for the
+// gather (compact == 2), [2 njobs + 1] their count, [2 njobs + 2] CTAs of the running pass that have finished.
+// Every CTA of a pass works from the same snapshot of the active jobs: it is rebuilt by the LAST CTA of the previous pass
+// (and by k_select_list before the first one), so the later relaxation rounds -- whose passes find the list empty --
+// cost a handful of near-empty launches instead of grids of tens of thousands of idle CTAs.
+__device__ void select_build_lists(const SelJob* jobs, int njobs, int* scratch) {
+  __shared__ int s_n[2];
+  if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
   __syncthreads();
-  for (int j0 = 0; j0 < njobs; j0 += blockDim.x) {  // ascending job order within a chunk is not needed: any order works
+  for (int j0 = 0; j0 < njobs; j0 += blockDim.x) {
     const int j = j0 + threadIdx.x;
-    const bool on = j < njobs && (mode == 0 ? jobs[j].active != 0 : (jobs[j].active != 0 && jobs[j].compact == 2));
-    if (on) list[atomicAdd(&s_n, 1)] = j;
+    if (j < njobs && ((volatile const SelJob*)jobs)[j].active != 0) {
+      scratch[atomicAdd(&s_n[0], 1)] = j;
+      if (((volatile const SelJob*)jobs)[j].compact == 2) scratch[njobs + 1 + atomicAdd(&s_n[1], 1)] = j;
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) *count = s_n;
+  if (threadIdx.x == 0) {
+    scratch[njobs] = s_n[0];
+    scratch[2 * njobs + 1] = s_n[1];
+    scratch[2 * njobs + 2] = 0;
+    __threadfence();
+  }
 }
 
-__global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, const int* __restrict__ list, const int* __restrict__ count,
-                                                     int nb, long long npos, const int* __restrict__ shifts, int nshift) {
-  __shared__ unsigned h[256];
+__global__ void k_select_list(const SelJob* __restrict__ jobs, int njobs, int* __restrict__ scratch) {
+  select_build_lists(jobs, njobs, scratch);
+}
+
+__global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, int* scratch, int nb, long long npos,
+                                                     const int* __restrict__ shifts, int nshift) {
+  __shared__ unsigned h[8][256];  // one histogram per warp: the digits of an adaptive first pass spread over all bins
   __shared__ int s_active, s_pass, s_last;
   __shared__ unsigned long long s_prefix, s_mask;
-  const int tid = threadIdx.x;
-  const int nwork = *count * nb;  // work item = (listed job, virtual block of nb)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int* list = scratch;
+  const int nwork = scratch[njobs] * nb;  // work item = (listed job, virtual block of nb)
   for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int vb = w % nb;
     SelJob* J = jobs + list[w / nb];
@@ -853,7 +867,8 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, const int* __
       s_prefix = J->prefix;
       s_mask = J->mask;
     }
-    h[tid] = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) h[q][tid] = 0;
     __syncthreads();
     if (!s_active) continue;
     int npass_job;
@@ -867,23 +882,42 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, const int* __
     // warp-aggregated histogram: distance values cluster in a few exponent bins, so per-lane shared-memory
     // atomics would serialise 32-way; lanes with the same bin elect one leader that adds their count
     const int lane = tid & 31;
-    for (long long i0 = (long long)vb * blockDim.x + (tid & ~31); i0 < n; i0 += (long long)nb * blockDim.x) {
-      const long long i = i0 + lane;
-      unsigned bin = 0xffffffffu;
-      if (i < n) {
-        const unsigned long long key = comp ? cbuf[i] : make_key_sub(map[i], i, sub);
-        if ((key & mask) == prefix) bin = (unsigned)(key >> shift) & 255u;
+    // four independent loads per thread and iteration (the pass streams whole maps: one 4-byte load in flight per
+    // thread reached 0.7 TB/s); the trip count is warp-uniform (the vote below needs every lane)
+    const long long stride = (long long)nb * blockDim.x;
+    const bool vote = s_pass == 0 && J->nv == 0;
+    for (long long i0 = (long long)vb * blockDim.x + (tid & ~31); i0 < n; i0 += 4 * stride) {
+      unsigned long long key[4];
+      bool in[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + u * stride + lane;
+        in[u] = i < n;
+        key[u] = 0;
+        if (in[u]) key[u] = comp ? cbuf[i] : make_key_sub(map[i], i, sub);
       }
-      if (s_pass == 0) {
-        // first digit (sign + high exponent bits): nearly every key falls into one or two bins -- aggregate per warp
-        const unsigned peers = __match_any_sync(0xffffffffu, bin);
-        if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
-      } else if (bin != 0xffffffffu) {
-        atomicAdd(&h[bin], 1u);  // later digits spread over the bins: plain shared-memory atomics are cheaper than the vote
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * stride >= n) break;  // warp-uniform
+        unsigned bin = 0xffffffffu;
+        if (in[u] && (key[u] & mask) == prefix) bin = (unsigned)(key[u] >> shift) & 255u;
+        if (vote) {
+          // first digit of the plain schedule (sign + high exponent bits): nearly every key falls into one or two bins --
+          // aggregate per warp
+          const unsigned peers = __match_any_sync(0xffffffffu, bin);
+          if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[warp][bin], (unsigned)__popc(peers));
+        } else if (bin != 0xffffffffu) {
+          atomicAdd(&h[warp][bin], 1u);  // digits that spread over the bins: plain shared-memory atomics are cheaper than the vote
+        }
       }
     }
     __syncthreads();
-    if (h[tid]) atomicAdd(&J->hist[tid], h[tid]);
+    {
+      unsigned tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot += h[q][tid];
+      if (tot) atomicAdd(&J->hist[tid], tot);
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == (unsigned)nb - 1u);
@@ -924,13 +958,22 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, const int* __
       __threadfence();
     }
   }
+  // the last CTA of the pass snapshots the jobs for the next launches (next pass / gather)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&scratch[2 * njobs + 2], 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) select_build_lists(jobs, njobs, scratch);
 }
 
 // Gathers the keys that match the decided prefix of every job marked by the second pass (compact == 2) into its
 // scratch list (order is irrelevant: keys are unique) and switches the job to list mode (compact = 1).
-__global__ void __launch_bounds__(256) k_select_compact(SelJob* jobs, const int* __restrict__ list, const int* __restrict__ count,
-                                                        int nb, long long npos) {
- const int nwork = *count * nb;
+__global__ void __launch_bounds__(256) k_select_compact(SelJob* jobs, int njobs, const int* __restrict__ scratch, int nb,
+                                                        long long npos) {
+ const int* list = scratch + njobs + 1;
+ const int nwork = scratch[2 * njobs + 1] * nb;
  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
   const int vb = w % nb;
   SelJob* J = jobs + list[w / nb];
@@ -940,20 +983,29 @@ __global__ void __launch_bounds__(256) k_select_compact(SelJob* jobs, const int*
   const float* __restrict__ map = J->map;
   unsigned long long* __restrict__ cbuf = J->cbuf;
   const int tid = threadIdx.x, lane = tid & 31;
-  for (long long i0 = (long long)vb * blockDim.x + (tid & ~31); i0 < npos; i0 += (long long)nb * blockDim.x) {
-    const long long i = i0 + lane;
-    unsigned long long key = 0;
-    bool hit = false;
-    if (i < npos) {
-      key = make_key_sub(map[i], i, sub);
-      hit = (key & mask) == prefix;
+  const long long stride = (long long)nb * blockDim.x;
+  for (long long i0 = (long long)vb * blockDim.x + (tid & ~31); i0 < npos; i0 += 4 * stride) {
+    unsigned long long key[4];
+    bool hit[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // four independent loads in flight
+      const long long i = i0 + u * stride + lane;
+      key[u] = 0;
+      hit[u] = false;
+      if (i < npos) {
+        key[u] = make_key_sub(map[i], i, sub);
+        hit[u] = (key[u] & mask) == prefix;
+      }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (bal) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(&J->ccount, (unsigned)__popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (hit) cbuf[base + __popc(bal & ((1u << lane) - 1u))] = key;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned bal = __ballot_sync(0xffffffffu, hit[u]);
+      if (bal) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&J->ccount, (unsigned)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit[u]) cbuf[base + __popc(bal & ((1u << lane) - 1u))] = key[u];
+      }
     }
   }
  }
@@ -978,22 +1030,20 @@ static int select_nb(int njobs, long long npos) {
 cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s,
                               int* launches, int* scratch) {
   const int nb = select_nb(njobs, npos);
-  int* list = scratch;
-  int* count = scratch + njobs;
-  const int grid = 148 * 4;  // persistent CTAs over (listed job, virtual block) work items
+  const int grid = 148 * 6;  // persistent CTAs over (listed job, virtual block) work items (8 KB of histograms each)
   int nl = 0;
+  k_select_list<<<1, 256, 0, s>>>(jobs, njobs, scratch);
+  ++nl;
   for (int pass = 0; pass < nshift; ++pass) {
-    k_select_list<<<1, 256, 0, s>>>(jobs, njobs, 0, list, count);
-    k_select_pass<<<grid, 256, 0, s>>>(jobs, list, count, nb, npos, shifts, nshift);
+    k_select_pass<<<grid, 256, 0, s>>>(jobs, njobs, scratch, nb, npos, shifts, nshift);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    nl += 2;
+    ++nl;
     if (pass <= 1 && nshift > 3) {  // gather point of adaptive jobs (after pass 0) and of plain ones (after pass 1)
-      k_select_list<<<1, 256, 0, s>>>(jobs, njobs, 1, list, count);
-      k_select_compact<<<grid, 256, 0, s>>>(jobs, list, count, nb, npos);
+      k_select_compact<<<grid, 256, 0, s>>>(jobs, njobs, scratch, nb, npos);
       k_select_compact_done<<<(njobs + 127) / 128, 128, 0, s>>>(jobs, njobs);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
-      nl += 3;
+      nl += 2;
     }
   }
   if (launches) *launches += nl;

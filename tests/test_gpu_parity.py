@@ -391,7 +391,8 @@ def test_iqsim_device_cut_equals_host_cut():
         assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("env", [{"IQB200_FFT_ZYFUSED": "1"}, {"IQB200_FFT_TMA": "1"}, {"IQB200_FFT_ZDIRECT": "0"}])
+@pytest.mark.parametrize("env", [{"IQB200_FFT_ZYFUSED": "1"}, {"IQB200_FFT_TMA": "1"}, {"IQB200_FFT_ZDIRECT": "0"},
+                                 {"IQB200_FFT_INV_TMA": "2"}, {"IQB200_FFT_INV_TMA": "1"}])
 def test_experimental_fft_variants_give_the_same_maps(env):
     """The opt-in FFT variants (fused z/y kernel, TMA double-buffered last pass, z transforms instead of the direct z
     pass) are alternative schedules of the same arithmetic: their distance maps must match the default path within
@@ -418,7 +419,7 @@ def test_experimental_fft_variants_give_the_same_maps(env):
     outs = []
     for extra in ({}, env):
         e = dict(os.environ)
-        for k in ("IQB200_FFT_ZYFUSED", "IQB200_FFT_TMA", "IQB200_FFT_ZDIRECT"):
+        for k in ("IQB200_FFT_ZYFUSED", "IQB200_FFT_TMA", "IQB200_FFT_ZDIRECT", "IQB200_FFT_INV_TMA"):
             e.pop(k, None)
         e.update(extra)
         path = os.path.join("/tmp", "iq_variant_%d_%s.npy" % (os.getpid(), "x" if extra else "d"))
@@ -431,3 +432,6 @@ def test_experimental_fft_variants_give_the_same_maps(env):
     assert np.allclose(d0, d1, rtol=1e-4, atol=1e-6 * scale)
     for a, b in zip(c0, c1):  # candidate sets identical except for a tie at the threshold inside that tolerance
         assert len(set(a) ^ set(b)) <= 1
+    if "IQB200_FFT_INV_TMA" in env:  # the TMA-fed inverse passes (2: one tensor-map request per tile; 1: row copies)
+        # are the same arithmetic as the register-staged default
+        assert np.array_equal(d0, d1)
