@@ -409,6 +409,7 @@ def main():
         "gpu_launches": int(sum(s["stats"]["kernel_launches"] for s in stats)),
         "roofline": roof,
         "pipeline": "device-resident (iq_sim_*)" if is_resident else "host-staged (iq_search_pick per step)",
+        "resident_status": int(max(s["stats"]["resident_status"] for s in stats)),  # != 0: a resident attempt was redone host-staged
         "breakdown_ms_per_step": {k: sum(s["stats"][k] for s in stats) / args.steps
                                   for k in ("search_ms", "search_device_ms", "cut_ms", "setup_ms", "total_ms", "device_ms",
                                             "select_ms", "cut_device_ms", "fetch_ms", "run_ms", "teardown_ms")},

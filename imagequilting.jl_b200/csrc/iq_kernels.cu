@@ -856,10 +856,12 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, in
   __shared__ unsigned long long s_prefix, s_mask;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int* list = scratch;
-  const int nwork = scratch[njobs] * nb;  // work item = (listed job, virtual block of nb)
+  const int nact = scratch[njobs];
+  const int nwork = nact * nb;  // work item = (listed job, virtual block of nb), job fastest: the few blocks a short
+                                // survivor list needs (vb < nbe below) are then spread over all CTAs
   for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-    const int vb = w % nb;
-    SelJob* J = jobs + list[w / nb];
+    const int vb = w / nact;
+    SelJob* J = jobs + list[w % nact];
     __syncthreads();  // the previous item's shared state is dead
     if (tid == 0) {
       s_active = J->active;
@@ -879,12 +881,16 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, in
     const bool comp = J->compact != 0;  // scan the compacted survivors instead of the map
     const unsigned long long* __restrict__ cbuf = J->cbuf;
     const long long n = comp ? (long long)J->ccount : npos;
+    // a short survivor list does not need all nb virtual blocks: every block has a fixed cost (state loads, histogram
+    // clear / merge, ticket) that dominated the list passes (650 us per pass for 128 jobs x 148 blocks on ~1 MB of keys)
+    const int nbe = comp ? (int)max(1ll, min((long long)nb, (n + 8191) / 8192)) : nb;
+    if (vb >= nbe) continue;
     // warp-aggregated histogram: distance values cluster in a few exponent bins, so per-lane shared-memory
     // atomics would serialise 32-way; lanes with the same bin elect one leader that adds their count
     const int lane = tid & 31;
     // four independent loads per thread and iteration (the pass streams whole maps: one 4-byte load in flight per
     // thread reached 0.7 TB/s); the trip count is warp-uniform (the vote below needs every lane)
-    const long long stride = (long long)nb * blockDim.x;
+    const long long stride = (long long)nbe * blockDim.x;
     const bool vote = s_pass == 0 && J->nv == 0;
     for (long long i0 = (long long)vb * blockDim.x + (tid & ~31); i0 < n; i0 += 4 * stride) {
       unsigned long long key[4];
@@ -920,7 +926,7 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, in
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == (unsigned)nb - 1u);
+    if (tid == 0) s_last = (atomicAdd(&J->ticket, 1u) == (unsigned)nbe - 1u);
     __syncthreads();
     if (!s_last) continue;
     if (tid == 0) {
@@ -973,10 +979,11 @@ __global__ void __launch_bounds__(256) k_select_pass(SelJob* jobs, int njobs, in
 __global__ void __launch_bounds__(256) k_select_compact(SelJob* jobs, int njobs, const int* __restrict__ scratch, int nb,
                                                         long long npos) {
  const int* list = scratch + njobs + 1;
- const int nwork = scratch[2 * njobs + 1] * nb;
+ const int nact = scratch[2 * njobs + 1];
+ const int nwork = nact * nb;
  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-  const int vb = w % nb;
-  SelJob* J = jobs + list[w / nb];
+  const int vb = w / nact;
+  SelJob* J = jobs + list[w % nact];
   if (!J->active || J->compact != 2) continue;
   const unsigned long long prefix = J->prefix, mask = J->mask;
   const unsigned sub = J->sub;
