@@ -20,6 +20,8 @@ c_double_p = C.POINTER(C.c_double)
 c_u8_p = C.POINTER(C.c_uint8)
 c_i32_p = C.POINTER(C.c_int32)
 c_i64_p = C.POINTER(C.c_int64)
+c_u32_p = C.POINTER(C.c_uint32)
+c_u64_p = C.POINTER(C.c_uint64)
 
 
 class IqCtxDesc(C.Structure):
@@ -95,6 +97,10 @@ SYMBOLS = {
     "iq_slice_distance": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqTile), C.c_int32, c_float_p]),
     "iq_slice_select": (C.c_int32, [C.c_void_p, C.c_double, c_float_p, c_i64_p]),
     "iq_slice_candidates": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(c_i64_p), C.POINTER(c_float_p)]),
+    "iq_slice_minmax": (C.c_int32, [C.c_void_p, C.c_int32, c_u32_p, c_u32_p]),
+    "iq_slice_hist": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_i32_p, c_i32_p, c_u32_p, c_i64_p]),
+    "iq_slice_kth": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, c_u64_p]),
+    "iq_slice_pick": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_u64_p, c_i64_p]),
     "iq_taumodel": (C.c_int32, [C.c_int64, C.c_int32, c_float_p, c_double_p]),
     "iq_sample": (C.c_int32, [c_double_p, C.c_int64, C.c_double, c_i64_p]),
     "iq_cut_batch": (C.c_int32, [C.c_void_p, C.POINTER(IqCutTask), C.c_int32, c_i32_p]),

@@ -138,6 +138,22 @@ def _prepare(img):
     return out, nan
 
 
+def _prepare_soft(soft, padsize):
+    """imagepreproc of the soft data (src/utils.jl:74-89): auxiliary variable padded symmetrically to the padded grid with
+    NaN -> 0, auxiliary training image prepared like the training image.  -> ([aux_pad], [aux_ti]) in FP32."""
+    aux_pad, aux_ti = [], []
+    for aux, auxTI in soft:
+        a = np.asarray(aux.filled(np.nan) if isinstance(aux, np.ma.MaskedArray) else aux, dtype=np.float64)
+        append = tuple(p - min(p, s) for p, s in zip(padsize, a.shape))
+        a = np.pad(a, [(0, ap) for ap in append], mode="symmetric")
+        a = a[tuple(slice(0, p) for p in padsize)]
+        a = np.where(np.isnan(a), 0.0, a)
+        aux_pad.append(_f(a, np.float32))
+        at, _ = _prepare(auxTI)
+        aux_ti.append(_f(at, np.float32))
+    return aux_pad, aux_ti
+
+
 def _unprepare_nonfloat(res, dtype):
     """NaN -> missing and back to the input element type: Array{Union{Missing,T}} (src/utils.jl:104-113) as a numpy
     masked array of dtype T."""
@@ -296,16 +312,7 @@ def iqsim(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), hard=None,
     ti32 = _f(TI, np.float32)
     ti64 = None if TI.dtype == np.float32 else _f(TI, np.float64)
     disabled = _finddisabled(nanmask, geo)
-    aux_pad, aux_ti = [], []
-    for aux, auxTI in soft:
-        a = np.asarray(aux.filled(np.nan) if isinstance(aux, np.ma.MaskedArray) else aux, dtype=np.float64)
-        append = tuple(p - min(p, s) for p, s in zip(padsize, a.shape))
-        a = np.pad(a, [(0, ap) for ap in append], mode="symmetric")
-        a = a[tuple(slice(0, p) for p in padsize)]
-        a = np.where(np.isnan(a), 0.0, a)
-        aux_pad.append(_f(a, np.float32))
-        at, _ = _prepare(auxTI)
-        aux_ti.append(_f(at, np.float32))
+    aux_pad, aux_ti = _prepare_soft(soft, padsize)
 
     # hard data as dense grids over the padded domain
     hard_has = hard_val = hard_nan = None
@@ -518,6 +525,7 @@ class SearchContext:
         self.tilevol = int(np.prod(self.tilesize))
         self._ti = _f(ti, np.float32)
         self._aux = [_f(a, np.float32) for a in auxti]
+        self.nsoft = len(self._aux)
         self._disabled = None if disabled is None else _f(np.asarray(disabled).astype(np.uint8), np.uint8)
         d = IqCtxDesc()
         d.ndim = self.N
@@ -614,14 +622,15 @@ class SearchContext:
                             dmin=float(res[i].dmin)))
         return out
 
-    def slice_distance(self, ovlmask, simdevs):
-        """Phase 1 of a position-slice search: overlap distances of the local positions -> local minima."""
+    def slice_distance(self, ovlmask, simdevs, softdevs=None):
+        """Phase 1 of a position-slice search: overlap (and soft) distances of the local positions -> local minima of the
+        overlap distance."""
         m = _f(np.asarray(ovlmask).astype(np.uint8), np.uint8)
         n = len(simdevs)
         arr = (IqTile * n)()
         keep = []
         for i, sd in enumerate(simdevs):
-            t, k = self._tile(sd)
+            t, k = self._tile(sd, softdev=softdevs[i] if softdevs else ())
             arr[i] = t
             keep.append(k)
         out = np.zeros(n, dtype=np.float32)
@@ -641,6 +650,46 @@ class SearchContext:
             out.append((np.ctypeslib.as_array(pi, shape=(n,)).copy() if n else np.zeros(0, np.int64),
                         np.ctypeslib.as_array(pv, shape=(n,)).copy() if n else np.zeros(0, np.float32)))
         return out
+
+    def slice_minmax(self, tile=0):
+        """Float bits of the local [min, max] of every source (0 = overlap, 1 + i = soft i) after slice_distance."""
+        n = 1 + self.nsoft
+        lo, hi = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        check(lib().iq_slice_minmax(self._h, int(tile), _ptr(lo, _lib.c_u32_p), _ptr(hi, _lib.c_u32_p)))
+        return lo, hi
+
+    def slice_hist(self, reqs, tile=0):
+        """Local digit histograms: reqs = [(source, level, prefix)] -> int64 [len(reqs), 256] (iq_slice_hist)."""
+        out = np.zeros((len(reqs), 256), dtype=np.int64)
+        for c0 in range(0, len(reqs), 8):
+            part = reqs[c0:c0 + 8]
+            src = np.array([r[0] for r in part], dtype=np.int32)
+            lev = np.array([r[1] for r in part], dtype=np.int32)
+            pre = np.array([r[2] for r in part], dtype=np.uint32)
+            h = np.zeros((len(part), 256), dtype=np.int64)
+            check(lib().iq_slice_hist(self._h, int(tile), len(part), _ptr(src, c_i32_p), _ptr(lev, c_i32_p),
+                                      _ptr(pre, _lib.c_u32_p), _ptr(h, c_i64_p)))
+            out[c0:c0 + len(part)] = h
+        return out
+
+    def slice_kth(self, src, k_local, tile=0):
+        """Local k-th smallest (value bits << 32 | position) key of a source (iq_slice_kth)."""
+        key = C.c_uint64(0)
+        check(lib().iq_slice_kth(self._h, int(tile), int(src), int(k_local), C.byref(key)))
+        return int(key.value)
+
+    def slice_pick(self, kth, tile=0):
+        """Local candidates with key <= kth[s] in every source -> (idx int64 [n], values float32 [nsrc, n])."""
+        k = np.array([int(v) for v in kth], dtype=np.uint64)
+        cnt = C.c_int64(0)
+        check(lib().iq_slice_pick(self._h, int(tile), int(k.size), _ptr(k, _lib.c_u64_p), C.byref(cnt)))
+        n = int(cnt.value)
+        if n == 0:
+            return np.zeros(0, np.int64), np.zeros((k.size, 0), np.float32)
+        pi, pv = c_i64_p(), c_float_p()
+        check(lib().iq_slice_candidates(self._h, int(tile), C.byref(pi), C.byref(pv)))
+        return (np.ctypeslib.as_array(pi, shape=(n,)).copy(),
+                np.ctypeslib.as_array(pv, shape=(int(k.size), n)).copy())
 
     def cut_batch(self, slabs):
         """Device boundary cuts (iq_cut_batch): slabs = [(A, B, dim), ...] -> ([keep masks], [sweeps])."""

@@ -965,6 +965,8 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
   cudaFree(c->d_cand_val);
   if (c->h_cand_idx) cudaFreeHost(c->h_cand_idx);
   if (c->h_cand_val) cudaFreeHost(c->h_cand_val);
+  cudaFree(c->d_slice_hist);
+  if (c->h_slice_hist) cudaFreeHost(c->h_slice_hist);
   cudaFree(c->d_shifts);
   cudaFree(c->d_fetch);
   if (c->h_cut) cudaFreeHost(c->h_cut);
@@ -1291,27 +1293,41 @@ int32_t iq_fetch_tile(iq_ctx* c, int64_t pos, float* out_tile) {
 int32_t iq_slice_distance(iq_ctx* c, const uint8_t* ovlmask, const iq_tile* tiles, int32_t ntile, float* dmin_local) {
   if (!c || !ovlmask || !tiles || !dmin_local || ntile <= 0) return fail(IQ_ERR_INVALID, "iq_slice_distance: bad argument");
   if (ntile > c->max_batch) return fail(IQ_ERR_INVALID, "iq_slice_distance: ntile exceeds max_batch");
-  if (c->nsoft > 0) return fail(IQ_ERR_INVALID, "position-slice mode supports the threshold path only (no soft data)");
-  for (int i = 0; i < ntile; ++i)
+  const int S = c->nsoft;
+  for (int i = 0; i < ntile; ++i) {
     if (!tiles[i].simdev || tiles[i].hard_nnz > 0) return fail(IQ_ERR_INVALID, "position-slice mode: simdev required, hard data unsupported");
+    for (int s = 0; s < S; ++s)
+      if (!tiles[i].softdev || !tiles[i].softdev[s]) return fail(IQ_ERR_INVALID, "tile %d lacks softdev[%d]", i, s);
+  }
   CK(cudaSetDevice(c->device));
   MaskEntry* e = nullptr;
   int rc = get_mask(c, ovlmask, &e);
   if (rc) return rc;
   const int rb = pick_rb(c, ntile);
   const int ngrp = (ntile + rb - 1) / rb;
-  rc = stage_reserve(c, 8192 + (size_t)ngrp * rb * e->tmpl_floats * sizeof(float) + (size_t)ntile * (c->tilevol * sizeof(float) + 64));
+  size_t need = 8192 + (size_t)ngrp * rb * e->tmpl_floats * sizeof(float) + (size_t)ntile * (c->tilevol * sizeof(float) + 64);
+  need += (size_t)(1 + S) * ((size_t)ntile * c->tilevol * sizeof(float) + 1024);
+  if (S > 0) need += (size_t)S * ((size_t)ngrp * rb * c->full_mask->tmpl_floats * sizeof(float) + ntile * sizeof(double) + 512);
+  rc = stage_reserve(c, need);
   if (rc) return rc;
   c->stage_used = 0;
   c->dist_ev_used = 0;
-  CK(iq::launch_fill_u32(c->d_minmax, 0x7f800000u, c->max_batch, c->stream));
-  CK(iq::launch_fill_u32(c->d_minmax + c->max_batch, 0u, c->max_batch, c->stream));
-  c->launches += 2;
+  const int nkind = 2 + S;
+  for (int k = 0; k < nkind; ++k) {
+    CK(iq::launch_fill_u32(c->d_minmax + (size_t)(k * 2 + 0) * c->max_batch, 0x7f800000u, c->max_batch, c->stream));
+    CK(iq::launch_fill_u32(c->d_minmax + (size_t)(k * 2 + 1) * c->max_batch, 0u, c->max_batch, c->stream));
+    c->launches += 2;
+  }
   std::vector<const float*> kern(ntile);
   for (int r = 0; r < ntile; ++r) kern[r] = tiles[r].simdev;
   rc = run_dense(c, e, -1, kern.data(), ntile, c->d_Dovl, 0);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, (size_t)2 * c->max_batch * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  for (int s = 0; s < S; ++s) {  // soft-data distances of the slab (src/iqsim.jl:222-227)
+    for (int r = 0; r < ntile; ++r) kern[r] = tiles[r].softdev[s];
+    rc = run_dense(c, c->full_mask, s, kern.data(), ntile, c->d_Dsoft[s], 2 + s);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, (size_t)nkind * 2 * c->max_batch * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   for (int r = 0; r < ntile; ++r) std::memcpy(&dmin_local[r], &c->h_minmax[r], 4);
   c->slice_ntile = ntile;
@@ -1380,6 +1396,129 @@ int32_t iq_slice_select(iq_ctx* c, double tol, const float* dmin_global, int64_t
     counts[r] = (int64_t)n;
     o += n;
   }
+  return IQ_OK;
+}
+
+// ---- relaxation path of position-slice mode ----
+static const float* slice_src(const iq_ctx* c, int tile, int src) {
+  return (src == 0 ? c->d_Dovl : c->d_Dsoft[src - 1]) + (size_t)tile * c->npos;
+}
+
+int32_t iq_slice_minmax(iq_ctx* c, int32_t tile, uint32_t* minbits, uint32_t* maxbits) {
+  if (!c || !minbits || !maxbits) return fail(IQ_ERR_INVALID, "iq_slice_minmax: NULL argument");
+  if (tile < 0 || tile >= c->slice_ntile) return fail(IQ_ERR_STATE, "iq_slice_minmax without a preceding iq_slice_distance");
+  for (int s = 0; s <= c->nsoft; ++s) {
+    const int kind = s == 0 ? 0 : 1 + s;
+    minbits[s] = c->h_minmax[(size_t)(kind * 2 + 0) * c->max_batch + tile];
+    maxbits[s] = c->h_minmax[(size_t)(kind * 2 + 1) * c->max_batch + tile];
+  }
+  return IQ_OK;
+}
+
+int32_t iq_slice_hist(iq_ctx* c, int32_t tile, int32_t nreq, const int32_t* src, const int32_t* level, const uint32_t* prefix,
+                      int64_t* hist) {
+  if (!c || !src || !level || !prefix || !hist) return fail(IQ_ERR_INVALID, "iq_slice_hist: NULL argument");
+  if (tile < 0 || tile >= c->slice_ntile) return fail(IQ_ERR_STATE, "iq_slice_hist without a preceding iq_slice_distance");
+  if (nreq <= 0 || nreq > 8) return fail(IQ_ERR_INVALID, "iq_slice_hist: 1..8 requests per call");
+  CK(cudaSetDevice(c->device));
+  if (!c->d_slice_hist) {
+    CK(iq::dmalloc((void**)&c->d_slice_hist, 8 * 256 * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void**)&c->h_slice_hist, 8 * 256 * sizeof(unsigned long long)));
+  }
+  iq::SliceHistParams P{};
+  for (int i = 0; i < nreq; ++i) {
+    if (src[i] < 0 || src[i] > c->nsoft || level[i] < 0 || level[i] > 3) return fail(IQ_ERR_INVALID, "iq_slice_hist: bad source or level");
+    P.req[i].map = slice_src(c, tile, src[i]);
+    P.req[i].level = level[i];
+    P.req[i].prefix = prefix[i];
+  }
+  P.nreq = nreq;
+  P.npos = c->npos;
+  P.out = c->d_slice_hist;
+  CK(cudaMemsetAsync(c->d_slice_hist, 0, (size_t)nreq * 256 * sizeof(unsigned long long), c->stream));
+  CK(iq::launch_slice_hist(P, c->stream));
+  c->launches++;
+  CK(cudaMemcpyAsync(c->h_slice_hist, c->d_slice_hist, (size_t)nreq * 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nreq * 256; ++i) hist[i] = (int64_t)c->h_slice_hist[i];
+  return IQ_OK;
+}
+
+int32_t iq_slice_kth(iq_ctx* c, int32_t tile, int32_t src, int64_t k_local, uint64_t* key) {
+  if (!c || !key) return fail(IQ_ERR_INVALID, "iq_slice_kth: NULL argument");
+  if (tile < 0 || tile >= c->slice_ntile) return fail(IQ_ERR_STATE, "iq_slice_kth without a preceding iq_slice_distance");
+  if (src < 0 || src > c->nsoft || k_local < 1 || k_local > c->npos) return fail(IQ_ERR_INVALID, "iq_slice_kth: bad source or rank");
+  CK(cudaSetDevice(c->device));
+  iq::SelJob& sj = c->h_sel[0];
+  std::memset(&sj, 0, sizeof sj);
+  sj.map = slice_src(c, tile, src);
+  sj.k = (unsigned long long)k_local;
+  sj.active = 1;
+  sj.cbuf = c->d_selbuf;
+  sj.ccap = c->sel_cap;
+  CK(cudaMemcpyAsync(c->d_sel, c->h_sel, sizeof(iq::SelJob), cudaMemcpyHostToDevice, c->stream));
+  int nl = 0;
+  CK(iq::launch_select_all(c->d_sel, 1, c->npos, c->d_shifts, c->nshift, c->stream, &nl, c->d_sel_list));
+  c->launches += nl;
+  CK(cudaMemcpyAsync(c->h_sel, c->d_sel, sizeof(iq::SelJob), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *key = (uint64_t)c->h_sel[0].kth;
+  return IQ_OK;
+}
+
+int32_t iq_slice_pick(iq_ctx* c, int32_t tile, int32_t nsrc, const uint64_t* kth, int64_t* count) {
+  if (!c || !kth || !count) return fail(IQ_ERR_INVALID, "iq_slice_pick: NULL argument");
+  if (tile < 0 || tile >= c->slice_ntile) return fail(IQ_ERR_STATE, "iq_slice_pick without a preceding iq_slice_distance");
+  if (nsrc < 1 || nsrc > 1 + c->nsoft) return fail(IQ_ERR_INVALID, "iq_slice_pick: bad number of sources");
+  CK(cudaSetDevice(c->device));
+  const int maxS = c->max_src;
+  for (int s = 0; s < nsrc; ++s) {
+    iq::SelJob& sj = c->h_sel[(size_t)tile * maxS + s];
+    std::memset(&sj, 0, sizeof sj);
+    sj.kth = (unsigned long long)kth[s];
+  }
+  CK(cudaMemcpyAsync(c->d_sel + (size_t)tile * maxS, c->h_sel + (size_t)tile * maxS, (size_t)nsrc * sizeof(iq::SelJob),
+                     cudaMemcpyHostToDevice, c->stream));
+  iq::PickJob& J = c->h_pick[tile];
+  std::memset(&J, 0, sizeof J);
+  J.mode = 1;
+  J.nsrc = nsrc;
+  for (int s = 0; s < nsrc; ++s) J.src[s] = slice_src(c, tile, s);
+  J.sel = c->d_sel + (size_t)tile * maxS;
+  J.blockcount = c->d_blockcount + (size_t)tile * iq::pick_nblk(c->npos);
+  J.total = c->d_total + tile;
+  J.cand_idx = c->d_cand_idx + (size_t)tile * c->npos;
+  J.cand_val = c->d_cand_val + (size_t)tile * maxS * c->npos;
+  J.cap = c->npos;
+  CK(cudaMemcpyAsync(c->d_pick + tile, &J, sizeof(iq::PickJob), cudaMemcpyHostToDevice, c->stream));
+  CK(iq::launch_pick_count(c->d_pick + tile, 1, c->npos, c->stream));
+  CK(iq::launch_pick_write(c->d_pick + tile, 1, c->npos, c->stream));
+  c->launches += 2;
+  CK(cudaMemcpyAsync(c->h_total + tile, c->d_total + tile, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const size_t n = c->h_total[tile];
+  if (n > c->h_cand_cap) {
+    if (c->h_cand_idx) cudaFreeHost(c->h_cand_idx);
+    if (c->h_cand_val) cudaFreeHost(c->h_cand_val);
+    c->h_cand_idx = nullptr; c->h_cand_val = nullptr;
+    const size_t cap = std::max<size_t>(n * 2, 1 << 16);
+    CK(cudaMallocHost((void**)&c->h_cand_idx, cap * sizeof(unsigned)));
+    CK(cudaMallocHost((void**)&c->h_cand_val, cap * maxS * sizeof(float)));
+    c->h_cand_cap = cap;
+  }
+  if (n) {
+    CK(cudaMemcpyAsync(c->h_cand_idx, J.cand_idx, n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    for (int s = 0; s < nsrc; ++s)
+      CK(cudaMemcpyAsync(c->h_cand_val + (size_t)s * n, J.cand_val + (size_t)s * c->npos, n * sizeof(float), cudaMemcpyDeviceToHost,
+                         c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  if ((int)c->slice_idx.size() <= tile) { c->slice_idx.resize(tile + 1); c->slice_val.resize(tile + 1); }
+  c->slice_idx[tile].resize(n);
+  for (size_t i = 0; i < n; ++i) c->slice_idx[tile][i] = (int64_t)c->h_cand_idx[i];
+  c->slice_val[tile].assign(c->h_cand_val, c->h_cand_val + n * (size_t)nsrc);  // [source][candidate]
+  *count = (int64_t)n;
   return IQ_OK;
 }
 

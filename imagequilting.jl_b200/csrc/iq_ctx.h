@@ -116,6 +116,8 @@ struct iq_ctx {
   std::vector<std::vector<int64_t>> slice_idx;
   std::vector<std::vector<float>> slice_val;
   int slice_ntile = 0;
+  unsigned long long* d_slice_hist = nullptr;  // [8][256] digit histograms of iq_slice_hist
+  unsigned long long* h_slice_hist = nullptr;  // page-locked
   char* h_cut = nullptr;  // pinned staging of the device boundary cut (slabs, masks, task records)
   char* d_cut = nullptr;
   size_t cut_cap = 0;

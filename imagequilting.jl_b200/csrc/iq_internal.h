@@ -137,6 +137,19 @@ cudaError_t launch_fill_u32(unsigned* p, unsigned v, long long n, cudaStream_t s
 // scratch: 2 * njobs + 3 ints of device memory (job lists + counts of the pass being launched, zero-initialised)
 cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int* shifts, int nshift, cudaStream_t s,
                               int* launches, int* scratch);
+// position-slice mode: digit histograms of the value bits of up to 8 local maps (k_slice_hist)
+struct SliceHistReq {
+  const float* map;
+  unsigned prefix;  // value of the `level` higher digits (bits >> (32 - 8 level))
+  int level;        // 0..3: digit = (bits >> (24 - 8 level)) & 255
+};
+struct SliceHistParams {
+  SliceHistReq req[8];
+  int nreq;
+  long long npos;
+  unsigned long long* out;  // [nreq][256], zeroed by the caller
+};
+cudaError_t launch_slice_hist(const SliceHistParams& P, cudaStream_t s);
 cudaError_t launch_pick_count(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
 cudaError_t launch_pick_write(PickJob* jobs, int njobs, long long npos, cudaStream_t s);
 // Threshold selection driven by chunk minima (chunk = chunklen consecutive positions): only chunks whose minimum

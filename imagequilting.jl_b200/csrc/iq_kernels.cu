@@ -1058,6 +1058,45 @@ cudaError_t launch_select_all(SelJob* jobs, int njobs, long long npos, const int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Position-slice mode (second axis), relaxation path: one 8-bit digit histogram of the VALUE bits of a
+// local map slab, restricted to the values whose higher digits equal `prefix`.  The host sums the histograms of all
+// ranks (all-gather), which turns the radix select of relaxation.jl:12,27 into a select over every slab at once; ties
+// on the k-th value are resolved by position with a local select (iq_slice_kth), the slabs being ordered by rank.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_slice_hist(const SliceHistParams P) {
+  const SliceHistReq rq = P.req[blockIdx.y];
+  __shared__ unsigned h[8][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const int hi_shift = 32 - 8 * rq.level;  // bits above the current digit (level 0: none)
+  const int shift = 24 - 8 * rq.level;
+  for (long long q = (long long)blockIdx.x * 256; q < P.npos; q += (long long)gridDim.x * 256) {  // block-uniform trip count
+    const long long p = q + tid;
+    unsigned bin = 0xffffffffu;
+    if (p < P.npos) {
+      const unsigned bits = __float_as_uint(rq.map[p]);
+      if (rq.level == 0 || (bits >> hi_shift) == rq.prefix) bin = (bits >> shift) & 255u;
+    }
+    // neighbouring positions carry similar distances: aggregate equal bins of a warp before the shared-memory atomic
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[warp][bin], (unsigned)__popc(peers));
+  }
+  __syncthreads();
+  unsigned t = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += h[w][tid];
+  if (t) atomicAdd(&P.out[(size_t)blockIdx.y * 256 + tid], (unsigned long long)t);
+}
+
+cudaError_t launch_slice_hist(const SliceHistParams& P, cudaStream_t s) {
+  long long nb = (P.npos + 256 * 16 - 1) / (256 * 16);
+  nb = std::max<long long>(1, std::min<long long>(nb, 148 * 4));
+  k_slice_hist<<<dim3((unsigned)nb, P.nreq), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // candidate predicate + ordered compaction
 // ------------------------------------------------------------------------------------------------
 constexpr int kPickChunk = 4096;  // positions per CTA (256 threads x 16)

@@ -136,11 +136,27 @@ int32_t iq_fetch_tile(iq_ctx* ctx, int64_t pos, float* out_tile);
  * A tile search becomes: iq_slice_distance on every rank (overlap distance + local minimum) -> the host
  * all-reduces the minimum -> iq_slice_select with the global minimum (threshold rule of src/iqsim.jl:237 on the
  * local positions) -> the host all-gathers the short candidate lists (local index + offset of the slab) and
- * evaluates the tau model (iq_taumodel) and the sampling walk (iq_sample) on the merged list.  Threshold path only
- * (no soft / hard data).  Buffers handed out by iq_slice_candidates stay valid until the next iq_slice_* call. */
+ * evaluates the tau model (iq_taumodel) and the sampling walk (iq_sample) on the merged list.  No hard data.
+ * Buffers handed out by iq_slice_candidates stay valid until the next iq_slice_* call. */
 int32_t iq_slice_distance(iq_ctx* ctx, const uint8_t* ovlmask, const iq_tile* tiles, int32_t ntile, float* dmin_local);
 int32_t iq_slice_select(iq_ctx* ctx, double tol, const float* dmin_global, int64_t* counts);
 int32_t iq_slice_candidates(const iq_ctx* ctx, int32_t tile, const int64_t** idx, const float** val);
+/* Relaxation path of position-slice mode (contexts with auxiliary images; src/relaxation.jl:5-48 with every k-th key
+ * selected over ALL slabs, SURVEY 8(e) "all-reduce of radix histograms").  Sources: 0 = overlap distance, 1 + i = soft
+ * distance i (iq_slice_distance computes them from tile->softdev).
+ *   iq_slice_minmax  float bits of the local [min, max] of every source (all-zero test of relaxation.jl:11)
+ *   iq_slice_hist    for up to 8 requests: local 256-bin histogram of digit `level` (0 = top byte) of the VALUE bits of
+ *                    a source, restricted to the values whose `level` higher digits equal `prefix`; the host sums the
+ *                    histograms of all ranks, picks the bin that holds the k-th value and descends (4 levels)
+ *   iq_slice_kth     ties on the k-th value are broken by position (partialsortperm, relaxation.jl:12,27): the rank whose
+ *                    slab holds the k-th entry selects its local k_local-th smallest (value, position) key exactly
+ *   iq_slice_pick    local candidates = positions whose key (value bits << 32 | local position) is <= kth[s] in every
+ *                    source s < nsrc; iq_slice_candidates then returns idx[count] and val[source][count] */
+int32_t iq_slice_minmax(iq_ctx* ctx, int32_t tile, uint32_t* minbits, uint32_t* maxbits);
+int32_t iq_slice_hist(iq_ctx* ctx, int32_t tile, int32_t nreq, const int32_t* src, const int32_t* level, const uint32_t* prefix,
+                      int64_t* hist);
+int32_t iq_slice_kth(iq_ctx* ctx, int32_t tile, int32_t src, int64_t k_local, uint64_t* key);
+int32_t iq_slice_pick(iq_ctx* ctx, int32_t tile, int32_t nsrc, const uint64_t* kth, int64_t* count);
 /* Host FP64 pieces exposed for hosts that merge candidate lists themselves: taumodel (src/taumodel.jl:5-45) on
  * vals[source][candidate] and the StatsBase.sample walk (src/iqsim.jl:243). */
 int32_t iq_taumodel(int64_t n, int32_t nsrc, const float* vals, double* prob);
