@@ -827,6 +827,7 @@ int search_chunk(iq_ctx* c, MaskEntry* e, const iq_tile* tiles, int R, double to
     CK(cudaMallocHost((void**)&c->h_cand_val, cap * maxS * sizeof(float)));
     c->h_cand_cap = cap;
   }
+  if (c->tau_device && !c->h_prob) CK(cudaMallocHost((void**)&c->h_prob, (size_t)c->max_batch * iq::kTauMax * sizeof(double)));
   {
     size_t o = 0;
     for (int r = 0; r < R; ++r) {
@@ -1073,7 +1074,9 @@ static int32_t ctx_create_impl(iq_ctx* c, const iq_ctx_desc* d) {
   CK(iq::dmalloc((void**)&c->d_rank, B * c->max_src * iq::kTauMax * sizeof(unsigned)));
   CK(iq::dmalloc((void**)&c->d_colsum, B * c->max_src * sizeof(unsigned long long)));
   CK(iq::dmalloc((void**)&c->d_prob, B * iq::kTauMax * sizeof(double)));
-  CK(cudaMallocHost((void**)&c->h_prob, B * iq::kTauMax * sizeof(double)));
+  // h_prob (page-locked mirror of d_prob: 256 KB per job slot, 64 MB for the 256 slots of a resident context) is
+  // allocated by the first iq_search that needs it -- page-locking it cost most of a context's set-up time, and the
+  // resident pipeline never reads probabilities back
   // radix-select schedule: 4 value bytes, then only the index bytes that can be non-zero
   std::vector<int> shifts = {56, 48, 40, 32};
   int nib = 1;

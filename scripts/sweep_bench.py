@@ -32,6 +32,19 @@ def main():
                           "best": [int(v) for v in out["best"]]}), flush=True)
         if pr:
             pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+        if os.environ.get("SWEEP_PER_SIZE"):
+            per = []
+            for t in range(tmin, tmax + 1, 3):
+                tilesize = tuple(t if d > 1 else 1 for d in ti.shape)
+                t0 = time.perf_counter()
+                (_, _, vox), ex = iqb200.iqsim(ti, tilesize, tuple(2 * (t - -(-t // 6)) + -(-t // 6) if d > 1 else 1 for d in ti.shape),
+                                                  nreal=10, debug=True, rng=np.random.default_rng(1), return_stats=True)
+                stats = ex["stats"]
+                per.append({"t": t, "ms": round(1e3 * (time.perf_counter() - t0), 1), "resident": stats["resident"],
+                            "status": stats["resident_status"], "total_ms": round(stats["total_ms"], 1),
+                            "cut_ms": round(stats["cut_ms"], 1), "setup_ms": round(stats["setup_ms"], 1),
+                            "device_ms": round(stats["device_ms"], 1), "teardown_ms": round(stats["teardown_ms"], 1)})
+            print(json.dumps({"sweep_per_size": name, "rows": per}), flush=True)
 
 
 if __name__ == "__main__":
