@@ -326,7 +326,16 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   // one lockstep group by default: a launch already carries every realization (FFT pairs, one cut CTA per slab).
   // Several groups (streams) overlap one group's cut tail with another's FFT passes: -10 % device time with 4 groups
   // of 16 on config 5, at the price of per-kernel timings that no longer describe a kernel alone.
-  int ngroups = D->ngroups > 0 ? D->ngroups : 1;
+  // Few realizations (what one rank of a strong-scaling run over nreal = 64 holds): a level's cut launch then lasts as
+  // long as its slowest cut on a mostly idle GPU, and four groups of two realizations fill that tail with each other's
+  // FFT passes (measured on config 5 with 8 realizations: 219 -> 189 ms per call, with 4: 134 -> 119; no gain from 16
+  // realizations up, a loss with 8 groups).  2-D simulations are launch-latency bound and gain likewise (config 2 with
+  // 16 realizations: 26.9 -> 21.6 ms).  Threshold path only: with soft or hard data four groups LOSE 6-11 % (configs
+  // 3 and 4: the selection kernels of a group already fill the GPU).
+  int ngroups = 1;
+  if (D->ngroups > 0) ngroups = D->ngroups;
+  else if (const char* ev = std::getenv("IQB200_GROUPS")) ngroups = std::max(1, std::atoi(ev));
+  else if (S == 0 && !D->hard_has && ((G.N == 3 && R >= 4 && R <= 8) || (G.N == 2 && R >= 8 && R <= 16))) ngroups = 4;
   ngroups = std::max(1, std::min(ngroups, R));
   // Tiles per launch (dependency-level batching, see below): a launch carries tiles x realizations jobs.  Soft data keep
   // one tile per launch (one auxiliary map per source is kept).  IQB200_JOBS overrides the job slots per launch.
