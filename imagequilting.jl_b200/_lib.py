@@ -88,6 +88,7 @@ SYMBOLS = {
     "iq_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "iq_host_free": (C.c_int32, [C.c_void_p]),
     "iq_ctx_matches": (C.c_int32, [C.c_void_p, C.POINTER(IqCtxDesc), c_i32_p]),
+    "iq_ctx_matches_ctx": (C.c_int32, [C.c_void_p, C.POINTER(IqCtxDesc), C.c_void_p, c_i32_p]),
     "iq_ctx_npos": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p]),
     "iq_search": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqTile), C.c_int32, C.c_double, C.POINTER(IqResult)]),
     "iq_search_pick": (C.c_int32, [C.c_void_p, c_u8_p, C.POINTER(IqTile), C.c_int32, C.c_double, c_double_p,

@@ -1138,9 +1138,20 @@ __global__ void __launch_bounds__(256) k_differs(const unsigned* __restrict__ a,
   if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(flag, 1);
 }
 
-int32_t iq_ctx_matches(iq_ctx* c, const iq_ctx_desc* d, int32_t* same) {
+static int32_t ctx_matches_impl(iq_ctx* c, const iq_ctx_desc* d, const iq_ctx* ref, int32_t* same);
+
+int32_t iq_ctx_matches(iq_ctx* c, const iq_ctx_desc* d, int32_t* same) { return ctx_matches_impl(c, d, nullptr, same); }
+
+int32_t iq_ctx_matches_ctx(iq_ctx* c, const iq_ctx_desc* d, const iq_ctx* ref, int32_t* same) {
+  if (!ref) return fail(IQ_ERR_INVALID, "iq_ctx_matches_ctx: NULL reference context");
+  return ctx_matches_impl(c, d, ref, same);
+}
+
+static int32_t ctx_matches_impl(iq_ctx* c, const iq_ctx_desc* d, const iq_ctx* ref, int32_t* same) {
   if (!c || !d || !same || !d->ti) return fail(IQ_ERR_INVALID, "iq_ctx_matches: NULL argument");
   *same = 0;
+  if (ref && (ref == c || ref->device != c->device || ref->nsoft != c->nsoft || ref->nx != c->nx || ref->ny != c->ny || ref->nz != c->nz))
+    return IQ_OK;
   if (c->sim) return IQ_OK;  // a simulation is open on it
   const int nz = d->ndim == 3 ? (int)d->ti_size[2] : 1, tz = d->ndim == 3 ? (int)d->tile_size[2] : 1;
   if (d->ndim != c->ndim || d->device != c->device || d->nsoft != c->nsoft || std::max(1, d->max_batch) != c->max_batch ||
@@ -1158,14 +1169,21 @@ int32_t iq_ctx_matches(iq_ctx* c, const iq_ctx_desc* d, int32_t* same) {
   const size_t nimg = (size_t)c->nx * c->ny * c->nz;
   float* d_new = nullptr;
   int* d_flag = nullptr;
-  CK(iq::dmalloc((void**)&d_new, nimg * sizeof(float)));
+  if (!ref) CK(iq::dmalloc((void**)&d_new, nimg * sizeof(float)));
   CK(iq::dmalloc((void**)&d_flag, sizeof(int)));
   CK(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
   for (int img = -1; img < c->nsoft; ++img) {
-    const float* src = img < 0 ? d->ti : (d->auxti ? d->auxti[img] : nullptr);
-    if (!src) { cudaFree(d_new); cudaFree(d_flag); return fail(IQ_ERR_INVALID, "iq_ctx_matches: auxti[%d] is NULL", img); }
-    CK(cudaMemcpyAsync(d_new, src, nimg * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    k_differs<<<1184, 256, 0, c->stream>>>((const unsigned*)d_new, (const unsigned*)(img < 0 ? c->d_ti : c->d_aux[img]),
+    const float* cmp = d_new;
+    if (ref) {
+      // the reference context was created from / matched against these very host arrays during this call and is idle:
+      // compare with its resident copy, no second upload
+      cmp = img < 0 ? ref->d_ti : ref->d_aux[img];
+    } else {
+      const float* src = img < 0 ? d->ti : (d->auxti ? d->auxti[img] : nullptr);
+      if (!src) { cudaFree(d_new); cudaFree(d_flag); return fail(IQ_ERR_INVALID, "iq_ctx_matches: auxti[%d] is NULL", img); }
+      CK(cudaMemcpyAsync(d_new, src, nimg * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    k_differs<<<1184, 256, 0, c->stream>>>((const unsigned*)cmp, (const unsigned*)(img < 0 ? c->d_ti : c->d_aux[img]),
                                            (long long)nimg, d_flag);
     CK(cudaGetLastError());
   }

@@ -232,7 +232,9 @@ struct CtxCache {
   std::mutex m;
   std::vector<iq_ctx*> parked;
   static constexpr size_t kMax = 4;
-  iq_ctx* take(const iq_ctx_desc& cd) {
+  // `ref`: a context of this call already known to hold cd's images (the other parked contexts are then compared with it
+  // on the device instead of uploading the images again)
+  iq_ctx* take(const iq_ctx_desc& cd, const iq_ctx* ref = nullptr) {
     std::vector<iq_ctx*> cand;
     {
       std::lock_guard<std::mutex> l(m);
@@ -242,7 +244,7 @@ struct CtxCache {
     std::vector<iq_ctx*> rest;
     for (iq_ctx* c : cand) {
       int32_t same = 0;
-      if (!hit && iq_ctx_matches(c, &cd, &same) == IQ_OK && same) hit = c;
+      if (!hit && (ref ? iq_ctx_matches_ctx(c, &cd, ref, &same) : iq_ctx_matches(c, &cd, &same)) == IQ_OK && same) hit = c;
       else rest.push_back(c);
     }
     std::lock_guard<std::mutex> l(m);
@@ -328,14 +330,15 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   // of 16 on config 5, at the price of per-kernel timings that no longer describe a kernel alone.
   // Few realizations (what one rank of a strong-scaling run over nreal = 64 holds): a level's cut launch then lasts as
   // long as its slowest cut on a mostly idle GPU, and four groups of two realizations fill that tail with each other's
-  // FFT passes (measured on config 5 with 8 realizations: 219 -> 189 ms per call, with 4: 134 -> 119; no gain from 16
-  // realizations up, a loss with 8 groups).  2-D simulations are launch-latency bound and gain likewise (config 2 with
+  // FFT passes (measured on config 5 with 8 realizations: 219 -> 189 ms per call, with 4: 134 -> 119, with 32: 730 -> 666,
+  // with 64: 1398 -> 1335; with 16 the device time drops too (353 -> 329 ms) but the call does not (370 -> 392); a loss
+  // with 8 groups, and with exactly 2).  2-D simulations are launch-latency bound and gain likewise (config 2 with
   // 16 realizations: 26.9 -> 21.6 ms).  Threshold path only: with soft or hard data four groups LOSE 6-11 % (configs
   // 3 and 4: the selection kernels of a group already fill the GPU).
   int ngroups = 1;
   if (D->ngroups > 0) ngroups = D->ngroups;
   else if (const char* ev = std::getenv("IQB200_GROUPS")) ngroups = std::max(1, std::atoi(ev));
-  else if (S == 0 && !D->hard_has && ((G.N == 3 && R >= 4 && R <= 8) || (G.N == 2 && R >= 8 && R <= 16))) ngroups = 4;
+  else if (S == 0 && !D->hard_has && ((G.N == 3 && ((R >= 4 && R <= 8) || R >= 32)) || (G.N == 2 && R >= 8 && R <= 16))) ngroups = 4;
   ngroups = std::max(1, std::min(ngroups, R));
   // Tiles per launch (dependency-level batching, see below): a launch carries tiles x realizations jobs.  Soft data keep
   // one tile per launch (one auxiliary map per source is kept).  IQB200_JOBS overrides the job slots per launch.
@@ -390,7 +393,7 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
     cd.auxti = D->auxti;
     cd.device = D->device;
     cd.max_batch = g.R * tiles_per_launch;
-    g.ctx = use_cache ? g_cache.take(cd) : nullptr;
+    g.ctx = use_cache ? g_cache.take(cd, gi > 0 ? groups[0].ctx : nullptr) : nullptr;
     if (!g.ctx) rc = iq_ctx_create(&g.ctx, &cd);
     if (rc != IQ_OK) break;
     iq_ctx_set_option(g.ctx, "fft", D->fft_mode);

@@ -105,6 +105,10 @@ int32_t iq_ctx_npos(const iq_ctx* ctx, int64_t* npos, int64_t* nenabled);
  * summed-volume tables, cached A2 maps, image spectra and work buffers -- instead of rebuilding it.  0 while a
  * simulation is open on the context. */
 int32_t iq_ctx_matches(iq_ctx* ctx, const iq_ctx_desc* desc, int32_t* same);
+/* The same test against the images of `ref`, a context on the same device that the caller has just created from, or
+ * matched against, these host arrays (device-to-device comparison: a host that keeps several contexts per call -- the
+ * lockstep groups of iqh_run -- uploads the images once). */
+int32_t iq_ctx_matches_ctx(iq_ctx* ctx, const iq_ctx_desc* desc, const iq_ctx* ref, int32_t* same);
 
 /* The hot path: for each of `ntile` tiles sharing `ovlmask` (tile-sized, nonzero = voxel belongs
  * to the overlap with an already pasted neighbour) compute the overlap / hard / soft distance maps,

@@ -164,6 +164,27 @@ def test_resident_many_realizations_groups():
         assert np.array_equal(x, y)
 
 
+def test_grouped_contexts_are_rechecked_against_the_images_of_every_call():
+    """The lockstep groups of one call keep a context each (parked between calls).  The first is compared with the
+    uploaded images, the others with the first on the device (iq_ctx_matches_ctx): a second call on the SAME image reuses
+    them and returns the same realizations; a call on a DIFFERENT image of the same geometry must not."""
+    ti = synth.gaussian_field((48, 40, 20), (6, 6, 3), 21)
+    ti2 = synth.gaussian_field((48, 40, 20), (6, 6, 3), 22)
+    kw = dict(nreal=8, pipeline="resident")
+    iqb200.api.release_device_memory(0)
+    first = iqb200.iqsim(ti, (16, 12, 8), rng=np.random.default_rng(4), ngroups=4, **kw)
+    again = iqb200.iqsim(ti, (16, 12, 8), rng=np.random.default_rng(4), ngroups=4, **kw)      # parked contexts reused
+    other = iqb200.iqsim(ti2, (16, 12, 8), rng=np.random.default_rng(4), ngroups=4, **kw)     # same geometry, new image
+    iqb200.api.release_device_memory(0)
+    fresh = iqb200.iqsim(ti2, (16, 12, 8), rng=np.random.default_rng(4), ngroups=1, **kw)     # nothing parked
+    one = iqb200.iqsim(ti, (16, 12, 8), rng=np.random.default_rng(4), ngroups=1, **kw)
+    for a, b, c in zip(first, again, one):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    for a, b in zip(other, fresh):
+        assert np.array_equal(a, b)
+    assert not all(np.array_equal(a, b) for a, b in zip(first, other))
+
+
 def test_resident_soft_data_random_path():
     """Random path with soft data: many tiles have no pasted neighbour (empty overlap mask) and go through
     iq_search + iq_sample on the host, interleaved with device steps on the same context."""
