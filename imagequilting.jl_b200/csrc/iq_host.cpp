@@ -332,13 +332,15 @@ int run_resident(const iqh_desc* D, const Geo& G, double* out_grids, uint8_t* ou
   // long as its slowest cut on a mostly idle GPU, and four groups of two realizations fill that tail with each other's
   // FFT passes (measured on config 5 with 8 realizations: 219 -> 189 ms per call, with 4: 134 -> 119, with 32: 730 -> 666,
   // with 64: 1398 -> 1335; with 16 the device time drops too (353 -> 329 ms) but the call does not (370 -> 392); a loss
-  // with 8 groups, and with exactly 2).  2-D simulations are launch-latency bound and gain likewise (config 2 with
+  // with 8 groups, and with exactly 2).  The default stays at one group from 9 realizations up: the 5-9 % at 32 / 64 are
+  // left to `ngroups = 4`, because kernels of concurrent groups time-slice the SMs and their CUDA-event durations (the
+  // roofline figures of bench.py) then no longer describe a kernel running alone.  2-D simulations are launch-latency bound and gain likewise (config 2 with
   // 16 realizations: 26.9 -> 21.6 ms).  Threshold path only: with soft or hard data four groups LOSE 6-11 % (configs
   // 3 and 4: the selection kernels of a group already fill the GPU).
   int ngroups = 1;
   if (D->ngroups > 0) ngroups = D->ngroups;
   else if (const char* ev = std::getenv("IQB200_GROUPS")) ngroups = std::max(1, std::atoi(ev));
-  else if (S == 0 && !D->hard_has && ((G.N == 3 && ((R >= 4 && R <= 8) || R >= 32)) || (G.N == 2 && R >= 8 && R <= 16))) ngroups = 4;
+  else if (S == 0 && !D->hard_has && ((G.N == 3 && R >= 4 && R <= 8) || (G.N == 2 && R >= 8 && R <= 16))) ngroups = 4;
   ngroups = std::max(1, std::min(ngroups, R));
   // Tiles per launch (dependency-level batching, see below): a launch carries tiles x realizations jobs.  Soft data keep
   // one tile per launch (one auxiliary map per source is kept).  IQB200_JOBS overrides the job slots per launch.
