@@ -268,9 +268,11 @@ def iqsim_sliced(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), tol
         return res
 
     # Candidate exchange: ONE fixed-size tensor all-gather per tile search -- no pickled Python objects.  A rank's record
-    # is [count, idx[0:cap], float bits of val[source][0:cap]] as int64; the capacity starts at 4096 candidates and doubles
-    # for the whole run when any rank's list does not fit (the search is then exchanged again with the larger records:
-    # counts are known to every rank, so all ranks take the same branch).
+    # is [count, idx[0:cap], float bits of val[source][0:cap]] as int64.  The capacity follows the searches: twice the
+    # largest list of the previous search (at least 4096), and when a list does not fit the search is exchanged again with
+    # records that do (counts are known to every rank, so all ranks take the same branch).  It must not simply grow: the
+    # first tile of a soft-data run admits a tenth of ALL positions (3.9 M at 39 M positions), and records of that size
+    # on every later search cost 50 ms per exchange.
     state = {"cap": 4096}
 
     def allgather(idx, val):
@@ -290,13 +292,16 @@ def iqsim_sliced(trainimg, tilesize, simsize=None, *, overlap=None, soft=(), tol
                 rec[o:o + m] = np.ascontiguousarray(val[s_, :m], dtype=np.float32).view(np.int32).astype(np.int64)
             parts = gather_i64(rec)
             counts = [int(pz[0]) for pz in parts]
+            fit = 4096
+            while fit < 2 * max(counts):
+                fit *= 2
             if max(counts) <= cap:
                 gi = np.concatenate([pz[1:1 + c] for pz, c in zip(parts, counts)])
                 gv = np.stack([np.concatenate([pz[1 + (1 + s_) * cap:1 + (1 + s_) * cap + c].astype(np.int32).view(np.float32)
                                                for pz, c in zip(parts, counts)]) for s_ in range(nsrc)])
+                state["cap"] = fit  # for the next search
                 return gi, gv
-            while state["cap"] < max(counts):
-                state["cap"] *= 2
+            state["cap"] = fit
 
     nsrc = 1 + len(soft)
 

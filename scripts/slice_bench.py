@@ -41,6 +41,10 @@ def main():
             reals = sharding.iqsim_sliced(ti, tile, simsize, nreal=1, seed=5, device=local, soft=soft, stats=st)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+        if rank != 0:
+            print(json.dumps({"slice_mode": name, "world": world, "rank": rank, "seconds": round(dt, 4),
+                              "collective_seconds": round(st["collective_s"], 4),
+                              "phases": {k: round(v, 4) for k, v in st.items() if k.startswith("t_")}}), flush=True)
         if rank == 0:
             t0 = time.perf_counter()
             want = iqb200.iqsim(ti, tile, simsize, nreal=1, rng=np.random.default_rng(5), device=local, pipeline="staged",
