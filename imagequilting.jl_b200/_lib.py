@@ -119,6 +119,7 @@ SYMBOLS = {
     "iq_last_search_stats": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
     "iq_last_search_path": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p, c_double_p, c_double_p]),
     "iq_last_search_kernel_ms": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),
+    "iq_ctx_direct_kernel_launches": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p]),
     "iq_bench_fma_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "iq_bench_fma2_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "iq_release_device_memory": (C.c_int32, [C.c_int32]),

@@ -729,6 +729,12 @@ class SearchContext:
         check(lib().iq_last_search_path(self._h, C.byref(nd), C.byref(nf), C.byref(fb), C.byref(fm)))
         return nd.value, nf.value, fb.value, fm.value
 
+    def direct_kernel_launches(self):
+        """(TMA-staged, register-staged) launches of the direct distance kernel since the context was created."""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().iq_ctx_direct_kernel_launches(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
 
 def taumodel(vals):
     """Host tau model of the library (src/taumodel.jl:5-45); vals: (nsrc, n) float32 distances of the candidates."""

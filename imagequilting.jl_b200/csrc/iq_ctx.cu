@@ -19,6 +19,7 @@
 
 #include "../../include/iqb200.h"
 #include "iq_internal.h"
+#include "iq_tma.cuh"
 #include "iq_fft.h"
 #include "iq_cut.h"
 
@@ -200,35 +201,6 @@ void decompose(const uint8_t* m, int tx, int ty, int tz, std::vector<BoxDesc>& o
   }
 }
 
-// Choose the CTA shape (warps along x / y) for a box list: minimise padded work x tail effect.
-void choose_shape(const iq_ctx* c, const std::vector<BoxDesc>& boxes, int rb, int ngrp_hint, int* WX, int* WY) {
-  double best = 1e300;
-  int bx = 1, by = 1;
-  const int maxwx = (c->nxo + iq::kWarpX - 1) / iq::kWarpX, maxwy = (c->nyo + iq::kWarpY - 1) / iq::kWarpY;
-  for (int wx = 1; wx <= 8; ++wx)
-    for (int wy = 1; wx * wy <= 8; ++wy) {
-      if (wx > maxwx || wy > maxwy) continue;
-      const size_t smem = iq::dist_boxes_smem(boxes.data(), (int)boxes.size(), wx, wy, rb, nullptr, nullptr);
-      if (smem > 200 * 1024) continue;
-      const long long gx = (c->nxo + wx * iq::kWarpX - 1) / (wx * iq::kWarpX);
-      const long long gy = (c->nyo + wy * iq::kWarpY - 1) / (wy * iq::kWarpY);
-      const double padded = (double)gx * wx * iq::kWarpX * gy * wy * iq::kWarpY;
-      const double nblk = (double)gx * gy * c->nzo * ngrp_hint;
-      // resident CTAs per SM: limited by smem (227 KB) and by 2048 threads / registers (~2 x 256)
-      int per_sm = (int)std::min<double>((227.0 * 1024) / std::max<size_t>(smem, 1), 16.0 / (wx * wy));
-      per_sm = std::max(per_sm, 1);
-      const double slots = 148.0 * per_sm;
-      const double waves = nblk / slots;
-      const double tail = std::ceil(waves) / waves;
-      // small CTAs pay relatively more halo staging and sync; mild preference for >= 4 warps
-      const double small_pen = 1.0 + 0.02 * (8 - wx * wy);
-      const double cost = padded * tail * small_pen;
-      if (cost < best) { best = cost; bx = wx; by = wy; }
-    }
-  *WX = bx;
-  *WY = by;
-}
-
 int get_mask(iq_ctx* c, const uint8_t* mask, MaskEntry** out) {
   const uint64_t h = fnv1a(mask, (size_t)c->tilevol);
   for (auto& e : c->masks)
@@ -252,7 +224,6 @@ int get_mask(iq_ctx* c, const uint8_t* mask, MaskEntry** out) {
   CK(iq::dmalloc((void**)&e->d_mask, (size_t)c->tilevol));
   CK(cudaMemcpyAsync(e->d_mask, e->mask.data(), (size_t)c->tilevol, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  choose_shape(c, e->boxes, 1, std::max(1, c->max_batch), &e->WX, &e->WY);
   *out = e.get();
   c->masks.push_back(std::move(e));
   return IQ_OK;
@@ -281,10 +252,7 @@ int pick_rb(const iq_ctx* c, int R) {
 
 // Pack R templates (tile-sized arrays `kern[r]`, masked by e->mask) into the kernel layout
 // [grp][box][qz][qy][chunk][r(RB)][8] at staging offset; also B2[r] = sum(mask * kern^2) in FP64.
-// tap_major = false: [grp][box][qz][qy][chunk][tile][8 taps]   (scalar kernels)
-// tap_major = true : [grp][box][qz][qy][chunk][8 taps][tile]   (packed FFMA2 kernel)
-void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* kern, int R, int rb, bool tap_major, float* dst,
-                    double* b2) {
+void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* kern, int R, int rb, float* dst, double* b2) {
   const int ngrp = (R + rb - 1) / rb;
   const long long gstride = e->tmpl_floats * rb;
   std::memset(dst, 0, (size_t)ngrp * gstride * sizeof(float));
@@ -302,8 +270,7 @@ void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* ker
           float* drow = base + ((long long)qz * b.h + qy) * b.nch * 8 * rb;
           for (int x = 0; x < b.w; ++x) {
             const float v = m[trow + x] ? k[trow + x] : 0.f;
-            if (tap_major) drow[(x >> 3) * 8 * rb + (x & 7) * rb + ri] = v;
-            else drow[(x >> 3) * 8 * rb + ri * 8 + (x & 7)] = v;
+            drow[(x >> 3) * 8 * rb + ri * 8 + (x & 7)] = v;
           }
         }
     }
@@ -449,9 +416,52 @@ int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R,
   return launch_fft(c, e, image, (const float*)(c->d_stage + off_t), (const double*)(c->d_stage + off_b), R, tint, d_out, kind);
 }
 
+// Tensor maps of `image` for the TMA-staged direct kernel at panel width XT (one per mask box), cached on the mask.
+// ok = false: no tensor-map encoder in this driver, or the encode failed -> the caller uses the register-staged kernel.
+static int get_flat_tma(iq_ctx* c, MaskEntry* e, int image, int XT, const iq::FlatTmaMaps** out, bool* ok) {
+  *ok = false;
+  const auto key = std::make_pair(image, XT);
+  auto it = e->tma.find(key);
+  if (it != e->tma.end()) { *out = &it->second; *ok = true; return IQ_OK; }
+  static const iqtma::EncodeTiledFn encode = iqtma::encode_tiled_fn();
+  if (!encode) return IQ_OK;
+  // TMA needs a row pitch of whole 16-byte units: images whose nx is not a multiple of 4 get a padded copy (once)
+  const float* img = image < 0 ? c->d_ti : c->d_aux[image];
+  const int nxp = (c->nx + 3) & ~3;
+  if (nxp != c->nx) {
+    auto ip = c->img_pad.find(image);
+    if (ip == c->img_pad.end()) {
+      float* d = nullptr;
+      CK(iq::dmalloc((void**)&d, (size_t)nxp * c->ny * c->nz * sizeof(float)));
+      CK(cudaMemsetAsync(d, 0, (size_t)nxp * c->ny * c->nz * sizeof(float), c->stream));
+      CK(cudaMemcpy2DAsync(d, (size_t)nxp * sizeof(float), img, (size_t)c->nx * sizeof(float), (size_t)c->nx * sizeof(float),
+                           (size_t)c->ny * c->nz, cudaMemcpyDeviceToDevice, c->stream));
+      ip = c->img_pad.emplace(image, d).first;
+    }
+    img = ip->second;
+  }
+  iq::FlatTmaMaps maps;
+  std::memset(&maps, 0, sizeof(maps));
+  for (size_t b = 0; b < e->boxes.size(); ++b) {
+    int bw = 0, bh = 0;
+    iq::dist_flat_box(e->boxes[b], XT, &bw, &bh);
+    const cuuint64_t gdim[3] = {(cuuint64_t)c->nx, (cuuint64_t)c->ny, (cuuint64_t)c->nz};
+    const cuuint64_t gstr[2] = {(cuuint64_t)nxp * sizeof(float), (cuuint64_t)nxp * c->ny * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = encode(&maps.m[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)img, gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return IQ_OK;
+  }
+  *out = &e->tma.emplace(key, maps).first->second;
+  *ok = true;
+  return IQ_OK;
+}
+
 // Direct correlation kernel on R templates already packed in device memory ([grp][box][qz][qy][chunk][r(rb)][8]).
-int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, const double* d_b2, int R, int rb, bool packed,
-                  float* d_out, int kind, int job0) {
+int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, const double* d_b2, int R, int rb, float* d_out,
+                  int kind, int job0) {
   const float* a2 = nullptr;
   int rc = get_a2(c, e, image, &a2);
   if (rc) return rc;
@@ -471,37 +481,56 @@ int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, con
   p.minbits = c->d_minmax + (size_t)(kind * 2 + 0) * c->max_batch + job0;
   p.maxbits = c->d_minmax + (size_t)(kind * 2 + 1) * c->max_batch + job0;
   p.R = R;
-  p.WX = e->WX;
-  p.WY = e->WY;
+  const int nxt = (c->nxo + iq::kT - 1) / iq::kT;
   size_t smem = 0;
-  if (c->variant != 1) {
-    // flat variants: fewest column panels whose patch + templates still let two CTAs share an SM
-    const int nxt = (c->nxo + iq::kT - 1) / iq::kT;
+  const iq::FlatTmaMaps* maps = nullptr;
+  bool tma = false;
+  if (c->variant == 0) {
+    // TMA kernel: fewest column panels (width a multiple of 4 x-threads) whose two stage buffers still let two CTAs
+    // share an SM, else one CTA per SM
+    int best_xt = 0;
+    for (int pass = 0; pass < 2 && !best_xt; ++pass) {
+      const size_t limit = pass == 0 ? 110 * 1024 : 220 * 1024;
+      for (int np = 1; np <= nxt; ++np) {
+        const int xt = (((nxt + np - 1) / np) + 3) & ~3;
+        const size_t need = iq::dist_flat_smem(e->boxes.data(), p.nbox, xt, rb, nullptr, nullptr);
+        if (need && need <= limit) { best_xt = xt; break; }
+      }
+    }
+    if (best_xt) {
+      rc = get_flat_tma(c, e, image, best_xt, &maps, &tma);
+      if (rc) return rc;
+    }
+    if (tma) {
+      p.XT = best_xt;
+      smem = iq::dist_flat_smem(e->boxes.data(), p.nbox, p.XT, rb, &p.patch_floats, &p.tmpl_floats);
+    }
+  }
+  if (!tma) {
+    // register-staged kernel: fewest column panels whose patch + templates still let two CTAs share an SM
     int best_xt = 0;
     for (int pass = 0; pass < 2 && !best_xt; ++pass) {
       const size_t limit = pass == 0 ? 110 * 1024 : 220 * 1024;
       for (int np = 1; np <= nxt; ++np) {
         const int xt = (nxt + np - 1) / np;
         if (xt > 256) continue;
-        if (iq::dist_flat_smem(e->boxes.data(), p.nbox, xt, rb, nullptr) <= limit) { best_xt = xt; break; }
+        if (iq::dist_flat_ldg_smem(e->boxes.data(), p.nbox, xt, rb, nullptr) <= limit) { best_xt = xt; break; }
       }
     }
-    if (!best_xt) return fail(IQ_ERR_INVALID, "tile too large for the shared-memory staging of the flat kernel");
+    if (!best_xt) return fail(IQ_ERR_INVALID, "tile too large for the shared-memory staging of the direct kernel");
     p.XT = best_xt;
-    smem = iq::dist_flat_smem(e->boxes.data(), p.nbox, p.XT, rb, &p.patch_floats);
-  } else {
-    smem = iq::dist_boxes_smem(e->boxes.data(), p.nbox, p.WX, p.WY, rb, &p.pitch_max, &p.patch_floats);
+    smem = iq::dist_flat_ldg_smem(e->boxes.data(), p.nbox, p.XT, rb, &p.patch_floats);
   }
   cudaEvent_t ea, eb;
   rc = dist_events(c, &ea, &eb, false);
   if (rc) return rc;
   CK(cudaEventRecord(ea, c->stream));
-  if (packed) CK(iq::launch_dist_flat2(p, rb, std::max<size_t>(smem, 64), c->stream));
-  else if (c->variant != 1) CK(iq::launch_dist_flat(p, rb, std::max<size_t>(smem, 64), c->stream));
-  else CK(iq::launch_dist_boxes(p, rb, std::max<size_t>(smem, 64), c->stream));
+  if (tma) CK(iq::launch_dist_flat(p, *maps, rb, smem, c->stream));
+  else CK(iq::launch_dist_flat_ldg(p, rb, std::max<size_t>(smem, 64), c->stream));
   CK(cudaEventRecord(eb, c->stream));
   c->launches++;
   c->last_direct_searches += R;
+  (tma ? c->direct_tma_launches : c->direct_ldg_launches)++;
   if (kind == 0) c->chunk_valid = false;
   return IQ_OK;
 }
@@ -527,12 +556,10 @@ int run_dense(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int 
   const size_t off_t = stage_alloc(c, std::max<size_t>(tbytes, 16));
   const size_t off_b = stage_alloc(c, (size_t)R * sizeof(double));
   if (c->stage_used > c->stage_cap) return fail(IQ_ERR_STATE, "staging overflow (internal)");
-  const bool packed = (c->variant == 2 && rb >= 2);  // experimental FFMA2 kernel
-  pack_templates(c, e, kern, R, rb, packed, (float*)(c->h_stage + off_t), (double*)(c->h_stage + off_b));
+  pack_templates(c, e, kern, R, rb, (float*)(c->h_stage + off_t), (double*)(c->h_stage + off_b));
   CK(cudaMemcpyAsync(c->d_stage + off_t, c->h_stage + off_t, (off_b + R * sizeof(double)) - off_t, cudaMemcpyHostToDevice,
                      c->stream));
-  return launch_direct(c, e, image, (const float*)(c->d_stage + off_t), (const double*)(c->d_stage + off_b), R, rb, packed,
-                       d_out, kind);
+  return launch_direct(c, e, image, (const float*)(c->d_stage + off_t), (const double*)(c->d_stage + off_b), R, rb, d_out, kind);
 }
 
 // Sums the event pairs recorded since dist_ev_used was last reset into last_dist_ms / last_fft_ms.
@@ -982,6 +1009,7 @@ int32_t iq_ctx_destroy(iq_ctx* c) {
     cudaFree(e->d_mask);
     for (auto& kv : e->a2) cudaFree(kv.second);
   }
+  for (auto& kv : c->img_pad) cudaFree(kv.second);
   iqfft::plan_destroy(c->fft);
   for (auto ev : c->dist_ev) cudaEventDestroy(ev);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1683,6 +1711,13 @@ int32_t iq_last_search_path(const iq_ctx* c, int64_t* direct_searches, int64_t* 
   return IQ_OK;
 }
 
+int32_t iq_ctx_direct_kernel_launches(const iq_ctx* c, int64_t* tma_staged, int64_t* register_staged) {
+  if (!c) return fail(IQ_ERR_INVALID, "NULL context");
+  if (tma_staged) *tma_staged = c->direct_tma_launches;
+  if (register_staged) *register_staged = c->direct_ldg_launches;
+  return IQ_OK;
+}
+
 int32_t iq_last_search_kernel_ms(const iq_ctx* c, double* dist_ms, int64_t* dist_launches) {
   if (!c) return fail(IQ_ERR_INVALID, "NULL context");
   if (dist_ms) *dist_ms = c->last_dist_ms;
@@ -1783,7 +1818,7 @@ int32_t iq_ctx_set_option(iq_ctx* c, const char* key, int64_t value) {
     return IQ_OK;
   }
   if (std::strcmp(key, "variant") == 0) {
-    if (value < 0 || value > 2) return fail(IQ_ERR_INVALID, "variant must be 0 (flat), 1 (tiled) or 2 (flat with packed f32x2 FMAs, experimental)");
+    if (value < 0 || value > 1) return fail(IQ_ERR_INVALID, "variant must be 0 (TMA-staged direct kernel) or 1 (register-staged direct kernel)");
     c->variant = (int)value;
     return IQ_OK;
   }

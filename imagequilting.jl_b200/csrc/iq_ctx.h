@@ -35,7 +35,8 @@ struct MaskEntry {
   long long nnz = 0;
   long long tmpl_floats = 0;           // packed template floats per tile
   std::map<int, float*> a2;            // image id (-1 = TI, s = aux s) -> A2 map
-  int WX = 1, WY = 1;
+  // tensor maps of the TMA-staged direct kernel, keyed by (image id, panel width XT): the TMA box of every mask box
+  std::map<std::pair<int, int>, iq::FlatTmaMaps> tma;
 };
 
 struct TileResult {
@@ -66,7 +67,9 @@ struct iq_ctx {
   std::map<int, bool> image_is_int;  // image id -> every voxel is integer-valued (exact rounding of AB)
   double last_fft_bytes = 0.0;
   int64_t last_fft_searches = 0, last_direct_searches = 0;
-  int variant = 0; // 0 = flat kernel (default), 1 = tiled kernel, 2 = flat kernel with packed FMAs (experimental: slower)
+  int64_t direct_tma_launches = 0, direct_ldg_launches = 0;  // direct-kernel launches since the context was created
+  int variant = 0; // direct kernel: 0 = TMA-staged, double-buffered (default), 1 = register-staged (also the fallback)
+  std::map<int, float*> img_pad;  // image id -> copy with the row pitch rounded up to 16 bytes (TMA needs it; only when nx % 4 != 0)
 
   float* d_ti = nullptr;
   std::vector<float*> d_aux;
@@ -161,8 +164,8 @@ int ensure_fft(iq_ctx* c, int image);
 // mix masks (e may then be nullptr).
 int launch_fft(iq_ctx* c, MaskEntry* e, int image, const float* d_tmpl, const double* d_b2, int R, bool tint, float* d_out,
                int kind, int job0 = 0, const float* const* a2_list = nullptr);
-int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, const double* d_b2, int R, int rb, bool packed,
-                  float* d_out, int kind, int job0 = 0);
+int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, const double* d_b2, int R, int rb, float* d_out,
+                  int kind, int job0 = 0);
 int collect_dist_times(iq_ctx* c);
 // Makes sure d_chunkmin describes the R overlap-distance maps in d_Dovl (FFT epilogue, or one extra pass).
 int ensure_chunkmin(iq_ctx* c, int R);

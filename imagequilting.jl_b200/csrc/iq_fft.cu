@@ -21,7 +21,7 @@
 #include "iq_fft.h"
 #include "iq_internal.h"
 
-#include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
+#include "iq_tma.cuh"  // CUtensorMap, mbarrier / cp.async.bulk helpers; cuTensorMapEncodeTiled through cudaGetDriverEntryPoint
 #include <math_constants.h>
 
 #include <algorithm>
@@ -676,32 +676,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_fft_x_final(const FinalArgs A) 
   final_epilogue<LOG2N>(A, res, pr, blockIdx.x, l0, nl, s_min, s_max);
 }
 
-// ---- TMA helpers (bulk asynchronous copies global -> shared, completion on an mbarrier) -------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// orders earlier generic-proxy accesses to shared memory before later asynchronous-proxy (TMA) writes
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA helpers (bulk asynchronous copies global -> shared, completion on an mbarrier): iq_tma.cuh
+using namespace iqtma;
 
 // ---- pass B, inverse transform along a strided axis with TMA-fed double buffering ------------------------------------
 // The inverse y pass is bound by memory latency (ncu: 5 warps per issue slot waiting on the long scoreboard, DRAM at
@@ -710,13 +686,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // every thread issues one 128-byte bulk asynchronous copy (cp.async.bulk, the TMA engine; completion counted on an
 // mbarrier) of row e of the tile straight into shared memory -- no registers, no LSU issue slots -- in the
 // element-major layout [e][16 lines] that the first Stockham pass reads (LIN = 2).  Same arithmetic, same results.
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-               : "memory");
-}
-
 // USE_MAP: ONE tensor-map request per tile (cp.async.bulk.tensor.2d: box of 16 elements x N rows of the work array seen
 // as a 2-D tensor [rows][Nx] of 8-byte elements) instead of N row copies.
 template <int LOG2N, bool USE_MAP>
@@ -1092,23 +1061,15 @@ cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int 
   p->workspace = mp * (p->w1_stride + p->w2_stride + p->w3_stride + p->w4_stride) * sizeof(float2);
   // tensor map of w3 for the TMA-fed inverse y pass: rows = (pair, z, ky), 16-element boxes over all Ny rows of a plane
   if (p->w3 && lines_per_block(p->ly) == 16 && p->Ny <= 256 && p->Nx % 16 == 0) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
-        qres == cudaDriverEntryPointSuccess) {
+    if (const iqtma::EncodeTiledFn encode = iqtma::encode_tiled_fn()) {
       const cuuint64_t gdim[2] = {(cuuint64_t)Nx, (cuuint64_t)mp * (cuuint64_t)p->nzo * (cuuint64_t)Ny};
       const cuuint64_t gstr[1] = {(cuuint64_t)Nx * sizeof(float2)};
       const cuuint32_t box[2] = {16u, (cuuint32_t)Ny};
       const cuuint32_t estr[2] = {1u, 1u};
-      const CUresult r = ((EncodeFn)fn)(&p->w3_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, p->w3, gdim, gstr, box, estr,
+      const CUresult r = encode(&p->w3_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, p->w3, gdim, gstr, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       p->w3_map_ok = (r == CUDA_SUCCESS);
-    } else {
-      cudaGetLastError();
     }
   }
   *out = p;

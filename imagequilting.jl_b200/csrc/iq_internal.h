@@ -1,6 +1,7 @@
 // iq_internal.h -- shared declarations between the kernel TU (iq_kernels.cu) and the context /
 // orchestration TU (iq_ctx.cu).  Not part of the public ABI (include/iqb200.h is).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -8,8 +9,7 @@ namespace iq {
 
 constexpr int kTauMax = 32768; // largest candidate set ranked on the device (shared-memory bitonic sort)
 constexpr int kT = 8;           // outputs per thread along x (register tile)
-constexpr int kWarpX = 32;      // outputs per warp along x  (4 lanes x 8)
-constexpr int kWarpY = 8;       // outputs per warp along y  (8 lanes)
+constexpr int kFlatTmaMaxBox = 8;  // mask boxes the TMA-staged direct kernel carries tensor maps for
 
 // One axis-aligned box of the (disjoint) mask decomposition, in tile coordinates.
 struct BoxDesc {
@@ -36,10 +36,15 @@ struct DistParams {
   unsigned* minbits;           // [R] atomicMin of float bits over enabled positions (or nullptr)
   unsigned* maxbits;           // [R] atomicMax of float bits over enabled positions (or nullptr)
   int R;                       // tiles in this launch
-  int WX, WY;                  // warps per CTA along x / y
-  int pitch_max;               // smem patch pitch upper bound (floats)
-  int patch_floats;            // smem floats reserved for the image patch
-  int XT;                      // flat variant: x-threads (8 outputs each) per panel row
+  int patch_floats;            // smem floats reserved for the image patch (per stage buffer)
+  int tmpl_floats;             // TMA kernel: smem floats reserved for the template plane (per stage buffer)
+  int XT;                      // x-threads (8 outputs each) per panel row
+};
+
+// Tensor maps of the image for the TMA-staged direct kernel, one per mask box: 3-D (x, y, z) FP32, box =
+// (XT + nch) * 8 + 4 columns x (rows of the CTA + h - 1) rows x 1 plane, no swizzle, out-of-bounds elements read as 0.
+struct FlatTmaMaps {
+  CUtensorMap m[kFlatTmaMaxBox];
 };
 
 struct SparseParams {
@@ -123,11 +128,12 @@ cudaError_t launch_graphcut_grid(const double* A, const double* B, unsigned char
 cudaError_t dmalloc(void** p, size_t bytes);
 
 // ---- launch wrappers (iq_kernels.cu) -------------------------------------------------
-cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
-cudaError_t launch_dist_flat(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
-cudaError_t launch_dist_flat2(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
-size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats);
-size_t dist_boxes_smem(const BoxDesc* boxes, int nbox, int WX, int WY, int rb, int* pitch_max, int* patch_floats);
+cudaError_t launch_dist_flat(const DistParams& p, const FlatTmaMaps& maps, int rb, size_t smem_bytes, cudaStream_t s);
+cudaError_t launch_dist_flat_ldg(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
+// shared memory of the TMA kernel for panel width XT (0 = the box list exceeds TMA's limits) / of the register-staged one
+size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats, int* tmpl_floats);
+size_t dist_flat_ldg_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats);
+void dist_flat_box(const BoxDesc& b, int XT, int* width, int* rows);  // TMA box of mask box b at panel width XT
 cudaError_t launch_dist_sparse(const SparseParams& p, cudaStream_t s);
 cudaError_t launch_sat_build(const float* img, double* sat, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_a2map(const double* sat, int nx, int ny, int nz, const BoxDesc* boxes, int nbox,

@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "iq_internal.h"
+#include "iq_tma.cuh"
 
 #include <math_constants.h>
 
@@ -62,117 +63,54 @@ __device__ __forceinline__ unsigned warp_max_u(unsigned v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// dense box correlation
+// dense box correlation (direct path, below the FFT crossover)
 // ------------------------------------------------------------------------------------------------
-// CTA = WX x WY warps; a warp covers 32 (x) x 8 (y) output positions of one z plane, a thread 8
-// consecutive x positions.  For every box of the mask and every z plane of the box the CTA stages the
-// image patch (plus the template plane of its RB tiles) in shared memory and slides the template rows
-// over it.  Patch pitch = PW + 4 floats (== 4 mod 8) so that the LDS.128 of a quarter warp
-// (4 x-lanes, 2 rows) hit 8 distinct 16-byte bank groups.
+// Mask -> disjoint boxes (host).  The distance map of one z plane is cut in column panels of XT x-threads (8
+// consecutive outputs each); a CTA of 256 threads takes 256 (x-thread, row) work items of a panel.  For every box of
+// the mask and every z plane of the box the CTA needs the image patch under its items (plus the template plane of its
+// RB tiles) in shared memory and slides the template rows over it with a 16-value register window: 64 RB FMAs per
+// 2 + 2 RB LDS.128.
+//
+//   k_dist_flat      (default)  the patch is one cp.async.bulk.tensor.3d box of the image's tensor map, the template
+//                    plane one cp.async.bulk copy, both landing on an mbarrier; two stage buffers, so the TMA engine
+//                    fetches (box, plane) s+1 while the FMAs of stage s run -- no staging instructions, no registers, one
+//                    __syncthreads per stage.  TMA writes the box densely (row pitch = box width), so the conflict-free
+//                    LDS.128 comes from the geometry instead of a swizzle: box width = 4 mod 8 floats and a quarter warp
+//                    = 4 x-threads of 2 consecutive rows (work items numbered in 2-row x 4-thread octets).
+//   k_dist_flat_ldg  (variant 1, and the fallback for boxes beyond TMA's 256-element limit)  items numbered row-major,
+//                    patch staged through registers with __ldg, single buffer, two barriers per stage; the two 16-byte
+//                    halves of every 8-float chunk are swapped in odd 128-byte groups for conflict-free LDS.128.
+constexpr int kFlatThreads = 256;
+
+__device__ __forceinline__ void ld8sw(float (&v)[8], const float* rowp, int ci) {
+  const float* a = rowp + ci * 8;
+  const int sw = ((ci >> 2) & 1) << 2;
+  const float4 lo = *reinterpret_cast<const float4*>(a + sw);
+  const float4 hi = *reinterpret_cast<const float4*>(a + (sw ^ 4));
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+  v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
+// Shared epilogue of the direct kernels: |A2 - 2AB + B2| in FP64 (utils.jl:12), disabled -> Inf (iqsim.jl:207),
+// min / max of the enabled entries (iqsim.jl:237, relaxation.jl:11).
 template <int RB>
-__global__ void __launch_bounds__(256) k_dist_boxes(const DistParams P) {
-  extern __shared__ __align__(16) float smem[];
-  float* patch = smem;
-  float* tmplS = smem + P.patch_floats;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int wx = warp % P.WX, wy = warp / P.WX;
-  const int lx = lane & 3, ly = lane >> 2;
-  const int X0 = blockIdx.x * (P.WX * kWarpX), Y0 = blockIdx.y * (P.WY * kWarpY);
-  const int pz = blockIdx.z % P.nzo, grp = blockIdx.z / P.nzo;
-  const int tx0 = (wx * 4 + lx) * kT;  // first output column of this thread, relative to X0
-  const int tyr = wy * kWarpY + ly;    // output row of this thread, relative to Y0
-
-  float tot[RB][8];
-#pragma unroll
-  for (int r = 0; r < RB; ++r)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) tot[r][t] = 0.f;
-
-  for (int b = 0; b < P.nbox; ++b) {
-    const BoxDesc bx = P.boxes[b];
-    const int PW = P.WX * kWarpX + bx.nch * 8;
-    const int pitch = PW + 4;
-    const int PH = P.WY * kWarpY + bx.h - 1;
-    const int plane_floats = bx.h * bx.nch * 8 * RB;
-    const float* tsrc = P.tmpl + (long long)grp * P.tmpl_grp_stride + (long long)bx.tmpl_off * RB;
-
-    for (int qz = 0; qz < bx.d; ++qz) {
-      __syncthreads();  // previous plane fully consumed
-      // ---- stage the image patch of plane pz + z0 + qz ----
-      const int gz = pz + bx.z0 + qz;
-      const float* src = P.img + (long long)gz * P.nx * P.ny;
-      for (int row = warp; row < PH; row += nwarps) {
-        const int gy = Y0 + bx.y0 + row;
-        const bool rowok = gy < P.ny;
-        const float* srow = src + (long long)gy * P.nx;
-        float* drow = patch + row * pitch;
-        for (int col = lane; col < PW; col += 32) {
-          const int gx = X0 + bx.x0 + col;
-          drow[col] = (rowok && gx < P.nx) ? __ldg(srow + gx) : 0.f;
-        }
-      }
-      // ---- stage the template plane of the RB tiles ----
-      {
-        const float4* t4 = reinterpret_cast<const float4*>(tsrc + (long long)qz * plane_floats);
-        float4* d4 = reinterpret_cast<float4*>(tmplS);
-        for (int i = tid; i < plane_floats / 4; i += nthreads) d4[i] = __ldg(t4 + i);
-      }
-      __syncthreads();
-
-      // ---- slide the template rows over the patch ----
-      float acc[RB][8];
-#pragma unroll
-      for (int r = 0; r < RB; ++r)
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc[r][t] = 0.f;
-
-      const float* rowp = patch + tyr * pitch + tx0;
-      const float* kp = tmplS;
-      for (int qy = 0; qy < bx.h; ++qy) {
-        float A[8], B[8];
-        ld8(A, rowp);
-        const float* rp = rowp + 8;
-        for (int c = 0; c < bx.nch; c += 2) {
-          ld8(B, rp);
-          rp += 8;
-          fma_chunk<RB>(acc, A, B, kp);
-          kp += RB * 8;
-          if (c + 1 < bx.nch) {
-            ld8(A, rp);
-            rp += 8;
-            fma_chunk<RB>(acc, B, A, kp);
-            kp += RB * 8;
-          }
-        }
-        rowp += pitch;
-      }
-      // two-level accumulation: per-plane partial sums keep the FP32 error growth ~sqrt(plane size)
-#pragma unroll
-      for (int r = 0; r < RB; ++r)
-#pragma unroll
-        for (int t = 0; t < 8; ++t) tot[r][t] += acc[r][t];
-    }
-  }
-
-  // ---- epilogue: |A2 - 2AB + B2|, disabled -> +Inf, min/max over enabled positions ----
-  __shared__ unsigned s_min[4], s_max[4];
+__device__ __forceinline__ void flat_epilogue(const DistParams& P, const float (&tot)[RB][8], int grp, int pz, int row, int x0,
+                                              bool valid, unsigned* s_min, unsigned* s_max) {
+  const int tid = threadIdx.x, lane = tid & 31;
   if (tid < 4) { s_min[tid] = 0x7f800000u; s_max[tid] = 0u; }
   __syncthreads();
-  const int py = Y0 + tyr;
 #pragma unroll
   for (int r = 0; r < RB; ++r) {
     const int tile = grp * RB + r;
     unsigned vmin = 0x7f800000u, vmax = 0u;
-    if (tile < P.R && py < P.nyo) {
+    if (tile < P.R && valid) {
       const double b2 = P.b2[tile];
       float* orow = P.out + (long long)tile * P.npos;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        const int x = X0 + tx0 + t;
+        const int x = x0 + t;
         if (x < P.nxo) {
-          const long long p = ((long long)pz * P.nyo + py) * P.nxo + x;
+          const long long p = ((long long)pz * P.nyo + row) * P.nxo + x;
           const double a2 = P.a2 ? (double)__ldg(P.a2 + p) : 0.0;
           float d = (float)fabs(a2 - 2.0 * (double)tot[r][t] + b2);
           const bool dis = P.disabled && P.disabled[p];
@@ -204,66 +142,116 @@ __global__ void __launch_bounds__(256) k_dist_boxes(const DistParams P) {
   }
 }
 
-size_t dist_boxes_smem(const BoxDesc* boxes, int nbox, int WX, int WY, int rb, int* pitch_max, int* patch_floats) {
-  int pf = 0, tf = 0, pm = 0;
-  for (int b = 0; b < nbox; ++b) {
-    const int PW = WX * kWarpX + boxes[b].nch * 8;
-    const int pitch = PW + 4;
-    const int PH = WY * kWarpY + boxes[b].h - 1;
-    pf = max(pf, PH * pitch);
-    pm = max(pm, pitch);
-    tf = max(tf, boxes[b].h * boxes[b].nch * 8 * rb);
-  }
-  pf = (pf + 3) & ~3;
-  if (pitch_max) *pitch_max = pm;
-  if (patch_floats) *patch_floats = pf;
-  return (size_t)(pf + tf) * sizeof(float);
+// ---- TMA-staged, double-buffered (default) ------------------------------------------------------------------------
+// rows a CTA's 32 octets can span: they start anywhere in a row pair and run over (XT/4 + 30) / (XT/4) + 1 pairs at most
+__host__ __device__ inline int flat_tma_rows(int XT) {
+  const int x4 = XT >> 2;
+  return 2 * ((x4 + 30) / x4 + 1);
 }
 
 template <int RB>
-static cudaError_t launch_dist_boxes_t(const DistParams& p, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_dist_boxes<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int ngrp = (p.R + RB - 1) / RB;
-  dim3 grid((p.nxo + p.WX * kWarpX - 1) / (p.WX * kWarpX), (p.nyo + p.WY * kWarpY - 1) / (p.WY * kWarpY),
-            p.nzo * ngrp);
-  dim3 block(p.WX * p.WY * 32);
-  k_dist_boxes<RB><<<grid, block, smem, s>>>(p);
-  return cudaGetLastError();
-}
+__global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat(const DistParams P, const __grid_constant__ FlatTmaMaps M) {
+  using namespace iqtma;
+  extern __shared__ __align__(128) unsigned char smraw_[];
+  float* sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smraw_) + 127) & ~(uintptr_t)127);  // TMA boxes: 128-byte aligned
+  auto patchS = [&](int buf) { return sm + buf * P.patch_floats; };                        // two stage buffers
+  auto tmplS = [&](int buf) { return sm + 2 * P.patch_floats + buf * P.tmpl_floats; };
+  __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ BoxDesc s_box[kFlatTmaMaxBox];
+  __shared__ unsigned s_min[4], s_max[4];
 
-cudaError_t launch_dist_boxes(const DistParams& p, int rb, size_t smem, cudaStream_t s) {
-  switch (rb) {
-    case 1: return launch_dist_boxes_t<1>(p, smem, s);
-    case 2: return launch_dist_boxes_t<2>(p, smem, s);
-    case 4: return launch_dist_boxes_t<4>(p, smem, s);
-    default: return cudaErrorInvalidValue;
+  const int tid = threadIdx.x;
+  const int XT = P.XT, XT4 = XT >> 2;
+  const int X0 = blockIdx.x * XT * kT;
+  const int noct = XT4 * ((P.nyo + 1) >> 1);
+  const int o0 = blockIdx.y * (kFlatThreads / 8);
+  const int oct = min(o0 + (tid >> 3), noct - 1);  // clamped threads recompute the last octet; they never store
+  const int rp = oct / XT4, xb = oct - rp * XT4;
+  const int row = 2 * rp + ((tid >> 2) & 1), xt = 4 * xb + (tid & 3);
+  const bool valid = (o0 + (tid >> 3)) < noct && row < P.nyo;
+  const int rlo = 2 * (o0 / XT4);
+  const int PHO = flat_tma_rows(XT);
+  const int pz = blockIdx.z % P.nzo, grp = blockIdx.z / P.nzo;
+  const float* tgrp = P.tmpl + (long long)grp * P.tmpl_grp_stride;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init_fence();
   }
+  if (tid < P.nbox) s_box[tid] = P.boxes[tid];
+  __syncthreads();
+
+  // one elected thread feeds the TMA engine: patch box + template plane of stage (b, qz) into buffer `buf`
+  auto issue = [&](int b, int qz, int buf) {
+    const BoxDesc& bx = s_box[b];
+    const int pitch = (XT + bx.nch) * 8 + 4;
+    const unsigned pbytes = (unsigned)(pitch * (PHO + bx.h - 1)) * 4u;
+    const int plane_floats = bx.h * bx.nch * 8 * RB;
+    fence_async_smem();  // the buffer was last read by ordinary loads (released by the barrier of the previous stage)
+    mbar_expect_tx(&bar[buf], pbytes + (unsigned)plane_floats * 4u);
+    tma_load_3d(patchS(buf), &M.m[b], X0 + bx.x0, rlo + bx.y0, pz + bx.z0 + qz, &bar[buf]);
+    bulk_g2s(tmplS(buf), tgrp + (long long)bx.tmpl_off * RB + (long long)qz * plane_floats, (unsigned)plane_floats * 4u, &bar[buf]);
+  };
+
+  float tot[RB][8];
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) tot[r][t] = 0.f;
+
+  if (tid == 0 && P.nbox > 0) issue(0, 0, 0);
+  int it = 0;
+  for (int b = 0; b < P.nbox; ++b) {
+    const int bh = s_box[b].h, bnch = s_box[b].nch, bd = s_box[b].d;
+    const int pitch = (XT + bnch) * 8 + 4;
+    for (int qz = 0; qz < bd; ++qz, ++it) {
+      const int buf = it & 1;
+      if (tid == 0) {  // next stage into the other buffer while this one is consumed
+        int nb = b, nq = qz + 1;
+        if (nq >= bd) { nq = 0; ++nb; }
+        if (nb < P.nbox) issue(nb, nq, buf ^ 1);
+      }
+      mbar_wait_bounded(&bar[buf], (unsigned)((it >> 1) & 1));
+
+      float acc[RB][8];
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[r][t] = 0.f;
+
+      const float* rowp = patchS(buf) + (row - rlo) * pitch + xt * 8;
+      const float* kp = tmplS(buf);
+      for (int qy = 0; qy < bh; ++qy) {
+        float A[8], B[8];
+        const float* a = rowp;
+        ld8(A, a);
+        for (int c = 0; c < bnch; c += 2) {
+          ld8(B, a + 8);
+          fma_chunk<RB>(acc, A, B, kp);
+          kp += RB * 8;
+          if (c + 1 < bnch) {
+            ld8(A, a + 16);
+            fma_chunk<RB>(acc, B, A, kp);
+            kp += RB * 8;
+          }
+          a += 16;
+        }
+        rowp += pitch;
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) tot[r][t] += acc[r][t];
+      __syncthreads();  // everybody is done with this buffer before it is refilled
+    }
+  }
+  flat_epilogue<RB>(P, tot, grp, pz, row, X0 + xt * kT, valid, s_min, s_max);
 }
 
-// ------------------------------------------------------------------------------------------------
-// dense box correlation, flat variant (default)
-// ------------------------------------------------------------------------------------------------
-// Same arithmetic as k_dist_boxes, different decomposition: the distance map of one z plane is cut in
-// column panels of XT x-threads (8 outputs each); inside a panel the (x-thread, row) work items are
-// numbered row-major and every CTA takes 256 consecutive items -- always 8 full warps (2 per SMSP), no
-// idle lanes and no padding beyond the 8-output granularity, whatever the image width.  A quarter warp
-// then reads 8 chunks of one patch row at a 32-byte stride; the patch is stored with the two 16-byte
-// halves of every 8-float chunk swapped in odd 128-byte groups (unit' = unit ^ ((unit >> 3) & 1)), which
-// makes those LDS.128 conflict-free.
-constexpr int kFlatThreads = 256;
-
-__device__ __forceinline__ void ld8sw(float (&v)[8], const float* rowp, int ci) {
-  const float* a = rowp + ci * 8;
-  const int sw = ((ci >> 2) & 1) << 2;
-  const float4 lo = *reinterpret_cast<const float4*>(a + sw);
-  const float4 hi = *reinterpret_cast<const float4*>(a + (sw ^ 4));
-  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-  v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-}
-
+// ---- register-staged (variant 1 / fallback) -----------------------------------------------------------------------
 template <int RB>
-__global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat(const DistParams P) {
+__global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat_ldg(const DistParams P) {
   extern __shared__ __align__(16) float smem[];
   float* patch = smem;
   float* tmplS = smem + P.patch_floats;
@@ -349,270 +337,10 @@ __global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat(const DistParams 
   }
 
   __shared__ unsigned s_min[4], s_max[4];
-  if (tid < 4) { s_min[tid] = 0x7f800000u; s_max[tid] = 0u; }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    const int tile = grp * RB + r;
-    unsigned vmin = 0x7f800000u, vmax = 0u;
-    if (tile < P.R && valid) {
-      const double b2 = P.b2[tile];
-      float* orow = P.out + (long long)tile * P.npos;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int x = X0 + xt * kT + t;
-        if (x < P.nxo) {
-          const long long p = ((long long)pz * P.nyo + row) * P.nxo + x;
-          const double a2 = P.a2 ? (double)__ldg(P.a2 + p) : 0.0;
-          float d = (float)fabs(a2 - 2.0 * (double)tot[r][t] + b2);
-          const bool dis = P.disabled && P.disabled[p];
-          if (dis) d = CUDART_INF_F;
-          orow[p] = d;
-          if (!dis) {
-            const unsigned u = __float_as_uint(d);
-            vmin = min(vmin, u);
-            vmax = max(vmax, u);
-          }
-        }
-      }
-    }
-    if (P.minbits) {
-      vmin = warp_min_u(vmin);
-      vmax = warp_max_u(vmax);
-      if (lane == 0 && tile < P.R) {
-        atomicMin(&s_min[r], vmin);
-        atomicMax(&s_max[r], vmax);
-      }
-    }
-  }
-  if (P.minbits) {
-    __syncthreads();
-    if (tid < RB && grp * RB + tid < P.R) {
-      atomicMin(P.minbits + grp * RB + tid, s_min[tid]);
-      atomicMax(P.maxbits + grp * RB + tid, s_max[tid]);
-    }
-  }
+  flat_epilogue<RB>(P, tot, grp, pz, row, X0 + xt * kT, valid, s_min, s_max);
 }
 
-// ------------------------------------------------------------------------------------------------
-// flat variant with packed FMAs (fma.rn.f32x2 -> SASS FFMA2): two tiles per instruction.
-// The accumulators of tiles (2rp, 2rp+1) share a 64-bit register pair, the template taps of the pair
-// arrive as one 64-bit word (template layout [chunk][tap][tile]), the image value is duplicated into
-// both halves once per value.  Same FMA count and same rounding as the scalar kernel (each half is an
-// IEEE fma.rn), half the issue slots: address arithmetic and LDS no longer compete with the FMA pipe.
-// ------------------------------------------------------------------------------------------------
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pack2(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
-  u64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-__device__ __forceinline__ void ld8sw_dup(u64 (&v)[8], const float* rowp, int ci) {
-  const float* a = rowp + ci * 8;
-  const int sw = ((ci >> 2) & 1) << 2;
-  const float4 lo = *reinterpret_cast<const float4*>(a + sw);
-  const float4 hi = *reinterpret_cast<const float4*>(a + (sw ^ 4));
-  v[0] = pack2(lo.x, lo.x); v[1] = pack2(lo.y, lo.y); v[2] = pack2(lo.z, lo.z); v[3] = pack2(lo.w, lo.w);
-  v[4] = pack2(hi.x, hi.x); v[5] = pack2(hi.y, hi.y); v[6] = pack2(hi.z, hi.z); v[7] = pack2(hi.w, hi.w);
-}
-
-// kp: [tap j = 0..7][tile pair rp][2] floats of this chunk
-template <int RP>
-__device__ __forceinline__ void fma_chunk2(u64 (&acc)[RP][8], const u64 (&lo)[8], const u64 (&hi)[8],
-                                           const float* __restrict__ kp) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    u64 k2[RP];
-    if constexpr (RP == 2) {
-      const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(kp + j * 4);
-      k2[0] = kv.x;
-      k2[RP - 1] = kv.y;
-    } else {
-      k2[0] = *reinterpret_cast<const u64*>(kp + j * 2);
-    }
-#pragma unroll
-    for (int rp = 0; rp < RP; ++rp) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const u64 w = (t + j < 8) ? lo[t + j] : hi[t + j - 8];
-        acc[rp][t] = ffma2(w, k2[rp], acc[rp][t]);
-      }
-    }
-  }
-}
-
-template <int RP>
-__global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat2(const DistParams P) {
-  constexpr int RB = 2 * RP;
-  extern __shared__ __align__(16) float smem[];
-  float* patch = smem;
-  float* tmplS = smem + P.patch_floats;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int XT = P.XT;
-  const int X0 = blockIdx.x * XT * kT;
-  const int nitem = XT * P.nyo;
-  const int i0 = blockIdx.y * kFlatThreads;
-  const int item = min(i0 + tid, nitem - 1);
-  const bool valid = (i0 + tid) < nitem;
-  const int row = item / XT, xt = item - row * XT;
-  const int rlo = i0 / XT;
-  const int rhi = min(i0 + kFlatThreads - 1, nitem - 1) / XT;
-  const int PHO = rhi - rlo + 1;
-  const int pz = blockIdx.z % P.nzo, grp = blockIdx.z / P.nzo;
-
-  u64 tot[RP][8];
-#pragma unroll
-  for (int r = 0; r < RP; ++r)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) tot[r][t] = 0ull;
-
-  for (int b = 0; b < P.nbox; ++b) {
-    const BoxDesc bx = P.boxes[b];
-    const int PW = (XT + bx.nch) * 8;
-    const int pitch = PW + 4;
-    const int PH = PHO + bx.h - 1;
-    const int plane_floats = bx.h * bx.nch * 8 * RB;
-    const float* tsrc = P.tmpl + (long long)grp * P.tmpl_grp_stride + (long long)bx.tmpl_off * RB;
-
-    for (int qz = 0; qz < bx.d; ++qz) {
-      __syncthreads();
-      const int gz = pz + bx.z0 + qz;
-      const float* src = P.img + (long long)gz * P.nx * P.ny;
-      for (int prow = warp; prow < PH; prow += kFlatThreads / 32) {
-        const int gy = rlo + bx.y0 + prow;
-        const bool rowok = gy < P.ny;
-        const float* srow = src + (long long)gy * P.nx;
-        float* drow = patch + prow * pitch;
-        for (int col = lane; col < PW; col += 32) {
-          const int gx = X0 + bx.x0 + col;
-          const int pcol = col ^ ((((col >> 5) & 1)) << 2);
-          drow[pcol] = (rowok && gx < P.nx) ? __ldg(srow + gx) : 0.f;
-        }
-      }
-      {
-        const float4* t4 = reinterpret_cast<const float4*>(tsrc + (long long)qz * plane_floats);
-        float4* d4 = reinterpret_cast<float4*>(tmplS);
-        for (int i = tid; i < plane_floats / 4; i += kFlatThreads) d4[i] = __ldg(t4 + i);
-      }
-      __syncthreads();
-
-      u64 acc[RP][8];
-#pragma unroll
-      for (int r = 0; r < RP; ++r)
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc[r][t] = 0ull;
-
-      const float* rowp = patch + (row - rlo) * pitch;
-      const float* kp = tmplS;
-      for (int qy = 0; qy < bx.h; ++qy) {
-        u64 A[8], B[8];
-        int ci = xt;
-        ld8sw_dup(A, rowp, ci);
-        for (int c = 0; c < bx.nch; c += 2) {
-          ld8sw_dup(B, rowp, ++ci);
-          fma_chunk2<RP>(acc, A, B, kp);
-          kp += RB * 8;
-          if (c + 1 < bx.nch) {
-            ld8sw_dup(A, rowp, ++ci);
-            fma_chunk2<RP>(acc, B, A, kp);
-            kp += RB * 8;
-          }
-        }
-        rowp += pitch;
-      }
-#pragma unroll
-      for (int r = 0; r < RP; ++r)
-#pragma unroll
-        for (int t = 0; t < 8; ++t) tot[r][t] = fadd2(tot[r][t], acc[r][t]);
-    }
-  }
-
-  __shared__ unsigned s_min[4], s_max[4];
-  if (tid < 4) { s_min[tid] = 0x7f800000u; s_max[tid] = 0u; }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    const int tile = grp * RB + r;
-    unsigned vmin = 0x7f800000u, vmax = 0u;
-    if (tile < P.R && valid) {
-      const double b2 = P.b2[tile];
-      float* orow = P.out + (long long)tile * P.npos;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int x = X0 + xt * kT + t;
-        if (x < P.nxo) {
-          float v0, v1;
-          unpack2(tot[r >> 1][t], v0, v1);
-          const float ab = (r & 1) ? v1 : v0;
-          const long long p = ((long long)pz * P.nyo + row) * P.nxo + x;
-          const double a2 = P.a2 ? (double)__ldg(P.a2 + p) : 0.0;
-          float d = (float)fabs(a2 - 2.0 * (double)ab + b2);
-          const bool dis = P.disabled && P.disabled[p];
-          if (dis) d = CUDART_INF_F;
-          orow[p] = d;
-          if (!dis) {
-            const unsigned u = __float_as_uint(d);
-            vmin = min(vmin, u);
-            vmax = max(vmax, u);
-          }
-        }
-      }
-    }
-    if (P.minbits) {
-      vmin = warp_min_u(vmin);
-      vmax = warp_max_u(vmax);
-      if (lane == 0 && tile < P.R) {
-        atomicMin(&s_min[r], vmin);
-        atomicMax(&s_max[r], vmax);
-      }
-    }
-  }
-  if (P.minbits) {
-    __syncthreads();
-    if (tid < RB && grp * RB + tid < P.R) {
-      atomicMin(P.minbits + grp * RB + tid, s_min[tid]);
-      atomicMax(P.maxbits + grp * RB + tid, s_max[tid]);
-    }
-  }
-}
-
-template <int RP>
-static cudaError_t launch_dist_flat2_t(const DistParams& p, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_dist_flat2<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int RB = 2 * RP;
-  const int ngrp = (p.R + RB - 1) / RB;
-  const int nxt = (p.nxo + kT - 1) / kT;
-  dim3 grid((nxt + p.XT - 1) / p.XT, (p.XT * p.nyo + kFlatThreads - 1) / kFlatThreads, p.nzo * ngrp);
-  k_dist_flat2<RP><<<grid, kFlatThreads, smem, s>>>(p);
-  return cudaGetLastError();
-}
-
-// packed kernel: rb must be 2 or 4; template layout [chunk][tap][tile]
-cudaError_t launch_dist_flat2(const DistParams& p, int rb, size_t smem, cudaStream_t s) {
-  switch (rb) {
-    case 2: return launch_dist_flat2_t<1>(p, smem, s);
-    case 4: return launch_dist_flat2_t<2>(p, smem, s);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
-size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats) {
+size_t dist_flat_ldg_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats) {
   int pf = 0, tf = 0;
   const int pho = (kFlatThreads + XT - 1) / XT + 1;
   for (int b = 0; b < nbox; ++b) {
@@ -625,22 +353,67 @@ size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch
   return (size_t)(pf + tf) * sizeof(float);
 }
 
+// TMA kernel: two stage buffers of (largest patch box + largest template plane), each rounded up to 128 bytes, plus the
+// alignment slack.  0 = this box list does not fit TMA's limits (box sides <= 256 elements, XT a multiple of 4).
+size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats, int* tmpl_floats) {
+  if (XT < 4 || (XT & 3) || nbox > kFlatTmaMaxBox) return 0;
+  int pf = 0, tf = 0;
+  const int pho = flat_tma_rows(XT);
+  for (int b = 0; b < nbox; ++b) {
+    const int pitch = (XT + boxes[b].nch) * 8 + 4, ph = pho + boxes[b].h - 1;
+    if (pitch > 256 || ph > 256) return 0;
+    pf = max(pf, ph * pitch);
+    tf = max(tf, boxes[b].h * boxes[b].nch * 8 * rb);
+  }
+  pf = (pf + 31) & ~31;
+  tf = (tf + 31) & ~31;
+  if (patch_floats) *patch_floats = pf;
+  if (tmpl_floats) *tmpl_floats = tf;
+  return (size_t)2 * (pf + tf) * sizeof(float) + 128;
+}
+
+void dist_flat_box(const BoxDesc& b, int XT, int* width, int* rows) {
+  *width = (XT + b.nch) * 8 + 4;
+  *rows = flat_tma_rows(XT) + b.h - 1;
+}
+
 template <int RB>
-static cudaError_t launch_dist_flat_t(const DistParams& p, size_t smem, cudaStream_t s) {
+static cudaError_t launch_dist_flat_t(const DistParams& p, const FlatTmaMaps& maps, size_t smem, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(k_dist_flat<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int ngrp = (p.R + RB - 1) / RB;
   const int nxt = (p.nxo + kT - 1) / kT;
-  dim3 grid((nxt + p.XT - 1) / p.XT, (p.XT * p.nyo + kFlatThreads - 1) / kFlatThreads, p.nzo * ngrp);
-  k_dist_flat<RB><<<grid, kFlatThreads, smem, s>>>(p);
+  const int noct = (p.XT >> 2) * ((p.nyo + 1) >> 1);
+  dim3 grid((nxt + p.XT - 1) / p.XT, (noct + kFlatThreads / 8 - 1) / (kFlatThreads / 8), p.nzo * ngrp);
+  k_dist_flat<RB><<<grid, kFlatThreads, smem, s>>>(p, maps);
   return cudaGetLastError();
 }
 
-cudaError_t launch_dist_flat(const DistParams& p, int rb, size_t smem, cudaStream_t s) {
+cudaError_t launch_dist_flat(const DistParams& p, const FlatTmaMaps& maps, int rb, size_t smem, cudaStream_t s) {
   switch (rb) {
-    case 1: return launch_dist_flat_t<1>(p, smem, s);
-    case 2: return launch_dist_flat_t<2>(p, smem, s);
-    case 4: return launch_dist_flat_t<4>(p, smem, s);
+    case 1: return launch_dist_flat_t<1>(p, maps, smem, s);
+    case 2: return launch_dist_flat_t<2>(p, maps, smem, s);
+    case 4: return launch_dist_flat_t<4>(p, maps, smem, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int RB>
+static cudaError_t launch_dist_flat_ldg_t(const DistParams& p, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(k_dist_flat_ldg<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int ngrp = (p.R + RB - 1) / RB;
+  const int nxt = (p.nxo + kT - 1) / kT;
+  dim3 grid((nxt + p.XT - 1) / p.XT, (p.XT * p.nyo + kFlatThreads - 1) / kFlatThreads, p.nzo * ngrp);
+  k_dist_flat_ldg<RB><<<grid, kFlatThreads, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dist_flat_ldg(const DistParams& p, int rb, size_t smem, cudaStream_t s) {
+  switch (rb) {
+    case 1: return launch_dist_flat_ldg_t<1>(p, smem, s);
+    case 2: return launch_dist_flat_ldg_t<2>(p, smem, s);
+    case 4: return launch_dist_flat_ldg_t<4>(p, smem, s);
     default: return cudaErrorInvalidValue;
   }
 }

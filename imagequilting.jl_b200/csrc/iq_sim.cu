@@ -891,7 +891,7 @@ static int sim_step_impl(iq_ctx* c, int ntile, const int64_t* steps, const int64
         CK(cudaGetLastError());
         c->launches++;
       }
-      return launch_direct(c, me, image, s->d_pack, d_b2, nt, rb, false, d_out, kind, job0);
+      return launch_direct(c, me, image, s->d_pack, d_b2, nt, rb, d_out, kind, job0);
     };
     k_sim_templates<double><<<dim3((unsigned)c->tz, (unsigned)NJ), 256, 0, c->stream>>>(
         s->d_grid, s->padvol, s->pad[0], s->pad[1], dt, R, s->d_shapes, nullptr, s->d_a2list, c->tx, c->ty, c->tz, s->d_tmpl,

@@ -267,7 +267,7 @@ int32_t iq_sim_end(iq_ctx* ctx);
  * of kernels launched by the most recent iq_search* call. */
 int32_t iq_last_search_stats(const iq_ctx* ctx, double* device_ms, int64_t* kernel_launches);
 
-/* Device time (ms) spent inside the dense correlation kernel (k_dist_boxes) alone during the most recent
+/* Device time (ms) spent inside the distance kernels (direct kernel or FFT passes) alone during the most recent
  * iq_search* call, measured with CUDA events on the context's stream, and the number of its launches. */
 int32_t iq_last_search_kernel_ms(const iq_ctx* ctx, double* dist_ms, int64_t* dist_launches);
 
@@ -275,6 +275,11 @@ int32_t iq_last_search_kernel_ms(const iq_ctx* ctx, double* dist_ms, int64_t* di
  * correlation kernel, by the FFT path, the algorithmic bytes the FFT passes moved and their device time. */
 int32_t iq_last_search_path(const iq_ctx* ctx, int64_t* direct_searches, int64_t* fft_searches, double* fft_bytes,
                             double* fft_ms);
+
+/* Direct-kernel launches since the context was created: through the TMA-staged kernel (k_dist_flat: tensor-map boxes of
+ * the image, double-buffered) and through the register-staged fallback (k_dist_flat_ldg: option "variant" = 1, mask
+ * boxes beyond TMA's 256-element box sides, more than 8 boxes, or a driver without cuTensorMapEncodeTiled). */
+int32_t iq_ctx_direct_kernel_launches(const iq_ctx* ctx, int64_t* tma_staged, int64_t* register_staged);
 
 /* FP32 FMA issue-rate microbenchmark on `device` (register-operand FFMA chains on every SM): writes the
  * measured rate in TFMA/s (1 FMA = 2 flop).  This is the denominator of the kernel's FMA roofline. */
@@ -297,7 +302,7 @@ int32_t iq_host_alloc(size_t bytes, void** out);
 int32_t iq_host_free(void* p);
 
 /* Tuning knobs (benchmarks/tests): key is one of "rb" (tiles per CTA pass: 0 = auto,
- * 1, 2, 4), "variant" (0 flat kernel, 1 tiled, 2 packed-FMA), "fft" (-1 never, 0 auto crossover, 1 always),
+ * 1, 2, 4), "variant" (direct kernel: 0 TMA-staged, 1 register-staged), "fft" (-1 never, 0 auto crossover, 1 always),
  * "cut_exact" (iq_cut_batch in exact integer arithmetic, for integer-valued slabs; see iq_sim_desc.exact_cut). */
 int32_t iq_ctx_set_option(iq_ctx* ctx, const char* key, int64_t value);
 

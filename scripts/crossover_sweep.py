@@ -1,9 +1,11 @@
 """Measured direct-vs-FFT crossover of the overlap-distance search.
 
 For a grid of training-image sizes, tile sizes, overlap masks (nnz) and batch sizes R the same search is timed with the
-direct correlation kernel (fft = -1) and with the FFT path (fft = 1): CUDA-event time of the distance kernels alone
-(iq_last_search_kernel_ms), best of 3 after a warm-up call.  The auto mode's decision (want_fft in csrc/iq_ctx.cu) is
-recorded next to the measured winner.  Writes profiles/r02_crossover.csv."""
+direct correlation kernel (fft = -1; TMA-staged k_dist_flat and register-staged k_dist_flat_ldg) and with the FFT path
+(fft = 1): CUDA-event time of the distance kernels alone (iq_last_search_kernel_ms), best of 3 after a warm-up call.
+The auto mode's decision (want_fft in csrc/iq_ctx.cu) is recorded next to the measured winner.  Writes
+gpurun_out/r02_crossover.csv (committed as profiles/r02_crossover_tma.csv; profiles/r02_crossover.csv is the sweep taken
+before the TMA-staged kernel existed)."""
 import csv
 import os
 import sys
@@ -33,8 +35,9 @@ def masks(tile, ovl):
     return out
 
 
-def timed(ctx, m, tiles, mode):
+def timed(ctx, m, tiles, mode, variant=0):
     ctx.set_option("fft", mode)
+    ctx.set_option("variant", variant)
     best = float("inf")
     for it in range(4):
         ctx.search(m, tiles, tol=0.1, u=[0.5] * len(tiles))
@@ -59,13 +62,15 @@ def main():
                     for _ in range(R):
                         p0 = tuple(int(r.integers(0, s)) for s in geo["distsize"])
                         tiles.append(dict(simdev=ti[tuple(slice(a, a + b) for a, b in zip(p0, tile))] + 0.1 * r.standard_normal(tile).astype(np.float32)))
-                    td = timed(ctx, m, tiles, -1)
+                    tl = timed(ctx, m, tiles, -1, 1)
+                    td = timed(ctx, m, tiles, -1, 0)
                     tf = timed(ctx, m, tiles, 1)
                     ctx.set_option("fft", 0)
                     ctx.search(m, tiles, tol=0.1, u=[0.5] * R)
                     nd, nf, _, _ = ctx.last_path()
                     rows.append(dict(case=name, ti="x".join(map(str, shape)), tile="x".join(map(str, tile)), mask=mname, nnz=int(m.sum()),
-                                     npos=npos, R=R, direct_ms=round(td, 4), fft_ms=round(tf, 4), measured="fft" if tf < td else "direct",
+                                     npos=npos, R=R, direct_ms=round(td, 4), direct_ldg_ms=round(tl, 4), tfma_per_s=round(int(m.sum()) * npos * R / td / 1e9, 2),
+                                     fft_ms=round(tf, 4), measured="fft" if tf < td else "direct",
                                      auto="fft" if nf > 0 else "direct", fma_per_search=int(m.sum()) * npos))
                     print(rows[-1], flush=True)
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02_crossover.csv")
