@@ -154,7 +154,8 @@ void decompose(const uint8_t* m, int tx, int ty, int tz, std::vector<BoxDesc>& o
     BoxDesc b;
     b.x0 = r.x0; b.y0 = r.y0; b.z0 = z0;
     b.w = r.x1 - r.x0; b.h = r.y1 - r.y0; b.d = z1 - z0;
-    b.nch = (b.w + 7) / 8;
+    b.pad = b.x0 & 3;
+    b.nch = (b.w + b.pad + 7) / 8;
     b.tmpl_off = 0;
     out.push_back(b);
   };
@@ -270,7 +271,8 @@ void pack_templates(const iq_ctx* c, const MaskEntry* e, const float* const* ker
           float* drow = base + ((long long)qz * b.h + qy) * b.nch * 8 * rb;
           for (int x = 0; x < b.w; ++x) {
             const float v = m[trow + x] ? k[trow + x] : 0.f;
-            drow[(x >> 3) * 8 * rb + ri * 8 + (x & 7)] = v;
+            const int t = x + b.pad;  // tap index in the packed row (b.pad leading zeros)
+            drow[(t >> 3) * 8 * rb + ri * 8 + (t & 7)] = v;
           }
         }
     }
@@ -416,11 +418,11 @@ int run_fft(iq_ctx* c, MaskEntry* e, int image, const float* const* kern, int R,
   return launch_fft(c, e, image, (const float*)(c->d_stage + off_t), (const double*)(c->d_stage + off_b), R, tint, d_out, kind);
 }
 
-// Tensor maps of `image` for the TMA-staged direct kernel at panel width XT (one per mask box), cached on the mask.
+// Tensor maps of `image` for the TMA-staged direct kernel at panel shape (XT, RS) (one per mask box), cached on the mask.
 // ok = false: no tensor-map encoder in this driver, or the encode failed -> the caller uses the register-staged kernel.
-static int get_flat_tma(iq_ctx* c, MaskEntry* e, int image, int XT, const iq::FlatTmaMaps** out, bool* ok) {
+static int get_flat_tma(iq_ctx* c, MaskEntry* e, int image, int XT, int RS, const iq::FlatTmaMaps** out, bool* ok) {
   *ok = false;
-  const auto key = std::make_pair(image, XT);
+  const auto key = std::make_pair(image, XT * 16 + RS);
   auto it = e->tma.find(key);
   if (it != e->tma.end()) { *out = &it->second; *ok = true; return IQ_OK; }
   static const iqtma::EncodeTiledFn encode = iqtma::encode_tiled_fn();
@@ -444,7 +446,7 @@ static int get_flat_tma(iq_ctx* c, MaskEntry* e, int image, int XT, const iq::Fl
   std::memset(&maps, 0, sizeof(maps));
   for (size_t b = 0; b < e->boxes.size(); ++b) {
     int bw = 0, bh = 0;
-    iq::dist_flat_box(e->boxes[b], XT, &bw, &bh);
+    iq::dist_flat_box(e->boxes[b], XT, RS, &bw, &bh);
     const cuuint64_t gdim[3] = {(cuuint64_t)c->nx, (cuuint64_t)c->ny, (cuuint64_t)c->nz};
     const cuuint64_t gstr[2] = {(cuuint64_t)nxp * sizeof(float), (cuuint64_t)nxp * c->ny * sizeof(float)};
     const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
@@ -486,24 +488,36 @@ int launch_direct(iq_ctx* c, MaskEntry* e, int image, const float* d_packed, con
   const iq::FlatTmaMaps* maps = nullptr;
   bool tma = false;
   if (c->variant == 0) {
-    // TMA kernel: fewest column panels (width a multiple of 4 x-threads) whose two stage buffers still let two CTAs
-    // share an SM, else one CTA per SM
-    int best_xt = 0;
-    for (int pass = 0; pass < 2 && !best_xt; ++pass) {
-      const size_t limit = pass == 0 ? 110 * 1024 : 220 * 1024;
+    // TMA kernel: panel width XT, octet shape RS and number of stage buffers NB that minimise the padded work (items
+    // are padded to whole octets: XT to a multiple of 8 / RS x-threads, the rows to a multiple of RS), preferring
+    // shapes whose shared memory lets two CTAs share an SM (one CTA per SM measured ~1.35x slower on large masks)
+    // and double buffering (single: the two CTAs of an SM overlap each other's loads instead)
+    const size_t lim2 = 115000, lim1 = 227 * 1024;
+    double best = 1e300;
+    int bxt = 0, brs = 0, bnb = 0;
+    for (int rs = 2; rs <= 8; rs *= 4) {
+      const int xs = 8 / rs;
       for (int np = 1; np <= nxt; ++np) {
-        const int xt = (((nxt + np - 1) / np) + 3) & ~3;
-        const size_t need = iq::dist_flat_smem(e->boxes.data(), p.nbox, xt, rb, nullptr, nullptr);
-        if (need && need <= limit) { best_xt = xt; break; }
+        const int xt = (((nxt + np - 1) / np) + xs - 1) / xs * xs;
+        if (np > 1 && (((nxt + np - 2) / (np - 1)) + xs - 1) / xs * xs == xt) continue;  // same width as with fewer panels
+        for (int nb = 2; nb >= 1; --nb) {
+          const size_t need = iq::dist_flat_smem(e->boxes.data(), p.nbox, xt, rs, nb, rb, nullptr, nullptr);
+          if (!need || need > lim1) continue;
+          const int npan = (nxt + xt - 1) / xt;
+          double cost = (double)npan * xt * (double)((c->nyo + rs - 1) / rs * rs) * (1.0 + 0.02 * npan);
+          if (need > lim2) cost *= 1.35;
+          if (nb == 1) cost *= 1.03;
+          if (cost < best) { best = cost; bxt = xt; brs = rs; bnb = nb; }
+        }
       }
     }
-    if (best_xt) {
-      rc = get_flat_tma(c, e, image, best_xt, &maps, &tma);
+    if (bxt) {
+      rc = get_flat_tma(c, e, image, bxt, brs, &maps, &tma);
       if (rc) return rc;
     }
     if (tma) {
-      p.XT = best_xt;
-      smem = iq::dist_flat_smem(e->boxes.data(), p.nbox, p.XT, rb, &p.patch_floats, &p.tmpl_floats);
+      p.XT = bxt; p.RS = brs; p.NB = bnb;
+      smem = iq::dist_flat_smem(e->boxes.data(), p.nbox, p.XT, p.RS, p.NB, rb, &p.patch_floats, &p.tmpl_floats);
     }
   }
   if (!tma) {

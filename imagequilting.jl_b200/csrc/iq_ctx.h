@@ -35,7 +35,7 @@ struct MaskEntry {
   long long nnz = 0;
   long long tmpl_floats = 0;           // packed template floats per tile
   std::map<int, float*> a2;            // image id (-1 = TI, s = aux s) -> A2 map
-  // tensor maps of the TMA-staged direct kernel, keyed by (image id, panel width XT): the TMA box of every mask box
+  // tensor maps of the TMA-staged direct kernel, keyed by (image id, panel shape XT * 16 + RS): the TMA box of every mask box
   std::map<std::pair<int, int>, iq::FlatTmaMaps> tma;
 };
 

@@ -15,8 +15,11 @@ constexpr int kFlatTmaMaxBox = 8;  // mask boxes the TMA-staged direct kernel ca
 struct BoxDesc {
   int x0, y0, z0;   // origin inside the tile
   int w, h, d;      // extent
-  int nch;          // ceil(w / 8): template rows are zero-padded to nch*8
+  int nch;          // ceil((pad + w) / 8): template rows are zero-padded to nch*8
   int tmpl_off;     // offset (floats, for ONE tile) of this box's packed template
+  int pad;          // x0 & 3: leading zero taps of every packed template row.  The kernels read the image patch from
+                    // x0 - pad, a multiple of 4 floats: a tensor-map box must start on a 16-byte boundary in its
+                    // innermost dimension (a misaligned start coordinate traps with "illegal instruction" on sm_100)
 };
 
 // Parameters of the dense (box) correlation kernel.
@@ -39,6 +42,8 @@ struct DistParams {
   int patch_floats;            // smem floats reserved for the image patch (per stage buffer)
   int tmpl_floats;             // TMA kernel: smem floats reserved for the template plane (per stage buffer)
   int XT;                      // x-threads (8 outputs each) per panel row
+  int RS;                      // TMA kernel: rows per octet of work items (2: 4 x-threads x 2 rows, 8: 1 x-thread x 8 rows)
+  int NB;                      // TMA kernel: stage buffers (2 = double-buffered, 1 = single)
 };
 
 // Tensor maps of the image for the TMA-staged direct kernel, one per mask box: 3-D (x, y, z) FP32, box =
@@ -131,9 +136,9 @@ cudaError_t dmalloc(void** p, size_t bytes);
 cudaError_t launch_dist_flat(const DistParams& p, const FlatTmaMaps& maps, int rb, size_t smem_bytes, cudaStream_t s);
 cudaError_t launch_dist_flat_ldg(const DistParams& p, int rb, size_t smem_bytes, cudaStream_t s);
 // shared memory of the TMA kernel for panel width XT (0 = the box list exceeds TMA's limits) / of the register-staged one
-size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats, int* tmpl_floats);
+size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int RS, int NB, int rb, int* patch_floats, int* tmpl_floats);
 size_t dist_flat_ldg_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats);
-void dist_flat_box(const BoxDesc& b, int XT, int* width, int* rows);  // TMA box of mask box b at panel width XT
+void dist_flat_box(const BoxDesc& b, int XT, int RS, int* width, int* rows);  // TMA box of mask box b at panel shape (XT, RS)
 cudaError_t launch_dist_sparse(const SparseParams& p, cudaStream_t s);
 cudaError_t launch_sat_build(const float* img, double* sat, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_a2map(const double* sat, int nx, int ny, int nz, const BoxDesc* boxes, int nbox,

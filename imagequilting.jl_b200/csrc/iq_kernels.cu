@@ -142,11 +142,14 @@ __device__ __forceinline__ void flat_epilogue(const DistParams& P, const float (
   }
 }
 
-// ---- TMA-staged, double-buffered (default) ------------------------------------------------------------------------
-// rows a CTA's 32 octets can span: they start anywhere in a row pair and run over (XT/4 + 30) / (XT/4) + 1 pairs at most
-__host__ __device__ inline int flat_tma_rows(int XT) {
-  const int x4 = XT >> 2;
-  return 2 * ((x4 + 30) / x4 + 1);
+// ---- TMA-staged (default) ---------------------------------------------------------------------------------------------
+// Work items are numbered in octets of RS rows x (8 / RS) x-threads, a quarter warp = one octet.  With a box width of
+// 4 mod 8 floats (an odd number of 16-byte units per row) both shapes give conflict-free LDS.128: RS = 2 (4 x-threads of 2
+// rows; XT a multiple of 4) and RS = 8 (one x-thread of 8 rows; any XT) -- the host picks the one that pads the map
+// least.  rows a CTA's 32 octets can span: they start anywhere in a row group and run over (XTB + 30) / XTB + 1 groups at most.
+__host__ __device__ inline int flat_tma_rows(int XT, int RS) {
+  const int xtb = XT / (8 / RS);
+  return RS * ((xtb + 30) / xtb + 1);
 }
 
 template <int RB>
@@ -154,23 +157,25 @@ __global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat(const DistParams 
   using namespace iqtma;
   extern __shared__ __align__(128) unsigned char smraw_[];
   float* sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smraw_) + 127) & ~(uintptr_t)127);  // TMA boxes: 128-byte aligned
-  auto patchS = [&](int buf) { return sm + buf * P.patch_floats; };                        // two stage buffers
-  auto tmplS = [&](int buf) { return sm + 2 * P.patch_floats + buf * P.tmpl_floats; };
+  const int NB = P.NB;  // stage buffers: 2 = the next stage is in flight during the FMAs, 1 = big boxes (two CTAs per SM overlap instead)
+  auto patchS = [&](int buf) { return sm + buf * P.patch_floats; };
+  auto tmplS = [&](int buf) { return sm + NB * P.patch_floats + buf * P.tmpl_floats; };
   __shared__ __align__(8) unsigned long long bar[2];
   __shared__ BoxDesc s_box[kFlatTmaMaxBox];
   __shared__ unsigned s_min[4], s_max[4];
 
   const int tid = threadIdx.x;
-  const int XT = P.XT, XT4 = XT >> 2;
+  const int XT = P.XT, RS = P.RS, XS = 8 / RS, XTB = XT / XS;
   const int X0 = blockIdx.x * XT * kT;
-  const int noct = XT4 * ((P.nyo + 1) >> 1);
+  const int noct = XTB * ((P.nyo + RS - 1) / RS);
   const int o0 = blockIdx.y * (kFlatThreads / 8);
   const int oct = min(o0 + (tid >> 3), noct - 1);  // clamped threads recompute the last octet; they never store
-  const int rp = oct / XT4, xb = oct - rp * XT4;
-  const int row = 2 * rp + ((tid >> 2) & 1), xt = 4 * xb + (tid & 3);
+  const int rg = oct / XTB, xb = oct - rg * XTB;
+  const int sub = tid & 7;
+  const int row = RS * rg + sub / XS, xt = XS * xb + sub % XS;
   const bool valid = (o0 + (tid >> 3)) < noct && row < P.nyo;
-  const int rlo = 2 * (o0 / XT4);
-  const int PHO = flat_tma_rows(XT);
+  const int rlo = RS * (o0 / XTB);
+  const int PHO = flat_tma_rows(XT, RS);
   const int pz = blockIdx.z % P.nzo, grp = blockIdx.z / P.nzo;
   const float* tgrp = P.tmpl + (long long)grp * P.tmpl_grp_stride;
 
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat(const DistParams 
     const int plane_floats = bx.h * bx.nch * 8 * RB;
     fence_async_smem();  // the buffer was last read by ordinary loads (released by the barrier of the previous stage)
     mbar_expect_tx(&bar[buf], pbytes + (unsigned)plane_floats * 4u);
-    tma_load_3d(patchS(buf), &M.m[b], X0 + bx.x0, rlo + bx.y0, pz + bx.z0 + qz, &bar[buf]);
+    tma_load_3d(patchS(buf), &M.m[b], X0 + bx.x0 - bx.pad, rlo + bx.y0, pz + bx.z0 + qz, &bar[buf]);  // x start: multiple of 4 floats
     bulk_g2s(tmplS(buf), tgrp + (long long)bx.tmpl_off * RB + (long long)qz * plane_floats, (unsigned)plane_floats * 4u, &bar[buf]);
   };
 
@@ -206,13 +211,11 @@ __global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat(const DistParams 
     const int bh = s_box[b].h, bnch = s_box[b].nch, bd = s_box[b].d;
     const int pitch = (XT + bnch) * 8 + 4;
     for (int qz = 0; qz < bd; ++qz, ++it) {
-      const int buf = it & 1;
-      if (tid == 0) {  // next stage into the other buffer while this one is consumed
-        int nb = b, nq = qz + 1;
-        if (nq >= bd) { nq = 0; ++nb; }
-        if (nb < P.nbox) issue(nb, nq, buf ^ 1);
-      }
-      mbar_wait_bounded(&bar[buf], (unsigned)((it >> 1) & 1));
+      const int buf = NB == 2 ? (it & 1) : 0;
+      int nb = b, nq = qz + 1;  // the stage after this one
+      if (nq >= bd) { nq = 0; ++nb; }
+      if (NB == 2 && tid == 0 && nb < P.nbox) issue(nb, nq, buf ^ 1);  // into the other buffer while this one is consumed
+      mbar_wait_bounded(&bar[buf], (unsigned)((NB == 2 ? (it >> 1) : it) & 1));
 
       float acc[RB][8];
 #pragma unroll
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat(const DistParams 
 #pragma unroll
         for (int t = 0; t < 8; ++t) tot[r][t] += acc[r][t];
       __syncthreads();  // everybody is done with this buffer before it is refilled
+      if (NB == 1 && tid == 0 && nb < P.nbox) issue(nb, nq, 0);
     }
   }
   flat_epilogue<RB>(P, tot, grp, pz, row, X0 + xt * kT, valid, s_min, s_max);
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(kFlatThreads, 2) k_dist_flat_ldg(const DistPar
         const float* srow = src + (long long)gy * P.nx;
         float* drow = patch + prow * pitch;
         for (int col = lane; col < PW; col += 32) {
-          const int gx = X0 + bx.x0 + col;
+          const int gx = X0 + bx.x0 - bx.pad + col;
           const int pcol = col ^ ((((col >> 5) & 1)) << 2);  // swap the chunk halves in odd 32-float groups
           drow[pcol] = (rowok && gx < P.nx) ? __ldg(srow + gx) : 0.f;
         }
@@ -353,12 +357,15 @@ size_t dist_flat_ldg_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* p
   return (size_t)(pf + tf) * sizeof(float);
 }
 
-// TMA kernel: two stage buffers of (largest patch box + largest template plane), each rounded up to 128 bytes, plus the
-// alignment slack.  0 = this box list does not fit TMA's limits (box sides <= 256 elements, XT a multiple of 4).
-size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch_floats, int* tmpl_floats) {
-  if (XT < 4 || (XT & 3) || nbox > kFlatTmaMaxBox) return 0;
+// TMA kernel: NB stage buffers of (largest patch box + largest template plane), each rounded up to 128 bytes, plus the
+// alignment slack.  0 = this box list does not fit TMA at this panel shape (box sides <= 256 elements, at most
+// kFlatTmaMaxBox boxes).  Boxes larger than the image or running over its edge are fine (zero-filled;
+// scripts/probe/tma_probe.cu).
+size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int RS, int NB, int rb, int* patch_floats, int* tmpl_floats) {
+  const int XS = 8 / RS;
+  if (XT < XS || (XT % XS) || nbox > kFlatTmaMaxBox) return 0;
   int pf = 0, tf = 0;
-  const int pho = flat_tma_rows(XT);
+  const int pho = flat_tma_rows(XT, RS);
   for (int b = 0; b < nbox; ++b) {
     const int pitch = (XT + boxes[b].nch) * 8 + 4, ph = pho + boxes[b].h - 1;
     if (pitch > 256 || ph > 256) return 0;
@@ -369,12 +376,12 @@ size_t dist_flat_smem(const BoxDesc* boxes, int nbox, int XT, int rb, int* patch
   tf = (tf + 31) & ~31;
   if (patch_floats) *patch_floats = pf;
   if (tmpl_floats) *tmpl_floats = tf;
-  return (size_t)2 * (pf + tf) * sizeof(float) + 128;
+  return (size_t)NB * (pf + tf) * sizeof(float) + 128;
 }
 
-void dist_flat_box(const BoxDesc& b, int XT, int* width, int* rows) {
+void dist_flat_box(const BoxDesc& b, int XT, int RS, int* width, int* rows) {
   *width = (XT + b.nch) * 8 + 4;
-  *rows = flat_tma_rows(XT) + b.h - 1;
+  *rows = flat_tma_rows(XT, RS) + b.h - 1;
 }
 
 template <int RB>
@@ -383,7 +390,7 @@ static cudaError_t launch_dist_flat_t(const DistParams& p, const FlatTmaMaps& ma
   if (e != cudaSuccess) return e;
   const int ngrp = (p.R + RB - 1) / RB;
   const int nxt = (p.nxo + kT - 1) / kT;
-  const int noct = (p.XT >> 2) * ((p.nyo + 1) >> 1);
+  const int noct = (p.XT / (8 / p.RS)) * ((p.nyo + p.RS - 1) / p.RS);
   dim3 grid((nxt + p.XT - 1) / p.XT, (noct + kFlatThreads / 8 - 1) / (kFlatThreads / 8), p.nzo * ngrp);
   k_dist_flat<RB><<<grid, kFlatThreads, smem, s>>>(p, maps);
   return cudaGetLastError();

@@ -184,9 +184,9 @@ __global__ void __launch_bounds__(256) k_sim_pack(const float* __restrict__ tmpl
   const int ch = (int)(q % B.nch); q /= B.nch;
   const int qy = (int)(q % B.h);
   const int qz = (int)(q / B.h);
-  const int x = ch * 8 + tap, r = g * rb + ri;
+  const int x = ch * 8 + tap - B.pad, r = g * rb + ri;  // B.pad leading zero taps per packed row
   float v = 0.f;
-  if (r < R && x < B.w) v = tmpl[(long long)r * tilevol + ((long long)(B.z0 + qz) * ty + (B.y0 + qy)) * tx + B.x0 + x];
+  if (r < R && x >= 0 && x < B.w) v = tmpl[(long long)r * tilevol + ((long long)(B.z0 + qz) * ty + (B.y0 + qy)) * tx + B.x0 + x];
   out[i] = v;
 }
 

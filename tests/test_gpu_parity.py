@@ -55,6 +55,9 @@ CASES = [
     ("cat", (30, 28, 12), (10, 9, 4), (2, 3, 2)),
     ("gauss", (50, 45, 20), (20, 20, 10), (4, 4, 2)),
     ("gauss", (41, 23, 9), (9, 17, 5), (7, 3, 2)),
+    ("gauss", (200, 120), (24, 20), (4, 4)),          # tensor-map boxes well inside the image (2-D)
+    ("cat", (96, 80, 10), (12, 10, 4), (2, 2, 2)),    # ... and 3-D
+    ("gauss", (90, 76, 8), (10, 12, 3), (3, 3, 1)),   # ... 3-D with nx % 4 != 0: padded copy behind the tensor map
 ]
 
 

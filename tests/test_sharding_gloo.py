@@ -73,6 +73,24 @@ def test_split_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
 
 
+
+def _wait_result(q, procs, timeout):
+    """Result of rank 0, failing fast (instead of waiting out the timeout) when a rank has died."""
+    import queue
+    import time
+    t0 = time.time()
+    while True:
+        try:
+            return q.get(timeout=1.0)
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > timeout:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError("worker exit codes %r" % dead if dead else "no result within %d s" % timeout)
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_gloo_equals_single_process():
     from oracle import iq_oracle as O
@@ -86,7 +104,7 @@ def test_two_rank_gloo_equals_single_process():
     procs = [ctx.Process(target=_worker, args=(rank, 2, port, ti, q)) for rank in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=240)
+    got = _wait_result(q, procs, 240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -101,6 +101,24 @@ def _worker(rank, world, port, ti, use_gpu, q, soft=False):
     dist.destroy_process_group()
 
 
+
+def _wait_result(q, procs, timeout):
+    """Result of rank 0, failing fast (instead of waiting out the timeout) when a rank has died."""
+    import queue
+    import time
+    t0 = time.time()
+    while True:
+        try:
+            return q.get(timeout=1.0)
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > timeout:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError("worker exit codes %r" % dead if dead else "no result within %d s" % timeout)
+
+
 def _run(use_gpu, soft=False):
     r = np.random.default_rng(1)
     ti = np.asfortranarray(r.integers(0, 3, (20, 15, 9)).astype(np.float64))
@@ -113,7 +131,7 @@ def _run(use_gpu, soft=False):
     procs = [ctx.Process(target=_worker, args=(rank, 2, port, ti, use_gpu, q, soft)) for rank in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=280)
+    got = _wait_result(q, procs, 280)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
