@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(kZdThreads) k_fft_zdirect(const ZDirectArgs A)
   }
 }
 
+#ifdef IQB200_EXPERIMENTS
 // ---- pass B'': direct z correlation FUSED with the inverse y transform --------------------------------------
 // One CTA per (template pair, kx): thread ky keeps the sliding window of its (kx, ky) column in registers exactly as
 // k_fft_zdirect does, but 16 consecutive output planes go straight into 16 shared-memory lines (ky along the line),
@@ -560,6 +561,8 @@ __global__ void __launch_bounds__(256) k_transpose_xzy(const float2* __restrict_
   __syncthreads();
   if (x0 + ty < nx && y0 + tx < ny) out[((long long)(x0 + ty) * nz + z) * ny + y0 + tx] = tile[tx][ty];
 }
+
+#endif  // IQB200_EXPERIMENTS
 
 // ---- pass C: last inverse pass along x + distance epilogue --------------------------------------------
 struct FinalArgs {
@@ -754,6 +757,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fft_strided_inv_tma(const Strid
   }
 }
 
+#ifdef IQB200_EXPERIMENTS
 // ---- pass C, streaming version: persistent CTAs, the next tile of LPB lines (one contiguous block of global
 //      memory) is fetched by ONE bulk TMA copy into the other half of a double buffer while the current tile is
 //      transformed in place and written out.  The first pass reads the unpadded lines the copy delivered.
@@ -798,6 +802,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_fft_x_final_tma(const FinalArgs
     __syncthreads();  // everybody is done with buf[b] and s_min before they are reused
   }
 }
+
+#endif  // IQB200_EXPERIMENTS
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -937,6 +943,7 @@ static cudaError_t launch_strided(const StridedArgs& a_in, int log2n, int batch,
                         k_fft_strided<L, MODE><<<grid, kThreads, sm, s>>>(a); });
   return cudaGetLastError();
 }
+#ifdef IQB200_EXPERIMENTS
 static bool tma_enabled() {
   // Experimental (IQB200_FFT_TMA=1): persistent CTAs with a TMA-fed double buffer.  Bit-identical results, but on
   // config 5 it is slower than one tile per CTA (1.19 ms vs 0.77 ms per 32 template pairs): the pass is bound by
@@ -969,16 +976,24 @@ static cudaError_t launch_final_tma(const FinalArgs& a, int npair, cudaStream_t 
   }
 }
 
+#endif  // IQB200_EXPERIMENTS
+
 static cudaError_t launch_final(const FinalArgs& a, int log2n, int npair, cudaStream_t s) {
+#ifdef IQB200_EXPERIMENTS
   if (tma_enabled() && inplace_ok(log2n) && log2n >= 4 && a.in_batch == 0) {
     FFT_DISPATCH(log2n, { return launch_final_tma<L>(a, npair, s); });
   }
+#endif
   const size_t sm = smem_bytes(log2n);
   const int LPB = lines_per_block(log2n);
   dim3 grid((a.nlines + LPB - 1) / LPB, npair);
-  if (a.in_batch > 0) {
+  if (a.in_batch > 0) {  // transposed input: only the fused z/y kernel of the experiments build produces it
+#ifdef IQB200_EXPERIMENTS
     FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_x_final<L, true>, sm); if (e != cudaSuccess) return e;
                           k_fft_x_final<L, true><<<grid, kThreads, sm, s>>>(a); });
+#else
+    return cudaErrorInvalidValue;
+#endif
   } else {
     FFT_DISPATCH(log2n, { cudaError_t e = set_smem(k_fft_x_final<L, false>, sm); if (e != cudaSuccess) return e;
                           k_fft_x_final<L, false><<<grid, kThreads, sm, s>>>(a); });
@@ -1019,6 +1034,7 @@ static bool zdirect_enabled() {
   return !(ev && ev[0] == '0');
 }
 
+#ifdef IQB200_EXPERIMENTS
 static bool zyfused_enabled() {
   // Experimental (IQB200_FFT_ZYFUSED=1).  Bit-identical results and 42 % less traffic, but 5 % SLOWER on config 5
   // (FFT passes 1.155 s vs 1.099 s per 512 steps): both halves are bound by instruction issue, and the fused kernel
@@ -1026,6 +1042,9 @@ static bool zyfused_enabled() {
   const char* ev = std::getenv("IQB200_FFT_ZYFUSED");
   return ev && ev[0] == '1';
 }
+#else
+static bool zyfused_enabled() { return false; }  // k_fft_zy is part of the experiments build (make EXTRA=-DIQB200_EXPERIMENTS)
+#endif
 
 cudaError_t plan_create(Plan** out, int nx, int ny, int nz, int tx, int ty, int tz, int max_templates, cudaStream_t s) {
   *out = nullptr;
@@ -1119,6 +1138,7 @@ cudaError_t plan_set_image(Plan* p, int id, const float* d_img, cudaStream_t s) 
       cudaFree(spec);
       a.scale = (float)(1.0 / ((double)Nx * (double)Ny));
       if ((e = launch_strided<0>(a, p->ly, 1, s)) != cudaSuccess) return e;
+#ifdef IQB200_EXPERIMENTS
       if (p->zyfused) {
         float2* tt = nullptr;
         if ((e = iq::dmalloc((void**)&tt, (size_t)p->nz * Ny * Nx * sizeof(float2))) != cudaSuccess) return e;
@@ -1127,6 +1147,7 @@ cudaError_t plan_set_image(Plan* p, int id, const float* d_img, cudaStream_t s) 
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         p->sxy_t[id] = tt;
       }
+#endif
       if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
       cudaFree(t1);
       p->sxy[id] = t2;
@@ -1185,6 +1206,7 @@ cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogu
       a.out_sa = (long long)p->tz * Ny; a.out_sb = Ny; a.out_se = 1;
     }
     if ((e = launch_strided<0>(a, p->ly, npair, s)) != cudaSuccess) return e;
+#ifdef IQB200_EXPERIMENTS
     if (p->zyfused) {
       auto itt = p->sxy_t.find(id);
       if (itt == p->sxy_t.end()) return cudaErrorInvalidValue;
@@ -1201,6 +1223,7 @@ cudaError_t correlate(Plan* p, int id, const float* d_tmpl, int R, const Epilogu
       if (launches) *launches = nl + 3;
       return cudaSuccess;
     }
+#endif
     if (p->zdirect) {
       ZDirectArgs z{};
       z.sxy = spec; z.tmpl = p->w2; z.out = p->w3;

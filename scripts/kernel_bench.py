@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Microbenchmark of the tile search on one config: interior-tile mask, templates cut from the training
-image + N(0, 0.1^2) noise.  Reports device ms per search call, ms inside k_dist_boxes,
+image + N(0, 0.1^2) noise.  Reports device ms per search call, ms inside the distance kernel,
 FMA rate and fraction of the measured FFMA peak; optional L2 flush between iterations."""
 import argparse
 import json
