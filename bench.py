@@ -223,6 +223,16 @@ def main():
     workload = (f"{cfg['name'].split(' nreal')[0]}; nreal = {nreal_total} in total"
                 + (f", {nreal_total // world if scaling == 'strong' else nreal_local} per GPU ({scaling} scaling)" if world > 1 else ""))
 
+    # host threads per rank: cut/paste pool of the host-staged pipeline (which leaves the GPU-driving thread and the clock
+    # sampler a core), export threads of the device-resident one (the driving thread is idle by then)
+    nthreads = max(1, ncores // max(world, 1) - (2 if args.pipeline == "staged" else 0))
+    # ONE config record for both arms (the reference arm times the B200 arm's workload)
+    config = {"workload": workload, "tilesize": list(tilesize), "trainimg": list(ti.shape), "nreal_total": nreal_total,
+              "nreal_per_gpu": nreal_local,
+              "l2": "whole-job steps: every search reads fresh templates and writes R x npos distance maps (> L2 at "
+                    "R >= 8 on config 5); the training image / its spectrum stay L2-resident by design, no flush applies",
+              "host_threads_per_rank": nthreads, "host_cores": ncores, "distance_path": {-1: "direct", 0: "auto", 1: "fft"}[args.fft]}
+
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
@@ -247,7 +257,7 @@ def main():
         line = {"impl": "reference", "metric": "iqsim voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
                 "steps": K, "warmup": W, "ms_per_step": 1e3 * (t1 - t0) / K, "higher_is_better": True,
                 "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload},
+                "config": config,
                 "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": ncores, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -275,9 +285,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # host threads per rank: cut/paste pool of the host-staged pipeline (which leaves the GPU-driving thread and the clock
-    # sampler a core), export threads of the device-resident one (the driving thread is idle by then)
-    nthreads = max(1, ncores // max(world, 1) - (2 if args.pipeline == "staged" else 0))
     seed0 = 1234
 
     def step(i):
@@ -399,11 +406,7 @@ def main():
         "metric": "iqsim voxels/sec", "value": vox_per_step * args.steps / resident_max, "unit": "voxels/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total_max / args.steps,
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "tilesize": list(tilesize), "trainimg": list(ti.shape), "nreal_total": nreal_total,
-                   "nreal_per_gpu": nreal_local,
-                   "l2": "whole-job steps: every search reads fresh templates and writes R x npos distance maps (> L2 at "
-                         "R >= 8 on config 5); the training image / its spectrum stay L2-resident by design, no flush applies",
-                   "host_threads_per_rank": nthreads, "host_cores": ncores, "distance_path": {-1: "direct", 0: "auto", 1: "fft"}[args.fft]},
+        "config": config,
         "e2e": {"value": vox_per_step * args.steps / t_total_max, "unit": "voxels/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(sum(s["stats"]["kernel_launches"] for s in stats)),
