@@ -478,6 +478,39 @@ def voxelreuse_sweep(trainimg, *, tmin=None, tmax=None, overlap=None, nreal=10, 
     return dict(ts=np.asarray(ts), mu=np.asarray(mus), sigma=np.asarray(sigmas), best=(min(best), max(best)))
 
 
+class IQ:
+    """Process object in the style of the high-level `IQ` wrapper GeoStats.jl puts around `iqsim`
+    (/root/reference/docs/src/index.md:47-60 points to it; the wrapper itself lives outside the reference repository):
+    the parameters of a simulation are fixed once, `rand` draws realizations on a grid.
+
+        proc = IQ(trainimg, (30, 30), overlap=(1/6, 1/6), path="raster", inactive=None, soft=[(aux, auxTI)], tol=0.1)
+        reals = proc.rand((100, 100), 8, data={(10, 12): 1.0}, rng=np.random.default_rng(0))
+
+    `inactive`: grid cells (0-based index tuples) that are never simulated -- they become NaN hard data, exactly how the
+    wrapper maps them onto `iqsim`'s `hard` argument; `data`: conditioning values per cell (the `hard` dictionary).
+    Everything else (`nthreads`, `fft`, `pipeline`, `device`, ...) is passed through to `iqsim`."""
+
+    def __init__(self, trainimg, tilesize, *, overlap=None, path="raster", inactive=None, soft=(), tol=0.1):
+        self.trainimg = trainimg
+        self.tilesize = tuple(int(t) for t in tilesize)
+        self.overlap = overlap
+        self.path = path
+        self.inactive = None if inactive is None else [tuple(int(i) for i in c) for c in inactive]
+        self.soft = list(soft)
+        self.tol = tol
+
+    def hard(self, data=None):
+        """The `hard` dictionary handed to iqsim: conditioning data, with NaN at the inactive cells (which win)."""
+        hard = {tuple(int(i) for i in k): v for k, v in (data or {}).items()}
+        for c in self.inactive or ():
+            hard[c] = float("nan")
+        return hard
+
+    def rand(self, simsize=None, nreals=1, *, data=None, rng=None, **kwargs):
+        return iqsim(self.trainimg, self.tilesize, simsize, overlap=self.overlap, soft=self.soft, hard=self.hard(data),
+                     tol=self.tol, path=self.path, nreal=int(nreals), rng=rng, **kwargs)
+
+
 def dependency_levels(tilesize, ovlsize, ntiles, path):
     """Dependency level of every step of a simulation path (iqh_dependency_levels): steps of one level touch disjoint
     windows of the simulation grid and are launched together by the device-resident pipeline."""

@@ -113,3 +113,19 @@ def test_voxelreuse_sweep_matches_single_calls():
     assert np.all((out["mu"] >= 0) & (out["mu"] <= 1))
     order = np.argsort(-out["mu"], kind="stable")[:5]
     assert out["best"] == (int(out["ts"][order].min()), int(out["ts"][order].max()))
+
+
+def test_iq_wrapper_equals_iqsim_with_nan_hard_data():
+    """GeoStats-style wrapper: inactive cells + conditioning data = iqsim's hard dictionary (runtests.jl:50-104 style)."""
+    from iqb200 import synth
+    ti = synth.gaussian_field((40, 36), (5, 5), 11)
+    inactive = [(i, j) for i in range(10) for j in range(12)]
+    data = {(20, 20): 0.5, (30, 8): -1.0}
+    proc = iqb200.IQ(ti, (12, 12), inactive=inactive, tol=0.1)
+    got = proc.rand((40, 36), 2, data=data, rng=np.random.default_rng(2))
+    hard = dict(data)
+    hard.update({c: np.nan for c in inactive})
+    want = iqb200.iqsim(ti, (12, 12), (40, 36), hard=hard, nreal=2, rng=np.random.default_rng(2))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b, equal_nan=True)
+        assert np.isnan(a[:10, :12]).all() and a[20, 20] == 0.5 and a[30, 8] == -1.0

@@ -153,3 +153,27 @@ def test_dependency_levels_rejects_bad_paths():
         api.dependency_levels((8, 8), (2, 2), (3, 3), [0, 1, 1])
     with pytest.raises(IqError):
         api.dependency_levels((8, 8), (2, 2), (3, 3), [0, 9])
+
+
+def test_iq_wrapper_maps_its_parameters_onto_iqsim(monkeypatch):
+    """The GeoStats-style IQ object: inactive cells become NaN hard data (and win over conditioning values at the same
+    cell), everything else is handed to iqsim unchanged."""
+    seen = {}
+
+    def fake_iqsim(trainimg, tilesize, simsize=None, **kw):
+        seen.update(kw, trainimg=trainimg, tilesize=tilesize, simsize=simsize)
+        return ["realization"] * kw["nreal"]
+
+    monkeypatch.setattr(api, "iqsim", fake_iqsim)
+    ti = np.zeros((20, 20))
+    aux = np.ones((20, 20))
+    proc = api.IQ(ti, (8, 8), overlap=(0.25, 0.25), path="random", inactive=[(0, 0), (3, 4)], soft=[(aux, aux)], tol=0.2)
+    out = proc.rand((30, 30), 3, data={(3, 4): 2.0, (5, 5): 1.0}, rng="rng", nthreads=2)
+    assert out == ["realization"] * 3
+    assert seen["tilesize"] == (8, 8) and seen["simsize"] == (30, 30) and seen["nreal"] == 3
+    assert seen["overlap"] == (0.25, 0.25) and seen["path"] == "random" and seen["tol"] == 0.2
+    assert seen["rng"] == "rng" and seen["nthreads"] == 2 and seen["soft"][0][0] is aux
+    hard = seen["hard"]
+    assert set(hard) == {(0, 0), (3, 4), (5, 5)} and hard[(5, 5)] == 1.0
+    assert np.isnan(hard[(0, 0)]) and np.isnan(hard[(3, 4)])
+    assert api.IQ(ti, (8, 8)).hard() == {}
