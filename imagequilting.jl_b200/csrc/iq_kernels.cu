@@ -74,9 +74,10 @@ __device__ __forceinline__ unsigned warp_max_u(unsigned v) {
 //   k_dist_flat      (default)  the patch is one cp.async.bulk.tensor.3d box of the image's tensor map, the template
 //                    plane one cp.async.bulk copy, both landing on an mbarrier; two stage buffers, so the TMA engine
 //                    fetches (box, plane) s+1 while the FMAs of stage s run -- no staging instructions, no registers, one
-//                    __syncthreads per stage.  TMA writes the box densely (row pitch = box width), so the conflict-free
-//                    LDS.128 comes from the geometry instead of a swizzle: box width = 4 mod 8 floats and a quarter warp
-//                    = 4 x-threads of 2 consecutive rows (work items numbered in 2-row x 4-thread octets).
+//                    __syncthreads per stage (one buffer when two would cost the second CTA of the SM).  TMA writes the
+//                    box densely (row pitch = box width), so the conflict-free LDS.128 comes from the geometry instead
+//                    of a swizzle: box width = 4 mod 8 floats and a quarter warp = an octet of work items, 4 x-threads
+//                    of 2 consecutive rows or 1 x-thread of 8 rows.  Box starts are 16-byte aligned (BoxDesc::pad).
 //   k_dist_flat_ldg  (variant 1, and the fallback for boxes beyond TMA's 256-element limit)  items numbered row-major,
 //                    patch staged through registers with __ldg, single buffer, two barriers per stage; the two 16-byte
 //                    halves of every 8-float chunk are swapped in odd 128-byte groups for conflict-free LDS.128.
