@@ -434,6 +434,9 @@ struct ZDirectArgs {
 #define IQ_ZD_THREADS 128  // 949 vs 990 ms of FFT passes per config-5 simulation with 256 (finer CTA scheduling)
 #endif
 constexpr int kZdThreads = IQ_ZD_THREADS;
+#ifndef IQ_ZPACKED_DEFAULT
+#define IQ_ZPACKED_DEFAULT 0  // the packed-FMA z pass is opt-in (IQB200_FFT_ZPACKED=1) until measured
+#endif
 template <int W>
 __global__ void __launch_bounds__(kZdThreads) k_fft_zdirect(const ZDirectArgs A) {
   // blockIdx.x = template pair (fastest): the CTAs that read the same spectrum columns are scheduled together, so the
@@ -479,6 +482,85 @@ __global__ void __launch_bounds__(kZdThreads) k_fft_zdirect(const ZDirectArgs A)
     }
   }
 }
+
+#ifdef IQB200_EXPERIMENTS
+// Same pass with packed FMAs (fma.rn.f32x2 -> SASS FFMA2; experiments build, IQB200_FFT_ZPACKED=1).  On sm_100 the packed
+// instruction has the FMA throughput of the scalar one but takes half the issue slots, and k_fft_zdirect is bound by
+// instruction issue (82 % of the issue slots, FMA pipe 67 %; profiles/r02_resident_ncu_full.txt) -- yet MEASURED SLOWER:
+// 984 ms against 949 ms of FFT passes per config-5 simulation (call AN of round 2; 512 FFMA2 instead of 1024 FFMA per 16
+// outputs, but 152 registers = 3 CTAs per SM instead of 4 and ~100 extra MOVs for the duplicated window).  Same maps
+// within FP32 rounding (the FFT parity tests pass with it).  Two packed accumulators per output,
+//   P = sum_q (sx, sx) * (tx, ty) = (sum sx tx, sum sx ty),   Q = sum_q (sy, sy) * (tx, ty) = (sum sy tx, sum sy ty),
+//   out = (P.x - Q.y, P.y + Q.x):
+// the template values are used as loaded (re, im pairs), only the spectrum window is kept duplicated ((sx, sx) and
+// (sy, sy) pairs, built once per plane and used by W outputs).  32 FFMA2 per output instead of 64 FFMA.
+typedef unsigned long long u64p;
+__device__ __forceinline__ u64p zpack2(float lo, float hi) {
+  u64p r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void zunpack2(u64p v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64p zffma2(u64p a, u64p b, u64p c) {
+  u64p d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+template <int W>
+__global__ void __launch_bounds__(kZdThreads) k_fft_zdirect2(const ZDirectArgs A) {
+  const long long col = (long long)blockIdx.y * kZdThreads + threadIdx.x;
+  if (col >= A.plane) return;
+  const float2* __restrict__ S = A.sxy + col;
+  const float2* __restrict__ T = A.tmpl + (long long)blockIdx.x * A.tmpl_batch + col;
+  float2* __restrict__ O = A.out + (long long)blockIdx.x * A.out_batch + col;
+  const float2 zero = make_float2(0.f, 0.f);
+  u64p t[W], sx[W], sy[W];
+#pragma unroll
+  for (int q = 0; q < W; ++q) {
+    const float2 v = q < A.tz ? T[(long long)q * A.plane] : zero;
+    t[q] = zpack2(v.x, v.y);
+  }
+#pragma unroll
+  for (int j = 0; j < W - 1; ++j) {
+    const float2 v = j < A.nz ? S[(long long)j * A.plane] : zero;
+    sx[j] = zpack2(v.x, v.x);
+    sy[j] = zpack2(v.y, v.y);
+  }
+  sx[W - 1] = sy[W - 1] = 0ull;
+  const float2* __restrict__ sp = S + (long long)(W - 1) * A.plane;  // next spectrum plane to enter the window
+  float2* __restrict__ op = O;
+  const long long step = A.plane;
+  for (int z0 = 0; z0 < A.nzo; z0 += W) {
+    float2 nxt[W];
+    const int navail = A.nz - (z0 + W - 1);  // spectrum planes left for this block of W outputs
+#pragma unroll
+    for (int m = 0; m < W; ++m) {
+      nxt[m] = m < navail ? *sp : zero;
+      sp += step;
+    }
+    const int nout = A.nzo - z0;
+#pragma unroll
+    for (int m = 0; m < W; ++m) {
+      sx[(m + W - 1) % W] = zpack2(nxt[m].x, nxt[m].x);
+      sy[(m + W - 1) % W] = zpack2(nxt[m].y, nxt[m].y);
+      u64p P = 0ull, Q = 0ull;
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        P = zffma2(sx[(m + q) % W], t[q], P);
+        Q = zffma2(sy[(m + q) % W], t[q], Q);
+      }
+      float px, py, qx, qy;
+      zunpack2(P, px, py);
+      zunpack2(Q, qx, qy);
+      if (m < nout) *op = make_float2(px - qy, py + qx);
+      op += step;
+    }
+  }
+}
+
+#endif  // IQB200_EXPERIMENTS
 
 #ifdef IQB200_EXPERIMENTS
 // ---- pass B'': direct z correlation FUSED with the inverse y transform --------------------------------------
@@ -1001,9 +1083,31 @@ static cudaError_t launch_final(const FinalArgs& a, int log2n, int npair, cudaSt
   return cudaGetLastError();
 }
 
+#ifdef IQB200_EXPERIMENTS
+// z pass with packed FMAs (k_fft_zdirect2) for windows of up to 16 planes: IQB200_FFT_ZPACKED = 1 / 0 overrides the default
+static bool zpacked_enabled() {
+  static const int mode = [] {
+    const char* ev = std::getenv("IQB200_FFT_ZPACKED");
+    return ev ? (ev[0] == '1' ? 1 : 0) : IQ_ZPACKED_DEFAULT;
+  }();
+  return mode != 0;
+}
+#endif
+
 static cudaError_t launch_zdirect(const ZDirectArgs& a, int npair, cudaStream_t s) {
   dim3 grid(npair, (unsigned)((a.plane + kZdThreads - 1) / kZdThreads));
   const int w = (a.tz + 3) / 4 * 4;
+#ifdef IQB200_EXPERIMENTS
+  if (w <= 16 && zpacked_enabled()) {
+    switch (w) {
+      case 4: k_fft_zdirect2<4><<<grid, kZdThreads, 0, s>>>(a); break;
+      case 8: k_fft_zdirect2<8><<<grid, kZdThreads, 0, s>>>(a); break;
+      case 12: k_fft_zdirect2<12><<<grid, kZdThreads, 0, s>>>(a); break;
+      default: k_fft_zdirect2<16><<<grid, kZdThreads, 0, s>>>(a); break;
+    }
+    return cudaGetLastError();
+  }
+#endif
   switch (w) {
     case 4: k_fft_zdirect<4><<<grid, kZdThreads, 0, s>>>(a); break;
     case 8: k_fft_zdirect<8><<<grid, kZdThreads, 0, s>>>(a); break;
