@@ -31,6 +31,31 @@ def test_library_exports_every_declared_symbol():
     assert L.iq_abi_version() == 1
 
 
+def test_default_build_stages_the_direct_kernel_with_tma_and_carries_no_experiments():
+    """SASS of the built library: every instantiation of the default direct kernel k_dist_flat issues tensor-map loads
+    (UTMALDG = cp.async.bulk.tensor) and bulk copies (UBLKCP) and waits on mbarriers (SYNCS); the register-staged
+    fallback has none; the FFT-path experiments that were measured slower are not in the default binary."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    funcs = {}
+    for blk in re.split(r"\n\s*Function : ", sass)[1:]:
+        name, _, body = blk.partition("\n")
+        funcs[name.strip()] = body
+    tma = [n for n in funcs if "k_dist_flatILi" in n]
+    ldg = [n for n in funcs if "k_dist_flat_ldgILi" in n]
+    assert len(tma) == 3 and len(ldg) == 3
+    for n in tma:
+        assert "UTMALDG" in funcs[n] and "UBLKCP" in funcs[n] and "SYNCS" in funcs[n], n
+    for n in ldg:
+        assert "UTMALDG" not in funcs[n] and "UBLKCP" not in funcs[n], n
+    for gone in ("k_fft_zy", "k_fft_x_final_tma", "k_fft_zdirect2", "k_dist_boxes", "k_dist_flat2"):
+        assert not any(gone in n for n in funcs), gone
+
+
 def test_no_device_fails_loudly():
     import torch
     if torch.cuda.is_available():
